@@ -1,0 +1,742 @@
+// HBM-bound kernels of the VLA hot path: norms, RoPE, gated activations, masked softmax,
+// reductions, AdamW.  All global traffic is 128-bit vectorised and coalesced; grids are sized
+// in multiples of the SM count with grid-stride loops.  Reference call sites are cited in
+// include/dexbotic_b200_ops.h next to each entry point.
+#include "../../include/dexbotic_b200_ops.h"
+#include "common.h"
+#include "vec.cuh"
+
+namespace b200 {
+
+using bf16 = __nv_bfloat16;
+constexpr int kMaxPacks = 4;  // packs of 8 columns per thread kept in registers (D <= 8 * 256 * 4)
+
+static inline int grid_for_rows(int64_t rows, int per_sm = 8) {
+  int64_t g = (int64_t)num_sms() * per_sm;
+  return (int)(rows < g ? rows : g);
+}
+
+// ------------------------------------------------------------------ RMSNorm
+template <typename T>
+__global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                          T* __restrict__ y, float* __restrict__ rstd, int M, int D,
+                                                          float eps, int unit_offset) {
+  __shared__ float red[33];
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const T* xr = x + (size_t)row * D;
+    T* yr = y + (size_t)row * D;
+    float ss = 0.0f;
+    for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
+      float v[8];
+      Pack8<T>::load(xr + i, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
+    }
+    ss = block_sum(ss, red);
+    const float r = rsqrtf(ss / (float)D + eps);
+    if (threadIdx.x == 0 && rstd != nullptr) rstd[row] = r;
+    for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
+      float v[8], g[8], o[8];
+      Pack8<T>::load(xr + i, v);
+      Pack8<T>::load(w + i, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = unit_offset ? (v[j] * r) * (1.0f + g[j]) : g[j] * round_to<T>(v[j] * r);
+      Pack8<T>::store(yr + i, o);
+    }
+  }
+}
+
+// dx = r*g - x*r^3*mean(g.x),  g = dy*w_eff ;  dw[col] += sum_rows dy * x * r   (fp32 atomics)
+template <typename T>
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                          const T* __restrict__ w, const float* __restrict__ rstd,
+                                                          T* __restrict__ dx, float* __restrict__ dw, int M, int D,
+                                                          int unit_offset, int accumulate_dx) {
+  __shared__ float red[33];
+  float wacc[kMaxPacks][8];
+#pragma unroll
+  for (int k = 0; k < kMaxPacks; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wacc[k][j] = 0.0f;
+
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const T* xr = x + (size_t)row * D;
+    const T* dyr = dy + (size_t)row * D;
+    T* dxr = dx + (size_t)row * D;
+    const float r = rstd[row];
+    float c = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kMaxPacks; ++k) {
+      const int i = (threadIdx.x + k * blockDim.x) * 8;
+      if (i < D) {
+        float xv[8], dv[8], wv[8];
+        Pack8<T>::load(xr + i, xv);
+        Pack8<T>::load(dyr + i, dv);
+        Pack8<T>::load(w + i, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float we = unit_offset ? 1.0f + wv[j] : wv[j];
+          c += dv[j] * we * xv[j];
+          wacc[k][j] += dv[j] * xv[j] * r;
+        }
+      }
+    }
+    c = block_sum(c, red);
+    const float coef = c * r * r * r / (float)D;
+#pragma unroll
+    for (int k = 0; k < kMaxPacks; ++k) {
+      const int i = (threadIdx.x + k * blockDim.x) * 8;
+      if (i < D) {
+        float xv[8], dv[8], wv[8], o[8];
+        Pack8<T>::load(xr + i, xv);
+        Pack8<T>::load(dyr + i, dv);
+        Pack8<T>::load(w + i, wv);
+        if (accumulate_dx) Pack8<T>::load(dxr + i, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float we = unit_offset ? 1.0f + wv[j] : wv[j];
+          const float t = r * dv[j] * we - xv[j] * coef;
+          o[j] = accumulate_dx ? o[j] + t : t;
+        }
+        Pack8<T>::store(dxr + i, o);
+      }
+    }
+  }
+  if (dw != nullptr) {
+#pragma unroll
+    for (int k = 0; k < kMaxPacks; ++k) {
+      const int i = (threadIdx.x + k * blockDim.x) * 8;
+      if (i < D) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dw + i + j, wacc[k][j]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                            const T* __restrict__ b, T* __restrict__ y,
+                                                            float* __restrict__ mean, float* __restrict__ rstd, int M,
+                                                            int D, float eps) {
+  __shared__ float red[33];
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const T* xr = x + (size_t)row * D;
+    T* yr = y + (size_t)row * D;
+    float s = 0.0f;
+    for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
+      float v[8];
+      Pack8<T>::load(xr + i, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[j];
+    }
+    const float mu = block_sum(s, red) / (float)D;
+    float ss = 0.0f;
+    for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
+      float v[8];
+      Pack8<T>::load(xr + i, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += (v[j] - mu) * (v[j] - mu);
+    }
+    const float r = rsqrtf(block_sum(ss, red) / (float)D + eps);
+    if (threadIdx.x == 0) {
+      if (mean != nullptr) mean[row] = mu;
+      if (rstd != nullptr) rstd[row] = r;
+    }
+    for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
+      float v[8], o[8];
+      Pack8<T>::load(xr + i, v);
+      float wv[8], bv[8];
+      if (w != nullptr) Pack8<T>::load(w + i, wv);
+      if (b != nullptr) Pack8<T>::load(b + i, bv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = (v[j] - mu) * r;
+        if (w != nullptr) t *= wv[j];
+        if (b != nullptr) t += bv[j];
+        o[j] = t;
+      }
+      Pack8<T>::store(yr + i, o);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                            const T* __restrict__ w, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, T* __restrict__ dx,
+                                                            float* __restrict__ dw, float* __restrict__ db, int M,
+                                                            int D, int accumulate_dx) {
+  __shared__ float red[33];
+  float wacc[kMaxPacks][8], bacc[kMaxPacks][8];
+#pragma unroll
+  for (int k = 0; k < kMaxPacks; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wacc[k][j] = bacc[k][j] = 0.0f;
+
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const T* xr = x + (size_t)row * D;
+    const T* dyr = dy + (size_t)row * D;
+    T* dxr = dx + (size_t)row * D;
+    const float mu = mean[row], r = rstd[row];
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kMaxPacks; ++k) {
+      const int i = (threadIdx.x + k * blockDim.x) * 8;
+      if (i < D) {
+        float xv[8], dv[8], wv[8];
+        Pack8<T>::load(xr + i, xv);
+        Pack8<T>::load(dyr + i, dv);
+        if (w != nullptr) Pack8<T>::load(w + i, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mu) * r;
+          const float g = w != nullptr ? dv[j] * wv[j] : dv[j];
+          s1 += g;
+          s2 += g * xh;
+          wacc[k][j] += dv[j] * xh;
+          bacc[k][j] += dv[j];
+        }
+      }
+    }
+    s1 = block_sum(s1, red) / (float)D;
+    s2 = block_sum(s2, red) / (float)D;
+#pragma unroll
+    for (int k = 0; k < kMaxPacks; ++k) {
+      const int i = (threadIdx.x + k * blockDim.x) * 8;
+      if (i < D) {
+        float xv[8], dv[8], wv[8], o[8];
+        Pack8<T>::load(xr + i, xv);
+        Pack8<T>::load(dyr + i, dv);
+        if (w != nullptr) Pack8<T>::load(w + i, wv);
+        if (accumulate_dx) Pack8<T>::load(dxr + i, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mu) * r;
+          const float g = w != nullptr ? dv[j] * wv[j] : dv[j];
+          const float t = r * (g - s1 - xh * s2);
+          o[j] = accumulate_dx ? o[j] + t : t;
+        }
+        Pack8<T>::store(dxr + i, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxPacks; ++k) {
+    const int i = (threadIdx.x + k * blockDim.x) * 8;
+    if (i < D) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (dw != nullptr) atomicAdd(dw + i + j, wacc[k][j]);
+        if (db != nullptr) atomicAdd(db + i + j, bacc[k][j]);
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------- RoPE
+// In-place rotate_half RoPE on the first `n_rot_heads` heads of every row of a packed
+// [M, row_stride] buffer (q heads then k heads).  cos/sin: fp32 tables [n_pos, hd/2].
+template <typename T>
+__global__ void rope_kernel(T* __restrict__ qkv, const int* __restrict__ pos, const float* __restrict__ cos_t,
+                            const float* __restrict__ sin_t, int M, int n_rot_heads, int hd, int64_t row_stride,
+                            int inverse) {
+  const int half = hd >> 1;
+  const int packs_per_head = half >> 3;
+  const int work = n_rot_heads * packs_per_head;
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const int p = pos[row];
+    const float* cr = cos_t + (size_t)p * half;
+    const float* sr = sin_t + (size_t)p * half;
+    T* base = qkv + (size_t)row * row_stride;
+    for (int t = threadIdx.x; t < work; t += blockDim.x) {
+      const int head = t / packs_per_head;
+      const int i = (t - head * packs_per_head) * 8;
+      T* lo = base + head * hd + i;
+      T* hi = lo + half;
+      float a[8], b[8], oa[8], ob[8];
+      Pack8<T>::load(lo, a);
+      Pack8<T>::load(hi, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float c = round_to<T>(cr[i + j]);
+        float s = round_to<T>(sr[i + j]);
+        if (inverse) s = -s;
+        oa[j] = a[j] * c - b[j] * s;
+        ob[j] = b[j] * c + a[j] * s;
+      }
+      Pack8<T>::store(lo, oa);
+      Pack8<T>::store(hi, ob);
+    }
+  }
+}
+
+// ------------------------------------------------------- activations / GLU
+template <typename T>
+__global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n8, int act) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8];
+    Pack8<T>::load(x + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = act_fwd(v[j], act);
+    Pack8<T>::store(y + i * 8, v);
+  }
+}
+template <typename T>
+__global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx, int64_t n8,
+                               int act) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8], d[8];
+    Pack8<T>::load(x + i * 8, v);
+    Pack8<T>::load(dy + i * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] *= act_grad(v[j], act);
+    Pack8<T>::store(dx + i * 8, d);
+  }
+}
+template <typename T>
+__global__ void glu_fwd_kernel(const T* __restrict__ g, const T* __restrict__ u, T* __restrict__ h, int64_t n8,
+                               int act) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    Pack8<T>::load(g + i * 8, a);
+    Pack8<T>::load(u + i * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = act_fwd(a[j], act) * b[j];
+    Pack8<T>::store(h + i * 8, a);
+  }
+}
+// dg = dh*u*act'(g), du = dh*act(g); dg/du may alias g/u; optional h_out = act(g)*u
+template <typename T>
+__global__ void glu_bwd_kernel(const T* __restrict__ dh, const T* g, const T* u, T* dg, T* du, T* __restrict__ h_out,
+                               int64_t n8, int act) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float a[8], b[8], d[8], og[8], ou[8], oh[8];
+    Pack8<T>::load(g + i * 8, a);
+    Pack8<T>::load(u + i * 8, b);
+    Pack8<T>::load(dh + i * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float f = act_fwd(a[j], act);
+      og[j] = d[j] * b[j] * act_grad(a[j], act);
+      ou[j] = d[j] * f;
+      oh[j] = f * b[j];
+    }
+    Pack8<T>::store(dg + i * 8, og);
+    Pack8<T>::store(du + i * 8, ou);
+    if (h_out != nullptr) Pack8<T>::store(h_out + i * 8, oh);
+  }
+}
+
+// ------------------------------------------------------------------ softmax
+// One warp per (z, q) row.  allowed(q,k) = (!keymask || keymask[b,k]) && (!bid || bid_k[b,k] <= bid_q[b,q]).
+// b = z / heads.  Scores are fp32 (already scaled); P is written as T.  Fully masked rows -> zeros.
+template <typename T>
+__global__ void softmax_fwd_kernel(const float* __restrict__ s, T* __restrict__ p, int64_t rows, int Sq, int Sk,
+                                   int64_t s_ld, int64_t p_ld, int heads, const uint8_t* __restrict__ keymask,
+                                   const int* __restrict__ bid_q, const int* __restrict__ bid_k) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
+    const int64_t z = row / Sq;
+    const int q = (int)(row - z * Sq);
+    const int b = (int)(z / heads);
+    const float* sr = s + row * s_ld;
+    T* pr = p + row * p_ld;
+    const uint8_t* km = keymask != nullptr ? keymask + (size_t)b * Sk : nullptr;
+    const int* bk = bid_k != nullptr ? bid_k + (size_t)b * Sk : nullptr;
+    const int bq = bid_q != nullptr ? bid_q[(size_t)b * Sq + q] : 0;
+    float mx = -INFINITY;
+    for (int k = lane; k < Sk; k += 32) {
+      const bool ok = (km == nullptr || km[k]) && (bk == nullptr || bk[k] <= bq);
+      if (ok) mx = fmaxf(mx, sr[k]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int k = lane; k < Sk; k += 32) {
+      const bool ok = (km == nullptr || km[k]) && (bk == nullptr || bk[k] <= bq);
+      if (ok) sum += __expf(sr[k] - mx);
+    }
+    sum = warp_sum(sum);
+    const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
+    for (int k = lane; k < Sk; k += 32) {
+      const bool ok = (km == nullptr || km[k]) && (bk == nullptr || bk[k] <= bq);
+      pr[k] = from_f<T>(ok ? __expf(sr[k] - mx) * inv : 0.0f);
+    }
+  }
+}
+// dS = scale * P * (dP - sum_k P*dP)
+template <typename T>
+__global__ void softmax_bwd_kernel(const T* __restrict__ p, const float* __restrict__ dp, T* __restrict__ ds,
+                                   int64_t rows, int Sk, int64_t p_ld, int64_t dp_ld, int64_t ds_ld, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
+    const T* pr = p + row * p_ld;
+    const float* dr = dp + row * dp_ld;
+    T* or_ = ds + row * ds_ld;
+    float acc = 0.0f;
+    for (int k = lane; k < Sk; k += 32) acc += to_f(pr[k]) * dr[k];
+    acc = warp_sum(acc);
+    for (int k = lane; k < Sk; k += 32) {
+      const float pv = to_f(pr[k]);
+      or_[k] = from_f<T>(scale * pv * (dr[k] - acc));
+    }
+  }
+}
+
+// --------------------------------------------------------------- reductions
+// out[col] += sum_rows x[row, col]   (bias gradients)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int M, int N,
+                                                     int rows_per_block) {
+  const int col8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (col8 >= N) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int r = r0; r < r1; ++r) {
+    float v[8];
+    Pack8<T>::load(x + (size_t)r * N + col8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(out + col8 + j, acc[j]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ x, int64_t n, float* __restrict__ out) {
+  __shared__ float red[33];
+  float acc = 0.0f;
+  const int64_t n8 = n >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8];
+    Pack8<T>::load(x + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += v[j] * v[j];
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (n8 << 3) + threadIdx.x; i < n; i += blockDim.x) {
+      float v = to_f(x[i]);
+      acc += v * v;
+    }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+// mean((a-b)^2) forward: out += sum/(n) ; backward: da = 2*(a-b)/n * gscale  (db = -da)
+template <typename T>
+__global__ void __launch_bounds__(256) mse_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t n,
+                                                      float inv_n, float* __restrict__ out) {
+  __shared__ float red[33];
+  float acc = 0.0f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = to_f(a[i]) - to_f(b[i]);
+    acc += d * d;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, acc * inv_n);
+}
+template <typename T>
+__global__ void mse_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t n, float coef,
+                               const float* __restrict__ gscale, T* __restrict__ da) {
+  const float g = gscale != nullptr ? *gscale : 1.0f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    da[i] = from_f<T>(coef * g * (to_f(a[i]) - to_f(b[i])));
+}
+
+// -------------------------------------------------------------------- AdamW
+// fp32 master weights + fp32 moments; gradient in G (bf16 or fp32); optional bf16 shadow written.
+// torch.optim.AdamW semantics (decoupled decay; bias-corrected).  *clip is the global-norm clip
+// coefficient computed on device (no host sync).
+template <typename G>
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const G* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v,
+                                                    bf16* __restrict__ shadow, int64_t n, float lr, float b1, float b2,
+                                                    float eps, float wd, float bc1, float bc2,
+                                                    const float* __restrict__ clip) {
+  const float cs = clip != nullptr ? *clip : 1.0f;
+  const int64_t n8 = n >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float pv[8], gv[8], mv[8], vv[8];
+    Pack8<float>::load(p + i * 8, pv);
+    Pack8<G>::load(g + i * 8, gv);
+    Pack8<float>::load(m + i * 8, mv);
+    Pack8<float>::load(v + i * 8, vv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gg = gv[j] * cs;
+      mv[j] = b1 * mv[j] + (1.0f - b1) * gg;
+      vv[j] = b2 * vv[j] + (1.0f - b2) * gg * gg;
+      const float denom = sqrtf(vv[j] / bc2) + eps;
+      pv[j] = pv[j] * (1.0f - lr * wd) - lr * (mv[j] / bc1) / denom;
+    }
+    Pack8<float>::store(p + i * 8, pv);
+    Pack8<float>::store(m + i * 8, mv);
+    Pack8<float>::store(v + i * 8, vv);
+    if (shadow != nullptr) Pack8<bf16>::store(shadow + i * 8, pv);
+  }
+  if (blockIdx.x == 0) {
+    for (int64_t i = (n8 << 3) + threadIdx.x; i < n; i += blockDim.x) {
+      const float gg = to_f(g[i]) * cs;
+      const float mm = b1 * m[i] + (1.0f - b1) * gg;
+      const float vv = b2 * v[i] + (1.0f - b2) * gg * gg;
+      const float pp = p[i] * (1.0f - lr * wd) - lr * (mm / bc1) / (sqrtf(vv / bc2) + eps);
+      m[i] = mm;
+      v[i] = vv;
+      p[i] = pp;
+      if (shadow != nullptr) shadow[i] = __float2bfloat16(pp);
+    }
+  }
+}
+
+// clip = min(1, max_norm / (sqrt(sumsq) + 1e-6))   (torch.nn.utils.clip_grad_norm_)
+__global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ clip,
+                                 float* __restrict__ norm_out) {
+  const float nrm = sqrtf(*sumsq);
+  if (norm_out != nullptr) *norm_out = nrm;
+  *clip = fminf(1.0f, max_norm / (nrm + 1e-6f));
+}
+
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, int64_t n) {
+  const int64_t n8 = n >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8];
+    Pack8<S>::load(src + i * 8, v);
+    Pack8<D>::store(dst + i * 8, v);
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (n8 << 3) + threadIdx.x; i < n; i += blockDim.x) dst[i] = from_f<D>(to_f(src[i]));
+}
+
+// y = a + b (optionally y may alias a)
+template <typename T>
+__global__ void add_kernel(const T* a, const T* __restrict__ b, T* y, int64_t n8) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float u[8], v[8];
+    Pack8<T>::load(a + i * 8, u);
+    Pack8<T>::load(b + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] += v[j];
+    Pack8<T>::store(y + i * 8, u);
+  }
+}
+
+static inline int grid_1d(int64_t work_items, int block) {
+  int64_t g = ceil_div(work_items, block);
+  int64_t cap = (int64_t)num_sms() * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace b200
+
+using namespace b200;
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+#define DISPATCH_T(dtype, ...)                   \
+  if ((dtype) == B200_F32) {                     \
+    using T = float;                             \
+    __VA_ARGS__;                                 \
+  } else {                                       \
+    using T = bf16;                              \
+    __VA_ARGS__;                                 \
+  }
+
+extern "C" {
+
+int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t M, int64_t D, float eps,
+                     int unit_offset, int dtype, void* stream) {
+  B200_CHECK(D % 8 == 0, "rmsnorm_fwd: D=%lld must be a multiple of 8", (long long)D);
+  if (M == 0) return 0;
+  DISPATCH_T(dtype, (rmsnorm_fwd_kernel<T><<<grid_for_rows(M), 256, 0, STREAM>>>(
+                        (const T*)x, (const T*)w, (T*)y, rstd, (int)M, (int)D, eps, unit_offset)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw, int64_t M,
+                     int64_t D, int unit_offset, int accumulate_dx, int dtype, void* stream) {
+  B200_CHECK(D % 8 == 0 && D <= 8 * 256 * kMaxPacks, "rmsnorm_bwd: unsupported D=%lld", (long long)D);
+  if (M == 0) return 0;
+  DISPATCH_T(dtype, (rmsnorm_bwd_kernel<T><<<grid_for_rows(M, 2), 256, 0, STREAM>>>(
+                        (const T*)dy, (const T*)x, (const T*)w, rstd, (T*)dx, dw, (int)M, (int)D, unit_offset,
+                        accumulate_dx)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t M,
+                       int64_t D, float eps, int dtype, void* stream) {
+  B200_CHECK(D % 8 == 0, "layernorm_fwd: D=%lld must be a multiple of 8", (long long)D);
+  if (M == 0) return 0;
+  DISPATCH_T(dtype, (layernorm_fwd_kernel<T><<<grid_for_rows(M), 256, 0, STREAM>>>(
+                        (const T*)x, (const T*)w, (const T*)b, (T*)y, mean, rstd, (int)M, (int)D, eps)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
+                       float* dw, float* db, int64_t M, int64_t D, int accumulate_dx, int dtype, void* stream) {
+  B200_CHECK(D % 8 == 0 && D <= 8 * 256 * kMaxPacks, "layernorm_bwd: unsupported D=%lld", (long long)D);
+  if (M == 0) return 0;
+  DISPATCH_T(dtype, (layernorm_bwd_kernel<T><<<grid_for_rows(M, 2), 256, 0, STREAM>>>(
+                        (const T*)dy, (const T*)x, (const T*)w, mean, rstd, (T*)dx, dw, db, (int)M, (int)D,
+                        accumulate_dx)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_rope(void* qkv, const int32_t* pos, const float* cos_t, const float* sin_t, int64_t M, int n_rot_heads,
+              int head_dim, int64_t row_stride, int inverse, int dtype, void* stream) {
+  B200_CHECK(head_dim % 16 == 0, "rope: head_dim=%d must be a multiple of 16", head_dim);
+  if (M == 0) return 0;
+  int work = n_rot_heads * (head_dim / 16);
+  int block = work < 32 ? 32 : (work > 512 ? 512 : ((work + 31) / 32) * 32);
+  DISPATCH_T(dtype, (rope_kernel<T><<<grid_for_rows(M), block, 0, STREAM>>>((T*)qkv, pos, cos_t, sin_t, (int)M,
+                                                                            n_rot_heads, head_dim, row_stride,
+                                                                            inverse)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_act_fwd(const void* x, void* y, int64_t n, int act, int dtype, void* stream) {
+  B200_CHECK(n % 8 == 0, "act_fwd: n must be a multiple of 8");
+  if (n == 0) return 0;
+  DISPATCH_T(dtype, (act_fwd_kernel<T><<<grid_1d(n / 8, 256), 256, 0, STREAM>>>((const T*)x, (T*)y, n / 8, act)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+int b200_act_bwd(const void* dy, const void* x, void* dx, int64_t n, int act, int dtype, void* stream) {
+  B200_CHECK(n % 8 == 0, "act_bwd: n must be a multiple of 8");
+  if (n == 0) return 0;
+  DISPATCH_T(dtype, (act_bwd_kernel<T><<<grid_1d(n / 8, 256), 256, 0, STREAM>>>((const T*)dy, (const T*)x, (T*)dx,
+                                                                                n / 8, act)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+int b200_glu_fwd(const void* g, const void* u, void* h, int64_t n, int act, int dtype, void* stream) {
+  B200_CHECK(n % 8 == 0, "glu_fwd: n must be a multiple of 8");
+  if (n == 0) return 0;
+  DISPATCH_T(dtype, (glu_fwd_kernel<T><<<grid_1d(n / 8, 256), 256, 0, STREAM>>>((const T*)g, (const T*)u, (T*)h,
+                                                                                n / 8, act)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+int b200_glu_bwd(const void* dh, const void* g, const void* u, void* dg, void* du, void* h_out, int64_t n, int act,
+                 int dtype, void* stream) {
+  B200_CHECK(n % 8 == 0, "glu_bwd: n must be a multiple of 8");
+  if (n == 0) return 0;
+  DISPATCH_T(dtype, (glu_bwd_kernel<T><<<grid_1d(n / 8, 256), 256, 0, STREAM>>>(
+                        (const T*)dh, (const T*)g, (const T*)u, (T*)dg, (T*)du, (T*)h_out, n / 8, act)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_softmax_fwd(const float* scores, void* p, int64_t Z, int64_t Sq, int64_t Sk, int64_t s_ld, int64_t p_ld,
+                     int heads, const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k, int p_dtype,
+                     void* stream) {
+  const int64_t rows = Z * Sq;
+  if (rows == 0) return 0;
+  B200_CHECK((bid_q == nullptr) == (bid_k == nullptr), "softmax_fwd: bid_q and bid_k go together");
+  const int dtype = p_dtype;
+  DISPATCH_T(dtype, (softmax_fwd_kernel<T><<<grid_1d(rows, 8), 256, 0, STREAM>>>(
+                        scores, (T*)p, rows, (int)Sq, (int)Sk, s_ld, p_ld, heads > 0 ? heads : 1, keymask, bid_q,
+                        bid_k)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+int b200_softmax_bwd(const void* p, const float* dp, void* ds, int64_t rows, int64_t Sk, int64_t p_ld, int64_t dp_ld,
+                     int64_t ds_ld, float scale, int p_dtype, void* stream) {
+  if (rows == 0) return 0;
+  const int dtype = p_dtype;
+  DISPATCH_T(dtype, (softmax_bwd_kernel<T><<<grid_1d(rows, 8), 256, 0, STREAM>>>((const T*)p, dp, (T*)ds, rows,
+                                                                                 (int)Sk, p_ld, dp_ld, ds_ld, scale)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_colsum(const void* x, float* out, int64_t M, int64_t N, int dtype, void* stream) {
+  B200_CHECK(N % 8 == 0, "colsum: N must be a multiple of 8");
+  if (M == 0) return 0;
+  const int rows_per_block = 128;
+  dim3 grid((unsigned)ceil_div(N / 8, 256), (unsigned)ceil_div(M, rows_per_block));
+  DISPATCH_T(dtype, (colsum_kernel<T><<<grid, 256, 0, STREAM>>>((const T*)x, out, (int)M, (int)N, rows_per_block)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_sumsq(const void* x, int64_t n, float* out, int dtype, void* stream) {
+  if (n == 0) return 0;
+  DISPATCH_T(dtype, (sumsq_kernel<T><<<grid_1d(n / 8 + 1, 256), 256, 0, STREAM>>>((const T*)x, n, out)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_mse_fwd(const void* a, const void* b, int64_t n, float* out, int dtype, void* stream) {
+  if (n == 0) return 0;
+  DISPATCH_T(dtype, (mse_fwd_kernel<T><<<grid_1d(n, 256), 256, 0, STREAM>>>((const T*)a, (const T*)b, n,
+                                                                            1.0f / (float)n, out)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+int b200_mse_bwd(const void* a, const void* b, int64_t n, const float* gscale, void* da, int dtype, void* stream) {
+  if (n == 0) return 0;
+  DISPATCH_T(dtype, (mse_bwd_kernel<T><<<grid_1d(n, 256), 256, 0, STREAM>>>((const T*)a, (const T*)b, n,
+                                                                            2.0f / (float)n, gscale, (T*)da)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_adamw(float* p, const void* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int64_t step, const float* clip, int g_dtype,
+               void* stream) {
+  if (n == 0) return 0;
+  B200_CHECK(step >= 1, "adamw: step must be >= 1");
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2 = 1.0f - powf(beta2, (float)step);
+  if (g_dtype == B200_F32)
+    adamw_kernel<float><<<grid_1d(n / 8 + 1, 256), 256, 0, STREAM>>>(p, (const float*)g, m, v, (bf16*)shadow_bf16, n,
+                                                                     lr, beta1, beta2, eps, weight_decay, bc1, bc2,
+                                                                     clip);
+  else
+    adamw_kernel<bf16><<<grid_1d(n / 8 + 1, 256), 256, 0, STREAM>>>(p, (const bf16*)g, m, v, (bf16*)shadow_bf16, n, lr,
+                                                                    beta1, beta2, eps, weight_decay, bc1, bc2, clip);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_clip_coef(const float* sumsq, float max_norm, float* clip, float* norm_out, void* stream) {
+  clip_coef_kernel<<<1, 1, 0, STREAM>>>(sumsq, max_norm, clip, norm_out);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream) {
+  if (n == 0) return 0;
+  const int g = grid_1d(n / 8 + 1, 256);
+  if (src_dtype == B200_F32 && dst_dtype == B200_BF16)
+    cast_kernel<float, bf16><<<g, 256, 0, STREAM>>>((const float*)src, (bf16*)dst, n);
+  else if (src_dtype == B200_BF16 && dst_dtype == B200_F32)
+    cast_kernel<bf16, float><<<g, 256, 0, STREAM>>>((const bf16*)src, (float*)dst, n);
+  else if (src_dtype == B200_F32)
+    cast_kernel<float, float><<<g, 256, 0, STREAM>>>((const float*)src, (float*)dst, n);
+  else
+    cast_kernel<bf16, bf16><<<g, 256, 0, STREAM>>>((const bf16*)src, (bf16*)dst, n);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_add(const void* a, const void* b, void* y, int64_t n, int dtype, void* stream) {
+  B200_CHECK(n % 8 == 0, "add: n must be a multiple of 8");
+  if (n == 0) return 0;
+  DISPATCH_T(dtype, (add_kernel<T><<<grid_1d(n / 8, 256), 256, 0, STREAM>>>((const T*)a, (const T*)b, (T*)y, n / 8)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

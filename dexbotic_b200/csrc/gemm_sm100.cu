@@ -1,0 +1,591 @@
+// tcgen05 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (TMEM accumulators,
+// double buffered) -> fused epilogue -> swizzled smem staging -> TMA store.
+//
+// One persistent CTA per SM, 8 warps:
+//   warp 0   TMA producer (one lane)            warp 2   TMEM allocator
+//   warp 1   MMA issuer   (one lane)            warps 4-7 epilogue (TMEM lane quarter = warp % 4)
+// Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static
+// round-robin tile schedule with an M-grouped order for L2 reuse.
+//
+// Everything is sized in BYTES so bf16 (kind::f16) and fp32 (kind::tf32) share one kernel:
+// a k-block is 128 bytes of K per row (64 bf16 / 32 fp32) = 4 UMMA instructions.
+// Operands may be K-major or MN-major (both via SWIZZLE_128B canonical layouts), so the
+// forward (x W^T), dgrad (dy W) and wgrad (dy^T x) forms of nn.Linear and the batched
+// attention products QK^T, PV, dP, dQ, dK, dV all run here without any transposes.
+//
+// Reference arithmetic replaced: see include/dexbotic_b200.h (b200_gemm).
+#include <cuda.h>
+
+#include "../../include/dexbotic_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int kBlockM = 128;
+constexpr int kStageABytes = kBlockM * 128;  // 16 KB
+constexpr int kGemmThreads = 256;
+constexpr int kGroupM = 16;
+constexpr int kStagingPerWarp = 2 * 32 * 128;  // two 32-row x 128-byte buffers
+
+struct GemmKParams {
+  CUtensorMap tmA, tmB, tmB2, tmD;
+  int M, N;
+  int m_blocks, n_blocks, tiles_per_batch, total_tiles;
+  int z_lo;
+  int kbps;      // k-blocks per K segment
+  int k_blocks;  // total k-blocks (= kbps * k_segs)
+  int bk_elems;  // elements of K per k-block (64 bf16 / 32 fp32)
+  int a_div, a_mul, a_seg, b_div, b_mul, b_seg;
+  int a_mn, b_mn;
+  int atom_elems;  // MN elements per 128-byte swizzle atom
+  int atom_bytes;  // bytes of one MN-major atom (bk_elems rows x 128 B)
+  int a_kadv, b_kadv, a_lbo, b_lbo;
+  int ab_fp32, d_fp32;
+  int dual;
+  int n_per_tile;  // output columns per tile (kBlockN, or 128 in dual mode)
+  float alpha;
+  const void* bias;
+  int bias_fp32;
+  const void* res;
+  int res_fp32;
+  long long res_ld, res_s2, res_s3;
+  void* aux;
+  void* aux2;
+  long long aux_ld, aux_s2, aux_s3;
+  int act;
+};
+
+template <int kBlockN>
+struct GemmCfg {
+  static constexpr int kStageBBytes = kBlockN * 128;
+  static constexpr int kStageBytes = kStageABytes + kStageBBytes;
+  static constexpr int kStages = kBlockN == 256 ? 4 : (kBlockN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * kBlockN;  // two accumulator stages
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 4 * kStagingPerWarp + kBarBytes;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case B200_ACT_GELU_ERF:
+      return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    case B200_ACT_GELU_TANH: {
+      float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+      return 0.5f * x * (1.0f + tanhf(u));
+    }
+    case B200_ACT_QUICK_GELU:
+      return x / (1.0f + __expf(-1.702f * x));
+    case B200_ACT_SILU:
+      return x / (1.0f + __expf(-x));
+    case B200_ACT_RELU:
+      return fmaxf(x, 0.0f);
+    default:
+      return x;
+  }
+}
+
+// Load up to 32 consecutive elements starting at p (16-byte aligned when valid >= 32).
+template <typename T>
+__device__ __forceinline__ void load_row32(const T* p, int valid, float (&out)[32]);
+
+template <>
+__device__ __forceinline__ void load_row32<__nv_bfloat16>(const __nv_bfloat16* p, int valid, float (&out)[32]) {
+  if (valid >= 32) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 v = __ldg(q + i);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(h[j]);
+        out[i * 8 + j * 2] = f.x;
+        out[i * 8 + j * 2 + 1] = f.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) out[i] = i < valid ? __bfloat162float(p[i]) : 0.0f;
+  }
+}
+template <>
+__device__ __forceinline__ void load_row32<float>(const float* p, int valid, float (&out)[32]) {
+  if (valid >= 32) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 v = __ldg(q + i);
+      out[i * 4] = v.x;
+      out[i * 4 + 1] = v.y;
+      out[i * 4 + 2] = v.z;
+      out[i * 4 + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) out[i] = i < valid ? p[i] : 0.0f;
+  }
+}
+__device__ __forceinline__ void load_row32_any(const void* base, long long elem_off, int fp32, int valid,
+                                               float (&out)[32]) {
+  if (fp32)
+    load_row32<float>(reinterpret_cast<const float*>(base) + elem_off, valid, out);
+  else
+    load_row32<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off, valid, out);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void store_row32_any(void* base, long long elem_off, int fp32, int valid,
+                                                const float (&v)[32]) {
+  if (fp32) {
+    float* p = reinterpret_cast<float*>(base) + elem_off;
+    if (valid >= 32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(p)[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < valid) p[i] = v[i];
+    }
+  } else {
+    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base) + elem_off;
+    if (valid >= 32) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<uint4*>(p)[i] =
+            make_uint4(pack_bf16(v[i * 8], v[i * 8 + 1]), pack_bf16(v[i * 8 + 2], v[i * 8 + 3]),
+                       pack_bf16(v[i * 8 + 4], v[i * 8 + 5]), pack_bf16(v[i * 8 + 6], v[i * 8 + 7]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < valid) p[i] = __float2bfloat16(v[i]);
+    }
+  }
+}
+
+struct TileCoord {
+  int zl, zh, m0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile) {
+  int z = tile / p.tiles_per_batch;
+  int t = tile - z * p.tiles_per_batch;
+  TileCoord c;
+  c.zh = z / p.z_lo;
+  c.zl = z - c.zh * p.z_lo;
+  int gsz = kGroupM * p.n_blocks;
+  int g = t / gsz;
+  int r = t - g * gsz;
+  int first_m = g * kGroupM;
+  int gm = min(p.m_blocks - first_m, kGroupM);
+  int nb = r / gm;
+  int mb = first_m + (r - nb * gm);
+  c.m0 = mb * kBlockM;
+  c.n0 = nb * p.n_per_tile;
+  return c;
+}
+
+template <int kBlockN>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
+  using Cfg = GemmCfg<kBlockN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 4 * kStagingPerWarp);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmD);
+    if (p.dual) tma_prefetch_desc(&p.tmB2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    mbar_fence_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int a_zbase = (tc.zl / p.a_div) * p.a_mul;
+        const int b_zbase = (tc.zl / p.b_div) * p.b_mul;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          const int seg = kb / p.kbps;
+          const int k0 = (kb - seg * p.kbps) * p.bk_elems;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + kStageABytes;
+          const int a_c2 = a_zbase + seg * p.a_seg;
+          const int b_c2 = b_zbase + seg * p.b_seg;
+          if (!p.a_mn) {
+            tma_load_4d(sa, &p.tmA, &full_bar[stage], k0, tc.m0, a_c2, tc.zh);
+          } else {
+            const int atoms = kBlockM / p.atom_elems;
+            for (int i = 0; i < atoms; ++i)
+              tma_load_4d(sa + i * p.atom_bytes, &p.tmA, &full_bar[stage], tc.m0 + i * p.atom_elems, k0, a_c2,
+                          tc.zh);
+          }
+          if (p.dual) {
+            tma_load_4d(sb, &p.tmB, &full_bar[stage], k0, tc.n0, b_c2, tc.zh);
+            tma_load_4d(sb + 128 * 128, &p.tmB2, &full_bar[stage], k0, tc.n0, b_c2, tc.zh);
+          } else if (!p.b_mn) {
+            tma_load_4d(sb, &p.tmB, &full_bar[stage], k0, tc.n0, b_c2, tc.zh);
+          } else {
+            const int atoms = kBlockN / p.atom_elems;
+            for (int i = 0; i < atoms; ++i)
+              tma_load_4d(sb + i * p.atom_bytes, &p.tmB, &full_bar[stage], tc.n0 + i * p.atom_elems, k0, b_c2,
+                          tc.zh);
+          }
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(p.ab_fp32 ? 2u : 1u, p.a_mn, p.b_mn, kBlockM, kBlockN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kBlockN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + kStageABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = umma_smem_desc(sa + k * p.a_kadv, p.a_lbo, 1024);
+            const uint64_t bd = umma_smem_desc(sb + k * p.b_kadv, p.b_lbo, 1024);
+            if (p.ab_fp32)
+              umma_tf32(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            else
+              umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue
+    const int w = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    uint8_t* stg = staging + w * kStagingPerWarp;
+    int buf = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int chunk_cols = p.d_fp32 ? 32 : 64;
+    const int sw = lane & 7;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = tc.m0 + w * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t trow = tmem_base + acc * kBlockN + (static_cast<uint32_t>(w * 32) << 16);
+      const long long res_row = tc.zh * p.res_s3 + tc.zl * p.res_s2 + static_cast<long long>(row) * p.res_ld;
+      const long long aux_row = tc.zh * p.aux_s3 + tc.zl * p.aux_s2 + static_cast<long long>(row) * p.aux_ld;
+
+      for (int c = 0; c < p.n_per_tile; c += chunk_cols) {
+        if (tc.n0 + c >= p.N) break;  // warp-uniform: fully out-of-range chunk
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        uint8_t* sbuf = stg + buf * (32 * 128) + lane * 128;
+        for (int h = 0; h < chunk_cols / 32; ++h) {
+          const int col0 = c + h * 32;
+          const int n = tc.n0 + col0;
+          const int valid = p.N - n;  // may be <= 0 or >= 32
+          uint32_t r[32];
+          float v[32];
+          tmem_ld_32x32(trow + col0, r);
+          if (p.dual) {
+            uint32_t r2[32];
+            tmem_ld_32x32(trow + 128 + col0, r2);
+            tmem_ld_wait();
+            float g[32], u[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              g[j] = __uint_as_float(r[j]) * p.alpha;
+              u[j] = __uint_as_float(r2[j]) * p.alpha;
+            }
+            if (p.aux != nullptr && row_ok && valid > 0) {
+              store_row32_any(p.aux, aux_row + n, p.d_fp32, valid, g);
+              store_row32_any(p.aux2, aux_row + n, p.d_fp32, valid, u);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(g[j], p.act) * u[j];
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+            if (p.bias != nullptr && valid > 0) {
+              float bv[32];
+              load_row32_any(p.bias, n, p.bias_fp32, valid, bv);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += bv[j];
+            }
+            if (p.aux != nullptr && row_ok && valid > 0) store_row32_any(p.aux, aux_row + n, p.d_fp32, valid, v);
+            if (p.act != B200_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+            }
+          }
+          if (p.res != nullptr && row_ok && valid > 0) {
+            float rv[32];
+            load_row32_any(p.res, res_row + n, p.res_fp32, valid, rv);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += rv[j];
+          }
+          // registers -> 128B-swizzled staging row (16-byte chunk index XOR row%8)
+          if (p.d_fp32) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(sbuf + ((q ^ sw) << 4)) =
+                  make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(sbuf + (((h * 4 + q) ^ sw) << 4)) =
+                  make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                             pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && tc.m0 + w * 32 < p.M) {
+          tma_store_4d(&p.tmD, stg + buf * (32 * 128), tc.n0 + c, tc.m0 + w * 32, tc.zl, tc.zh);
+          tma_store_commit();
+        }
+        buf ^= 1;
+      }
+      // this warp's TMEM reads of the tile are complete -> hand the accumulator back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// dims/strides in ELEMENTS (stride of dim 0 is 1); box = (b0, b1, 1, 1); SWIZZLE_128B.
+static int encode_4d(CUtensorMap* m, int fp32, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                     int64_t s1, int64_t s2, int64_t s3, uint32_t b0, uint32_t b1, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  B200_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  const uint64_t es = fp32 ? 4 : 2;
+  cuuint64_t dims[4] = {d0, d1, d2, d3};
+  // unit dims still need a legal (multiple of 16 B, non-zero) stride
+  if (s1 <= 0) s1 = (int64_t)((d0 + 15) / 16 * 16);
+  if (s2 <= 0) s2 = s1 * (int64_t)d1;
+  if (s3 <= 0) s3 = s2 * (int64_t)d2;
+  cuuint64_t strides[3] = {(cuuint64_t)s1 * es, (cuuint64_t)s2 * es, (cuuint64_t)s3 * es};
+  cuuint32_t box[4] = {b0, b1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  B200_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "%s: base pointer not 16-byte aligned", what);
+  for (int i = 0; i < 3; ++i)
+    B200_CHECK(strides[i] % 16 == 0, "%s: stride %d (%llu bytes) not a multiple of 16", what, i + 1,
+               (unsigned long long)strides[i]);
+  CUresult r = fn(m, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK(r == CUDA_SUCCESS,
+             "%s: cuTensorMapEncodeTiled failed (%d) dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) box=(%u,%u)",
+             what, (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+             (unsigned long long)d3, (unsigned long long)strides[0], (unsigned long long)strides[1],
+             (unsigned long long)strides[2], b0, b1);
+  return 0;
+}
+
+template <int kBlockN>
+static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
+  using Cfg = GemmCfg<kBlockN>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kBlockN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
+    configured = true;
+  }
+  int grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
+  gemm_tcgen05_kernel<kBlockN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(kp);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_gemm(const b200_gemm_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK(a != nullptr, "b200_gemm: null args");
+  B200_CHECK(a->m > 0 && a->n > 0 && a->k > 0, "b200_gemm: empty problem m=%lld n=%lld k=%lld", (long long)a->m,
+             (long long)a->n, (long long)a->k);
+  const int fp32 = a->ab_dtype == B200_F32;
+  const int es = fp32 ? 4 : 2;
+  const int z_lo = a->z_lo > 0 ? a->z_lo : 1, z_hi = a->z_hi > 0 ? a->z_hi : 1;
+  const int k_segs = a->k_segs > 0 ? a->k_segs : 1;
+
+  int bn = a->block_n;
+  if (a->dual_b) {
+    bn = 256;
+    B200_CHECK(!a->a_mn_major && !a->b_mn_major && a->b2 != nullptr, "b200_gemm: dual_b needs K-major A, B, B2");
+  } else if (bn == 0) {
+    bn = a->n <= 64 ? 64 : (a->n <= 128 ? 128 : 256);
+  }
+  B200_CHECK(bn == 64 || bn == 128 || bn == 256, "b200_gemm: block_n must be 64/128/256");
+
+  GemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.M = (int)a->m;
+  kp.N = (int)a->n;
+  kp.bk_elems = 128 / es;
+  kp.atom_elems = 128 / es;
+  kp.atom_bytes = kp.bk_elems * 128;
+  kp.n_per_tile = a->dual_b ? 128 : bn;
+  kp.m_blocks = (int)ceil_div(a->m, kBlockM);
+  kp.n_blocks = (int)ceil_div(a->n, kp.n_per_tile);
+  kp.tiles_per_batch = kp.m_blocks * kp.n_blocks;
+  kp.total_tiles = kp.tiles_per_batch * z_lo * z_hi;
+  kp.z_lo = z_lo;
+  kp.kbps = (int)ceil_div(a->k, kp.bk_elems);
+  kp.k_blocks = kp.kbps * k_segs;
+  kp.a_div = a->a_div > 0 ? a->a_div : 1;
+  kp.a_mul = a->a_mul;
+  kp.a_seg = a->a_seg;
+  kp.b_div = a->b_div > 0 ? a->b_div : 1;
+  kp.b_mul = a->b_mul;
+  kp.b_seg = a->b_seg;
+  if (z_lo == 1 && a->a_mul == 0 && a->a_div <= 1) kp.a_mul = 1;
+  if (z_lo == 1 && a->b_mul == 0 && a->b_div <= 1) kp.b_mul = 1;
+  kp.a_mn = a->a_mn_major ? 1 : 0;
+  kp.b_mn = a->b_mn_major ? 1 : 0;
+  // K-major: advance 32 B inside the swizzle row; LBO unused (16).  MN-major: advance UMMA_K rows of 128 B,
+  // LBO = distance between 128-byte MN atoms = one atom (bk_elems rows x 128 B).
+  kp.a_kadv = kp.a_mn ? (32 / es) * 128 : 32;
+  kp.b_kadv = kp.b_mn ? (32 / es) * 128 : 32;
+  kp.a_lbo = kp.a_mn ? kp.atom_bytes : 16;
+  kp.b_lbo = kp.b_mn ? kp.atom_bytes : 16;
+  kp.ab_fp32 = fp32;
+  kp.d_fp32 = a->d_dtype == B200_F32;
+  kp.dual = a->dual_b ? 1 : 0;
+  kp.alpha = a->alpha == 0.0f ? 1.0f : a->alpha;
+  kp.bias = a->bias;
+  kp.bias_fp32 = a->bias_dtype == B200_F32;
+  kp.res = a->residual;
+  kp.res_fp32 = a->res_dtype == B200_F32;
+  kp.res_ld = a->res_ld;
+  kp.res_s2 = a->res_s2;
+  kp.res_s3 = a->res_s3;
+  kp.aux = a->aux;
+  kp.aux2 = a->aux2;
+  kp.aux_ld = a->aux_ld;
+  kp.aux_s2 = a->d_s2;
+  kp.aux_s3 = a->d_s3;
+  kp.act = a->act;
+  if (kp.dual) B200_CHECK((kp.aux == nullptr) == (kp.aux2 == nullptr), "b200_gemm: dual_b aux and aux2 go together");
+  if (kp.res) B200_CHECK(a->res_ld % (16 / (kp.res_fp32 ? 4 : 2)) == 0, "b200_gemm: residual ld not 16B-multiple");
+  if (kp.aux) B200_CHECK(a->aux_ld % (16 / (kp.d_fp32 ? 4 : 2)) == 0, "b200_gemm: aux ld not 16B-multiple");
+
+  const uint32_t a_z2 = a->a_z2 > 0 ? a->a_z2 : 1, b_z2 = a->b_z2 > 0 ? a->b_z2 : 1;
+  // A
+  if (!kp.a_mn) {
+    if (encode_4d(&kp.tmA, fp32, a->a, a->k, a->m, a_z2, z_hi, a->a_ld, a->a_s2, a->a_s3, kp.bk_elems, kBlockM, "A"))
+      return 1;
+  } else {
+    if (encode_4d(&kp.tmA, fp32, a->a, a->m, a->k, a_z2, z_hi, a->a_ld, a->a_s2, a->a_s3, kp.atom_elems, kp.bk_elems,
+                  "A(mn)"))
+      return 1;
+  }
+  // B
+  if (kp.dual) {
+    if (encode_4d(&kp.tmB, fp32, a->b, a->k, a->n, 1, 1, a->b_ld, 0, 0, kp.bk_elems, 128, "B(gate)")) return 1;
+    if (encode_4d(&kp.tmB2, fp32, a->b2, a->k, a->n, 1, 1, a->b_ld, 0, 0, kp.bk_elems, 128, "B2(up)")) return 1;
+  } else if (!kp.b_mn) {
+    if (encode_4d(&kp.tmB, fp32, a->b, a->k, a->n, b_z2, z_hi, a->b_ld, a->b_s2, a->b_s3, kp.bk_elems, bn, "B"))
+      return 1;
+  } else {
+    if (encode_4d(&kp.tmB, fp32, a->b, a->n, a->k, b_z2, z_hi, a->b_ld, a->b_s2, a->b_s3, kp.atom_elems, kp.bk_elems,
+                  "B(mn)"))
+      return 1;
+  }
+  // D: store boxes are 32 rows x 128 bytes
+  if (encode_4d(&kp.tmD, kp.d_fp32, a->d, a->n, a->m, z_lo, z_hi, a->d_ld, a->d_s2, a->d_s3, kp.d_fp32 ? 32 : 64, 32,
+                "D"))
+    return 1;
+
+  switch (bn) {
+    case 64:
+      return launch_gemm<64>(kp, stream);
+    case 128:
+      return launch_gemm<128>(kp, stream);
+    default:
+      return launch_gemm<256>(kp, stream);
+  }
+}

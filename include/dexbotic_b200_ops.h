@@ -1,0 +1,133 @@
+/*
+ * dexbotic_b200 — C-ABI, part 2: the HBM-bound operators of the VLA hot path.
+ * Same conventions as dexbotic_b200.h (device pointers, stream as void*, 0 = ok).
+ * `dtype` is B200_BF16 or B200_F32 and names the activation/storage type; all arithmetic
+ * accumulates in fp32.  Citations are the reference Python call sites (under
+ * /root/reference) whose arithmetic each entry point replaces; where the arithmetic lives in
+ * an un-vendored third-party module (HF transformers 4.51/4.54, timm — SURVEY.md §8c) the
+ * reference line is the call into it.
+ */
+#ifndef DEXBOTIC_B200_OPS_H
+#define DEXBOTIC_B200_OPS_H
+
+#include <stdint.h>
+
+#include "dexbotic_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* RMSNorm  y = w * round(x * rsqrt(mean(x^2)+eps))            (HF Qwen2RMSNorm / LlamaRMSNorm,
+ * unit_offset=1: y = (x*rstd) * (1+w)  (HF GemmaRMSNorm);  decoder built at dexbotic_arch.py:55-62,
+ * final norm read at cogact_arch.py:108.  rstd[M] (fp32) is saved for backward (may be NULL). */
+int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t M, int64_t D, float eps,
+                     int unit_offset, int dtype, void* stream);
+/* dx (=, or += if accumulate_dx) and dw[D] (fp32, += via atomics; may be NULL). */
+int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw, int64_t M,
+                     int64_t D, int unit_offset, int accumulate_dx, int dtype, void* stream);
+
+/* LayerNorm (w, b optional): HF CLIPEncoderLayer.layer_norm1/2, pre_layrnorm (clip_encoder.py:50-54);
+ * DiT norm1/norm2/norm_final, elementwise_affine=False (dit.py:141,147,167). */
+int b200_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t M,
+                       int64_t D, float eps, int dtype, void* stream);
+int b200_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
+                       float* dw, float* db, int64_t M, int64_t D, int accumulate_dx, int dtype, void* stream);
+
+/* rotate_half RoPE, in place, on the first n_rot_heads heads (q then k) of each row of a packed
+ * [M, row_stride] qkv buffer.  cos/sin: fp32 [n_pos, head_dim/2] tables, pos: int32 [M].
+ * inverse=1 applies the transpose (backward).  HF apply_rotary_pos_emb inside Qwen2/Llama
+ * attention; position_ids come from dexbotic_arch.py:368-371. */
+int b200_rope(void* qkv, const int32_t* pos, const float* cos_t, const float* sin_t, int64_t M, int n_rot_heads,
+              int head_dim, int64_t row_stride, int inverse, int dtype, void* stream);
+
+/* y = act(x) ; dx = dy * act'(x).  act codes: B200_ACT_*. */
+int b200_act_fwd(const void* x, void* y, int64_t n, int act, int dtype, void* stream);
+int b200_act_bwd(const void* dy, const void* x, void* dx, int64_t n, int act, int dtype, void* stream);
+/* h = act(g) * u  (HF Qwen2MLP: down(silu(gate(x)) * up(x)); GemmaMLP with gelu_tanh) */
+int b200_glu_fwd(const void* g, const void* u, void* h, int64_t n, int act, int dtype, void* stream);
+/* dg = dh*u*act'(g), du = dh*act(g) (may alias g/u); h_out optional recompute of h. */
+int b200_glu_bwd(const void* dh, const void* g, const void* u, void* dg, void* du, void* h_out, int64_t n, int act,
+                 int dtype, void* stream);
+
+/* Masked softmax over fp32 score rows [Z, Sq, s_ld] -> P [Z, Sq, p_ld] (p_dtype).  Batch b = z / heads.
+ * allowed(q,k) = (keymask==NULL || keymask[b,k]) && (bid_q==NULL || bid_k[b,k] <= bid_q[b,q]):
+ *   causal decoder: bid = position index (HF SDPA causal mask + padding mask);
+ *   pi0 block-causal: bid = cumsum(ar_mask) (pi0_arch.py:22-33);  ViT / DiT: no mask. */
+int b200_softmax_fwd(const float* scores, void* p, int64_t Z, int64_t Sq, int64_t Sk, int64_t s_ld, int64_t p_ld,
+                     int heads, const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k, int p_dtype,
+                     void* stream);
+/* dS = scale * P * (dP - rowsum(P*dP)) */
+int b200_softmax_bwd(const void* p, const float* dp, void* ds, int64_t rows, int64_t Sk, int64_t p_ld, int64_t dp_ld,
+                     int64_t ds_ld, float scale, int p_dtype, void* stream);
+
+/* out[N] (fp32) += column sums of x[M,N]  (bias gradients) */
+int b200_colsum(const void* x, float* out, int64_t M, int64_t N, int dtype, void* stream);
+/* *out (fp32) += sum(x^2)  (global grad-norm, trainer.py:122 max_grad_norm=1.0) */
+int b200_sumsq(const void* x, int64_t n, float* out, int dtype, void* stream);
+int b200_clip_coef(const float* sumsq, float max_norm, float* clip, float* norm_out, void* stream);
+
+/* *out += mean((a-b)^2)   (action_models.py:119-121; pi0_arch.py:388) ; da = 2(a-b)/n * (*gscale) */
+int b200_mse_fwd(const void* a, const void* b, int64_t n, float* out, int dtype, void* stream);
+int b200_mse_bwd(const void* a, const void* b, int64_t n, const float* gscale, void* da, int dtype, void* stream);
+
+/* torch.optim.AdamW step on a flat fp32 master buffer (trainer.py:25-36 create_optimizer); gradient
+ * in g (g_dtype), optional bf16 shadow of the updated weights, device-side clip coefficient. */
+int b200_adamw(float* p, const void* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int64_t step, const float* clip, int g_dtype, void* stream);
+
+int b200_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
+int b200_add(const void* a, const void* b, void* y, int64_t n, int dtype, void* stream);
+
+/* ---- image-token splice (dexbotic_arch.py:182-373) -------------------------------------------------
+ * Plan: for every sample, drop padding (attention_mask), replace each IMAGE_TOKEN_INDEX (-200) by the
+ * next n_img_tokens rows of the image features, truncate to max_len, pad to S (right or left).
+ * Outputs: src[B*S] (>=0: token id; -1-j: image-feature row j; INT32_MIN: pad), new_labels[B*S]
+ * (int64, -100 on image span / pad), new_mask[B*S] (uint8), pos[B*S] (int32), lengths[B] (int32).
+ * S must be >= max length (b200_splice_lengths computes lengths first; host reads the max). */
+int b200_splice_lengths(const int64_t* input_ids, const uint8_t* attention_mask, int64_t B, int64_t L,
+                        int n_img_tokens, int64_t max_len, int32_t* lengths, void* stream);
+int b200_splice_plan(const int64_t* input_ids, const uint8_t* attention_mask, const int64_t* labels, int64_t B,
+                     int64_t L, int n_img_tokens, int64_t max_len, int64_t S, int left_pad, int32_t* src,
+                     int64_t* new_labels, uint8_t* new_mask, int32_t* pos, void* stream);
+/* out[r,:] = src[r]>=0 ? table[src[r]] : (src[r]==INT32_MIN ? 0 : feats[-1-src[r]])   rows of D elements */
+int b200_splice_gather(const int32_t* src, const void* table, const void* feats, void* out, int64_t rows, int64_t D,
+                       int dtype, void* stream);
+/* backward: d_table[id] += sum of dout rows whose src == id (fp32 sum, one deterministic add per id);
+ * d_feats[-1-src[r]] = dout[r].  Either output may be NULL (frozen embedding / frozen tower). */
+int b200_splice_scatter(const int32_t* src, const void* dout, void* d_table, void* d_feats, int64_t rows, int64_t D,
+                        int dtype, void* stream);
+
+/* out[i,:] = x[idx[i],:] ; backward dx[idx[i],:] += dout[i,:]   (cognition token: cogact_arch.py:110-120;
+ * OFT action-position extract: oft_arch.py:204-210) */
+int b200_gather_rows(const void* x, const int32_t* idx, void* out, int64_t n_idx, int64_t D, int dtype, void* stream);
+int b200_scatter_rows_add(const void* dout, const int32_t* idx, void* dx, int64_t n_idx, int64_t D, int dtype,
+                          void* stream);
+/* idx[b] = b*S + (index of last position with mask[b,:]!=0)   (cogact_arch.py:112-117) */
+int b200_last_valid_index(const uint8_t* mask, int64_t B, int64_t S, int32_t* idx, void* stream);
+
+/* x_t = sqrt_ac[t]*x + sqrt_1mac[t]*noise   (diffusion.py:308-326 q_sample; tables from diffusion.py:187-231) */
+int b200_q_sample(const void* x, const void* noise, const int32_t* t, const float* sqrt_ac, const float* sqrt_1mac,
+                  void* x_t, int64_t B, int64_t per_sample, int dtype, void* stream);
+/* sinusoidal timestep embedding [B, dim] = [cos(t*f) | sin(t*f)]  (dit.py:37-56) */
+int b200_timestep_embedding(const float* t, void* out, int64_t B, int dim, float max_period, int dtype, void* stream);
+
+/* ---- OFT discrete action tokenizer (integer path; bit-exact) ---------------------------------------
+ * bins[i] = (int64) round_half_even((clamp(a,-1,1)+1)/2 * (n_bins-1))          oft/action_model/model.py:303-312
+ * cont[i] = bins[i] / (n_bins-1) * 2 - 1                                        model.py:314-323
+ * idx[r]  = argmax_j logits[r, V-n_last+j], first maximum wins                 oft_discrete_arch.py:222-224 */
+int b200_discretize_actions(const float* actions, int64_t n, int n_bins, int64_t* bins, void* stream);
+int b200_bins_to_continuous(const int64_t* bins, int64_t n, int n_bins, float* out, void* stream);
+int b200_argmax_last(const void* logits, int64_t rows, int64_t V, int n_last, int64_t* idx, int dtype, void* stream);
+/* Cross entropy over fp32-upcast logits rows with int64 labels (ignore_index=-100), mean over valid rows:
+ * *loss += sum(-log softmax[label]) / n_valid ; lse[rows] saved.  Backward: dlogits = (softmax - onehot) * g / n_valid.
+ * oft_discrete_arch.py:187-191 (F.cross_entropy under fp32 autocast); DexboticForCausalLM loss (dexbotic_arch.py:489). */
+int b200_cross_entropy_fwd(const void* logits, const int64_t* labels, int64_t rows, int64_t V, float* lse,
+                           float* loss_sum, int32_t* n_valid, int dtype, void* stream);
+int b200_cross_entropy_bwd(const void* logits, const int64_t* labels, const float* lse, const int32_t* n_valid,
+                           const float* gscale, void* dlogits, int64_t rows, int64_t V, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
