@@ -40,7 +40,7 @@ struct GemmKParams {
   int a_mn, b_mn;
   int atom_elems;  // MN elements per 128-byte swizzle atom
   int atom_bytes;  // bytes of one MN-major atom (bk_elems rows x 128 B)
-  int a_kadv, b_kadv, a_lbo, b_lbo;
+  int a_kadv, b_kadv, a_lbo, b_lbo, a_sbo, b_sbo, a_lt, b_lt;
   int ab_fp32, d_fp32;
   int dual;
   int n_per_tile;  // output columns per tile (kBlockN, or 128 in dual mode)
@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           const uint32_t sb = sa + kStageABytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = umma_smem_desc(sa + k * p.a_kadv, p.a_lbo, 1024);
-            const uint64_t bd = umma_smem_desc(sb + k * p.b_kadv, p.b_lbo, 1024);
+            const uint64_t ad = umma_smem_desc(sa + k * p.a_kadv, p.a_lbo, p.a_sbo, p.a_lt);
+            const uint64_t bd = umma_smem_desc(sb + k * p.b_kadv, p.b_lbo, p.b_sbo, p.b_lt);
             if (p.ab_fp32)
               umma_tf32(d_tmem, ad, bd, idesc, (kb | k) != 0);
             else
@@ -434,9 +434,11 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// dims/strides in ELEMENTS (stride of dim 0 is 1); box = (b0, b1, 1, 1); SWIZZLE_128B.
+// dims/strides in ELEMENTS (stride of dim 0 is 1); box = (b0, b1, 1, 1); SWIZZLE_128B, or the
+// 32-byte-atom variant (SWIZZLE_128B_ATOM_32B) that MN-major tf32 operands require.
 static int encode_4d(CUtensorMap* m, int fp32, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
-                     int64_t s1, int64_t s2, int64_t s3, uint32_t b0, uint32_t b1, const char* what) {
+                     int64_t s1, int64_t s2, int64_t s3, uint32_t b0, uint32_t b1, const char* what,
+                     bool atom32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   B200_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
   const uint64_t es = fp32 ? 4 : 2;
@@ -454,7 +456,8 @@ static int encode_4d(CUtensorMap* m, int fp32, const void* ptr, uint64_t d0, uin
                (unsigned long long)strides[i]);
   CUresult r = fn(m, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_CHECK(r == CUDA_SUCCESS,
              "%s: cuTensorMapEncodeTiled failed (%d) dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) box=(%u,%u)",
              what, (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
@@ -532,6 +535,12 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream_) {
   kp.b_kadv = kp.b_mn ? (32 / es) * 128 : 32;
   kp.a_lbo = kp.a_mn ? kp.atom_bytes : 16;
   kp.b_lbo = kp.b_mn ? kp.atom_bytes : 16;
+  // MN-major tf32: SWIZZLE_128B_BASE32B atoms are 128 B x 4 k-rows -> SBO (next k-group) = 512 B
+  const bool a_atom32 = kp.a_mn && fp32, b_atom32 = kp.b_mn && fp32;
+  kp.a_sbo = a_atom32 ? 512 : 1024;
+  kp.b_sbo = b_atom32 ? 512 : 1024;
+  kp.a_lt = a_atom32 ? 1 : 2;
+  kp.b_lt = b_atom32 ? 1 : 2;
   kp.ab_fp32 = fp32;
   kp.d_fp32 = a->d_dtype == B200_F32;
   kp.dual = a->dual_b ? 1 : 0;
@@ -560,7 +569,7 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream_) {
       return 1;
   } else {
     if (encode_4d(&kp.tmA, fp32, a->a, a->m, a->k, a_z2, z_hi, a->a_ld, a->a_s2, a->a_s3, kp.atom_elems, kp.bk_elems,
-                  "A(mn)"))
+                  "A(mn)", a_atom32))
       return 1;
   }
   // B
@@ -572,7 +581,7 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream_) {
       return 1;
   } else {
     if (encode_4d(&kp.tmB, fp32, a->b, a->n, a->k, b_z2, z_hi, a->b_ld, a->b_s2, a->b_s3, kp.atom_elems, kp.bk_elems,
-                  "B(mn)"))
+                  "B(mn)", b_atom32))
       return 1;
   }
   // D: store boxes are 32 rows x 128 bytes

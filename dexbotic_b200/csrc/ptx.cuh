@@ -148,11 +148,13 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------ smem / idesc
-// UMMA shared-memory matrix descriptor, SWIZZLE_128B (layout_type = 2), version = 1 (Blackwell).
+// UMMA shared-memory matrix descriptor, version = 1 (Blackwell).  layout_type: 2 = SWIZZLE_128B,
+// 1 = SWIZZLE_128B_BASE32B (the only legal layout for MN-major tf32 operands).
 // lbo/sbo are byte offsets (16-byte units in the descriptor).
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
   uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
-  uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+  uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 // Instruction descriptor (upper 32 bits of the 64-bit idesc): fp32 accumulate, dense.

@@ -1,0 +1,191 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.pt by running the UNMODIFIED reference
+(/root/reference, via oracle/ref_loader.py) in THIS container, and checks the oracle restatement
+(oracle/vla_oracle.py) against it.  Run:  python -m oracle.make_golden
+
+Fixtures hold inputs + the reference's outputs only; weights are regenerated from a per-tensor seed
+(oracle.weights.seeded_state_dict) so the files stay small.  The GPU box has no /root/reference: there
+the committed fixtures + the restatement are the checker.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle import ref_loader, vla_oracle  # noqa: E402
+from oracle.weights import seeded_state_dict  # noqa: E402
+
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def tiny_cogact_configs():
+    from transformers import CLIPVisionConfig, Qwen2Config
+    llm = Qwen2Config(vocab_size=128, hidden_size=64, intermediate_size=160, num_hidden_layers=2,
+                      num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256, rope_theta=1e6,
+                      rms_norm_eps=1e-6)
+    clip = CLIPVisionConfig(hidden_size=32, intermediate_size=64, num_hidden_layers=3, num_attention_heads=2,
+                            image_size=28, patch_size=14, hidden_act="quick_gelu")
+    cfg = dict(
+        llm=dict(vocab_size=128, hidden_size=64, intermediate_size=160, num_hidden_layers=2, num_attention_heads=4,
+                 num_key_value_heads=2, rope_theta=1e6, rms_norm_eps=1e-6, hidden_act="silu", attention_bias=True,
+                 model_type="qwen2"),
+        vision=dict(hidden_size=32, intermediate_size=64, num_hidden_layers=3, num_attention_heads=2, image_size=28,
+                    patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5),
+        action_model_type="DiT-S", action_dim=7, chunk_size=16, projector_depth=2, diffusion_steps=100,
+        tokenizer_model_max_length=None, tokenizer_padding_side="right")
+    return llm, clip, cfg
+
+
+def make_cogact_tiny(seed: int = 1234):
+    llm, clip, cfg = tiny_cogact_configs()
+    model = ref_loader.build_reference_cogact(llm, clip, "DiT-S")
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+    missing = model.load_state_dict(sd, strict=True)
+    model.train()
+
+    g = torch.Generator().manual_seed(seed)
+    B, L = 3, 14
+    ids = torch.randint(1, 128, (B, L), generator=g)
+    ids[:, 1] = vla_oracle.IMAGE_TOKEN_INDEX
+    mask = torch.ones(B, L, dtype=torch.long)
+    mask[1, 10:] = 0
+    mask[2, 12:] = 0
+    images = torch.randn(B, 3, 28, 28, generator=g)
+    actions = torch.rand(B, 16 * 7, generator=g) * 2 - 1
+
+    # the reference draws noise / timesteps / drop ids from the global RNG, in this order:
+    #   torch.randn_like(x) (action_models.py:106), torch.randint (:107-109), torch.rand (dit.py:86-88)
+    R = 4
+    torch.manual_seed(seed + 1)
+    out = model(input_ids=ids, attention_mask=mask, images=images, actions=actions, repeated_diffusion_steps=R)
+    out.loss.backward()
+    torch.manual_seed(seed + 1)
+    noise = torch.randn(R * B, 16, 7)
+    timesteps = torch.randint(0, 100, (R * B,))
+    drop = torch.rand(R * B) < 0.1
+
+    ora = vla_oracle.cogact_forward(sd, cfg, ids, mask, images, actions, noise, timesteps, drop, R)
+    err_loss = abs(ora["loss"].item() - out.loss.item())
+    valid = ora["attention_mask"][:, :, None]      # rows at padded positions are unspecified (never consumed)
+    err_hid = ((ora["last_hidden"] - out.logits) * valid).abs().max().item()
+    print(f"[cogact_tiny] reference loss {out.loss.item():.8f} oracle {ora['loss'].item():.8f} |d|={err_loss:.2e}; "
+          f"last_hidden max|d|={err_hid:.2e}")
+    assert err_loss < 1e-5 and err_hid < 1e-4, "oracle restatement disagrees with the reference"
+
+    # reference gradients for a few parameters (checks the product's backward)
+    grads = {}
+    for name in ["model.llm.layers.0.self_attn.q_proj.weight", "model.llm.layers.1.mlp.down_proj.weight",
+                 "model.llm.embed_tokens.weight", "model.mm_projector.0.weight",
+                 "model.action_head.net.blocks.0.attn.qkv.weight", "model.action_head.net.z_embedder.linear.weight",
+                 "model.llm.norm.weight", "model.llm.layers.0.self_attn.k_proj.bias"]:
+        p = dict(model.named_parameters())[name]
+        grads[name] = p.grad.clone()
+    # oracle gradient check (autograd through the restatement)
+    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
+    ora_g = vla_oracle.cogact_forward(sd_g, cfg, ids, mask, images, actions, noise, timesteps, drop, R)
+    ora_g["loss"].backward()
+    for name, gref in grads.items():
+        d = (sd_g[name].grad - gref).abs().max().item()
+        assert d < 1e-5 + 1e-3 * gref.abs().max().item(), f"oracle grad mismatch for {name}: {d}"
+    fixture = dict(
+        seed=seed, cfg=cfg, shapes={k: tuple(v.shape) for k, v in sd.items()},
+        inputs=dict(input_ids=ids, attention_mask=mask, images=images, actions=actions, noise=noise,
+                    timesteps=timesteps, drop_mask=drop, repeated_diffusion_steps=R),
+        outputs=dict(loss=out.loss.detach(), last_hidden=(out.logits * valid).detach(),
+                     valid=ora["attention_mask"], cognition=ora["cognition"].detach(),
+                     grads=grads))
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    torch.save(fixture, GOLDEN / "cogact_tiny.pt")
+    print(f"[cogact_tiny] wrote {GOLDEN / 'cogact_tiny.pt'}")
+
+
+def make_splice_cases(seed: int = 7):
+    """Splice layouts from the reference's own _prepare_inputs_labels_for_multimodal (dexbotic_arch.py:182-373)."""
+    llm, clip, cfg = tiny_cogact_configs()
+    model = ref_loader.build_reference_cogact(llm, clip, "DiT-S")
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+    model.load_state_dict(sd)
+    model.eval()
+    g = torch.Generator().manual_seed(seed)
+    cases = []
+    for name, n_img, side, max_len in [("one_image_right", 1, "right", None), ("no_image_row", 1, "right", None),
+                                       ("two_images_left", 2, "left", None), ("truncate", 1, "right", 9)]:
+        B, L = 4, 12
+        ids = torch.randint(1, 128, (B, L), generator=g)
+        labels = torch.randint(0, 128, (B, L), generator=g)
+        mask = torch.ones(B, L, dtype=torch.long)
+        mask[0, 8:] = 0
+        mask[3, 11:] = 0
+        n_entries = 0
+        for b in range(B):
+            k = 0 if (name == "no_image_row" and b == 2) else n_img
+            pos = torch.randperm(7, generator=g)[:k] + 1
+            ids[b, pos] = vla_oracle.IMAGE_TOKEN_INDEX
+            n_entries += max(k, 1)
+        images = torch.randn(n_entries, 3, 28, 28, generator=g)
+        model.model.config.tokenizer_padding_side = side
+        model.model.config.tokenizer_model_max_length = max_len
+        with torch.no_grad():
+            _, pid, m, _, emb, lab, _ = model.model._prepare_inputs_labels_for_multimodal(
+                ids, None, mask, None, labels, None, images)
+            feats = model.model._extract_vision_features(images)
+        o_emb, o_lab, o_msk, o_pid = vla_oracle.splice(sd["model.llm.embed_tokens.weight"], feats, ids, mask, labels,
+                                                       max_len, side)
+        assert torch.equal(o_emb, emb) and torch.equal(o_lab, lab) and torch.equal(o_msk, m.bool())
+        cases.append(dict(name=name, input_ids=ids, attention_mask=mask, labels=labels, padding_side=side,
+                          max_len=max_len, n_img_tokens=feats.shape[1], image_features=feats,
+                          embed_weight=sd["model.llm.embed_tokens.weight"], inputs_embeds=emb, new_labels=lab,
+                          new_mask=m.bool()))
+        print(f"[splice] {name}: S={emb.shape[1]} ok")
+    torch.save(cases, GOLDEN / "splice_cases.pt")
+
+
+def make_integer_kats():
+    """Known-answer vectors for the OFT discrete tokenizer, from the reference's own code."""
+    ref_loader.load_reference()
+    from dexbotic.model.oft.action_model.model import DiscreteActionHead
+    from dexbotic.data.dataset.transform.action import ActionNormAnd2String
+    head = DiscreteActionHead(input_dim=64, vocab_size=512, action_dim=7, action_chunk=8, num_bins=256)
+    g = torch.Generator().manual_seed(99)
+    k = torch.arange(0, 255, dtype=torch.float32)
+    a = torch.cat([torch.rand(4096, generator=g) * 2.4 - 1.2,
+                   torch.tensor([-1.0, 1.0, 0.0, 1 / 255, -1 / 255, 0.5 / 255, 1.5 / 255, 2.5 / 255]),
+                   (k + 0.5) / 255 * 2 - 1])           # exact ties under the x255 map (half-to-even)
+    a = a[: (a.numel() // 56) * 56].reshape(-1, 8, 7)
+    bins = head.discretize_actions(a)
+    cont = head.discrete_tokens_to_continuous(bins.reshape(bins.shape[0], -1))
+    assert np.array_equal(vla_oracle.oft_discretize(a.numpy()), bins.numpy())
+    assert np.array_equal(vla_oracle.oft_bins_to_continuous(bins.numpy()), cont.numpy())
+    logits = torch.randn(2, 56, 512, generator=g)
+    logits[0, 3, -255:] = 0.25
+    idx = torch.argmax(logits[:, :, -255:], dim=-1)     # oft_discrete_arch.py:222-224
+    assert np.array_equal(vla_oracle.oft_argmax_decode(logits.numpy()), idx.numpy())
+    t = ActionNormAnd2String.__new__(ActionNormAnd2String)
+    a64 = (torch.rand(512, 7, generator=g, dtype=torch.float64) * 2.2 - 1.1).numpy()
+    data_bins = t._action2bin(a64, 255)
+    assert np.array_equal(vla_oracle.data_action_to_bin(a64, 255), data_bins)
+    torch.save(dict(actions=a, bins=bins, continuous=cont, logits=logits, argmax=idx,
+                    data_actions=torch.from_numpy(a64), data_bins=torch.from_numpy(data_bins)),
+               GOLDEN / "oft_integer_kats.pt")
+    print("[oft] integer KATs ok")
+    # cosine schedule constants observed in the reference (SURVEY.md §8c golden (i))
+    from dexbotic.model.cogact.action_model.diffusion import create_diffusion
+    d = create_diffusion(timestep_respacing="", noise_schedule="squaredcos_cap_v2", diffusion_steps=100,
+                         sigma_small=True, learn_sigma=False)
+    sa, sb = vla_oracle.cosine_schedule(100)
+    assert np.array_equal(sa, d.sqrt_alphas_cumprod) and np.array_equal(sb, d.sqrt_one_minus_alphas_cumprod)
+    torch.save(dict(sqrt_alphas_cumprod=torch.from_numpy(d.sqrt_alphas_cumprod),
+                    sqrt_one_minus_alphas_cumprod=torch.from_numpy(d.sqrt_one_minus_alphas_cumprod)),
+               GOLDEN / "cosine_schedule_T100.pt")
+    print("[diffusion] schedule ok", d.sqrt_alphas_cumprod[[0, 50, 99]])
+
+
+if __name__ == "__main__":
+    make_cogact_tiny()
+    make_splice_cases()
+    make_integer_kats()

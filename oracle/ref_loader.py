@@ -1,0 +1,183 @@
+"""TEST INFRASTRUCTURE — not part of the product path.
+
+Loads the UNMODIFIED reference (dexmal/dexbotic, read-only at /root/reference) in this container so
+that the oracle restatement (oracle/vla_oracle.py) can be validated against it and golden vectors can be
+generated (oracle/make_golden.py).  /root/reference does not exist on the GPU box; nothing under
+tests/ -m gpu, smoke() or bench.py imports this module.
+
+Compatibility recipe, all in memory, /root/reference untouched:
+  1. import transformers first (it probes find_spec('timm'));
+  2. inject stub modules for the un-vendored, un-pinned third-party deps the reference imports:
+     timm.models.vision_transformer.{Attention, Mlp} (restated from timm's published definition: fused
+     qkv Linear, SDPA, proj; fc1/act/fc2) and diffusers' DDIMScheduler (import-only);
+  3. exec dexbotic_arch.py / pi0_arch.py with the un-defaulted dataclass fields given `= None` (transformers
+     >= 5 turns PretrainedConfig subclasses into dataclasses);
+  4. vision towers are built from config objects instead of from_pretrained (no network / weights).
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.machinery
+import sys
+import types
+from pathlib import Path
+
+REFERENCE_ROOT = Path("/root/reference")
+
+
+def reference_available() -> bool:
+    return (REFERENCE_ROOT / "dexbotic" / "model" / "dexbotic_arch.py").exists()
+
+
+def _stub_module(name: str) -> types.ModuleType:
+    m = types.ModuleType(name)
+    m.__spec__ = importlib.machinery.ModuleSpec(name, loader=None)
+    m.__path__ = []  # behaves like a package
+    sys.modules[name] = m
+    return m
+
+
+def _install_timm_stub():
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    if "timm" in sys.modules:
+        return
+
+    class Attention(nn.Module):
+        """timm.models.vision_transformer.Attention (fused_attn path), restated."""
+
+        def __init__(self, dim, num_heads=8, qkv_bias=False, qk_norm=False, attn_drop=0.0, proj_drop=0.0,
+                     norm_layer=nn.LayerNorm, **_):
+            super().__init__()
+            assert dim % num_heads == 0 and not qk_norm
+            self.num_heads = num_heads
+            self.head_dim = dim // num_heads
+            self.scale = self.head_dim ** -0.5
+            self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+            self.proj = nn.Linear(dim, dim)
+
+        def forward(self, x, attn_mask=None):
+            B, N, C = x.shape
+            qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4)
+            q, k, v = qkv.unbind(0)
+            x = F.scaled_dot_product_attention(q, k, v, attn_mask=attn_mask)
+            x = x.transpose(1, 2).reshape(B, N, C)
+            return self.proj(x)
+
+    class Mlp(nn.Module):
+        """timm.layers.Mlp, restated (drop=0)."""
+
+        def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, norm_layer=None,
+                     bias=True, drop=0.0, **_):
+            super().__init__()
+            out_features = out_features or in_features
+            hidden_features = hidden_features or in_features
+            self.fc1 = nn.Linear(in_features, hidden_features, bias=bias)
+            self.act = act_layer()
+            self.fc2 = nn.Linear(hidden_features, out_features, bias=bias)
+
+        def forward(self, x):
+            return self.fc2(self.act(self.fc1(x)))
+
+    _stub_module("timm")
+    _stub_module("timm.models")
+    vt = _stub_module("timm.models.vision_transformer")
+    vt.Attention, vt.Mlp = Attention, Mlp
+    layers = _stub_module("timm.layers")
+    layers.Mlp = Mlp
+
+
+def _install_diffusers_stub():
+    if "diffusers" in sys.modules:
+        return
+
+    class DDIMScheduler:  # import-only: the OFT *discrete* path never instantiates it
+        def __init__(self, *a, **k):
+            raise NotImplementedError("diffusers is not available in this container")
+
+    _stub_module("diffusers")
+    _stub_module("diffusers.schedulers")
+    m = _stub_module("diffusers.schedulers.scheduling_ddim")
+    m.DDIMScheduler = DDIMScheduler
+    sys.modules["diffusers"].DDIMScheduler = DDIMScheduler
+
+
+def _exec_patched(modname: str, relpath: str, replacements: list[tuple[str, str]]):
+    src = (REFERENCE_ROOT / relpath).read_text()
+    for old, new in replacements:
+        assert old in src, f"compat patch target not found in {relpath}: {old!r}"
+        src = src.replace(old, new)
+    mod = types.ModuleType(modname)
+    mod.__file__ = str(REFERENCE_ROOT / relpath)
+    mod.__spec__ = importlib.machinery.ModuleSpec(modname, loader=None)
+    sys.modules[modname] = mod
+    exec(compile(src, mod.__file__, "exec"), mod.__dict__)
+    parent, _, child = modname.rpartition(".")
+    setattr(importlib.import_module(parent), child, mod)
+    return mod
+
+
+_loaded = False
+
+
+def load_reference():
+    """Make `import dexbotic.model...` work here; returns the patched dexbotic_arch module."""
+    global _loaded
+    if not reference_available():
+        raise RuntimeError("/root/reference is not present (expected on the GPU box): the oracle restatement "
+                           "and the committed golden vectors are the checker there")
+    import transformers  # noqa: F401  (must come first)
+    if _loaded:
+        return sys.modules["dexbotic.model.dexbotic_arch"]
+    _install_timm_stub()
+    _install_diffusers_stub()
+    if str(REFERENCE_ROOT) not in sys.path:
+        sys.path.insert(0, str(REFERENCE_ROOT))
+    import dexbotic.model  # noqa: F401  (namespace/package import only)
+    arch = _exec_patched("dexbotic.model.dexbotic_arch", "dexbotic/model/dexbotic_arch.py",
+                         [("    llm_config: str | PretrainedConfig\n", "    llm_config: str | PretrainedConfig = None\n")])
+    _patch_vision_towers()
+    _loaded = True
+    return arch
+
+
+def _patch_vision_towers():
+    """Build HF vision models from config objects (random init) instead of from_pretrained."""
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    from dexbotic.model.modules.mm_vision.clip import clip_encoder
+
+    def clip_load_model(self):
+        if self.is_loaded:
+            return
+        cfg = self.vision_tower_name
+        assert isinstance(cfg, CLIPVisionConfig), "oracle builds CLIP towers from a CLIPVisionConfig"
+        self.image_processor = None
+        self.vision_tower = CLIPVisionModel(cfg)
+        self.vision_tower.requires_grad_(False)
+        self.is_loaded = True
+
+    clip_encoder.CLIPVisionTower.load_model = clip_load_model
+
+    from dexbotic.model.modules.mm_vision import builder as vbuilder
+
+    orig_build = vbuilder.build_vision_tower
+
+    def build_vision_tower(mm_vision_tower, **kwargs):
+        if isinstance(mm_vision_tower, CLIPVisionConfig):
+            return clip_encoder.CLIPVisionTower(mm_vision_tower)
+        return orig_build(mm_vision_tower, **kwargs)
+
+    vbuilder.build_vision_tower = build_vision_tower
+    sys.modules["dexbotic.model.dexbotic_arch"].build_vision_tower = build_vision_tower
+
+
+def build_reference_cogact(llm_config, clip_config, action_model_type: str = "DiT-S", action_dim: int = 7,
+                           chunk_size: int = 16, mm_projector_type: str = "mlp2x_gelu"):
+    """Reference CogACTForCausalLM (cogact_arch.py:47-54) with random-init weights."""
+    load_reference()
+    from dexbotic.model.cogact.cogact_arch import CogActConfig, CogACTForCausalLM
+    cfg = CogActConfig(llm_config=llm_config, mm_projector_type=mm_projector_type, mm_vision_tower=clip_config,
+                       action_model_type=action_model_type, action_dim=action_dim, chunk_size=chunk_size)
+    return CogACTForCausalLM(cfg)

@@ -1,0 +1,338 @@
+"""TEST INFRASTRUCTURE — CPU restatement (plain fp32 PyTorch / numpy) of the reference's VLA hot path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module, and only as the checker (or as the timed CPU baseline) — never on the product path.
+
+Parity pin: validated in this container against the UNMODIFIED reference (oracle/ref_loader.py) by
+oracle/make_golden.py, which also writes the committed fixtures under tests/golden/.  The third-party
+arithmetic the reference calls into (HF transformers Qwen2/Llama/CLIP, timm Attention/Mlp — un-vendored;
+pins transformers==4.51.0/4.54.0 in /root/reference/Dockerfile:37, dockerfiles/Dockerfile.c130t28:22; timm
+un-pinned) is restated from its published algorithm and checked against transformers 5.5.0 (the version in
+this image) + the timm restatement in ref_loader — "parity unpinned" at the timm boundary.
+
+Every function works on a flat state_dict with the reference's parameter names
+(model.llm.*, model.mm_vision_tower.*, model.mm_projector.*, model.action_head.*).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+IGNORE_INDEX = -100        # dexbotic/constants.py
+IMAGE_TOKEN_INDEX = -200   # dexbotic/constants.py
+
+
+# ----------------------------------------------------------------------------------------------
+# diffusion schedule — cogact/action_model/diffusion.py:205-209 (squaredcos_cap_v2), :214-231
+# (betas_for_alpha_bar), GaussianDiffusion.__init__ (alphas_cumprod in float64)
+# ----------------------------------------------------------------------------------------------
+def cosine_schedule(num_steps: int = 100, max_beta: float = 0.999):
+    def alpha_bar(t):
+        return math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2
+
+    betas = []
+    for i in range(num_steps):
+        t1, t2 = i / num_steps, (i + 1) / num_steps
+        betas.append(min(1 - alpha_bar(t2) / alpha_bar(t1), max_beta))
+    betas = np.array(betas, dtype=np.float64)
+    alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
+    return np.sqrt(alphas_cumprod), np.sqrt(1.0 - alphas_cumprod)
+
+
+def q_sample(x_start, t, noise, sqrt_ac, sqrt_1mac):
+    """diffusion.py:308-326; _extract_into_tensor (:975-987) casts the float64 table entry to float32."""
+    a = torch.from_numpy(sqrt_ac)[t].float()[:, None, None]
+    b = torch.from_numpy(sqrt_1mac)[t].float()[:, None, None]
+    return a * x_start + b * noise
+
+
+# ----------------------------------------------------------------------------------------------
+# CLIP vision tower — modules/mm_vision/clip/clip_encoder.py:31-57 calling HF CLIPVisionModel
+# ----------------------------------------------------------------------------------------------
+def quick_gelu(x):
+    return x * torch.sigmoid(1.702 * x)
+
+
+ACT = {
+    "quick_gelu": quick_gelu,
+    "gelu": F.gelu,
+    "gelu_pytorch_tanh": lambda x: F.gelu(x, approximate="tanh"),
+    "gelu_tanh": lambda x: F.gelu(x, approximate="tanh"),
+    "silu": F.silu,
+}
+
+
+def _mha(x, wq, bq, wk, bk, wv, bv, wo, bo, heads, mask=None):
+    B, S, D = x.shape
+    hd = D // heads
+    q = F.linear(x, wq, bq).view(B, S, heads, hd).transpose(1, 2)
+    k = F.linear(x, wk, bk).view(B, S, heads, hd).transpose(1, 2)
+    v = F.linear(x, wv, bv).view(B, S, heads, hd).transpose(1, 2)
+    s = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    if mask is not None:
+        s = s.masked_fill(~mask, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    o = (p @ v).transpose(1, 2).reshape(B, S, D)
+    return F.linear(o, wo, bo)
+
+
+def clip_vision_features(sd, prefix: str, images: torch.Tensor, cfg: dict) -> torch.Tensor:
+    """hidden_states[-2][:, 1:] of HF CLIPVisionModel (feature_select, clip_encoder.py:31-36)."""
+    p = prefix + "vision_tower.vision_model."
+    patch, heads, eps = cfg["patch_size"], cfg["num_attention_heads"], cfg.get("layer_norm_eps", 1e-5)
+    act = ACT[cfg.get("hidden_act", "quick_gelu")]
+    x = F.conv2d(images, sd[p + "embeddings.patch_embedding.weight"], stride=patch)     # [B, D, h, w]
+    x = x.flatten(2).transpose(1, 2)
+    cls = sd[p + "embeddings.class_embedding"].expand(x.shape[0], 1, -1)
+    x = torch.cat([cls, x], dim=1) + sd[p + "embeddings.position_embedding.weight"][None]
+    D = x.shape[-1]
+    x = F.layer_norm(x, (D,), sd[p + "pre_layrnorm.weight"], sd[p + "pre_layrnorm.bias"], eps)
+    n_layers = cfg["num_hidden_layers"]
+    for i in range(n_layers - 1):       # select_layer = -2: the last encoder layer's output is never used
+        q = f"{p}encoder.layers.{i}."
+        h = F.layer_norm(x, (D,), sd[q + "layer_norm1.weight"], sd[q + "layer_norm1.bias"], eps)
+        x = x + _mha(h, sd[q + "self_attn.q_proj.weight"], sd[q + "self_attn.q_proj.bias"],
+                     sd[q + "self_attn.k_proj.weight"], sd[q + "self_attn.k_proj.bias"],
+                     sd[q + "self_attn.v_proj.weight"], sd[q + "self_attn.v_proj.bias"],
+                     sd[q + "self_attn.out_proj.weight"], sd[q + "self_attn.out_proj.bias"], heads)
+        h = F.layer_norm(x, (D,), sd[q + "layer_norm2.weight"], sd[q + "layer_norm2.bias"], eps)
+        x = x + F.linear(act(F.linear(h, sd[q + "mlp.fc1.weight"], sd[q + "mlp.fc1.bias"])),
+                         sd[q + "mlp.fc2.weight"], sd[q + "mlp.fc2.bias"])
+    return x[:, 1:]
+
+
+def mlp_projector(sd, prefix: str, x: torch.Tensor, depth: int = 2) -> torch.Tensor:
+    """mlpNx_gelu: Linear -> (GELU(erf) -> Linear)*(N-1)   (mm_projector/builder.py:69-79)."""
+    x = F.linear(x, sd[prefix + "0.weight"], sd[prefix + "0.bias"])
+    for i in range(1, depth):
+        x = F.linear(F.gelu(x), sd[f"{prefix}{2 * i}.weight"], sd[f"{prefix}{2 * i}.bias"])
+    return x
+
+
+# ----------------------------------------------------------------------------------------------
+# image-token splice — dexbotic_arch.py:182-373
+# ----------------------------------------------------------------------------------------------
+def splice(embed_weight, image_features, input_ids, attention_mask, labels, max_len: Optional[int],
+           padding_side: str = "right"):
+    """Returns inputs_embeds [B,S,D], labels [B,S], attention_mask [B,S] (bool), position_ids [B,S]."""
+    B = input_ids.shape[0]
+    if attention_mask is None:
+        attention_mask = torch.ones_like(input_ids, dtype=torch.bool)
+    attention_mask = attention_mask.bool()
+    if labels is None:
+        labels = torch.full_like(input_ids, IGNORE_INDEX)
+    new_embeds, new_labels = [], []
+    img_idx = 0
+    for b in range(B):
+        ids = input_ids[b][attention_mask[b]]
+        lab = labels[b][attention_mask[b]]
+        pos = (ids == IMAGE_TOKEN_INDEX).nonzero().flatten().tolist()
+        if len(pos) == 0:                                            # :264-272
+            new_embeds.append(embed_weight[ids])
+            new_labels.append(lab)
+            img_idx += 1
+            continue
+        bounds = [-1] + pos + [ids.shape[0]]
+        e, l = [], []
+        for i in range(len(bounds) - 1):
+            seg = slice(bounds[i] + 1, bounds[i + 1])
+            e.append(embed_weight[ids[seg]])
+            l.append(lab[seg])
+            if i < len(pos):
+                feat = image_features[img_idx]
+                e.append(feat)
+                l.append(torch.full((feat.shape[0],), IGNORE_INDEX, dtype=lab.dtype))
+                img_idx += 1
+        new_embeds.append(torch.cat(e))
+        new_labels.append(torch.cat(l))
+    if max_len is not None:                                          # :236-243
+        new_embeds = [x[:max_len] for x in new_embeds]
+        new_labels = [x[:max_len] for x in new_labels]
+    S = max(x.shape[0] for x in new_embeds)
+    D = new_embeds[0].shape[1]
+    emb = torch.zeros(B, S, D, dtype=new_embeds[0].dtype)
+    lab = torch.full((B, S), IGNORE_INDEX, dtype=labels.dtype)
+    msk = torch.zeros(B, S, dtype=torch.bool)
+    pid = torch.zeros(B, S, dtype=torch.long)
+    for b in range(B):                                               # :315-373
+        n = new_embeds[b].shape[0]
+        if n == 0:
+            continue
+        sl = slice(S - n, S) if padding_side == "left" else slice(0, n)
+        emb[b, sl] = new_embeds[b]
+        lab[b, sl] = new_labels[b]
+        msk[b, sl] = True
+        pid[b, sl] = torch.arange(n)
+    return emb, lab, msk, pid
+
+
+# ----------------------------------------------------------------------------------------------
+# decoder — HF Qwen2Model / LlamaModel as built by AutoModel at dexbotic_arch.py:55-62
+# ----------------------------------------------------------------------------------------------
+def rms_norm(x, w, eps, unit_offset=False):
+    n = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)
+    return n * (1 + w) if unit_offset else w * n
+
+
+def rope_tables(positions: torch.Tensor, head_dim: int, theta: float):
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    f = positions.float()[..., None] * inv
+    emb = torch.cat([f, f], dim=-1)
+    return emb.cos(), emb.sin()
+
+
+def rotate_half(x):
+    h = x.shape[-1] // 2
+    return torch.cat([-x[..., h:], x[..., :h]], dim=-1)
+
+
+def decoder_layer(sd, q: str, x, cos, sin, allow, cfg: dict):
+    B, S, D = x.shape
+    H, KVH = cfg["num_attention_heads"], cfg["num_key_value_heads"]
+    hd = cfg.get("head_dim") or D // H
+    eps = cfg["rms_norm_eps"]
+    h = rms_norm(x, sd[q + "input_layernorm.weight"], eps)
+    qh = F.linear(h, sd[q + "self_attn.q_proj.weight"], sd.get(q + "self_attn.q_proj.bias")).view(B, S, H, hd)
+    kh = F.linear(h, sd[q + "self_attn.k_proj.weight"], sd.get(q + "self_attn.k_proj.bias")).view(B, S, KVH, hd)
+    vh = F.linear(h, sd[q + "self_attn.v_proj.weight"], sd.get(q + "self_attn.v_proj.bias")).view(B, S, KVH, hd)
+    qh, kh, vh = qh.transpose(1, 2), kh.transpose(1, 2), vh.transpose(1, 2)
+    c, s = cos[:, None], sin[:, None]
+    qh = qh * c + rotate_half(qh) * s
+    kh = kh * c + rotate_half(kh) * s
+    G = H // KVH
+    kh = kh.repeat_interleave(G, dim=1)
+    vh = vh.repeat_interleave(G, dim=1)
+    sc = (qh @ kh.transpose(-1, -2)) * hd ** -0.5
+    sc = sc.masked_fill(~allow, float("-inf"))
+    p = torch.nan_to_num(torch.softmax(sc, dim=-1), nan=0.0)
+    o = (p @ vh).transpose(1, 2).reshape(B, S, H * hd)
+    x = x + F.linear(o, sd[q + "self_attn.o_proj.weight"], sd.get(q + "self_attn.o_proj.bias"))
+    h = rms_norm(x, sd[q + "post_attention_layernorm.weight"], eps)
+    act = ACT[cfg.get("hidden_act", "silu")]
+    m = F.linear(act(F.linear(h, sd[q + "mlp.gate_proj.weight"])) * F.linear(h, sd[q + "mlp.up_proj.weight"]),
+                 sd[q + "mlp.down_proj.weight"])
+    return x + m
+
+
+def decoder_forward(sd, prefix: str, inputs_embeds, attention_mask, position_ids, cfg: dict, collect=None):
+    """Causal decoder with key-padding mask; returns the final-norm hidden states [B,S,D]."""
+    B, S, D = inputs_embeds.shape
+    hd = cfg.get("head_dim") or D // cfg["num_attention_heads"]
+    cos, sin = rope_tables(position_ids, hd, cfg.get("rope_theta", 10000.0))
+    causal = torch.tril(torch.ones(S, S, dtype=torch.bool))
+    allow = causal[None, None] & attention_mask.bool()[:, None, None, :]
+    x = inputs_embeds
+    for i in range(cfg["num_hidden_layers"]):
+        x = decoder_layer(sd, f"{prefix}layers.{i}.", x, cos, sin, allow, cfg)
+        if collect is not None:
+            collect.append(x)
+    return rms_norm(x, sd[prefix + "norm.weight"], cfg["rms_norm_eps"])
+
+
+def cognition_features(last_hidden, attention_mask):
+    """cogact_arch.py:110-120: hidden state at the first position where cumsum(mask) reaches its max."""
+    cs = attention_mask.long().cumsum(dim=1)
+    idx = (cs == cs.max(dim=1, keepdim=True)[0]).float().argmax(dim=1)
+    return last_hidden[torch.arange(last_hidden.shape[0]), idx][:, None, :], idx
+
+
+# ----------------------------------------------------------------------------------------------
+# DiT action head — cogact/action_model/dit.py, action_models.py:102-125
+# ----------------------------------------------------------------------------------------------
+def timestep_embedding(t, dim=256, max_period=10000):
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    args = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+def dit_forward(sd, prefix: str, x, t, z, drop_mask, num_heads: int):
+    """dit.py:273-292.  drop_mask[b]=True replaces z[b] by the learned `uncondition` (token_drop, :80-95)."""
+    p = prefix + "net."
+    x = F.linear(x, sd[p + "x_embedder.linear.weight"], sd[p + "x_embedder.linear.bias"])
+    te = timestep_embedding(t)
+    te = F.linear(F.silu(F.linear(te, sd[p + "t_embedder.mlp.0.weight"], sd[p + "t_embedder.mlp.0.bias"])),
+                  sd[p + "t_embedder.mlp.2.weight"], sd[p + "t_embedder.mlp.2.bias"])
+    if drop_mask is not None:
+        z = torch.where(drop_mask[:, None, None], sd[p + "z_embedder.uncondition"][None], z)
+    ze = F.linear(z, sd[p + "z_embedder.linear.weight"], sd[p + "z_embedder.linear.bias"])
+    c = te[:, None] + ze
+    x = torch.cat([c, x], dim=1) + sd[p + "positional_embedding"]
+    D = x.shape[-1]
+    i = 0
+    while f"{p}blocks.{i}.attn.qkv.weight" in sd:
+        q = f"{p}blocks.{i}."
+        h = F.layer_norm(x, (D,), None, None, 1e-6)
+        wqkv, bqkv = sd[q + "attn.qkv.weight"], sd[q + "attn.qkv.bias"]
+        x = x + _mha(h, wqkv[:D], bqkv[:D], wqkv[D:2 * D], bqkv[D:2 * D], wqkv[2 * D:], bqkv[2 * D:],
+                     sd[q + "attn.proj.weight"], sd[q + "attn.proj.bias"], num_heads)
+        h = F.layer_norm(x, (D,), None, None, 1e-6)
+        x = x + F.linear(F.gelu(F.linear(h, sd[q + "mlp.fc1.weight"], sd[q + "mlp.fc1.bias"]), approximate="tanh"),
+                         sd[q + "mlp.fc2.weight"], sd[q + "mlp.fc2.bias"])
+        i += 1
+    x = F.layer_norm(x, (D,), None, None, 1e-6)
+    x = F.linear(x, sd[p + "final_layer.linear.weight"], sd[p + "final_layer.linear.bias"])
+    return x[:, 1:]
+
+
+DIT_HEADS = {384: 4, 768: 12, 1024: 16}   # action_models.py:48-58 (DiT-S/B/L)
+
+
+# ----------------------------------------------------------------------------------------------
+# CogACT training forward — cogact_arch.py:56-147
+# ----------------------------------------------------------------------------------------------
+def cogact_forward(sd, cfg: dict, input_ids, attention_mask, images, actions, noise, timesteps, drop_mask,
+                   repeated_diffusion_steps: int = 4, labels=None):
+    """Returns dict(loss, last_hidden, cognition, inputs_embeds, attention_mask, image_features).
+
+    noise [R*B,T,A], timesteps [R*B], drop_mask [R*B] are injected (the reference draws them with
+    torch.randn_like / randint / rand: action_models.py:106-109, dit.py:86-88)."""
+    feats = clip_vision_features(sd, "model.mm_vision_tower.", images, cfg["vision"])
+    feats = mlp_projector(sd, "model.mm_projector.", feats, cfg.get("projector_depth", 2))
+    emb, lab, msk, pid = splice(sd["model.llm.embed_tokens.weight"], feats, input_ids, attention_mask, labels,
+                                cfg.get("tokenizer_model_max_length"), cfg.get("tokenizer_padding_side", "right"))
+    hs = decoder_forward(sd, "model.llm.", emb, msk, pid, cfg["llm"])
+    cog, idx = cognition_features(hs, msk)
+    A, T = cfg["action_dim"], cfg["chunk_size"]
+    a = actions.reshape(actions.shape[0], -1, A)[:, :T].float()
+    a_rep = a.repeat(repeated_diffusion_steps, 1, 1)
+    z_rep = cog.repeat(repeated_diffusion_steps, 1, 1)
+    sa, sb = cosine_schedule(cfg.get("diffusion_steps", 100))
+    x_t = q_sample(a_rep, timesteps, noise, sa, sb)
+    width = sd["model.action_head.net.x_embedder.linear.weight"].shape[0]
+    pred = dit_forward(sd, "model.action_head.", x_t, timesteps, z_rep, drop_mask, DIT_HEADS[width])
+    loss = ((pred - noise) ** 2).mean()
+    return dict(loss=loss, last_hidden=hs, cognition=cog, cognition_index=idx, inputs_embeds=emb,
+                attention_mask=msk, position_ids=pid, labels=lab, image_features=feats, noise_pred=pred)
+
+
+# ----------------------------------------------------------------------------------------------
+# OFT discrete action tokenizer (integer path) — oft/action_model/model.py:303-347,
+# oft_discrete_arch.py:207-235, data/dataset/transform/action.py:378-390
+# ----------------------------------------------------------------------------------------------
+def oft_discretize(actions: np.ndarray, num_bins: int = 256) -> np.ndarray:
+    """model.py:303-312: ((clamp(a,-1,1)+1)/2*(num_bins-1)).round().long(); float32, round-half-even."""
+    a = np.clip(actions.astype(np.float32), np.float32(-1), np.float32(1))
+    y = (a + np.float32(1)) / np.float32(2) * np.float32(num_bins - 1)
+    return np.rint(y).astype(np.int64)
+
+
+def oft_bins_to_continuous(bins: np.ndarray, num_bins: int = 256) -> np.ndarray:
+    """model.py:314-347: (ids.float() / (num_bins-1)) * 2 - 1."""
+    return (bins.astype(np.float32) / np.float32(num_bins - 1)) * np.float32(2) - np.float32(1)
+
+
+def oft_argmax_decode(logits: np.ndarray, n_last: int = 255) -> np.ndarray:
+    """oft_discrete_arch.py:222-224: argmax over the last 255 vocabulary entries, first maximum wins."""
+    return np.argmax(logits[..., -n_last:], axis=-1).astype(np.int64)
+
+
+def data_action_to_bin(action: np.ndarray, vocab_size: int = 255) -> np.ndarray:
+    """data/dataset/transform/action.py:386-390 (_action2bin): np.round((a+1)/2*(V-1)) clipped to [0,V-1].
+    NOTE the 254-vs-255 scale mismatch with the model side is the reference's; reproduced, not fixed."""
+    a = np.round((action + 1) / 2 * (vocab_size - 1))
+    return np.clip(a, 0, vocab_size - 1)

@@ -1,0 +1,69 @@
+"""CPU tests: the oracle restatement (oracle/vla_oracle.py) against the committed golden vectors that
+oracle/make_golden.py produced from the UNMODIFIED reference (tests/golden/*.pt)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vla_oracle
+from oracle.weights import seeded_state_dict
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def cogact_tiny():
+    return torch.load(GOLDEN / "cogact_tiny.pt", weights_only=False)
+
+
+def test_cogact_tiny_forward_matches_reference(cogact_tiny):
+    fx = cogact_tiny
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    i = fx["inputs"]
+    out = vla_oracle.cogact_forward(sd, fx["cfg"], i["input_ids"], i["attention_mask"], i["images"], i["actions"],
+                                    i["noise"], i["timesteps"], i["drop_mask"], i["repeated_diffusion_steps"])
+    assert abs(out["loss"].item() - fx["outputs"]["loss"].item()) < 1e-5
+    valid = fx["outputs"]["valid"][:, :, None]
+    assert ((out["last_hidden"] * valid) - fx["outputs"]["last_hidden"]).abs().max().item() < 1e-4
+    assert (out["cognition"] - fx["outputs"]["cognition"]).abs().max().item() < 1e-4
+
+
+def test_cogact_tiny_gradients_match_reference(cogact_tiny):
+    fx = cogact_tiny
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    sd = {k: (v.requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    i = fx["inputs"]
+    out = vla_oracle.cogact_forward(sd, fx["cfg"], i["input_ids"], i["attention_mask"], i["images"], i["actions"],
+                                    i["noise"], i["timesteps"], i["drop_mask"], i["repeated_diffusion_steps"])
+    out["loss"].backward()
+    for name, gref in fx["outputs"]["grads"].items():
+        d = (sd[name].grad - gref).abs().max().item()
+        assert d < 1e-5 + 1e-3 * gref.abs().max().item(), name
+
+
+def test_splice_cases_bit_exact():
+    for c in torch.load(GOLDEN / "splice_cases.pt", weights_only=False):
+        emb, lab, msk, pid = vla_oracle.splice(c["embed_weight"], c["image_features"], c["input_ids"],
+                                               c["attention_mask"], c["labels"], c["max_len"], c["padding_side"])
+        assert torch.equal(emb, c["inputs_embeds"]), c["name"]
+        assert torch.equal(lab, c["new_labels"]), c["name"]
+        assert torch.equal(msk, c["new_mask"]), c["name"]
+
+
+def test_oft_integer_kats_bit_exact():
+    k = torch.load(GOLDEN / "oft_integer_kats.pt", weights_only=False)
+    assert np.array_equal(vla_oracle.oft_discretize(k["actions"].numpy()), k["bins"].numpy())
+    assert np.array_equal(vla_oracle.oft_bins_to_continuous(k["bins"].numpy()), k["continuous"].numpy())
+    assert np.array_equal(vla_oracle.oft_argmax_decode(k["logits"].numpy()), k["argmax"].numpy())
+    assert np.array_equal(vla_oracle.data_action_to_bin(k["data_actions"].numpy(), 255), k["data_bins"].numpy())
+    # ties: half-way points round to even, +-1 map to the end bins
+    assert vla_oracle.oft_discretize(np.array([-1.0, 1.0, 0.0], np.float32)).tolist() == [0, 255, 128]
+
+
+def test_cosine_schedule_matches_reference():
+    k = torch.load(GOLDEN / "cosine_schedule_T100.pt", weights_only=False)
+    sa, sb = vla_oracle.cosine_schedule(100)
+    assert np.array_equal(sa, k["sqrt_alphas_cumprod"].numpy())
+    assert np.array_equal(sb, k["sqrt_one_minus_alphas_cumprod"].numpy())
+    assert abs(sa[0] - 0.999684309) < 1e-9 and abs(sa[50] - 0.691566796) < 1e-9 and abs(sa[99] - 4.92805467e-4) < 1e-12
