@@ -38,6 +38,7 @@ struct GemmKParams {
   int bk_elems;  // elements of K per k-block (64 bf16 / 32 fp32)
   int a_div, a_mul, a_seg, b_div, b_mul, b_seg;
   int a_mn, b_mn;
+  int a_5d, b_5d;  // MN-major operand described by a 5-D map (all atoms of a tile in one TMA)
   int atom_elems;  // MN elements per 128-byte swizzle atom
   int atom_bytes;  // bytes of one MN-major atom (bk_elems rows x 128 B)
   int a_kadv, b_kadv, a_lbo, b_lbo, a_sbo, b_sbo, a_lt, b_lt;
@@ -236,9 +237,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         const TileCoord tc = decode_tile(p, tile);
         const int a_zbase = (tc.zl / p.a_div) * p.a_mul;
         const int b_zbase = (tc.zl / p.b_div) * p.b_mul;
+        int seg = 0, kin = 0;  // K segment and k-block inside it (no divisions in the loop)
+        const int a_atom0 = tc.m0 / p.atom_elems, b_atom0 = tc.n0 / p.atom_elems;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          const int seg = kb / p.kbps;
-          const int k0 = (kb - seg * p.kbps) * p.bk_elems;
+          const int k0 = kin * p.bk_elems;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
@@ -247,6 +249,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           const int b_c2 = b_zbase + seg * p.b_seg;
           if (!p.a_mn) {
             tma_load_4d(sa, &p.tmA, &full_bar[stage], k0, tc.m0, a_c2, tc.zh);
+          } else if (p.a_5d) {
+            tma_load_5d(sa, &p.tmA, &full_bar[stage], 0, k0, a_atom0, a_c2, tc.zh);
           } else {
             const int atoms = kBlockM / p.atom_elems;
             for (int i = 0; i < atoms; ++i)
@@ -258,11 +262,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             tma_load_4d(sb + 128 * 128, &p.tmB2, &full_bar[stage], k0, tc.n0, b_c2, tc.zh);
           } else if (!p.b_mn) {
             tma_load_4d(sb, &p.tmB, &full_bar[stage], k0, tc.n0, b_c2, tc.zh);
+          } else if (p.b_5d) {
+            tma_load_5d(sb, &p.tmB, &full_bar[stage], 0, k0, b_atom0, b_c2, tc.zh);
           } else {
             const int atoms = kBlockN / p.atom_elems;
             for (int i = 0; i < atoms; ++i)
               tma_load_4d(sb + i * p.atom_bytes, &p.tmB, &full_bar[stage], tc.n0 + i * p.atom_elems, k0, b_c2,
                           tc.zh);
+          }
+          if (++kin == p.kbps) {
+            kin = 0;
+            ++seg;
           }
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -466,6 +476,31 @@ static int encode_4d(CUtensorMap* m, int fp32, const void* ptr, uint64_t d0, uin
   return 0;
 }
 
+// MN-major operand as a 5-D map: (atom_elems, K, MN/atom_elems, z2, z3) with box (atom, bk, n_atoms, 1, 1):
+// the box lands in smem as [atom][k-row][128 B], i.e. exactly the canonical MN-major SWIZZLE_128B tile.
+static int encode_mn_5d(CUtensorMap* m, int fp32, const void* ptr, uint64_t mn, uint64_t k, uint64_t d3, uint64_t d4,
+                        int64_t ld, int64_t s3, int64_t s4, uint32_t atom_elems, uint32_t bk, uint32_t n_atoms,
+                        const char* what, bool atom32) {
+  EncodeTiledFn fn = get_encode_fn();
+  B200_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  const uint64_t es = fp32 ? 4 : 2;
+  cuuint64_t dims[5] = {atom_elems, k, mn / atom_elems, d3, d4};
+  if (s3 <= 0) s3 = ld * (int64_t)k;
+  if (s4 <= 0) s4 = s3 * (int64_t)d3;
+  cuuint64_t strides[4] = {(cuuint64_t)ld * es, (cuuint64_t)atom_elems * es, (cuuint64_t)s3 * es, (cuuint64_t)s4 * es};
+  cuuint32_t box[5] = {atom_elems, bk, n_atoms, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  B200_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "%s: base pointer not 16-byte aligned", what);
+  for (int i = 0; i < 4; ++i)
+    B200_CHECK(strides[i] % 16 == 0, "%s: stride %d not a multiple of 16 bytes", what, i + 1);
+  CUresult r = fn(m, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(5d) failed (%d)", what, (int)r);
+  return 0;
+}
+
 template <int kBlockN>
 static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
   using Cfg = GemmCfg<kBlockN>;
@@ -567,6 +602,11 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream_) {
   if (!kp.a_mn) {
     if (encode_4d(&kp.tmA, fp32, a->a, a->k, a->m, a_z2, z_hi, a->a_ld, a->a_s2, a->a_s3, kp.bk_elems, kBlockM, "A"))
       return 1;
+  } else if (a->m % kp.atom_elems == 0) {
+    kp.a_5d = 1;
+    if (encode_mn_5d(&kp.tmA, fp32, a->a, a->m, a->k, a_z2, z_hi, a->a_ld, a->a_s2, a->a_s3, kp.atom_elems,
+                     kp.bk_elems, kBlockM / kp.atom_elems, "A(mn5)", a_atom32))
+      return 1;
   } else {
     if (encode_4d(&kp.tmA, fp32, a->a, a->m, a->k, a_z2, z_hi, a->a_ld, a->a_s2, a->a_s3, kp.atom_elems, kp.bk_elems,
                   "A(mn)", a_atom32))
@@ -578,6 +618,11 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream_) {
     if (encode_4d(&kp.tmB2, fp32, a->b2, a->k, a->n, 1, 1, a->b_ld, 0, 0, kp.bk_elems, 128, "B2(up)")) return 1;
   } else if (!kp.b_mn) {
     if (encode_4d(&kp.tmB, fp32, a->b, a->k, a->n, b_z2, z_hi, a->b_ld, a->b_s2, a->b_s3, kp.bk_elems, bn, "B"))
+      return 1;
+  } else if (a->n % kp.atom_elems == 0) {
+    kp.b_5d = 1;
+    if (encode_mn_5d(&kp.tmB, fp32, a->b, a->n, a->k, b_z2, z_hi, a->b_ld, a->b_s2, a->b_s3, kp.atom_elems,
+                     kp.bk_elems, bn / kp.atom_elems, "B(mn5)", b_atom32))
       return 1;
   } else {
     if (encode_4d(&kp.tmB, fp32, a->b, a->n, a->k, b_z2, z_hi, a->b_ld, a->b_s2, a->b_s3, kp.atom_elems, kp.bk_elems,

@@ -76,6 +76,16 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, ui
         "r"(c2), "r"(c3)
       : "memory");
 }
+// 5-D variant (MN-major operands: one instruction fetches all 128-byte atoms of a tile)
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 // 4-D tiled store, shared -> global (bulk async-group completion); clips out-of-bounds
 __device__ __forceinline__ void tma_store_4d(const void* tmap, const void* smem_src, int c0, int c1, int c2,
                                              int c3) {

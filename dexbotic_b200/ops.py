@@ -562,3 +562,47 @@ def cross_entropy_bwd(logits2d, labels, lse, n_valid, gscale=None, out=None):
                                                   n_valid.data_ptr(), _p(gscale), d.data_ptr(), rows, V,
                                                   _dt(logits2d), _stream()), "cross_entropy_bwd")
     return d
+
+
+# ------------------------------------------------------------------ ViT front end
+def im2col_patches(images, patch: int, k_pad: int, out_dtype=torch.bfloat16):
+    _cuda(images)
+    B, Cc, H, W = images.shape
+    assert images.is_contiguous()
+    P = (H // patch) * (W // patch)
+    out = torch.empty((B * P, k_pad), device=images.device, dtype=out_dtype)
+    _lib.check(_lib.load().b200_im2col_patches(images.data_ptr(), out.data_ptr(), B, Cc, H, W, patch, k_pad,
+                                               _dt(images), _dt(out), _stream()), "im2col_patches")
+    return out
+
+
+def vit_embed_fwd(patches, cls, pos, B: int, P: int):
+    _cuda(patches, cls, pos)
+    D = patches.shape[-1]
+    out = torch.empty((B, P + 1, D), device=patches.device, dtype=patches.dtype)
+    _lib.check(_lib.load().b200_vit_embed_fwd(patches.data_ptr(), cls.data_ptr(), pos.data_ptr(), out.data_ptr(), B, P,
+                                              D, _dt(patches), _stream()), "vit_embed_fwd")
+    return out
+
+
+def vit_embed_bwd(dout, d_patches, d_cls_f32, d_pos_f32, B: int, P: int):
+    _cuda(dout, d_patches, d_cls_f32, d_pos_f32)
+    D = dout.shape[-1]
+    assert dout.is_contiguous()
+    _lib.check(_lib.load().b200_vit_embed_bwd(dout.data_ptr(), _p(d_patches), _p(d_cls_f32), _p(d_pos_f32), B, P, D,
+                                              _dt(dout), _stream()), "vit_embed_bwd")
+
+
+def cast_add_(src_f32, dst, accumulate: bool):
+    _cuda(src_f32, dst)
+    assert src_f32.dtype == torch.float32 and src_f32.numel() == dst.numel()
+    _lib.check(_lib.load().b200_cast_add(src_f32.data_ptr(), dst.data_ptr(), dst.numel(), _dt(dst), int(accumulate),
+                                         _stream()), "cast_add")
+    return dst
+
+
+def copy2d_(src, dst, rows: int, cols: int, accumulate: bool = False):
+    _cuda(src, dst)
+    _lib.check(_lib.load().b200_copy2d(src.data_ptr(), dst.data_ptr(), rows, cols, src.stride(0), dst.stride(0),
+                                       _dt(src), _dt(dst), int(accumulate), _stream()), "copy2d")
+    return dst

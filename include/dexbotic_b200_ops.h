@@ -127,6 +127,21 @@ int b200_cross_entropy_fwd(const void* logits, const int64_t* labels, int64_t ro
 int b200_cross_entropy_bwd(const void* logits, const int64_t* labels, const float* lse, const int32_t* n_valid,
                            const float* gscale, void* dlogits, int64_t rows, int64_t V, int dtype, void* stream);
 
+/* ---- ViT front end (HF CLIPVisionEmbeddings, called from clip_encoder.py:50-54) ----------------------
+ * Patchify: the stride=patch Conv2d is a GEMM over im2col rows; out[B*P, Kpad] with columns
+ * c*ps*ps + i*ps + j (the conv weight's own flattening) and zero padding up to Kpad (16-byte rows). */
+int b200_im2col_patches(const void* images, void* out, int64_t B, int C, int H, int W, int patch, int Kpad,
+                        int in_dtype, int out_dtype, void* stream);
+/* out[b,0] = class_embedding + pos[0]; out[b,1+p] = patches[b,p] + pos[1+p] */
+int b200_vit_embed_fwd(const void* patches, const void* cls, const void* pos, void* out, int64_t B, int64_t P,
+                       int64_t D, int dtype, void* stream);
+int b200_vit_embed_bwd(const void* dout, void* d_patches, float* d_cls, float* d_pos, int64_t B, int64_t P, int64_t D,
+                       int dtype, void* stream);
+/* dst (+)= src (fp32 scratch -> parameter gradient) ; 2-D strided copy/accumulate with dtype conversion */
+int b200_cast_add(const float* src, void* dst, int64_t n, int dst_dtype, int accumulate, void* stream);
+int b200_copy2d(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd, int src_dtype,
+                int dst_dtype, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
