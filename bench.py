@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — VLA training samples/sec (BASELINE.json metric) for the CogACT hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun for N>1)
+  python bench.py --impl reference ...                     the reference's own CPU implementation (oracle port)
+
+One "step" = one full training step over one synthetic batch: ViT-L/14 -> mlp2x_gelu projector -> image-token
+splice -> Qwen2.5-7B-shaped decoder -> DiT action head -> loss, backward, global-norm clip, AdamW.
+Prints ONE JSON line (see the task contract).  Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "VLA training samples/sec (img+text+action-chunk)"
+
+# public model-card dimensions: Qwen2.5-7B, CLIP ViT-L/14 @224, DiT-S
+WORKLOADS = {
+    "cogact_7b": dict(
+        llm=dict(model_type="qwen2", vocab_size=152064, hidden_size=3584, intermediate_size=18944,
+                 num_hidden_layers=28, num_attention_heads=28, num_key_value_heads=4, rms_norm_eps=1e-6,
+                 rope_theta=1e6, hidden_act="silu"),
+        vision=dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                    image_size=224, patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5),
+        action_model_type="DiT-S", action_dim=7, chunk_size=16, batch=32, instr_tokens=32, template_tokens=20),
+    # small stand-in with the same structure for smoke tests / CPU-only debugging of the harness
+    "cogact_tiny": dict(
+        llm=dict(model_type="qwen2", vocab_size=1024, hidden_size=256, intermediate_size=704, num_hidden_layers=2,
+                 num_attention_heads=4, num_key_value_heads=2, rms_norm_eps=1e-6, rope_theta=1e6, hidden_act="silu"),
+        vision=dict(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=2, image_size=56,
+                    patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5),
+        action_model_type="DiT-S", action_dim=7, chunk_size=16, batch=4, instr_tokens=8, template_tokens=6),
+}
+
+
+def train_flops_per_sample(w: dict, S: int) -> float:
+    """Algorithmic FLOPs (2*MACs; training = 3x forward; recompute NOT counted) — SURVEY.md §8(d) formulae."""
+    L = w["llm"]
+    d, I, nl = L["hidden_size"], L["intermediate_size"], L["num_hidden_layers"]
+    H, KV = L["num_attention_heads"], L["num_key_value_heads"]
+    hd = d // H
+    dec = nl * (2 * S * (d * H * hd + 2 * d * KV * hd + H * hd * d + 3 * d * I) + 4 * S * S * H * hd)
+    V = w["vision"]
+    dv, mv, lv = V["hidden_size"], V["intermediate_size"], V["num_hidden_layers"] - 1
+    T = (V["image_size"] // V["patch_size"]) ** 2 + 1
+    vit = lv * (2 * T * (4 * dv * dv + 2 * dv * mv) + 4 * T * T * dv)
+    proj = 2 * (T - 1) * (dv * d + d * d)
+    depth, wd, _ = {"DiT-S": (6, 384, 4), "DiT-B": (12, 768, 12), "DiT-L": (24, 1024, 16)}[w["action_model_type"]]
+    dit = 4 * depth * (2 * 17 * 12 * wd * wd + 4 * 17 * 17 * wd)
+    return 3.0 * (dec + vit + proj + dit)
+
+
+def make_batch(w: dict, rank: int, pinned: bool):
+    """Seeded synthetic batch on the HOST: [bos, <image>, instruction, template] ids,
+    10 % of rows right-padded by 1-8 tokens, images ~N(0,1), actions ~U(-1,1)."""
+    import torch
+    g = torch.Generator().manual_seed(1234 + rank)
+    B = w["batch"]
+    L = 2 + w["instr_tokens"] + w["template_tokens"]
+    V = w["llm"]["vocab_size"]
+    ids = torch.randint(1000 if V > 40000 else 1, min(30000, V), (B, L), generator=g)
+    ids[:, 0] = 1
+    ids[:, 1] = -200
+    mask = torch.ones(B, L, dtype=torch.long)
+    for b in range(B):
+        if torch.rand((), generator=g).item() < 0.10:
+            n = int(torch.randint(1, 9, (), generator=g).item())
+            mask[b, L - n:] = 0
+    img = w["vision"]["image_size"]
+    images = torch.randn(B, 3, img, img, generator=g)
+    actions = torch.rand(B, w["chunk_size"] * w["action_dim"], generator=g) * 2 - 1
+    batch = dict(input_ids=ids, attention_mask=mask, images=images, actions=actions)
+    if pinned:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    return batch
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+class GemmTimer:
+    """CUDA events around every tcgen05 GEMM launch on the launching stream (roofline.achieved)."""
+
+    def __init__(self):
+        self.records = []
+        self.enabled = False
+
+    def install(self):
+        import torch
+        from dexbotic_b200 import _lib, ops
+        lib = _lib.load()
+        orig = lib.b200_gemm
+        timer = self
+
+        def wrapped(args_ref, stream):
+            if not timer.enabled:
+                return orig(args_ref, stream)
+            a = args_ref._obj
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = orig(args_ref, stream)
+            e.record()
+            z = max(a.z_lo, 1) * max(a.z_hi, 1)
+            fl = 2.0 * a.m * a.n * a.k * max(a.k_segs, 1) * z * (2 if a.dual_b else 1)
+            timer.records.append((s, e, fl))
+            return rc
+
+        class _Proxy:
+            def __getattr__(self, name):
+                return wrapped if name == "b200_gemm" else getattr(lib, name)
+
+        _lib._lib = _Proxy()
+
+    def summary(self):
+        t = sum(s.elapsed_time(e) for s, e, _ in self.records) * 1e-3
+        f = sum(fl for _, _, fl in self.records)
+        return t, f, len(self.records)
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def run_ours(args) -> dict:
+    import torch
+    import torch.distributed as dist
+    from dexbotic_b200 import _lib
+    from dexbotic_b200.model import CogActConfig, CogACTForCausalLM
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOADS[args.workload]
+    cfg = CogActConfig(llm_config=w["llm"], mm_vision_tower=w["vision"], mm_projector_type="mlp2x_gelu",
+                       action_model_type=w["action_model_type"], action_dim=w["action_dim"], chunk_size=w["chunk_size"])
+    model = CogACTForCausalLM(cfg, device=dev)
+    model.init_weights_(seed=1234)          # same seeded random init on every rank (no checkpoints offline)
+    model.train()
+    host = make_batch(w, rank, pinned=True)
+    B = w["batch"]
+
+    def to_dev(hb):
+        return {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+
+    def step(batch):
+        model.zero_grad()
+        out = model(**batch)
+        out.loss.backward()
+        if world > 1:       # data-parallel: gradient all-reduce only (north_star); AVG == sum / world
+            if model.store.n_a:
+                dist.all_reduce(model.store.grad_a, op=dist.ReduceOp.AVG)
+            if model.store.n_b:
+                dist.all_reduce(model.store.grad_b, op=dist.ReduceOp.AVG)
+        model.optimizer_step(base_lr=2e-5)
+        return out
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, from_host: bool, gemm_timer=None):
+        sync_all()
+        launches0 = _lib.launch_count()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if gemm_timer is not None:
+            gemm_timer.enabled = True
+        s.record()
+        last = None
+        for _ in range(n_steps):
+            batch = to_dev(host) if from_host else resident
+            out = step(batch)
+            if from_host:
+                last = out.loss.item()             # device->host read of the step's result, every step
+        e.record()
+        if gemm_timer is not None:
+            gemm_timer.enabled = False
+        sync_all()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, _lib.launch_count() - launches0, (last if from_host else out.loss.item())
+
+    resident = to_dev(host)
+    S = None
+    for _ in range(max(args.warmup, 3)):
+        out = step(resident)
+        S = out.logits.shape[1]
+    gt = GemmTimer()
+    gt.install()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches, loss_dev = timed(args.steps, from_host=False, gemm_timer=gt)
+    ms_e2e, _, loss_e2e = timed(args.steps, from_host=True)
+    clocks = sampler.stop() if rank == 0 else {}
+    gemm_s, gemm_flops, gemm_n = gt.summary()
+
+    peaks, peak_src = measured_peaks()
+    flops_sample = train_flops_per_sample(w, S)
+    value = B * world * args.steps / (ms_dev * 1e-3)
+    e2e = B * world * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    achieved_tf = gemm_flops / gemm_s / 1e12 if gemm_s > 0 else 0.0
+    res = {
+        "metric": METRIC, "value": round(value, 3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: CogACT ViT-L/14@224 + Qwen2.5-7B-shaped decoder + "
+                               f"{w['action_model_type']}, batch={B}/GPU, S={S}, random-init weights, AdamW + clip, "
+                               "full-layer activation recompute; inputs (19 MB/step) << L2 but weights+grads+moments "
+                               "(>120 GB/step) stream through HBM every step, so L2 is cold for the timed kernels",
+                   "global_batch": B * world, "seq_len": S, "parallelism": f"dp{world}",
+                   "train_tflop_per_sample": round(flops_sample / 1e12, 3)},
+        "e2e": {"value": round(e2e, 3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": round(achieved_tf, 1), "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": round(achieved_tf / peak_tf, 4) if peak_tf else None, "traffic": None,
+                     "kernel": "gemm_tcgen05_kernel", "launches_timed": gemm_n,
+                     "peak_source": f"{peak_src} (bf16_tflops_sustained)",
+                     "gemm_share_of_step": round(gemm_s / (ms_dev * 1e-3), 4),
+                     "step_mfu_algorithmic": round(value / world * flops_sample / 1e12 / peak_tf, 4) if peak_tf else None},
+        "loss": round(float(loss_dev), 5),
+    }
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        res["cpu_baseline"] = cpu_baseline(w, S, seconds_budget=20.0)
+    if world > 1:
+        dist.destroy_process_group()
+    return res if rank == 0 else {}
+
+
+def cpu_baseline(w: dict, S: int, seconds_budget: float = 20.0, steps: int = 1) -> dict:
+    """The oracle port (oracle/cpu_baseline.py) timed on this box's host cores on a bounded sample."""
+    from oracle.cpu_baseline import time_cogact_sample
+    return time_cogact_sample(w, S, seconds_budget=seconds_budget, steps=steps)
+
+
+def run_reference(args) -> dict:
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the Python reference
+    itself cannot travel to the GPU box), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return {}
+    w = WORKLOADS[args.workload]
+    S = 2 + w["instr_tokens"] + w["template_tokens"] - 1 + (w["vision"]["image_size"] // w["vision"]["patch_size"]) ** 2
+    cb = cpu_baseline(w, S, seconds_budget=30.0, steps=max(1, min(args.steps, 3)))
+    return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / cb["value"], 1) if cb["value"] else None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload} (CPU oracle port, bounded sample: {cb['sample']})"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cogact_7b", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    res = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if res:
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,324 @@
+"""autograd.Function layer over the CUDA kernels.
+
+Every Function has a hand-written backward that (a) launches the dgrad kernels for its inputs and
+(b) writes parameter gradients straight into the flat gradient buffers of the ParamStore (side effect;
+the Function returns None for parameter handles).  Tiny glue between Functions (cat / where / repeat on
+action-head tensors of a few MB) is left to torch autograd.
+
+TransformerBlockFn keeps ONLY its input: the whole block is recomputed inside backward — the same
+memory/compute trade the reference makes with gradient_checkpointing=True (dexbotic/exp/base_exp.py:245,
+trainer.py:120), without torch.utils.checkpoint's replay overhead.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import ops
+from .params import ParamStore
+
+
+# ------------------------------------------------------------------------------- handles
+@dataclass
+class Lin:
+    """nn.Linear weights as the kernels see them: w [out, in] (+ bias) and their gradient slots."""
+    w: torch.Tensor
+    b: Optional[torch.Tensor] = None
+    gw: Optional[torch.Tensor] = None
+    gb: Optional[torch.Tensor] = None
+
+    @staticmethod
+    def of(store: ParamStore, w_names, b_names=None) -> "Lin":
+        w_names = [w_names] if isinstance(w_names, str) else list(w_names)
+        b_names = None if b_names is None else ([b_names] if isinstance(b_names, str) else list(b_names))
+        w = store.fused_w(w_names)
+        gw = store.fused_g(w_names)
+        b = gb = None
+        if b_names is not None:
+            b = store.fused_w(b_names)
+            gb = store.fused_g(b_names)
+        return Lin(w, b, gw, gb)
+
+
+@dataclass
+class Norm:
+    kind: str                      # "rms" | "rms1p" (Gemma 1+w) | "ln" | "ln_noaffine"
+    eps: float
+    w: Optional[torch.Tensor] = None
+    b: Optional[torch.Tensor] = None
+    gw: Optional[torch.Tensor] = None
+    gb: Optional[torch.Tensor] = None
+
+
+@dataclass
+class BlockCfg:
+    d: int
+    heads: int
+    kv_heads: int
+    head_dim: int
+    inter: int
+    mlp: str = "glu"               # "glu": down(act(gate x) * up x);  "mlp": fc2(act(fc1 x))
+    act: str = "silu"
+    rope: bool = True
+
+
+@dataclass
+class BlockW:
+    cfg: BlockCfg
+    norm1: Norm
+    qkv: Lin
+    o: Lin
+    norm2: Norm
+    gate: Optional[Lin] = None
+    up: Optional[Lin] = None
+    down: Optional[Lin] = None
+    fc1: Optional[Lin] = None
+    fc2: Optional[Lin] = None
+
+
+@dataclass
+class AttnEnv:
+    """Per-forward attention environment shared by a stack of blocks."""
+    B: int
+    S: int
+    keymask: Optional[torch.Tensor] = None   # uint8 [B,S]
+    bid: Optional[torch.Tensor] = None       # int32 [B,S] (causal order / pi0 block ids)
+    pos: Optional[torch.Tensor] = None       # int32 [B*S] RoPE positions
+    cos: Optional[torch.Tensor] = None       # fp32 [n_pos, hd/2]
+    sin: Optional[torch.Tensor] = None
+
+
+# ------------------------------------------------------------------------- raw fwd / bwd
+def linear_fwd(x2d, lin: Lin, act=None, residual=None, want_aux=False, out=None):
+    aux = torch.empty((x2d.shape[0], lin.w.shape[0]), device=x2d.device, dtype=x2d.dtype) if want_aux else None
+    y = ops.gemm(x2d, lin.w, bias=lin.b, residual=residual, act=act or 0, aux=aux, out=out)
+    return y, aux
+
+
+def linear_wgrad(store: ParamStore, dy2d, x2d, lin: Lin):
+    """dW (+)= dy^T x ; db (+)= colsum(dy)."""
+    if lin.gw is not None:
+        first = store.first_write(lin.gw)
+        ops.gemm(dy2d, x2d, a_mn=True, b_mn=True, out=lin.gw, residual=None if first else lin.gw)
+    if lin.b is not None and lin.gb is not None:
+        if lin.gb.dtype == torch.float32 and dy2d.shape[1] % 8 == 0:
+            ops.colsum_(dy2d, lin.gb)
+        elif dy2d.shape[1] % 8 == 0:
+            sc = store.scratch_f32(lin.gb.numel())
+            ops.colsum_(dy2d, sc)
+            store.accumulate_small(sc, lin.gb)
+        else:   # tiny odd widths (DiT final layer N=7): plain torch reduction on a few KB
+            lin.gb.add_(dy2d.sum(0).to(lin.gb.dtype))
+
+
+def linear_dgrad(dy2d, lin: Lin, out=None, residual=None):
+    return ops.gemm(dy2d, lin.w, b_mn=True, out=out, residual=residual)
+
+
+def norm_fwd(x, n: Norm, out=None):
+    if n.kind in ("rms", "rms1p"):
+        y, rstd = ops.rmsnorm_fwd(x, n.w, n.eps, n.kind == "rms1p", out=out)
+        return y, (rstd,)
+    y, mean, rstd = ops.layernorm_fwd(x, n.w, n.b, n.eps, out=out)
+    return y, (mean, rstd)
+
+
+def norm_bwd(store: ParamStore, dy, x, n: Norm, stats, dx=None, accumulate_dx=False):
+    D = x.shape[-1]
+    if n.kind in ("rms", "rms1p"):
+        dw = store.scratch_f32(D) if n.gw is not None else None
+        dx = ops.rmsnorm_bwd(dy, x, n.w, stats[0], n.kind == "rms1p", dx=dx, dw=dw, accumulate_dx=accumulate_dx)
+        if dw is not None:
+            store.accumulate_small(dw, n.gw)
+        return dx
+    dw = store.scratch_f32(D) if (n.w is not None and n.gw is not None) else None
+    db = store.scratch_f32(D) if (n.b is not None and n.gb is not None) else None
+    dx = ops.layernorm_bwd(dy, x, n.w, stats[0], stats[1], dx=dx, dw=dw, db=db, accumulate_dx=accumulate_dx)
+    if dw is not None:
+        store.accumulate_small(dw, n.gw)
+    if db is not None:
+        store.accumulate_small(db, n.gb)
+    return dx
+
+
+def block_forward(x2d: torch.Tensor, bw: BlockW, env: AttnEnv, keep: bool):
+    """One pre-norm transformer block on [B*S, d].  keep=True returns every intermediate backward needs."""
+    c = bw.cfg
+    sh = ops.AttnShape(env.B, env.S, c.heads, c.kv_heads, c.head_dim, x2d.dtype)
+    h, st1 = norm_fwd(x2d, bw.norm1)
+    qkv, _ = linear_fwd(h, bw.qkv)
+    if c.rope:
+        ops.rope_(qkv, env.pos, env.cos, env.sin, c.heads + c.kv_heads, c.head_dim)
+    attn, probs = ops.attention_fwd(qkv.view(env.B, env.S, -1), sh, keymask=env.keymask, bid_q=env.bid, bid_k=env.bid)
+    attn2d = attn.view(x2d.shape[0], -1)
+    x1, _ = linear_fwd(attn2d, bw.o, residual=x2d)
+    h2, st2 = norm_fwd(x1, bw.norm2)
+    saved = None
+    if c.mlp == "glu":
+        if keep:
+            g = torch.empty((x2d.shape[0], c.inter), device=x2d.device, dtype=x2d.dtype)
+            u = torch.empty_like(g)
+            hm = ops.gemm_dual(h2, bw.gate.w, bw.up.w, c.act, aux_gate=g, aux_up=u)
+        else:
+            g = u = None
+            hm = ops.gemm_dual(h2, bw.gate.w, bw.up.w, c.act)
+        y, _ = linear_fwd(hm, bw.down, residual=x1)
+        if keep:
+            saved = dict(h=h, st1=st1, qkv=qkv, probs=probs, attn=attn2d, x1=x1, h2=h2, st2=st2, g=g, u=u, hm=hm, sh=sh)
+    else:
+        hm, pre = linear_fwd(h2, bw.fc1, act=c.act, want_aux=keep)
+        y, _ = linear_fwd(hm, bw.fc2, residual=x1)
+        if keep:
+            saved = dict(h=h, st1=st1, qkv=qkv, probs=probs, attn=attn2d, x1=x1, h2=h2, st2=st2, pre=pre, hm=hm, sh=sh)
+    return y, saved
+
+
+def block_backward(store: ParamStore, dy: torch.Tensor, x2d: torch.Tensor, bw: BlockW, env: AttnEnv, s: dict):
+    """Gradient of block_forward; dy is consumed (reused as the residual-stream gradient buffer)."""
+    c = bw.cfg
+    # ---- MLP
+    if c.mlp == "glu":
+        linear_wgrad(store, dy, s["hm"], bw.down)
+        dhm = linear_dgrad(dy, bw.down)                                  # [M, inter]
+        dg, du = ops.glu_bwd(dhm, s["g"], s["u"], c.act, dg=s["g"], du=s["u"])   # in place over g / u
+        linear_wgrad(store, dg, s["h2"], bw.gate)
+        linear_wgrad(store, du, s["h2"], bw.up)
+        dh2 = linear_dgrad(dg, bw.gate)
+        linear_dgrad(du, bw.up, out=dh2, residual=dh2)
+    else:
+        linear_wgrad(store, dy, s["hm"], bw.fc2)
+        dhm = linear_dgrad(dy, bw.fc2)
+        dpre = ops.act_bwd(dhm, s["pre"], c.act, out=dhm)
+        linear_wgrad(store, dpre, s["h2"], bw.fc1)
+        dh2 = linear_dgrad(dpre, bw.fc1)
+    dx1 = norm_bwd(store, dh2, s["x1"], bw.norm2, s["st2"], dx=dy, accumulate_dx=True)   # dy += norm2 bwd
+    # ---- attention
+    linear_wgrad(store, dx1, s["attn"], bw.o)
+    dattn = linear_dgrad(dx1, bw.o)
+    dqkv = ops.attention_bwd(dattn.view(env.B, env.S, -1), s["qkv"].view(env.B, env.S, -1), s["probs"], s["sh"])
+    dqkv2d = dqkv.view(x2d.shape[0], -1)
+    if c.rope:
+        ops.rope_(dqkv2d, env.pos, env.cos, env.sin, c.heads + c.kv_heads, c.head_dim, inverse=True)
+    linear_wgrad(store, dqkv2d, s["h"], bw.qkv)
+    dh = linear_dgrad(dqkv2d, bw.qkv)
+    return norm_bwd(store, dh, x2d, bw.norm1, s["st1"], dx=dx1, accumulate_dx=True)
+
+
+# --------------------------------------------------------------------- autograd Functions
+class TransformerBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, bw: BlockW, env: AttnEnv, store: ParamStore):
+        y, _ = block_forward(x2d, bw, env, keep=False)
+        ctx.save_for_backward(x2d)
+        ctx.bw, ctx.env, ctx.store = bw, env, store
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x2d,) = ctx.saved_tensors
+        _, saved = block_forward(x2d, ctx.bw, ctx.env, keep=True)          # recompute
+        # block_backward accumulates the residual-stream gradient in place: work on a private buffer unless
+        # the incoming gradient is a whole, contiguous tensor nobody else can be holding a view of
+        dy = dy.contiguous() if dy._base is None and dy.is_contiguous() else dy.clone(memory_format=torch.contiguous_format)
+        dx = block_backward(ctx.store, dy, x2d, ctx.bw, ctx.env, saved)
+        return dx, None, None, None
+
+
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, lin: Lin, act, store: ParamStore, need_dx: bool, anchor=None):
+        # `anchor` (a scalar that requires grad) makes autograd run this backward when x2d itself does not
+        # require grad (first layer after a data tensor): parameter gradients are a side effect.
+        y, aux = linear_fwd(x2d, lin, act=act, want_aux=act is not None and act != "none")
+        ctx.save_for_backward(x2d, aux) if aux is not None else ctx.save_for_backward(x2d)
+        ctx.lin, ctx.act, ctx.store, ctx.need_dx = lin, act, store, need_dx
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        saved = ctx.saved_tensors
+        x2d = saved[0]
+        dy = dy.contiguous()
+        if len(saved) > 1:
+            dy = ops.act_bwd(dy, saved[1], ctx.act)
+        linear_wgrad(ctx.store, dy, x2d, ctx.lin)
+        dx = linear_dgrad(dy, ctx.lin) if ctx.need_dx else None
+        return dx, None, None, None, None, None
+
+
+class NormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, n: Norm, store: ParamStore):
+        y, stats = norm_fwd(x2d, n)
+        ctx.save_for_backward(x2d, *stats)
+        ctx.n, ctx.store = n, store
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, *stats = ctx.saved_tensors
+        return norm_bwd(ctx.store, dy.contiguous(), x2d, ctx.n, tuple(stats)), None, None
+
+
+class GatherRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, idx):
+        ctx.save_for_backward(idx)
+        ctx.shape = x2d.shape
+        return ops.gather_rows(x2d, idx)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        dx = torch.zeros(ctx.shape, device=dout.device, dtype=dout.dtype)
+        ops.scatter_rows_add_(dout.contiguous(), idx, dx)
+        return dx, None
+
+
+class SpliceFn(torch.autograd.Function):
+    """inputs_embeds = splice(embed_tokens.weight, image features)  (dexbotic_arch.py:182-373)."""
+
+    @staticmethod
+    def forward(ctx, feats2d, src, table, g_table, store: ParamStore):
+        ctx.save_for_backward(src)
+        ctx.g_table, ctx.store, ctx.fshape = g_table, store, feats2d.shape
+        return ops.splice_gather(src, table, feats2d)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (src,) = ctx.saved_tensors
+        d_feats = torch.zeros(ctx.fshape, device=dout.device, dtype=dout.dtype)
+        ops.splice_scatter(src, dout.contiguous(), ctx.g_table, d_feats)
+        return d_feats, None, None, None, None
+
+
+class MSELossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        pred, target = pred.contiguous(), target.contiguous()
+        out = torch.zeros((), device=pred.device, dtype=torch.float32)
+        ops.mse_fwd(pred, target, out)
+        ctx.save_for_backward(pred, target)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target = ctx.saved_tensors
+        return ops.mse_bwd(pred, target, g.contiguous().float()), None
+
+
+class CastFn(torch.autograd.Function):
+    """dtype boundary between the bf16 trunk and the fp32 action head (cogact_arch.py:125-135)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src_dtype = x.dtype
+        out = torch.empty(x.shape, device=x.device, dtype=dtype)
+        return ops.cast_(x.contiguous(), out)
+
+    @staticmethod
+    def backward(ctx, g):
+        out = torch.empty(g.shape, device=g.device, dtype=ctx.src_dtype)
+        return ops.cast_(g.contiguous(), out), None

@@ -1,0 +1,5 @@
+"""Host-side mirror of dexbotic/model (reference: /root/reference/dexbotic/model): same class names,
+forward signatures, config fields and state-dict keys; the arithmetic runs in libdexbotic_b200.so."""
+from .dexbotic_arch import (CausalLMOutputDexbotic, DexboticConfig, DexboticVLMModel, IGNORE_INDEX,  # noqa: F401
+                            IMAGE_TOKEN_INDEX)
+from .cogact_arch import CogActConfig, CogActModel, CogACTForCausalLM  # noqa: F401

@@ -1,0 +1,139 @@
+"""Mirror of dexbotic/model/cogact/cogact_arch.py: CogActConfig / CogActModel / CogACTForCausalLM with the
+reference's forward(...) keyword signature and CausalLMOutputDexbotic return type (cogact_arch.py:56-147),
+running on the B200 kernels.  state_dict keys == the reference's (model.llm.*, model.mm_vision_tower.*,
+model.mm_projector.*, model.action_head.*, lm_head.weight).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..functional import CastFn, GatherRowsFn
+from ..params import ParamSpec
+from ._module import B200Module
+from .action_model import ActionModel, action_head_specs
+from .dexbotic_arch import (CausalLMOutputDexbotic, DexboticConfig, DexboticVLMModel, cfg_get, clip_specs, llm_specs,
+                            projector_specs)
+
+
+class CogActConfig(DexboticConfig):
+    """cogact_arch.py:13-17."""
+    model_type = "dexbotic_cogact"
+
+    def __init__(self, action_model_type: Optional[str] = None, action_dim: Optional[int] = None,
+                 chunk_size: Optional[int] = None, **kwargs):
+        super().__init__(**kwargs)
+        self.action_model_type = action_model_type
+        self.action_dim = action_dim
+        self.chunk_size = chunk_size
+        self.freeze_action_head = kwargs.get("freeze_action_head", False)
+
+
+class CogActModel(DexboticVLMModel):
+    """cogact_arch.py:20-44 (`model.model`): VLM shell + action head."""
+    action_head_prefix = "action_head"
+
+    def __init__(self, store, config: CogActConfig):
+        super().__init__(store, config)
+        self.action_head = ActionModel(store, config.action_model_type, cfg_get(config.llm_config, "hidden_size"),
+                                       config.action_dim, config.chunk_size - 1)   # action_model/builder.py:7-27
+
+    @property
+    def action_head_module(self):
+        return self.action_head
+
+
+class CogACTForCausalLM(B200Module):
+    """cogact_arch.py:47-198."""
+    config_class = CogActConfig
+
+    def __init__(self, config: CogActConfig, device="cuda"):
+        super().__init__()
+        self.config = config
+        llm = config.llm_config
+        d, V = cfg_get(llm, "hidden_size"), cfg_get(llm, "vocab_size")
+        vis = config.mm_vision_tower
+        specs = (llm_specs(llm, trainable=not config.freeze_llm)
+                 + clip_specs(vis, trainable=not config.freeze_mm_vision)
+                 + projector_specs(config.mm_projector_type, cfg_get(vis, "hidden_size"), d,
+                                   trainable=not config.freeze_mm_projector)
+                 + action_head_specs(config.action_model_type, d, config.action_dim, config.chunk_size,
+                                     trainable=not getattr(config, "freeze_action_head", False))
+                 # lm_head exists in the reference (cogact_arch.py:52) but never receives a gradient in CogACT
+                 + [ParamSpec("lm_head.weight", (V, d), "lm_head", trainable=False)])
+        store = self._materialize(specs, device)
+        # fp32 (region B) parameters take their torch .grad directly from the flat gradient buffer
+        for name in store.order:
+            s = store.slots[name]
+            if s.region == "B":
+                self.get_parameter(name).grad = store.g(name)
+        self.model_engine = CogActModel(store, config)
+
+    # `model.model` must stay the nn.Module that owns the parameters (state-dict keys); the engine with the
+    # reference's properties (backbone, mm_projector_prefix, action_head_module ...) is `model_engine`.
+    @property
+    def engine(self) -> CogActModel:
+        return self.model_engine
+
+    def _after_weights_changed(self) -> None:
+        self.model_engine.refresh()
+
+    def forward(self,
+                input_ids: torch.LongTensor = None,
+                attention_mask: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.LongTensor] = None,
+                past_key_values: Optional[List[torch.FloatTensor]] = None,
+                inputs_embeds: Optional[torch.FloatTensor] = None,
+                labels: Optional[torch.LongTensor] = None,
+                use_cache: Optional[bool] = None,
+                output_attentions: Optional[bool] = None,
+                output_hidden_states: Optional[bool] = None,
+                images: Optional[torch.FloatTensor] = None,
+                return_dict: Optional[bool] = None,
+                cache_position: Optional[torch.LongTensor] = None,
+                actions: Optional[torch.LongTensor] = None,
+                states: Optional[torch.LongTensor] = None,
+                repeated_diffusion_steps: int = 4,
+                noise: Optional[torch.Tensor] = None,          # parity hooks: inject the reference's random draws
+                timesteps: Optional[torch.Tensor] = None,
+                drop_mask: Optional[torch.Tensor] = None,
+                **kwargs) -> CausalLMOutputDexbotic:
+        if images is None or input_ids is None:
+            raise NotImplementedError("CogACT training forward needs input_ids and images (cogact_arch.py:75-91)")
+        if not input_ids.is_cuda:
+            raise RuntimeError("dexbotic_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        eng = self.model_engine
+        cfg = self.config
+        emb, new_labels, new_mask, pos, S = eng._prepare_inputs_labels_for_multimodal(
+            input_ids, attention_mask, labels, images)
+        B = input_ids.shape[0]
+        hidden2d = eng.llm.forward(emb.view(B * S, -1), B, S, new_mask, pos)           # cogact_arch.py:97-108
+        last_hidden_state = hidden2d.view(B, S, -1)
+
+        loss = None
+        if actions is not None:
+            idx = ops.last_valid_index(new_mask)                                        # :110-120
+            cognition = GatherRowsFn.apply(hidden2d, idx)                               # [B, D]
+            cog32 = CastFn.apply(cognition, torch.float32)[:, None, :]                  # autocast(float32), :133
+            a = actions.reshape(B, -1, cfg.action_dim).to(torch.float32)[:, :cfg.chunk_size, :]
+            R = repeated_diffusion_steps
+            loss = eng.action_head.loss(self, a.repeat(R, 1, 1), cog32.repeat(R, 1, 1), noise, timesteps, drop_mask,
+                                        training=self.training)
+        return CausalLMOutputDexbotic(loss=loss, logits=last_hidden_state)
+
+    # ---- training utilities that the reference delegates to HF Trainer / DeepSpeed ------------------
+    def zero_grad(self, set_to_none: bool = False):        # noqa: D401
+        self.store.zero_grad()
+
+    def optimizer_step(self, base_lr: float = 2e-5, mm_projector_lr=None, mm_vision_lr=None, action_head_lr=None,
+                       betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, max_grad_norm=1.0):
+        """Fused AdamW over the flat buffers with the reference's per-module learning rates
+        (OptimizerConfig, base_exp.py:64-203) and max_grad_norm=1.0 (trainer.py:122)."""
+        lrs = {"llm": base_lr, "projector": mm_projector_lr or base_lr, "vision": mm_vision_lr or base_lr,
+               "action_head": action_head_lr or base_lr, "lm_head": base_lr}
+        norm = self.store.adamw_step(lrs, betas, eps, weight_decay, max_grad_norm)
+        self.model_engine.refresh()
+        return norm

@@ -1,0 +1,245 @@
+"""Flat parameter / gradient / optimizer-state storage for the B200 backend.
+
+HBM layout: one fp32 master buffer (the nn.Parameters are views of it, so state_dict keys,
+shapes and dtype match the reference's fp32 checkpoints), one bf16 shadow buffer that the tensor-core
+kernels read, one bf16 gradient buffer (fp32 for the action head, which the reference computes in
+fp32/TF32 — cogact_arch.py:133), and fp32 Adam moments.  Flat buffers make the optimizer one launch per
+(lr, weight-decay) segment and the data-parallel all-reduce a handful of large NCCL calls with no copies.
+
+Reference behaviour mirrored: torch.optim.AdamW via HF Trainer.create_optimizer (dexbotic/exp/trainer.py:
+25-36), parameter groups from OptimizerConfig._get_optimizer_grouped_parameters (base_exp.py:95-203),
+max_grad_norm=1.0 (trainer.py:122).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import ops
+
+ALIGN = 64  # elements; keeps every tensor 128-byte aligned in the bf16 buffers (TMA needs 16 B)
+
+
+@dataclass
+class ParamSpec:
+    name: str
+    shape: tuple
+    group: str = "llm"            # llm | vision | projector | action_head | lm_head
+    compute: str = "bf16"         # dtype the kernels read: "bf16" (region A) or "fp32" (region B)
+    fuse: Optional[str] = None    # consecutive specs with the same tag are packed without padding
+    trainable: bool = True
+    no_decay: Optional[bool] = None   # default: 1-D tensors and biases are not decayed
+
+    @property
+    def numel(self) -> int:
+        n = 1
+        for s in self.shape:
+            n *= int(s)
+        return n
+
+
+@dataclass
+class _Slot:
+    spec: ParamSpec
+    region: str
+    offset: int       # element offset inside the region
+    g_offset: int     # element offset in the global (A then B) fp32 master / moment buffers
+
+
+class ParamStore:
+    """Regions: A = trainable, bf16 compute; B = trainable, fp32 compute; FA / FB = frozen counterparts
+    (master + shadow only: no gradient, no optimizer state — e.g. lm_head in CogACT, or a frozen tower)."""
+
+    def __init__(self, specs: list[ParamSpec], device):
+        self.device = torch.device(device)
+        self.slots: dict[str, _Slot] = {}
+        self.order: list[str] = []
+        size = {"A": 0, "B": 0, "FA": 0, "FB": 0}
+        prev_fuse = {k: None for k in size}
+        placed = []
+        for sp in specs:
+            region = ("A" if sp.compute == "bf16" else "B") if sp.trainable else ("FA" if sp.compute == "bf16" else "FB")
+            if not (sp.fuse is not None and sp.fuse == prev_fuse[region]):
+                size[region] = (size[region] + ALIGN - 1) // ALIGN * ALIGN
+            placed.append((sp, region, size[region]))
+            size[region] += sp.numel
+            prev_fuse[region] = sp.fuse
+        al = lambda n: (n + ALIGN - 1) // ALIGN * ALIGN  # noqa: E731
+        self.n_a, self.n_b, self.n_fa, self.n_fb = al(size["A"]), al(size["B"]), al(size["FA"]), al(size["FB"])
+        base = {"A": 0, "B": self.n_a, "FA": self.n_a + self.n_b, "FB": self.n_a + self.n_b + self.n_fa}
+        for sp, region, off in placed:
+            assert sp.name not in self.slots, f"duplicate parameter {sp.name}"
+            self.slots[sp.name] = _Slot(sp, region, off, base[region] + off)
+            self.order.append(sp.name)
+        dev = self.device
+        n_train = self.n_a + self.n_b
+        # one fp32 master for everything; trainable tensors first so moments / AdamW cover a prefix
+        self.master = torch.zeros(n_train + self.n_fa + self.n_fb, device=dev, dtype=torch.float32)
+        self.n_train = n_train
+        self.shadow = torch.zeros(self.n_a, device=dev, dtype=torch.bfloat16)
+        self.shadow_f = torch.zeros(self.n_fa, device=dev, dtype=torch.bfloat16)
+        self.grad_a = torch.zeros(self.n_a, device=dev, dtype=torch.bfloat16)
+        self.grad_b = torch.zeros(self.n_b, device=dev, dtype=torch.float32)
+        self.exp_avg: Optional[torch.Tensor] = None
+        self.exp_avg_sq: Optional[torch.Tensor] = None
+        self.step_count = 0
+        self._written: set[int] = set()       # grad tensors (by data_ptr) written since zero_grad
+        self._always_zero: list[tuple[int, int]] = []   # region-A ranges that need an explicit memset per step
+        self.grad_ready_hook = None            # callable(region, start, end) — data-parallel overlap
+
+    # ------------------------------------------------------------------ views
+    def _view(self, buf: torch.Tensor, off: int, shape) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        return buf[off:off + n].view(*shape)
+
+    def master_view(self, name: str) -> torch.Tensor:
+        s = self.slots[name]
+        return self._view(self.master, s.g_offset, s.spec.shape)
+
+    def w(self, name: str) -> torch.Tensor:
+        """The tensor the kernels read (bf16 shadow for region A, fp32 master for region B)."""
+        s = self.slots[name]
+        if s.region == "A":
+            return self._view(self.shadow, s.offset, s.spec.shape)
+        if s.region == "FA":
+            return self._view(self.shadow_f, s.offset, s.spec.shape)
+        return self._view(self.master, s.g_offset, s.spec.shape)
+
+    def g(self, name: str) -> Optional[torch.Tensor]:
+        s = self.slots[name]
+        if not s.spec.trainable:
+            return None
+        buf = self.grad_a if s.region == "A" else self.grad_b
+        return self._view(buf, s.offset, s.spec.shape)
+
+    def _fused(self, names: list[str], getter) -> Optional[torch.Tensor]:
+        first = self.slots[names[0]]
+        rows, off = 0, first.offset
+        tail = first.spec.shape[1:]
+        for n in names:
+            s = self.slots[n]
+            assert s.region == first.region and s.offset == off and s.spec.shape[1:] == tail, \
+                f"{names} are not packed contiguously (fuse tag missing?)"
+            off += s.spec.numel
+            rows += s.spec.shape[0]
+        if getter == "w":
+            buf = {"A": self.shadow, "FA": self.shadow_f}.get(first.region, self.master)
+            base = first.offset if first.region in ("A", "FA") else first.g_offset
+        else:
+            if not first.spec.trainable:
+                return None
+            buf = self.grad_a if first.region == "A" else self.grad_b
+            base = first.offset
+        return self._view(buf, base, (rows,) + tuple(tail))
+
+    def fused_w(self, names: list[str]) -> torch.Tensor:
+        return self._fused(names, "w")
+
+    def fused_g(self, names: list[str]) -> Optional[torch.Tensor]:
+        return self._fused(names, "g")
+
+    # ---------------------------------------------------------------- gradients
+    def first_write(self, g: torch.Tensor) -> bool:
+        """True the first time a gradient tensor is written after zero_grad (overwrite instead of accumulate).
+        Region-B (fp32) gradients are memset by zero_grad and always accumulate."""
+        if g.dtype == torch.float32:
+            return False
+        key = g.data_ptr()
+        if key in self._written:
+            return False
+        self._written.add(key)
+        return True
+
+    def mark_sparse_grad(self, name: str) -> None:
+        """Gradient rows written by scatter (embedding table): needs a real memset every step."""
+        s = self.slots[name]
+        assert s.region == "A"
+        self._always_zero.append((s.offset, s.offset + s.spec.numel))
+
+    def zero_grad(self) -> None:
+        self._written.clear()
+        self.grad_b.zero_()
+        for a, b in self._always_zero:
+            self.grad_a[a:b].zero_()
+            self._written.add(self.grad_a[a:].data_ptr())
+
+    def scratch_f32(self, n: int, tag: str = "") -> torch.Tensor:
+        """Zeroed fp32 scratch (norm-weight / bias gradient accumulators)."""
+        return torch.zeros(n, device=self.device, dtype=torch.float32)
+
+    def accumulate_small(self, scratch_f32: torch.Tensor, g: Optional[torch.Tensor]) -> None:
+        if g is None:
+            return
+        ops.cast_add_(scratch_f32, g.reshape(-1), accumulate=not self.first_write(g))
+
+    # ---------------------------------------------------------------- optimizer
+    def refresh_shadow(self) -> None:
+        """bf16 shadow <- fp32 master (after loading weights)."""
+        if self.n_a:
+            ops.cast_(self.master[: self.n_a], self.shadow)
+        if self.n_fa:
+            a = self.n_a + self.n_b
+            ops.cast_(self.master[a: a + self.n_fa], self.shadow_f)
+
+    def segments(self, lrs: dict, weight_decay: float):
+        """Contiguous (start, end, lr, wd) runs over the global master buffer, trainable tensors only."""
+        runs = []
+        for name in self.order:
+            s = self.slots[name]
+            if not s.spec.trainable:
+                continue
+            lr = lrs.get(s.spec.group, lrs["llm"])
+            nd = s.spec.no_decay if s.spec.no_decay is not None else (len(s.spec.shape) <= 1 or name.endswith("bias"))
+            wd = 0.0 if nd else weight_decay
+            a, b = s.g_offset, s.g_offset + s.spec.numel
+            b_al = (b + ALIGN - 1) // ALIGN * ALIGN
+            if runs and runs[-1][2] == lr and runs[-1][3] == wd and runs[-1][4] == s.region and runs[-1][1] >= a:
+                runs[-1][1] = b_al
+            else:
+                runs.append([a, b_al, lr, wd, s.region])
+        return runs
+
+    def grad_norm_sq(self, out: torch.Tensor) -> torch.Tensor:
+        if self.n_a:
+            ops.sumsq_(self.grad_a, out)
+        if self.n_b:
+            ops.sumsq_(self.grad_b, out)
+        return out
+
+    def adamw_step(self, lrs: dict, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                   max_grad_norm: Optional[float] = 1.0, grad_scale: float = 1.0):
+        """One fused AdamW step over every trainable segment; returns the (device) gradient norm."""
+        dev = self.device
+        if self.exp_avg is None:
+            self.exp_avg = torch.zeros(self.n_train, device=dev, dtype=torch.float32)
+            self.exp_avg_sq = torch.zeros(self.n_train, device=dev, dtype=torch.float32)
+        self.step_count += 1
+        clip = None
+        norm = torch.zeros((), device=dev, dtype=torch.float32)
+        if max_grad_norm is not None:
+            ssq = torch.zeros((), device=dev, dtype=torch.float32)
+            self.grad_norm_sq(ssq)
+            clip = torch.empty((), device=dev, dtype=torch.float32)
+            ops.clip_coef(ssq, max_grad_norm, clip, norm)
+        for a, b, lr, wd, region in self.segments(lrs, weight_decay):
+            p = self.master[a:b]
+            if region == "A":
+                g = self.grad_a[a:b]
+                sh = self.shadow[a:b]
+            else:
+                g = self.grad_b[a - self.n_a:b - self.n_a]
+                sh = None
+            ops.adamw_(p, g, self.exp_avg[a:b], self.exp_avg_sq[a:b], sh, lr, betas[0], betas[1], eps, wd,
+                       self.step_count, clip)
+        return norm
+
+    def bytes_allocated(self) -> int:
+        n = (self.master.numel() * 4 + (self.shadow.numel() + self.shadow_f.numel()) * 2 + self.grad_a.numel() * 2 +
+             self.grad_b.numel() * 4)
+        if self.exp_avg is not None:
+            n += 2 * self.exp_avg.numel() * 4
+        return n
