@@ -182,6 +182,7 @@ def run_ours(args) -> dict:
     import torch.distributed as dist
     from dexbotic_b200 import _lib
     from dexbotic_b200.model import CogActConfig, CogACTForCausalLM
+    from dexbotic_b200.parallel import allreduce_gradients
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,11 +207,8 @@ def run_ours(args) -> dict:
         model.zero_grad()
         out = model(**batch)
         out.loss.backward()
-        if world > 1:       # data-parallel: gradient all-reduce only (north_star); AVG == sum / world
-            if model.store.n_a:
-                dist.all_reduce(model.store.grad_a, op=dist.ReduceOp.AVG)
-            if model.store.n_b:
-                dist.all_reduce(model.store.grad_b, op=dist.ReduceOp.AVG)
+        if world > 1:       # data-parallel: gradient all-reduce only (north_star), in place on the flat buffers
+            allreduce_gradients(model.store)
         model.optimizer_step(base_lr=2e-5)
         return out
 
@@ -286,6 +284,7 @@ def run_ours(args) -> dict:
                      "gemm_share_of_step": round(gemm_s / (ms_dev * 1e-3), 4),
                      "step_mfu_algorithmic": round(value / world * flops_sample / 1e12 / peak_tf, 4) if peak_tf else None},
         "loss": round(float(loss_dev), 5),
+        "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         res["cpu_baseline"] = cpu_baseline(w, S, seconds_budget=20.0)

@@ -310,7 +310,7 @@ __global__ void glu_fwd_kernel(const T* __restrict__ g, const T* __restrict__ u,
 }
 // dg = dh*u*act'(g), du = dh*act(g); dg/du may alias g/u; optional h_out = act(g)*u
 template <typename T>
-__global__ void glu_bwd_kernel(const T* __restrict__ dh, const T* g, const T* u, T* dg, T* du, T* __restrict__ h_out,
+__global__ void glu_bwd_kernel(const T* dh, const T* g, const T* u, T* dg, T* du, T* h_out,
                                int64_t n8, int act) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     float a[8], b[8], d[8], og[8], ou[8], oh[8];

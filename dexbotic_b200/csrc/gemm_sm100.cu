@@ -15,6 +15,8 @@
 //
 // Reference arithmetic replaced: see include/dexbotic_b200.h (b200_gemm).
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "../../include/dexbotic_b200.h"
 #include "common.h"
@@ -57,11 +59,11 @@ struct GemmKParams {
   int act;
 };
 
-template <int kBlockN>
+template <int kBlockN, int kCtas = 1>
 struct GemmCfg {
-  static constexpr int kStageBBytes = kBlockN * 128;
+  static constexpr int kStageBBytes = kBlockN / kCtas * 128;  // a CTA pair splits the B tile
   static constexpr int kStageBytes = kStageABytes + kStageBBytes;
-  static constexpr int kStages = kBlockN == 256 ? 4 : (kBlockN == 128 ? 6 : 8);
+  static constexpr int kStages = (kBlockN == 256 && kCtas == 1) ? 4 : (kBlockN / kCtas == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * kBlockN;  // two accumulator stages
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 4 * kStagingPerWarp + kBarBytes;
@@ -170,7 +172,8 @@ __device__ __forceinline__ void store_row32_any(void* base, long long elem_off, 
 struct TileCoord {
   int zl, zh, m0, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile) {
+template <int kCtas>
+__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile, int cta_rank) {
   int z = tile / p.tiles_per_batch;
   int t = tile - z * p.tiles_per_batch;
   TileCoord c;
@@ -183,14 +186,17 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile)
   int gm = min(p.m_blocks - first_m, kGroupM);
   int nb = r / gm;
   int mb = first_m + (r - nb * gm);
-  c.m0 = mb * kBlockM;
+  c.m0 = mb * (kBlockM * kCtas) + cta_rank * kBlockM;
   c.n0 = nb * p.n_per_tile;
   return c;
 }
 
-template <int kBlockN>
+template <int kBlockN, int kCtas>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
-  using Cfg = GemmCfg<kBlockN>;
+  using Cfg = GemmCfg<kBlockN, kCtas>;
+  const int cta_rank = kCtas == 2 ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int tile0 = blockIdx.x / kCtas, tile_step = gridDim.x / kCtas;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -217,14 +223,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 4 * kCtas);  // the leader collects the epilogue warps of both CTAs
     }
     mbar_fence_init();
     fence_proxy_async_smem();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 2) {
+    if (kCtas == 2)
+      tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+    else
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2)
+    cluster_sync_all();  // peer barriers are initialised before any remote arrive / multicast commit
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -233,42 +247,59 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
+        const TileCoord tc = decode_tile<kCtas>(p, tile, cta_rank);
         const int a_zbase = (tc.zl / p.a_div) * p.a_mul;
         const int b_zbase = (tc.zl / p.b_div) * p.b_mul;
         int seg = 0, kin = 0;  // K segment and k-block inside it (no divisions in the loop)
-        const int a_atom0 = tc.m0 / p.atom_elems, b_atom0 = tc.n0 / p.atom_elems;
+        // a CTA pair splits the B tile: rank r stages columns [n0 + r*kBlockN/2, ...) (dual: rank 0 = gate, 1 = up)
+        const int bn0 = tc.n0 + ((kCtas == 2 && !p.dual) ? cta_rank * (kBlockN / 2) : 0);
+        const void* tmB = (kCtas == 2 && p.dual && cta_rank == 1) ? &p.tmB2 : &p.tmB;
+        const int a_atom0 = tc.m0 / p.atom_elems, b_atom0 = bn0 / p.atom_elems;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           const int k0 = kin * p.bk_elems;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kStageABytes;
           const int a_c2 = a_zbase + seg * p.a_seg;
           const int b_c2 = b_zbase + seg * p.b_seg;
-          if (!p.a_mn) {
-            tma_load_4d(sa, &p.tmA, &full_bar[stage], k0, tc.m0, a_c2, tc.zh);
-          } else if (p.a_5d) {
-            tma_load_5d(sa, &p.tmA, &full_bar[stage], 0, k0, a_atom0, a_c2, tc.zh);
+          if constexpr (kCtas == 2) {
+            // both CTAs' bytes complete on the leader's barrier; only the leader arms it
+            const uint32_t lbar = smem_u32(&full_bar[stage]) & kPeerBitMask;
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            if (!p.a_mn)
+              tma_load_4d_2sm(sa, &p.tmA, lbar, k0, tc.m0, a_c2, tc.zh);
+            else
+              tma_load_5d_2sm(sa, &p.tmA, lbar, 0, k0, a_atom0, a_c2, tc.zh);
+            if (!p.b_mn)
+              tma_load_4d_2sm(sb, tmB, lbar, k0, bn0, b_c2, tc.zh);
+            else
+              tma_load_5d_2sm(sb, tmB, lbar, 0, k0, b_atom0, b_c2, tc.zh);
           } else {
-            const int atoms = kBlockM / p.atom_elems;
-            for (int i = 0; i < atoms; ++i)
-              tma_load_4d(sa + i * p.atom_bytes, &p.tmA, &full_bar[stage], tc.m0 + i * p.atom_elems, k0, a_c2,
-                          tc.zh);
-          }
-          if (p.dual) {
-            tma_load_4d(sb, &p.tmB, &full_bar[stage], k0, tc.n0, b_c2, tc.zh);
-            tma_load_4d(sb + 128 * 128, &p.tmB2, &full_bar[stage], k0, tc.n0, b_c2, tc.zh);
-          } else if (!p.b_mn) {
-            tma_load_4d(sb, &p.tmB, &full_bar[stage], k0, tc.n0, b_c2, tc.zh);
-          } else if (p.b_5d) {
-            tma_load_5d(sb, &p.tmB, &full_bar[stage], 0, k0, b_atom0, b_c2, tc.zh);
-          } else {
-            const int atoms = kBlockN / p.atom_elems;
-            for (int i = 0; i < atoms; ++i)
-              tma_load_4d(sb + i * p.atom_bytes, &p.tmB, &full_bar[stage], tc.n0 + i * p.atom_elems, k0, b_c2,
-                          tc.zh);
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            if (!p.a_mn) {
+              tma_load_4d(sa, &p.tmA, &full_bar[stage], k0, tc.m0, a_c2, tc.zh);
+            } else if (p.a_5d) {
+              tma_load_5d(sa, &p.tmA, &full_bar[stage], 0, k0, a_atom0, a_c2, tc.zh);
+            } else {
+              const int atoms = kBlockM / p.atom_elems;
+              for (int i = 0; i < atoms; ++i)
+                tma_load_4d(sa + i * p.atom_bytes, &p.tmA, &full_bar[stage], tc.m0 + i * p.atom_elems, k0, a_c2,
+                            tc.zh);
+            }
+            if (p.dual) {
+              tma_load_4d(sb, &p.tmB, &full_bar[stage], k0, tc.n0, b_c2, tc.zh);
+              tma_load_4d(sb + 128 * 128, &p.tmB2, &full_bar[stage], k0, tc.n0, b_c2, tc.zh);
+            } else if (!p.b_mn) {
+              tma_load_4d(sb, &p.tmB, &full_bar[stage], k0, tc.n0, b_c2, tc.zh);
+            } else if (p.b_5d) {
+              tma_load_5d(sb, &p.tmB, &full_bar[stage], 0, k0, b_atom0, b_c2, tc.zh);
+            } else {
+              const int atoms = kBlockN / p.atom_elems;
+              for (int i = 0; i < atoms; ++i)
+                tma_load_4d(sb + i * p.atom_bytes, &p.tmB, &full_bar[stage], tc.n0 + i * p.atom_elems, k0, b_c2,
+                            tc.zh);
+            }
           }
           if (++kin == p.kbps) {
             kin = 0;
@@ -283,13 +314,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(p.ab_fp32 ? 2u : 1u, p.a_mn, p.b_mn, kBlockM, kBlockN);
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_idesc(p.ab_fp32 ? 2u : 1u, p.a_mn, p.b_mn, kBlockM * kCtas, kBlockN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kBlockN;
@@ -302,18 +333,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           for (int k = 0; k < 4; ++k) {
             const uint64_t ad = umma_smem_desc(sa + k * p.a_kadv, p.a_lbo, p.a_sbo, p.a_lt);
             const uint64_t bd = umma_smem_desc(sb + k * p.b_kadv, p.b_lbo, p.b_sbo, p.b_lt);
-            if (p.ab_fp32)
-              umma_tf32(d_tmem, ad, bd, idesc, (kb | k) != 0);
-            else
-              umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            if constexpr (kCtas == 2) {
+              if (p.ab_fp32)
+                umma_tf32_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0);
+              else
+                umma_f16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            } else {
+              if (p.ab_fp32)
+                umma_tf32(d_tmem, ad, bd, idesc, (kb | k) != 0);
+              else
+                umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            }
           }
-          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+          // smem slot is free (in both CTAs of a pair) once these MMAs retire
+          if constexpr (kCtas == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (kCtas == 2) umma_commit_2sm(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -327,8 +367,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     uint32_t acc_phase = 0;
     const int chunk_cols = p.d_fp32 ? 32 : 64;
     const int sw = lane & 7;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
+    for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
+      const TileCoord tc = decode_tile<kCtas>(p, tile, cta_rank);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row = tc.m0 + w * 32 + lane;
@@ -412,7 +452,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       // this warp's TMEM reads of the tile are complete -> hand the accumulator back
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (kCtas == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -420,10 +462,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2)
+    cluster_sync_all();  // the peer's smem / barriers stay alive until the leader's last MMA and arrive are done
+  else
+    __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (kCtas == 2)
+      tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    else
+      tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -501,19 +549,41 @@ static int encode_mn_5d(CUtensorMap* m, int fp32, const void* ptr, uint64_t mn, 
   return 0;
 }
 
-template <int kBlockN>
+template <int kBlockN, int kCtas>
 static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
-  using Cfg = GemmCfg<kBlockN>;
+  using Cfg = GemmCfg<kBlockN, kCtas>;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kBlockN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kBlockN, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
     configured = true;
   }
-  int grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
-  gemm_tcgen05_kernel<kBlockN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(kp);
+  int units = num_sms() / kCtas;                       // CTAs, or CTA pairs
+  if (kp.total_tiles < units) units = kp.total_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(units * kCtas);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<kBlockN, kCtas>, kp));
   B200_LAUNCH_OK();
   return 0;
+}
+
+static bool use_cta_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_GEMM_2CTA");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 }  // namespace b200
@@ -547,7 +617,11 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream_) {
   kp.atom_elems = 128 / es;
   kp.atom_bytes = kp.bk_elems * 128;
   kp.n_per_tile = a->dual_b ? 128 : bn;
-  kp.m_blocks = (int)ceil_div(a->m, kBlockM);
+  // CTA pairs (256-row tiles) for the large GEMMs: every MN-major operand must be 5-D describable
+  const int atom_e = 128 / es;
+  const bool pair = use_cta_pairs() && bn == 256 && a->m >= 1024 && (!a->a_mn_major || a->m % atom_e == 0) &&
+                    (!a->b_mn_major || a->n % atom_e == 0) && a->block_n >= 0;
+  kp.m_blocks = (int)ceil_div(a->m, pair ? 2 * kBlockM : kBlockM);
   kp.n_blocks = (int)ceil_div(a->n, kp.n_per_tile);
   kp.tiles_per_batch = kp.m_blocks * kp.n_blocks;
   kp.total_tiles = kp.tiles_per_batch * z_lo * z_hi;
@@ -617,12 +691,13 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream_) {
     if (encode_4d(&kp.tmB, fp32, a->b, a->k, a->n, 1, 1, a->b_ld, 0, 0, kp.bk_elems, 128, "B(gate)")) return 1;
     if (encode_4d(&kp.tmB2, fp32, a->b2, a->k, a->n, 1, 1, a->b_ld, 0, 0, kp.bk_elems, 128, "B2(up)")) return 1;
   } else if (!kp.b_mn) {
-    if (encode_4d(&kp.tmB, fp32, a->b, a->k, a->n, b_z2, z_hi, a->b_ld, a->b_s2, a->b_s3, kp.bk_elems, bn, "B"))
+    if (encode_4d(&kp.tmB, fp32, a->b, a->k, a->n, b_z2, z_hi, a->b_ld, a->b_s2, a->b_s3, kp.bk_elems,
+                  pair ? bn / 2 : bn, "B"))
       return 1;
   } else if (a->n % kp.atom_elems == 0) {
     kp.b_5d = 1;
     if (encode_mn_5d(&kp.tmB, fp32, a->b, a->n, a->k, b_z2, z_hi, a->b_ld, a->b_s2, a->b_s3, kp.atom_elems,
-                     kp.bk_elems, bn / kp.atom_elems, "B(mn5)", b_atom32))
+                     kp.bk_elems, (pair ? bn / 2 : bn) / kp.atom_elems, "B(mn5)", b_atom32))
       return 1;
   } else {
     if (encode_4d(&kp.tmB, fp32, a->b, a->n, a->k, b_z2, z_hi, a->b_ld, a->b_s2, a->b_s3, kp.atom_elems, kp.bk_elems,
@@ -636,10 +711,10 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream_) {
 
   switch (bn) {
     case 64:
-      return launch_gemm<64>(kp, stream);
+      return launch_gemm<64, 1>(kp, stream);
     case 128:
-      return launch_gemm<128>(kp, stream);
+      return launch_gemm<128, 1>(kp, stream);
     default:
-      return launch_gemm<256>(kp, stream);
+      return pair ? launch_gemm<256, 2>(kp, stream) : launch_gemm<256, 1>(kp, stream);
   }
 }

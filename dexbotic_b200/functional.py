@@ -156,22 +156,23 @@ def block_forward(x2d: torch.Tensor, bw: BlockW, env: AttnEnv, keep: bool):
     x1, _ = linear_fwd(attn2d, bw.o, residual=x2d)
     h2, st2 = norm_fwd(x1, bw.norm2)
     saved = None
-    if c.mlp == "glu":
-        if keep:
-            g = torch.empty((x2d.shape[0], c.inter), device=x2d.device, dtype=x2d.dtype)
-            u = torch.empty_like(g)
-            hm = ops.gemm_dual(h2, bw.gate.w, bw.up.w, c.act, aux_gate=g, aux_up=u)
+    if keep:
+        # recompute pass (inside backward): the block OUTPUT is not needed, so the down / fc2 GEMM is skipped;
+        # gate and up run as two plain GEMMs (g, u feed glu_bwd, which also re-creates hm for the down wgrad)
+        if c.mlp == "glu":
+            g, _ = linear_fwd(h2, bw.gate)
+            u, _ = linear_fwd(h2, bw.up)
+            saved = dict(h=h, st1=st1, qkv=qkv, probs=probs, attn=attn2d, x1=x1, h2=h2, st2=st2, g=g, u=u, sh=sh)
         else:
-            g = u = None
-            hm = ops.gemm_dual(h2, bw.gate.w, bw.up.w, c.act)
-        y, _ = linear_fwd(hm, bw.down, residual=x1)
-        if keep:
-            saved = dict(h=h, st1=st1, qkv=qkv, probs=probs, attn=attn2d, x1=x1, h2=h2, st2=st2, g=g, u=u, hm=hm, sh=sh)
-    else:
-        hm, pre = linear_fwd(h2, bw.fc1, act=c.act, want_aux=keep)
-        y, _ = linear_fwd(hm, bw.fc2, residual=x1)
-        if keep:
+            hm, pre = linear_fwd(h2, bw.fc1, act=c.act, want_aux=True)
             saved = dict(h=h, st1=st1, qkv=qkv, probs=probs, attn=attn2d, x1=x1, h2=h2, st2=st2, pre=pre, hm=hm, sh=sh)
+        return None, saved
+    if c.mlp == "glu":
+        hm = ops.gemm_dual(h2, bw.gate.w, bw.up.w, c.act)
+        y, _ = linear_fwd(hm, bw.down, residual=x1)
+    else:
+        hm, _ = linear_fwd(h2, bw.fc1, act=c.act)
+        y, _ = linear_fwd(hm, bw.fc2, residual=x1)
     return y, saved
 
 
@@ -180,9 +181,10 @@ def block_backward(store: ParamStore, dy: torch.Tensor, x2d: torch.Tensor, bw: B
     c = bw.cfg
     # ---- MLP
     if c.mlp == "glu":
-        linear_wgrad(store, dy, s["hm"], bw.down)
         dhm = linear_dgrad(dy, bw.down)                                  # [M, inter]
-        dg, du = ops.glu_bwd(dhm, s["g"], s["u"], c.act, dg=s["g"], du=s["u"])   # in place over g / u
+        # one pass: dg, du (in place over g / u) and hm = act(g)*u (in place over dhm) for the down wgrad
+        dg, du = ops.glu_bwd(dhm, s["g"], s["u"], c.act, dg=s["g"], du=s["u"], h_out=dhm)
+        linear_wgrad(store, dy, dhm, bw.down)
         linear_wgrad(store, dg, s["h2"], bw.gate)
         linear_wgrad(store, du, s["h2"], bw.up)
         dh2 = linear_dgrad(dg, bw.gate)

@@ -39,7 +39,8 @@ def _check(out, ref, K, dtype, what=""):
                       f"ref_absmax={ref.abs().max().item():.4g} at {torch.nonzero(err > tol)[:4].tolist()}")
 
 
-GEMM_SHAPES = [(128, 256, 64), (256, 512, 256), (300, 200, 136), (1000, 3584, 1024), (77, 72, 96), (129, 257, 65 * 8)]
+GEMM_SHAPES = [(128, 256, 64), (256, 512, 256), (300, 200, 136), (1000, 3584, 1024), (77, 72, 96), (129, 257, 65 * 8),
+               (2176, 1152, 384), (1300, 768, 2048 + 64)]   # >= 1024 rows: CTA-pair (cta_group::2) path
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
@@ -76,9 +77,10 @@ def test_gemm_block_n(block_n):
 
 @pytest.mark.parametrize("act", ["none", "gelu", "gelu_tanh", "quick_gelu", "silu", "relu"])
 @pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
-def test_gemm_epilogue(act, out_dtype):
+@pytest.mark.parametrize("M", [333, 1290])
+def test_gemm_epilogue(act, out_dtype, M):
     o = ops()
-    M, N, K = 333, 264, 192
+    N, K = 264, 192
     a, b = _rand((M, K), torch.bfloat16, 5), _rand((N, K), torch.bfloat16, 6, 0.2)
     bias = _rand((N,), torch.bfloat16, 7)
     res = _rand((M, N), torch.bfloat16, 8)
@@ -104,9 +106,10 @@ def test_gemm_accumulate_fp32():
 
 
 @pytest.mark.parametrize("act", ["silu", "gelu_tanh"])
-def test_gemm_dual(act):
+@pytest.mark.parametrize("M", [300, 1411])
+def test_gemm_dual(act, M):
     o = ops()
-    M, N, K = 300, 648, 256
+    N, K = 648, 256
     a = _rand((M, K), torch.bfloat16, 12)
     wg, wu = _rand((N, K), torch.bfloat16, 13, 0.1), _rand((N, K), torch.bfloat16, 14, 0.1)
     ag = torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
@@ -154,6 +157,7 @@ def _ref_attention(qkv, B, S, H, KVH, hd, keymask, bid):
     (3, 257, 16, 16, 64, False, torch.bfloat16),
     (4, 17, 4, 4, 96, False, torch.float32),
     (2, 50, 8, 1, 256, True, torch.bfloat16),
+    (1, 1100, 4, 2, 64, True, torch.bfloat16),     # S >= 1024: batched GEMMs take the CTA-pair path
 ])
 def test_attention_fwd_bwd(B, S, H, KVH, hd, causal, dtype):
     o = ops()
