@@ -57,6 +57,7 @@ struct GemmKParams {
   void* aux2;
   long long aux_ld, aux_s2, aux_s3;
   int act;
+  int debug;  // bit0: skip TMA loads (MMA-only pipeline), bit1: skip MMAs (load-only pipeline) — perf experiments
 };
 
 template <int kBlockN, int kCtas = 1>
@@ -191,6 +192,54 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile,
   return c;
 }
 
+// The single MMA-issuing thread.  Everything that does not change per instruction is hoisted: the descriptor
+// high words, the LBO field and the per-UMMA address steps are computed once; per k-block the thread does one
+// barrier wait, one fence, four (add, add, issue) and one commit.  (Measured: with descriptors rebuilt per MMA
+// this thread took ~465 ns per k-block and bounded the whole GEMM, in 1-CTA and 2-CTA mode alike.)
+template <int kBlockN, int kCtas, bool kTF32>
+__device__ __forceinline__ void mma_issue_loop(const GemmKParams& p, uint8_t* smem, uint64_t* full_bar,
+                                               uint64_t* empty_bar, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                               uint32_t tmem_base, int tile0, int tile_step) {
+  using Cfg = GemmCfg<kBlockN, kCtas>;
+  const uint32_t idesc = umma_idesc(kTF32 ? 2u : 1u, p.a_mn, p.b_mn, kBlockM * kCtas, kBlockN);
+  const uint32_t a_hi = ((static_cast<uint32_t>(p.a_sbo) >> 4) & 0x3FFFu) | (1u << 14) | (static_cast<uint32_t>(p.a_lt) << 29);
+  const uint32_t b_hi = ((static_cast<uint32_t>(p.b_sbo) >> 4) & 0x3FFFu) | (1u << 14) | (static_cast<uint32_t>(p.b_lt) << 29);
+  const uint32_t a_lo0 = ((static_cast<uint32_t>(p.a_lbo) >> 4) & 0x3FFFu) << 16;
+  const uint32_t b_lo0 = ((static_cast<uint32_t>(p.b_lbo) >> 4) & 0x3FFFu) << 16;
+  const uint32_t a_step = static_cast<uint32_t>(p.a_kadv) >> 4, b_step = static_cast<uint32_t>(p.b_kadv) >> 4;
+  const uint32_t smem16 = smem_u32(smem) >> 4;
+  const int k_blocks = p.k_blocks;
+  int stage = 0;
+  uint32_t phase = 0;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
+    mbar_wait_fast(&tempty_bar[acc], acc_phase ^ 1);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + acc * kBlockN;
+    uint32_t accum = 0;
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      mbar_wait_fast(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t a_lo = a_lo0 | (smem16 + stage * (Cfg::kStageBytes >> 4));
+      const uint32_t b_lo = b_lo0 | (smem16 + stage * (Cfg::kStageBytes >> 4) + (kStageABytes >> 4));
+      umma_issue<kCtas, kTF32>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accum);
+      umma_issue<kCtas, kTF32>(d_tmem, a_lo + a_step, a_hi, b_lo + b_step, b_hi, idesc, 1u);
+      umma_issue<kCtas, kTF32>(d_tmem, a_lo + 2 * a_step, a_hi, b_lo + 2 * b_step, b_hi, idesc, 1u);
+      umma_issue<kCtas, kTF32>(d_tmem, a_lo + 3 * a_step, a_hi, b_lo + 3 * b_step, b_hi, idesc, 1u);
+      accum = 1u;
+      umma_commit_n<kCtas>(&empty_bar[stage]);  // smem slot is free (in both CTAs of a pair) once these retire
+      if (++stage == Cfg::kStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    umma_commit_n<kCtas>(&tfull_bar[acc]);  // accumulator complete -> epilogue (of both CTAs)
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
+}
+
 template <int kBlockN, int kCtas>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
   using Cfg = GemmCfg<kBlockN, kCtas>;
@@ -263,7 +312,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           uint8_t* sb = sa + kStageABytes;
           const int a_c2 = a_zbase + seg * p.a_seg;
           const int b_c2 = b_zbase + seg * p.b_seg;
-          if constexpr (kCtas == 2) {
+          if (p.debug & 1) {
+            if (leader) mbar_arrive(&full_bar[stage]);
+          } else if constexpr (kCtas == 2) {
             // both CTAs' bytes complete on the leader's barrier; only the leader arms it
             const uint32_t lbar = smem_u32(&full_bar[stage]) & kPeerBitMask;
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
@@ -315,48 +366,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
     if (lane == 0 && leader) {
-      const uint32_t idesc = umma_idesc(p.ab_fp32 ? 2u : 1u, p.a_mn, p.b_mn, kBlockM * kCtas, kBlockN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kBlockN;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + kStageABytes;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = umma_smem_desc(sa + k * p.a_kadv, p.a_lbo, p.a_sbo, p.a_lt);
-            const uint64_t bd = umma_smem_desc(sb + k * p.b_kadv, p.b_lbo, p.b_sbo, p.b_lt);
-            if constexpr (kCtas == 2) {
-              if (p.ab_fp32)
-                umma_tf32_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0);
-              else
-                umma_f16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0);
-            } else {
-              if (p.ab_fp32)
-                umma_tf32(d_tmem, ad, bd, idesc, (kb | k) != 0);
-              else
-                umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
-            }
-          }
-          // smem slot is free (in both CTAs of a pair) once these MMAs retire
-          if constexpr (kCtas == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        // accumulator complete -> epilogue (of both CTAs)
-        if constexpr (kCtas == 2) umma_commit_2sm(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
+      if (p.ab_fp32)
+        mma_issue_loop<kBlockN, kCtas, true>(p, smem, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base, tile0,
+                                             tile_step);
+      else
+        mma_issue_loop<kBlockN, kCtas, false>(p, smem, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base, tile0,
+                                              tile_step);
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
@@ -667,6 +682,14 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream_) {
   kp.aux_s2 = a->d_s2;
   kp.aux_s3 = a->d_s3;
   kp.act = a->act;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("B200_GEMM_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    kp.debug = dbg;
+  }
   if (kp.dual) B200_CHECK((kp.aux == nullptr) == (kp.aux2 == nullptr), "b200_gemm: dual_b aux and aux2 go together");
   if (kp.res) B200_CHECK(a->res_ld % (16 / (kp.res_fp32 ? 4 : 2)) == 0, "b200_gemm: residual ld not 16B-multiple");
   if (kp.aux) B200_CHECK(a->aux_ld % (16 / (kp.d_fp32 ? 4 : 2)) == 0, "b200_gemm: aux ld not 16B-multiple");

@@ -235,6 +235,49 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
+// Lean issue forms: descriptors passed as (lo, hi) 32-bit halves so the per-MMA work of the single issuing
+// thread is two integer adds (the issue thread, not the tensor pipe, was the measured bottleneck).
+template <int kCtas, bool kTF32>
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kCtas == 1 && !kTF32) {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 da, db;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\nsetp.ne.b32 p, %6, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else if constexpr (kCtas == 1 && kTF32) {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 da, db;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\nsetp.ne.b32 p, %6, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else if constexpr (kCtas == 2 && !kTF32) {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 da, db;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\nsetp.ne.b32 p, %6, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 da, db;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\nsetp.ne.b32 p, %6, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+template <int kCtas>
+__device__ __forceinline__ void umma_commit_n(uint64_t* bar) {
+  if constexpr (kCtas == 2)
+    umma_commit_2sm(bar);
+  else
+    umma_commit(bar);
+}
+// single try_wait fast path, spin (with the dead-lock trap) only when not yet complete
+__device__ __forceinline__ void mbar_wait_fast(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait(bar, parity);
+}
+
 // ------------------------------------------------------------ smem / idesc
 // UMMA shared-memory matrix descriptor, version = 1 (Blackwell).  layout_type: 2 = SWIZZLE_128B,
 // 1 = SWIZZLE_128B_BASE32B (the only legal layout for MN-major tf32 operands).
