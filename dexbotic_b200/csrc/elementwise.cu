@@ -333,12 +333,16 @@ __global__ void glu_bwd_kernel(const T* dh, const T* g, const T* u, T* dg, T* du
 // ------------------------------------------------------------------ softmax
 // One warp per (z, q) row.  allowed(q,k) = (!keymask || keymask[b,k]) && (!bid || bid_k[b,k] <= bid_q[b,q]).
 // b = z / heads.  Scores are fp32 (already scaled); P is written as T.  Fully masked rows -> zeros.
+// Rows up to 32*kSoftmaxCache keys are read ONCE (values cached in registers); longer rows fall back to
+// re-reading from L2.
+constexpr int kSoftmaxCache = 32;
 template <typename T>
 __global__ void softmax_fwd_kernel(const float* __restrict__ s, T* __restrict__ p, int64_t rows, int Sq, int Sk,
                                    int64_t s_ld, int64_t p_ld, int heads, const uint8_t* __restrict__ keymask,
                                    const int* __restrict__ bid_q, const int* __restrict__ bid_k) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
+  const bool cached = Sk <= 32 * kSoftmaxCache;
   for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
     const int64_t z = row / Sq;
     const int q = (int)(row - z * Sq);
@@ -348,6 +352,32 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ s, T* __restrict__ 
     const uint8_t* km = keymask != nullptr ? keymask + (size_t)b * Sk : nullptr;
     const int* bk = bid_k != nullptr ? bid_k + (size_t)b * Sk : nullptr;
     const int bq = bid_q != nullptr ? bid_q[(size_t)b * Sq + q] : 0;
+    if (cached) {
+      float v[kSoftmaxCache];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < kSoftmaxCache; ++i) {
+        const int k = lane + 32 * i;
+        v[i] = -INFINITY;
+        if (k < Sk && (km == nullptr || km[k]) && (bk == nullptr || bk[k] <= bq)) v[i] = sr[k];
+        mx = fmaxf(mx, v[i]);
+      }
+      mx = warp_max(mx);
+      float sum = 0.0f;
+#pragma unroll
+      for (int i = 0; i < kSoftmaxCache; ++i) {
+        v[i] = v[i] == -INFINITY ? 0.0f : __expf(v[i] - mx);
+        sum += v[i];
+      }
+      sum = warp_sum(sum);
+      const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
+#pragma unroll
+      for (int i = 0; i < kSoftmaxCache; ++i) {
+        const int k = lane + 32 * i;
+        if (k < Sk) pr[k] = from_f<T>(v[i] * inv);
+      }
+      continue;
+    }
     float mx = -INFINITY;
     for (int k = lane; k < Sk; k += 32) {
       const bool ok = (km == nullptr || km[k]) && (bk == nullptr || bk[k] <= bq);

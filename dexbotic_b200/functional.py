@@ -143,9 +143,16 @@ def norm_bwd(store: ParamStore, dy, x, n: Norm, stats, dx=None, accumulate_dx=Fa
     return dx
 
 
-def block_forward(x2d: torch.Tensor, bw: BlockW, env: AttnEnv, keep: bool):
-    """One pre-norm transformer block on [B*S, d].  keep=True returns every intermediate backward needs."""
+def block_forward(x2d: torch.Tensor, bw: BlockW, env: AttnEnv, mode: str):
+    """One pre-norm transformer block on [B*S, d].
+
+    mode "out":     forward only, nothing kept (the block is recomputed in backward);
+    mode "saved":   backward-time recompute: every intermediate backward needs, no block output
+                    (the down / fc2 GEMM is skipped);
+    mode "both":    forward that also keeps the intermediates (no recompute later; +1.2 GB per 7B layer).
+    The normed activations h / h2 are never stored: re-normalising is an HBM-bound 2-pass over [M, d]."""
     c = bw.cfg
+    keep = mode != "out"
     sh = ops.AttnShape(env.B, env.S, c.heads, c.kv_heads, c.head_dim, x2d.dtype)
     h, st1 = norm_fwd(x2d, bw.norm1)
     qkv, _ = linear_fwd(h, bw.qkv)
@@ -155,45 +162,48 @@ def block_forward(x2d: torch.Tensor, bw: BlockW, env: AttnEnv, keep: bool):
     attn2d = attn.view(x2d.shape[0], -1)
     x1, _ = linear_fwd(attn2d, bw.o, residual=x2d)
     h2, st2 = norm_fwd(x1, bw.norm2)
-    saved = None
-    if keep:
-        # recompute pass (inside backward): the block OUTPUT is not needed, so the down / fc2 GEMM is skipped;
-        # gate and up run as two plain GEMMs (g, u feed glu_bwd, which also re-creates hm for the down wgrad)
-        if c.mlp == "glu":
-            g, _ = linear_fwd(h2, bw.gate)
-            u, _ = linear_fwd(h2, bw.up)
-            saved = dict(h=h, st1=st1, qkv=qkv, probs=probs, attn=attn2d, x1=x1, h2=h2, st2=st2, g=g, u=u, sh=sh)
-        else:
-            hm, pre = linear_fwd(h2, bw.fc1, act=c.act, want_aux=True)
-            saved = dict(h=h, st1=st1, qkv=qkv, probs=probs, attn=attn2d, x1=x1, h2=h2, st2=st2, pre=pre, hm=hm, sh=sh)
-        return None, saved
+    saved, y = None, None
     if c.mlp == "glu":
-        hm = ops.gemm_dual(h2, bw.gate.w, bw.up.w, c.act)
-        y, _ = linear_fwd(hm, bw.down, residual=x1)
+        g, _ = linear_fwd(h2, bw.gate)
+        u, _ = linear_fwd(h2, bw.up)
+        if mode != "saved":
+            hm = ops.glu_fwd(g, u, c.act)
+            y, _ = linear_fwd(hm, bw.down, residual=x1)
+        if keep:
+            saved = dict(st1=st1, qkv=qkv, probs=probs, attn=attn2d, x1=x1, st2=st2, g=g, u=u, sh=sh)
     else:
-        hm, _ = linear_fwd(h2, bw.fc1, act=c.act)
-        y, _ = linear_fwd(hm, bw.fc2, residual=x1)
+        hm, pre = linear_fwd(h2, bw.fc1, act=c.act, want_aux=keep)
+        if mode != "saved":
+            y, _ = linear_fwd(hm, bw.fc2, residual=x1)
+        if keep:
+            saved = dict(st1=st1, qkv=qkv, probs=probs, attn=attn2d, x1=x1, st2=st2, pre=pre, sh=sh)
+    if mode == "saved":       # recompute pass: h / h2 are already here, hand them over instead of re-normalising
+        saved["h"], saved["h2"] = h, h2
     return y, saved
 
 
 def block_backward(store: ParamStore, dy: torch.Tensor, x2d: torch.Tensor, bw: BlockW, env: AttnEnv, s: dict):
     """Gradient of block_forward; dy is consumed (reused as the residual-stream gradient buffer)."""
     c = bw.cfg
+    h2 = s.get("h2")
+    if h2 is None:
+        h2, _ = norm_fwd(s["x1"], bw.norm2)
     # ---- MLP
     if c.mlp == "glu":
         dhm = linear_dgrad(dy, bw.down)                                  # [M, inter]
         # one pass: dg, du (in place over g / u) and hm = act(g)*u (in place over dhm) for the down wgrad
         dg, du = ops.glu_bwd(dhm, s["g"], s["u"], c.act, dg=s["g"], du=s["u"], h_out=dhm)
         linear_wgrad(store, dy, dhm, bw.down)
-        linear_wgrad(store, dg, s["h2"], bw.gate)
-        linear_wgrad(store, du, s["h2"], bw.up)
+        linear_wgrad(store, dg, h2, bw.gate)
+        linear_wgrad(store, du, h2, bw.up)
         dh2 = linear_dgrad(dg, bw.gate)
         linear_dgrad(du, bw.up, out=dh2, residual=dh2)
     else:
-        linear_wgrad(store, dy, s["hm"], bw.fc2)
-        dhm = linear_dgrad(dy, bw.fc2)
+        hm = ops.act_fwd(s["pre"], c.act)
+        linear_wgrad(store, dy, hm, bw.fc2)
+        dhm = linear_dgrad(dy, bw.fc2, out=hm)
         dpre = ops.act_bwd(dhm, s["pre"], c.act, out=dhm)
-        linear_wgrad(store, dpre, s["h2"], bw.fc1)
+        linear_wgrad(store, dpre, h2, bw.fc1)
         dh2 = linear_dgrad(dpre, bw.fc1)
     dx1 = norm_bwd(store, dh2, s["x1"], bw.norm2, s["st2"], dx=dy, accumulate_dx=True)   # dy += norm2 bwd
     # ---- attention
@@ -203,29 +213,38 @@ def block_backward(store: ParamStore, dy: torch.Tensor, x2d: torch.Tensor, bw: B
     dqkv2d = dqkv.view(x2d.shape[0], -1)
     if c.rope:
         ops.rope_(dqkv2d, env.pos, env.cos, env.sin, c.heads + c.kv_heads, c.head_dim, inverse=True)
-    linear_wgrad(store, dqkv2d, s["h"], bw.qkv)
+    h = s.get("h")
+    if h is None:
+        h, _ = norm_fwd(x2d, bw.norm1)
+    linear_wgrad(store, dqkv2d, h, bw.qkv)
     dh = linear_dgrad(dqkv2d, bw.qkv)
     return norm_bwd(store, dh, x2d, bw.norm1, s["st1"], dx=dx1, accumulate_dx=True)
 
 
 # --------------------------------------------------------------------- autograd Functions
 class TransformerBlockFn(torch.autograd.Function):
+    """recompute=True: keep only the block input and recompute inside backward (the reference's
+    gradient_checkpointing=True trade, base_exp.py:245); recompute=False: keep the intermediates."""
+
     @staticmethod
-    def forward(ctx, x2d, bw: BlockW, env: AttnEnv, store: ParamStore):
-        y, _ = block_forward(x2d, bw, env, keep=False)
+    def forward(ctx, x2d, bw: BlockW, env: AttnEnv, store: ParamStore, recompute: bool = True):
+        y, saved = block_forward(x2d, bw, env, "out" if recompute else "both")
         ctx.save_for_backward(x2d)
-        ctx.bw, ctx.env, ctx.store = bw, env, store
+        ctx.bw, ctx.env, ctx.store, ctx.kept = bw, env, store, saved
         return y
 
     @staticmethod
     def backward(ctx, dy):
         (x2d,) = ctx.saved_tensors
-        _, saved = block_forward(x2d, ctx.bw, ctx.env, keep=True)          # recompute
+        saved = ctx.kept
+        ctx.kept = None
+        if saved is None:
+            _, saved = block_forward(x2d, ctx.bw, ctx.env, "saved")          # recompute
         # block_backward accumulates the residual-stream gradient in place: work on a private buffer unless
         # the incoming gradient is a whole, contiguous tensor nobody else can be holding a view of
         dy = dy.contiguous() if dy._base is None and dy.is_contiguous() else dy.clone(memory_format=torch.contiguous_format)
         dx = block_backward(ctx.store, dy, x2d, ctx.bw, ctx.env, saved)
-        return dx, None, None, None
+        return dx, None, None, None, None
 
 
 class LinearFn(torch.autograd.Function):

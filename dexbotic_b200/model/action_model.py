@@ -128,7 +128,7 @@ class ActionModel:
         x2d = x.reshape(N * (T + 1), w).contiguous()
         env = AttnEnv(B=N, S=T + 1)
         for bw in self.blocks:
-            x2d = TransformerBlockFn.apply(x2d, bw, env, st)
+            x2d = TransformerBlockFn.apply(x2d, bw, env, st, False)      # ~30 MB of activations: never recompute
         x2d = NormFn.apply(x2d, self.norm_final, st)
         out = LinearFn.apply(x2d, self.final, None, st, True, None)                                      # FinalLayer
         return out.view(N, T + 1, A)[:, 1:, :]

@@ -228,6 +228,8 @@ class CLIPVisionTower:
         L = cfg_get(cfg, "num_hidden_layers")
         bc = BlockCfg(d=self.D, heads=self.heads, kv_heads=self.heads, head_dim=self.D // self.heads,
                       inter=cfg_get(cfg, "intermediate_size"), mlp="mlp", act=self.act, rope=False)
+        self.keep_layers = None          # blocks that keep intermediates (None: planned from free HBM at first use)
+        self.decoder_reserve_gb = 0.0    # set by the VLM shell: HBM the decoder's kept activations will need
         self.blocks = []
         for i in range(L - 1):                      # select_layer = -2
             q = f"{p}encoder.layers.{i}."
@@ -263,8 +265,13 @@ class CLIPVisionTower:
         x = PatchEmbedFn.apply(anchor.t, images, self)
         x = NormFn.apply(x, self.pre_ln, self.store)
         env = AttnEnv(B=N, S=self.P + 1)
-        for bw in self.blocks:
-            x = TransformerBlockFn.apply(x, bw, env, self.store)
+        if self.keep_layers is None and torch.is_grad_enabled():
+            # the decoder plans first (it is 95 % of the FLOPs); the tower keeps what still fits
+            self.keep_layers = plan_keep_layers(self.store, self.blocks[0].cfg, len(self.blocks), N, self.P + 1,
+                                                x.device, reserve_gb=14.0 + self.decoder_reserve_gb)
+        keep = self.keep_layers if torch.is_grad_enabled() else 0
+        for i, bw in enumerate(self.blocks):
+            x = TransformerBlockFn.apply(x, bw, env, self.store, i >= (keep or 0))
         return x
 
 
@@ -304,6 +311,9 @@ class Decoder:
         self.final_norm = Norm(kind, eps, store.w(prefix + "norm.weight"), None, store.g(prefix + "norm.weight"))
         self.theta = rope_theta_of(cfg)
         self._rope_cache = None
+        # layers [0, keep_layers) keep their intermediates (no recompute in backward); the rest recompute.
+        # None = decide from free HBM at the first forward (1 full-recompute layer costs ~25 % more GEMM work).
+        self.keep_layers = None
 
     def rope_tables(self, n_pos: int, device):
         """cos/sin exactly as HF's rotary embedding computes them (fp32 inv_freq, fp32 outer product)."""
@@ -316,12 +326,40 @@ class Decoder:
 
     def forward(self, x2d, B: int, S: int, mask_u8, pos_i32):
         dev = x2d.device
+        self._last_B = B
         cos, sin = self.rope_tables(S + 1, dev)
         bid = torch.arange(S, device=dev, dtype=torch.int32)[None, :].expand(B, S).contiguous()
         env = AttnEnv(B=B, S=S, keymask=mask_u8, bid=bid, pos=pos_i32.reshape(-1), cos=cos, sin=sin)
-        for bw in self.blocks:
-            x2d = TransformerBlockFn.apply(x2d, bw, env, self.store)
+        keep = self._decide_keep_layers(x2d) if torch.is_grad_enabled() else 0
+        for i, bw in enumerate(self.blocks):
+            x2d = TransformerBlockFn.apply(x2d, bw, env, self.store, i >= keep)
         return NormFn.apply(x2d, self.final_norm, self.store)
+
+    def _decide_keep_layers(self, x2d) -> int:
+        if self.keep_layers is None:
+            B = self._last_B
+            self.keep_layers = plan_keep_layers(self.store, self.blocks[0].cfg, len(self.blocks), B, x2d.shape[0] // B,
+                                                x2d.device)
+        return self.keep_layers
+
+
+def kept_bytes_per_block(bc: BlockCfg, B: int, S: int, es: int = 2) -> int:
+    """Bytes a block keeps alive when it is NOT recomputed: qkv, probs, attn, x1 and the MLP pre-activations."""
+    M = B * S
+    W = (bc.heads + 2 * bc.kv_heads) * bc.head_dim
+    inter = 2 * bc.inter if bc.mlp == "glu" else bc.inter
+    return es * M * (W + bc.heads * bc.head_dim + bc.d + inter) + es * B * bc.heads * S * ((S + 7) // 8 * 8)
+
+
+def plan_keep_layers(store: ParamStore, bc: BlockCfg, n_layers: int, B: int, S: int, device, reserve_gb: float = 14.0) -> int:
+    """How many blocks can keep their intermediates instead of being recomputed, from the HBM that is free
+    right now (minus Adam moments still to be allocated, backward transients and a fragmentation reserve)."""
+    free, _ = torch.cuda.mem_get_info(device)
+    cached = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    moments = 0 if store.exp_avg is not None else 8 * store.n_train
+    budget = free + cached - moments - int(reserve_gb * (1 << 30))
+    per = int(kept_bytes_per_block(bc, B, S) * 1.08) + (64 << 20)
+    return int(max(0, min(n_layers, budget // per)))
 
 
 class DexboticVLMModel:
@@ -372,9 +410,12 @@ class DexboticVLMModel:
         """dexbotic_arch.py:182-259 + :261-373, as three kernels (lengths, plan, gather) and ONE 4-byte
         device->host read (the padded length), instead of a per-sample Python loop with >= 3 syncs each."""
         cfg = self.config
-        feats, views = self._extract_vision_features(images)
         P = self.mm_vision_tower.P
         B, L = input_ids.shape
+        if self.mm_vision_tower.keep_layers is None:      # leave room for the decoder's kept activations first
+            need = kept_bytes_per_block(self.llm.blocks[0].cfg, B, L - 1 + P) * 1.08 * len(self.llm.blocks)
+            self.mm_vision_tower.decoder_reserve_gb = need / (1 << 30)
+        feats, views = self._extract_vision_features(images)
         mask_u8 = None if attention_mask is None else attention_mask.to(torch.uint8).contiguous()
         ids = input_ids.contiguous()
         max_len = cfg.tokenizer_model_max_length or 0

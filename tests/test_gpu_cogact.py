@@ -39,9 +39,14 @@ def test_state_dict_keys_match_reference():
     assert ours == ref
 
 
-def test_cogact_tiny_matches_reference_golden():
+@pytest.mark.parametrize("recompute", [True, False])
+def test_cogact_tiny_matches_reference_golden(recompute):
     fx = torch.load(GOLDEN / "cogact_tiny.pt", weights_only=False)
     model, _ = _build(fx["cfg"], fx["shapes"], fx["seed"])
+    # recompute=True: every block keeps only its input (gradient-checkpointing trade); False: keep intermediates
+    keep = 0 if recompute else 10 ** 6
+    model.model_engine.llm.keep_layers = min(keep, len(model.model_engine.llm.blocks))
+    model.model_engine.mm_vision_tower.keep_layers = min(keep, len(model.model_engine.mm_vision_tower.blocks))
     model.train()
     i = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in fx["inputs"].items()}
     model.zero_grad()
