@@ -76,6 +76,7 @@ class BlockW:
     down: Optional[Lin] = None
     fc1: Optional[Lin] = None
     fc2: Optional[Lin] = None
+    grad_range: Optional[tuple] = None   # [start, end) element range of this block's gradients in ParamStore.grad_a
 
 
 @dataclass
@@ -244,6 +245,9 @@ class TransformerBlockFn(torch.autograd.Function):
         # the incoming gradient is a whole, contiguous tensor nobody else can be holding a view of
         dy = dy.contiguous() if dy._base is None and dy.is_contiguous() else dy.clone(memory_format=torch.contiguous_format)
         dx = block_backward(ctx.store, dy, x2d, ctx.bw, ctx.env, saved)
+        hook = ctx.store.grad_ready_hook
+        if hook is not None and ctx.bw.grad_range is not None:
+            hook(*ctx.bw.grad_range)       # this block's gradients are final: data-parallel all-reduce may start
         return dx, None, None, None, None
 
 

@@ -308,6 +308,9 @@ class Decoder:
                            store.g(q + "post_attention_layernorm.weight")),
                 gate=Lin.of(store, q + "mlp.gate_proj.weight"), up=Lin.of(store, q + "mlp.up_proj.weight"),
                 down=Lin.of(store, q + "mlp.down_proj.weight")))
+        for i, bw in enumerate(self.blocks):
+            q = f"{prefix}layers.{i}."
+            bw.grad_range = store.grad_range([n for n in store.order if n.startswith(q)])
         self.final_norm = Norm(kind, eps, store.w(prefix + "norm.weight"), None, store.g(prefix + "norm.weight"))
         self.theta = rope_theta_of(cfg)
         self._rope_cache = None

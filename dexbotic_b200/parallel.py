@@ -35,3 +35,61 @@ def broadcast_parameters(store: ParamStore, src: int = 0, group=None) -> None:
     """Rank `src`'s master weights to everyone (identical replicas at start); shadows are refreshed by the caller."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.broadcast(store.master, src=src, group=group)
+
+
+class GradientOverlap:
+    """Bucketed gradient all-reduce overlapped with backward.
+
+    `TransformerBlockFn.backward` reports each block's gradient range in the flat bf16 buffer as soon as that
+    block's wgrad kernels are enqueued (`ParamStore.grad_ready_hook`); consecutive ranges are merged into
+    buckets of >= `bucket_bytes` and all-reduced asynchronously on NCCL's stream (which first waits for the
+    compute stream), so NVLink traffic hides behind the backward of the earlier layers.  `finish()` reduces what
+    is left (embeddings, projector, tower front end, fp32 action head) and joins the streams."""
+
+    def __init__(self, store: ParamStore, group=None, bucket_bytes: int = 512 << 20):
+        self.store, self.group, self.bucket_bytes = store, group, bucket_bytes
+        self.enabled = dist.is_initialized() and dist.get_world_size(group) > 1
+        self.works = []
+        self.done = []          # list of (start, end) already reduced this step (element offsets in grad_a)
+        self.pending = None     # (start, end) accumulated but not launched yet
+        if self.enabled:
+            store.grad_ready_hook = self.on_ready
+
+    def _launch(self, a: int, b: int) -> None:
+        chunk = self.store.grad_a[a:b]
+        self.works.append(dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        self.done.append((a, b))
+
+    def on_ready(self, a: int, b: int) -> None:
+        if self.pending is None:
+            self.pending = (a, b)
+        elif b == self.pending[0]:                 # backward walks the layers from the end: ranges grow downwards
+            self.pending = (a, self.pending[1])
+        elif a == self.pending[1]:
+            self.pending = (self.pending[0], b)
+        else:                                       # not adjacent: flush what we have
+            self._launch(*self.pending)
+            self.pending = (a, b)
+        if (self.pending[1] - self.pending[0]) * 2 >= self.bucket_bytes:
+            self._launch(*self.pending)
+            self.pending = None
+
+    def finish(self) -> None:
+        if not self.enabled:
+            return
+        if self.pending is not None:
+            self._launch(*self.pending)
+            self.pending = None
+        # everything not covered by a reported range
+        covered = sorted(self.done)
+        cur = 0
+        for a, b in covered + [(self.store.n_a, self.store.n_a)]:
+            if a > cur:
+                self.works.append(dist.all_reduce(self.store.grad_a[cur:a], op=dist.ReduceOp.AVG, group=self.group,
+                                                  async_op=True))
+            cur = max(cur, b)
+        if self.store.n_b:
+            self.works.append(dist.all_reduce(self.store.grad_b, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        for w in self.works:
+            w.wait()
+        self.works, self.done = [], []

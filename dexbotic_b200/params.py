@@ -136,6 +136,15 @@ class ParamStore:
             base = first.offset
         return self._view(buf, base, (rows,) + tuple(tail))
 
+    def grad_range(self, names: list[str]) -> Optional[tuple]:
+        """[start, end) element range in grad_a spanned by the trainable region-A tensors in `names`."""
+        sl = [self.slots[n] for n in names if n in self.slots and self.slots[n].region == "A"]
+        if not sl:
+            return None
+        a = min(s.offset for s in sl)
+        b = max(s.offset + s.spec.numel for s in sl)
+        return (a // ALIGN * ALIGN, min(self.n_a, (b + ALIGN - 1) // ALIGN * ALIGN))
+
     def fused_w(self, names: list[str]) -> torch.Tensor:
         return self._fused(names, "w")
 

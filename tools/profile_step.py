@@ -1,0 +1,48 @@
+"""Per-kernel device time of one CogACT-7B training step via torch.profiler (CUPTI), low overhead."""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import bench  # noqa: E402
+from dexbotic_b200.model import CogActConfig, CogACTForCausalLM  # noqa: E402
+
+
+def main():
+    w = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cogact_7b"]
+    dev = torch.device("cuda", 0)
+    cfg = CogActConfig(llm_config=w["llm"], mm_vision_tower=w["vision"], action_model_type=w["action_model_type"],
+                       action_dim=w["action_dim"], chunk_size=w["chunk_size"])
+    model = CogACTForCausalLM(cfg, device=dev)
+    model.init_weights_(seed=1234)
+    model.train()
+    batch = {k: v.to(dev) for k, v in bench.make_batch(w, 0, pinned=False).items()}
+
+    def step():
+        model.zero_grad()
+        out = model(**batch)
+        out.loss.backward()
+        model.optimizer_step(base_lr=2e-5)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        step()
+        torch.cuda.synchronize()
+    rows = []
+    for e in prof.key_averages():
+        t = getattr(e, "device_time_total", 0) or getattr(e, "cuda_time_total", 0)
+        if t > 0 and e.device_type is not None and "cuda" in str(e.device_type).lower():
+            rows.append((t, e.count, e.key))
+    rows.sort(reverse=True)
+    tot = sum(r[0] for r in rows)
+    print(f"total device time {tot/1e3:.1f} ms over {sum(r[1] for r in rows)} launches")
+    for t, n, k in rows[:40]:
+        print(f"{t/1e3:9.2f} ms {100*t/tot:5.1f}% n={n:5d} {k[:100]}")
+
+
+if __name__ == "__main__":
+    main()
