@@ -347,3 +347,20 @@ class CastFn(torch.autograd.Function):
     def backward(ctx, g):
         out = torch.empty(g.shape, device=g.device, dtype=ctx.src_dtype)
         return ops.cast_(g.contiguous(), out), None
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """mean cross entropy over rows with label != -100, fp32 math on bf16/fp32 logits
+    (F.cross_entropy under fp32 autocast: oft_discrete_arch.py:169-191; dexbotic_arch.py:489)."""
+
+    @staticmethod
+    def forward(ctx, logits2d, labels):
+        logits2d = logits2d.contiguous()
+        loss_sum, n_valid, lse = ops.cross_entropy_fwd(logits2d, labels.contiguous())
+        ctx.save_for_backward(logits2d, labels, lse, n_valid)
+        return loss_sum / n_valid.clamp(min=1).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        logits2d, labels, lse, n_valid = ctx.saved_tensors
+        return ops.cross_entropy_bwd(logits2d, labels.contiguous(), lse, n_valid, g.contiguous().float()), None

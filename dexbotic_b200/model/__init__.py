@@ -3,3 +3,4 @@ forward signatures, config fields and state-dict keys; the arithmetic runs in li
 from .dexbotic_arch import (CausalLMOutputDexbotic, DexboticConfig, DexboticVLMModel, IGNORE_INDEX,  # noqa: F401
                             IMAGE_TOKEN_INDEX)
 from .cogact_arch import CogActConfig, CogActModel, CogACTForCausalLM  # noqa: F401
+from .oft_arch import OFTConfig, OFTDiscreteConfig, OFTDiscreteForCausalLM  # noqa: F401

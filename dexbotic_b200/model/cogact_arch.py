@@ -107,7 +107,7 @@ class CogACTForCausalLM(B200Module):
             raise RuntimeError("dexbotic_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         eng = self.model_engine
         cfg = self.config
-        emb, new_labels, new_mask, pos, S = eng._prepare_inputs_labels_for_multimodal(
+        emb, new_labels, new_mask, pos, S, _ = eng._prepare_inputs_labels_for_multimodal(
             input_ids, attention_mask, labels, images)
         B = input_ids.shape[0]
         hidden2d = eng.llm.forward(emb.view(B * S, -1), B, S, new_mask, pos)           # cogact_arch.py:97-108

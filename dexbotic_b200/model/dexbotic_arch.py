@@ -409,14 +409,20 @@ class DexboticVLMModel:
             x = LinearFn.apply(x, lin, act, self.store, tower.g_patch is not None, self.anchor.t if i == 0 else None)
         return x, views
 
-    def _prepare_inputs_labels_for_multimodal(self, input_ids, attention_mask, labels, images):
+    def _prepare_inputs_labels_for_multimodal(self, input_ids, attention_mask, labels, images, append_tokens: int = 0,
+                                              append_token_id: int = 1):
         """dexbotic_arch.py:182-259 + :261-373, as three kernels (lengths, plan, gather) and ONE 4-byte
-        device->host read (the padded length), instead of a per-sample Python loop with >= 3 syncs each."""
+        device->host read (the padded length), instead of a per-sample Python loop with >= 3 syncs each.
+
+        append_tokens > 0 additionally inserts that many copies of embed_tokens[append_token_id] right after the
+        last valid token of every sample (OFT's action placeholders: oft_arch.py:169-201 insert_action_embedding
+        applied to embed_tokens(ones), oft_discrete_arch.py:125-130) — folded into the same gather.
+        Returns (inputs_embeds [B,S,D], labels, mask u8 [B,S], position ids i32 [B,S], S, lengths i32 [B])."""
         cfg = self.config
         P = self.mm_vision_tower.P
         B, L = input_ids.shape
         if self.mm_vision_tower.keep_layers is None:      # leave room for the decoder's kept activations first
-            need = kept_bytes_per_block(self.llm.blocks[0].cfg, B, L - 1 + P) * 1.08 * len(self.llm.blocks)
+            need = kept_bytes_per_block(self.llm.blocks[0].cfg, B, L - 1 + P + append_tokens) * 1.08 * len(self.llm.blocks)
             self.mm_vision_tower.decoder_reserve_gb = need / (1 << 30)
         feats, views = self._extract_vision_features(images)
         mask_u8 = None if attention_mask is None else attention_mask.to(torch.uint8).contiguous()
@@ -426,12 +432,28 @@ class DexboticVLMModel:
             raise NotImplementedError("multi-view (5-D images) splice: next round (MemVLA / pi0 rows of SURVEY §8)")
         lengths = ops.splice_lengths(ids, mask_u8, P, max_len)
         S = int(lengths.max().item())
-        src, new_labels, new_mask, pos = ops.splice_plan(ids, mask_u8, labels, P, max_len, S,
-                                                         cfg.tokenizer_padding_side == "left")
+        left = cfg.tokenizer_padding_side == "left"
+        src, new_labels, new_mask, pos = ops.splice_plan(ids, mask_u8, labels, P, max_len, S, left)
         # feature rows carry a CLS row per image: entry e, token t lives at row e*(P+1) + 1 + t
         src = _shift_image_rows(src, P)
+        if append_tokens > 0:
+            if left:
+                raise NotImplementedError("action-token insertion assumes right padding (oft_arch.py:188-199)")
+            A = append_tokens
+            idx = torch.arange(S + A, device=src.device, dtype=torch.int32)[None, :]
+            ln = lengths[:, None]
+            pad = torch.full((B, A), -(2 ** 31), device=src.device, dtype=torch.int32)
+            src_ext = torch.cat([src, pad], dim=1)
+            shifted = torch.cat([pad, src], dim=1)              # src[b, s - A] for the tail
+            src = torch.where(idx < ln, src_ext, torch.where(idx < ln + A, torch.full_like(src_ext, append_token_id),
+                                                             shifted)).contiguous()
+            new_mask = (idx < ln + A).to(torch.uint8).contiguous()
+            pos = idx.expand(B, S + A).contiguous()             # HF default position ids: arange (position_ids=None)
+            new_labels = torch.cat([new_labels, torch.full((B, A), IGNORE_INDEX, device=src.device,
+                                                           dtype=new_labels.dtype)], dim=1)
+            S = S + A
         emb = SpliceFn.apply(feats, src, self.llm.embed_w, self.llm.embed_g, self.store)
-        return emb, new_labels, new_mask, pos, S
+        return emb, new_labels, new_mask, pos, S, lengths
 
 
 def _shift_image_rows(src: torch.Tensor, P: int) -> torch.Tensor:

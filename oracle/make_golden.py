@@ -185,7 +185,56 @@ def make_integer_kats():
     print("[diffusion] schedule ok", d.sqrt_alphas_cumprod[[0, 50, 99]])
 
 
+def make_oft_discrete_tiny(seed: int = 4321):
+    llm, clip, cfg = tiny_cogact_configs()
+    llm.vocab_size = 512
+    cfg = dict(cfg, chunk_size=8, action_dim=7, num_bins=256)
+    cfg["llm"] = dict(cfg["llm"], vocab_size=512)
+    model = ref_loader.build_reference_oft_discrete(llm, clip, 7, 8, 256)
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    g = torch.Generator().manual_seed(seed)
+    B, A = 3, 56
+    L = 10 + A + 1 + 3                       # prefix(10) + action labels(56) + suffix token + up to 3 pads
+    ids = torch.randint(1, 250, (B, L), generator=g)
+    ids[:, 1] = vla_oracle.IMAGE_TOKEN_INDEX
+    mask = torch.ones(B, L, dtype=torch.long)
+    mask[1, L - 3:] = 0
+    mask[2, L - 1:] = 0
+    labels = torch.full((B, L), -100, dtype=torch.long)
+    for b in range(B):
+        npl = int(mask[b].sum())
+        tok = torch.randint(512 - 255, 512, (A,), generator=g)      # action tokens live in the last 255 vocab entries
+        ids[b, npl - 1 - A:npl - 1] = tok
+        labels[b, npl - 1 - A:npl - 1] = tok
+    images = torch.randn(B, 3, 28, 28, generator=g)
+    actions = torch.rand(B, 8 * 7, generator=g) * 2 - 1      # only `actions is not None` matters (oft_discrete_arch.py:171)
+    out = model(input_ids=ids, attention_mask=mask, images=images, labels=labels, actions=actions)
+    out.loss.backward()
+    ora = vla_oracle.oft_discrete_forward(sd, cfg, ids, mask, images, labels)
+    d_loss = abs(ora["loss"].item() - out.loss.item())
+    d_log = (ora["logits"] - out.logits).abs().max().item()
+    print(f"[oft_discrete_tiny] reference loss {out.loss.item():.8f} oracle {ora['loss'].item():.8f}; logits max|d|={d_log:.2e}")
+    assert d_loss < 1e-5 and d_log < 1e-4
+    model.eval()
+    with torch.no_grad():
+        inf = model(input_ids=ids[:, :11], attention_mask=torch.ones(B, 11, dtype=torch.long), images=images)
+        ref_idx = torch.argmax(inf.logits[:, :, -255:], dim=-1)          # oft_discrete_arch.py:222-224
+        ref_cont = model.model.action_head.discrete_tokens_to_continuous(ref_idx)
+    grads = {n: dict(model.named_parameters())[n].grad.clone() for n in
+             ["lm_head.weight", "model.llm.layers.1.mlp.up_proj.weight", "model.llm.embed_tokens.weight",
+              "model.mm_projector.2.weight", "model.llm.layers.0.self_attn.v_proj.weight"]}
+    torch.save(dict(seed=seed, cfg=cfg, shapes={k: tuple(v.shape) for k, v in sd.items()},
+                    inputs=dict(input_ids=ids, attention_mask=mask, images=images, labels=labels, actions=actions),
+                    outputs=dict(loss=out.loss.detach(), logits=out.logits.detach(), grads=grads,
+                                 infer_logits=inf.logits, infer_idx=ref_idx, infer_cont=ref_cont)),
+               GOLDEN / "oft_discrete_tiny.pt")
+    print("[oft_discrete_tiny] wrote fixture")
+
+
 if __name__ == "__main__":
     make_cogact_tiny()
+    make_oft_discrete_tiny()
     make_splice_cases()
     make_integer_kats()

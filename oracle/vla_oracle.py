@@ -336,3 +336,48 @@ def data_action_to_bin(action: np.ndarray, vocab_size: int = 255) -> np.ndarray:
     NOTE the 254-vs-255 scale mismatch with the model side is the reference's; reproduced, not fixed."""
     a = np.round((action + 1) / 2 * (vocab_size - 1))
     return np.clip(a, 0, vocab_size - 1)
+
+
+# ----------------------------------------------------------------------------------------------
+# OFT-discrete training forward — oft_discrete_arch.py:26-205, oft_arch.py:169-210
+# ----------------------------------------------------------------------------------------------
+def oft_discrete_forward(sd, cfg: dict, input_ids, attention_mask, images, labels=None):
+    """Returns dict(loss, logits [B, A, V], action_labels).  A = chunk_size * action_dim placeholder tokens
+    (embed_tokens of token id 1) are inserted after the last valid token of every sample."""
+    A = cfg["chunk_size"] * cfg["action_dim"]
+    B = input_ids.shape[0]
+    action_labels = None
+    if labels is not None:                                            # :66-106
+        ids2, mask2, al = [], [], []
+        for i in range(B):
+            npl = int(attention_mask[i].sum())
+            prefix = npl - A - 1
+            ids2.append(torch.cat([input_ids[i, :prefix], input_ids[i, npl - 1:]]))
+            al.append(labels[i, prefix:prefix + A])
+            m = torch.zeros(ids2[-1].shape[0], dtype=attention_mask.dtype)
+            m[:prefix + 1] = 1
+            mask2.append(m)
+        input_ids, attention_mask, action_labels = torch.stack(ids2), torch.stack(mask2), torch.stack(al)
+    feats = clip_vision_features(sd, "model.mm_vision_tower.", images, cfg["vision"])
+    feats = mlp_projector(sd, "model.mm_projector.", feats, cfg.get("projector_depth", 2))
+    emb, _, msk, _ = splice(sd["model.llm.embed_tokens.weight"], feats, input_ids, attention_mask, None,
+                            cfg.get("tokenizer_model_max_length"), "right")
+    S, D = emb.shape[1], emb.shape[2]
+    act_emb = sd["model.llm.embed_tokens.weight"][torch.ones(A, dtype=torch.long)]       # :125-130
+    lens = msk.long().sum(dim=1)
+    emb2 = torch.zeros(B, S + A, D, dtype=emb.dtype)
+    msk2 = torch.zeros(B, S + A, dtype=torch.bool)
+    for i in range(B):                                                 # insert_action_embedding, oft_arch.py:169-201
+        n = int(lens[i])
+        emb2[i, :n] = emb[i, :n]
+        emb2[i, n:n + A] = act_emb
+        emb2[i, n + A:] = emb[i, n:]
+        msk2[i, :n + A] = True
+    pid = torch.arange(S + A)[None, :].expand(B, S + A)                # position_ids=None -> HF arange
+    hs = decoder_forward(sd, "model.llm.", emb2, msk2, pid, cfg["llm"])
+    ah = torch.stack([hs[i, int(lens[i]):int(lens[i]) + A] for i in range(B)])           # :204-210
+    logits = F.linear(ah, sd["lm_head.weight"])
+    loss = None
+    if action_labels is not None:
+        loss = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), action_labels.reshape(-1), reduction="mean")
+    return dict(loss=loss, logits=logits, action_labels=action_labels, action_hidden=ah)

@@ -67,3 +67,17 @@ def test_cosine_schedule_matches_reference():
     assert np.array_equal(sa, k["sqrt_alphas_cumprod"].numpy())
     assert np.array_equal(sb, k["sqrt_one_minus_alphas_cumprod"].numpy())
     assert abs(sa[0] - 0.999684309) < 1e-9 and abs(sa[50] - 0.691566796) < 1e-9 and abs(sa[99] - 4.92805467e-4) < 1e-12
+
+
+def test_oft_discrete_tiny_matches_reference():
+    fx = torch.load(GOLDEN / "oft_discrete_tiny.pt", weights_only=False)
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    i = fx["inputs"]
+    out = vla_oracle.oft_discrete_forward(sd, fx["cfg"], i["input_ids"], i["attention_mask"], i["images"], i["labels"])
+    assert abs(out["loss"].item() - fx["outputs"]["loss"].item()) < 1e-5
+    assert (out["logits"] - fx["outputs"]["logits"]).abs().max().item() < 1e-4
+    # integer decode of the reference's own inference logits (oft_discrete_arch.py:222-224; model.py:314-347)
+    idx = vla_oracle.oft_argmax_decode(fx["outputs"]["infer_logits"].numpy())
+    assert np.array_equal(idx, fx["outputs"]["infer_idx"].numpy())
+    cont = vla_oracle.oft_bins_to_continuous(idx).reshape(idx.shape[0], 8, 7)
+    assert np.array_equal(cont, fx["outputs"]["infer_cont"].numpy())
