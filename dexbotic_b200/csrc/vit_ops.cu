@@ -97,6 +97,67 @@ __global__ void copy2d_kernel(const S* __restrict__ src, D* __restrict__ dst, in
   }
 }
 
+// dst[b, r, 0:cols] (+)= alpha * src[b, r, 0:cols]   (row-block moves between packed / joint sequence buffers)
+template <typename T>
+__global__ void copy3d_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int rows, int cols8, int64_t sbs,
+                              int64_t sld, int64_t dbs, int64_t dld, float alpha, int accumulate) {
+  const int64_t total = (int64_t)B * rows * cols8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols8) * 8;
+    const int64_t t = i / cols8;
+    const int r = (int)(t % rows);
+    const int b = (int)(t / rows);
+    float v[8];
+    Pack8<T>::load(src + b * sbs + r * sld + c, v);
+    T* d = dst + b * dbs + r * dld + c;
+    if (accumulate) {
+      float o[8];
+      Pack8<T>::load(d, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = o[j] + alpha * v[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= alpha;
+    }
+    Pack8<T>::store(d, v);
+  }
+}
+// out[b, p, :] = x[b, p, :] + pos[p, :]    (SigLIP position embedding, no CLS token)
+template <typename T>
+__global__ void add_pos_fwd_kernel(const T* __restrict__ x, const T* __restrict__ pos, T* __restrict__ out, int B, int P,
+                                   int D8) {
+  const int64_t total = (int64_t)B * P * D8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % D8) * 8;
+    const int64_t r = i / D8;
+    const int p = (int)(r % P);
+    float a[8], e[8];
+    Pack8<T>::load(x + r * D8 * 8 + c, a);
+    Pack8<T>::load(pos + (size_t)p * D8 * 8 + c, e);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += e[j];
+    Pack8<T>::store(out + r * D8 * 8 + c, a);
+  }
+}
+// d_pos[p, :] += sum_b dout[b, p, :]
+template <typename T>
+__global__ void add_pos_bwd_kernel(const T* __restrict__ dout, float* __restrict__ d_pos, int B, int P, int D8) {
+  const int64_t total = (int64_t)P * D8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % D8) * 8;
+    const int p = (int)(i / D8);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < B; ++b) {
+      float v[8];
+      Pack8<T>::load(dout + ((size_t)b * P + p) * D8 * 8 + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d_pos[(size_t)p * D8 * 8 + c + j] += acc[j];
+  }
+}
+
 static inline int grid_cap(int64_t want) {
   int64_t cap = (int64_t)num_sms() * 8;
   if (want > cap) want = cap;
@@ -164,6 +225,52 @@ int b200_cast_add(const float* src, void* dst, int64_t n, int dst_dtype, int acc
     cast_add_kernel<float><<<grid_cap(ceil_div(n, 256)), 256, 0, STREAM>>>(src, (float*)dst, n, accumulate);
   else
     cast_add_kernel<bf16><<<grid_cap(ceil_div(n, 256)), 256, 0, STREAM>>>(src, (bf16*)dst, n, accumulate);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_copy3d(const void* src, void* dst, int64_t B, int64_t rows, int64_t cols, int64_t src_bs, int64_t src_ld,
+                int64_t dst_bs, int64_t dst_ld, float alpha, int accumulate, int dtype, void* stream) {
+  B200_CHECK(cols % 8 == 0 && src_ld % 8 == 0 && dst_ld % 8 == 0 && src_bs % 8 == 0 && dst_bs % 8 == 0,
+             "copy3d: cols / strides must be multiples of 8");
+  const int64_t total = B * rows * (cols / 8);
+  if (total == 0) return 0;
+  const int g = grid_cap(ceil_div(total, 256));
+  if (dtype == B200_F32)
+    copy3d_kernel<float><<<g, 256, 0, STREAM>>>((const float*)src, (float*)dst, (int)B, (int)rows, (int)(cols / 8),
+                                                 src_bs, src_ld, dst_bs, dst_ld, alpha, accumulate);
+  else
+    copy3d_kernel<bf16><<<g, 256, 0, STREAM>>>((const bf16*)src, (bf16*)dst, (int)B, (int)rows, (int)(cols / 8), src_bs,
+                                                src_ld, dst_bs, dst_ld, alpha, accumulate);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_add_pos_fwd(const void* x, const void* pos, void* out, int64_t B, int64_t P, int64_t D, int dtype,
+                     void* stream) {
+  B200_CHECK(D % 8 == 0, "add_pos_fwd: D must be a multiple of 8");
+  const int64_t total = B * P * (D / 8);
+  if (total == 0) return 0;
+  const int g = grid_cap(ceil_div(total, 256));
+  if (dtype == B200_F32)
+    add_pos_fwd_kernel<float><<<g, 256, 0, STREAM>>>((const float*)x, (const float*)pos, (float*)out, (int)B, (int)P,
+                                                      (int)(D / 8));
+  else
+    add_pos_fwd_kernel<bf16><<<g, 256, 0, STREAM>>>((const bf16*)x, (const bf16*)pos, (bf16*)out, (int)B, (int)P,
+                                                     (int)(D / 8));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_add_pos_bwd(const void* dout, float* d_pos, int64_t B, int64_t P, int64_t D, int dtype, void* stream) {
+  B200_CHECK(D % 8 == 0, "add_pos_bwd: D must be a multiple of 8");
+  const int64_t total = P * (D / 8);
+  if (total == 0 || B == 0) return 0;
+  const int g = grid_cap(ceil_div(total, 128));
+  if (dtype == B200_F32)
+    add_pos_bwd_kernel<float><<<g, 128, 0, STREAM>>>((const float*)dout, d_pos, (int)B, (int)P, (int)(D / 8));
+  else
+    add_pos_bwd_kernel<bf16><<<g, 128, 0, STREAM>>>((const bf16*)dout, d_pos, (int)B, (int)P, (int)(D / 8));
   B200_LAUNCH_OK();
   return 0;
 }

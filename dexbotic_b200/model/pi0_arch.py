@@ -1,0 +1,516 @@
+"""Mirror of dexbotic/model/pi0/pi0_arch.py: Pi0Config / Pi0ForCausalLM — SigLIP tower,
+linear projector, Gemma LLM + Gemma action expert executed layer by layer with SHARED attention over the joint
+[prefix | suffix] sequence (`_inner_forward_mot`, pi0_arch.py:116-228), flow-matching loss (:337-388).
+
+State-dict keys == the reference's (model.llm.*, model.action_expert.*, model.mm_vision_tower.*,
+model.mm_projector.*, model.state_proj.*, model.action_in_proj.*, model.action_time_mlp_{in,out}.*,
+model.action_out_proj.*).  The block-causal mask (make_attn_mask, :22-33) is evaluated inside the softmax kernel
+from two small per-token arrays (validity, cumsum(ar_mask)) instead of a dense fp32 [B,1,S,S] tensor.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..functional import (AttnEnv, BlockCfg, BlockW, CastFn, Lin, LinearFn, MSELossFn, Norm, NormFn,
+                          TransformerBlockFn, linear_dgrad, linear_fwd, linear_wgrad, norm_bwd, norm_fwd)
+from ..params import ParamSpec, ParamStore
+from ._module import B200Module
+from .dexbotic_arch import CausalLMOutputDexbotic, DexboticConfig, _Anchor, cfg_get, rope_theta_of
+
+
+class Pi0Config(DexboticConfig):
+    """pi0_arch.py:53-83 (llm_config / action_config / vision_config: HF config objects or dicts)."""
+    model_type = "dexbotic_pi0"
+
+    def __init__(self, vision_config=None, processor_config=None, action_config=None, action_dim: int = 32,
+                 chunk_size: int = 50, **kw):
+        kw.setdefault("mm_projector_type", "linear")
+        super().__init__(**kw)
+        self.vision_config, self.processor_config, self.action_config = vision_config, processor_config, action_config
+        self.action_dim, self.chunk_size = action_dim, chunk_size
+
+
+# ------------------------------------------------------------------------------------ specs
+def siglip_specs(cfg, trainable: bool, prefix: str = "model.mm_vision_tower.vision_tower.vision_model.") -> list[ParamSpec]:
+    D, inter, L = cfg_get(cfg, "hidden_size"), cfg_get(cfg, "intermediate_size"), cfg_get(cfg, "num_hidden_layers")
+    ps, img, C = cfg_get(cfg, "patch_size"), cfg_get(cfg, "image_size"), cfg_get(cfg, "num_channels", 3)
+    P = (img // ps) ** 2
+    g = "vision"
+    sp = [ParamSpec(prefix + "embeddings.patch_embedding.weight", (D, C, ps, ps), g, trainable=trainable),
+          ParamSpec(prefix + "embeddings.patch_embedding.bias", (D,), g, trainable=trainable),
+          ParamSpec(prefix + "embeddings.position_embedding.weight", (P, D), g, trainable=trainable, no_decay=False)]
+    for i in range(L):
+        q = f"{prefix}encoder.layers.{i}."
+        for n in ("layer_norm1", "layer_norm2"):
+            sp.append(ParamSpec(f"{q}{n}.weight", (D,), g, trainable=trainable))
+            sp.append(ParamSpec(f"{q}{n}.bias", (D,), g, trainable=trainable))
+        for n in "qkv":
+            sp.append(ParamSpec(f"{q}self_attn.{n}_proj.bias", (D,), g, fuse=q + "qkvb", trainable=trainable))
+        for n in "qkv":
+            sp.append(ParamSpec(f"{q}self_attn.{n}_proj.weight", (D, D), g, fuse=q + "qkvw", trainable=trainable))
+        sp += [ParamSpec(q + "self_attn.out_proj.weight", (D, D), g, trainable=trainable),
+               ParamSpec(q + "self_attn.out_proj.bias", (D,), g, trainable=trainable),
+               ParamSpec(q + "mlp.fc1.weight", (inter, D), g, trainable=trainable),
+               ParamSpec(q + "mlp.fc1.bias", (inter,), g, trainable=trainable),
+               ParamSpec(q + "mlp.fc2.weight", (D, inter), g, trainable=trainable),
+               ParamSpec(q + "mlp.fc2.bias", (D,), g, trainable=trainable)]
+    sp += [ParamSpec(prefix + "post_layernorm.weight", (D,), g, trainable=trainable),
+           ParamSpec(prefix + "post_layernorm.bias", (D,), g, trainable=trainable)]
+    # multi-head attention pooling head: part of HF SiglipVisionModel's state dict, never on this path
+    h = prefix + "head."
+    sp += [ParamSpec(h + "probe", (1, 1, D), g, trainable=False),
+           ParamSpec(h + "attention.in_proj_weight", (3 * D, D), g, trainable=False),
+           ParamSpec(h + "attention.in_proj_bias", (3 * D,), g, trainable=False),
+           ParamSpec(h + "attention.out_proj.weight", (D, D), g, trainable=False),
+           ParamSpec(h + "attention.out_proj.bias", (D,), g, trainable=False),
+           ParamSpec(h + "layernorm.weight", (D,), g, trainable=False),
+           ParamSpec(h + "layernorm.bias", (D,), g, trainable=False),
+           ParamSpec(h + "mlp.fc1.weight", (inter, D), g, trainable=False),
+           ParamSpec(h + "mlp.fc1.bias", (inter,), g, trainable=False),
+           ParamSpec(h + "mlp.fc2.weight", (D, inter), g, trainable=False),
+           ParamSpec(h + "mlp.fc2.bias", (D,), g, trainable=False)]
+    return sp
+
+
+def gemma_specs(cfg, prefix: str, group: str, trainable: bool, embed_trainable: bool, skip_tail_of_last: bool):
+    """Gemma decoder parameters.  skip_tail_of_last: the prefix stream's last-layer o_proj / MLP / post-norm and the
+    final norm never influence the loss (only suffix_out is read, pi0_arch.py:386) -> frozen region, like the
+    reference where they simply receive no gradient."""
+    d, V = cfg_get(cfg, "hidden_size"), cfg_get(cfg, "vocab_size")
+    H, KVH = cfg_get(cfg, "num_attention_heads"), cfg_get(cfg, "num_key_value_heads")
+    hd = cfg_get(cfg, "head_dim") or d // H
+    inter, L = cfg_get(cfg, "intermediate_size"), cfg_get(cfg, "num_hidden_layers")
+    sp = [ParamSpec(prefix + "embed_tokens.weight", (V, d), group, trainable=embed_trainable, no_decay=False)]
+    for i in range(L):
+        q = f"{prefix}layers.{i}."
+        tail = trainable and not (skip_tail_of_last and i == L - 1)
+        sp.append(ParamSpec(q + "input_layernorm.weight", (d,), group, trainable=trainable))
+        sp.append(ParamSpec(q + "post_attention_layernorm.weight", (d,), group, trainable=tail))
+        for n, rows in (("q", H * hd), ("k", KVH * hd), ("v", KVH * hd)):
+            sp.append(ParamSpec(f"{q}self_attn.{n}_proj.weight", (rows, d), group, fuse=q + "qkvw", trainable=trainable))
+        sp.append(ParamSpec(q + "self_attn.o_proj.weight", (d, H * hd), group, trainable=tail))
+        sp.append(ParamSpec(q + "mlp.gate_proj.weight", (inter, d), group, trainable=tail))
+        sp.append(ParamSpec(q + "mlp.up_proj.weight", (inter, d), group, trainable=tail))
+        sp.append(ParamSpec(q + "mlp.down_proj.weight", (d, inter), group, trainable=tail))
+    sp.append(ParamSpec(prefix + "norm.weight", (d,), group, trainable=trainable and not skip_tail_of_last))
+    return sp
+
+
+# ----------------------------------------------------------------------------------- SigLIP
+class SiglipEmbedFn(torch.autograd.Function):
+    """HF SiglipVisionEmbeddings: conv(stride=patch, +bias) as im2col GEMM, + learned position embedding."""
+
+    @staticmethod
+    def forward(ctx, anchor, images, tower: "SiglipVisionTower"):
+        N = images.shape[0]
+        cols = ops.im2col_patches(images.contiguous(), tower.patch, tower.k_pad)
+        patches = ops.gemm(cols, tower.patch_w_pad, bias=tower.patch_b)
+        out = ops.add_pos_fwd(patches, tower.pos_w, N, tower.P)
+        ctx.save_for_backward(cols)
+        ctx.tower, ctx.N = tower, N
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (cols,) = ctx.saved_tensors
+        t, N = ctx.tower, ctx.N
+        st = t.store
+        if t.g_patch is None:
+            return None, None, None
+        dout = dout.contiguous()
+        d_pos = st.scratch_f32(t.P * t.D)
+        ops.add_pos_bwd(dout, d_pos, N, t.P)
+        st.accumulate_small(d_pos, t.g_pos)
+        sc = st.scratch_f32(t.D)
+        ops.colsum_(dout, sc)
+        st.accumulate_small(sc, t.g_patch_b)
+        dw_pad = ops.gemm(dout, cols, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        K = t.g_patch.numel() // t.D
+        ops.copy2d_(dw_pad, t.g_patch.view(t.D, K), t.D, K, accumulate=not st.first_write(t.g_patch))
+        return None, None, None
+
+
+class SiglipVisionTower:
+    """modules/mm_vision/siglip/siglip_encoder.py with select_layer=None: last_hidden_state (post-LN), no CLS."""
+
+    def __init__(self, store: ParamStore, cfg, prefix: str = "model.mm_vision_tower.vision_tower.vision_model."):
+        self.store, self.cfg, self.prefix = store, cfg, prefix
+        self.D, self.patch = cfg_get(cfg, "hidden_size"), cfg_get(cfg, "patch_size")
+        self.P = (cfg_get(cfg, "image_size") // self.patch) ** 2
+        self.C = cfg_get(cfg, "num_channels", 3)
+        heads, eps = cfg_get(cfg, "num_attention_heads"), cfg_get(cfg, "layer_norm_eps", 1e-6)
+        K = self.C * self.patch * self.patch
+        self.k_pad = (K + 7) // 8 * 8
+        p = prefix
+        self.patch_w_pad = torch.zeros((self.D, self.k_pad), device=store.device, dtype=torch.bfloat16)
+        self.g_patch = store.g(p + "embeddings.patch_embedding.weight")
+        self.patch_b, self.g_patch_b = store.w(p + "embeddings.patch_embedding.bias"), store.g(p + "embeddings.patch_embedding.bias")
+        self.pos_w, self.g_pos = store.w(p + "embeddings.position_embedding.weight"), store.g(p + "embeddings.position_embedding.weight")
+        bc = BlockCfg(d=self.D, heads=heads, kv_heads=heads, head_dim=self.D // heads,
+                      inter=cfg_get(cfg, "intermediate_size"), mlp="mlp",
+                      act=cfg_get(cfg, "hidden_act", "gelu_pytorch_tanh"), rope=False)
+        ln = lambda n: Norm("ln", eps, store.w(n + ".weight"), store.w(n + ".bias"), store.g(n + ".weight"), store.g(n + ".bias"))  # noqa: E731
+        self.blocks = []
+        for i in range(cfg_get(cfg, "num_hidden_layers")):
+            q = f"{p}encoder.layers.{i}."
+            self.blocks.append(BlockW(cfg=bc, norm1=ln(q + "layer_norm1"),
+                                      qkv=Lin.of(store, [f"{q}self_attn.{n}_proj.weight" for n in "qkv"],
+                                                 [f"{q}self_attn.{n}_proj.bias" for n in "qkv"]),
+                                      o=Lin.of(store, q + "self_attn.out_proj.weight", q + "self_attn.out_proj.bias"),
+                                      norm2=ln(q + "layer_norm2"),
+                                      fc1=Lin.of(store, q + "mlp.fc1.weight", q + "mlp.fc1.bias"),
+                                      fc2=Lin.of(store, q + "mlp.fc2.weight", q + "mlp.fc2.bias")))
+        self.post_ln = ln(p + "post_layernorm")
+
+    @property
+    def hidden_size(self):
+        return self.D
+
+    def refresh(self):
+        K = self.C * self.patch * self.patch
+        w = self.store.master_view(self.prefix + "embeddings.patch_embedding.weight").view(self.D, K)
+        ops.copy2d_(w, self.patch_w_pad, self.D, K)
+
+    def forward(self, anchor: _Anchor, images: torch.Tensor) -> torch.Tensor:
+        """[N,3,H,W] -> [N*P, D]"""
+        N = images.shape[0]
+        x = SiglipEmbedFn.apply(anchor.t, images, self)
+        env = AttnEnv(B=N, S=self.P)
+        for bw in self.blocks:
+            x = TransformerBlockFn.apply(x, bw, env, self.store, False)
+        return NormFn.apply(x, self.post_ln, self.store)
+
+
+# ------------------------------------------------------------------- mixture of transformers
+@dataclass
+class StreamW:
+    d: int
+    inter: int
+    norm1: Norm
+    qkv: Lin
+    o: Lin
+    norm2: Norm
+    gate: Lin
+    up: Lin
+    down: Lin
+
+
+@dataclass
+class MoTEnv:
+    B: int
+    lens: tuple            # (Sp, Ss)
+    heads: int
+    kv_heads: int
+    head_dim: int
+    act: str
+    keymask: torch.Tensor  # uint8 [B, S]
+    bid: torch.Tensor      # int32 [B, S]  cumsum(ar_mask)
+    pos: torch.Tensor      # int32 [B*S]
+    cos: torch.Tensor
+    sin: torch.Tensor
+
+
+def _stream_w(store: ParamStore, cfg, prefix: str, i: int) -> StreamW:
+    q = f"{prefix}layers.{i}."
+    eps = cfg_get(cfg, "rms_norm_eps", 1e-6)
+    rn = lambda n: Norm("rms1p", eps, store.w(n), None, store.g(n))  # noqa: E731  (GemmaRMSNorm: x * (1 + w))
+    return StreamW(d=cfg_get(cfg, "hidden_size"), inter=cfg_get(cfg, "intermediate_size"),
+                   norm1=rn(q + "input_layernorm.weight"),
+                   qkv=Lin.of(store, [f"{q}self_attn.{n}_proj.weight" for n in "qkv"]),
+                   o=Lin.of(store, q + "self_attn.o_proj.weight"), norm2=rn(q + "post_attention_layernorm.weight"),
+                   gate=Lin.of(store, q + "mlp.gate_proj.weight"), up=Lin.of(store, q + "mlp.up_proj.weight"),
+                   down=Lin.of(store, q + "mlp.down_proj.weight"))
+
+
+class MoTLayerFn(torch.autograd.Function):
+    """One joint layer of `_inner_forward_mot` (pi0_arch.py:131-216): per-stream norm + QKV, attention over the
+    concatenated sequence with shared RoPE, per-stream O / residual / norm / GeGLU MLP / residual.
+    `tail[t] = False` skips stream t's post-attention half (prefix stream of the last layer: its output is unused)."""
+
+    @staticmethod
+    def forward(ctx, x_p, x_s, streams, env: MoTEnv, store: ParamStore, tail):
+        B, (Sp, Ss) = env.B, env.lens
+        S = Sp + Ss
+        W = (env.heads + 2 * env.kv_heads) * env.head_dim
+        C = env.heads * env.head_dim
+        xs = (x_p, x_s)
+        joint = torch.empty((B, S, W), device=x_p.device, dtype=x_p.dtype)
+        st1 = []
+        off = 0
+        for x, sw, n in zip(xs, streams, (Sp, Ss)):
+            h, s1 = norm_fwd(x, sw.norm1)
+            st1.append(s1)
+            qkv, _ = linear_fwd(h, sw.qkv)
+            ops.copy3d_(qkv, joint, B, n, W, n * W, W, S * W, W, dst_off=off * W)
+            off += n
+        ops.rope_(joint, env.pos, env.cos, env.sin, env.heads + env.kv_heads, env.head_dim)
+        sh = ops.AttnShape(B, S, env.heads, env.kv_heads, env.head_dim, x_p.dtype)
+        attn, probs = ops.attention_fwd(joint, sh, keymask=env.keymask, bid_q=env.bid, bid_k=env.bid)
+        outs, keep = [], []
+        off = 0
+        for x, sw, n, has_tail in zip(xs, streams, (Sp, Ss), tail):
+            if not has_tail:
+                outs.append(torch.zeros(1, device=x.device, dtype=x.dtype))
+                keep.append(None)
+                off += n
+                continue
+            a = torch.empty((B * n, C), device=x.device, dtype=x.dtype)
+            ops.copy3d_(attn, a, B, n, C, S * C, C, n * C, C, src_off=off * C)
+            off += n
+            x1, _ = linear_fwd(a, sw.o, residual=x)
+            h2, s2 = norm_fwd(x1, sw.norm2)
+            g, _ = linear_fwd(h2, sw.gate)
+            u, _ = linear_fwd(h2, sw.up)
+            hm = ops.glu_fwd(g, u, env.act)
+            y, _ = linear_fwd(hm, sw.down, residual=x1)
+            outs.append(y)
+            keep.append(dict(a=a, x1=x1, s2=s2, g=g, u=u))
+        ctx.save_for_backward(x_p, x_s)
+        ctx.misc = (streams, env, store, tail, joint, probs, st1, keep, sh)
+        return outs[0], outs[1]
+
+    @staticmethod
+    def backward(ctx, dy_p, dy_s):
+        x_p, x_s = ctx.saved_tensors
+        streams, env, store, tail, joint, probs, st1, keep, sh = ctx.misc
+        ctx.misc = None
+        B, (Sp, Ss) = env.B, env.lens
+        S = Sp + Ss
+        W = (env.heads + 2 * env.kv_heads) * env.head_dim
+        C = env.heads * env.head_dim
+        dattn = torch.zeros((B, S, C), device=x_p.device, dtype=x_p.dtype)
+        dx1s = []
+        off = 0
+        for x, dy, sw, n, kp in zip((x_p, x_s), (dy_p, dy_s), streams, (Sp, Ss), keep):
+            if kp is None:                      # no post-attention half: nothing flows into this stream's attn rows
+                dx1s.append(None)
+                off += n
+                continue
+            dy = dy.contiguous() if dy._base is None and dy.is_contiguous() else dy.clone(memory_format=torch.contiguous_format)
+            h2, _ = norm_fwd(kp["x1"], sw.norm2)
+            dhm = linear_dgrad(dy, sw.down)
+            dg, du = ops.glu_bwd(dhm, kp["g"], kp["u"], env.act, dg=kp["g"], du=kp["u"], h_out=dhm)
+            linear_wgrad(store, dy, dhm, sw.down)
+            linear_wgrad(store, dg, h2, sw.gate)
+            linear_wgrad(store, du, h2, sw.up)
+            dh2 = linear_dgrad(dg, sw.gate)
+            linear_dgrad(du, sw.up, out=dh2, residual=dh2)
+            dx1 = norm_bwd(store, dh2, kp["x1"], sw.norm2, kp["s2"], dx=dy, accumulate_dx=True)
+            linear_wgrad(store, dx1, kp["a"], sw.o)
+            da = linear_dgrad(dx1, sw.o)
+            ops.copy3d_(da, dattn, B, n, C, n * C, C, S * C, C, dst_off=off * C)
+            dx1s.append(dx1)
+            off += n
+        dqkv = ops.attention_bwd(dattn, joint, probs, sh)
+        ops.rope_(dqkv, env.pos, env.cos, env.sin, env.heads + env.kv_heads, env.head_dim, inverse=True)
+        dxs = []
+        off = 0
+        for x, sw, n, s1, dx1 in zip((x_p, x_s), streams, (Sp, Ss), st1, dx1s):
+            dq = torch.empty((B * n, W), device=x.device, dtype=x.dtype)
+            ops.copy3d_(dqkv, dq, B, n, W, S * W, W, n * W, W, src_off=off * W)
+            off += n
+            h, _ = norm_fwd(x, sw.norm1)
+            linear_wgrad(store, dq, h, sw.qkv)
+            dh = linear_dgrad(dq, sw.qkv)
+            if dx1 is None:
+                dxs.append(norm_bwd(store, dh, x, sw.norm1, s1))
+            else:
+                dxs.append(norm_bwd(store, dh, x, sw.norm1, s1, dx=dx1, accumulate_dx=True))
+        return dxs[0], dxs[1], None, None, None, None
+
+
+class PrefixEmbedFn(torch.autograd.Function):
+    """embed_prefix (pi0_arch.py:235-269): [camera tokens ... | embed_tokens(ids) * sqrt(hidden)] per sample."""
+
+    @staticmethod
+    def forward(ctx, feats, ids32, table, g_table, store, B, n_cam, P, L):
+        D = table.shape[1]
+        Sp = n_cam * P + L
+        out = torch.empty((B * Sp, D), device=feats.device, dtype=feats.dtype)
+        for c in range(n_cam):       # feats rows are camera-major: (c*B + b)*P + p
+            ops.copy3d_(feats, out, B, P, D, P * D, D, Sp * D, D, src_off=c * B * P * D, dst_off=c * P * D)
+        text = ops.splice_gather(ids32, table, None)
+        ops.copy3d_(text, out, B, L, D, L * D, D, Sp * D, D, alpha=math.sqrt(D), dst_off=n_cam * P * D)
+        ctx.save_for_backward(ids32)
+        ctx.misc = (g_table, store, B, n_cam, P, L, D, feats.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids32,) = ctx.saved_tensors
+        g_table, store, B, n_cam, P, L, D, fshape = ctx.misc
+        Sp = n_cam * P + L
+        dout = dout.contiguous()
+        d_feats = torch.empty(fshape, device=dout.device, dtype=dout.dtype)
+        for c in range(n_cam):
+            ops.copy3d_(dout, d_feats, B, P, D, Sp * D, D, P * D, D, src_off=c * P * D, dst_off=c * B * P * D)
+        if g_table is not None:
+            d_text = torch.empty((B * L, D), device=dout.device, dtype=dout.dtype)
+            ops.copy3d_(dout, d_text, B, L, D, Sp * D, D, L * D, D, alpha=math.sqrt(D), src_off=n_cam * P * D)
+            ops.splice_scatter(ids32, d_text, g_table, None)
+        return d_feats, None, None, None, None, None, None, None, None
+
+
+def posemb_sincos(time: torch.Tensor, dim: int, min_period: float, max_period: float) -> torch.Tensor:
+    """pi0_arch.py:36-50 (float64 periods)."""
+    fraction = torch.linspace(0.0, 1.0, dim // 2, dtype=torch.float64, device=time.device)
+    period = min_period * (max_period / min_period) ** fraction
+    s = time[:, None].float() / period[None, :] * 2 * np.pi
+    return torch.cat([torch.sin(s), torch.cos(s)], dim=-1)
+
+
+class Pi0ForCausalLM(B200Module):
+    """pi0_arch.py:109-400 (training forward)."""
+    config_class = Pi0Config
+
+    def __init__(self, config: Pi0Config, device="cuda"):
+        super().__init__()
+        self.config = config
+        llm, exp, vis = config.llm_config, config.action_config, config.vision_config
+        d, w = cfg_get(llm, "hidden_size"), cfg_get(exp, "hidden_size")
+        A = config.action_dim
+        lin = lambda n, o, i: [ParamSpec(f"model.{n}.weight", (o, i), "action_head"),  # noqa: E731
+                               ParamSpec(f"model.{n}.bias", (o,), "action_head")]
+        specs = (gemma_specs(llm, "model.llm.", "llm", not config.freeze_llm, not config.freeze_llm, True)
+                 + siglip_specs(vis, trainable=not config.freeze_mm_vision)
+                 + [ParamSpec("model.mm_projector.weight", (d, cfg_get(vis, "hidden_size")), "projector",
+                              trainable=not config.freeze_mm_projector),
+                    ParamSpec("model.mm_projector.bias", (d,), "projector", trainable=not config.freeze_mm_projector)]
+                 # the expert's own embedding table is never used (pi0 feeds it the suffix embeddings)
+                 + gemma_specs(exp, "model.action_expert.", "action_head", True, False, False)
+                 + lin("state_proj", w, A) + lin("action_in_proj", w, A) + lin("action_time_mlp_in", w, 2 * w)
+                 + lin("action_time_mlp_out", w, w) + lin("action_out_proj", A, w))
+        store = self._materialize(specs, device)
+        self.anchor = _Anchor(store.device)
+        self.tower = SiglipVisionTower(store, vis)
+        self.proj = Lin.of(store, "model.mm_projector.weight", "model.mm_projector.bias")
+        self.embed_w = store.w("model.llm.embed_tokens.weight")
+        self.embed_g = store.g("model.llm.embed_tokens.weight")
+        if self.embed_g is not None:
+            store.mark_sparse_grad("model.llm.embed_tokens.weight")
+        L = cfg_get(llm, "num_hidden_layers")
+        assert L == cfg_get(exp, "num_hidden_layers")
+        self.layers = [(_stream_w(store, llm, "model.llm.", i), _stream_w(store, exp, "model.action_expert.", i))
+                       for i in range(L)]
+        self.expert_norm = Norm("rms1p", cfg_get(exp, "rms_norm_eps", 1e-6), store.w("model.action_expert.norm.weight"),
+                                None, store.g("model.action_expert.norm.weight"))
+        mk = lambda n: Lin.of(store, f"model.{n}.weight", f"model.{n}.bias")  # noqa: E731
+        self.state_proj, self.action_in, self.mlp_in = mk("state_proj"), mk("action_in_proj"), mk("action_time_mlp_in")
+        self.mlp_out, self.action_out = mk("action_time_mlp_out"), mk("action_out_proj")
+        self.H, self.KVH = cfg_get(llm, "num_attention_heads"), cfg_get(llm, "num_key_value_heads")
+        self.hd = cfg_get(llm, "head_dim") or d // self.H
+        self.act = cfg_get(llm, "hidden_act") or cfg_get(llm, "hidden_activation") or "gelu_pytorch_tanh"
+        self.theta = rope_theta_of(llm)
+        self._rope = None
+        self.d, self.w = d, w
+
+    def _after_weights_changed(self) -> None:
+        self.tower.refresh()
+
+    def _rope_tables(self, n_pos: int, device):
+        if self._rope is None or self._rope[0].shape[0] < n_pos:
+            n = max(n_pos, 1024)
+            inv = 1.0 / (self.theta ** (torch.arange(0, self.hd, 2, dtype=torch.float32, device=device) / self.hd))
+            f = torch.arange(n, dtype=torch.float32, device=device)[:, None] * inv[None, :]
+            self._rope = (f.cos().contiguous(), f.sin().contiguous())
+        return self._rope
+
+    def forward(self,
+                input_ids: torch.LongTensor = None,
+                attention_mask: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.LongTensor] = None,
+                past_key_values=None,
+                inputs_embeds: Optional[torch.FloatTensor] = None,
+                labels: Optional[torch.LongTensor] = None,
+                use_cache: Optional[bool] = None,
+                output_attentions: Optional[bool] = None,
+                output_hidden_states: Optional[bool] = None,
+                return_dict: Optional[bool] = None,
+                actions: Optional[torch.FloatTensor] = None,
+                states: Optional[torch.FloatTensor] = None,
+                images: Optional[torch.FloatTensor] = None,
+                cache_position: Optional[torch.LongTensor] = None,
+                repeated_diffusion_steps: int = 4,
+                image_masks: Optional[torch.BoolTensor] = None,
+                noise: Optional[torch.Tensor] = None,     # parity hooks: inject the reference's random draws
+                time: Optional[torch.Tensor] = None,
+                **kwargs) -> CausalLMOutputDexbotic:
+        if not actions.is_cuda:
+            raise RuntimeError("dexbotic_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        cfg, st, dev = self.config, self.store, actions.device
+        B, T, A = actions.shape[0], cfg.chunk_size, cfg.action_dim
+        actions = actions.float()
+        if noise is None:                                                     # pi0_arch.py:337-354
+            noise = torch.randn_like(actions)
+        if time is None:
+            time = torch.distributions.Beta(1.5, 1.0).sample((B,)).to(dev) * 0.999 + 0.001
+        te = time[:, None, None].float()
+        x_t = te * noise + (1 - te) * actions
+        u_t = noise - actions
+
+        # ---- embed_prefix: all cameras through SigLIP in one batch (camera-major), linear projector, text
+        n_cam, L = images.shape[1], input_ids.shape[1]
+        imgs = images.transpose(0, 1).reshape(n_cam * B, *images.shape[2:])
+        if self.tower.g_patch is None:
+            with torch.no_grad():
+                f = self.tower.forward(self.anchor, imgs)
+        else:
+            f = self.tower.forward(self.anchor, imgs)
+        f = LinearFn.apply(f, self.proj, None, st, self.tower.g_patch is not None, self.anchor.t)
+        P = self.tower.P
+        prefix = PrefixEmbedFn.apply(f, input_ids.to(torch.int32).contiguous(), self.embed_w, self.embed_g, st, B, n_cam,
+                                     P, L)
+        Sp = n_cam * P + L
+        prefix_mask = torch.cat([image_masks.bool()[:, :, None].expand(B, n_cam, P).reshape(B, n_cam * P),
+                                 attention_mask.bool()], dim=1)
+
+        # ---- embed_suffix (:271-315)
+        bf = torch.bfloat16
+        state_tok = LinearFn.apply(states.to(bf).contiguous(), self.state_proj, None, st, False, self.anchor.t)
+        a_tok = LinearFn.apply(x_t.to(bf).reshape(B * T, A).contiguous(), self.action_in, None, st, False, self.anchor.t)
+        temb = posemb_sincos(time, self.w, 4e-3, 4.0).to(bf)[:, None, :].expand(B, T, self.w)
+        at = torch.cat([a_tok.view(B, T, self.w), temb], dim=-1).reshape(B * T, 2 * self.w).contiguous()
+        at = LinearFn.apply(at, self.mlp_in, "silu", st, True, None)
+        at = LinearFn.apply(at, self.mlp_out, None, st, True, None)
+        suffix = torch.cat([state_tok.view(B, 1, self.w), at.view(B, T, self.w)], dim=1)
+        Ss = T + 1
+        suffix = suffix.reshape(B * Ss, self.w).contiguous()
+
+        # ---- joint attention environment (:365-370)
+        S = Sp + Ss
+        input_mask = torch.cat([prefix_mask, torch.ones(B, Ss, dtype=torch.bool, device=dev)], dim=1)
+        ar = torch.zeros(S, dtype=torch.int32, device=dev)
+        ar[Sp] = 1
+        ar[Sp + 1] = 1
+        bid = torch.cumsum(ar, 0).to(torch.int32)[None, :].expand(B, S).contiguous()
+        pos = (torch.cumsum(input_mask.to(torch.int32), dim=1) - 1).clamp_(min=0).to(torch.int32).reshape(-1).contiguous()
+        cos, sin = self._rope_tables(S + 1, dev)
+        env = MoTEnv(B=B, lens=(Sp, Ss), heads=self.H, kv_heads=self.KVH, head_dim=self.hd, act=self.act,
+                     keymask=input_mask.to(torch.uint8).contiguous(), bid=bid, pos=pos, cos=cos, sin=sin)
+        xp, xs = prefix, suffix
+        for i, streams in enumerate(self.layers):
+            last = i == len(self.layers) - 1
+            xp, xs = MoTLayerFn.apply(xp, xs, streams, env, st, (not last, True))
+        suffix_out = NormFn.apply(xs, self.expert_norm, st)
+        tail = suffix_out.view(B, Ss, self.w)[:, -T:].reshape(B * T, self.w).contiguous()
+        v_t = LinearFn.apply(tail, self.action_out, None, st, True, None)                   # :386
+        v32 = CastFn.apply(v_t, torch.float32).view(B, T, A)
+        loss = MSELossFn.apply(v32, u_t)                                                     # :387-388
+        return CausalLMOutputDexbotic(loss=loss, logits=v_t.view(B, T, A))
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.store.zero_grad()
+
+    def optimizer_step(self, base_lr: float = 2e-5, mm_projector_lr=None, mm_vision_lr=None, action_head_lr=None,
+                       betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, max_grad_norm=1.0):
+        lrs = {"llm": base_lr, "projector": mm_projector_lr or base_lr, "vision": mm_vision_lr or base_lr,
+               "action_head": action_head_lr or base_lr}
+        norm = self.store.adamw_step(lrs, betas, eps, weight_decay, max_grad_norm)
+        self.tower.refresh()
+        return norm

@@ -606,3 +606,29 @@ def copy2d_(src, dst, rows: int, cols: int, accumulate: bool = False):
     _lib.check(_lib.load().b200_copy2d(src.data_ptr(), dst.data_ptr(), rows, cols, src.stride(0), dst.stride(0),
                                        _dt(src), _dt(dst), int(accumulate), _stream()), "copy2d")
     return dst
+
+
+def copy3d_(src, dst, B: int, rows: int, cols: int, src_bs: int, src_ld: int, dst_bs: int, dst_ld: int,
+            alpha: float = 1.0, accumulate: bool = False, src_off: int = 0, dst_off: int = 0):
+    """dst[b, r, :cols] (+)= alpha * src[b, r, :cols]; offsets / strides in elements over the flat storage."""
+    _cuda(src, dst)
+    assert src.dtype == dst.dtype
+    es = src.element_size()
+    _lib.check(_lib.load().b200_copy3d(src.data_ptr() + src_off * es, dst.data_ptr() + dst_off * es, B, rows, cols,
+                                       src_bs, src_ld, dst_bs, dst_ld, float(alpha), int(accumulate), _dt(src),
+                                       _stream()), "copy3d")
+    return dst
+
+
+def add_pos_fwd(x, pos, B: int, P: int):
+    _cuda(x, pos)
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().b200_add_pos_fwd(x.data_ptr(), pos.data_ptr(), out.data_ptr(), B, P, x.shape[-1], _dt(x),
+                                            _stream()), "add_pos_fwd")
+    return out
+
+
+def add_pos_bwd(dout, d_pos_f32, B: int, P: int):
+    _cuda(dout, d_pos_f32)
+    _lib.check(_lib.load().b200_add_pos_bwd(dout.data_ptr(), d_pos_f32.data_ptr(), B, P, dout.shape[-1], _dt(dout),
+                                            _stream()), "add_pos_bwd")

@@ -141,6 +141,16 @@ int b200_vit_embed_bwd(const void* dout, void* d_patches, float* d_cls, float* d
 int b200_cast_add(const float* src, void* dst, int64_t n, int dst_dtype, int accumulate, void* stream);
 int b200_copy2d(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd, int src_dtype,
                 int dst_dtype, int accumulate, void* stream);
+/* dst[b, r, :cols] (+)= alpha * src[b, r, :cols] with independent batch / row strides (elements): moves row blocks
+ * between per-stream buffers and the joint [prefix | suffix] sequence of pi0's mixture-of-transformers layers
+ * (torch.cat / slicing in pi0_arch.py:163-165,196-206,258-262), alpha = sqrt(hidden) for the text embeddings. */
+int b200_copy3d(const void* src, void* dst, int64_t B, int64_t rows, int64_t cols, int64_t src_bs, int64_t src_ld,
+                int64_t dst_bs, int64_t dst_ld, float alpha, int accumulate, int dtype, void* stream);
+/* SigLIP embeddings: out[b,p] = patches[b,p] + position_embedding[p] (HF SiglipVisionEmbeddings via
+ * siglip_encoder.py:79-84); backward d_pos[p] += sum_b dout[b,p]. */
+int b200_add_pos_fwd(const void* x, const void* pos, void* out, int64_t B, int64_t P, int64_t D, int dtype,
+                     void* stream);
+int b200_add_pos_bwd(const void* dout, float* d_pos, int64_t B, int64_t P, int64_t D, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -233,8 +233,72 @@ def make_oft_discrete_tiny(seed: int = 4321):
     print("[oft_discrete_tiny] wrote fixture")
 
 
+def tiny_pi0_configs():
+    llm = dict(model_type="gemma", vocab_size=128, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+               num_attention_heads=4, num_key_value_heads=1, head_dim=16, rms_norm_eps=1e-6, rope_theta=10000.0,
+               hidden_act="gelu_pytorch_tanh")
+    exp = dict(llm, hidden_size=32, intermediate_size=64)
+    vis = dict(model_type="siglip_vision_model", hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+               num_attention_heads=2, image_size=28, patch_size=14, hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6)
+    return llm, exp, vis
+
+
+def make_pi0_tiny(seed: int = 2468):
+    llm, exp, vis = tiny_pi0_configs()
+    T, A = 10, 32
+    drop = ("rms_norm_eps", "rope_theta", "hidden_act", "layer_norm_eps")
+    model = ref_loader.build_reference_pi0({k: v for k, v in llm.items() if k not in drop},
+                                           {k: v for k, v in exp.items() if k not in drop},
+                                           {k: v for k, v in vis.items() if k not in drop}, A, T)
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    g = torch.Generator().manual_seed(seed)
+    B, L = 3, 12
+    ids = torch.randint(1, 128, (B, L), generator=g)
+    mask = torch.ones(B, L, dtype=torch.bool)
+    mask[1, 8:] = False
+    mask[2, 5:] = False
+    images = torch.randn(B, 3, 3, 28, 28, generator=g)
+    image_masks = torch.ones(B, 3, dtype=torch.bool)
+    image_masks[1, 2] = False
+    actions = torch.randn(B, T, A, generator=g)
+    states = torch.randn(B, A, generator=g)
+    # reference RNG order: torch.normal (pi0_arch.py:338-344) then Beta(1.5, 1).sample (:345-351)
+    torch.manual_seed(seed + 1)
+    out = model(input_ids=ids, attention_mask=mask, images=images, image_masks=image_masks, actions=actions,
+                states=states)
+    out.loss.backward()
+    torch.manual_seed(seed + 1)
+    noise = torch.normal(mean=torch.zeros_like(actions), std=torch.ones_like(actions))
+    time = torch.distributions.Beta(1.5, 1).sample((B,)) * 0.999 + 0.001
+    cfg = dict(llm=llm, expert=exp, vision=vis, chunk_size=T, action_dim=A)
+    ora = vla_oracle.pi0_forward(sd, cfg, ids, mask, images, image_masks, actions, states, noise, time)
+    d_loss = abs(ora["loss"].item() - out.loss.item())
+    d_v = (ora["v_t"] - out.logits).abs().max().item()
+    print(f"[pi0_tiny] reference loss {out.loss.item():.8f} oracle {ora['loss'].item():.8f}; v_t max|d|={d_v:.2e}")
+    assert d_loss < 1e-5 and d_v < 1e-4
+    names = ["model.llm.layers.0.self_attn.q_proj.weight", "model.llm.layers.1.mlp.gate_proj.weight",
+             "model.action_expert.layers.1.mlp.down_proj.weight", "model.action_expert.layers.0.self_attn.k_proj.weight",
+             "model.action_in_proj.weight", "model.action_time_mlp_in.weight", "model.action_out_proj.bias",
+             "model.state_proj.weight", "model.mm_projector.weight", "model.llm.embed_tokens.weight",
+             "model.mm_vision_tower.vision_tower.vision_model.encoder.layers.0.mlp.fc1.weight",
+             "model.mm_vision_tower.vision_tower.vision_model.embeddings.patch_embedding.weight",
+             "model.action_expert.norm.weight"]
+    params = dict(model.named_parameters())
+    grads = {n: params[n].grad.clone() for n in names if params[n].grad is not None}
+    none_grad = sorted(n for n, p in params.items() if p.grad is None)
+    torch.save(dict(seed=seed, cfg=cfg, shapes={k: tuple(v.shape) for k, v in sd.items()},
+                    inputs=dict(input_ids=ids, attention_mask=mask, images=images, image_masks=image_masks,
+                                actions=actions, states=states, noise=noise, time=time),
+                    outputs=dict(loss=out.loss.detach(), v_t=out.logits.detach(), grads=grads, none_grad=none_grad)),
+               GOLDEN / "pi0_tiny.pt")
+    print("[pi0_tiny] wrote fixture; params without grad:", none_grad[:6], len(none_grad))
+
+
 if __name__ == "__main__":
     make_cogact_tiny()
+    make_pi0_tiny()
     make_oft_discrete_tiny()
     make_splice_cases()
     make_integer_kats()

@@ -192,3 +192,53 @@ def build_reference_oft_discrete(llm_config, clip_config, action_dim: int = 7, c
                             action_model_type="Discrete", action_dim=action_dim, chunk_size=chunk_size,
                             use_proprio=False, proprio_dim=None, num_bins=num_bins)
     return OFTDiscreteForCausalLM(cfg)
+
+
+_pi0_loaded = False
+
+
+def load_reference_pi0():
+    """pi0_arch.py needs the same dataclass-default patch (Pi0Config's annotated fields) and a SigLIP tower
+    that is built from a config object (no image processor / weights download)."""
+    global _pi0_loaded
+    load_reference()
+    if _pi0_loaded:
+        return sys.modules["dexbotic.model.pi0.pi0_arch"]
+    from transformers import SiglipVisionModel
+    from dexbotic.model.modules.mm_vision.siglip import siglip_encoder
+
+    def siglip_load_model(self):
+        if self.is_loaded:
+            return
+        self.image_processor = None
+        self.vision_tower = SiglipVisionModel(self.vision_tower_config)
+        self.is_loaded = True
+
+    siglip_encoder.SiglipVisionTower.load_model = siglip_load_model
+    import dexbotic.model.pi0  # noqa: F401
+    mod = _exec_patched("dexbotic.model.pi0.pi0_arch", "dexbotic/model/pi0/pi0_arch.py",
+                        [("    vision_config: dict | str\n", "    vision_config: dict | str = None\n"),
+                         ("    processor_config: str\n", "    processor_config: str = None\n"),
+                         ("    action_config: dict | str\n", "    action_config: dict | str = None\n")])
+    _pi0_loaded = True
+    return mod
+
+
+def build_reference_pi0(llm_config: dict, action_config: dict, vision_config: dict, action_dim: int = 32,
+                        chunk_size: int = 50):
+    """Reference Pi0ForCausalLM (pi0_arch.py:109-114) with random-init weights; configs are plain dicts with a
+    `model_type` key (Pi0Config resolves them through CONFIG_MAPPING, pi0_arch.py:61-83)."""
+    mod = load_reference_pi0()
+    cfg = mod.Pi0Config(llm_config=llm_config, action_config=action_config, vision_config=vision_config,
+                        processor_config="unused", mm_projector_type="linear", action_dim=action_dim,
+                        chunk_size=chunk_size)
+    model = mod.Pi0ForCausalLM(cfg)
+    # Version artifact, neutralised: under the reference's pinned transformers (4.51.0 / 4.54.0, Dockerfile:37,
+    # Dockerfile.c130t28:22) GemmaModel.embed_tokens is a plain nn.Embedding and pi0_arch.py:258-261 applies the
+    # sqrt(hidden) scale itself; transformers 5.5.0 (this image) moved that scale INTO the embedding module
+    # (GemmaTextScaledWordEmbedding), which would apply it twice.  Reset the in-module scale to 1 so the run here
+    # computes what the pinned reference computes.
+    for m in (model.model.llm, model.model.action_expert):
+        if hasattr(m.embed_tokens, "embed_scale"):
+            m.embed_tokens.embed_scale.fill_(1.0)
+    return model

@@ -381,3 +381,121 @@ def oft_discrete_forward(sd, cfg: dict, input_ids, attention_mask, images, label
     if action_labels is not None:
         loss = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), action_labels.reshape(-1), reduction="mean")
     return dict(loss=loss, logits=logits, action_labels=action_labels, action_hidden=ah)
+
+
+# ----------------------------------------------------------------------------------------------
+# pi0 — dexbotic/model/pi0/pi0_arch.py (SigLIP tower: modules/mm_vision/siglip/siglip_encoder.py:61-86)
+# ----------------------------------------------------------------------------------------------
+def siglip_vision_features(sd, prefix: str, images: torch.Tensor, cfg: dict) -> torch.Tensor:
+    """HF SiglipVisionModel(...).last_hidden_state (select_layer=None, siglip_encoder.py:62-63): conv(+bias) patchify,
+    learned position embedding, pre-LN encoder with gelu_tanh MLP, post_layernorm.  No CLS token."""
+    p = prefix + "vision_tower.vision_model."
+    patch, heads, eps = cfg["patch_size"], cfg["num_attention_heads"], cfg.get("layer_norm_eps", 1e-6)
+    act = ACT[cfg.get("hidden_act", "gelu_pytorch_tanh")]
+    x = F.conv2d(images, sd[p + "embeddings.patch_embedding.weight"], sd[p + "embeddings.patch_embedding.bias"],
+                 stride=patch).flatten(2).transpose(1, 2)
+    x = x + sd[p + "embeddings.position_embedding.weight"][None]
+    D = x.shape[-1]
+    for i in range(cfg["num_hidden_layers"]):
+        q = f"{p}encoder.layers.{i}."
+        h = F.layer_norm(x, (D,), sd[q + "layer_norm1.weight"], sd[q + "layer_norm1.bias"], eps)
+        x = x + _mha(h, sd[q + "self_attn.q_proj.weight"], sd[q + "self_attn.q_proj.bias"],
+                     sd[q + "self_attn.k_proj.weight"], sd[q + "self_attn.k_proj.bias"],
+                     sd[q + "self_attn.v_proj.weight"], sd[q + "self_attn.v_proj.bias"],
+                     sd[q + "self_attn.out_proj.weight"], sd[q + "self_attn.out_proj.bias"], heads)
+        h = F.layer_norm(x, (D,), sd[q + "layer_norm2.weight"], sd[q + "layer_norm2.bias"], eps)
+        x = x + F.linear(act(F.linear(h, sd[q + "mlp.fc1.weight"], sd[q + "mlp.fc1.bias"])),
+                         sd[q + "mlp.fc2.weight"], sd[q + "mlp.fc2.bias"])
+    return F.layer_norm(x, (D,), sd[p + "post_layernorm.weight"], sd[p + "post_layernorm.bias"], eps)
+
+
+def posemb_sincos(position: torch.Tensor, dim: int, min_period: float, max_period: float) -> torch.Tensor:
+    """pi0_arch.py:36-50 (float64 periods; returns float64)."""
+    fraction = torch.linspace(0.0, 1.0, dim // 2, dtype=torch.float64)
+    period = min_period * (max_period / min_period) ** fraction
+    s = position[:, None].float() / period[None, :] * 2 * np.pi
+    return torch.cat([torch.sin(s), torch.cos(s)], dim=-1)
+
+
+def pi0_make_attn_mask(input_mask: torch.Tensor, ar_mask: torch.Tensor) -> torch.Tensor:
+    """pi0_arch.py:22-29: attend iff cumsum(ar)[k] <= cumsum(ar)[q], both positions valid."""
+    cs = torch.cumsum(ar_mask.broadcast_to(input_mask.shape).long(), dim=1)
+    allow = cs[:, None, :] <= cs[:, :, None]
+    valid = input_mask[:, None, :] & input_mask[:, :, None]
+    return allow & valid
+
+
+def pi0_forward(sd, cfg: dict, input_ids, attention_mask, images, image_masks, actions, states, noise, time):
+    """Pi0ForCausalLM.forward (pi0_arch.py:317-400) with injected noise [B,T,A] and time [B].
+    Returns dict(loss, v_t, u_t, suffix_out, prefix_tokens, input_mask)."""
+    L, E, V = cfg["llm"], cfg["expert"], cfg["vision"]
+    T = cfg["chunk_size"]
+    B = actions.shape[0]
+    te = time[:, None, None]
+    x_t = te * noise + (1 - te) * actions
+    u_t = noise - actions
+    # embed_prefix (:235-269): cameras one by one, then text * sqrt(hidden)
+    toks, masks = [], []
+    for c in range(images.shape[1]):
+        f = siglip_vision_features(sd, "model.mm_vision_tower.", images[:, c], V)
+        f = F.linear(f, sd["model.mm_projector.weight"], sd["model.mm_projector.bias"])
+        toks.append(f)
+        masks.append(image_masks[:, c][:, None].expand(B, f.shape[1]))
+    toks.append(sd["model.llm.embed_tokens.weight"][input_ids] * L["hidden_size"] ** 0.5)
+    masks.append(attention_mask.bool())
+    prefix = torch.cat(toks, dim=1)
+    prefix_mask = torch.cat(masks, dim=1)
+    # embed_suffix (:271-315)
+    w = E["hidden_size"]
+    state_tok = F.linear(states, sd["model.state_proj.weight"], sd["model.state_proj.bias"])[:, None]
+    temb = posemb_sincos(time, w, 4e-3, 4.0)[:, None].expand(B, T, w)
+    a_tok = F.linear(x_t, sd["model.action_in_proj.weight"], sd["model.action_in_proj.bias"])
+    at = torch.cat([a_tok, temb.to(a_tok.dtype)], dim=-1)
+    at = F.linear(F.silu(F.linear(at, sd["model.action_time_mlp_in.weight"], sd["model.action_time_mlp_in.bias"])),
+                  sd["model.action_time_mlp_out.weight"], sd["model.action_time_mlp_out.bias"])
+    suffix = torch.cat([state_tok, at], dim=1)
+    Sp, Ss = prefix.shape[1], suffix.shape[1]
+    input_mask = torch.cat([prefix_mask, torch.ones(B, Ss, dtype=torch.bool)], dim=1)
+    ar = torch.tensor([False] * Sp + [True, True] + [False] * (T - 1))
+    allow = pi0_make_attn_mask(input_mask, ar)[:, None]                      # [B,1,S,S]
+    positions = torch.cumsum(input_mask.long(), dim=1) - 1
+    H, KVH, hd = L["num_attention_heads"], L["num_key_value_heads"], L["head_dim"]
+    cos, sin = rope_tables(positions, hd, L.get("rope_theta", 10000.0))
+    c, s = cos[:, None], sin[:, None]
+    xs = [prefix, suffix]
+    prefixes = ["model.llm.", "model.action_expert."]
+    cfgs = [L, E]
+    for li in range(L["num_hidden_layers"]):                                  # _inner_forward_mot (:116-228)
+        qs, ks, vs = [], [], []
+        for x, pf, cc in zip(xs, prefixes, cfgs):
+            q = f"{pf}layers.{li}."
+            h = rms_norm(x, sd[q + "input_layernorm.weight"], cc["rms_norm_eps"], unit_offset=True)
+            n = h.shape[1]
+            qs.append(F.linear(h, sd[q + "self_attn.q_proj.weight"]).view(B, n, H, hd).transpose(1, 2))
+            ks.append(F.linear(h, sd[q + "self_attn.k_proj.weight"]).view(B, n, KVH, hd).transpose(1, 2))
+            vs.append(F.linear(h, sd[q + "self_attn.v_proj.weight"]).view(B, n, KVH, hd).transpose(1, 2))
+        qh, kh, vh = torch.cat(qs, dim=2), torch.cat(ks, dim=2), torch.cat(vs, dim=2)
+        qh = qh * c + rotate_half(qh) * s
+        kh = kh * c + rotate_half(kh) * s
+        G = H // KVH
+        sc = (qh @ kh.repeat_interleave(G, dim=1).transpose(-1, -2)) * hd ** -0.5
+        sc = sc + torch.where(allow, 0.0, -2.3819763e38)
+        p = torch.softmax(sc.float(), dim=-1)
+        o = (p @ vh.repeat_interleave(G, dim=1)).transpose(1, 2).reshape(B, Sp + Ss, H * hd)
+        outs, start = [], 0
+        for x, pf, cc in zip(xs, prefixes, cfgs):
+            q = f"{pf}layers.{li}."
+            n = x.shape[1]
+            a = F.linear(o[:, start:start + n], sd[q + "self_attn.o_proj.weight"])
+            start += n
+            r = x + a
+            h = rms_norm(r, sd[q + "post_attention_layernorm.weight"], cc["rms_norm_eps"], unit_offset=True)
+            act = ACT[cc.get("hidden_act", "gelu_pytorch_tanh")]
+            m = F.linear(act(F.linear(h, sd[q + "mlp.gate_proj.weight"])) * F.linear(h, sd[q + "mlp.up_proj.weight"]),
+                         sd[q + "mlp.down_proj.weight"])
+            outs.append(r + m)
+        xs = outs
+    suffix_out = rms_norm(xs[1], sd["model.action_expert.norm.weight"], E["rms_norm_eps"], unit_offset=True)
+    v_t = F.linear(suffix_out[:, -T:], sd["model.action_out_proj.weight"], sd["model.action_out_proj.bias"])
+    loss = ((v_t - u_t) ** 2).mean()
+    return dict(loss=loss, v_t=v_t, u_t=u_t, suffix_out=suffix_out, prefix_tokens=prefix, input_mask=input_mask)

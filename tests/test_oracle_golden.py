@@ -81,3 +81,27 @@ def test_oft_discrete_tiny_matches_reference():
     assert np.array_equal(idx, fx["outputs"]["infer_idx"].numpy())
     cont = vla_oracle.oft_bins_to_continuous(idx).reshape(idx.shape[0], 8, 7)
     assert np.array_equal(cont, fx["outputs"]["infer_cont"].numpy())
+
+
+def test_pi0_tiny_matches_reference():
+    fx = torch.load(GOLDEN / "pi0_tiny.pt", weights_only=False)
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    i = fx["inputs"]
+    out = vla_oracle.pi0_forward(sd, fx["cfg"], i["input_ids"], i["attention_mask"], i["images"], i["image_masks"],
+                                 i["actions"], i["states"], i["noise"], i["time"])
+    assert abs(out["loss"].item() - fx["outputs"]["loss"].item()) < 1e-5
+    assert (out["v_t"] - fx["outputs"]["v_t"]).abs().max().item() < 1e-4
+
+
+def test_pi0_attn_mask_truth_table():
+    """make_attn_mask (pi0_arch.py:22-33): prefix bidirectional, state token sees prefix + itself, action tokens see
+    prefix + state + each other; invalid positions neither attend nor are attended."""
+    input_mask = torch.tensor([[True, True, False, True, True, True]])
+    ar = torch.tensor([False, False, False, True, True, False])
+    m = vla_oracle.pi0_make_attn_mask(input_mask, ar)[0].int().tolist()
+    assert m == [[1, 1, 0, 0, 0, 0],
+                 [1, 1, 0, 0, 0, 0],
+                 [0, 0, 0, 0, 0, 0],
+                 [1, 1, 0, 1, 0, 0],
+                 [1, 1, 0, 1, 1, 1],
+                 [1, 1, 0, 1, 1, 1]]
