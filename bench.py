@@ -33,6 +33,20 @@ WORKLOADS = {
         vision=dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
                     image_size=224, patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5),
         action_model_type="DiT-S", action_dim=7, chunk_size=16, batch=32, instr_tokens=32, template_tokens=20),
+    # BASELINE.json configs[2] (pi0: SigLIP-So400m + Gemma-2B + flow-matching action expert), per-GPU share of the
+    # global batch 64 on 8 GPUs; ONE training forward per sample ("50" is the action horizon)
+    "pi0_2b": dict(
+        kind="pi0",
+        llm=dict(model_type="gemma", vocab_size=257152, hidden_size=2048, intermediate_size=16384, num_hidden_layers=18,
+                 num_attention_heads=8, num_key_value_heads=1, head_dim=256, rms_norm_eps=1e-6, rope_theta=10000.0,
+                 hidden_act="gelu_pytorch_tanh"),
+        expert=dict(model_type="gemma", vocab_size=257152, hidden_size=1024, intermediate_size=4096,
+                    num_hidden_layers=18, num_attention_heads=8, num_key_value_heads=1, head_dim=256, rms_norm_eps=1e-6,
+                    rope_theta=10000.0, hidden_act="gelu_pytorch_tanh"),
+        vision=dict(model_type="siglip_vision_model", hidden_size=1152, intermediate_size=4304, num_hidden_layers=27,
+                    num_attention_heads=16, image_size=224, patch_size=14, hidden_act="gelu_pytorch_tanh",
+                    layer_norm_eps=1e-6),
+        action_dim=32, chunk_size=50, batch=8, n_cam=3, text_tokens=48),
     # small stand-in with the same structure for smoke tests / CPU-only debugging of the harness
     "cogact_tiny": dict(
         llm=dict(model_type="qwen2", vocab_size=1024, hidden_size=256, intermediate_size=704, num_hidden_layers=2,
@@ -43,8 +57,26 @@ WORKLOADS = {
 }
 
 
+def _gemma_flops(c: dict, n_tok: int, S_attn: int) -> float:
+    d, I, nl, H, KV, hd = (c["hidden_size"], c["intermediate_size"], c["num_hidden_layers"], c["num_attention_heads"],
+                           c["num_key_value_heads"], c["head_dim"])
+    return nl * (2 * n_tok * (d * H * hd + 2 * d * KV * hd + H * hd * d + 3 * d * I) + 4 * n_tok * S_attn * H * hd)
+
+
+def pi0_flops_per_sample(w: dict) -> float:
+    V = w["vision"]
+    dv, mv, lv = V["hidden_size"], V["intermediate_size"], V["num_hidden_layers"]
+    P = (V["image_size"] // V["patch_size"]) ** 2
+    vit = w["n_cam"] * lv * (2 * P * (4 * dv * dv + 2 * dv * mv) + 4 * P * P * dv)
+    Sp, Ss = w["n_cam"] * P + w["text_tokens"], w["chunk_size"] + 1
+    proj = 2 * w["n_cam"] * P * dv * w["llm"]["hidden_size"]
+    return 3.0 * (vit + proj + _gemma_flops(w["llm"], Sp, Sp + Ss) + _gemma_flops(w["expert"], Ss, Sp + Ss))
+
+
 def train_flops_per_sample(w: dict, S: int) -> float:
     """Algorithmic FLOPs (2*MACs; training = 3x forward; recompute NOT counted) — SURVEY.md §8(d) formulae."""
+    if w.get("kind") == "pi0":
+        return pi0_flops_per_sample(w)
     L = w["llm"]
     d, I, nl = L["hidden_size"], L["intermediate_size"], L["num_hidden_layers"]
     H, KV = L["num_attention_heads"], L["num_key_value_heads"]
@@ -66,6 +98,17 @@ def make_batch(w: dict, rank: int, pinned: bool):
     import torch
     g = torch.Generator().manual_seed(1234 + rank)
     B = w["batch"]
+    if w.get("kind") == "pi0":
+        L, V, img = w["text_tokens"], w["llm"]["vocab_size"], w["vision"]["image_size"]
+        ids = torch.randint(1, min(30000, V), (B, L), generator=g)
+        n_real = torch.randint(8, 41, (B,), generator=g)
+        mask = torch.arange(L)[None, :] < n_real[:, None]
+        ids = ids * mask
+        batch = dict(input_ids=ids, attention_mask=mask, images=torch.randn(B, w["n_cam"], 3, img, img, generator=g),
+                     image_masks=torch.ones(B, w["n_cam"], dtype=torch.bool),
+                     actions=torch.randn(B, w["chunk_size"], w["action_dim"], generator=g),
+                     states=torch.randn(B, w["action_dim"], generator=g))
+        return {k: v.pin_memory() for k, v in batch.items()} if pinned else batch
     L = 2 + w["instr_tokens"] + w["template_tokens"]
     V = w["llm"]["vocab_size"]
     ids = torch.randint(1000 if V > 40000 else 1, min(30000, V), (B, L), generator=g)
@@ -192,9 +235,16 @@ def run_ours(args) -> dict:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     w = WORKLOADS[args.workload]
-    cfg = CogActConfig(llm_config=w["llm"], mm_vision_tower=w["vision"], mm_projector_type="mlp2x_gelu",
-                       action_model_type=w["action_model_type"], action_dim=w["action_dim"], chunk_size=w["chunk_size"])
-    model = CogACTForCausalLM(cfg, device=dev)
+    if w.get("kind") == "pi0":
+        from dexbotic_b200.model import Pi0Config, Pi0ForCausalLM
+        cfg = Pi0Config(llm_config=w["llm"], action_config=w["expert"], vision_config=w["vision"],
+                        action_dim=w["action_dim"], chunk_size=w["chunk_size"])
+        model = Pi0ForCausalLM(cfg, device=dev)
+    else:
+        cfg = CogActConfig(llm_config=w["llm"], mm_vision_tower=w["vision"], mm_projector_type="mlp2x_gelu",
+                           action_model_type=w["action_model_type"], action_dim=w["action_dim"],
+                           chunk_size=w["chunk_size"])
+        model = CogACTForCausalLM(cfg, device=dev)
     model.init_weights_(seed=1234)          # same seeded random init on every rank (no checkpoints offline)
     model.train()
     host = make_batch(w, rank, pinned=True)
@@ -248,6 +298,8 @@ def run_ours(args) -> dict:
     for _ in range(max(args.warmup, 3)):
         out = step(resident)
         S = out.logits.shape[1]
+    if w.get("kind") == "pi0":
+        S = w["n_cam"] * (w["vision"]["image_size"] // w["vision"]["patch_size"]) ** 2 + w["text_tokens"] + w["chunk_size"] + 1
     gt = GemmTimer()
     gt.install()
     sampler = ClockSampler(local)
@@ -264,15 +316,24 @@ def run_ours(args) -> dict:
     e2e = B * world * args.steps / (ms_e2e * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    traffic = None
+    tp = ROOT / "profiles" / "r1_gemm_traffic.json"
+    if tp.exists():       # dram__bytes_read+write of one `ncu --set full` capture of the dominant kernel (committed)
+        traffic = json.loads(tp.read_text())
     achieved_tf = gemm_flops / gemm_s / 1e12 if gemm_s > 0 else 0.0
     res = {
         "metric": METRIC, "value": round(value, 3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: CogACT ViT-L/14@224 + Qwen2.5-7B-shaped decoder + "
-                               f"{w['action_model_type']}, batch={B}/GPU, S={S}, random-init weights, AdamW + clip, "
-                               f"{model.model_engine.llm.keep_layers}/{len(model.model_engine.llm.blocks)} decoder blocks keep activations (rest recompute); inputs (19 MB/step) << L2 but weights+grads+moments "
-                               "(>120 GB/step) stream through HBM every step, so L2 is cold for the timed kernels",
+        "config": {"workload": (f"{args.workload}: pi0 SigLIP-So400m x{w['n_cam']} cams + Gemma-2B + 300M action expert, "
+                                f"chunk {w['chunk_size']}, batch={B}/GPU, joint S={S}, random-init weights, AdamW + clip; "
+                                "no recompute;" if w.get("kind") == "pi0" else
+                                f"{args.workload}: CogACT ViT-L/14@224 + Qwen2.5-7B-shaped decoder + "
+                                f"{w['action_model_type']}, batch={B}/GPU, S={S}, random-init weights, AdamW + clip, "
+                                f"{model.model_engine.llm.keep_layers}/{len(model.model_engine.llm.blocks)} decoder "
+                                "blocks keep activations (rest recompute);") +
+                               " inputs << L2 but weights+grads+moments stream through HBM every step "
+                               "(>120 GB for the 7B model), so L2 is cold for the timed kernels",
                    "global_batch": B * world, "seq_len": S, "parallelism": f"dp{world}",
                    "train_tflop_per_sample": round(flops_sample / 1e12, 3)},
         "e2e": {"value": round(e2e, 3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -280,7 +341,7 @@ def run_ours(args) -> dict:
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": round(achieved_tf, 1), "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": round(achieved_tf / peak_tf, 4) if peak_tf else None, "traffic": None,
+                     "frac": round(achieved_tf / peak_tf, 4) if peak_tf else None, "traffic": traffic,
                      "kernel": "gemm_tcgen05_kernel", "launches_timed": gemm_n,
                      "peak_source": f"{peak_src} (bf16_tflops_sustained)",
                      "gemm_share_of_step": round(gemm_s / (ms_dev * 1e-3), 4),
