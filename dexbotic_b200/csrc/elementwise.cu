@@ -11,6 +11,12 @@ namespace b200 {
 using bf16 = __nv_bfloat16;
 constexpr int kMaxPacks = 4;  // packs of 8 columns per thread kept in registers (D <= 8 * 256 * 4)
 
+// threads per row-block for the norm kernels: ~2 packs of 8 columns per thread, 64..256 threads
+static inline int norm_threads(int64_t D) {
+  int64_t t = ((D / 8 + 1) / 2 + 31) / 32 * 32;
+  return (int)(t < 64 ? 64 : (t > 256 ? 256 : t));
+}
+
 static inline int grid_for_rows(int64_t rows, int per_sm = 8) {
   int64_t g = (int64_t)num_sms() * per_sm;
   return (int)(rows < g ? rows : g);
@@ -47,38 +53,46 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const T* __restrict__ 
   }
 }
 
-// dx = r*g - x*r^3*mean(g.x),  g = dy*w_eff ;  dw[col] += sum_rows dy * x * r   (fp32 atomics)
+// dx = r*g - x*r^3*mean(g.x),  g = dy*w_eff ;  dw[col] += sum_rows dy * x * r.
+// x / dy are read once per row (kept in registers between the two phases).  dw partials go to a per-block row of
+// `ws` (no atomics; reduced by colsum afterwards) when a workspace is given, else fp32 atomics.
 template <typename T>
-__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
-                                                          const T* __restrict__ w, const float* __restrict__ rstd,
-                                                          T* __restrict__ dx, float* __restrict__ dw, int M, int D,
-                                                          int unit_offset, int accumulate_dx) {
+__global__ void __launch_bounds__(256, 4) rmsnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                             const T* __restrict__ w, const float* __restrict__ rstd,
+                                                             T* dx, float* __restrict__ dw, float* __restrict__ ws,
+                                                             int M, int D, int unit_offset, int accumulate_dx) {
   __shared__ float red[33];
-  float wacc[kMaxPacks][8];
+  float wacc[kMaxPacks][8], we[kMaxPacks][8];
 #pragma unroll
-  for (int k = 0; k < kMaxPacks; ++k)
+  for (int k = 0; k < kMaxPacks; ++k) {
+    const int i = (threadIdx.x + k * blockDim.x) * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) wacc[k][j] = 0.0f;
-
+    if (i < D) {
+      Pack8<T>::load(w + i, we[k]);
+      if (unit_offset) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) we[k][j] += 1.0f;
+      }
+    }
+  }
   for (int row = blockIdx.x; row < M; row += gridDim.x) {
     const T* xr = x + (size_t)row * D;
     const T* dyr = dy + (size_t)row * D;
     T* dxr = dx + (size_t)row * D;
     const float r = rstd[row];
+    float xv[kMaxPacks][8], dv[kMaxPacks][8];
     float c = 0.0f;
 #pragma unroll
     for (int k = 0; k < kMaxPacks; ++k) {
       const int i = (threadIdx.x + k * blockDim.x) * 8;
       if (i < D) {
-        float xv[8], dv[8], wv[8];
-        Pack8<T>::load(xr + i, xv);
-        Pack8<T>::load(dyr + i, dv);
-        Pack8<T>::load(w + i, wv);
+        Pack8<T>::load(xr + i, xv[k]);
+        Pack8<T>::load(dyr + i, dv[k]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float we = unit_offset ? 1.0f + wv[j] : wv[j];
-          c += dv[j] * we * xv[j];
-          wacc[k][j] += dv[j] * xv[j] * r;
+          c += dv[k][j] * we[k][j] * xv[k][j];
+          wacc[k][j] += dv[k][j] * xv[k][j] * r;
         }
       }
     }
@@ -88,15 +102,11 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const T* __restrict__ 
     for (int k = 0; k < kMaxPacks; ++k) {
       const int i = (threadIdx.x + k * blockDim.x) * 8;
       if (i < D) {
-        float xv[8], dv[8], wv[8], o[8];
-        Pack8<T>::load(xr + i, xv);
-        Pack8<T>::load(dyr + i, dv);
-        Pack8<T>::load(w + i, wv);
+        float o[8];
         if (accumulate_dx) Pack8<T>::load(dxr + i, o);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float we = unit_offset ? 1.0f + wv[j] : wv[j];
-          const float t = r * dv[j] * we - xv[j] * coef;
+          const float t = r * dv[k][j] * we[k][j] - xv[k][j] * coef;
           o[j] = accumulate_dx ? o[j] + t : t;
         }
         Pack8<T>::store(dxr + i, o);
@@ -108,8 +118,12 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const T* __restrict__ 
     for (int k = 0; k < kMaxPacks; ++k) {
       const int i = (threadIdx.x + k * blockDim.x) * 8;
       if (i < D) {
+        if (ws != nullptr) {
+          Pack8<float>::store(ws + (size_t)blockIdx.x * D + i, wacc[k]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(dw + i + j, wacc[k][j]);
+          for (int j = 0; j < 8; ++j) atomicAdd(dw + i + j, wacc[k][j]);
+        }
       }
     }
   }
@@ -164,39 +178,45 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
-                                                            const T* __restrict__ w, const float* __restrict__ mean,
-                                                            const float* __restrict__ rstd, T* __restrict__ dx,
-                                                            float* __restrict__ dw, float* __restrict__ db, int M,
-                                                            int D, int accumulate_dx) {
+__global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                               const T* __restrict__ w, const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, T* dx,
+                                                               float* __restrict__ dw, float* __restrict__ db,
+                                                               float* __restrict__ ws, int M, int D,
+                                                               int accumulate_dx) {
   __shared__ float red[33];
-  float wacc[kMaxPacks][8], bacc[kMaxPacks][8];
+  float wacc[kMaxPacks][8], bacc[kMaxPacks][8], wv[kMaxPacks][8];
 #pragma unroll
-  for (int k = 0; k < kMaxPacks; ++k)
+  for (int k = 0; k < kMaxPacks; ++k) {
+    const int i = (threadIdx.x + k * blockDim.x) * 8;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) wacc[k][j] = bacc[k][j] = 0.0f;
-
+    for (int j = 0; j < 8; ++j) {
+      wacc[k][j] = bacc[k][j] = 0.0f;
+      wv[k][j] = 1.0f;
+    }
+    if (w != nullptr && i < D) Pack8<T>::load(w + i, wv[k]);
+  }
   for (int row = blockIdx.x; row < M; row += gridDim.x) {
     const T* xr = x + (size_t)row * D;
     const T* dyr = dy + (size_t)row * D;
     T* dxr = dx + (size_t)row * D;
     const float mu = mean[row], r = rstd[row];
+    float xh[kMaxPacks][8], gv[kMaxPacks][8];
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
     for (int k = 0; k < kMaxPacks; ++k) {
       const int i = (threadIdx.x + k * blockDim.x) * 8;
       if (i < D) {
-        float xv[8], dv[8], wv[8];
+        float xv[8], dv[8];
         Pack8<T>::load(xr + i, xv);
         Pack8<T>::load(dyr + i, dv);
-        if (w != nullptr) Pack8<T>::load(w + i, wv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float xh = (xv[j] - mu) * r;
-          const float g = w != nullptr ? dv[j] * wv[j] : dv[j];
-          s1 += g;
-          s2 += g * xh;
-          wacc[k][j] += dv[j] * xh;
+          xh[k][j] = (xv[j] - mu) * r;
+          gv[k][j] = dv[j] * wv[k][j];
+          s1 += gv[k][j];
+          s2 += gv[k][j] * xh[k][j];
+          wacc[k][j] += dv[j] * xh[k][j];
           bacc[k][j] += dv[j];
         }
       }
@@ -207,16 +227,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
     for (int k = 0; k < kMaxPacks; ++k) {
       const int i = (threadIdx.x + k * blockDim.x) * 8;
       if (i < D) {
-        float xv[8], dv[8], wv[8], o[8];
-        Pack8<T>::load(xr + i, xv);
-        Pack8<T>::load(dyr + i, dv);
-        if (w != nullptr) Pack8<T>::load(w + i, wv);
+        float o[8];
         if (accumulate_dx) Pack8<T>::load(dxr + i, o);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float xh = (xv[j] - mu) * r;
-          const float g = w != nullptr ? dv[j] * wv[j] : dv[j];
-          const float t = r * (g - s1 - xh * s2);
+          const float t = r * (gv[k][j] - s1 - xh[k][j] * s2);
           o[j] = accumulate_dx ? o[j] + t : t;
         }
         Pack8<T>::store(dxr + i, o);
@@ -227,10 +242,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
   for (int k = 0; k < kMaxPacks; ++k) {
     const int i = (threadIdx.x + k * blockDim.x) * 8;
     if (i < D) {
+      if (ws != nullptr) {
+        Pack8<float>::store(ws + (size_t)blockIdx.x * 2 * D + i, wacc[k]);
+        Pack8<float>::store(ws + (size_t)blockIdx.x * 2 * D + D + i, bacc[k]);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (dw != nullptr) atomicAdd(dw + i + j, wacc[k][j]);
-        if (db != nullptr) atomicAdd(db + i + j, bacc[k][j]);
+        for (int j = 0; j < 8; ++j) {
+          if (dw != nullptr) atomicAdd(dw + i + j, wacc[k][j]);
+          if (db != nullptr) atomicAdd(db + i + j, bacc[k][j]);
+        }
       }
     }
   }
@@ -299,7 +319,23 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x
 template <typename T>
 __global__ void glu_fwd_kernel(const T* __restrict__ g, const T* __restrict__ u, T* __restrict__ h, int64_t n8,
                                int act) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; i + stride < n8; i += 2 * stride) {      // two packs in flight per thread
+    float a0[8], b0[8], a1[8], b1[8];
+    Pack8<T>::load(g + i * 8, a0);
+    Pack8<T>::load(u + i * 8, b0);
+    Pack8<T>::load(g + (i + stride) * 8, a1);
+    Pack8<T>::load(u + (i + stride) * 8, b1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a0[j] = act_fwd(a0[j], act) * b0[j];
+      a1[j] = act_fwd(a1[j], act) * b1[j];
+    }
+    Pack8<T>::store(h + i * 8, a0);
+    Pack8<T>::store(h + (i + stride) * 8, a1);
+  }
+  for (; i < n8; i += stride) {
     float a[8], b[8];
     Pack8<T>::load(g + i * 8, a);
     Pack8<T>::load(u + i * 8, b);
@@ -333,16 +369,33 @@ __global__ void glu_bwd_kernel(const T* dh, const T* g, const T* u, T* dg, T* du
 // ------------------------------------------------------------------ softmax
 // One warp per (z, q) row.  allowed(q,k) = (!keymask || keymask[b,k]) && (!bid || bid_k[b,k] <= bid_q[b,q]).
 // b = z / heads.  Scores are fp32 (already scaled); P is written as T.  Fully masked rows -> zeros.
-// Rows up to 32*kSoftmaxCache keys are read ONCE (values cached in registers); longer rows fall back to
-// re-reading from L2.
-constexpr int kSoftmaxCache = 32;
+// One warp per (z, q) row; the row is read ONCE with 128-bit loads (lane owns 4 consecutive keys per step, up to
+// 8 steps = 1024 keys cached in registers; longer rows fall back to re-reading).  causal != 0: bid_* are not read,
+// allowed(q,k) = k <= q, and keys beyond q are never loaded.
 template <typename T>
-__global__ void softmax_fwd_kernel(const float* __restrict__ s, T* __restrict__ p, int64_t rows, int Sq, int Sk,
-                                   int64_t s_ld, int64_t p_ld, int heads, const uint8_t* __restrict__ keymask,
-                                   const int* __restrict__ bid_q, const int* __restrict__ bid_k) {
+__device__ __forceinline__ void store4(T* p, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store4<bf16>(bf16* p, float a, float b, float c, float d) {
+  uint2 u;
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename T, int kSoftmaxSteps>
+__global__ void __launch_bounds__(256, kSoftmaxSteps <= 4 ? 6 : 3) softmax_fwd_kernel(const float* __restrict__ s, T* __restrict__ p, int64_t rows,
+                                                          int Sq, int Sk, int64_t s_ld, int64_t p_ld, int heads,
+                                                          const uint8_t* __restrict__ keymask,
+                                                          const int* __restrict__ bid_q, const int* __restrict__ bid_k,
+                                                          int causal) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  const bool cached = Sk <= 32 * kSoftmaxCache;
+  const bool vec_ok = (s_ld % 4 == 0) && (p_ld % 4 == 0) && Sk <= 128 * kSoftmaxSteps;
   for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
     const int64_t z = row / Sq;
     const int q = (int)(row - z * Sq);
@@ -350,49 +403,63 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ s, T* __restrict__ 
     const float* sr = s + row * s_ld;
     T* pr = p + row * p_ld;
     const uint8_t* km = keymask != nullptr ? keymask + (size_t)b * Sk : nullptr;
-    const int* bk = bid_k != nullptr ? bid_k + (size_t)b * Sk : nullptr;
-    const int bq = bid_q != nullptr ? bid_q[(size_t)b * Sq + q] : 0;
-    if (cached) {
-      float v[kSoftmaxCache];
+    const int* bk = (!causal && bid_k != nullptr) ? bid_k + (size_t)b * Sk : nullptr;
+    const int bq = (!causal && bid_q != nullptr) ? bid_q[(size_t)b * Sq + q] : 0;
+    const int limit = causal ? min(Sk, q + 1) : Sk;      // keys >= limit are masked
+    if (vec_ok) {
+      float v[kSoftmaxSteps][4];
       float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < kSoftmaxCache; ++i) {
-        const int k = lane + 32 * i;
-        v[i] = -INFINITY;
-        if (k < Sk && (km == nullptr || km[k]) && (bk == nullptr || bk[k] <= bq)) v[i] = sr[k];
-        mx = fmaxf(mx, v[i]);
+      for (int i = 0; i < kSoftmaxSteps; ++i) {
+        const int k0 = (lane + 32 * i) * 4;
+        v[i][0] = v[i][1] = v[i][2] = v[i][3] = -INFINITY;
+        if (k0 < limit) {
+          const float4 f = *reinterpret_cast<const float4*>(sr + k0);   // row padding up to s_ld is readable
+          const float t[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            bool ok = k < limit;
+            if (ok && km != nullptr) ok = km[k] != 0;
+            if (ok && bk != nullptr) ok = bk[k] <= bq;
+            if (ok) v[i][j] = t[j];
+            mx = fmaxf(mx, v[i][j]);
+          }
+        }
       }
       mx = warp_max(mx);
       float sum = 0.0f;
 #pragma unroll
-      for (int i = 0; i < kSoftmaxCache; ++i) {
-        v[i] = v[i] == -INFINITY ? 0.0f : __expf(v[i] - mx);
-        sum += v[i];
-      }
+      for (int i = 0; i < kSoftmaxSteps; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[i][j] = v[i][j] == -INFINITY ? 0.0f : __expf(v[i][j] - mx);
+          sum += v[i][j];
+        }
       sum = warp_sum(sum);
       const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
 #pragma unroll
-      for (int i = 0; i < kSoftmaxCache; ++i) {
-        const int k = lane + 32 * i;
-        if (k < Sk) pr[k] = from_f<T>(v[i] * inv);
+      for (int i = 0; i < kSoftmaxSteps; ++i) {
+        const int k0 = (lane + 32 * i) * 4;
+        if (k0 < Sk) store4<T>(pr + k0, v[i][0] * inv, v[i][1] * inv, v[i][2] * inv, v[i][3] * inv);
       }
       continue;
     }
     float mx = -INFINITY;
-    for (int k = lane; k < Sk; k += 32) {
+    for (int k = lane; k < limit; k += 32) {
       const bool ok = (km == nullptr || km[k]) && (bk == nullptr || bk[k] <= bq);
       if (ok) mx = fmaxf(mx, sr[k]);
     }
     mx = warp_max(mx);
     float sum = 0.0f;
-    for (int k = lane; k < Sk; k += 32) {
+    for (int k = lane; k < limit; k += 32) {
       const bool ok = (km == nullptr || km[k]) && (bk == nullptr || bk[k] <= bq);
       if (ok) sum += __expf(sr[k] - mx);
     }
     sum = warp_sum(sum);
     const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
     for (int k = lane; k < Sk; k += 32) {
-      const bool ok = (km == nullptr || km[k]) && (bk == nullptr || bk[k] <= bq);
+      const bool ok = k < limit && (km == nullptr || km[k]) && (bk == nullptr || bk[k] <= bq);
       pr[k] = from_f<T>(ok ? __expf(sr[k] - mx) * inv : 0.0f);
     }
   }
@@ -430,6 +497,24 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
   for (int r = r0; r < r1; ++r) {
     float v[8];
     Pack8<T>::load(x + (size_t)r * N + col8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(out + col8 + j, acc[j]);
+}
+
+// out[col] += sum_rows x[row*ld + col]  (fp32 partials with a leading dimension)
+__global__ void colsum_strided_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, int64_t ld,
+                                      int rows_per_block) {
+  const int col8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (col8 >= N) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int r = r0; r < r1; ++r) {
+    float v[8];
+    Pack8<float>::load(x + (size_t)r * ld + col8, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += v[j];
   }
@@ -583,20 +668,36 @@ int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t
                      int unit_offset, int dtype, void* stream) {
   B200_CHECK(D % 8 == 0, "rmsnorm_fwd: D=%lld must be a multiple of 8", (long long)D);
   if (M == 0) return 0;
-  DISPATCH_T(dtype, (rmsnorm_fwd_kernel<T><<<grid_for_rows(M), 256, 0, STREAM>>>(
+  const int nt = norm_threads(D);
+  DISPATCH_T(dtype, (rmsnorm_fwd_kernel<T><<<grid_for_rows(M, 2048 / nt), nt, 0, STREAM>>>(
                         (const T*)x, (const T*)w, (T*)y, rstd, (int)M, (int)D, eps, unit_offset)));
   B200_LAUNCH_OK();
   return 0;
 }
 
-int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw, int64_t M,
-                     int64_t D, int unit_offset, int accumulate_dx, int dtype, void* stream) {
+// rows of fp32 workspace the backward norm kernels want (one per launched block); 0 -> atomics path
+int64_t b200_norm_bwd_workspace_rows(int64_t M, int64_t D) {
+  const int nt = norm_threads(D);
+  return grid_for_rows(M, 1024 / nt);
+}
+
+int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw,
+                     float* workspace, int64_t M, int64_t D, int unit_offset, int accumulate_dx, int dtype,
+                     void* stream) {
   B200_CHECK(D % 8 == 0 && D <= 8 * 256 * kMaxPacks, "rmsnorm_bwd: unsupported D=%lld", (long long)D);
   if (M == 0) return 0;
-  DISPATCH_T(dtype, (rmsnorm_bwd_kernel<T><<<grid_for_rows(M, 2), 256, 0, STREAM>>>(
-                        (const T*)dy, (const T*)x, (const T*)w, rstd, (T*)dx, dw, (int)M, (int)D, unit_offset,
+  const int nt = norm_threads(D);
+  const int grid = grid_for_rows(M, 1024 / nt);
+  float* ws = dw != nullptr ? workspace : nullptr;
+  DISPATCH_T(dtype, (rmsnorm_bwd_kernel<T><<<grid, nt, 0, STREAM>>>(
+                        (const T*)dy, (const T*)x, (const T*)w, rstd, (T*)dx, dw, ws, (int)M, (int)D, unit_offset,
                         accumulate_dx)));
   B200_LAUNCH_OK();
+  if (ws != nullptr) {   // dw[D] += column sums of the [grid, D] partials
+    dim3 g2((unsigned)ceil_div(D / 8, 64), (unsigned)ceil_div(grid, 64));
+    colsum_kernel<float><<<g2, 64, 0, STREAM>>>(ws, dw, grid, (int)D, 64);
+    B200_LAUNCH_OK();
+  }
   return 0;
 }
 
@@ -604,20 +705,40 @@ int b200_layernorm_fwd(const void* x, const void* w, const void* b, void* y, flo
                        int64_t D, float eps, int dtype, void* stream) {
   B200_CHECK(D % 8 == 0, "layernorm_fwd: D=%lld must be a multiple of 8", (long long)D);
   if (M == 0) return 0;
-  DISPATCH_T(dtype, (layernorm_fwd_kernel<T><<<grid_for_rows(M), 256, 0, STREAM>>>(
+  const int nt = norm_threads(D);
+  DISPATCH_T(dtype, (layernorm_fwd_kernel<T><<<grid_for_rows(M, 2048 / nt), nt, 0, STREAM>>>(
                         (const T*)x, (const T*)w, (const T*)b, (T*)y, mean, rstd, (int)M, (int)D, eps)));
   B200_LAUNCH_OK();
   return 0;
 }
 
 int b200_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
-                       float* dw, float* db, int64_t M, int64_t D, int accumulate_dx, int dtype, void* stream) {
+                       float* dw, float* db, float* workspace, int64_t M, int64_t D, int accumulate_dx, int dtype,
+                       void* stream) {
   B200_CHECK(D % 8 == 0 && D <= 8 * 256 * kMaxPacks, "layernorm_bwd: unsupported D=%lld", (long long)D);
   if (M == 0) return 0;
-  DISPATCH_T(dtype, (layernorm_bwd_kernel<T><<<grid_for_rows(M, 2), 256, 0, STREAM>>>(
-                        (const T*)dy, (const T*)x, (const T*)w, mean, rstd, (T*)dx, dw, db, (int)M, (int)D,
+  const int nt = norm_threads(D);
+  const int grid = grid_for_rows(M, 1024 / nt);
+  // workspace rows hold [dw partial | db partial]; it is only usable when both gradients are wanted
+  float* ws = (dw != nullptr && db != nullptr) ? workspace : nullptr;
+  DISPATCH_T(dtype, (layernorm_bwd_kernel<T><<<grid, nt, 0, STREAM>>>(
+                        (const T*)dy, (const T*)x, (const T*)w, mean, rstd, (T*)dx, dw, db, ws, (int)M, (int)D,
                         accumulate_dx)));
   B200_LAUNCH_OK();
+  if (ws != nullptr) {
+    dim3 g2((unsigned)ceil_div(2 * D / 8, 64), (unsigned)ceil_div(grid, 64));
+    // dw and db are reduced in one pass over the [grid, 2D] partials when they are adjacent; else two passes
+    if (db == dw + D) {
+      colsum_kernel<float><<<g2, 64, 0, STREAM>>>(ws, dw, grid, (int)(2 * D), 64);
+      B200_LAUNCH_OK();
+    } else {
+      dim3 g1((unsigned)ceil_div(D / 8, 64), (unsigned)ceil_div(grid, 64));
+      colsum_strided_kernel<<<g1, 64, 0, STREAM>>>(ws, dw, grid, (int)D, 2 * D, 64);
+      B200_LAUNCH_OK();
+      colsum_strided_kernel<<<g1, 64, 0, STREAM>>>(ws + D, db, grid, (int)D, 2 * D, 64);
+      B200_LAUNCH_OK();
+    }
+  }
   return 0;
 }
 
@@ -668,15 +789,23 @@ int b200_glu_bwd(const void* dh, const void* g, const void* u, void* dg, void* d
 }
 
 int b200_softmax_fwd(const float* scores, void* p, int64_t Z, int64_t Sq, int64_t Sk, int64_t s_ld, int64_t p_ld,
-                     int heads, const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k, int p_dtype,
-                     void* stream) {
+                     int heads, const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k, int causal,
+                     int p_dtype, void* stream) {
   const int64_t rows = Z * Sq;
   if (rows == 0) return 0;
   B200_CHECK((bid_q == nullptr) == (bid_k == nullptr), "softmax_fwd: bid_q and bid_k go together");
   const int dtype = p_dtype;
-  DISPATCH_T(dtype, (softmax_fwd_kernel<T><<<grid_1d(rows, 8), 256, 0, STREAM>>>(
-                        scores, (T*)p, rows, (int)Sq, (int)Sk, s_ld, p_ld, heads > 0 ? heads : 1, keymask, bid_q,
-                        bid_k)));
+  const int steps = (int)ceil_div(Sk, 128);
+#define SMX(T_, N_)                                                                                              \
+  softmax_fwd_kernel<T_, N_><<<grid_1d(ceil_div(rows, 8), 1), 256, 0, STREAM>>>(                                  \
+      scores, (T_*)p, rows, (int)Sq, (int)Sk, s_ld, p_ld, heads > 0 ? heads : 1, keymask, bid_q, bid_k, causal)
+  if (dtype == B200_F32) {
+    if (steps <= 1) SMX(float, 1); else if (steps <= 2) SMX(float, 2); else if (steps <= 4) SMX(float, 4); else SMX(float, 8);
+  } else {
+    if (steps <= 1) SMX(bf16, 1); else if (steps <= 2) SMX(bf16, 2); else if (steps <= 3) SMX(bf16, 3);
+    else if (steps <= 4) SMX(bf16, 4); else SMX(bf16, 8);
+  }
+#undef SMX
   B200_LAUNCH_OK();
   return 0;
 }
@@ -693,9 +822,9 @@ int b200_softmax_bwd(const void* p, const float* dp, void* ds, int64_t rows, int
 int b200_colsum(const void* x, float* out, int64_t M, int64_t N, int dtype, void* stream) {
   B200_CHECK(N % 8 == 0, "colsum: N must be a multiple of 8");
   if (M == 0) return 0;
-  const int rows_per_block = 128;
-  dim3 grid((unsigned)ceil_div(N / 8, 256), (unsigned)ceil_div(M, rows_per_block));
-  DISPATCH_T(dtype, (colsum_kernel<T><<<grid, 256, 0, STREAM>>>((const T*)x, out, (int)M, (int)N, rows_per_block)));
+  const int rows_per_block = 64;
+  dim3 grid((unsigned)ceil_div(N / 8, 64), (unsigned)ceil_div(M, rows_per_block));
+  DISPATCH_T(dtype, (colsum_kernel<T><<<grid, 64, 0, STREAM>>>((const T*)x, out, (int)M, (int)N, rows_per_block)));
   B200_LAUNCH_OK();
   return 0;
 }

@@ -85,7 +85,8 @@ class AttnEnv:
     B: int
     S: int
     keymask: Optional[torch.Tensor] = None   # uint8 [B,S]
-    bid: Optional[torch.Tensor] = None       # int32 [B,S] (causal order / pi0 block ids)
+    bid: Optional[torch.Tensor] = None       # int32 [B,S] (pi0 block ids: allowed iff bid[k] <= bid[q])
+    causal: bool = False                     # plain causal order by index (decoder LLM)
     pos: Optional[torch.Tensor] = None       # int32 [B*S] RoPE positions
     cos: Optional[torch.Tensor] = None       # fp32 [n_pos, hd/2]
     sin: Optional[torch.Tensor] = None
@@ -159,7 +160,8 @@ def block_forward(x2d: torch.Tensor, bw: BlockW, env: AttnEnv, mode: str):
     qkv, _ = linear_fwd(h, bw.qkv)
     if c.rope:
         ops.rope_(qkv, env.pos, env.cos, env.sin, c.heads + c.kv_heads, c.head_dim)
-    attn, probs = ops.attention_fwd(qkv.view(env.B, env.S, -1), sh, keymask=env.keymask, bid_q=env.bid, bid_k=env.bid)
+    attn, probs = ops.attention_fwd(qkv.view(env.B, env.S, -1), sh, keymask=env.keymask, bid_q=env.bid, bid_k=env.bid,
+                                    causal=env.causal)
     attn2d = attn.view(x2d.shape[0], -1)
     x1, _ = linear_fwd(attn2d, bw.o, residual=x2d)
     h2, st2 = norm_fwd(x1, bw.norm2)

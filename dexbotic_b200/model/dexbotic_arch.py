@@ -331,8 +331,7 @@ class Decoder:
         dev = x2d.device
         self._last_B = B
         cos, sin = self.rope_tables(S + 1, dev)
-        bid = torch.arange(S, device=dev, dtype=torch.int32)[None, :].expand(B, S).contiguous()
-        env = AttnEnv(B=B, S=S, keymask=mask_u8, bid=bid, pos=pos_i32.reshape(-1), cos=cos, sin=sin)
+        env = AttnEnv(B=B, S=S, keymask=mask_u8, causal=True, pos=pos_i32.reshape(-1), cos=cos, sin=sin)
         keep = self._decide_keep_layers(x2d) if torch.is_grad_enabled() else 0
         for i, bw in enumerate(self.blocks):
             x2d = TransformerBlockFn.apply(x2d, bw, env, self.store, i >= keep)

@@ -166,7 +166,7 @@ def _qkv_ptrs(qkv: torch.Tensor, sh: AttnShape):
 
 
 def attention_fwd(qkv: torch.Tensor, sh: AttnShape, *, keymask: Optional[torch.Tensor] = None,
-                  bid_q: Optional[torch.Tensor] = None, bid_k: Optional[torch.Tensor] = None,
+                  bid_q: Optional[torch.Tensor] = None, bid_k: Optional[torch.Tensor] = None, causal: bool = False,
                   scores: Optional[torch.Tensor] = None, probs: Optional[torch.Tensor] = None,
                   out: Optional[torch.Tensor] = None):
     """softmax(mask(Q K^T / sqrt(hd))) V over packed qkv (RoPE already applied).  Returns (out[B,S,H*hd], probs)."""
@@ -186,7 +186,7 @@ def attention_fwd(qkv: torch.Tensor, sh: AttnShape, *, keymask: Optional[torch.T
              a_ld=W, a_s2=hd, a_s3=S * W, a_z2=H, b_ld=W, b_s2=hd, b_s3=S * W, b_z2=KVH,
              d_ld=sh.ld_s, d_s2=S * sh.ld_s, d_s3=H * S * sh.ld_s, z_lo=H, z_hi=B,
              a_div=1, a_mul=1, a_seg=0, b_div=G, b_mul=1, b_seg=0, k_segs=1, alpha=sh.scale)
-    softmax_fwd(scores, probs, S, S, heads=H, keymask=keymask, bid_q=bid_q, bid_k=bid_k)
+    softmax_fwd(scores, probs, S, S, heads=H, keymask=keymask, bid_q=bid_q, bid_k=bid_k, causal=causal)
     # out = P V
     gemm_raw(a=probs.data_ptr(), b=v, d=out.data_ptr(), ab_dtype=dt, d_dtype=dt, a_mn_major=0, b_mn_major=1,
              m=S, n=hd, k=S, a_ld=sh.ld_p, a_s2=S * sh.ld_p, a_s3=H * S * sh.ld_p, a_z2=H,
@@ -259,11 +259,13 @@ def rmsnorm_bwd(dy, x, w, rstd, unit_offset: bool = False, dx=None, dw=None, acc
     if dx is None:
         assert not accumulate_dx
         dx = torch.empty_like(x)
+    ws = None
     if dw is not None:
         assert dw.dtype == torch.float32 and dw.numel() == D
+        ws = torch.empty((int(_lib.load().b200_norm_bwd_workspace_rows(M, D)), D), device=x.device, dtype=torch.float32)
     _lib.check(_lib.load().b200_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
-                                            _p(dw), M, D, int(unit_offset), int(accumulate_dx), _dt(x), _stream()),
-               "rmsnorm_bwd")
+                                            _p(dw), _p(ws), M, D, int(unit_offset), int(accumulate_dx), _dt(x),
+                                            _stream()), "rmsnorm_bwd")
     return dx
 
 
@@ -288,8 +290,12 @@ def layernorm_bwd(dy, x, w, mean, rstd, dx=None, dw=None, db=None, accumulate_dx
     if dx is None:
         assert not accumulate_dx
         dx = torch.empty_like(x)
+    ws = None
+    if dw is not None and db is not None:
+        ws = torch.empty((int(_lib.load().b200_norm_bwd_workspace_rows(M, D)), 2 * D), device=x.device,
+                         dtype=torch.float32)
     _lib.check(_lib.load().b200_layernorm_bwd(dy.data_ptr(), x.data_ptr(), _p(w), mean.data_ptr(), rstd.data_ptr(),
-                                              dx.data_ptr(), _p(dw), _p(db), M, D, int(accumulate_dx), _dt(x),
+                                              dx.data_ptr(), _p(dw), _p(db), _p(ws), M, D, int(accumulate_dx), _dt(x),
                                               _stream()), "layernorm_bwd")
     return dx
 
@@ -340,7 +346,8 @@ def glu_bwd(dh, g, u, act, dg=None, du=None, h_out=None):
     return dg, du
 
 
-def softmax_fwd(scores, probs, Sq: int, Sk: int, heads: int = 1, keymask=None, bid_q=None, bid_k=None):
+def softmax_fwd(scores, probs, Sq: int, Sk: int, heads: int = 1, keymask=None, bid_q=None, bid_k=None,
+                causal: bool = False):
     _cuda(scores, probs, keymask, bid_q, bid_k)
     assert scores.dtype == torch.float32
     Z = scores.numel() // (Sq * scores.shape[-1])
@@ -350,8 +357,8 @@ def softmax_fwd(scores, probs, Sq: int, Sk: int, heads: int = 1, keymask=None, b
         if t is not None:
             assert t.dtype == torch.int32 and t.is_contiguous()
     _lib.check(_lib.load().b200_softmax_fwd(scores.data_ptr(), probs.data_ptr(), Z, Sq, Sk, scores.shape[-1],
-                                            probs.shape[-1], heads, _p(keymask), _p(bid_q), _p(bid_k), _dt(probs),
-                                            _stream()), "softmax_fwd")
+                                            probs.shape[-1], heads, _p(keymask), _p(bid_q), _p(bid_k), int(causal),
+                                            _dt(probs), _stream()), "softmax_fwd")
     return probs
 
 

@@ -23,16 +23,21 @@ extern "C" {
  * final norm read at cogact_arch.py:108.  rstd[M] (fp32) is saved for backward (may be NULL). */
 int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t M, int64_t D, float eps,
                      int unit_offset, int dtype, void* stream);
-/* dx (=, or += if accumulate_dx) and dw[D] (fp32, += via atomics; may be NULL). */
-int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw, int64_t M,
-                     int64_t D, int unit_offset, int accumulate_dx, int dtype, void* stream);
+/* dx (=, or += if accumulate_dx) and dw[D] (fp32, +=; may be NULL).  workspace: optional fp32 scratch of
+ * b200_norm_bwd_workspace_rows(M, D) x D floats (x 2D for layernorm) for contention-free partial sums; NULL falls
+ * back to fp32 atomics. */
+int64_t b200_norm_bwd_workspace_rows(int64_t M, int64_t D);
+int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw,
+                     float* workspace, int64_t M, int64_t D, int unit_offset, int accumulate_dx, int dtype,
+                     void* stream);
 
 /* LayerNorm (w, b optional): HF CLIPEncoderLayer.layer_norm1/2, pre_layrnorm (clip_encoder.py:50-54);
  * DiT norm1/norm2/norm_final, elementwise_affine=False (dit.py:141,147,167). */
 int b200_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t M,
                        int64_t D, float eps, int dtype, void* stream);
 int b200_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
-                       float* dw, float* db, int64_t M, int64_t D, int accumulate_dx, int dtype, void* stream);
+                       float* dw, float* db, float* workspace, int64_t M, int64_t D, int accumulate_dx, int dtype,
+                       void* stream);
 
 /* rotate_half RoPE, in place, on the first n_rot_heads heads (q then k) of each row of a packed
  * [M, row_stride] qkv buffer.  cos/sin: fp32 [n_pos, head_dim/2] tables, pos: int32 [M].
@@ -52,11 +57,12 @@ int b200_glu_bwd(const void* dh, const void* g, const void* u, void* dg, void* d
 
 /* Masked softmax over fp32 score rows [Z, Sq, s_ld] -> P [Z, Sq, p_ld] (p_dtype).  Batch b = z / heads.
  * allowed(q,k) = (keymask==NULL || keymask[b,k]) && (bid_q==NULL || bid_k[b,k] <= bid_q[b,q]):
- *   causal decoder: bid = position index (HF SDPA causal mask + padding mask);
+ *   causal decoder: causal=1 (k <= q by index; bid_* ignored and keys beyond q never read) — HF SDPA causal +
+ *   padding mask;
  *   pi0 block-causal: bid = cumsum(ar_mask) (pi0_arch.py:22-33);  ViT / DiT: no mask. */
 int b200_softmax_fwd(const float* scores, void* p, int64_t Z, int64_t Sq, int64_t Sk, int64_t s_ld, int64_t p_ld,
-                     int heads, const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k, int p_dtype,
-                     void* stream);
+                     int heads, const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k, int causal,
+                     int p_dtype, void* stream);
 /* dS = scale * P * (dP - rowsum(P*dP)) */
 int b200_softmax_bwd(const void* p, const float* dp, void* ds, int64_t rows, int64_t Sk, int64_t p_ld, int64_t dp_ld,
                      int64_t ds_ld, float scale, int p_dtype, void* stream);

@@ -131,6 +131,69 @@ def test_cogact_medium_matches_oracle(left_pad):
     assert not bad, bad[:12]
 
 
+def test_cogact_production_dims_one_layer_matches_oracle():
+    """One decoder layer and one CLIP layer at the PRODUCTION widths (Qwen2.5-7B: d=3584, 28/4 heads x 128, inter
+    18944; CLIP-L/14@224: d=1024, 16 heads, 257 tokens; DiT-B) so that the exact tile / head / GQA geometry of the
+    benchmark is parity-checked, not only the tiny fixtures."""
+    from oracle import vla_oracle
+    from oracle.weights import seeded_state_dict
+    from dexbotic_b200.model import CogActConfig, CogACTForCausalLM
+    cfg = dict(
+        llm=dict(vocab_size=2048, hidden_size=3584, intermediate_size=18944, num_hidden_layers=1, num_attention_heads=28,
+                 num_key_value_heads=4, rope_theta=1e6, rms_norm_eps=1e-6, hidden_act="silu", model_type="qwen2"),
+        vision=dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=2, num_attention_heads=16, image_size=224,
+                    patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5),
+        action_model_type="DiT-B", action_dim=7, chunk_size=16, projector_depth=2, diffusion_steps=100,
+        tokenizer_model_max_length=None, tokenizer_padding_side="right")
+    c = CogActConfig(llm_config=cfg["llm"], mm_vision_tower=cfg["vision"], action_model_type="DiT-B", action_dim=7,
+                     chunk_size=16)
+    model = CogACTForCausalLM(c)
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 5)
+    model.load_state_dict(sd)
+    model.train()
+    g = torch.Generator().manual_seed(9)
+    B, L, R = 2, 54, 4
+    ids = torch.randint(1, 2048, (B, L), generator=g)
+    ids[:, 1] = -200
+    mask = torch.ones(B, L, dtype=torch.long)
+    mask[1, 47:] = 0
+    images = torch.randn(B, 3, 224, 224, generator=g)
+    actions = torch.rand(B, 112, generator=g) * 2 - 1
+    noise = torch.randn(R * B, 16, 7, generator=g)
+    t = torch.randint(0, 100, (R * B,), generator=g)
+    drop = torch.tensor([False, True] * (R * B // 2))
+    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ora = vla_oracle.cogact_forward(sd_g, cfg, ids, mask, images, actions, noise, t, drop, R)
+    ora["loss"].backward()
+    for recompute in (False, True):
+        model.model_engine.llm.keep_layers = 0 if recompute else 1
+        model.model_engine.mm_vision_tower.keep_layers = 0 if recompute else 1
+        model.zero_grad()
+        out = model(input_ids=ids.cuda(), attention_mask=mask.cuda(), images=images.cuda(), actions=actions.cuda(),
+                    repeated_diffusion_steps=R, noise=noise.cuda(), timesteps=t.cuda(), drop_mask=drop.cuda())
+        assert out.logits.shape == (B, 53 + 256, 3584)
+        assert abs(out.loss.item() - ora["loss"].item()) < 2e-2 * abs(ora["loss"].item()), (out.loss.item(), ora["loss"].item())
+        valid = ora["attention_mask"][:, :, None]
+        rel, cos = _rel(out.logits.float().cpu() * valid, ora["last_hidden"].detach() * valid)
+        assert rel < 3e-2 and cos > 0.999, (rel, cos)
+        out.loss.backward()
+        bad = []
+        for name in ["model.llm.layers.0.self_attn.q_proj.weight", "model.llm.layers.0.self_attn.k_proj.weight",
+                     "model.llm.layers.0.self_attn.v_proj.weight", "model.llm.layers.0.self_attn.o_proj.weight",
+                     "model.llm.layers.0.mlp.gate_proj.weight", "model.llm.layers.0.mlp.down_proj.weight",
+                     "model.llm.layers.0.self_attn.q_proj.bias", "model.llm.layers.0.input_layernorm.weight",
+                     "model.mm_projector.0.weight", "model.mm_projector.2.bias",
+                     "model.mm_vision_tower.vision_tower.vision_model.encoder.layers.0.self_attn.q_proj.weight",
+                     "model.mm_vision_tower.vision_tower.vision_model.encoder.layers.0.mlp.fc2.weight",
+                     "model.mm_vision_tower.vision_tower.vision_model.embeddings.patch_embedding.weight",
+                     "model.action_head.net.blocks.0.attn.qkv.weight", "model.action_head.net.final_layer.linear.weight",
+                     "model.action_head.net.z_embedder.uncondition"]:
+            rel, cos = _rel(model.store.g(name).cpu(), sd_g[name].grad)
+            if not (rel < 0.12 and cos > 0.99):
+                bad.append((name, round(rel, 4), round(cos, 5)))
+        assert not bad, (recompute, bad)
+
+
 def test_training_steps_reduce_loss():
     fx = torch.load(GOLDEN / "cogact_tiny.pt", weights_only=False)
     model, _ = _build(fx["cfg"], fx["shapes"], fx["seed"])

@@ -1,0 +1,75 @@
+"""GB/s of the HBM-bound kernels on the CogACT-7B shapes (CUDA events, L2 flushed between reps)."""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from dexbotic_b200 import ops  # noqa: E402
+from tools.bench_gemm import timeit  # noqa: E402
+
+PEAK = 6485.5
+
+
+def report(name, nbytes, fn):
+    t = timeit(fn, reps=7)
+    print(f"{name:28s} {t*1e3:8.1f} us  {nbytes/t/1e6:7.0f} GB/s  {100*nbytes/t/1e6/PEAK:5.1f}% of measured copy peak", flush=True)
+
+
+def main():
+    dev, bf = "cuda", torch.bfloat16
+    M, d, I, W = 9888, 3584, 18944, 4608
+    x = torch.randn(M, d, device=dev, dtype=bf)
+    dy = torch.randn(M, d, device=dev, dtype=bf)
+    w = torch.randn(d, device=dev, dtype=bf)
+    y, rstd = ops.rmsnorm_fwd(x, w, 1e-6)
+    report("rmsnorm_fwd", 2 * M * d * 2, lambda: ops.rmsnorm_fwd(x, w, 1e-6, out=y))
+    dx = torch.empty_like(x)
+    dw = torch.zeros(d, device=dev)
+    report("rmsnorm_bwd", 3 * M * d * 2, lambda: ops.rmsnorm_bwd(dy, x, w, rstd, dx=dx, dw=dw))
+    report("rmsnorm_bwd(accum)", 4 * M * d * 2, lambda: ops.rmsnorm_bwd(dy, x, w, rstd, dx=dx, dw=dw, accumulate_dx=True))
+    g = torch.randn(M, I, device=dev, dtype=bf)
+    u = torch.randn(M, I, device=dev, dtype=bf)
+    h = torch.empty_like(g)
+    dh = torch.randn(M, I, device=dev, dtype=bf)
+    report("glu_fwd", 3 * M * I * 2, lambda: ops.glu_fwd(g, u, "silu", out=h))
+    dg, du = torch.empty_like(g), torch.empty_like(g)
+    report("glu_bwd(+h)", 6 * M * I * 2, lambda: ops.glu_bwd(dh, g, u, "silu", dg=dg, du=du, h_out=h))
+    B, H, S = 32, 28, 309
+    sh = ops.AttnShape(B, S, H, 4, 128, bf)
+    sc = torch.randn(B, H, S, sh.ld_s, device=dev)
+    pr = torch.empty(B, H, S, sh.ld_p, device=dev, dtype=bf)
+    km = torch.ones(B, S, device=dev, dtype=torch.uint8)
+    bid = torch.arange(S, device=dev, dtype=torch.int32)[None].expand(B, S).contiguous()
+    nb = B * H * S * S * (4 + 2)
+    report("softmax_fwd causal", nb, lambda: ops.softmax_fwd(sc, pr, S, S, heads=H, keymask=km, causal=True))
+    report("softmax_fwd bid arrays", nb, lambda: ops.softmax_fwd(sc, pr, S, S, heads=H, keymask=km, bid_q=bid, bid_k=bid))
+    report("softmax_fwd nomask", nb, lambda: ops.softmax_fwd(sc, pr, S, S, heads=H))
+    ds = torch.empty_like(pr)
+    report("softmax_bwd", B * H * S * S * (2 + 4 + 2), lambda: ops.softmax_bwd(pr, sc, ds, B * H * S, S, sh.ld_p, sh.ld_s, sh.ld_p, 0.1))
+    qkv = torch.randn(M, W, device=dev, dtype=bf)
+    out = torch.zeros(W, device=dev)
+    report("colsum [M,4608]", M * W * 2, lambda: ops.colsum_(qkv, out))
+    pos = torch.arange(M, device=dev, dtype=torch.int32) % S
+    inv = 1.0 / (1e6 ** (torch.arange(0, 128, 2, dtype=torch.float32, device=dev) / 128))
+    f = torch.arange(1024, dtype=torch.float32, device=dev)[:, None] * inv[None]
+    cos, sin = f.cos().contiguous(), f.sin().contiguous()
+    report("rope (q,k of qkv)", 2 * M * 32 * 128 * 2, lambda: ops.rope_(qkv, pos, cos, sin, 32, 128))
+    xv = torch.randn(8224, 1024, device=dev, dtype=bf)
+    wv, bv = torch.randn(1024, device=dev, dtype=bf), torch.randn(1024, device=dev, dtype=bf)
+    yv, mean, rs = ops.layernorm_fwd(xv, wv, bv, 1e-5)
+    report("layernorm_fwd [8224,1024]", 2 * xv.numel() * 2, lambda: ops.layernorm_fwd(xv, wv, bv, 1e-5, out=yv))
+    dxv = torch.empty_like(xv)
+    dwv, dbv = torch.zeros(1024, device=dev), torch.zeros(1024, device=dev)
+    report("layernorm_bwd [8224,1024]", 3 * xv.numel() * 2, lambda: ops.layernorm_bwd(xv, xv, wv, mean, rs, dx=dxv, dw=dwv, db=dbv))
+    n = 1 << 28
+    p32, m32, v32 = (torch.zeros(n, device=dev) for _ in range(3))
+    g16 = torch.zeros(n, device=dev, dtype=bf)
+    s16 = torch.empty(n, device=dev, dtype=bf)
+    report("adamw (268M params)", 28 * n, lambda: ops.adamw_(p32, g16, m32, v32, s16, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1))
+    ss = torch.zeros((), device=dev)
+    report("sumsq bf16", 2 * n, lambda: ops.sumsq_(g16, ss))
+
+
+if __name__ == "__main__":
+    main()
