@@ -148,3 +148,49 @@ class ActionModel:
         pred = self.net(module, x_t, t32, z, drop_mask)
         assert pred.shape == noise.shape == x.shape
         return MSELossFn.apply(pred, noise)
+
+
+    # ------------------------------------------------------------------ inference (cogact_arch.py:149-198)
+    def ddim_tables(self, ddim_steps: int):
+        """space_timesteps('ddimN') + SpacedDiffusion.__init__ (diffusion.py:990-1080): respaced timestep map and
+        float64 alphas_cumprod / alphas_cumprod_prev."""
+        sa, _ = cosine_schedule(self.num_timesteps)
+        ac = sa ** 2
+        stride = next(i for i in range(1, self.num_timesteps) if len(range(0, self.num_timesteps, i)) == ddim_steps)
+        tmap = list(range(0, self.num_timesteps, stride))
+        last, betas = 1.0, []
+        for i in tmap:
+            betas.append(1 - ac[i] / last)
+            last = ac[i]
+        ac2 = np.cumprod(1.0 - np.array(betas, dtype=np.float64))
+        return tmap, ac2, np.append(1.0, ac2[:-1])
+
+    @torch.no_grad()
+    def sample(self, module, cognition, noise, cfg_scale: float = 1.5, num_ddim_steps: int = 10):
+        """ddim_sample_loop (diffusion.py:714-795) with eta=0, clip_denoised=False, classifier-free guidance through
+        forward_with_cfg (dit.py:294-311).  cognition [B,1,D] fp32, noise [B,T,A] fp32 -> samples [B,T,A]."""
+        B = cognition.shape[0]
+        use_cfg = cfg_scale > 1.0
+        x = torch.cat([noise, noise], 0) if use_cfg else noise
+        if use_cfg:
+            unc = self._param("z_embedder.uncondition", module)[None].expand(B, 1, -1).to(cognition.dtype)
+            z = torch.cat([cognition, unc], 0)
+        else:
+            z = cognition
+        tmap, ac, ac_prev = self.ddim_tables(num_ddim_steps)
+        f32 = lambda v: float(np.float32(v))  # noqa: E731   (_extract_into_tensor: float64 table -> float32)
+        for i in reversed(range(len(tmap))):
+            t = torch.full((x.shape[0],), tmap[i], device=x.device, dtype=torch.int32)
+            if use_cfg:
+                half = x[: x.shape[0] // 2]
+                out = self.net(module, torch.cat([half, half], 0).contiguous(), t, z, None)
+                cond, uncond = out.chunk(2, dim=0)
+                e = uncond + cfg_scale * (cond - uncond)
+                eps_model = torch.cat([e, e], 0)
+            else:
+                eps_model = self.net(module, x.contiguous(), t, z, None)
+            sr, srm1 = f32(np.sqrt(1.0 / ac[i])), f32(np.sqrt(1.0 / ac[i] - 1))
+            pred_x0 = sr * x - srm1 * eps_model
+            eps = (sr * x - pred_x0) / srm1
+            x = pred_x0 * f32(np.sqrt(np.float32(ac_prev[i]))) + f32(np.sqrt(1 - np.float32(ac_prev[i]))) * eps
+        return x[:B] if use_cfg else x

@@ -124,6 +124,23 @@ class CogACTForCausalLM(B200Module):
                                         training=self.training)
         return CausalLMOutputDexbotic(loss=loss, logits=last_hidden_state)
 
+    @torch.no_grad()
+    def inference_action(self, input_ids, image_tensor, inference_args={}, noise: Optional[torch.Tensor] = None, **kwargs):
+        """cogact_arch.py:149-198: one VLM forward -> cognition token -> CFG + DDIM -> denormalised action chunk."""
+        cfg_scale = inference_args.get("cfg_scale", 1.5)
+        num_ddim_steps = inference_args.get("num_ddim_steps", 10)
+        action_norms = inference_args.get("action_norms")
+        out = self.forward(input_ids=input_ids, images=image_tensor)
+        cognition = out.logits[:, -1, :].float()[:, None, :].contiguous()            # :158
+        B = cognition.shape[0]
+        if noise is None:
+            noise = torch.randn(B, self.config.chunk_size, self.config.action_dim, device=cognition.device)
+        samples = self.model_engine.action_head.sample(self, cognition, noise.float(), cfg_scale, num_ddim_steps)
+        actions = np.clip(samples[0].float().cpu().numpy(), -1, 1)                   # _denorm, dexbotic_arch.py:546-563
+        mn = np.array(action_norms["min"]).reshape(1, -1)
+        mx = np.array(action_norms["max"]).reshape(1, -1)
+        return (mn + (actions + 1) * 0.5 * (mx - mn)).tolist()
+
     # ---- training utilities that the reference delegates to HF Trainer / DeepSpeed ------------------
     def zero_grad(self, set_to_none: bool = False):        # noqa: D401
         self.store.zero_grad()

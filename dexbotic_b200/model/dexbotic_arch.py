@@ -421,19 +421,20 @@ class DexboticVLMModel:
         P = self.mm_vision_tower.P
         B, L = input_ids.shape
         if self.mm_vision_tower.keep_layers is None:      # leave room for the decoder's kept activations first
-            need = kept_bytes_per_block(self.llm.blocks[0].cfg, B, L - 1 + P + append_tokens) * 1.08 * len(self.llm.blocks)
+            n_views = images.shape[1] if images.dim() == 5 else 1
+            need = kept_bytes_per_block(self.llm.blocks[0].cfg, B, L - 1 + P * n_views + append_tokens) * 1.08 * len(self.llm.blocks)
             self.mm_vision_tower.decoder_reserve_gb = need / (1 << 30)
         feats, views = self._extract_vision_features(images)
         mask_u8 = None if attention_mask is None else attention_mask.to(torch.uint8).contiguous()
         ids = input_ids.contiguous()
         max_len = cfg.tokenizer_model_max_length or 0
-        if views > 1:
-            raise NotImplementedError("multi-view (5-D images) splice: next round (MemVLA / pi0 rows of SURVEY §8)")
-        lengths = ops.splice_lengths(ids, mask_u8, P, max_len)
+        # 5-D images: the n views of a sample form ONE image entry of n*P tokens (dexbotic_arch.py:163-175)
+        P_entry = P * views
+        lengths = ops.splice_lengths(ids, mask_u8, P_entry, max_len)
         S = int(lengths.max().item())
         left = cfg.tokenizer_padding_side == "left"
-        src, new_labels, new_mask, pos = ops.splice_plan(ids, mask_u8, labels, P, max_len, S, left)
-        # feature rows carry a CLS row per image: entry e, token t lives at row e*(P+1) + 1 + t
+        src, new_labels, new_mask, pos = ops.splice_plan(ids, mask_u8, labels, P_entry, max_len, S, left)
+        # feature rows carry a CLS row per image view: token j of the dense numbering lives at row j + j // P + 1
         src = _shift_image_rows(src, P)
         if append_tokens > 0:
             if left:

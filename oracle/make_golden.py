@@ -296,8 +296,39 @@ def make_pi0_tiny(seed: int = 2468):
     print("[pi0_tiny] wrote fixture; params without grad:", none_grad[:6], len(none_grad))
 
 
+def make_cogact_inference_tiny(seed: int = 1234):
+    """CogACT inference_action (CFG 1.5, 10-step DDIM, eta=0) from the reference (cogact_arch.py:149-198)."""
+    llm, clip, cfg = tiny_cogact_configs()
+    model = ref_loader.build_reference_cogact(llm, clip, "DiT-S")
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    g = torch.Generator().manual_seed(seed + 7)
+    B, L = 2, 11
+    ids = torch.randint(1, 128, (B, L), generator=g)
+    ids[:, 1] = vla_oracle.IMAGE_TOKEN_INDEX
+    images = torch.randn(B, 3, 28, 28, generator=g)
+    norms = {"min": [-1.0] * 7, "max": [1.0] * 7}
+    outs = {}
+    for scale in (1.5, 1.0):
+        model.model.action_head.ddim_diffusion = None
+        torch.manual_seed(seed + 9)
+        acts = model.inference_action(ids, images, {"cfg_scale": scale, "num_ddim_steps": 10, "action_norms": norms})
+        torch.manual_seed(seed + 9)
+        noise = torch.randn(B, 16, 7)                      # cogact_arch.py:161-166
+        ora = vla_oracle.cogact_inference(sd, cfg, ids, images, noise, scale, 10)
+        ref = torch.tensor(acts)
+        d = (ora[0].clamp(-1, 1) - ref).abs().max().item()
+        print(f"[cogact_inference] cfg_scale={scale}: oracle vs reference max|d|={d:.2e}")
+        assert d < 1e-4
+        outs[scale] = dict(noise=noise, actions_sample0=ref, samples=ora.detach())
+    torch.save(dict(seed=seed, cfg=cfg, shapes={k: tuple(v.shape) for k, v in sd.items()},
+                    inputs=dict(input_ids=ids, images=images), outputs=outs), GOLDEN / "cogact_inference_tiny.pt")
+
+
 if __name__ == "__main__":
     make_cogact_tiny()
+    make_cogact_inference_tiny()
     make_pi0_tiny()
     make_oft_discrete_tiny()
     make_splice_cases()

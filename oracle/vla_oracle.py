@@ -291,8 +291,14 @@ def cogact_forward(sd, cfg: dict, input_ids, attention_mask, images, actions, no
 
     noise [R*B,T,A], timesteps [R*B], drop_mask [R*B] are injected (the reference draws them with
     torch.randn_like / randint / rand: action_models.py:106-109, dit.py:86-88)."""
-    feats = clip_vision_features(sd, "model.mm_vision_tower.", images, cfg["vision"])
-    feats = mlp_projector(sd, "model.mm_projector.", feats, cfg.get("projector_depth", 2))
+    if images.dim() == 5:        # [B, n_view, C, H, W]: views are encoded in one batch and concatenated per sample
+        Bv, nv = images.shape[:2]   # (dexbotic_arch.py:163-175)
+        feats = clip_vision_features(sd, "model.mm_vision_tower.", images.flatten(0, 1), cfg["vision"])
+        feats = mlp_projector(sd, "model.mm_projector.", feats, cfg.get("projector_depth", 2))
+        feats = feats.reshape(Bv, nv * feats.shape[1], feats.shape[2])
+    else:
+        feats = clip_vision_features(sd, "model.mm_vision_tower.", images, cfg["vision"])
+        feats = mlp_projector(sd, "model.mm_projector.", feats, cfg.get("projector_depth", 2))
     emb, lab, msk, pid = splice(sd["model.llm.embed_tokens.weight"], feats, input_ids, attention_mask, labels,
                                 cfg.get("tokenizer_model_max_length"), cfg.get("tokenizer_padding_side", "right"))
     hs = decoder_forward(sd, "model.llm.", emb, msk, pid, cfg["llm"])
@@ -499,3 +505,59 @@ def pi0_forward(sd, cfg: dict, input_ids, attention_mask, images, image_masks, a
     v_t = F.linear(suffix_out[:, -T:], sd["model.action_out_proj.weight"], sd["model.action_out_proj.bias"])
     loss = ((v_t - u_t) ** 2).mean()
     return dict(loss=loss, v_t=v_t, u_t=u_t, suffix_out=suffix_out, prefix_tokens=prefix, input_mask=input_mask)
+
+
+# ----------------------------------------------------------------------------------------------
+# CogACT inference — cogact_arch.py:149-198, diffusion.py:626-673 (ddim_sample), :990-1112 (respacing)
+# ----------------------------------------------------------------------------------------------
+def ddim_tables(num_steps: int = 100, ddim_steps: int = 10):
+    """Spaced-diffusion constants: timestep_map and float64 alphas_cumprod / alphas_cumprod_prev of the respaced
+    process (space_timesteps 'ddimN' + SpacedDiffusion.__init__)."""
+    sa, _ = cosine_schedule(num_steps)
+    ac = sa ** 2
+    stride = next(i for i in range(1, num_steps) if len(range(0, num_steps, i)) == ddim_steps)
+    tmap = list(range(0, num_steps, stride))
+    last, betas = 1.0, []
+    for i in tmap:
+        betas.append(1 - ac[i] / last)
+        last = ac[i]
+    ac2 = np.cumprod(1.0 - np.array(betas, dtype=np.float64))
+    return tmap, ac2, np.append(1.0, ac2[:-1])
+
+
+def cogact_inference(sd, cfg: dict, input_ids, images, noise, cfg_scale: float = 1.5, num_ddim_steps: int = 10):
+    """CogACTForCausalLM.inference_action up to (excluding) _denorm: returns samples [B, T, A] (normalised actions)."""
+    feats = clip_vision_features(sd, "model.mm_vision_tower.", images, cfg["vision"])
+    feats = mlp_projector(sd, "model.mm_projector.", feats, cfg.get("projector_depth", 2))
+    emb, _, msk, pid = splice(sd["model.llm.embed_tokens.weight"], feats, input_ids, None, None,
+                              cfg.get("tokenizer_model_max_length"), "right")
+    hs = decoder_forward(sd, "model.llm.", emb, msk, pid, cfg["llm"])
+    cog = hs[:, -1, :][:, None]                                             # :158
+    B = cog.shape[0]
+    width = sd["model.action_head.net.x_embedder.linear.weight"].shape[0]
+    heads = DIT_HEADS[width]
+    use_cfg = cfg_scale > 1.0
+    x = noise
+    if use_cfg:
+        x = torch.cat([noise, noise], 0)
+        unc = sd["model.action_head.net.z_embedder.uncondition"][None].expand(B, 1, -1)
+        z = torch.cat([cog, unc], 0)
+    else:
+        z = cog
+    tmap, ac, ac_prev = ddim_tables(cfg.get("diffusion_steps", 100), num_ddim_steps)
+    f32 = lambda v: torch.tensor(v, dtype=torch.float64).float()          # noqa: E731 (_extract_into_tensor)
+    for i in reversed(range(len(tmap))):
+        t = torch.full((x.shape[0],), tmap[i], dtype=torch.long)
+        if use_cfg:                                                          # forward_with_cfg, dit.py:294-311
+            half = x[: x.shape[0] // 2]
+            out = dit_forward(sd, "model.action_head.", torch.cat([half, half], 0), t, z, None, heads)
+            cond, uncond = out.chunk(2, dim=0)
+            e = uncond + cfg_scale * (cond - uncond)
+            eps_model = torch.cat([e, e], 0)
+        else:
+            eps_model = dit_forward(sd, "model.action_head.", x, t, z, None, heads)
+        sr, srm1 = f32(np.sqrt(1.0 / ac[i])), f32(np.sqrt(1.0 / ac[i] - 1))
+        pred_x0 = sr * x - srm1 * eps_model                                  # _predict_xstart_from_eps
+        eps = (sr * x - pred_x0) / srm1                                      # _predict_eps_from_xstart
+        x = pred_x0 * torch.sqrt(f32(ac_prev[i])) + torch.sqrt(1 - f32(ac_prev[i])) * eps   # eta = 0
+    return x[:B] if use_cfg else x

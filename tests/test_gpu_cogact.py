@@ -194,6 +194,48 @@ def test_cogact_production_dims_one_layer_matches_oracle():
         assert not bad, (recompute, bad)
 
 
+def test_cogact_multi_view_images_match_oracle():
+    """5-D images [B, n_view, C, H, W]: one <image> token expands to n_view * P tokens (dexbotic_arch.py:163-175);
+    the MemVLA / multi-camera input layout of BASELINE.json config 5."""
+    from oracle import vla_oracle
+    from oracle.weights import seeded_state_dict
+    fx = torch.load(GOLDEN / "cogact_tiny.pt", weights_only=False)
+    model, sd = _build(fx["cfg"], fx["shapes"], fx["seed"])
+    model.train()
+    g = torch.Generator().manual_seed(21)
+    i = fx["inputs"]
+    B = i["input_ids"].shape[0]
+    images = torch.randn(B, 3, 3, 28, 28, generator=g)
+    sd_full = seeded_state_dict(fx["shapes"], fx["seed"])
+    ora = vla_oracle.cogact_forward(sd_full, fx["cfg"], i["input_ids"], i["attention_mask"], images, i["actions"],
+                                    i["noise"], i["timesteps"], i["drop_mask"], 4)
+    out = model(input_ids=i["input_ids"].cuda(), attention_mask=i["attention_mask"].cuda(), images=images.cuda(),
+                actions=i["actions"].cuda(), noise=i["noise"].cuda(), timesteps=i["timesteps"].cuda(),
+                drop_mask=i["drop_mask"].cuda())
+    assert out.logits.shape[1] == ora["last_hidden"].shape[1] == 13 + 3 * 4
+    assert abs(out.loss.item() - ora["loss"].item()) < 2e-2 * abs(ora["loss"].item())
+    valid = ora["attention_mask"][:, :, None]
+    rel, cos = _rel(out.logits.float().cpu() * valid, ora["last_hidden"] * valid)
+    assert rel < 3e-2 and cos > 0.999, (rel, cos)
+    out.loss.backward()
+
+
+@pytest.mark.parametrize("scale", [1.5, 1.0])
+def test_cogact_inference_action_matches_reference(scale):
+    """inference_action (CFG + 10-step DDIM, eta=0; cogact_arch.py:149-198) against the reference's own output."""
+    fx = torch.load(GOLDEN / "cogact_inference_tiny.pt", weights_only=False)
+    model, _ = _build(fx["cfg"], fx["shapes"], fx["seed"])
+    model.eval()
+    o = fx["outputs"][scale]
+    acts = model.inference_action(fx["inputs"]["input_ids"].cuda(), fx["inputs"]["images"].cuda(),
+                                  {"cfg_scale": scale, "num_ddim_steps": 10,
+                                   "action_norms": {"min": [-1.0] * 7, "max": [1.0] * 7}}, noise=o["noise"].cuda())
+    got, ref = torch.tensor(acts), o["actions_sample0"]
+    assert got.shape == ref.shape == (16, 7)
+    # ten DiT evaluations amplify the bf16 rounding of the cognition token: 5e-2 absolute on actions in [-1, 1]
+    assert (got - ref).abs().max().item() < 5e-2, (got - ref).abs().max().item()
+
+
 def test_training_steps_reduce_loss():
     fx = torch.load(GOLDEN / "cogact_tiny.pt", weights_only=False)
     model, _ = _build(fx["cfg"], fx["shapes"], fx["seed"])

@@ -105,3 +105,14 @@ def test_pi0_attn_mask_truth_table():
                  [1, 1, 0, 1, 0, 0],
                  [1, 1, 0, 1, 1, 1],
                  [1, 1, 0, 1, 1, 1]]
+
+
+def test_cogact_inference_matches_reference():
+    fx = torch.load(GOLDEN / "cogact_inference_tiny.pt", weights_only=False)
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    for scale, o in fx["outputs"].items():
+        x = vla_oracle.cogact_inference(sd, fx["cfg"], fx["inputs"]["input_ids"], fx["inputs"]["images"], o["noise"],
+                                        scale, 10)
+        assert (x[0].clamp(-1, 1) - o["actions_sample0"]).abs().max().item() < 1e-4
+    tmap, ac, ac_prev = vla_oracle.ddim_tables(100, 10)
+    assert tmap == list(range(0, 100, 10)) and ac_prev[0] == 1.0 and abs(ac[0] - 0.999684309 ** 2) < 1e-8
