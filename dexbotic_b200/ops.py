@@ -165,6 +165,23 @@ def _qkv_ptrs(qkv: torch.Tensor, sh: AttnShape):
     return base, base + sh.H * sh.hd * es, base + (sh.H + sh.KVH) * sh.hd * es
 
 
+def _fused_scores_ok(qkv: torch.Tensor, sh: AttnShape) -> bool:
+    import os
+    return (qkv.dtype == torch.bfloat16 and sh.hd <= 128 and sh.S <= 512 and
+            os.environ.get("B200_FUSED_ATTN_SCORES", "1") != "0")
+
+
+def attn_scores(a_ptr: int, a_ld: int, a_s_head: int, a_s_batch: int, b_ptr: int, b_ld: int, b_s_head: int,
+                b_s_batch: int, sh: AttnShape, out: torch.Tensor, *, p_in: Optional[torch.Tensor] = None, keymask=None,
+                bid_q=None, bid_k=None, causal: bool = False) -> torch.Tensor:
+    """mode 0 (p_in None): out = softmax_mask(scale * A B^T); mode 1: out = scale * P * (A B^T - rowsum(P * A B^T))."""
+    _lib.check(_lib.load().b200_attn_scores(a_ptr, b_ptr, _p(p_in), out.data_ptr(), sh.B, sh.H, sh.KVH, sh.S, sh.S,
+                                            sh.hd, a_ld, a_s_head, a_s_batch, b_ld, b_s_head, b_s_batch, sh.ld_p,
+                                            float(sh.scale), int(causal), _p(keymask), _p(bid_q), _p(bid_k),
+                                            0 if p_in is None else 1, _stream()), "attn_scores")
+    return out
+
+
 def attention_fwd(qkv: torch.Tensor, sh: AttnShape, *, keymask: Optional[torch.Tensor] = None,
                   bid_q: Optional[torch.Tensor] = None, bid_k: Optional[torch.Tensor] = None, causal: bool = False,
                   scores: Optional[torch.Tensor] = None, probs: Optional[torch.Tensor] = None,
@@ -174,19 +191,23 @@ def attention_fwd(qkv: torch.Tensor, sh: AttnShape, *, keymask: Optional[torch.T
     B, S, H, KVH, hd, G, W = sh.B, sh.S, sh.H, sh.KVH, sh.hd, sh.G, sh.W
     dt = _dt(qkv)
     dev = qkv.device
-    if scores is None:
-        scores = torch.empty((B, H, S, sh.ld_s), device=dev, dtype=torch.float32)
     if probs is None:
         probs = torch.empty((B, H, S, sh.ld_p), device=dev, dtype=qkv.dtype)
     if out is None:
         out = torch.empty((B, S, H * hd), device=dev, dtype=qkv.dtype)
     q, k, v = _qkv_ptrs(qkv, sh)
-    # scores = scale * Q K^T
-    gemm_raw(a=q, b=k, d=scores.data_ptr(), ab_dtype=dt, d_dtype=F32, a_mn_major=0, b_mn_major=0, m=S, n=S, k=hd,
-             a_ld=W, a_s2=hd, a_s3=S * W, a_z2=H, b_ld=W, b_s2=hd, b_s3=S * W, b_z2=KVH,
-             d_ld=sh.ld_s, d_s2=S * sh.ld_s, d_s3=H * S * sh.ld_s, z_lo=H, z_hi=B,
-             a_div=1, a_mul=1, a_seg=0, b_div=G, b_mul=1, b_seg=0, k_segs=1, alpha=sh.scale)
-    softmax_fwd(scores, probs, S, S, heads=H, keymask=keymask, bid_q=bid_q, bid_k=bid_k, causal=causal)
+    if _fused_scores_ok(qkv, sh):
+        # scores stay in TMEM: P = softmax(scale * Q K^T) is written once, as bf16
+        attn_scores(q, W, hd, S * W, k, W, hd, S * W, sh, probs, keymask=keymask, bid_q=bid_q, bid_k=bid_k,
+                    causal=causal)
+    else:
+        if scores is None:
+            scores = torch.empty((B, H, S, sh.ld_s), device=dev, dtype=torch.float32)
+        gemm_raw(a=q, b=k, d=scores.data_ptr(), ab_dtype=dt, d_dtype=F32, a_mn_major=0, b_mn_major=0, m=S, n=S, k=hd,
+                 a_ld=W, a_s2=hd, a_s3=S * W, a_z2=H, b_ld=W, b_s2=hd, b_s3=S * W, b_z2=KVH,
+                 d_ld=sh.ld_s, d_s2=S * sh.ld_s, d_s3=H * S * sh.ld_s, z_lo=H, z_hi=B,
+                 a_div=1, a_mul=1, a_seg=0, b_div=G, b_mul=1, b_seg=0, k_segs=1, alpha=sh.scale)
+        softmax_fwd(scores, probs, S, S, heads=H, keymask=keymask, bid_q=bid_q, bid_k=bid_k, causal=causal)
     # out = P V
     gemm_raw(a=probs.data_ptr(), b=v, d=out.data_ptr(), ab_dtype=dt, d_dtype=dt, a_mn_major=0, b_mn_major=1,
              m=S, n=hd, k=S, a_ld=sh.ld_p, a_s2=S * sh.ld_p, a_s3=H * S * sh.ld_p, a_z2=H,
@@ -195,7 +216,7 @@ def attention_fwd(qkv: torch.Tensor, sh: AttnShape, *, keymask: Optional[torch.T
     return out, probs
 
 
-def attention_bwd(dout: torch.Tensor, qkv: torch.Tensor, probs: torch.Tensor, sh: AttnShape, *,
+def attention_bwd(dout: torch.Tensor, qkv: torch.Tensor, probs: torch.Tensor, sh: AttnShape, *, causal: bool = False,
                   dqkv: Optional[torch.Tensor] = None, scratch: Optional[torch.Tensor] = None,
                   dprobs: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Gradient of attention_fwd w.r.t. the packed qkv buffer (before the inverse RoPE)."""
@@ -206,25 +227,29 @@ def attention_bwd(dout: torch.Tensor, qkv: torch.Tensor, probs: torch.Tensor, sh
     assert dout.is_contiguous() and dout.shape == (B, S, H * hd)
     if dqkv is None:
         dqkv = torch.empty_like(qkv)
-    if scratch is None:
-        scratch = torch.empty((B, H, S, sh.ld_s), device=dev, dtype=torch.float32)
     if dprobs is None:
         dprobs = torch.empty_like(probs)
     q, k, v = _qkv_ptrs(qkv, sh)
     dq, dk, dv = _qkv_ptrs(dqkv, sh)
     ldp, lds = sh.ld_p, sh.ld_s
-    # dP = dO V^T   (fp32)
-    gemm_raw(a=dout.data_ptr(), b=v, d=scratch.data_ptr(), ab_dtype=dt, d_dtype=F32, a_mn_major=0, b_mn_major=0,
-             m=S, n=S, k=hd, a_ld=H * hd, a_s2=hd, a_s3=S * H * hd, a_z2=H, b_ld=W, b_s2=hd, b_s3=S * W, b_z2=KVH,
-             d_ld=lds, d_s2=S * lds, d_s3=H * S * lds, z_lo=H, z_hi=B, a_div=1, a_mul=1, a_seg=0, b_div=G, b_mul=1,
-             b_seg=0, k_segs=1, alpha=1.0)
     # dV = sum_g P_g^T dO_g
     gemm_raw(a=probs.data_ptr(), b=dout.data_ptr(), d=dv, ab_dtype=dt, d_dtype=dt, a_mn_major=1, b_mn_major=1,
              m=S, n=hd, k=S, a_ld=ldp, a_s2=S * ldp, a_s3=H * S * ldp, a_z2=H, b_ld=H * hd, b_s2=hd,
              b_s3=S * H * hd, b_z2=H, d_ld=W, d_s2=hd, d_s3=S * W, z_lo=KVH, z_hi=B, a_div=1, a_mul=G, a_seg=1,
              b_div=1, b_mul=G, b_seg=1, k_segs=G, alpha=1.0)
-    # dS = scale * P * (dP - rowsum(P dP))
-    softmax_bwd(probs, scratch, dprobs, B * H * S, S, ldp, lds, ldp, sh.scale)
+    if _fused_scores_ok(qkv, sh):
+        # dS = scale * P * (dO V^T - rowsum(P * dO V^T)): dP never leaves TMEM
+        attn_scores(dout.data_ptr(), H * hd, hd, S * H * hd, v, W, hd, S * W, sh, dprobs, p_in=probs, causal=causal)
+    else:
+        if scratch is None:
+            scratch = torch.empty((B, H, S, sh.ld_s), device=dev, dtype=torch.float32)
+        # dP = dO V^T   (fp32)
+        gemm_raw(a=dout.data_ptr(), b=v, d=scratch.data_ptr(), ab_dtype=dt, d_dtype=F32, a_mn_major=0, b_mn_major=0,
+                 m=S, n=S, k=hd, a_ld=H * hd, a_s2=hd, a_s3=S * H * hd, a_z2=H, b_ld=W, b_s2=hd, b_s3=S * W,
+                 b_z2=KVH, d_ld=lds, d_s2=S * lds, d_s3=H * S * lds, z_lo=H, z_hi=B, a_div=1, a_mul=1, a_seg=0,
+                 b_div=G, b_mul=1, b_seg=0, k_segs=1, alpha=1.0)
+        # dS = scale * P * (dP - rowsum(P dP))
+        softmax_bwd(probs, scratch, dprobs, B * H * S, S, ldp, lds, ldp, sh.scale)
     # dQ = dS K
     gemm_raw(a=dprobs.data_ptr(), b=k, d=dq, ab_dtype=dt, d_dtype=dt, a_mn_major=0, b_mn_major=1, m=S, n=hd, k=S,
              a_ld=ldp, a_s2=S * ldp, a_s3=H * S * ldp, a_z2=H, b_ld=W, b_s2=hd, b_s3=S * W, b_z2=KVH,

@@ -67,6 +67,16 @@ int b200_softmax_fwd(const float* scores, void* p, int64_t Z, int64_t Sq, int64_
 int b200_softmax_bwd(const void* p, const float* dp, void* ds, int64_t rows, int64_t Sk, int64_t p_ld, int64_t dp_ld,
                      int64_t ds_ld, float scale, int p_dtype, void* stream);
 
+/* Fused attention scores (bf16, head_dim <= 128, Sk <= 512): the [128 x Sk] score block of a (batch, head, query
+ * tile) stays in TMEM.  mode 0: P = masked softmax(scale * A B^T) with A = Q, B = K;  mode 1: dS = scale * P *
+ * (A B^T - rowsum(P * A B^T)) with A = dO, B = V.  A: (hd, Sq, H, B) / B: (hd, Sk, KVH, B) strided views (element
+ * strides a_ld / a_s_head / a_s_batch ...), out / p_in: [B*H, Sq, p_ld] bf16.  Mask rule as b200_softmax_fwd.
+ * Replaces QK^T + softmax (and dP + softmax backward) of HF attention without an fp32 score round trip. */
+int b200_attn_scores(const void* a, const void* b, const void* p_in, void* out, int64_t B, int64_t H, int64_t KVH,
+                     int64_t Sq, int64_t Sk, int64_t head_dim, int64_t a_ld, int64_t a_s_head, int64_t a_s_batch,
+                     int64_t b_ld, int64_t b_s_head, int64_t b_s_batch, int64_t p_ld, float scale, int causal,
+                     const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k, int mode, void* stream);
+
 /* out[N] (fp32) += column sums of x[M,N]  (bias gradients) */
 int b200_colsum(const void* x, float* out, int64_t M, int64_t N, int dtype, void* stream);
 /* *out (fp32) += sum(x^2)  (global grad-norm, trainer.py:122 max_grad_norm=1.0) */

@@ -158,6 +158,9 @@ def _ref_attention(qkv, B, S, H, KVH, hd, keymask, bid):
     (4, 17, 4, 4, 96, False, torch.float32),
     (2, 50, 8, 1, 256, True, torch.bfloat16),
     (1, 1100, 4, 2, 64, True, torch.bfloat16),     # S >= 1024: batched GEMMs take the CTA-pair path
+    (2, 365, 28, 4, 128, True, torch.bfloat16),    # OFT length: 384 + 128 TMEM columns
+    (2, 512, 4, 4, 72, False, torch.bfloat16),     # SigLIP head_dim 72, Sk = 512 (TMEM full)
+    (2, 130, 2, 1, 96, True, torch.bfloat16),
 ])
 def test_attention_fwd_bwd(B, S, H, KVH, hd, causal, dtype):
     o = ops()
@@ -167,7 +170,10 @@ def test_attention_fwd_bwd(B, S, H, KVH, hd, causal, dtype):
     keymask = (torch.arange(S, device=DEV)[None, :] < lens[:, None]).to(torch.uint8) if causal else None
     bid = torch.arange(S, device=DEV, dtype=torch.int32)[None, :].expand(B, S).contiguous() if causal else None
     sh = o.AttnShape(B, S, H, KVH, hd, dtype)
-    out, probs = o.attention_fwd(qkv, sh, keymask=keymask, bid_q=bid, bid_k=bid)
+    if causal and S % 2 == 1:      # exercise the index-causal fast path as well as the block-id rule
+        out, probs = o.attention_fwd(qkv, sh, keymask=keymask, causal=True)
+    else:
+        out, probs = o.attention_fwd(qkv, sh, keymask=keymask, bid_q=bid, bid_k=bid)
 
     qkv_ref = qkv.float().requires_grad_(True)
     ref = _ref_attention(qkv_ref, B, S, H, KVH, hd, keymask, bid)
@@ -175,7 +181,7 @@ def test_attention_fwd_bwd(B, S, H, KVH, hd, causal, dtype):
     _check(out * rowmask, ref * rowmask, S, dtype, "attention fwd")
 
     dout = _rand((B, S, H * hd), dtype, 21) * rowmask.to(dtype)
-    dqkv = o.attention_bwd(dout, qkv, probs, sh)
+    dqkv = o.attention_bwd(dout, qkv, probs, sh, causal=bool(causal and S % 2 == 1))
     (ref * rowmask).backward(dout.float())
     _check(dqkv, qkv_ref.grad, S * 4, dtype, "attention bwd")
 
