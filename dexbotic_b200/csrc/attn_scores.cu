@@ -21,7 +21,11 @@
 namespace b200 {
 
 using bf16 = __nv_bfloat16;
-constexpr int kAttnThreads = 160;  // warp 0: TMA + MMA + TMEM alloc; warps 1-4: one TMEM lane quarter each
+// warp 0: TMA + MMA + TMEM alloc; warps 1-16: epilogue — warp w reads TMEM lane quarter (w & 3) and the 32-column
+// chunks c with c % 4 == (w - 1) / 4, so every query row is shared by four threads (softmax is issue-bound: exp +
+// masking per score; 4 warps per SM were the bottleneck)
+constexpr int kAttnThreads = 32 + 16 * 32;
+constexpr int kColGroups = 4;
 constexpr int kAttnMaxSk = 512;
 
 struct AttnKParams {
@@ -40,6 +44,12 @@ struct AttnKParams {
   int m_tiles;
 };
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void store8_bf16(bf16* p, const float* v) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
   __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
@@ -56,6 +66,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar_load, bar_mma;
   __shared__ uint32_t tmem_slot;
+  __shared__ float red[kColGroups][128], red2[kColGroups][128];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x % p.m_tiles;
@@ -116,60 +127,88 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
   } else {
     // ------------------------------------------------------------- epilogue
     const int quarter = warp & 3;
-    const int q = m0 + quarter * 32 + lane;
+    const int cg = (warp - 1) >> 2;                 // column group: chunks cg, cg + 4, cg + 8, ...
+    const int rt = quarter * 32 + lane;             // row inside the tile == TMEM lane
+    const int q = m0 + rt;
     const bool row_ok = q < p.Sq;
     const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint8_t* km = p.keymask != nullptr ? p.keymask + (size_t)b * p.Sk : nullptr;
     const int* bk = (!p.causal && p.bid_k != nullptr) ? p.bid_k + (size_t)b * p.Sk : nullptr;
-    const int bq = (!p.causal && p.bid_q != nullptr && row_ok) ? p.bid_q[(size_t)b * p.Sq + q] : 0;
+    const int bq = (bk != nullptr && row_ok) ? p.bid_q[(size_t)b * p.Sq + q] : 0;
     const int limit = p.causal ? min(n_eff, q + 1) : n_eff;
     const long long row_off = ((long long)z * p.Sq + q) * p.ld;
     bf16* orow = p.out + row_off;
     const bf16* prow = p.mode == 1 ? p.p_in + row_off : nullptr;
+    const int n_chunks = (n_mma + 31) >> 5;
+    constexpr int kMaxOwn = (kAttnMaxSk / 32 + kColGroups - 1) / kColGroups;   // chunks one thread can own (4)
+    // validity bits of this thread's chunks: the key-padding byte of key c*32+j is loaded once by lane j and
+    // shared with a ballot; the causal / length limit is a per-row bit count
+    uint32_t okbits[kMaxOwn];
+#pragma unroll
+    for (int i = 0; i < kMaxOwn; ++i) {
+      const int c = cg + i * kColGroups;
+      uint32_t w = 0;
+      if (c < n_chunks) {
+        const int k = c * 32 + lane;
+        const bool kv = k < p.Sk && (km == nullptr || km[k] != 0);
+        w = __ballot_sync(0xffffffffu, kv);
+        const int rem = limit - c * 32;
+        w &= rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+        if (bk != nullptr) {                      // generic block-id rule (pi0-style masks): per-element compare
+          uint32_t w2 = 0;
+          for (int j = 0; j < 32; ++j) {
+            const int kk = c * 32 + j;
+            if (kk < p.Sk && bk[kk] <= bq) w2 |= 1u << j;
+          }
+          w &= w2;
+        }
+      }
+      okbits[i] = w;
+    }
     mbar_wait(&bar_mma, 0);
     tc_fence_after();
-    const int n_chunks = (n_mma + 31) >> 5;
+    const float sl2 = p.scale * 1.4426950408889634f;   // exp(x * scale - m) = exp2(x * sl2 - m * log2e)
     uint32_t r[32];
     if (p.mode == 0) {
       float mx = -INFINITY;
-      for (int c = 0; c < n_chunks; ++c) {
+#pragma unroll
+      for (int i = 0; i < kMaxOwn; ++i) {
+        const int c = cg + i * kColGroups;
+        if (c >= n_chunks) break;
         tmem_ld_32x32(trow + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int k = c * 32 + j;
-          bool ok = k < limit;
-          if (ok && km != nullptr) ok = km[k] != 0;
-          if (ok && bk != nullptr) ok = bk[k] <= bq;
-          if (ok) mx = fmaxf(mx, __uint_as_float(r[j]) * p.scale);
-        }
+        for (int j = 0; j < 32; ++j)
+          if ((okbits[i] >> j) & 1u) mx = fmaxf(mx, __uint_as_float(r[j]) * sl2);
       }
+      red[cg][rt] = mx;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      mx = fmaxf(fmaxf(red[0][rt], red[1][rt]), fmaxf(red[2][rt], red[3][rt]));
       float sum = 0.0f;
-      for (int c = 0; c < n_chunks; ++c) {
+#pragma unroll
+      for (int i = 0; i < kMaxOwn; ++i) {
+        const int c = cg + i * kColGroups;
+        if (c >= n_chunks) break;
         tmem_ld_32x32(trow + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int k = c * 32 + j;
-          bool ok = k < limit;
-          if (ok && km != nullptr) ok = km[k] != 0;
-          if (ok && bk != nullptr) ok = bk[k] <= bq;
-          if (ok) sum += __expf(__uint_as_float(r[j]) * p.scale - mx);
-        }
+        for (int j = 0; j < 32; ++j)
+          if ((okbits[i] >> j) & 1u) sum += fast_exp2(__uint_as_float(r[j]) * sl2 - mx);
       }
+      red2[cg][rt] = sum;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      sum = (red2[0][rt] + red2[1][rt]) + (red2[2][rt] + red2[3][rt]);
       const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
-      for (int c = 0; c < n_chunks; ++c) {
+#pragma unroll
+      for (int i = 0; i < kMaxOwn; ++i) {
+        const int c = cg + i * kColGroups;
+        if (c >= n_chunks) break;
         tmem_ld_32x32(trow + c * 32, r);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int k = c * 32 + j;
-          bool ok = k < limit;
-          if (ok && km != nullptr) ok = km[k] != 0;
-          if (ok && bk != nullptr) ok = bk[k] <= bq;
-          v[j] = ok ? __expf(__uint_as_float(r[j]) * p.scale - mx) * inv : 0.0f;
-        }
+        for (int j = 0; j < 32; ++j)
+          v[j] = ((okbits[i] >> j) & 1u) ? fast_exp2(__uint_as_float(r[j]) * sl2 - mx) * inv : 0.0f;
         if (row_ok) {
 #pragma unroll
           for (int g = 0; g < 4; ++g)
@@ -178,7 +217,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
       }
     } else {
       float delta = 0.0f;
-      for (int c = 0; c < n_chunks; ++c) {
+#pragma unroll
+      for (int i = 0; i < kMaxOwn; ++i) {
+        const int c = cg + i * kColGroups;
+        if (c >= n_chunks) break;
         tmem_ld_32x32(trow + c * 32, r);
         tmem_ld_wait();
         if (row_ok) {
@@ -197,7 +239,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
           }
         }
       }
-      for (int c = 0; c < n_chunks; ++c) {
+      red[cg][rt] = delta;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      delta = (red[0][rt] + red[1][rt]) + (red[2][rt] + red[3][rt]);
+#pragma unroll
+      for (int i = 0; i < kMaxOwn; ++i) {
+        const int c = cg + i * kColGroups;
+        if (c >= n_chunks) break;
         tmem_ld_32x32(trow + c * 32, r);
         tmem_ld_wait();
         if (row_ok) {
@@ -224,7 +272,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
     // columns beyond this tile's visible keys are zero (the P V / dS K GEMMs read whole rows)
     if (row_ok) {
       const float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int k0 = n_chunks * 32; k0 < p.ld; k0 += 8) store8_bf16(orow + k0, zero);
+      for (int k0 = n_chunks * 32 + cg * 8; k0 < p.ld; k0 += 8 * kColGroups) store8_bf16(orow + k0, zero);
     }
     tc_fence_before();
   }
