@@ -421,6 +421,123 @@ class Pi0ForCausalLM(B200Module):
             self._rope = (f.cos().contiguous(), f.sin().contiguous())
         return self._rope
 
+    def _embed_prefix(self, input_ids, attention_mask, images, image_masks):
+        """embed_prefix (pi0_arch.py:235-269): all cameras through SigLIP in one batch (camera-major), linear
+        projector, text embeddings * sqrt(hidden).  Returns (prefix [B*Sp, d], prefix_mask [B, Sp] bool, Sp)."""
+        st = self.store
+        B, n_cam, L = images.shape[0], images.shape[1], input_ids.shape[1]
+        imgs = images.transpose(0, 1).reshape(n_cam * B, *images.shape[2:])
+        if self.tower.g_patch is None:
+            with torch.no_grad():
+                f = self.tower.forward(self.anchor, imgs)
+        else:
+            f = self.tower.forward(self.anchor, imgs)
+        f = LinearFn.apply(f, self.proj, None, st, self.tower.g_patch is not None, self.anchor.t)
+        P = self.tower.P
+        prefix = PrefixEmbedFn.apply(f, input_ids.to(torch.int32).contiguous(), self.embed_w, self.embed_g, st, B, n_cam,
+                                     P, L)
+        prefix_mask = torch.cat([image_masks.bool()[:, :, None].expand(B, n_cam, P).reshape(B, n_cam * P),
+                                 attention_mask.bool()], dim=1)
+        return prefix, prefix_mask, n_cam * P + L
+
+    def _embed_suffix(self, states, x_t, time):
+        """embed_suffix (pi0_arch.py:271-315): [state token | action_time_mlp(action_in(x_t) ++ posemb(time))]."""
+        st, bf = self.store, torch.bfloat16
+        B, T, A = x_t.shape
+        state_tok = LinearFn.apply(states.to(bf).contiguous(), self.state_proj, None, st, False, self.anchor.t)
+        a_tok = LinearFn.apply(x_t.to(bf).reshape(B * T, A).contiguous(), self.action_in, None, st, False, self.anchor.t)
+        temb = posemb_sincos(time, self.w, 4e-3, 4.0).to(bf)[:, None, :].expand(B, T, self.w)
+        at = torch.cat([a_tok.view(B, T, self.w), temb], dim=-1).reshape(B * T, 2 * self.w).contiguous()
+        at = LinearFn.apply(at, self.mlp_in, "silu", st, True, None)
+        at = LinearFn.apply(at, self.mlp_out, None, st, True, None)
+        suffix = torch.cat([state_tok.view(B, 1, self.w), at.view(B, T, self.w)], dim=1)
+        return suffix.reshape(B * (T + 1), self.w).contiguous()
+
+    @staticmethod
+    def _stream_tail(x, attn2d, sw: StreamW, act):
+        """o_proj + residual, post-attention norm, GeGLU MLP + residual (pi0_arch.py:205-212), inference form."""
+        x1, _ = linear_fwd(attn2d, sw.o, residual=x)
+        h2, _ = norm_fwd(x1, sw.norm2)
+        g, _ = linear_fwd(h2, sw.gate)
+        u, _ = linear_fwd(h2, sw.up)
+        y, _ = linear_fwd(ops.glu_fwd(g, u, act), sw.down, residual=x1)
+        return y
+
+    @torch.no_grad()
+    def inference_action(self,
+                         input_ids: torch.LongTensor = None,
+                         attention_mask: Optional[torch.Tensor] = None,
+                         states: Optional[torch.FloatTensor] = None,
+                         images: Optional[torch.FloatTensor] = None,
+                         image_masks: Optional[torch.BoolTensor] = None,
+                         diffusion_steps: int = 10,
+                         noise: Optional[torch.Tensor] = None,     # parity hook: the reference draws it inside
+                         **kwargs) -> torch.Tensor:
+        """pi0_arch.py:402-491.  One prefix pass through the Gemma stream that leaves the RoPE'd K and V of every
+        layer in a [B, Sp+Ss, 2*KVH*hd] cache, then `diffusion_steps` Euler steps in which only the Ss = chunk+1
+        suffix rows run through the action expert and attend over [cached prefix | own] keys."""
+        if not states.is_cuda:
+            raise RuntimeError("dexbotic_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        cfg, dev = self.config, states.device
+        B, T, A = states.shape[0], cfg.chunk_size, cfg.action_dim
+        H, KVH, hd = self.H, self.KVH, self.hd
+        W, C, Wkv = (H + 2 * KVH) * hd, H * hd, 2 * KVH * hd
+        if noise is None:
+            noise = torch.randn(B, T, A, device=dev)                         # :417-422
+        x_t = noise.float()
+        prefix, prefix_mask, Sp = self._embed_prefix(input_ids, attention_mask, images, image_masks)
+        Ss = T + 1
+        S = Sp + Ss
+        pm = prefix_mask.to(torch.int32)
+        pos_p = (torch.cumsum(pm, dim=1) - 1).clamp_(min=0).to(torch.int32).reshape(-1).contiguous()
+        pos_s = (pm.sum(dim=1, keepdim=True) + torch.arange(Ss, device=dev, dtype=torch.int32)[None, :])
+        pos_s = pos_s.to(torch.int32).reshape(-1).contiguous()                # :465-469
+        cos, sin = self._rope_tables(S + 1, dev)
+        keymask_p = prefix_mask.to(torch.uint8).contiguous()
+        keymask = torch.cat([keymask_p, torch.ones(B, Ss, dtype=torch.uint8, device=dev)], dim=1).contiguous()
+        blk = torch.cat([torch.zeros(Sp, dtype=torch.int32, device=dev),     # make_attn_mask (:22-29): cumsum(ar)
+                         torch.ones(1, dtype=torch.int32, device=dev),
+                         torch.full((T,), 2, dtype=torch.int32, device=dev)])
+        bid_k = blk[None, :].expand(B, S).contiguous()
+        bid_q = blk[None, Sp:].expand(B, Ss).contiguous()
+
+        # ---- prefix pass (:432-444): fill the K/V cache; the last layer's post-attention half is never read
+        caches = []
+        x = prefix
+        shp = ops.AttnShape(B, Sp, H, KVH, hd, x.dtype)
+        for i, (sw_p, _) in enumerate(self.layers):
+            h, _ = norm_fwd(x, sw_p.norm1)
+            qkv, _ = linear_fwd(h, sw_p.qkv)
+            ops.rope_(qkv.view(B, Sp, W), pos_p, cos, sin, H + KVH, hd)
+            kv = torch.empty((B, S, Wkv), device=dev, dtype=x.dtype)
+            ops.copy3d_(qkv, kv, B, Sp, Wkv, Sp * W, W, S * Wkv, Wkv, src_off=C)
+            caches.append(kv)
+            if i == len(self.layers) - 1:
+                break
+            attn, _ = ops.attention_fwd(qkv.view(B, Sp, W), shp, keymask=keymask_p)
+            x = self._stream_tail(x, attn.view(B * Sp, C), sw_p, self.act)
+
+        # ---- Euler steps (:446-489)
+        dt = np.float32(-1.0 / diffusion_steps)
+        t = np.float32(1.0)
+        while t > -dt / 2:
+            time = torch.full((B,), float(t), dtype=torch.float32, device=dev)
+            xs = self._embed_suffix(states, x_t, time)
+            for i, (_, sw_s) in enumerate(self.layers):
+                h, _ = norm_fwd(xs, sw_s.norm1)
+                qkv, _ = linear_fwd(h, sw_s.qkv)
+                ops.rope_(qkv.view(B, Ss, W), pos_s, cos, sin, H + KVH, hd)
+                ops.copy3d_(qkv, caches[i], B, Ss, Wkv, Ss * W, W, S * Wkv, Wkv, src_off=C, dst_off=Sp * Wkv)
+                attn = ops.attention_cross(qkv.view(B, Ss, W), caches[i], B, Ss, S, H, KVH, hd, keymask=keymask,
+                                           bid_q=bid_q, bid_k=bid_k)
+                xs = self._stream_tail(xs, attn.view(B * Ss, C), sw_s, self.act)
+            out, _ = norm_fwd(xs, self.expert_norm)
+            tail = out.view(B, Ss, self.w)[:, -T:].reshape(B * T, self.w).contiguous()
+            v_t, _ = linear_fwd(tail, self.action_out)
+            x_t = x_t + v_t.float().view(B, T, A) * float(dt)
+            t = np.float32(t + dt)
+        return x_t
+
     def forward(self,
                 input_ids: torch.LongTensor = None,
                 attention_mask: Optional[torch.Tensor] = None,
@@ -454,33 +571,9 @@ class Pi0ForCausalLM(B200Module):
         x_t = te * noise + (1 - te) * actions
         u_t = noise - actions
 
-        # ---- embed_prefix: all cameras through SigLIP in one batch (camera-major), linear projector, text
-        n_cam, L = images.shape[1], input_ids.shape[1]
-        imgs = images.transpose(0, 1).reshape(n_cam * B, *images.shape[2:])
-        if self.tower.g_patch is None:
-            with torch.no_grad():
-                f = self.tower.forward(self.anchor, imgs)
-        else:
-            f = self.tower.forward(self.anchor, imgs)
-        f = LinearFn.apply(f, self.proj, None, st, self.tower.g_patch is not None, self.anchor.t)
-        P = self.tower.P
-        prefix = PrefixEmbedFn.apply(f, input_ids.to(torch.int32).contiguous(), self.embed_w, self.embed_g, st, B, n_cam,
-                                     P, L)
-        Sp = n_cam * P + L
-        prefix_mask = torch.cat([image_masks.bool()[:, :, None].expand(B, n_cam, P).reshape(B, n_cam * P),
-                                 attention_mask.bool()], dim=1)
-
-        # ---- embed_suffix (:271-315)
-        bf = torch.bfloat16
-        state_tok = LinearFn.apply(states.to(bf).contiguous(), self.state_proj, None, st, False, self.anchor.t)
-        a_tok = LinearFn.apply(x_t.to(bf).reshape(B * T, A).contiguous(), self.action_in, None, st, False, self.anchor.t)
-        temb = posemb_sincos(time, self.w, 4e-3, 4.0).to(bf)[:, None, :].expand(B, T, self.w)
-        at = torch.cat([a_tok.view(B, T, self.w), temb], dim=-1).reshape(B * T, 2 * self.w).contiguous()
-        at = LinearFn.apply(at, self.mlp_in, "silu", st, True, None)
-        at = LinearFn.apply(at, self.mlp_out, None, st, True, None)
-        suffix = torch.cat([state_tok.view(B, 1, self.w), at.view(B, T, self.w)], dim=1)
+        prefix, prefix_mask, Sp = self._embed_prefix(input_ids, attention_mask, images, image_masks)
+        suffix = self._embed_suffix(states, x_t, time)
         Ss = T + 1
-        suffix = suffix.reshape(B * Ss, self.w).contiguous()
 
         # ---- joint attention environment (:365-370)
         S = Sp + Ss

@@ -216,6 +216,36 @@ def attention_fwd(qkv: torch.Tensor, sh: AttnShape, *, keymask: Optional[torch.T
     return out, probs
 
 
+def attention_cross(q_packed: torch.Tensor, kv: torch.Tensor, B: int, Sq: int, Sk: int, H: int, KVH: int, hd: int, *,
+                    keymask: Optional[torch.Tensor] = None, bid_q: Optional[torch.Tensor] = None,
+                    bid_k: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Inference attention of Sq new query rows over an Sk-row K/V cache (pi0_arch.py:172-192 with
+    update_cache=False).  q_packed [B, Sq, (H+2KVH)*hd] (its q columns are read); kv [B, Sk, 2*KVH*hd] with K in the
+    first KVH*hd columns and V in the rest.  Returns out [B, Sq, H*hd]."""
+    _cuda(q_packed, kv)
+    dt, dev, es = _dt(q_packed), q_packed.device, q_packed.element_size()
+    G, W, Wkv = H // KVH, (H + 2 * KVH) * hd, 2 * KVH * hd
+    assert q_packed.is_contiguous() and kv.is_contiguous() and kv.shape[-1] == Wkv and q_packed.shape[-1] == W
+    lds = (Sk + 3) // 4 * 4
+    ldp = (Sk + 7) // 8 * 8 if q_packed.dtype == torch.bfloat16 else lds
+    scores = torch.empty((B, H, Sq, lds), device=dev, dtype=torch.float32)
+    probs = torch.empty((B, H, Sq, ldp), device=dev, dtype=q_packed.dtype)
+    if out is None:
+        out = torch.empty((B, Sq, H * hd), device=dev, dtype=q_packed.dtype)
+    k_ptr = kv.data_ptr()
+    v_ptr = k_ptr + KVH * hd * es
+    gemm_raw(a=q_packed.data_ptr(), b=k_ptr, d=scores.data_ptr(), ab_dtype=dt, d_dtype=F32, a_mn_major=0, b_mn_major=0,
+             m=Sq, n=Sk, k=hd, a_ld=W, a_s2=hd, a_s3=Sq * W, a_z2=H, b_ld=Wkv, b_s2=hd, b_s3=Sk * Wkv, b_z2=KVH,
+             d_ld=lds, d_s2=Sq * lds, d_s3=H * Sq * lds, z_lo=H, z_hi=B,
+             a_div=1, a_mul=1, a_seg=0, b_div=G, b_mul=1, b_seg=0, k_segs=1, alpha=hd ** -0.5)
+    softmax_fwd(scores, probs, Sq, Sk, heads=H, keymask=keymask, bid_q=bid_q, bid_k=bid_k)
+    gemm_raw(a=probs.data_ptr(), b=v_ptr, d=out.data_ptr(), ab_dtype=dt, d_dtype=dt, a_mn_major=0, b_mn_major=1,
+             m=Sq, n=hd, k=Sk, a_ld=ldp, a_s2=Sq * ldp, a_s3=H * Sq * ldp, a_z2=H,
+             b_ld=Wkv, b_s2=hd, b_s3=Sk * Wkv, b_z2=KVH, d_ld=H * hd, d_s2=hd, d_s3=Sq * H * hd, z_lo=H, z_hi=B,
+             a_div=1, a_mul=1, a_seg=0, b_div=G, b_mul=1, b_seg=0, k_segs=1, alpha=1.0)
+    return out
+
+
 def attention_bwd(dout: torch.Tensor, qkv: torch.Tensor, probs: torch.Tensor, sh: AttnShape, *, causal: bool = False,
                   dqkv: Optional[torch.Tensor] = None, scratch: Optional[torch.Tensor] = None,
                   dprobs: Optional[torch.Tensor] = None) -> torch.Tensor:

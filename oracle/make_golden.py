@@ -296,6 +296,130 @@ def make_pi0_tiny(seed: int = 2468):
     print("[pi0_tiny] wrote fixture; params without grad:", none_grad[:6], len(none_grad))
 
 
+def make_pi0_inference_tiny(seed: int = 2468):
+    """Pi0 inference_action (KV-cached prefix + Euler steps, pi0_arch.py:402-491) from the reference."""
+    llm, exp, vis = tiny_pi0_configs()
+    T, A = 10, 32
+    drop = ("rms_norm_eps", "rope_theta", "hidden_act", "layer_norm_eps")
+    model = ref_loader.build_reference_pi0({k: v for k, v in llm.items() if k not in drop},
+                                           {k: v for k, v in exp.items() if k not in drop},
+                                           {k: v for k, v in vis.items() if k not in drop}, A, T)
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    g = torch.Generator().manual_seed(seed + 3)
+    B, L = 3, 12
+    ids = torch.randint(1, 128, (B, L), generator=g)
+    mask = torch.ones(B, L, dtype=torch.bool)
+    mask[0, 9:] = False
+    mask[2, 4:] = False
+    images = torch.randn(B, 3, 3, 28, 28, generator=g)
+    image_masks = torch.ones(B, 3, dtype=torch.bool)
+    image_masks[2, 1] = False
+    states = torch.randn(B, A, generator=g)
+    cfg = dict(llm=llm, expert=exp, vision=vis, chunk_size=T, action_dim=A)
+    outs = {}
+    for steps in (10, 4):
+        torch.manual_seed(seed + 5)
+        ref = model.inference_action(input_ids=ids, attention_mask=mask, states=states, images=images,
+                                     image_masks=image_masks, diffusion_steps=steps)
+        torch.manual_seed(seed + 5)
+        noise = torch.normal(0, 1, size=(B, T, A))                     # pi0_arch.py:417-422
+        ora = vla_oracle.pi0_inference(sd, cfg, ids, mask, images, image_masks, states, noise, steps)
+        d = (ora - ref).abs().max().item()
+        print(f"[pi0_inference] steps={steps}: oracle vs reference max|d|={d:.2e} (|x|max {ref.abs().max():.3f})")
+        assert d < 1e-4
+        outs[steps] = dict(noise=noise, actions=ref.detach())
+    torch.save(dict(seed=seed, cfg=cfg, shapes={k: tuple(v.shape) for k, v in sd.items()},
+                    inputs=dict(input_ids=ids, attention_mask=mask, images=images, image_masks=image_masks,
+                                states=states), outputs=outs), GOLDEN / "pi0_inference_tiny.pt")
+
+
+MEMVLA_MEM = dict(dataloader_type="group", group_size=3, per_token_size=16, mem_length=2, retrieval_layers=2,
+                  use_timestep_pe=True, fusion_type="gate", consolidate_type="tome", update_fused=True)
+
+
+def make_memvla_tiny(seed: int = 1357):
+    """MemVLA training forward/backward (memvla_arch.py:546-664) with dropout 0: two episodes (3 + 2 frames) in one
+    `group` batch, mem_length 2 so the third frame of episode 0 triggers the token-merge consolidation."""
+    llm, clip, cfg = tiny_cogact_configs()
+    model = ref_loader.build_reference_memvla(llm, clip, "DiT-S", **MEMVLA_MEM)
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    g = torch.Generator().manual_seed(seed)
+    B, L, R = 5, 11, 4
+    ids = torch.randint(1, 128, (B, L), generator=g)
+    ids[:, 1] = vla_oracle.IMAGE_TOKEN_INDEX
+    mask = torch.ones(B, L, dtype=torch.bool)
+    mask[1, 9:] = False
+    mask[3, 7:] = False
+    ids[~mask] = 0
+    images = torch.randn(B, 3, 28, 28, generator=g)
+    actions = torch.rand(B, 16 * 7, generator=g) * 2 - 1
+    indexes = [(0, 4, 0), (0, 4, 1), (0, 4, 2), (0, 9, 5), (0, 9, 6)]
+    # reference RNG order inside ActionModel.loss: randn_like(x), randint (action_models.py:76-79), then token_drop's
+    # torch.rand (dit.py:86-88)
+    torch.manual_seed(seed + 1)
+    out = model(input_ids=ids, attention_mask=mask, images=images, actions=actions, indexes=indexes, labels=None)
+    out.loss.backward()
+    torch.manual_seed(seed + 1)
+    noise = torch.randn(R * B, 16, 7)
+    timesteps = torch.randint(0, 100, (R * B,))
+    drop = torch.rand(R * B) < 0.1
+    mcfg = dict(cfg, mem=MEMVLA_MEM)
+    ora = vla_oracle.memvla_forward(sd, mcfg, ids, mask, images, actions, indexes, noise, timesteps, drop, R)
+    d = abs(ora["loss"].item() - out.loss.item())
+    print(f"[memvla_tiny] reference loss {out.loss.item():.8f} oracle {ora['loss'].item():.8f}")
+    assert d < 1e-5, d
+    # intermediate pins straight from the reference modules
+    with torch.no_grad():
+        per_ref = model.model.per_compr(out.vision_proj_feats)
+    d_per = (per_ref - ora["per_tokens"]).abs().max().item()
+    print(f"[memvla_tiny] per_compr max|d| {d_per:.2e}")
+    assert d_per < 1e-4
+    names = ["model.per_compr.excite.1.weight", "model.per_compr.excite.3.bias", "model.per_compr.reduce.0.weight",
+             "model.per_compr.reduce.2.weight",
+             "model.per_cog_mem_bank.retrieval_blocks.cog.0.q_proj.weight",
+             "model.per_cog_mem_bank.retrieval_blocks.cog.1.k_proj.weight",
+             "model.per_cog_mem_bank.retrieval_blocks.cog.1.ffn.0.weight",
+             "model.per_cog_mem_bank.retrieval_blocks.per.0.v_proj.weight",
+             "model.per_cog_mem_bank.retrieval_blocks.per.1.ffn.3.weight",
+             "model.per_cog_mem_bank.retrieval_blocks.per.1.ffn_norm.weight",
+             "model.per_cog_mem_bank.gate_fusion_blocks.cog.proj.weight",
+             "model.per_cog_mem_bank.gate_fusion_blocks.per.proj.bias",
+             "model.per_cog_mem_bank.timestep_embedders.cog.mlp.0.weight",
+             "model.per_cog_mem_bank.timestep_embedders.per.mlp.2.weight",
+             "model.action_head.net.per_token_embedder.linear.weight",
+             "model.action_head.net.blocks.0.per_attn.in_proj_bias",
+             "model.action_head.net.blocks.5.per_attn.out_proj.weight",
+             "model.action_head.net.blocks.3.norm3.weight",
+             "model.action_head.net.blocks.2.mlp.fc1.bias",
+             "model.action_head.net.z_embedder.linear.weight",
+             "model.mm_projector.0.weight", "model.mm_projector.2.weight",
+             "model.llm.layers.1.mlp.down_proj.weight", "model.llm.layers.0.self_attn.q_proj.weight",
+             "model.llm.embed_tokens.weight"]
+    params = dict(model.named_parameters())
+    grads = {n: params[n].grad.clone() for n in names if params[n].grad is not None}
+    missing = [n for n in names if params[n].grad is None]
+    # oracle gradients must agree with the reference's
+    osd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    ora2 = vla_oracle.memvla_forward(osd, mcfg, ids, mask, images, actions, indexes, noise, timesteps, drop, R)
+    ora2["loss"].backward()
+    worst = max(((osd[n].grad - g_).norm() / (g_.norm() + 1e-12)).item() for n, g_ in grads.items())
+    print(f"[memvla_tiny] oracle-vs-reference worst relative grad error {worst:.2e}; params without grad: {missing}")
+    assert worst < 2e-3
+    none_grad = sorted(n for n, p in params.items() if p.grad is None)
+    torch.save(dict(seed=seed, cfg=mcfg, shapes={k: tuple(v.shape) for k, v in sd.items()},
+                    inputs=dict(input_ids=ids, attention_mask=mask, images=images, actions=actions, indexes=indexes,
+                                noise=noise, timesteps=timesteps, drop_mask=drop),
+                    outputs=dict(loss=out.loss.detach(), per_tokens=per_ref, cog_fused=ora["cog_fused"].detach(),
+                                 per_fused=ora["per_fused"].detach(), noise_pred=ora["noise_pred"].detach(),
+                                 grads=grads, none_grad=none_grad)),
+               GOLDEN / "memvla_tiny.pt")
+    print("[memvla_tiny] wrote fixture;", len(none_grad), "params without grad")
+
+
 def make_cogact_inference_tiny(seed: int = 1234):
     """CogACT inference_action (CFG 1.5, 10-step DDIM, eta=0) from the reference (cogact_arch.py:149-198)."""
     llm, clip, cfg = tiny_cogact_configs()
@@ -330,6 +454,8 @@ if __name__ == "__main__":
     make_cogact_tiny()
     make_cogact_inference_tiny()
     make_pi0_tiny()
+    make_pi0_inference_tiny()
+    make_memvla_tiny()
     make_oft_discrete_tiny()
     make_splice_cases()
     make_integer_kats()

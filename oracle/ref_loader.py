@@ -194,6 +194,28 @@ def build_reference_oft_discrete(llm_config, clip_config, action_dim: int = 7, c
     return OFTDiscreteForCausalLM(cfg)
 
 
+def build_reference_memvla(llm_config, clip_config, action_model_type: str = "DiT-S", action_dim: int = 7,
+                           chunk_size: int = 16, mm_projector_type: str = "mlp2x_gelu", dropout: float = 0.0, **mem):
+    """Reference MemVLAForCausalLM (memvla_arch.py:536-544) with random-init weights.  `mem` = the memory-module config
+    keys memvla_exp.py:198-236 sets (dataloader_type, group_size, per_token_size, mem_length, retrieval_layers,
+    use_timestep_pe, fusion_type, consolidate_type, update_fused).  CrossTransformerBlock hard-codes dropout=0.1 and
+    passes it to SDPA unconditionally (memvla_arch.py:83,122-124); parity runs set the instance attributes to
+    `dropout` (0 by default) — no reference code is changed."""
+    load_reference()
+    from dexbotic.model.memvla.memvla_arch import CrossTransformerBlock, MemVLAConfig, MemVLAForCausalLM
+    import torch.nn as nn
+    cfg = MemVLAConfig(llm_config=llm_config, mm_projector_type=mm_projector_type, mm_vision_tower=clip_config,
+                       action_model_type=action_model_type, action_dim=action_dim, chunk_size=chunk_size, **mem)
+    model = MemVLAForCausalLM(cfg)
+    for m in model.modules():
+        if isinstance(m, CrossTransformerBlock):
+            m.dropout = dropout
+            for sub in m.ffn:
+                if isinstance(sub, nn.Dropout):
+                    sub.p = dropout
+    return model
+
+
 _pi0_loaded = False
 
 
@@ -215,6 +237,13 @@ def load_reference_pi0():
         self.is_loaded = True
 
     siglip_encoder.SiglipVisionTower.load_model = siglip_load_model
+    # Version artifact, neutralised: pi0_arch.py:179-182 reads `past_key_values.key_cache[layer]` /
+    # `.value_cache[layer]` — list attributes DynamicCache had under the pinned transformers 4.5x; 5.5.0 keeps the
+    # same tensors in `cache.layers[layer].keys / .values`.  Expose the old read-only views.
+    from transformers import DynamicCache
+    if not hasattr(DynamicCache, "key_cache"):
+        DynamicCache.key_cache = property(lambda self: [l.keys for l in self.layers])
+        DynamicCache.value_cache = property(lambda self: [l.values for l in self.layers])
     import dexbotic.model.pi0  # noqa: F401
     mod = _exec_patched("dexbotic.model.pi0.pi0_arch", "dexbotic/model/pi0/pi0_arch.py",
                         [("    vision_config: dict | str\n", "    vision_config: dict | str = None\n"),

@@ -80,6 +80,20 @@ def _mha(x, wq, bq, wk, bk, wv, bv, wo, bo, heads, mask=None):
     return F.linear(o, wo, bo)
 
 
+def _mha_cross(xq, xk, xv, wq, bq, wk, bk, wv, bv, wo, bo, heads):
+    """softmax((xq Wq)(xk Wk)^T / sqrt(hd)) (xv Wv) [Wo]: nn.MultiheadAttention(batch_first) and the SDPA call of
+    CrossTransformerBlock (memvla_arch.py:111-124), dropout 0."""
+    B, N, D = xq.shape
+    M = xk.shape[1]
+    hd = D // heads
+    q = F.linear(xq, wq, bq).view(B, N, heads, hd).transpose(1, 2)
+    k = F.linear(xk, wk, bk).view(B, M, heads, hd).transpose(1, 2)
+    v = F.linear(xv, wv, bv).view(B, M, heads, hd).transpose(1, 2)
+    p = torch.softmax((q @ k.transpose(-1, -2)) * hd ** -0.5, dim=-1)
+    o = (p @ v).transpose(1, 2).reshape(B, N, D)
+    return o if wo is None else F.linear(o, wo, bo)
+
+
 def clip_vision_features(sd, prefix: str, images: torch.Tensor, cfg: dict) -> torch.Tensor:
     """hidden_states[-2][:, 1:] of HF CLIPVisionModel (feature_select, clip_encoder.py:31-36)."""
     p = prefix + "vision_tower.vision_model."
@@ -250,9 +264,14 @@ def timestep_embedding(t, dim=256, max_period=10000):
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
 
-def dit_forward(sd, prefix: str, x, t, z, drop_mask, num_heads: int):
-    """dit.py:273-292.  drop_mask[b]=True replaces z[b] by the learned `uncondition` (token_drop, :80-95)."""
+def dit_forward(sd, prefix: str, x, t, z, drop_mask, num_heads: int, per_token=None):
+    """dit.py:273-292.  drop_mask[b]=True replaces z[b] by the learned `uncondition` (token_drop, :80-95).
+    per_token [N,P,D_per] (MemVLA, memvla/action_model/dit.py:176-187,302-323): embedded once, then every block
+    cross-attends to it (nn.MultiheadAttention on norm3(x)) between self-attention and the MLP."""
     p = prefix + "net."
+    if per_token is not None:
+        per_token = F.linear(per_token, sd[p + "per_token_embedder.linear.weight"],
+                             sd[p + "per_token_embedder.linear.bias"])
     x = F.linear(x, sd[p + "x_embedder.linear.weight"], sd[p + "x_embedder.linear.bias"])
     te = timestep_embedding(t)
     te = F.linear(F.silu(F.linear(te, sd[p + "t_embedder.mlp.0.weight"], sd[p + "t_embedder.mlp.0.bias"])),
@@ -270,6 +289,12 @@ def dit_forward(sd, prefix: str, x, t, z, drop_mask, num_heads: int):
         wqkv, bqkv = sd[q + "attn.qkv.weight"], sd[q + "attn.qkv.bias"]
         x = x + _mha(h, wqkv[:D], bqkv[:D], wqkv[D:2 * D], bqkv[D:2 * D], wqkv[2 * D:], bqkv[2 * D:],
                      sd[q + "attn.proj.weight"], sd[q + "attn.proj.bias"], num_heads)
+        if per_token is not None:
+            h = F.layer_norm(x, (D,), sd[q + "norm3.weight"], sd[q + "norm3.bias"], 1e-6)
+            wi, bi = sd[q + "per_attn.in_proj_weight"], sd[q + "per_attn.in_proj_bias"]
+            x = x + _mha_cross(h, per_token, per_token, wi[:D], bi[:D], wi[D:2 * D], bi[D:2 * D], wi[2 * D:],
+                               bi[2 * D:], sd[q + "per_attn.out_proj.weight"], sd[q + "per_attn.out_proj.bias"],
+                               num_heads)
         h = F.layer_norm(x, (D,), None, None, 1e-6)
         x = x + F.linear(F.gelu(F.linear(h, sd[q + "mlp.fc1.weight"], sd[q + "mlp.fc1.bias"]), approximate="tanh"),
                          sd[q + "mlp.fc2.weight"], sd[q + "mlp.fc2.bias"])
@@ -291,18 +316,11 @@ def cogact_forward(sd, cfg: dict, input_ids, attention_mask, images, actions, no
 
     noise [R*B,T,A], timesteps [R*B], drop_mask [R*B] are injected (the reference draws them with
     torch.randn_like / randint / rand: action_models.py:106-109, dit.py:86-88)."""
-    if images.dim() == 5:        # [B, n_view, C, H, W]: views are encoded in one batch and concatenated per sample
-        Bv, nv = images.shape[:2]   # (dexbotic_arch.py:163-175)
-        feats = clip_vision_features(sd, "model.mm_vision_tower.", images.flatten(0, 1), cfg["vision"])
-        feats = mlp_projector(sd, "model.mm_projector.", feats, cfg.get("projector_depth", 2))
-        feats = feats.reshape(Bv, nv * feats.shape[1], feats.shape[2])
-    else:
-        feats = clip_vision_features(sd, "model.mm_vision_tower.", images, cfg["vision"])
-        feats = mlp_projector(sd, "model.mm_projector.", feats, cfg.get("projector_depth", 2))
-    emb, lab, msk, pid = splice(sd["model.llm.embed_tokens.weight"], feats, input_ids, attention_mask, labels,
-                                cfg.get("tokenizer_model_max_length"), cfg.get("tokenizer_padding_side", "right"))
-    hs = decoder_forward(sd, "model.llm.", emb, msk, pid, cfg["llm"])
-    cog, idx = cognition_features(hs, msk)
+    # [B, n_view, C, H, W] images: views are encoded in one batch and concatenated per sample (dexbotic_arch.py:163-175)
+    tr = cogact_like_trunk(sd, cfg, input_ids, attention_mask, images, labels)
+    feats, emb, lab, msk, pid = (tr["image_features"], tr["inputs_embeds"], tr["labels"], tr["attention_mask"],
+                                 tr["position_ids"])
+    hs, cog, idx = tr["last_hidden"], tr["cognition"], tr["cognition_index"]
     A, T = cfg["action_dim"], cfg["chunk_size"]
     a = actions.reshape(actions.shape[0], -1, A)[:, :T].float()
     a_rep = a.repeat(repeated_diffusion_steps, 1, 1)
@@ -314,6 +332,161 @@ def cogact_forward(sd, cfg: dict, input_ids, attention_mask, images, actions, no
     loss = ((pred - noise) ** 2).mean()
     return dict(loss=loss, last_hidden=hs, cognition=cog, cognition_index=idx, inputs_embeds=emb,
                 attention_mask=msk, position_ids=pid, labels=lab, image_features=feats, noise_pred=pred)
+
+
+# ----------------------------------------------------------------------------------------------
+# MemVLA — memvla_arch.py:82-427 (memory modules), :546-664 (training forward)
+# ----------------------------------------------------------------------------------------------
+def bottleneck_se(sd, p: str, x: torch.Tensor) -> torch.Tensor:
+    """BottleneckSE (memvla_arch.py:136-173): squeeze-excite over channels (token mean -> 1x1 conv -> ReLU -> 1x1 conv
+    -> sigmoid), rescale, then a per-token 1x1-conv bottleneck MLP.  1x1 convs on the [B,C,H,W] view are per-token
+    linears; x [B,N,C] -> [B,N,C_out]."""
+    lin = lambda t, n: F.linear(t, sd[p + n + ".weight"].flatten(1), sd[p + n + ".bias"])  # noqa: E731
+    w = torch.sigmoid(lin(F.relu(lin(x.mean(dim=1), "excite.1")), "excite.3"))
+    x = x * w[:, None, :]
+    return lin(F.relu(lin(x, "reduce.0")), "reduce.2")
+
+
+def cross_transformer_block(sd, p: str, query, k, v, heads: int = 4):
+    """CrossTransformerBlock.forward (memvla_arch.py:105-133), dropout 0: attention WITHOUT an output projection,
+    post-LN residuals, erf-GELU FFN."""
+    D = query.shape[-1]
+    a = _mha_cross(query, k, v, sd[p + "q_proj.weight"], sd[p + "q_proj.bias"], sd[p + "k_proj.weight"],
+                   sd[p + "k_proj.bias"], sd[p + "v_proj.weight"], sd[p + "v_proj.bias"], None, None, heads)
+    x = F.layer_norm(query + a, (D,), sd[p + "attn_norm.weight"], sd[p + "attn_norm.bias"])
+    f = F.linear(F.gelu(F.linear(x, sd[p + "ffn.0.weight"], sd[p + "ffn.0.bias"])), sd[p + "ffn.3.weight"],
+                 sd[p + "ffn.3.bias"])
+    return F.layer_norm(x + f, (D,), sd[p + "ffn_norm.weight"], sd[p + "ffn_norm.bias"])
+
+
+class MemBankOracle:
+    """PerCogMemBank (memvla_arch.py:195-427) for one role, `group` / `stream` / `parallel_stream` training semantics
+    and the eval-mode episode-id rewrite.  State: banks[eid] = [(timestep, feat[N,D] detached), ...]."""
+
+    def __init__(self, sd, prefix: str, role: str, mem_length: int, retrieval_layers: int, dataloader_type="group",
+                 use_timestep_pe=True, fusion_type="gate", consolidate_type="tome", update_fused=True):
+        self.sd, self.p, self.role = sd, prefix, role
+        self.mem_length, self.layers, self.dl = mem_length, retrieval_layers, dataloader_type
+        self.use_pe, self.fusion, self.consolidate, self.update_fused = (use_timestep_pe, fusion_type, consolidate_type,
+                                                                        update_fused)
+        self.banks, self.prev_eids, self.eid_stream = {}, {}, None
+
+    def _pe(self, t):
+        q = f"{self.p}timestep_embedders.{self.role}.mlp."
+        e = timestep_embedding(t, 256)
+        return F.linear(F.silu(F.linear(e, self.sd[q + "0.weight"], self.sd[q + "0.bias"])), self.sd[q + "2.weight"],
+                        self.sd[q + "2.bias"])
+
+    def _consolidate(self, eid, feat, timestep):
+        bank = self.banks.setdefault(eid, [])
+        bank.append((timestep, feat.detach().clone()))
+        while len(bank) > self.mem_length:
+            if self.consolidate == "fifo":
+                del bank[:-self.mem_length]
+                continue
+            # token merge (:247-274): fuse the adjacent pair with the highest mean cosine similarity
+            sims = [F.cosine_similarity(bank[i][1].flatten(1) if bank[i][1].dim() > 1 else bank[i][1][None],
+                                        bank[i + 1][1].flatten(1) if bank[i + 1][1].dim() > 1 else bank[i + 1][1][None],
+                                        dim=1).mean().item() for i in range(len(bank) - 1)]
+            j = int(torch.tensor(sims).argmax().item())
+            (ti, fi), (tj, fj) = bank[j], bank[j + 1]
+            bank[j] = (0.5 * (ti + tj) if ti is not None else None, (0.5 * (fi + fj)).detach().clone())
+            bank.pop(j + 1)
+
+    def process_batch(self, tokens, episode_ids, timesteps, training=True):
+        B, N, D = tokens.shape
+        if training:
+            if self.dl == "group":
+                self.banks.clear(); self.prev_eids.clear(); self.eid_stream = None
+            elif self.dl == "stream":
+                if self.eid_stream is not None and self.eid_stream != episode_ids[0]:
+                    self.banks.pop(self.eid_stream, None)
+                self.eid_stream = episode_ids[0]
+            else:
+                episode_ids = [(i, e[0], e[1]) for i, e in enumerate(episode_ids)]
+        else:
+            episode_ids = [(0, 0)] * B if self.dl in ("group", "stream") else [(i, 0, 0) for i in range(B)]
+        outs = []
+        for i in range(B):
+            eid = episode_ids[i]
+            if training and self.dl == "stream" and i > 0 and episode_ids[i] != episode_ids[i - 1]:
+                self.banks.pop(episode_ids[i - 1], None)
+                self.eid_stream = episode_ids[i]
+            if training and self.dl == "parallel_stream":
+                prev = self.prev_eids.get(i)
+                if prev is not None and prev != eid:
+                    self.banks.pop(prev, None)
+                self.prev_eids[i] = eid
+            work = tokens[i][None]
+            hist = self.banks.get(eid, [])
+            if hist:
+                mem = torch.stack([f for _, f in hist]).reshape(-1, D)[None]
+                pe = (self._pe(torch.stack([t for t, _ in hist]))[None].repeat_interleave(N, dim=1) if self.use_pe
+                      else torch.zeros_like(mem))
+            else:
+                mem = work
+                pe = (self._pe(timesteps[i].reshape(1))[None].repeat_interleave(N, dim=1) if self.use_pe
+                      else torch.zeros_like(mem))
+            q = work
+            for l in range(self.layers):
+                q = cross_transformer_block(self.sd, f"{self.p}retrieval_blocks.{self.role}.{l}.", q, mem + pe, mem)
+            if self.fusion == "add":
+                fused = (work + q) * 0.5
+            else:
+                g = f"{self.p}gate_fusion_blocks.{self.role}.proj."
+                sc = torch.sigmoid(F.linear(torch.cat([work, q], dim=-1), self.sd[g + "weight"], self.sd[g + "bias"]))
+                fused = sc * work + (1 - sc) * q
+            outs.append(fused)
+            self._consolidate(eid, fused[0] if self.update_fused else tokens[i], timesteps[i] if self.use_pe else None)
+        return torch.cat(outs, dim=0)
+
+
+def memvla_forward(sd, cfg: dict, input_ids, attention_mask, images, actions, indexes, noise, timesteps, drop_mask,
+                   repeated_diffusion_steps: int = 4, banks=None, training=True):
+    """MemVLAForCausalLM.forward (memvla_arch.py:546-664), dropout 0.  indexes[b] = (dataset, episode, frame).
+    `banks` (dict role -> MemBankOracle) carries state across calls for the stream modes / inference."""
+    out = cogact_like_trunk(sd, cfg, input_ids, attention_mask, images)
+    cog, feats = out["cognition"], out["image_features"]
+    m = cfg["mem"]
+    if banks is None:
+        banks = {r: MemBankOracle(sd, "model.per_cog_mem_bank.", r, m["mem_length"], m["retrieval_layers"],
+                                  m.get("dataloader_type", "group"), m.get("use_timestep_pe", True),
+                                  m.get("fusion_type", "gate"), m.get("consolidate_type", "tome"),
+                                  m.get("update_fused", True)) for r in ("per", "cog")}
+    per = bottleneck_se(sd, "model.per_compr.", feats)
+    eids = [tuple(i[:2]) for i in indexes]
+    ts = [torch.tensor(i[2]) for i in indexes]
+    cog_f = banks["cog"].process_batch(cog, eids, ts, training)
+    per_f = banks["per"].process_batch(per, eids, ts, training)
+    A, T = cfg["action_dim"], cfg["chunk_size"]
+    R = repeated_diffusion_steps
+    a = actions.reshape(actions.shape[0], -1, A)[:, :T].float()
+    sa, sb = cosine_schedule(cfg.get("diffusion_steps", 100))
+    x_t = q_sample(a.repeat(R, 1, 1), timesteps, noise, sa, sb)
+    width = sd["model.action_head.net.x_embedder.linear.weight"].shape[0]
+    pred = dit_forward(sd, "model.action_head.", x_t, timesteps, cog_f.repeat(R, 1, 1), drop_mask, DIT_HEADS[width],
+                       per_token=per_f.repeat(R, 1, 1))
+    out.update(loss=((pred - noise) ** 2).mean(), cog_fused=cog_f, per_fused=per_f, per_tokens=per, noise_pred=pred,
+               banks=banks)
+    return out
+
+
+def cogact_like_trunk(sd, cfg: dict, input_ids, attention_mask, images, labels=None):
+    """vision tower -> projector -> splice -> decoder -> cognition token (shared by CogACT and MemVLA)."""
+    if images.dim() == 5:
+        Bv, nv = images.shape[:2]
+        feats = clip_vision_features(sd, "model.mm_vision_tower.", images.flatten(0, 1), cfg["vision"])
+        feats = mlp_projector(sd, "model.mm_projector.", feats, cfg.get("projector_depth", 2))
+        feats = feats.reshape(Bv, nv * feats.shape[1], feats.shape[2])
+    else:
+        feats = clip_vision_features(sd, "model.mm_vision_tower.", images, cfg["vision"])
+        feats = mlp_projector(sd, "model.mm_projector.", feats, cfg.get("projector_depth", 2))
+    emb, lab, msk, pid = splice(sd["model.llm.embed_tokens.weight"], feats, input_ids, attention_mask, labels,
+                                cfg.get("tokenizer_model_max_length"), cfg.get("tokenizer_padding_side", "right"))
+    hs = decoder_forward(sd, "model.llm.", emb, msk, pid, cfg["llm"])
+    cog, idx = cognition_features(hs, msk)
+    return dict(last_hidden=hs, cognition=cog, cognition_index=idx, inputs_embeds=emb, attention_mask=msk,
+                position_ids=pid, labels=lab, image_features=feats)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -434,12 +607,38 @@ def pi0_make_attn_mask(input_mask: torch.Tensor, ar_mask: torch.Tensor) -> torch
 def pi0_forward(sd, cfg: dict, input_ids, attention_mask, images, image_masks, actions, states, noise, time):
     """Pi0ForCausalLM.forward (pi0_arch.py:317-400) with injected noise [B,T,A] and time [B].
     Returns dict(loss, v_t, u_t, suffix_out, prefix_tokens, input_mask)."""
-    L, E, V = cfg["llm"], cfg["expert"], cfg["vision"]
-    T = cfg["chunk_size"]
-    B = actions.shape[0]
     te = time[:, None, None]
     x_t = te * noise + (1 - te) * actions
     u_t = noise - actions
+    out = pi0_velocity(sd, cfg, input_ids, attention_mask, images, image_masks, states, x_t, time)
+    out["u_t"] = u_t
+    out["loss"] = ((out["v_t"] - u_t) ** 2).mean()
+    return out
+
+
+def pi0_inference(sd, cfg: dict, input_ids, attention_mask, images, image_masks, states, noise,
+                  diffusion_steps: int = 10):
+    """Pi0ForCausalLM.inference_action (pi0_arch.py:402-491): Euler integration of the flow from t=1 (noise) to t=0
+    with dt = -1/steps.  The reference caches the prefix K/V (the prefix never attends to the suffix, :432-444) and
+    runs only the suffix through the action expert per step; recomputing the joint forward each step — as done
+    here — is the same arithmetic (same masks :452-458, same positions :465-469)."""
+    B = states.shape[0]
+    dt = -1.0 / diffusion_steps
+    x = noise
+    time = torch.tensor(1.0)
+    while time > -dt / 2:
+        v = pi0_velocity(sd, cfg, input_ids, attention_mask, images, image_masks, states, x,
+                         time.broadcast_to(B))["v_t"]
+        x = x + v * dt
+        time = time + dt
+    return x
+
+
+def pi0_velocity(sd, cfg: dict, input_ids, attention_mask, images, image_masks, states, x_t, time):
+    """embed_prefix + embed_suffix + _inner_forward_mot + action_out_proj (pi0_arch.py:116-315, 356-386)."""
+    L, E, V = cfg["llm"], cfg["expert"], cfg["vision"]
+    T = cfg["chunk_size"]
+    B = x_t.shape[0]
     # embed_prefix (:235-269): cameras one by one, then text * sqrt(hidden)
     toks, masks = [], []
     for c in range(images.shape[1]):
@@ -503,8 +702,7 @@ def pi0_forward(sd, cfg: dict, input_ids, attention_mask, images, image_masks, a
         xs = outs
     suffix_out = rms_norm(xs[1], sd["model.action_expert.norm.weight"], E["rms_norm_eps"], unit_offset=True)
     v_t = F.linear(suffix_out[:, -T:], sd["model.action_out_proj.weight"], sd["model.action_out_proj.bias"])
-    loss = ((v_t - u_t) ** 2).mean()
-    return dict(loss=loss, v_t=v_t, u_t=u_t, suffix_out=suffix_out, prefix_tokens=prefix, input_mask=input_mask)
+    return dict(v_t=v_t, suffix_out=suffix_out, prefix_tokens=prefix, input_mask=input_mask)
 
 
 # ----------------------------------------------------------------------------------------------

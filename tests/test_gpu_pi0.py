@@ -70,3 +70,40 @@ def test_pi0_training_steps_reduce_loss():
         model.optimizer_step(base_lr=2e-3)
         losses.append(out.loss.item())
     assert losses[-1] < losses[0] * 0.9, losses
+
+
+@pytest.mark.parametrize("steps", [10, 4])
+def test_pi0_inference_matches_reference_golden(steps):
+    """inference_action (KV-cached prefix + Euler loop, pi0_arch.py:402-491) vs the reference's own output on the
+    same noise draw, and vs a cache-free evaluation of our training graph (same velocity field)."""
+    fx = torch.load(GOLDEN / "pi0_inference_tiny.pt", weights_only=False)
+    model = _build(fx)
+    model.eval()
+    i = {k: v.cuda() for k, v in fx["inputs"].items()}
+    ref = fx["outputs"][steps]
+    acts = model.inference_action(input_ids=i["input_ids"], attention_mask=i["attention_mask"], states=i["states"],
+                                  images=i["images"], image_masks=i["image_masks"], diffusion_steps=steps,
+                                  noise=ref["noise"].cuda())
+    assert acts.shape == ref["actions"].shape and acts.dtype == torch.float32
+    rel, cos = _rel(acts, ref["actions"].cuda())
+    assert rel < 3e-2 and cos > 0.999, (rel, cos)      # bf16 backbone, 4-10 chained Euler steps
+
+
+def test_pi0_inference_cache_equals_joint_forward():
+    """One Euler step from the cached-prefix path == x + dt * v_t of the joint training forward at time 1."""
+    fx = torch.load(GOLDEN / "pi0_inference_tiny.pt", weights_only=False)
+    model = _build(fx)
+    model.eval()
+    i = {k: v.cuda() for k, v in fx["inputs"].items()}
+    noise = fx["outputs"][10]["noise"].cuda()
+    one = model.inference_action(input_ids=i["input_ids"], attention_mask=i["attention_mask"], states=i["states"],
+                                 images=i["images"], image_masks=i["image_masks"], diffusion_steps=1, noise=noise)
+    B = noise.shape[0]
+    with torch.no_grad():
+        # time = 1  =>  x_t = noise regardless of `actions`
+        out = model(input_ids=i["input_ids"], attention_mask=i["attention_mask"], images=i["images"],
+                    image_masks=i["image_masks"], actions=torch.zeros_like(noise), states=i["states"], noise=noise,
+                    time=torch.ones(B, device="cuda"))
+    want = noise - out.logits.float()
+    rel, cos = _rel(one, want)
+    assert rel < 1e-2 and cos > 0.9999, (rel, cos)

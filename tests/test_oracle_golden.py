@@ -93,6 +93,30 @@ def test_pi0_tiny_matches_reference():
     assert (out["v_t"] - fx["outputs"]["v_t"]).abs().max().item() < 1e-4
 
 
+def test_pi0_inference_matches_reference():
+    """Oracle Euler sampler (cache-free restatement) vs the reference's KV-cached inference_action output."""
+    fx = torch.load(GOLDEN / "pi0_inference_tiny.pt", weights_only=False)
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    i = fx["inputs"]
+    for steps, ref in fx["outputs"].items():
+        got = vla_oracle.pi0_inference(sd, fx["cfg"], i["input_ids"], i["attention_mask"], i["images"],
+                                       i["image_masks"], i["states"], ref["noise"], steps)
+        assert (got - ref["actions"]).abs().max().item() < 1e-4
+
+
+def test_memvla_tiny_matches_reference():
+    """MemVLA oracle (BottleneckSE, memory bank with token-merge consolidation, DiT per_attn) vs the reference."""
+    fx = torch.load(GOLDEN / "memvla_tiny.pt", weights_only=False)
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    i, ref = fx["inputs"], fx["outputs"]
+    out = vla_oracle.memvla_forward(sd, fx["cfg"], i["input_ids"], i["attention_mask"], i["images"], i["actions"],
+                                    i["indexes"], i["noise"], i["timesteps"], i["drop_mask"])
+    assert abs(out["loss"].item() - ref["loss"].item()) < 1e-5
+    assert (out["per_tokens"] - ref["per_tokens"]).abs().max().item() < 1e-4
+    # episode 0 holds 3 frames with mem_length 2: the token merge must have fired (bank length stays 2)
+    assert [len(v) for v in out["banks"]["cog"].banks.values()] == [2, 2]
+
+
 def test_pi0_attn_mask_truth_table():
     """make_attn_mask (pi0_arch.py:22-33): prefix bidirectional, state token sees prefix + itself, action tokens see
     prefix + state + each other; invalid positions neither attend nor are attended."""
