@@ -111,8 +111,8 @@ def linear_wgrad(store: ParamStore, dy2d, x2d, lin: Lin):
             sc = store.scratch_f32(lin.gb.numel())
             ops.colsum_(dy2d, sc)
             store.accumulate_small(sc, lin.gb)
-        else:   # tiny odd widths (DiT final layer N=7): plain torch reduction on a few KB
-            lin.gb.add_(dy2d.sum(0).to(lin.gb.dtype))
+        else:   # tiny odd widths (DiT final layer N=7, SE excite C/16): plain torch reduction on a few KB
+            store.accumulate_small(dy2d.float().sum(0), lin.gb)
 
 
 def linear_dgrad(dy2d, lin: Lin, out=None, residual=None):
@@ -367,3 +367,108 @@ class CrossEntropyFn(torch.autograd.Function):
     def backward(ctx, g):
         logits2d, labels, lse, n_valid = ctx.saved_tensors
         return ops.cross_entropy_bwd(logits2d, labels.contiguous(), lse, n_valid, g.contiguous().float()), None
+
+
+# ------------------------------------------------------------------ MemVLA memory path (memvla_arch.py)
+class CrossAttnFn(torch.autograd.Function):
+    """softmax(Q K^T / sqrt(hd)) V, no mask, separate query / key lengths, optional dropout on the attention weights
+    (F.scaled_dot_product_attention(q, k, v, dropout_p) at memvla_arch.py:122-124; nn.MultiheadAttention's core at
+    memvla/action_model/dit.py:181).  q [B*Sq, D], k / v [B*Sk, D]."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, B, Sq, Sk, H, dropout_p=0.0, seed=0):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        out, probs, pd = ops.cross_attention_fwd(q, k, v, B, Sq, Sk, H, dropout_p=dropout_p, seed=seed)
+        ctx.save_for_backward(q, k, v, probs) if pd is None else ctx.save_for_backward(q, k, v, probs, pd)
+        ctx.geom = (B, Sq, Sk, H, dropout_p, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, probs, *rest = ctx.saved_tensors
+        B, Sq, Sk, H, p, seed = ctx.geom
+        need_dq, need_dkv = ctx.needs_input_grad[0], ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dq, dk, dv = ops.cross_attention_bwd(dout.contiguous(), q, k, v, probs, rest[0] if rest else None, B, Sq, Sk, H,
+                                             dropout_p=p, seed=seed, need_dq=need_dq, need_dkv=need_dkv)
+        return dq, dk, dv, None, None, None, None, None, None
+
+
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout (memvla_arch.py:100,102) with the library's counter-based generator; backward re-applies the mask."""
+
+    @staticmethod
+    def forward(ctx, x2d, p, seed):
+        ctx.p, ctx.seed = p, seed
+        return ops.dropout(x2d.contiguous(), p, seed)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.dropout(g.contiguous(), ctx.p, ctx.seed), None, None
+
+
+class GateFuseFn(torch.autograd.Function):
+    """GateFusion's elementwise tail (memvla_arch.py:183-192): sigmoid(z) * x1 + (1 - sigmoid(z)) * x2."""
+
+    @staticmethod
+    def forward(ctx, z, x1, x2):
+        z, x1, x2 = z.contiguous(), x1.contiguous(), x2.contiguous()
+        ctx.save_for_backward(z, x1, x2)
+        return ops.gate_fuse_fwd(z, x1, x2)
+
+    @staticmethod
+    def backward(ctx, g):
+        z, x1, x2 = ctx.saved_tensors
+        return ops.gate_fuse_bwd(g.contiguous(), z, x1, x2)
+
+
+class SEPoolFn(torch.autograd.Function):
+    """AdaptiveAvgPool2d(1) over the token grid (memvla_arch.py:146): [B,P,C] -> [B,C] (same dtype)."""
+
+    @staticmethod
+    def forward(ctx, x3d):
+        ctx.shape = x3d.shape
+        return ops.se_reduce(x3d.contiguous(), None, 1.0 / x3d.shape[1]).to(x3d.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, P, Cc = ctx.shape
+        ones = torch.ones((B, P, Cc), device=g.device, dtype=g.dtype)   # never built in SEScaleFn's fused path
+        return ops.se_scale(ones, g.contiguous(), None, 0.0).mul_(1.0 / P)
+
+
+class SEGateFn(torch.autograd.Function):
+    """The squeeze-excite of BottleneckSE (memvla_arch.py:146-151,164-165) as ONE function of x:
+        pool = mean_p x ; w = sigmoid(W2 relu(W1 pool + b1) + b2) ; out = x * w
+    The two excite GEMMs have M = batch rows; their backward is chained by hand so the token map x is read twice in
+    forward (pool, scale) and three times in backward (dw reduction, dx) — never materialising a broadcast."""
+
+    @staticmethod
+    def forward(ctx, x3d, l1: Lin, l2: Lin, store: ParamStore):
+        x3d = x3d.contiguous()
+        B, P, Cc = x3d.shape
+        pool = ops.se_reduce(x3d, None, 1.0 / P).to(x3d.dtype)
+        pre1, _ = linear_fwd(pool, l1)                                     # [B, C/16]: a few KB, any width
+        h = torch.relu(pre1)
+        z, _ = linear_fwd(h, l2)
+        w = torch.sigmoid(z.float()).to(x3d.dtype)                       # [B, C]: a few KB
+        out = ops.se_scale(x3d, w)
+        ctx.save_for_backward(x3d, pool, pre1, h, w)
+        ctx.misc = (l1, l2, store)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x3d, pool, pre1, h, w = ctx.saved_tensors
+        l1, l2, store = ctx.misc
+        dout = dout.contiguous()
+        B, P, Cc = x3d.shape
+        dw = ops.se_reduce(dout, x3d, 1.0)                                # [B, C] fp32 = sum_p dout * x
+        wf = w.float()
+        dz = (dw * wf * (1.0 - wf)).to(x3d.dtype)                         # sigmoid'
+        linear_wgrad(store, dz, h, l2)
+        dh = linear_dgrad(dz, l2)
+        dpre = dh * (pre1 > 0).to(dh.dtype)
+        linear_wgrad(store, dpre, pool, l1)
+        dpool = linear_dgrad(dpre, l1)
+        dx = ops.se_scale(dout, w, dpool, 1.0 / P)                        # dout * w + dpool / P
+        return dx, None, None, None

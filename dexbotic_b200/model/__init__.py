@@ -5,3 +5,4 @@ from .dexbotic_arch import (CausalLMOutputDexbotic, DexboticConfig, DexboticVLMM
 from .cogact_arch import CogActConfig, CogActModel, CogACTForCausalLM  # noqa: F401
 from .oft_arch import OFTConfig, OFTDiscreteConfig, OFTDiscreteForCausalLM  # noqa: F401
 from .pi0_arch import Pi0Config, Pi0ForCausalLM  # noqa: F401
+from .memvla_arch import MemVLAConfig, MemVLAForCausalLM, MemVLAModel  # noqa: F401

@@ -12,7 +12,8 @@ import numpy as np
 import torch
 
 from .. import ops
-from ..functional import AttnEnv, BlockCfg, BlockW, Lin, LinearFn, MSELossFn, Norm, NormFn, TransformerBlockFn
+from ..functional import (AttnEnv, BlockCfg, BlockW, CrossAttnFn, Lin, LinearFn, MSELossFn, Norm, NormFn,
+                          TransformerBlockFn)
 from ..params import ParamSpec, ParamStore
 
 DIT_SIZES = {"DiT-S": (6, 384, 4), "DiT-B": (12, 768, 12), "DiT-L": (24, 1024, 16)}   # action_models.py:48-58
@@ -29,16 +30,21 @@ def cosine_schedule(num_steps: int = 100, max_beta: float = 0.999):
 
 
 def action_head_specs(model_type: str, token_size: int, action_dim: int, chunk_size: int, trainable: bool = True,
-                      prefix: str = "model.action_head.net.") -> list[ParamSpec]:
+                      prefix: str = "model.action_head.net.", per_token_size: Optional[int] = None) -> list[ParamSpec]:
+    """per_token_size None: CogACT's DiT (cogact/action_model/dit.py); an int: MemVLA's DiT with the perceptual
+    cross-attention (memvla/action_model/dit.py:158-175,241-249) and without the unused history embedder."""
     depth, w, heads = DIT_SIZES[model_type]
     g, c = "action_head", "fp32"
     T = chunk_size - 1 + 2                                         # future_action_window_size + 2 (dit.py:228-236)
     P = lambda n, s, **k: ParamSpec(prefix + n, s, g, c, trainable=trainable, **k)  # noqa: E731
-    sp = [P("positional_embedding", (T, w), no_decay=True),
-          # history_embedder is built but never called (dit.py:205-207 "Action history is not used now")
-          ParamSpec(prefix + "history_embedder.linear.weight", (w, action_dim), g, c, trainable=False),
-          ParamSpec(prefix + "history_embedder.linear.bias", (w,), g, c, trainable=False),
-          P("x_embedder.linear.weight", (w, action_dim)), P("x_embedder.linear.bias", (w,)),
+    sp = [P("positional_embedding", (T, w), no_decay=True)]
+    if per_token_size is None:
+        # history_embedder is built but never called (dit.py:205-207 "Action history is not used now")
+        sp += [ParamSpec(prefix + "history_embedder.linear.weight", (w, action_dim), g, c, trainable=False),
+               ParamSpec(prefix + "history_embedder.linear.bias", (w,), g, c, trainable=False)]
+    else:
+        sp += [P("per_token_embedder.linear.weight", (w, per_token_size)), P("per_token_embedder.linear.bias", (w,))]
+    sp += [P("x_embedder.linear.weight", (w, action_dim)), P("x_embedder.linear.bias", (w,)),
           P("t_embedder.mlp.0.weight", (w, 256)), P("t_embedder.mlp.0.bias", (w,)),
           P("t_embedder.mlp.2.weight", (w, w)), P("t_embedder.mlp.2.bias", (w,)),
           P("z_embedder.uncondition", (1, token_size), no_decay=True),
@@ -49,6 +55,10 @@ def action_head_specs(model_type: str, token_size: int, action_dim: int, chunk_s
                P(q + "attn.proj.weight", (w, w)), P(q + "attn.proj.bias", (w,)),
                P(q + "mlp.fc1.weight", (4 * w, w)), P(q + "mlp.fc1.bias", (4 * w,)),
                P(q + "mlp.fc2.weight", (w, 4 * w)), P(q + "mlp.fc2.bias", (w,))]
+        if per_token_size is not None:
+            sp += [P(q + "per_attn.in_proj_weight", (3 * w, w)), P(q + "per_attn.in_proj_bias", (3 * w,)),
+                   P(q + "per_attn.out_proj.weight", (w, w)), P(q + "per_attn.out_proj.bias", (w,)),
+                   P(q + "norm3.weight", (w,), no_decay=True), P(q + "norm3.bias", (w,), no_decay=True)]
     sp += [P("final_layer.linear.weight", (action_dim, w)), P("final_layer.linear.bias", (action_dim,))]
     return sp
 
@@ -69,8 +79,11 @@ class ActionModel:
     """action_models.py:63-135 (ActionModel) wrapping dit.py:181-292 (DiT)."""
 
     def __init__(self, store: ParamStore, model_type: str, token_size: int, in_channels: int,
-                 future_action_window_size: int, diffusion_steps: int = 100, prefix: str = "model.action_head."):
+                 future_action_window_size: int, diffusion_steps: int = 100, prefix: str = "model.action_head.",
+                 use_per_attn: bool = False):
         self.store = store
+        self.model_type = model_type
+        self.use_per_attn = use_per_attn
         self.depth, self.w, self.heads = DIT_SIZES[model_type]
         self.in_channels = in_channels
         self.T = future_action_window_size + 1
@@ -97,6 +110,21 @@ class ActionModel:
                                       fc1=Lin.of(store, q + "mlp.fc1.weight", q + "mlp.fc1.bias"),
                                       fc2=Lin.of(store, q + "mlp.fc2.weight", q + "mlp.fc2.bias")))
         self.norm_final = Norm("ln_noaffine", 1e-6)
+        self.per = []
+        if use_per_attn:                       # memvla/action_model/dit.py:158-175: one nn.MultiheadAttention per block
+            self.per_emb = L("per_token_embedder.linear.weight", "per_token_embedder.linear.bias")
+            w = self.w
+            for i in range(self.depth):
+                q = f"{p}blocks.{i}."
+                wi, bi = store.w(q + "per_attn.in_proj_weight"), store.w(q + "per_attn.in_proj_bias")
+                gi, gbi = store.g(q + "per_attn.in_proj_weight"), store.g(q + "per_attn.in_proj_bias")
+                sl = lambda t, a, b: None if t is None else t[a:b]  # noqa: E731
+                self.per.append(dict(
+                    norm3=Norm("ln", 1e-6, store.w(q + "norm3.weight"), store.w(q + "norm3.bias"),
+                               store.g(q + "norm3.weight"), store.g(q + "norm3.bias")),
+                    q=Lin(wi[:w], bi[:w], sl(gi, 0, w), sl(gbi, 0, w)),
+                    kv=Lin(wi[w:], bi[w:], sl(gi, w, 3 * w), sl(gbi, w, 3 * w)),
+                    o=Lin.of(store, q + "per_attn.out_proj.weight", q + "per_attn.out_proj.bias")))
         sa, sb = cosine_schedule(diffusion_steps)
         # _extract_into_tensor (diffusion.py:975-987): float64 table entry -> float32
         self.sqrt_ac = torch.from_numpy(sa).float().to(store.device)
@@ -109,8 +137,34 @@ class ActionModel:
             mod = getattr(mod, part)
         return mod
 
-    def net(self, module, x_t, t, z, drop_mask):
-        """DiT.forward (dit.py:273-292) on fp32 tensors: x_t [N,T,A], t [N] int32, z [N,1,D] -> eps_hat [N,T,A]."""
+    def _block_with_per_attn(self, x2d, bw: BlockW, pa: dict, per_emb, N: int, S: int, groups: int):
+        """MemVLA DiTBlock.forward (memvla/action_model/dit.py:176-187) from the small Functions:
+        x += attn(norm1 x); x += per_attn(norm3 x, per, per); x += mlp(norm2 x).
+
+        The reference repeats per_token `groups` times along the batch (memvla_arch.py:641-645); cross-attention has
+        no mask, so the repeats of one sample are stacked as extra QUERY rows of that sample instead: K/V are
+        projected once per sample and no repeated copy exists."""
+        st, w, H = self.store, self.w, self.heads
+        h = NormFn.apply(x2d, bw.norm1, st)
+        qkv = LinearFn.apply(h, bw.qkv, None, st, True, None)
+        a = CrossAttnFn.apply(qkv[:, :w], qkv[:, w:2 * w], qkv[:, 2 * w:], N, S, S, H)
+        x2d = x2d + LinearFn.apply(a, bw.o, None, st, True, None)
+        Bs = N // groups
+        P = per_emb.shape[0] // Bs
+        h = NormFn.apply(x2d, pa["norm3"], st)
+        q = LinearFn.apply(h, pa["q"], None, st, True, None)
+        q = q.view(groups, Bs, S, w).transpose(0, 1).reshape(Bs * groups * S, w)         # [(b, r, s), w]
+        kv = LinearFn.apply(per_emb, pa["kv"], None, st, True, None)
+        c = CrossAttnFn.apply(q, kv[:, :w], kv[:, w:], Bs, groups * S, P, H)
+        c = c.view(Bs, groups, S, w).transpose(0, 1).reshape(N * S, w)
+        x2d = x2d + LinearFn.apply(c.contiguous(), pa["o"], None, st, True, None)
+        h = NormFn.apply(x2d, bw.norm2, st)
+        m = LinearFn.apply(h, bw.fc1, "gelu_tanh", st, True, None)
+        return x2d + LinearFn.apply(m, bw.fc2, None, st, True, None)
+
+    def net(self, module, x_t, t, z, drop_mask, per_token=None, groups: int = 1):
+        """DiT.forward (dit.py:273-292) on fp32 tensors: x_t [N,T,A], t [N] int32, z [N,1,D] -> eps_hat [N,T,A].
+        MemVLA: per_token [N/groups, P, D_per] fp32 (one copy per sample; `groups` = how often the batch repeats it)."""
         st = self.store
         N, T, A = x_t.shape
         w = self.w
@@ -127,14 +181,21 @@ class ActionModel:
         x = torch.cat([c[:, None, :], x.view(N, T, w)], dim=1) + pos                               # :283-284
         x2d = x.reshape(N * (T + 1), w).contiguous()
         env = AttnEnv(B=N, S=T + 1)
-        for bw in self.blocks:
-            x2d = TransformerBlockFn.apply(x2d, bw, env, st, False)      # ~30 MB of activations: never recompute
+        if self.use_per_attn:
+            assert per_token is not None and N % groups == 0
+            Bs, P, Dp = per_token.shape
+            per_emb = LinearFn.apply(per_token.reshape(Bs * P, Dp).contiguous(), self.per_emb, None, st, True, None)
+            for bw, pa in zip(self.blocks, self.per):
+                x2d = self._block_with_per_attn(x2d, bw, pa, per_emb, N, T + 1, groups)
+        else:
+            for bw in self.blocks:
+                x2d = TransformerBlockFn.apply(x2d, bw, env, st, False)  # ~30 MB of activations: never recompute
         x2d = NormFn.apply(x2d, self.norm_final, st)
         out = LinearFn.apply(x2d, self.final, None, st, True, None)                                      # FinalLayer
         return out.view(N, T + 1, A)[:, 1:, :]
 
     def loss(self, module, x, z, noise: Optional[torch.Tensor] = None, timestep: Optional[torch.Tensor] = None,
-             drop_mask: Optional[torch.Tensor] = None, training: bool = True):
+             drop_mask: Optional[torch.Tensor] = None, training: bool = True, per_token=None, groups: int = 1):
         """ActionModel.loss (action_models.py:102-125).  noise / timestep / drop_mask may be injected for parity."""
         N = x.shape[0]
         if noise is None:
@@ -145,7 +206,7 @@ class ActionModel:
             drop_mask = torch.rand(N, device=x.device) < self.class_dropout_prob
         t32 = timestep.to(torch.int32)
         x_t = _QSampleFn.apply(x, noise, t32, self.sqrt_ac, self.sqrt_1mac)
-        pred = self.net(module, x_t, t32, z, drop_mask)
+        pred = self.net(module, x_t, t32, z, drop_mask, per_token, groups)
         assert pred.shape == noise.shape == x.shape
         return MSELossFn.apply(pred, noise)
 
@@ -166,7 +227,7 @@ class ActionModel:
         return tmap, ac2, np.append(1.0, ac2[:-1])
 
     @torch.no_grad()
-    def sample(self, module, cognition, noise, cfg_scale: float = 1.5, num_ddim_steps: int = 10):
+    def sample(self, module, cognition, noise, cfg_scale: float = 1.5, num_ddim_steps: int = 10, per_token=None):
         """ddim_sample_loop (diffusion.py:714-795) with eta=0, clip_denoised=False, classifier-free guidance through
         forward_with_cfg (dit.py:294-311).  cognition [B,1,D] fp32, noise [B,T,A] fp32 -> samples [B,T,A]."""
         B = cognition.shape[0]
@@ -183,12 +244,12 @@ class ActionModel:
             t = torch.full((x.shape[0],), tmap[i], device=x.device, dtype=torch.int32)
             if use_cfg:
                 half = x[: x.shape[0] // 2]
-                out = self.net(module, torch.cat([half, half], 0).contiguous(), t, z, None)
+                out = self.net(module, torch.cat([half, half], 0).contiguous(), t, z, None, per_token, 2)
                 cond, uncond = out.chunk(2, dim=0)
                 e = uncond + cfg_scale * (cond - uncond)
                 eps_model = torch.cat([e, e], 0)
             else:
-                eps_model = self.net(module, x.contiguous(), t, z, None)
+                eps_model = self.net(module, x.contiguous(), t, z, None, per_token, 1)
             sr, srm1 = f32(np.sqrt(1.0 / ac[i])), f32(np.sqrt(1.0 / ac[i] - 1))
             pred_x0 = sr * x - srm1 * eps_model
             eps = (sr * x - pred_x0) / srm1

@@ -425,6 +425,7 @@ class DexboticVLMModel:
             need = kept_bytes_per_block(self.llm.blocks[0].cfg, B, L - 1 + P * n_views + append_tokens) * 1.08 * len(self.llm.blocks)
             self.mm_vision_tower.decoder_reserve_gb = need / (1 << 30)
         feats, views = self._extract_vision_features(images)
+        self.last_image_features = feats      # projector output rows [n_img*(P+1), D] (MemVLA reads it back)
         mask_u8 = None if attention_mask is None else attention_mask.to(torch.uint8).contiguous()
         ids = input_ids.contiguous()
         max_len = cfg.tokenizer_model_max_length or 0

@@ -694,3 +694,132 @@ def add_pos_bwd(dout, d_pos_f32, B: int, P: int):
     _cuda(dout, d_pos_f32)
     _lib.check(_lib.load().b200_add_pos_bwd(dout.data_ptr(), d_pos_f32.data_ptr(), B, P, dout.shape[-1], _dt(dout),
                                             _stream()), "add_pos_bwd")
+
+
+# ------------------------------------------------------------------- MemVLA memory path
+def dropout(x2d: torch.Tensor, p: float, seed: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Counter-based dropout over the logical [rows, cols] region of a (possibly row-padded) 2-D tensor; the same
+    (p, seed, shape) on the gradient is the backward pass."""
+    _cuda(x2d)
+    assert x2d.dim() == 2 and x2d.stride(1) == 1
+    if out is None:
+        out = torch.empty_like(x2d)
+    _lib.check(_lib.load().b200_dropout(x2d.data_ptr(), out.data_ptr(), x2d.shape[0], x2d.shape[1], x2d.stride(0),
+                                        out.stride(0), float(p), int(seed) & (2 ** 64 - 1), _dt(x2d), _stream()),
+               "dropout")
+    return out
+
+
+def se_reduce(x3d: torch.Tensor, y3d: Optional[torch.Tensor], scale: float) -> torch.Tensor:
+    """out_f32[b, c] = scale * sum_p x[b,p,c] * (y[b,p,c] if y is given else 1)."""
+    _cuda(x3d, y3d)
+    B, P, Cc = x3d.shape
+    out = torch.zeros((B, Cc), device=x3d.device, dtype=torch.float32)
+    _lib.check(_lib.load().b200_se_reduce(x3d.data_ptr(), _p(y3d), out.data_ptr(), B, P, Cc, float(scale), _dt(x3d),
+                                          _stream()), "se_reduce")
+    return out
+
+
+def se_scale(x3d: torch.Tensor, w2d: torch.Tensor, add2d: Optional[torch.Tensor] = None, add_scale: float = 0.0,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b,p,c] = x[b,p,c] * w[b,c] (+ add[b,c] * add_scale)."""
+    _cuda(x3d, w2d, add2d)
+    B, P, Cc = x3d.shape
+    assert x3d.is_contiguous() and w2d.is_contiguous() and w2d.dtype == x3d.dtype
+    if out is None:
+        out = torch.empty_like(x3d)
+    _lib.check(_lib.load().b200_se_scale(x3d.data_ptr(), w2d.data_ptr(), _p(add2d), out.data_ptr(), B, P, Cc,
+                                         float(add_scale), _dt(x3d), _stream()), "se_scale")
+    return out
+
+
+def gate_fuse_fwd(z, x1, x2):
+    _cuda(z, x1, x2)
+    out = torch.empty_like(x1)
+    _lib.check(_lib.load().b200_gate_fuse_fwd(z.data_ptr(), x1.data_ptr(), x2.data_ptr(), out.data_ptr(), x1.numel(),
+                                              _dt(x1), _stream()), "gate_fuse_fwd")
+    return out
+
+
+def gate_fuse_bwd(dout, z, x1, x2):
+    _cuda(dout, z, x1, x2)
+    dz, dx1, dx2 = torch.empty_like(z), torch.empty_like(x1), torch.empty_like(x2)
+    _lib.check(_lib.load().b200_gate_fuse_bwd(dout.data_ptr(), z.data_ptr(), x1.data_ptr(), x2.data_ptr(), dz.data_ptr(),
+                                              dx1.data_ptr(), dx2.data_ptr(), x1.numel(), _dt(x1), _stream()),
+               "gate_fuse_bwd")
+    return dz, dx1, dx2
+
+
+def cross_attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, Sq: int, Sk: int, H: int, *,
+                        dropout_p: float = 0.0, seed: int = 0):
+    """softmax(Q K^T / sqrt(hd)) V with separate query / key lengths and no mask: q [B*Sq, H*hd], k, v [B*Sk, H*hd]
+    (row-major, heads side by side).  Returns (out [B*Sq, H*hd], probs [B,H,Sq,ld], probs_dropped or None)."""
+    _cuda(q, k, v)
+    dt, dev = _dt(q), q.device
+    D = q.shape[1]
+    hd = D // H
+    if (hd * q.element_size()) % 16 != 0:
+        raise RuntimeError(f"cross_attention: head_dim {hd} x {q.element_size()} B must be a multiple of 16 B (TMA)")
+    lds = (Sk + 3) // 4 * 4
+    ldp = (Sk + 7) // 8 * 8 if q.dtype == torch.bfloat16 else lds
+    scores = torch.empty((B, H, Sq, lds), device=dev, dtype=torch.float32)
+    probs = torch.empty((B, H, Sq, ldp), device=dev, dtype=q.dtype)
+    gemm_raw(a=q.data_ptr(), b=k.data_ptr(), d=scores.data_ptr(), ab_dtype=dt, d_dtype=F32, a_mn_major=0, b_mn_major=0,
+             m=Sq, n=Sk, k=hd, a_ld=D, a_s2=hd, a_s3=Sq * D, a_z2=H, b_ld=D, b_s2=hd, b_s3=Sk * D, b_z2=H,
+             d_ld=lds, d_s2=Sq * lds, d_s3=H * Sq * lds, z_lo=H, z_hi=B,
+             a_div=1, a_mul=1, a_seg=0, b_div=1, b_mul=1, b_seg=0, k_segs=1, alpha=hd ** -0.5)
+    softmax_fwd(scores, probs, Sq, Sk, heads=H)
+    pd = None
+    if dropout_p > 0.0:
+        pd = torch.zeros_like(probs)       # padding columns stay zero (they are read as K by the PV GEMM)
+        dropout(probs.view(-1, ldp)[:, :Sk], dropout_p, seed, out=pd.view(-1, ldp)[:, :Sk])
+    pa = probs if pd is None else pd
+    out = torch.empty((B * Sq, D), device=dev, dtype=q.dtype)
+    gemm_raw(a=pa.data_ptr(), b=v.data_ptr(), d=out.data_ptr(), ab_dtype=dt, d_dtype=dt, a_mn_major=0, b_mn_major=1,
+             m=Sq, n=hd, k=Sk, a_ld=ldp, a_s2=Sq * ldp, a_s3=H * Sq * ldp, a_z2=H,
+             b_ld=D, b_s2=hd, b_s3=Sk * D, b_z2=H, d_ld=D, d_s2=hd, d_s3=Sq * D, z_lo=H, z_hi=B,
+             a_div=1, a_mul=1, a_seg=0, b_div=1, b_mul=1, b_seg=0, k_segs=1, alpha=1.0)
+    return out, probs, pd
+
+
+def cross_attention_bwd(dout: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, probs: torch.Tensor,
+                        probs_dropped: Optional[torch.Tensor], B: int, Sq: int, Sk: int, H: int, *,
+                        dropout_p: float = 0.0, seed: int = 0, need_dq: bool = True, need_dkv: bool = True):
+    """Gradients (dq, dk, dv) of cross_attention_fwd."""
+    _cuda(dout, q, k, v, probs)
+    dt, dev = _dt(q), q.device
+    D = q.shape[1]
+    hd = D // H
+    ldp = probs.shape[-1]
+    lds = (Sk + 3) // 4 * 4
+    scale = hd ** -0.5
+    pa = probs if probs_dropped is None else probs_dropped
+    dq = dk = dv = None
+    if need_dkv:
+        dv = torch.empty_like(v)
+        gemm_raw(a=pa.data_ptr(), b=dout.data_ptr(), d=dv.data_ptr(), ab_dtype=dt, d_dtype=dt, a_mn_major=1,
+                 b_mn_major=1, m=Sk, n=hd, k=Sq, a_ld=ldp, a_s2=Sq * ldp, a_s3=H * Sq * ldp, a_z2=H, b_ld=D, b_s2=hd,
+                 b_s3=Sq * D, b_z2=H, d_ld=D, d_s2=hd, d_s3=Sk * D, z_lo=H, z_hi=B, a_div=1, a_mul=1, a_seg=0,
+                 b_div=1, b_mul=1, b_seg=0, k_segs=1, alpha=1.0)
+    dp = torch.empty((B, H, Sq, lds), device=dev, dtype=torch.float32)
+    gemm_raw(a=dout.data_ptr(), b=v.data_ptr(), d=dp.data_ptr(), ab_dtype=dt, d_dtype=F32, a_mn_major=0, b_mn_major=0,
+             m=Sq, n=Sk, k=hd, a_ld=D, a_s2=hd, a_s3=Sq * D, a_z2=H, b_ld=D, b_s2=hd, b_s3=Sk * D, b_z2=H,
+             d_ld=lds, d_s2=Sq * lds, d_s3=H * Sq * lds, z_lo=H, z_hi=B, a_div=1, a_mul=1, a_seg=0,
+             b_div=1, b_mul=1, b_seg=0, k_segs=1, alpha=1.0)
+    if dropout_p > 0.0:
+        dropout(dp.view(-1, lds)[:, :Sk], dropout_p, seed, out=dp.view(-1, lds)[:, :Sk])
+    ds = torch.zeros_like(probs) if ldp != Sk else torch.empty_like(probs)
+    softmax_bwd(probs, dp, ds, B * H * Sq, Sk, ldp, lds, ldp, scale)
+    if need_dq:
+        dq = torch.empty_like(q)
+        gemm_raw(a=ds.data_ptr(), b=k.data_ptr(), d=dq.data_ptr(), ab_dtype=dt, d_dtype=dt, a_mn_major=0, b_mn_major=1,
+                 m=Sq, n=hd, k=Sk, a_ld=ldp, a_s2=Sq * ldp, a_s3=H * Sq * ldp, a_z2=H, b_ld=D, b_s2=hd, b_s3=Sk * D,
+                 b_z2=H, d_ld=D, d_s2=hd, d_s3=Sq * D, z_lo=H, z_hi=B, a_div=1, a_mul=1, a_seg=0, b_div=1, b_mul=1,
+                 b_seg=0, k_segs=1, alpha=1.0)
+    if need_dkv:
+        dk = torch.empty_like(k)
+        gemm_raw(a=ds.data_ptr(), b=q.data_ptr(), d=dk.data_ptr(), ab_dtype=dt, d_dtype=dt, a_mn_major=1, b_mn_major=1,
+                 m=Sk, n=hd, k=Sq, a_ld=ldp, a_s2=Sq * ldp, a_s3=H * Sq * ldp, a_z2=H, b_ld=D, b_s2=hd, b_s3=Sq * D,
+                 b_z2=H, d_ld=D, d_s2=hd, d_s3=Sk * D, z_lo=H, z_hi=B, a_div=1, a_mul=1, a_seg=0, b_div=1, b_mul=1,
+                 b_seg=0, k_segs=1, alpha=1.0)
+    return dq, dk, dv

@@ -168,6 +168,28 @@ int b200_add_pos_fwd(const void* x, const void* pos, void* out, int64_t B, int64
                      void* stream);
 int b200_add_pos_bwd(const void* dout, float* d_pos, int64_t B, int64_t P, int64_t D, int dtype, void* stream);
 
+/* ---- MemVLA memory path (memvla_arch.py) ---------------------------------------------------------------
+ * Stateless counter-based dropout: out[r,c] = u(seed, r*cols+c) >= p ? x[r,c]/(1-p) : 0.  Replaces the dropout
+ * inside F.scaled_dot_product_attention(dropout_p=...) and the two nn.Dropout of CrossTransformerBlock.ffn
+ * (memvla_arch.py:97-103,122-124); applying it to the incoming gradient with the same (seed, shape) IS the
+ * backward pass, so no mask is stored.  The random stream is this library's own (the reference's is cuRAND Philox
+ * driven by torch's global generator): parity holds in distribution, bit parity at p = 0. */
+int b200_dropout(const void* x, void* out, int64_t rows, int64_t cols, int64_t x_ld, int64_t out_ld, float p,
+                 uint64_t seed, int dtype, void* stream);
+/* BottleneckSE (memvla_arch.py:136-173).  se_reduce: out_f32[b,c] += scale * sum_p x[b,p,c] * (y ? y[b,p,c] : 1) —
+ * AdaptiveAvgPool2d(1) with scale = 1/P, and the channel-gate gradient sum_p dout*x.  se_scale:
+ * out[b,p,c] = x[b,p,c]*w[b,c] + (add ? add[b,c]*add_scale : 0) — `x * w` forward, and
+ * dx = dout*w + dpool/P backward.  x is the projected vision feature map [B, P, C] (channel-last view of the
+ * reference's [B,C,H,W] permute; the 1x1 convs are GEMMs on this layout). */
+int b200_se_reduce(const void* x, const void* y, float* out_f32, int64_t B, int64_t P, int64_t C, float scale, int dtype,
+                   void* stream);
+int b200_se_scale(const void* x, const void* w, const void* add, void* out, int64_t B, int64_t P, int64_t C,
+                  float add_scale, int dtype, void* stream);
+/* GateFusion (memvla_arch.py:176-192): s = sigmoid(z); out = s*x1 + (1-s)*x2; backward gives dz, dx1, dx2. */
+int b200_gate_fuse_fwd(const void* z, const void* x1, const void* x2, void* out, int64_t n, int dtype, void* stream);
+int b200_gate_fuse_bwd(const void* dout, const void* z, const void* x1, const void* x2, void* dz, void* dx1, void* dx2,
+                       int64_t n, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -335,7 +335,7 @@ def make_pi0_inference_tiny(seed: int = 2468):
                                 states=states), outputs=outs), GOLDEN / "pi0_inference_tiny.pt")
 
 
-MEMVLA_MEM = dict(dataloader_type="group", group_size=3, per_token_size=16, mem_length=2, retrieval_layers=2,
+MEMVLA_MEM = dict(dataloader_type="group", group_size=3, per_token_size=32, mem_length=2, retrieval_layers=2,
                   use_timestep_pe=True, fusion_type="gate", consolidate_type="tome", update_fused=True)
 
 
