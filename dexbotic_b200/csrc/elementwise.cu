@@ -256,6 +256,56 @@ __global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const T* __restri
   }
 }
 
+// Rows wider than the register-cached kernel holds (D > 8*256*kMaxPacks; OFT's MLPResNet input LayerNorm has
+// D = action_dim * hidden = 25088, oft/action_model/model.py:108,146): one block per row, two streaming passes,
+// dw / db by fp32 atomics (such inputs have a few hundred rows).
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_bwd_wide_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                 const T* __restrict__ w, const float* __restrict__ mean,
+                                                                 const float* __restrict__ rstd, T* dx,
+                                                                 float* __restrict__ dw, float* __restrict__ db, int M,
+                                                                 int D, int accumulate_dx) {
+  __shared__ float red[33];
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const T* xr = x + (size_t)row * D;
+    const T* dyr = dy + (size_t)row * D;
+    T* dxr = dx + (size_t)row * D;
+    const float mu = mean[row], r = rstd[row];
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
+      float xv[8], dv[8], wv[8];
+      Pack8<T>::load(xr + i, xv);
+      Pack8<T>::load(dyr + i, dv);
+      if (w != nullptr) Pack8<T>::load(w + i, wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = dv[j] * (w != nullptr ? wv[j] : 1.0f);
+        s1 += g;
+        s2 += g * (xv[j] - mu) * r;
+      }
+    }
+    s1 = block_sum(s1, red) / (float)D;
+    s2 = block_sum(s2, red) / (float)D;
+    for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
+      float xv[8], dv[8], wv[8], o[8];
+      Pack8<T>::load(xr + i, xv);
+      Pack8<T>::load(dyr + i, dv);
+      if (w != nullptr) Pack8<T>::load(w + i, wv);
+      if (accumulate_dx) Pack8<T>::load(dxr + i, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xv[j] - mu) * r;
+        const float g = dv[j] * (w != nullptr ? wv[j] : 1.0f);
+        const float t = r * (g - s1 - xh * s2);
+        o[j] = accumulate_dx ? o[j] + t : t;
+        if (dw != nullptr) atomicAdd(dw + i + j, dv[j] * xh);
+        if (db != nullptr) atomicAdd(db + i + j, dv[j]);
+      }
+      Pack8<T>::store(dxr + i, o);
+    }
+  }
+}
+
 // --------------------------------------------------------------------- RoPE
 // In-place rotate_half RoPE on the first `n_rot_heads` heads of every row of a packed
 // [M, row_stride] buffer (q heads then k heads).  cos/sin: fp32 tables [n_pos, hd/2].
@@ -715,8 +765,15 @@ int b200_layernorm_fwd(const void* x, const void* w, const void* b, void* y, flo
 int b200_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
                        float* dw, float* db, float* workspace, int64_t M, int64_t D, int accumulate_dx, int dtype,
                        void* stream) {
-  B200_CHECK(D % 8 == 0 && D <= 8 * 256 * kMaxPacks, "layernorm_bwd: unsupported D=%lld", (long long)D);
+  B200_CHECK(D % 8 == 0, "layernorm_bwd: D=%lld must be a multiple of 8", (long long)D);
   if (M == 0) return 0;
+  if (D > 8 * 256 * kMaxPacks) {
+    DISPATCH_T(dtype, (layernorm_bwd_wide_kernel<T><<<grid_for_rows(M, 4), 256, 0, STREAM>>>(
+                          (const T*)dy, (const T*)x, (const T*)w, mean, rstd, (T*)dx, dw, db, (int)M, (int)D,
+                          accumulate_dx)));
+    B200_LAUNCH_OK();
+    return 0;
+  }
   const int nt = norm_threads(D);
   const int grid = grid_for_rows(M, 1024 / nt);
   // workspace rows hold [dw partial | db partial]; it is only usable when both gradients are wanted

@@ -3,6 +3,6 @@ forward signatures, config fields and state-dict keys; the arithmetic runs in li
 from .dexbotic_arch import (CausalLMOutputDexbotic, DexboticConfig, DexboticVLMModel, IGNORE_INDEX,  # noqa: F401
                             IMAGE_TOKEN_INDEX)
 from .cogact_arch import CogActConfig, CogActModel, CogACTForCausalLM  # noqa: F401
-from .oft_arch import OFTConfig, OFTDiscreteConfig, OFTDiscreteForCausalLM  # noqa: F401
+from .oft_arch import OFTConfig, OFTDiscreteConfig, OFTDiscreteForCausalLM, OFTForCausalLM  # noqa: F401
 from .pi0_arch import Pi0Config, Pi0ForCausalLM  # noqa: F401
 from .memvla_arch import MemVLAConfig, MemVLAForCausalLM, MemVLAModel  # noqa: F401

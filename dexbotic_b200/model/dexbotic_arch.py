@@ -385,8 +385,22 @@ class DexboticVLMModel:
             self.proj = [Lin.of(store, f"{p}{2 * i}.weight", f"{p}{2 * i}.bias") for i in range(n)]
 
     @property
-    def backbone(self):
+    def backbone(self):                       # dexbotic_arch.py:153-155
         return self.llm
+
+    @property
+    def mm_projector_module(self):            # :125-127
+        return self.proj
+
+    @property
+    def mm_vision_module(self):               # :133-135
+        return self.mm_vision_tower
+
+    def initialize_model(self, extra_config: dict):
+        """dexbotic_arch.py:122-129.  The reference (re)builds the vision tower / projector / action head here for
+        checkpoints that lack them; this backend always builds every module in __init__, so only the config moves."""
+        for key, value in extra_config.items():
+            setattr(self.config, key, value)
 
     def refresh(self):
         self.mm_vision_tower.refresh()
@@ -446,7 +460,9 @@ class DexboticVLMModel:
             pad = torch.full((B, A), -(2 ** 31), device=src.device, dtype=torch.int32)
             src_ext = torch.cat([src, pad], dim=1)
             shifted = torch.cat([pad, src], dim=1)              # src[b, s - A] for the tail
-            src = torch.where(idx < ln, src_ext, torch.where(idx < ln + A, torch.full_like(src_ext, append_token_id),
+            # append_token_id None: zero rows (the caller adds its own embeddings there, OFT's action_query)
+            fill = -(2 ** 31) if append_token_id is None else append_token_id
+            src = torch.where(idx < ln, src_ext, torch.where(idx < ln + A, torch.full_like(src_ext, fill),
                                                              shifted)).contiguous()
             new_mask = (idx < ln + A).to(torch.uint8).contiguous()
             pos = idx.expand(B, S + A).contiguous()             # HF default position ids: arange (position_ids=None)

@@ -1,5 +1,7 @@
-"""Mirror of dexbotic/model/oft/{oft_arch.py, oft_discrete_arch.py} for the DISCRETE action tokenizer
-(SURVEY.md §8a row A9): OFTDiscreteConfig / OFTDiscreteForCausalLM with the reference's forward signature.
+"""Mirror of dexbotic/model/oft/{oft_arch.py, oft_discrete_arch.py}: OFTConfig /
+OFTForCausalLM with the `Linear` L1-regression head (oft_arch.py:58-166, oft/action_model/model.py:104-165) and
+OFTDiscreteConfig / OFTDiscreteForCausalLM (the discrete action tokenizer), with the reference's forward signatures.
+The `DiT` DiffusionActionHead variant needs diffusers' DDIMScheduler (un-pinned, not installable offline): not built.
 
 Integer semantics (bit-exact, tests/test_gpu_oft.py): inference indices = argmax over the last num_bins-1
 vocabulary logits, first maximum wins (oft_discrete_arch.py:222-224); bins -> continuous idx/(num_bins-1)*2-1
@@ -13,7 +15,7 @@ import numpy as np
 import torch
 
 from .. import ops
-from ..functional import CrossEntropyFn, GatherRowsFn, Lin, LinearFn
+from ..functional import CastFn, CrossEntropyFn, GatherRowsFn, Lin, LinearFn, Norm, NormFn
 from ..params import ParamSpec
 from ._module import B200Module
 from .dexbotic_arch import (CausalLMOutputDexbotic, DexboticConfig, DexboticVLMModel, cfg_get, clip_specs, llm_specs,
@@ -164,6 +166,179 @@ class OFTDiscreteForCausalLM(B200Module):
                        eps: float = 1e-8, weight_decay: float = 0.0, max_grad_norm=1.0):
         lrs = {"llm": base_lr, "projector": mm_projector_lr or base_lr, "vision": mm_vision_lr or base_lr,
                "lm_head": base_lr}
+        norm = self.store.adamw_step(lrs, betas, eps, weight_decay, max_grad_norm)
+        self.model_engine.refresh()
+        return norm
+
+
+# ------------------------------------------------------------------------------------------------
+# OFT with the L1-regression head
+# ------------------------------------------------------------------------------------------------
+def oft_linear_head_specs(d: int, action_dim: int, chunk: int, use_proprio: bool, proprio_dim, trainable: bool = True,
+                          prefix: str = "model.action_head.") -> list[ParamSpec]:
+    """L1RegressionActionHead (oft/action_model/model.py:133-152): fp32 storage like the other action heads."""
+    g, c = "action_head", "fp32"
+    P = lambda n, s, **k: ParamSpec(prefix + n, s, g, c, trainable=trainable, **k)  # noqa: E731
+    din = d * action_dim
+    sp = [P("action_query", (1, chunk * action_dim, d), no_decay=True),
+          P("model.layer_norm1.weight", (din,)), P("model.layer_norm1.bias", (din,)),
+          P("model.fc1.weight", (d, din)), P("model.fc1.bias", (d,))]
+    for i in range(2):
+        q = f"model.mlp_resnet_blocks.{i}.ffn."
+        sp += [P(q + "0.weight", (d,)), P(q + "0.bias", (d,)), P(q + "1.weight", (d, d)), P(q + "1.bias", (d,))]
+    sp += [P("model.layer_norm2.weight", (d,)), P("model.layer_norm2.bias", (d,)),
+           P("model.fc2.weight", (action_dim, d)), P("model.fc2.bias", (action_dim,))]
+    if use_proprio:
+        sp += [P("proprio_projector.fc1.weight", (d, proprio_dim)), P("proprio_projector.fc1.bias", (d,)),
+               P("proprio_projector.fc2.weight", (d, d)), P("proprio_projector.fc2.bias", (d,))]
+    return sp
+
+
+class InsertRowsFn(torch.autograd.Function):
+    """insert_action_embedding (oft_arch.py:169-201): the sequence buffer already has zero rows at the action slots
+    (the splice plan leaves them empty); this returns a copy with the action embeddings added there."""
+
+    @staticmethod
+    def forward(ctx, emb2d, act2d, idx):
+        ctx.save_for_backward(idx)
+        out = emb2d.clone()
+        ops.scatter_rows_add_(act2d.contiguous(), idx, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        g = g.contiguous()
+        return g, ops.gather_rows(g, idx), None
+
+
+class L1RegressionActionHead:
+    """oft/action_model/model.py:104-165 (MLPResNet with two residual blocks)."""
+
+    def __init__(self, store, d: int, action_dim: int, chunk: int, use_proprio: bool, prefix: str = "model.action_head."):
+        self.store, self.d, self.action_dim, self.action_chunk = store, d, action_dim, chunk
+        L = lambda n: Lin.of(store, prefix + n + ".weight", prefix + n + ".bias")  # noqa: E731
+        N_ = lambda n: Norm("ln", 1e-5, store.w(prefix + n + ".weight"), store.w(prefix + n + ".bias"),  # noqa: E731
+                            store.g(prefix + n + ".weight"), store.g(prefix + n + ".bias"))
+        self.ln1, self.fc1 = N_("model.layer_norm1"), L("model.fc1")
+        self.blocks = [(N_(f"model.mlp_resnet_blocks.{i}.ffn.0"), L(f"model.mlp_resnet_blocks.{i}.ffn.1")) for i in range(2)]
+        self.ln2, self.fc2 = N_("model.layer_norm2"), L("model.fc2")
+        self.proprio = (L("proprio_projector.fc1"), L("proprio_projector.fc2")) if use_proprio else None
+
+    def predict_action(self, hidden2d_f32: torch.Tensor, B: int) -> torch.Tensor:
+        """hidden2d [B*chunk*action_dim, d] fp32 -> [B, chunk, action_dim]."""
+        st = self.store
+        x = hidden2d_f32.reshape(B * self.action_chunk, self.action_dim * self.d)
+        x = LinearFn.apply(NormFn.apply(x, self.ln1, st), self.fc1, "relu", st, True, None)
+        for ln, lin in self.blocks:
+            x = x + LinearFn.apply(NormFn.apply(x, ln, st), lin, "relu", st, True, None)
+        x = LinearFn.apply(NormFn.apply(x, self.ln2, st), self.fc2, None, st, True, None)
+        return x.view(B, self.action_chunk, self.action_dim)
+
+    def proprio_projector(self, states: torch.Tensor, anchor) -> torch.Tensor:
+        st = self.store
+        h = LinearFn.apply(states.float().contiguous(), self.proprio[0], "gelu", st, False, anchor)
+        return LinearFn.apply(h, self.proprio[1], None, st, True, None)
+
+
+class OFTForCausalLM(B200Module):
+    """oft_arch.py:50-251 with action_model_type 'Linear'."""
+    config_class = OFTConfig
+
+    def __init__(self, config: OFTConfig, device="cuda"):
+        super().__init__()
+        if "Linear" not in (config.action_model_type or ""):
+            raise NotImplementedError("OFTForCausalLM mirrors the L1-regression ('Linear') head; the 'DiT' head needs "
+                                      "diffusers' DDIMScheduler (oft/action_model/model.py:9,220) and is not built; "
+                                      "'Discrete' is OFTDiscreteForCausalLM")
+        self.config = config
+        llm, vis = config.llm_config, config.mm_vision_tower
+        d, V = cfg_get(llm, "hidden_size"), cfg_get(llm, "vocab_size")
+        specs = (llm_specs(llm, trainable=not config.freeze_llm)
+                 + clip_specs(vis, trainable=not config.freeze_mm_vision)
+                 + projector_specs(config.mm_projector_type, cfg_get(vis, "hidden_size"), d,
+                                   trainable=not config.freeze_mm_projector)
+                 + oft_linear_head_specs(d, config.action_dim, config.chunk_size, config.use_proprio, config.proprio_dim)
+                 + [ParamSpec("lm_head.weight", (V, d), "lm_head", trainable=False)])   # never used by this head
+        store = self._materialize(specs, device)
+        for name in store.order:
+            if store.slots[name].region == "B":
+                self.get_parameter(name).grad = store.g(name)
+        self.model_engine = DexboticVLMModel(store, config)
+        self.model_engine.action_head = L1RegressionActionHead(store, d, config.action_dim, config.chunk_size,
+                                                               config.use_proprio)
+
+    def _after_weights_changed(self) -> None:
+        self.model_engine.refresh()
+
+    def forward(self,
+                input_ids: torch.LongTensor = None,
+                attention_mask: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.LongTensor] = None,
+                past_key_values: Optional[List[torch.FloatTensor]] = None,
+                inputs_embeds: Optional[torch.FloatTensor] = None,
+                labels: Optional[torch.LongTensor] = None,
+                use_cache: Optional[bool] = None,
+                output_attentions: Optional[bool] = None,
+                output_hidden_states: Optional[bool] = None,
+                images: Optional[torch.FloatTensor] = None,
+                return_dict: Optional[bool] = None,
+                cache_position: Optional[torch.LongTensor] = None,
+                actions: Optional[torch.LongTensor] = None,
+                states: Optional[torch.LongTensor] = None,
+                noisy_dict: Optional[dict] = None,
+                **kwargs) -> CausalLMOutputDexbotic:
+        if not input_ids.is_cuda:
+            raise RuntimeError("dexbotic_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        cfg, eng, st = self.config, self.model_engine, self.store
+        head = eng.action_head
+        B, A, T = input_ids.shape[0], cfg.action_dim, cfg.chunk_size
+        n_q = T * A
+        n_act = n_q + (1 if cfg.use_proprio else 0)
+        if attention_mask is None:
+            attention_mask = torch.ones_like(input_ids)
+        emb, _, new_mask, pos, S, lengths = eng._prepare_inputs_labels_for_multimodal(
+            input_ids, attention_mask, None, images, append_tokens=n_act, append_token_id=None)
+        dev = emb.device
+        d = emb.shape[-1]
+        # action embeddings: [proprio token |] action_query, the same learned rows for every sample (:107-121)
+        aq = self.get_parameter("model.action_head.action_query")                     # fp32 [1, n_q, d]
+        act = aq.expand(B, n_q, d)
+        if cfg.use_proprio:
+            assert states is not None, "states is required when use_proprio is True"
+            s_tok = head.proprio_projector(states, eng.anchor.t).view(B, 1, d)
+            act = torch.cat([s_tok, act], dim=1)
+        act2d = act.to(emb.dtype).reshape(B * n_act, d)
+        rows = (torch.arange(B, device=dev, dtype=torch.int32)[:, None] * S + lengths[:, None]
+                + torch.arange(n_act, device=dev, dtype=torch.int32)[None, :]).reshape(-1).contiguous()
+        emb2d = InsertRowsFn.apply(emb.view(B * S, d), act2d, rows)
+        hidden2d = eng.llm.forward(emb2d, B, S, new_mask, pos)
+        # extract_action_hidden_states (:204-210), minus the proprio row (:139-140)
+        qrows = rows.view(B, n_act)[:, n_act - n_q:].reshape(-1).contiguous()
+        ah = CastFn.apply(GatherRowsFn.apply(hidden2d, qrows), torch.float32)         # [B*n_q, d]
+        predicted = head.predict_action(ah, B)
+        loss = None
+        if actions is not None:                                                        # :149-152, fp32
+            a = actions.reshape(B, -1, A)[:, :T, :].to(torch.float32)
+            loss = (a - predicted).abs().mean()
+        return CausalLMOutputDexbotic(loss=loss, logits=predicted)
+
+    @torch.no_grad()
+    def inference_action(self, input_ids, image_tensor, inference_args={}, **kwargs):
+        """oft_arch.py:212-251 ('Linear' branch)."""
+        action_norms = inference_args.get("action_norms")
+        out = self.forward(input_ids=input_ids, images=image_tensor, states=inference_args.get("states"))
+        actions = np.clip(out.logits[0].float().cpu().numpy(), -1, 1)        # _denorm, dexbotic_arch.py:546-563
+        mn, mx = np.array(action_norms["min"]).reshape(1, -1), np.array(action_norms["max"]).reshape(1, -1)
+        return (mn + (actions + 1) * 0.5 * (mx - mn)).tolist()
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.store.zero_grad()
+
+    def optimizer_step(self, base_lr: float = 2e-5, mm_projector_lr=None, mm_vision_lr=None, action_head_lr=None,
+                       betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, max_grad_norm=1.0):
+        lrs = {"llm": base_lr, "projector": mm_projector_lr or base_lr, "vision": mm_vision_lr or base_lr,
+               "action_head": action_head_lr or base_lr, "lm_head": base_lr}
         norm = self.store.adamw_step(lrs, betas, eps, weight_decay, max_grad_norm)
         self.model_engine.refresh()
         return norm

@@ -105,7 +105,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         _lib.check(lib.b200_gemm(C.byref(g), _stream()), "gemm")
     else:
         if aux is not None:
-            raise RuntimeError("gemm: aux output needs TMA-compatible (16-byte) strides")
+            # odd-stride operands (e.g. a 9-wide proprio state): pre-activation by the SIMT kernel, then the activation
+            if residual is not None or not aux.is_contiguous() or not out.is_contiguous():
+                raise RuntimeError("gemm: aux output on the SIMT path needs contiguous out/aux and no residual")
+            g.d, g.d_ld, g.act, g.aux = aux.data_ptr(), aux.stride(0), 0, None
+            _lib.check(lib.b200_gemm_simt(C.byref(g), _stream()), "gemm_simt")
+            return act_fwd(aux, act, out=out)
         _lib.check(lib.b200_gemm_simt(C.byref(g), _stream()), "gemm_simt")
     return out
 
@@ -346,7 +351,7 @@ def layernorm_bwd(dy, x, w, mean, rstd, dx=None, dw=None, db=None, accumulate_dx
         assert not accumulate_dx
         dx = torch.empty_like(x)
     ws = None
-    if dw is not None and db is not None:
+    if dw is not None and db is not None and D <= 8192:     # wider rows take the streaming kernel (no workspace)
         ws = torch.empty((int(_lib.load().b200_norm_bwd_workspace_rows(M, D)), 2 * D), device=x.device,
                          dtype=torch.float32)
     _lib.check(_lib.load().b200_layernorm_bwd(dy.data_ptr(), x.data_ptr(), _p(w), mean.data_ptr(), rstd.data_ptr(),

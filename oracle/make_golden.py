@@ -233,6 +233,52 @@ def make_oft_discrete_tiny(seed: int = 4321):
     print("[oft_discrete_tiny] wrote fixture")
 
 
+def make_oft_linear_tiny(seed: int = 8642):
+    """OFTForCausalLM with the L1-regression head, with and without the proprio token (oft_arch.py:58-166)."""
+    out_fx = {}
+    for use_proprio in (False, True):
+        llm, clip, cfg = tiny_cogact_configs()
+        cfg = dict(cfg, chunk_size=8, action_dim=7, use_proprio=use_proprio, proprio_dim=9 if use_proprio else None)
+        model = ref_loader.build_reference_oft_linear(llm, clip, 7, 8, use_proprio, cfg["proprio_dim"])
+        sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        g = torch.Generator().manual_seed(seed)
+        B, L = 3, 12
+        ids = torch.randint(1, 128, (B, L), generator=g)
+        ids[:, 1] = vla_oracle.IMAGE_TOKEN_INDEX
+        mask = torch.ones(B, L, dtype=torch.long)
+        mask[1, L - 3:] = 0
+        mask[2, L - 1:] = 0
+        images = torch.randn(B, 3, 28, 28, generator=g)
+        actions = torch.rand(B, 8 * 7, generator=g) * 2 - 1
+        states = torch.randn(B, 9, generator=g) if use_proprio else None
+        out = model(input_ids=ids, attention_mask=mask, images=images, actions=actions, states=states)
+        out.loss.backward()
+        ora = vla_oracle.oft_l1_forward(sd, cfg, ids, mask, images, actions, states)
+        d_loss = abs(ora["loss"].item() - out.loss.item())
+        d_pred = (ora["predicted_actions"] - out.logits).abs().max().item()
+        print(f"[oft_linear_tiny proprio={use_proprio}] reference loss {out.loss.item():.8f} oracle "
+              f"{ora['loss'].item():.8f}; actions max|d|={d_pred:.2e}")
+        assert d_loss < 1e-5 and d_pred < 1e-4
+        names = ["model.action_head.action_query", "model.action_head.model.fc1.weight",
+                 "model.action_head.model.layer_norm1.weight", "model.action_head.model.mlp_resnet_blocks.1.ffn.1.weight",
+                 "model.action_head.model.fc2.bias", "model.llm.layers.1.mlp.up_proj.weight",
+                 "model.llm.layers.0.self_attn.v_proj.weight", "model.mm_projector.2.weight",
+                 "model.llm.embed_tokens.weight"]
+        if use_proprio:
+            names += ["model.action_head.proprio_projector.fc1.weight", "model.action_head.proprio_projector.fc2.bias"]
+        params = dict(model.named_parameters())
+        grads = {n: params[n].grad.clone() for n in names}
+        out_fx[use_proprio] = dict(cfg=cfg, shapes={k: tuple(v.shape) for k, v in sd.items()},
+                                   inputs=dict(input_ids=ids, attention_mask=mask, images=images, actions=actions,
+                                               states=states),
+                                   outputs=dict(loss=out.loss.detach(), predicted_actions=out.logits.detach(),
+                                                grads=grads))
+    torch.save(dict(seed=seed, cases=out_fx), GOLDEN / "oft_linear_tiny.pt")
+    print("[oft_linear_tiny] wrote fixture")
+
+
 def tiny_pi0_configs():
     llm = dict(model_type="gemma", vocab_size=128, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
                num_attention_heads=4, num_key_value_heads=1, head_dim=16, rms_norm_eps=1e-6, rope_theta=10000.0,
@@ -457,5 +503,6 @@ if __name__ == "__main__":
     make_pi0_inference_tiny()
     make_memvla_tiny()
     make_oft_discrete_tiny()
+    make_oft_linear_tiny()
     make_splice_cases()
     make_integer_kats()

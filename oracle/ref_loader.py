@@ -194,6 +194,17 @@ def build_reference_oft_discrete(llm_config, clip_config, action_dim: int = 7, c
     return OFTDiscreteForCausalLM(cfg)
 
 
+def build_reference_oft_linear(llm_config, clip_config, action_dim: int = 7, chunk_size: int = 8,
+                               use_proprio: bool = False, proprio_dim=None, mm_projector_type: str = "mlp2x_gelu"):
+    """Reference OFTForCausalLM (oft_arch.py:50-56) with the `Linear` L1-regression head, random-init weights."""
+    load_reference()
+    from dexbotic.model.oft.oft_arch import OFTConfig, OFTForCausalLM
+    cfg = OFTConfig(llm_config=llm_config, mm_projector_type=mm_projector_type, mm_vision_tower=clip_config,
+                    action_model_type="Linear", action_dim=action_dim, chunk_size=chunk_size,
+                    use_proprio=use_proprio, proprio_dim=proprio_dim)
+    return OFTForCausalLM(cfg)
+
+
 def build_reference_memvla(llm_config, clip_config, action_model_type: str = "DiT-S", action_dim: int = 7,
                            chunk_size: int = 16, mm_projector_type: str = "mlp2x_gelu", dropout: float = 0.0, **mem):
     """Reference MemVLAForCausalLM (memvla_arch.py:536-544) with random-init weights.  `mem` = the memory-module config

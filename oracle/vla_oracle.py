@@ -562,6 +562,58 @@ def oft_discrete_forward(sd, cfg: dict, input_ids, attention_mask, images, label
     return dict(loss=loss, logits=logits, action_labels=action_labels, action_hidden=ah)
 
 
+def mlp_resnet(sd, p: str, x, num_blocks: int = 2):
+    """MLPResNet (oft/action_model/model.py:104-130): LN -> fc1 -> ReLU -> n x [x + ReLU(Linear(LN(x)))] -> LN -> fc2."""
+    ln = lambda t, n: F.layer_norm(t, (t.shape[-1],), sd[p + n + ".weight"], sd[p + n + ".bias"])  # noqa: E731
+    x = F.relu(F.linear(ln(x, "layer_norm1"), sd[p + "fc1.weight"], sd[p + "fc1.bias"]))
+    for i in range(num_blocks):
+        q = f"{p}mlp_resnet_blocks.{i}.ffn."
+        h = F.layer_norm(x, (x.shape[-1],), sd[q + "0.weight"], sd[q + "0.bias"])
+        x = x + F.relu(F.linear(h, sd[q + "1.weight"], sd[q + "1.bias"]))
+    return F.linear(ln(x, "layer_norm2"), sd[p + "fc2.weight"], sd[p + "fc2.bias"])
+
+
+def oft_l1_forward(sd, cfg: dict, input_ids, attention_mask, images, actions=None, states=None):
+    """OFTForCausalLM.forward with the `Linear` (L1 regression) head (oft_arch.py:58-166; head
+    oft/action_model/model.py:133-165): the learned action_query rows (+ an optional proprio token in front) are
+    inserted after the last valid token, the LLM runs causally over them, and the hidden states of the action rows go
+    through the MLPResNet, chunk-wise ([B, chunk, action_dim * hidden]).  Returns dict(loss, predicted_actions)."""
+    A, T = cfg["action_dim"], cfg["chunk_size"]
+    B = input_ids.shape[0]
+    feats = clip_vision_features(sd, "model.mm_vision_tower.", images, cfg["vision"])
+    feats = mlp_projector(sd, "model.mm_projector.", feats, cfg.get("projector_depth", 2))
+    emb, _, msk, _ = splice(sd["model.llm.embed_tokens.weight"], feats, input_ids, attention_mask, None,
+                            cfg.get("tokenizer_model_max_length"), "right")
+    h = "model.action_head."
+    act = sd[h + "action_query"].expand(B, -1, -1)
+    if cfg.get("use_proprio"):
+        st = F.linear(F.gelu(F.linear(states, sd[h + "proprio_projector.fc1.weight"], sd[h + "proprio_projector.fc1.bias"])),
+                      sd[h + "proprio_projector.fc2.weight"], sd[h + "proprio_projector.fc2.bias"])
+        act = torch.cat([st.reshape(B, -1, emb.shape[-1]), act], dim=1)
+    n_act = act.shape[1]
+    S, D = emb.shape[1], emb.shape[2]
+    lens = msk.long().sum(dim=1)
+    emb2 = torch.zeros(B, S + n_act, D, dtype=emb.dtype)
+    msk2 = torch.zeros(B, S + n_act, dtype=torch.bool)
+    for i in range(B):                                                 # insert_action_embedding, oft_arch.py:169-201
+        n = int(lens[i])
+        emb2[i, :n] = emb[i, :n]
+        emb2[i, n:n + n_act] = act[i]
+        emb2[i, n + n_act:] = emb[i, n:]
+        msk2[i, :n + n_act] = True
+    pid = torch.arange(S + n_act)[None, :].expand(B, S + n_act)
+    hs = decoder_forward(sd, "model.llm.", emb2, msk2, pid, cfg["llm"])
+    ah = torch.stack([hs[i, int(lens[i]):int(lens[i]) + n_act] for i in range(B)])       # :204-210
+    if cfg.get("use_proprio"):
+        ah = ah[:, 1:]
+    pred = mlp_resnet(sd, h + "model.", ah.reshape(B, T, -1))
+    loss = None
+    if actions is not None:
+        a = actions.reshape(B, -1, A)[:, :T]
+        loss = (a - pred).abs().mean()
+    return dict(loss=loss, predicted_actions=pred, action_hidden=ah)
+
+
 # ----------------------------------------------------------------------------------------------
 # pi0 — dexbotic/model/pi0/pi0_arch.py (SigLIP tower: modules/mm_vision/siglip/siglip_encoder.py:61-86)
 # ----------------------------------------------------------------------------------------------

@@ -250,3 +250,39 @@ def test_training_steps_reduce_loss():
         model.optimizer_step(base_lr=1e-3)
         losses.append(out.loss.item())
     assert losses[-1] < losses[0] * 0.9, losses
+
+
+def test_reference_facing_surface_and_checkpoint_roundtrip(tmp_path):
+    """`model.model.<property>` accessors the reference's optimizer grouping reads (base_exp.py:95-203),
+    gradient-checkpointing switches, and an HF-layout save_pretrained / from_pretrained round trip."""
+    from dexbotic_b200.model import CogACTForCausalLM
+    fx = torch.load(GOLDEN / "cogact_tiny.pt", weights_only=False)
+    model, _ = _build(fx["cfg"], fx["shapes"], fx["seed"])
+    mm = model.model
+    assert mm.mm_projector_prefix == "mm_projector" and mm.mm_vision_prefix == "mm_vision"
+    assert mm.action_head_prefix == "action_head" and mm.backbone is model.model_engine.llm
+    assert mm.action_head_module is model.model_engine.action_head and mm.mm_vision_module is not None
+    names = [n for n, _ in model.named_parameters()]
+    for prefix in (mm.mm_projector_prefix, mm.mm_vision_prefix, mm.action_head_prefix):
+        assert any(prefix in n for n in names), prefix
+    mm.initialize_model({"chunk_size": fx["cfg"]["chunk_size"]})
+    assert CogACTForCausalLM.supports_gradient_checkpointing
+    model.gradient_checkpointing_enable()
+    assert model.model_engine.llm.keep_layers == 0
+    model.gradient_checkpointing_disable()
+    assert model.model_engine.llm.keep_layers is None
+
+    i = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in fx["inputs"].items()}
+    kw = dict(input_ids=i["input_ids"], attention_mask=i["attention_mask"], images=i["images"], actions=i["actions"],
+              repeated_diffusion_steps=i["repeated_diffusion_steps"], noise=i["noise"], timesteps=i["timesteps"],
+              drop_mask=i["drop_mask"])
+    with torch.no_grad():
+        l0 = model(**kw).loss.item()
+    model.save_pretrained(tmp_path / "ckpt", max_shard_size=1 << 20)        # force the sharded layout
+    assert (tmp_path / "ckpt" / "config.json").exists() and (tmp_path / "ckpt" / "model.safetensors.index.json").exists()
+    again = CogACTForCausalLM.from_pretrained(tmp_path / "ckpt")
+    a, b = model.state_dict(), again.state_dict()
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    with torch.no_grad():
+        l1 = again(**kw).loss.item()
+    assert l0 == l1, (l0, l1)

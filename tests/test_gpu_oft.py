@@ -83,3 +83,94 @@ def test_oft_integer_path_bit_exact():
     acts = model.inference_action(i["input_ids"][:1, :11].cuda(), i["images"][:1].cuda(),
                                   {"action_norms": {"min": [-1.0] * 7, "max": [1.0] * 7}})
     assert np.asarray(acts).shape == (8, 7)
+
+
+# ------------------------------------------------------------------ OFT with the L1-regression head
+def _build_linear(case, seed):
+    from dexbotic_b200.model import OFTConfig, OFTForCausalLM
+    from oracle.weights import seeded_state_dict
+    cfg = case["cfg"]
+    c = OFTConfig(llm_config=cfg["llm"], mm_vision_tower=cfg["vision"], mm_projector_type="mlp2x_gelu",
+                  action_model_type="Linear", action_dim=cfg["action_dim"], chunk_size=cfg["chunk_size"],
+                  use_proprio=cfg["use_proprio"], proprio_dim=cfg["proprio_dim"])
+    model = OFTForCausalLM(c, device="cuda")
+    sd = {k: v for k, v in seeded_state_dict(case["shapes"], seed).items() if "position_ids" not in k}
+    model.load_state_dict(sd, strict=True)
+    return model
+
+
+@pytest.mark.parametrize("use_proprio", [False, True])
+def test_oft_linear_matches_reference_golden(use_proprio):
+    """OFTForCausalLM + L1RegressionActionHead (oft_arch.py:58-166) vs the unmodified reference: state-dict keys,
+    predicted actions, L1 loss, gradients (bf16 trunk, fp32/TF32 head)."""
+    fx = torch.load(GOLDEN / "oft_linear_tiny.pt", weights_only=False)
+    case = fx["cases"][use_proprio]
+    model = _build_linear(case, fx["seed"])
+    ours = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert ours == {k: tuple(v) for k, v in case["shapes"].items() if "position_ids" not in k}
+    model.train()
+    i = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in case["inputs"].items()}
+    model.zero_grad()
+    out = model(input_ids=i["input_ids"], attention_mask=i["attention_mask"], images=i["images"], actions=i["actions"],
+                states=i["states"])
+    ref = case["outputs"]
+    assert abs(out.loss.item() - ref["loss"].item()) < 2e-2 * abs(ref["loss"].item()), (out.loss.item(), ref["loss"].item())
+    a, b = out.logits.float().flatten(), ref["predicted_actions"].cuda().flatten()
+    rel = ((a - b).norm() / b.norm()).item()
+    assert rel < 5e-2, rel
+    out.loss.backward()
+    bad = []
+    for name, gref in ref["grads"].items():
+        g = model.store.g(name).float().flatten()
+        r = gref.cuda().flatten()
+        relg = ((g - r).norm() / (r.norm() + 1e-12)).item()
+        cos = torch.nn.functional.cosine_similarity(g, r, dim=0).item()
+        # |x| has a sign() derivative: a prediction within bf16 noise of its target flips whole gradient rows, so the
+        # bound is looser than for the smooth losses (56 sign terms per sample)
+        if not (relg < 0.35 and cos > 0.94):
+            bad.append((name, round(relg, 4), round(cos, 5)))
+    assert not bad, bad
+
+
+def test_oft_linear_training_and_inference():
+    fx = torch.load(GOLDEN / "oft_linear_tiny.pt", weights_only=False)
+    case = fx["cases"][True]
+    model = _build_linear(case, fx["seed"])
+    model.train()
+    i = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in case["inputs"].items()}
+    losses = []
+    for _ in range(8):
+        model.zero_grad()
+        out = model(input_ids=i["input_ids"], attention_mask=i["attention_mask"], images=i["images"],
+                    actions=i["actions"], states=i["states"])
+        out.loss.backward()
+        model.optimizer_step(base_lr=2e-3)
+        losses.append(out.loss.item())
+    assert losses[-1] < 0.8 * losses[0], losses
+    model.eval()
+    n = int(i["attention_mask"][0].sum())
+    acts = model.inference_action(i["input_ids"][:1, :n], i["images"][:1],
+                                  {"action_norms": {"min": [-2.0] * 7, "max": [2.0] * 7}, "states": i["states"][:1]})
+    t = torch.tensor(acts)
+    assert t.shape == (8, 7) and torch.isfinite(t).all() and t.abs().max() <= 2.0
+
+
+def test_layernorm_wide_rows():
+    """D = action_dim * hidden = 25088 (OFT MLPResNet input LayerNorm) takes the streaming backward kernel."""
+    from dexbotic_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    M, D = 96, 25088
+    x = torch.randn(M, D, device="cuda", generator=g)
+    w = torch.randn(D, device="cuda", generator=g)
+    b = torch.randn(D, device="cuda", generator=g)
+    dy = torch.randn(M, D, device="cuda", generator=g)
+    y, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-5)
+    xr = x.clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), wr, br, 1e-5)
+    ref.backward(dy)
+    assert torch.allclose(y, ref, atol=1e-4, rtol=1e-4)
+    dw, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    dx = ops.layernorm_bwd(dy, x, w, mean, rstd, dw=dw, db=db)
+    assert torch.allclose(dx, xr.grad, atol=2e-4, rtol=1e-3)
+    assert torch.allclose(dw, wr.grad, atol=2e-3, rtol=1e-3) and torch.allclose(db, br.grad, atol=2e-3, rtol=1e-3)

@@ -104,6 +104,17 @@ def test_pi0_inference_matches_reference():
         assert (got - ref["actions"]).abs().max().item() < 1e-4
 
 
+def test_oft_linear_tiny_matches_reference():
+    fx = torch.load(GOLDEN / "oft_linear_tiny.pt", weights_only=False)
+    for use_proprio, case in fx["cases"].items():
+        sd = seeded_state_dict(case["shapes"], fx["seed"])
+        i, ref = case["inputs"], case["outputs"]
+        out = vla_oracle.oft_l1_forward(sd, case["cfg"], i["input_ids"], i["attention_mask"], i["images"], i["actions"],
+                                        i["states"])
+        assert abs(out["loss"].item() - ref["loss"].item()) < 1e-5
+        assert (out["predicted_actions"] - ref["predicted_actions"]).abs().max().item() < 1e-4
+
+
 def test_memvla_tiny_matches_reference():
     """MemVLA oracle (BottleneckSE, memory bank with token-merge consolidation, DiT per_attn) vs the reference."""
     fx = torch.load(GOLDEN / "memvla_tiny.pt", weights_only=False)
