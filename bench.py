@@ -47,6 +47,27 @@ WORKLOADS = {
                     num_attention_heads=16, image_size=224, patch_size=14, hidden_act="gelu_pytorch_tanh",
                     layer_norm_eps=1e-6),
         action_dim=32, chunk_size=50, batch=8, n_cam=3, text_tokens=48),
+    # SURVEY §8d cfg-5 (single-view layout the reference supports): CogACT trunk + memory bank + DiT-L with per_attn,
+    # two 16-frame episode groups per rank batch
+    "memvla_7b": dict(
+        kind="memvla",
+        llm=dict(model_type="qwen2", vocab_size=152064, hidden_size=3584, intermediate_size=18944,
+                 num_hidden_layers=28, num_attention_heads=28, num_key_value_heads=4, rms_norm_eps=1e-6,
+                 rope_theta=1e6, hidden_act="silu"),
+        vision=dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                    image_size=224, patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5),
+        action_model_type="DiT-L", action_dim=7, chunk_size=16, batch=32, instr_tokens=32, template_tokens=20,
+        mem=dict(dataloader_type="group", group_size=16, per_token_size=256, mem_length=16, retrieval_layers=2,
+                 use_timestep_pe=True, fusion_type="gate", consolidate_type="tome", update_fused=True)),
+    # SURVEY §8d cfg-4 with the L1-regression head (OpenVLA-OFT style): chunk 8 x dim 7 = 56 action-query rows
+    "oft_l1_7b": dict(
+        kind="oft_l1",
+        llm=dict(model_type="qwen2", vocab_size=152064, hidden_size=3584, intermediate_size=18944,
+                 num_hidden_layers=28, num_attention_heads=28, num_key_value_heads=4, rms_norm_eps=1e-6,
+                 rope_theta=1e6, hidden_act="silu"),
+        vision=dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                    image_size=224, patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5),
+        action_dim=7, chunk_size=8, batch=32, instr_tokens=32, template_tokens=20, extra_tokens=56),
     # small stand-in with the same structure for smoke tests / CPU-only debugging of the harness
     "cogact_tiny": dict(
         llm=dict(model_type="qwen2", vocab_size=1024, hidden_size=256, intermediate_size=704, num_hidden_layers=2,
@@ -87,6 +108,10 @@ def train_flops_per_sample(w: dict, S: int) -> float:
     T = (V["image_size"] // V["patch_size"]) ** 2 + 1
     vit = lv * (2 * T * (4 * dv * dv + 2 * dv * mv) + 4 * T * T * dv)
     proj = 2 * (T - 1) * (dv * d + d * d)
+    if w.get("kind") == "oft_l1":      # MLPResNet head: fc1 [A*d -> d] + 2 residual blocks + fc2, per chunk row
+        A, Tc = w["action_dim"], w["chunk_size"]
+        head = Tc * 2 * (A * d * d + 2 * d * d + d * A)
+        return 3.0 * (dec + vit + proj + head)
     depth, wd, _ = {"DiT-S": (6, 384, 4), "DiT-B": (12, 768, 12), "DiT-L": (24, 1024, 16)}[w["action_model_type"]]
     dit = 4 * depth * (2 * 17 * 12 * wd * wd + 4 * 17 * 17 * wd)
     return 3.0 * (dec + vit + proj + dit)
@@ -125,6 +150,9 @@ def make_batch(w: dict, rank: int, pinned: bool):
     batch = dict(input_ids=ids, attention_mask=mask, images=images, actions=actions)
     if pinned:
         batch = {k: v.pin_memory() for k, v in batch.items()}
+    if w.get("kind") == "memvla":      # (dataset, episode, frame): consecutive frames of B/group episodes
+        G = w["mem"]["group_size"]
+        batch["indexes"] = [(0, 100 * rank + b // G, 10 + b % G) for b in range(B)]
     return batch
 
 
@@ -235,23 +263,48 @@ def run_ours(args) -> dict:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     w = WORKLOADS[args.workload]
+    model = build_model(w, dev)
+    model.init_weights_(seed=1234)          # same seeded random init on every rank (no checkpoints offline)
+    model.train()
+    host = make_batch(w, rank, pinned=True)
+    B = w["batch"]
+    return _run_timed(args, w, model, host, B, rank, world, local, dev)
+
+
+def build_model(w: dict, dev):
+    from dexbotic_b200.model import CogActConfig, CogACTForCausalLM
     if w.get("kind") == "pi0":
         from dexbotic_b200.model import Pi0Config, Pi0ForCausalLM
         cfg = Pi0Config(llm_config=w["llm"], action_config=w["expert"], vision_config=w["vision"],
                         action_dim=w["action_dim"], chunk_size=w["chunk_size"])
         model = Pi0ForCausalLM(cfg, device=dev)
+    elif w.get("kind") == "memvla":
+        from dexbotic_b200.model import MemVLAConfig, MemVLAForCausalLM
+        cfg = MemVLAConfig(llm_config=w["llm"], mm_vision_tower=w["vision"], mm_projector_type="mlp2x_gelu",
+                           action_model_type=w["action_model_type"], action_dim=w["action_dim"],
+                           chunk_size=w["chunk_size"], **w["mem"])
+        model = MemVLAForCausalLM(cfg, device=dev)
+    elif w.get("kind") == "oft_l1":
+        from dexbotic_b200.model import OFTConfig, OFTForCausalLM
+        cfg = OFTConfig(llm_config=w["llm"], mm_vision_tower=w["vision"], mm_projector_type="mlp2x_gelu",
+                        action_model_type="Linear", action_dim=w["action_dim"], chunk_size=w["chunk_size"])
+        model = OFTForCausalLM(cfg, device=dev)
     else:
         cfg = CogActConfig(llm_config=w["llm"], mm_vision_tower=w["vision"], mm_projector_type="mlp2x_gelu",
                            action_model_type=w["action_model_type"], action_dim=w["action_dim"],
                            chunk_size=w["chunk_size"])
         model = CogACTForCausalLM(cfg, device=dev)
-    model.init_weights_(seed=1234)          # same seeded random init on every rank (no checkpoints offline)
-    model.train()
-    host = make_batch(w, rank, pinned=True)
-    B = w["batch"]
+    return model
+
+
+def _run_timed(args, w, model, host, B, rank, world, local, dev):
+    import torch
+    import torch.distributed as dist
+    from dexbotic_b200 import _lib
+    from dexbotic_b200.parallel import GradientOverlap
 
     def to_dev(hb):
-        return {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        return {k: (v.to(dev, non_blocking=True) if hasattr(v, "to") else v) for k, v in hb.items()}
 
     # data-parallel: gradient all-reduce only (north_star), in place on the flat buffers, overlapped with backward
     overlap = GradientOverlap(model.store)
@@ -300,6 +353,9 @@ def run_ours(args) -> dict:
         S = out.logits.shape[1]
     if w.get("kind") == "pi0":
         S = w["n_cam"] * (w["vision"]["image_size"] // w["vision"]["patch_size"]) ** 2 + w["text_tokens"] + w["chunk_size"] + 1
+    if w.get("kind") == "oft_l1":       # logits are the predicted actions there; S = text + image + action-query rows
+        S = (1 + w["instr_tokens"] + w["template_tokens"] + (w["vision"]["image_size"] // w["vision"]["patch_size"]) ** 2
+             + w["extra_tokens"])
     gt = GemmTimer()
     gt.install()
     sampler = ClockSampler(local)
@@ -314,7 +370,7 @@ def run_ours(args) -> dict:
     flops_sample = train_flops_per_sample(w, S)
     value = B * world * args.steps / (ms_dev * 1e-3)
     e2e = B * world * args.steps / (ms_e2e * 1e-3)
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if hasattr(v, "numel"))
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     traffic = None
     tp = ROOT / "profiles" / "r1_gemm_traffic.json"
@@ -329,7 +385,7 @@ def run_ours(args) -> dict:
                                 f"chunk {w['chunk_size']}, batch={B}/GPU, joint S={S}, random-init weights, AdamW + clip; "
                                 "no recompute;" if w.get("kind") == "pi0" else
                                 f"{args.workload}: CogACT ViT-L/14@224 + Qwen2.5-7B-shaped decoder + "
-                                f"{w['action_model_type']}, batch={B}/GPU, S={S}, random-init weights, AdamW + clip, "
+                                f"{w.get('action_model_type', w.get('kind'))}, batch={B}/GPU, S={S}, random-init weights, AdamW + clip, "
                                 f"{model.model_engine.llm.keep_layers}/{len(model.model_engine.llm.blocks)} decoder "
                                 "blocks keep activations (rest recompute);") +
                                " inputs << L2 but weights+grads+moments stream through HBM every step "

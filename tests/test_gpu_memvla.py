@@ -224,3 +224,69 @@ def test_memvla_inference_is_stateful():
     assert not torch.equal(t[0], t[1]), "the second frame must see the memory of the first"
     b0 = model.inference_action(ids, img, "True", norms, noise=noise)
     assert torch.allclose(torch.tensor(b0), t[0], atol=1e-6), "episode_first_frame='True' resets bank and timestep"
+
+
+def test_memvla_production_dims_one_layer_matches_oracle():
+    """Production widths (Qwen2.5-7B d=3584 -> cog role head_dim 896, FFN 14336; per_token_size 256, 256 vision
+    tokens; CLIP-L width; DiT-B with per_attn) with one decoder layer: the tile / head geometry the real model hits."""
+    from oracle import vla_oracle
+    from oracle.weights import seeded_state_dict
+    from dexbotic_b200.model import MemVLAConfig, MemVLAForCausalLM
+    mem = dict(dataloader_type="group", group_size=3, per_token_size=256, mem_length=2, retrieval_layers=2,
+               use_timestep_pe=True, fusion_type="gate", consolidate_type="tome", update_fused=True)
+    cfg = dict(
+        llm=dict(vocab_size=2048, hidden_size=3584, intermediate_size=18944, num_hidden_layers=1, num_attention_heads=28,
+                 num_key_value_heads=4, rope_theta=1e6, rms_norm_eps=1e-6, hidden_act="silu", model_type="qwen2"),
+        vision=dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=2, num_attention_heads=16, image_size=224,
+                    patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5),
+        action_model_type="DiT-B", action_dim=7, chunk_size=16, projector_depth=2, diffusion_steps=100,
+        tokenizer_model_max_length=None, tokenizer_padding_side="right", mem=mem)
+    c = MemVLAConfig(llm_config=cfg["llm"], mm_vision_tower=cfg["vision"], action_model_type="DiT-B", action_dim=7,
+                     chunk_size=16, mem_dropout=0.0, **mem)
+    model = MemVLAForCausalLM(c)
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 11)
+    model.load_state_dict(sd)
+    model.train()
+    g = torch.Generator().manual_seed(13)
+    B, L, R = 4, 40, 4
+    ids = torch.randint(1, 2048, (B, L), generator=g)
+    ids[:, 1] = -200
+    mask = torch.ones(B, L, dtype=torch.long)
+    mask[2, 33:] = 0
+    images = torch.randn(B, 3, 224, 224, generator=g)
+    actions = torch.rand(B, 112, generator=g) * 2 - 1
+    indexes = [(0, 1, 0), (0, 1, 1), (0, 1, 2), (0, 2, 7)]          # 3 frames of one episode (one token merge) + 1
+    noise = torch.randn(R * B, 16, 7, generator=g)
+    t = torch.randint(0, 100, (R * B,), generator=g)
+    drop = torch.tensor([False, False, False, True] * R)
+    names = ["model.per_compr.excite.1.weight", "model.per_compr.reduce.0.weight", "model.per_compr.reduce.2.weight",
+             "model.per_cog_mem_bank.retrieval_blocks.cog.0.q_proj.weight",
+             "model.per_cog_mem_bank.retrieval_blocks.cog.1.k_proj.weight",
+             "model.per_cog_mem_bank.retrieval_blocks.cog.1.ffn.0.weight",
+             "model.per_cog_mem_bank.retrieval_blocks.per.0.v_proj.weight",
+             "model.per_cog_mem_bank.retrieval_blocks.per.1.ffn.3.weight",
+             "model.per_cog_mem_bank.gate_fusion_blocks.cog.proj.weight",
+             "model.per_cog_mem_bank.timestep_embedders.per.mlp.2.weight",
+             "model.action_head.net.per_token_embedder.linear.weight",
+             "model.action_head.net.blocks.0.per_attn.in_proj_weight",
+             "model.action_head.net.blocks.11.per_attn.out_proj.weight", "model.action_head.net.blocks.5.norm3.weight",
+             "model.mm_projector.2.weight", "model.llm.layers.0.mlp.down_proj.weight"]
+    sd_g = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in sd.items()}
+    ora = vla_oracle.memvla_forward(sd_g, cfg, ids, mask, images, actions, indexes, noise, t, drop, R)
+    ora["loss"].backward()
+    model.zero_grad()
+    out = model(input_ids=ids.cuda(), attention_mask=mask.cuda(), images=images.cuda(), actions=actions.cuda(),
+                indexes=indexes, repeated_diffusion_steps=R, noise=noise.cuda(), timesteps=t.cuda(), drop_mask=drop.cuda())
+    assert abs(out.loss.item() - ora["loss"].item()) < 3e-2 * abs(ora["loss"].item()), (out.loss.item(), ora["loss"].item())
+    bank = model.model_engine.per_cog_mem_bank
+    rel, cos = _rel(bank.banks["cog"][(0, 2)][-1][1].cpu(), ora["cog_fused"][3].detach())
+    assert rel < 4e-2 and cos > 0.999, ("cog_fused", rel, cos)
+    rel, cos = _rel(bank.banks["per"][(0, 2)][-1][1].cpu(), ora["per_fused"][3].detach())
+    assert rel < 4e-2 and cos > 0.999, ("per_fused", rel, cos)
+    out.loss.backward()
+    bad = []
+    for name in names:
+        rel, cos = _rel(model.store.g(name).cpu(), sd_g[name].grad)
+        if not (rel < 0.2 and cos > 0.98):
+            bad.append((name, round(rel, 4), round(cos, 5)))
+    assert not bad, bad

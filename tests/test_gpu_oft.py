@@ -174,3 +174,56 @@ def test_layernorm_wide_rows():
     dx = ops.layernorm_bwd(dy, x, w, mean, rstd, dw=dw, db=db)
     assert torch.allclose(dx, xr.grad, atol=2e-4, rtol=1e-3)
     assert torch.allclose(dw, wr.grad, atol=2e-3, rtol=1e-3) and torch.allclose(db, br.grad, atol=2e-3, rtol=1e-3)
+
+
+def test_oft_linear_production_dims_one_layer_matches_oracle():
+    """d=3584, chunk 8 x dim 7: the MLPResNet input LayerNorm / fc1 run at D = 25088 (streaming LayerNorm backward,
+    K = 25088 TF32 GEMM), 56 action-query rows spliced after the 256 image tokens."""
+    from oracle import vla_oracle
+    from oracle.weights import seeded_state_dict
+    from dexbotic_b200.model import OFTConfig, OFTForCausalLM
+    cfg = dict(
+        llm=dict(vocab_size=2048, hidden_size=3584, intermediate_size=18944, num_hidden_layers=1, num_attention_heads=28,
+                 num_key_value_heads=4, rope_theta=1e6, rms_norm_eps=1e-6, hidden_act="silu", model_type="qwen2"),
+        vision=dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=2, num_attention_heads=16, image_size=224,
+                    patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5),
+        action_dim=7, chunk_size=8, projector_depth=2, use_proprio=True, proprio_dim=8,
+        tokenizer_model_max_length=None, tokenizer_padding_side="right")
+    c = OFTConfig(llm_config=cfg["llm"], mm_vision_tower=cfg["vision"], action_model_type="Linear", action_dim=7,
+                  chunk_size=8, use_proprio=True, proprio_dim=8)
+    model = OFTForCausalLM(c)
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 21)
+    model.load_state_dict(sd)
+    model.train()
+    g = torch.Generator().manual_seed(23)
+    B, L = 3, 30
+    ids = torch.randint(1, 2048, (B, L), generator=g)
+    ids[:, 1] = -200
+    mask = torch.ones(B, L, dtype=torch.long)
+    mask[1, 22:] = 0
+    images = torch.randn(B, 3, 224, 224, generator=g)
+    actions = torch.rand(B, 56, generator=g) * 2 - 1
+    states = torch.randn(B, 8, generator=g)
+    names = ["model.action_head.action_query", "model.action_head.model.fc1.weight",
+             "model.action_head.model.layer_norm1.weight", "model.action_head.model.layer_norm1.bias",
+             "model.action_head.model.mlp_resnet_blocks.0.ffn.1.weight", "model.action_head.model.fc2.weight",
+             "model.action_head.proprio_projector.fc1.weight", "model.llm.layers.0.mlp.up_proj.weight",
+             "model.mm_projector.0.weight"]
+    sd_g = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in sd.items()}
+    ora = vla_oracle.oft_l1_forward(sd_g, cfg, ids, mask, images, actions, states)
+    ora["loss"].backward()
+    model.zero_grad()
+    out = model(input_ids=ids.cuda(), attention_mask=mask.cuda(), images=images.cuda(), actions=actions.cuda(),
+                states=states.cuda())
+    assert abs(out.loss.item() - ora["loss"].item()) < 2e-2 * abs(ora["loss"].item()), (out.loss.item(), ora["loss"].item())
+    a, b = out.logits.float().cpu().flatten(), ora["predicted_actions"].detach().flatten()
+    assert ((a - b).norm() / b.norm()).item() < 5e-2
+    out.loss.backward()
+    bad = []
+    for name in names:
+        gq, r = model.store.g(name).float().cpu().flatten(), sd_g[name].grad.flatten()
+        rel = ((gq - r).norm() / (r.norm() + 1e-12)).item()
+        cos = torch.nn.functional.cosine_similarity(gq, r, dim=0).item()
+        if not (rel < 0.35 and cos > 0.94):                 # sign()-gradient of the L1 loss, see the tiny test
+            bad.append((name, round(rel, 4), round(cos, 5)))
+    assert not bad, bad

@@ -1,4 +1,5 @@
-"""Per-kernel device time of one CogACT-7B training step via torch.profiler (CUPTI), low overhead."""
+"""Per-kernel device time of one training step of a bench workload via torch.profiler (CUPTI), low overhead.
+Usage: python tools/profile_step.py [workload]"""
 import sys
 from pathlib import Path
 
@@ -6,18 +7,15 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import bench  # noqa: E402
-from dexbotic_b200.model import CogActConfig, CogACTForCausalLM  # noqa: E402
 
 
 def main():
     w = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cogact_7b"]
     dev = torch.device("cuda", 0)
-    cfg = CogActConfig(llm_config=w["llm"], mm_vision_tower=w["vision"], action_model_type=w["action_model_type"],
-                       action_dim=w["action_dim"], chunk_size=w["chunk_size"])
-    model = CogACTForCausalLM(cfg, device=dev)
+    model = bench.build_model(w, dev)
     model.init_weights_(seed=1234)
     model.train()
-    batch = {k: v.to(dev) for k, v in bench.make_batch(w, 0, pinned=False).items()}
+    batch = {k: (v.to(dev) if hasattr(v, "to") else v) for k, v in bench.make_batch(w, 0, pinned=False).items()}
 
     def step():
         model.zero_grad()
