@@ -308,6 +308,9 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
 
     # data-parallel: gradient all-reduce only (north_star), in place on the flat buffers, overlapped with backward
     overlap = GradientOverlap(model.store)
+    # the HBM-bound per-block AdamW of step t runs on a side stream under the tensor-bound forward of step t+1
+    # (ParamStore.adamw_step); the timed region below waits for the LAST step's updates before it closes
+    model.store.async_optimizer = True
 
     def step(batch):
         model.zero_grad()
@@ -335,6 +338,7 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
             out = step(batch)
             if from_host:
                 last = out.loss.item()             # device->host read of the step's result, every step
+        model.store.wait_all_params()              # the last step's overlapped optimizer updates belong to this region
         e.record()
         if gemm_timer is not None:
             gemm_timer.enabled = False

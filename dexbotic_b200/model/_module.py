@@ -68,7 +68,12 @@ class B200Module(nn.Module):
         if name == "model_engine" and "model" in self._modules:
             self._modules["model"].__dict__["_engine"] = value
 
+    def state_dict(self, *args, **kwargs):
+        self.store.wait_all_params()           # an overlapped optimizer step may still be writing the master buffer
+        return super().state_dict(*args, **kwargs)
+
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        self.store.wait_all_params()
         res = super().load_state_dict(state_dict, strict=strict, assign=False)
         self.store.refresh_shadow()
         self._after_weights_changed()

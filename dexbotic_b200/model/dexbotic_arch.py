@@ -312,6 +312,8 @@ class Decoder:
             q = f"{prefix}layers.{i}."
             bw.grad_range = store.grad_range([n for n in store.order if n.startswith(q)])
         self.final_norm = Norm(kind, eps, store.w(prefix + "norm.weight"), None, store.g(prefix + "norm.weight"))
+        if all(bw.grad_range is not None for bw in self.blocks):
+            store.set_param_chunks([bw.grad_range for bw in self.blocks])
         self.theta = rope_theta_of(cfg)
         self._rope_cache = None
         # layers [0, keep_layers) keep their intermediates (no recompute in backward); the rest recompute.
@@ -334,6 +336,7 @@ class Decoder:
         env = AttnEnv(B=B, S=S, keymask=mask_u8, causal=True, pos=pos_i32.reshape(-1), cos=cos, sin=sin)
         keep = self._decide_keep_layers(x2d) if torch.is_grad_enabled() else 0
         for i, bw in enumerate(self.blocks):
+            self.store.wait_chunk(i)        # block i's AdamW update of the previous step (ParamStore.async_optimizer)
             x2d = TransformerBlockFn.apply(x2d, bw, env, self.store, i >= keep)
         return NormFn.apply(x2d, self.final_norm, self.store)
 

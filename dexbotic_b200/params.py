@@ -88,6 +88,15 @@ class ParamStore:
         self._written: set[int] = set()       # grad tensors (by data_ptr) written since zero_grad
         self._always_zero: list[tuple[int, int]] = []   # region-A ranges that need an explicit memset per step
         self.grad_ready_hook = None            # callable(region, start, end) — data-parallel overlap
+        # Optional overlap of the optimizer with the NEXT step's forward: AdamW is HBM-bound, the forward GEMMs are
+        # tensor-bound, so the per-block updates run on a side stream in forward order and block i's forward waits
+        # only for its own event (set_param_chunks / wait_chunk).  Off by default: every reader of the weights has to
+        # go through wait_chunk / wait_all_params.
+        self.async_optimizer = False
+        self._opt_stream = None
+        self._chunk_bounds: list[tuple[int, int]] = []     # [a, b) in region-A coordinates, forward order
+        self._chunk_events: dict[int, "torch.cuda.Event"] = {}
+        self._opt_keepalive = None
 
     # ------------------------------------------------------------------ views
     def _view(self, buf: torch.Tensor, off: int, shape) -> torch.Tensor:
@@ -169,6 +178,21 @@ class ParamStore:
         assert s.region == "A"
         self._always_zero.append((s.offset, s.offset + s.spec.numel))
 
+    # ---------------------------------------------------------------- optimizer / forward overlap
+    def set_param_chunks(self, bounds: list) -> None:
+        """Region-A element ranges (e.g. one per decoder block, BlockW.grad_range) whose AdamW update may still be in
+        flight when the next forward starts; the consumer calls wait_chunk(i) right before reading chunk i."""
+        self._chunk_bounds = [tuple(b) for b in bounds if b is not None]
+
+    def wait_chunk(self, i: int) -> None:
+        ev = self._chunk_events.pop(i, None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def wait_all_params(self) -> None:
+        for i in list(self._chunk_events):
+            self.wait_chunk(i)
+
     def zero_grad(self) -> None:
         self._written.clear()
         self.grad_b.zero_()
@@ -234,7 +258,7 @@ class ParamStore:
             self.grad_norm_sq(ssq)
             clip = torch.empty((), device=dev, dtype=torch.float32)
             ops.clip_coef(ssq, max_grad_norm, clip, norm)
-        for a, b, lr, wd, region in self.segments(lrs, weight_decay):
+        def update(a, b, lr, wd, region):
             p = self.master[a:b]
             if region == "A":
                 g = self.grad_a[a:b]
@@ -244,6 +268,53 @@ class ParamStore:
                 sh = None
             ops.adamw_(p, g, self.exp_avg[a:b], self.exp_avg_sq[a:b], sh, lr, betas[0], betas[1], eps, wd,
                        self.step_count, clip)
+
+        segs = self.segments(lrs, weight_decay)
+        if not (self.async_optimizer and self._chunk_bounds):
+            self.wait_all_params()
+            for seg in segs:
+                update(*seg)
+            return norm
+
+        # split every segment at the chunk boundaries: `rest` (embeddings, towers, heads ...) first, then the chunks in
+        # forward order, all on the side stream; the caller's stream waits for `rest` only
+        rest, per_chunk = [], [[] for _ in self._chunk_bounds]
+        for a, b, lr, wd, region in segs:
+            if region != "A":
+                rest.append((a, b, lr, wd, region))
+                continue
+            cur = a
+            for i, (ca, cb) in enumerate(self._chunk_bounds):
+                lo, hi = max(cur, ca), min(b, cb)
+                if lo >= hi:
+                    continue
+                if cur < lo:
+                    rest.append((cur, lo, lr, wd, region))
+                per_chunk[i].append((lo, hi, lr, wd, region))
+                cur = hi
+            if cur < b:
+                rest.append((cur, b, lr, wd, region))
+        main = torch.cuda.current_stream()
+        if self._opt_stream is None:
+            self._opt_stream = torch.cuda.Stream(device=dev)
+        side = self._opt_stream
+        self.wait_all_params()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)
+        self._opt_keepalive = (clip, norm)            # read by side-stream kernels after this function returns
+        with torch.cuda.stream(side):
+            for seg in rest:
+                update(*seg)
+            ev_rest = torch.cuda.Event()
+            ev_rest.record(side)
+            for i, pieces in enumerate(per_chunk):
+                for seg in pieces:
+                    update(*seg)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                self._chunk_events[i] = ev
+        main.wait_event(ev_rest)
         return norm
 
     def bytes_allocated(self) -> int:
