@@ -6,3 +6,4 @@ from .cogact_arch import CogActConfig, CogActModel, CogACTForCausalLM  # noqa: F
 from .oft_arch import OFTConfig, OFTDiscreteConfig, OFTDiscreteForCausalLM, OFTForCausalLM  # noqa: F401
 from .pi0_arch import Pi0Config, Pi0ForCausalLM  # noqa: F401
 from .memvla_arch import MemVLAConfig, MemVLAForCausalLM, MemVLAModel  # noqa: F401
+from .pi05_arch import Pi05Config, Pi05ForCausalLM  # noqa: F401

@@ -228,23 +228,53 @@ def _stream_w(store: ParamStore, cfg, prefix: str, i: int) -> StreamW:
                    down=Lin.of(store, q + "mlp.down_proj.weight"))
 
 
+def ada_apply(n2d: torch.Tensor, mod: torch.Tensor, B: int) -> torch.Tensor:
+    """AdaRMS modulation (pi05/transformers_pi05/gemma/modeling_gemma.py:80-87): normed * (1 + scale) + shift in fp32,
+    scale / shift = the first two thirds of `mod` [B, 3w], shared by all rows of a sample.  A few hundred KB."""
+    w = n2d.shape[1]
+    sc, sh = mod[:, :w].float(), mod[:, w:2 * w].float()
+    y = n2d.view(B, -1, w).float() * (1.0 + sc)[:, None, :] + sh[:, None, :]
+    return y.to(n2d.dtype).view(-1, w)
+
+
+def ada_bwd(dh2d: torch.Tensor, n2d: torch.Tensor, mod: torch.Tensor, B: int):
+    """Gradient of ada_apply: (dn [rows, w], dscale [B, w] fp32, dshift [B, w] fp32)."""
+    w = n2d.shape[1]
+    dhf = dh2d.view(B, -1, w).float()
+    dsc = (dhf * n2d.view(B, -1, w).float()).sum(dim=1)
+    dsh = dhf.sum(dim=1)
+    dn = (dhf * (1.0 + mod[:, :w].float())[:, None, :]).to(dh2d.dtype).view(-1, w).contiguous()
+    return dn, dsc, dsh
+
+
+def gated_residual(x2d, y2d, gate, B: int):
+    """_gated_residual (modeling_gemma.py:101-119): x + y * gate, gate [B, w] broadcast over the rows of a sample."""
+    w = x2d.shape[1]
+    return (x2d.view(B, -1, w) + y2d.view(B, -1, w) * gate[:, None, :]).view(-1, w).contiguous()
+
+
 class MoTLayerFn(torch.autograd.Function):
     """One joint layer of `_inner_forward_mot` (pi0_arch.py:131-216): per-stream norm + QKV, attention over the
     concatenated sequence with shared RoPE, per-stream O / residual / norm / GeGLU MLP / residual.
     `tail[t] = False` skips stream t's post-attention half (prefix stream of the last layer: its output is unused)."""
 
     @staticmethod
-    def forward(ctx, x_p, x_s, streams, env: MoTEnv, store: ParamStore, tail):
+    def forward(ctx, x_p, x_s, streams, env: MoTEnv, store: ParamStore, tail, mod1=None, mod2=None):
+        """mod1 / mod2 [B, 3w]: pi0.5's AdaRMS modulation (scale | shift | gate) of the SUFFIX stream's two norms
+        (pi05_arch.py:146-152,217-228); None = pi0's plain norms and residuals."""
         B, (Sp, Ss) = env.B, env.lens
         S = Sp + Ss
         W = (env.heads + 2 * env.kv_heads) * env.head_dim
         C = env.heads * env.head_dim
         xs = (x_p, x_s)
+        ada = (None, (mod1, mod2) if mod1 is not None else None)
         joint = torch.empty((B, S, W), device=x_p.device, dtype=x_p.dtype)
         st1 = []
         off = 0
-        for x, sw, n in zip(xs, streams, (Sp, Ss)):
+        for x, sw, n, ad in zip(xs, streams, (Sp, Ss), ada):
             h, s1 = norm_fwd(x, sw.norm1)
+            if ad is not None:
+                h = ada_apply(h, ad[0], B)
             st1.append(s1)
             qkv, _ = linear_fwd(h, sw.qkv)
             ops.copy3d_(qkv, joint, B, n, W, n * W, W, S * W, W, dst_off=off * W)
@@ -254,7 +284,7 @@ class MoTLayerFn(torch.autograd.Function):
         attn, probs = ops.attention_fwd(joint, sh, keymask=env.keymask, bid_q=env.bid, bid_k=env.bid)
         outs, keep = [], []
         off = 0
-        for x, sw, n, has_tail in zip(xs, streams, (Sp, Ss), tail):
+        for x, sw, n, has_tail, ad in zip(xs, streams, (Sp, Ss), tail, ada):
             if not has_tail:
                 outs.append(torch.zeros(1, device=x.device, dtype=x.dtype))
                 keep.append(None)
@@ -263,66 +293,106 @@ class MoTLayerFn(torch.autograd.Function):
             a = torch.empty((B * n, C), device=x.device, dtype=x.dtype)
             ops.copy3d_(attn, a, B, n, C, S * C, C, n * C, C, src_off=off * C)
             off += n
-            x1, _ = linear_fwd(a, sw.o, residual=x)
-            h2, s2 = norm_fwd(x1, sw.norm2)
+            if ad is None:
+                x1, _ = linear_fwd(a, sw.o, residual=x)
+                h2, s2 = norm_fwd(x1, sw.norm2)
+                y_o = y_m = None
+            else:
+                w_ = x.shape[1]
+                y_o, _ = linear_fwd(a, sw.o)
+                x1 = gated_residual(x, y_o, ad[0][:, 2 * w_:], B)
+                h2, s2 = norm_fwd(x1, sw.norm2)
+                h2 = ada_apply(h2, ad[1], B)
             g, _ = linear_fwd(h2, sw.gate)
             u, _ = linear_fwd(h2, sw.up)
             hm = ops.glu_fwd(g, u, env.act)
-            y, _ = linear_fwd(hm, sw.down, residual=x1)
+            if ad is None:
+                y, _ = linear_fwd(hm, sw.down, residual=x1)
+            else:
+                y_m, _ = linear_fwd(hm, sw.down)
+                y = gated_residual(x1, y_m, ad[1][:, 2 * w_:], B)
             outs.append(y)
-            keep.append(dict(a=a, x1=x1, s2=s2, g=g, u=u))
-        ctx.save_for_backward(x_p, x_s)
+            keep.append(dict(a=a, x1=x1, s2=s2, g=g, u=u, y_o=y_o, y_m=y_m))
+        if mod1 is not None:
+            ctx.save_for_backward(x_p, x_s, mod1, mod2)
+        else:
+            ctx.save_for_backward(x_p, x_s)
         ctx.misc = (streams, env, store, tail, joint, probs, st1, keep, sh)
         return outs[0], outs[1]
 
     @staticmethod
     def backward(ctx, dy_p, dy_s):
-        x_p, x_s = ctx.saved_tensors
+        x_p, x_s, *mods = ctx.saved_tensors
         streams, env, store, tail, joint, probs, st1, keep, sh = ctx.misc
         ctx.misc = None
         B, (Sp, Ss) = env.B, env.lens
         S = Sp + Ss
         W = (env.heads + 2 * env.kv_heads) * env.head_dim
         C = env.heads * env.head_dim
+        ada = (None, tuple(mods) if mods else None)
+        dmods = [None, None]          # [d(scale|shift|gate) of norm1, of norm2] for the suffix stream
         dattn = torch.zeros((B, S, C), device=x_p.device, dtype=x_p.dtype)
         dx1s = []
         off = 0
-        for x, dy, sw, n, kp in zip((x_p, x_s), (dy_p, dy_s), streams, (Sp, Ss), keep):
+        for x, dy, sw, n, kp, ad in zip((x_p, x_s), (dy_p, dy_s), streams, (Sp, Ss), keep, ada):
             if kp is None:                      # no post-attention half: nothing flows into this stream's attn rows
                 dx1s.append(None)
                 off += n
                 continue
             dy = dy.contiguous() if dy._base is None and dy.is_contiguous() else dy.clone(memory_format=torch.contiguous_format)
             h2, _ = norm_fwd(kp["x1"], sw.norm2)
-            dhm = linear_dgrad(dy, sw.down)
+            w_ = x.shape[1]
+            if ad is not None:                  # y = x1 + y_m * g2
+                n2 = h2
+                h2 = ada_apply(n2, ad[1], B)
+                dgate2 = (dy.view(B, -1, w_).float() * kp["y_m"].view(B, -1, w_).float()).sum(dim=1)
+                dym = (dy.view(B, -1, w_) * ad[1][:, None, 2 * w_:]).view(-1, w_).contiguous()
+            else:
+                dym = dy
+            dhm = linear_dgrad(dym, sw.down)
             dg, du = ops.glu_bwd(dhm, kp["g"], kp["u"], env.act, dg=kp["g"], du=kp["u"], h_out=dhm)
-            linear_wgrad(store, dy, dhm, sw.down)
+            linear_wgrad(store, dym, dhm, sw.down)
             linear_wgrad(store, dg, h2, sw.gate)
             linear_wgrad(store, du, h2, sw.up)
             dh2 = linear_dgrad(dg, sw.gate)
             linear_dgrad(du, sw.up, out=dh2, residual=dh2)
+            if ad is not None:
+                dh2, dsc2, dsh2 = ada_bwd(dh2, n2, ad[1], B)
+                dmods[1] = torch.cat([dsc2, dsh2, dgate2], dim=-1).to(ad[1].dtype)
             dx1 = norm_bwd(store, dh2, kp["x1"], sw.norm2, kp["s2"], dx=dy, accumulate_dx=True)
-            linear_wgrad(store, dx1, kp["a"], sw.o)
-            da = linear_dgrad(dx1, sw.o)
+            if ad is not None:                  # x1 = x + y_o * g1
+                dgate1 = (dx1.view(B, -1, w_).float() * kp["y_o"].view(B, -1, w_).float()).sum(dim=1)
+                dyo = (dx1.view(B, -1, w_) * ad[0][:, None, 2 * w_:]).view(-1, w_).contiguous()
+            else:
+                dyo = dx1
+            linear_wgrad(store, dyo, kp["a"], sw.o)
+            da = linear_dgrad(dyo, sw.o)
             ops.copy3d_(da, dattn, B, n, C, n * C, C, S * C, C, dst_off=off * C)
-            dx1s.append(dx1)
+            dx1s.append((dx1, dgate1) if ad is not None else dx1)
             off += n
         dqkv = ops.attention_bwd(dattn, joint, probs, sh)
         ops.rope_(dqkv, env.pos, env.cos, env.sin, env.heads + env.kv_heads, env.head_dim, inverse=True)
         dxs = []
         off = 0
-        for x, sw, n, s1, dx1 in zip((x_p, x_s), streams, (Sp, Ss), st1, dx1s):
+        for x, sw, n, s1, dx1, ad in zip((x_p, x_s), streams, (Sp, Ss), st1, dx1s, ada):
             dq = torch.empty((B * n, W), device=x.device, dtype=x.dtype)
             ops.copy3d_(dqkv, dq, B, n, W, S * W, W, n * W, W, src_off=off * W)
             off += n
             h, _ = norm_fwd(x, sw.norm1)
+            if ad is not None:
+                n1 = h
+                h = ada_apply(n1, ad[0], B)
             linear_wgrad(store, dq, h, sw.qkv)
             dh = linear_dgrad(dq, sw.qkv)
+            if ad is not None:
+                dx1, dgate1 = dx1
+                dh, dsc1, dsh1 = ada_bwd(dh, n1, ad[0], B)
+                dmods[0] = torch.cat([dsc1, dsh1, dgate1], dim=-1).to(ad[0].dtype)
             if dx1 is None:
                 dxs.append(norm_bwd(store, dh, x, sw.norm1, s1))
             else:
                 dxs.append(norm_bwd(store, dh, x, sw.norm1, s1, dx=dx1, accumulate_dx=True))
-        return dxs[0], dxs[1], None, None, None, None
+        return dxs[0], dxs[1], None, None, None, None, dmods[0], dmods[1]
 
 
 class PrefixEmbedFn(torch.autograd.Function):
@@ -589,7 +659,7 @@ class Pi0ForCausalLM(B200Module):
         xp, xs = prefix, suffix
         for i, streams in enumerate(self.layers):
             last = i == len(self.layers) - 1
-            xp, xs = MoTLayerFn.apply(xp, xs, streams, env, st, (not last, True))
+            xp, xs = MoTLayerFn.apply(xp, xs, streams, env, st, (not last, True), None, None)
         suffix_out = NormFn.apply(xs, self.expert_norm, st)
         tail = suffix_out.view(B, Ss, self.w)[:, -T:].reshape(B * T, self.w).contiguous()
         v_t = LinearFn.apply(tail, self.action_out, None, st, True, None)                   # :386

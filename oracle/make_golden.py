@@ -466,6 +466,78 @@ def make_memvla_tiny(seed: int = 1357):
     print("[memvla_tiny] wrote fixture;", len(none_grad), "params without grad")
 
 
+def make_pi05_tiny(seed: int = 9753):
+    """pi0.5 training forward/backward and inference_action from the reference (pi05_arch.py)."""
+    llm, exp, vis = tiny_pi0_configs()
+    exp = dict(exp, use_adarms=True, adarms_cond_dim=exp["hidden_size"], width=exp["hidden_size"])
+    T, A = 10, 32
+    drop = ("rms_norm_eps", "hidden_act", "layer_norm_eps", "model_type")
+    model = ref_loader.build_reference_pi05({k: v for k, v in llm.items() if k not in drop},
+                                            {k: v for k, v in exp.items() if k not in drop},
+                                            {k: v for k, v in vis.items() if k not in ("rms_norm_eps", "rope_theta",
+                                                                                        "hidden_act", "layer_norm_eps")},
+                                            A, T)
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    g = torch.Generator().manual_seed(seed)
+    B, L = 3, 12
+    ids = torch.randint(1, 128, (B, L), generator=g)
+    mask = torch.ones(B, L, dtype=torch.bool)
+    mask[1, 8:] = False
+    mask[2, 5:] = False
+    images = torch.randn(B, 3, 3, 28, 28, generator=g)
+    image_masks = torch.ones(B, 3, dtype=torch.bool)
+    image_masks[1, 2] = False
+    actions = torch.randn(B, T, A, generator=g)
+    torch.manual_seed(seed + 1)
+    out = model(input_ids=ids, attention_mask=mask, images=images, image_masks=image_masks, actions=actions)
+    out.loss.backward()
+    torch.manual_seed(seed + 1)
+    noise = torch.normal(mean=torch.zeros_like(actions), std=torch.ones_like(actions))       # pi05_arch.py:352-358
+    time = torch.distributions.Beta(1.5, 1).sample((B,)) * 0.999 + 0.001
+    cfg = dict(llm=llm, expert=exp, vision=vis, chunk_size=T, action_dim=A)
+    ora = vla_oracle.pi05_forward(sd, cfg, ids, mask, images, image_masks, actions, noise, time)
+    d_loss = abs(ora["loss"].item() - out.loss.item())
+    d_v = (ora["v_t"] - out.logits).abs().max().item()
+    print(f"[pi05_tiny] reference loss {out.loss.item():.8f} oracle {ora['loss'].item():.8f}; v_t max|d|={d_v:.2e}")
+    assert d_loss < 1e-5 and d_v < 1e-4
+    names = ["model.llm.layers.0.self_attn.q_proj.weight", "model.llm.layers.1.self_attn.k_proj.weight",
+             "model.action_expert.layers.1.mlp.down_proj.weight", "model.action_expert.layers.0.self_attn.k_proj.weight",
+             "model.action_expert.layers.0.input_layernorm.dense.weight",
+             "model.action_expert.layers.1.post_attention_layernorm.dense.bias",
+             "model.action_expert.norm.dense.weight", "model.time_mlp_in.weight", "model.time_mlp_out.bias",
+             "model.action_in_proj.weight", "model.action_out_proj.bias", "model.mm_projector.weight",
+             "model.llm.embed_tokens.weight",
+             "model.mm_vision_tower.vision_tower.vision_model.encoder.layers.0.mlp.fc1.weight"]
+    params = dict(model.named_parameters())
+    grads = {n: params[n].grad.clone() for n in names if params[n].grad is not None}
+    none_grad = sorted(n for n, p in params.items() if p.grad is None)
+    # inference
+    model.eval()
+    states = torch.randn(B, A, generator=g)
+    inf = {}
+    for steps in (10, 4):
+        torch.manual_seed(seed + 5)
+        with torch.no_grad():
+            ref = model.inference_action(input_ids=ids, attention_mask=mask, states=states, images=images,
+                                         image_masks=image_masks, diffusion_steps=steps)
+        torch.manual_seed(seed + 5)
+        n0 = torch.normal(0, 1, size=(B, T, A))
+        got = vla_oracle.pi05_inference(sd, cfg, ids, mask, images, image_masks, n0, steps)
+        d = (got - ref).abs().max().item()
+        print(f"[pi05_inference] steps={steps}: oracle vs reference max|d|={d:.2e}")
+        assert d < 1e-4
+        inf[steps] = dict(noise=n0, actions=ref.detach())
+    torch.save(dict(seed=seed, cfg=cfg, shapes={k: tuple(v.shape) for k, v in sd.items()},
+                    inputs=dict(input_ids=ids, attention_mask=mask, images=images, image_masks=image_masks,
+                                actions=actions, noise=noise, time=time, states=states),
+                    outputs=dict(loss=out.loss.detach(), v_t=out.logits.detach(), grads=grads, none_grad=none_grad,
+                                 inference=inf)),
+               GOLDEN / "pi05_tiny.pt")
+    print("[pi05_tiny] wrote fixture; params without grad:", len(none_grad), [n for n in names if n not in grads])
+
+
 def make_cogact_inference_tiny(seed: int = 1234):
     """CogACT inference_action (CFG 1.5, 10-step DDIM, eta=0) from the reference (cogact_arch.py:149-198)."""
     llm, clip, cfg = tiny_cogact_configs()
@@ -501,6 +573,7 @@ if __name__ == "__main__":
     make_cogact_inference_tiny()
     make_pi0_tiny()
     make_pi0_inference_tiny()
+    make_pi05_tiny()
     make_memvla_tiny()
     make_oft_discrete_tiny()
     make_oft_linear_tiny()

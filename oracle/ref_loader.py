@@ -282,3 +282,53 @@ def build_reference_pi0(llm_config: dict, action_config: dict, vision_config: di
         if hasattr(m.embed_tokens, "embed_scale"):
             m.embed_tokens.embed_scale.fill_(1.0)
     return model
+
+
+_pi05_loaded = False
+
+
+def load_reference_pi05():
+    """pi05_arch.py + its vendored AdaRMS Gemma (pi05/transformers_pi05/gemma/modeling_gemma.py).  That file imports
+    five names from `transformers.models.gemma.modeling_gemma` which the pinned transformers 4.5x re-exported there and
+    5.5.0 keeps in their home modules; they are only referenced by code paths pi05 never calls (AdaRMSGemmaModel.forward,
+    the *ForCausalLM heads).  Alias them in memory so the import succeeds — no reference code is changed."""
+    global _pi05_loaded
+    load_reference_pi0()
+    if _pi05_loaded:
+        return sys.modules["dexbotic.model.pi05.pi05_arch"]
+    from typing import TypedDict
+    import transformers.models.gemma.modeling_gemma as mg
+    from transformers.cache_utils import StaticCache
+    from transformers.modeling_attn_mask_utils import AttentionMaskConverter
+    from transformers.modeling_outputs import SequenceClassifierOutputWithPast, TokenClassifierOutput
+
+    class KwargsForCausalLM(TypedDict, total=False):
+        pass
+
+    for name, obj in dict(AttentionMaskConverter=AttentionMaskConverter, StaticCache=StaticCache,
+                          SequenceClassifierOutputWithPast=SequenceClassifierOutputWithPast,
+                          TokenClassifierOutput=TokenClassifierOutput, KwargsForCausalLM=KwargsForCausalLM).items():
+        if not hasattr(mg, name):
+            setattr(mg, name, obj)
+    import dexbotic.model.pi05  # noqa: F401   (registers the adarms_gemma config / model with the Auto classes)
+    mod = _exec_patched("dexbotic.model.pi05.pi05_arch", "dexbotic/model/pi05/pi05_arch.py",
+                        [("    vision_config: dict | str\n", "    vision_config: dict | str = None\n"),
+                         ("    processor_config: str\n", "    processor_config: str = None\n"),
+                         ("    action_config: dict | str\n", "    action_config: dict | str = None\n")])
+    _pi05_loaded = True
+    return mod
+
+
+def build_reference_pi05(llm_config: dict, action_config: dict, vision_config: dict, action_dim: int = 32,
+                         chunk_size: int = 50):
+    """Reference Pi05ForCausalLM (pi05_arch.py:110-116), random init.  llm / action configs are `adarms_gemma` dicts;
+    `rope_parameters` is added because transformers 5.5's GemmaRotaryEmbedding reads it from the config object
+    (the 4.5x one read rope_theta) — a constructor-compat field, same RoPE."""
+    mod = load_reference_pi05()
+    rp = dict(rope_type="default", rope_theta=float(llm_config.get("rope_theta", 10000.0)))
+    llm_config = dict(llm_config, model_type="adarms_gemma", rope_parameters=rp)
+    action_config = dict(action_config, model_type="adarms_gemma", rope_parameters=rp)
+    cfg = mod.Pi05Config(llm_config=llm_config, action_config=action_config, vision_config=vision_config,
+                         processor_config="unused", mm_projector_type="linear", action_dim=action_dim,
+                         chunk_size=chunk_size)
+    return mod.Pi05ForCausalLM(cfg)

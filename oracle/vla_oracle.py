@@ -758,6 +758,109 @@ def pi0_velocity(sd, cfg: dict, input_ids, attention_mask, images, image_masks, 
 
 
 # ----------------------------------------------------------------------------------------------
+# pi0.5 — dexbotic/model/pi05/pi05_arch.py + pi05/transformers_pi05/gemma/modeling_gemma.py:38-119 (AdaRMS)
+# ----------------------------------------------------------------------------------------------
+def ada_rms_norm(x, sd, p: str, eps: float, cond=None):
+    """GemmaRMSNorm.forward (modeling_gemma.py:38-88): plain `(1 + weight)` RMSNorm when the module has no `dense`
+    (or no cond), else scale/shift/gate = chunk(dense(cond), 3): normed * (1 + scale) + shift, and the gate for the
+    gated residual.  Returns (y, gate or None)."""
+    n = x * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + eps)
+    if cond is None or (p + "dense.weight") not in sd:
+        return n * (1.0 + sd[p + "weight"].float()), None
+    mod = F.linear(cond, sd[p + "dense.weight"], sd[p + "dense.bias"])[:, None, :]
+    scale, shift, gate = torch.chunk(mod, 3, dim=-1)
+    return n * (1 + scale.float()) + shift.float(), gate
+
+
+def pi05_velocity(sd, cfg: dict, input_ids, attention_mask, images, image_masks, x_t, time):
+    """embed_prefix + embed_suffix + _inner_forward_mot + action_out_proj (pi05_arch.py:117-420).  Differences from
+    pi0: no state token; time enters only through adarms_cond = silu(time_mlp_out(silu(time_mlp_in(posemb(t)))))
+    (:303-315), which modulates every norm of the action expert and gates its residuals (:146-152,217-228)."""
+    L, E, V = cfg["llm"], cfg["expert"], cfg["vision"]
+    T = cfg["chunk_size"]
+    B = x_t.shape[0]
+    toks, masks = [], []
+    for c in range(images.shape[1]):
+        f = siglip_vision_features(sd, "model.mm_vision_tower.", images[:, c], V)
+        toks.append(F.linear(f, sd["model.mm_projector.weight"], sd["model.mm_projector.bias"]))
+        masks.append(image_masks[:, c][:, None].expand(B, f.shape[1]))
+    toks.append(sd["model.llm.embed_tokens.weight"][input_ids] * L["hidden_size"] ** 0.5)
+    masks.append(attention_mask.bool())
+    prefix, prefix_mask = torch.cat(toks, dim=1), torch.cat(masks, dim=1)
+    w = E["hidden_size"]
+    temb = posemb_sincos(time, w, 4e-3, 4.0).to(x_t.dtype)
+    cond = F.silu(F.linear(F.silu(F.linear(temb, sd["model.time_mlp_in.weight"], sd["model.time_mlp_in.bias"])),
+                           sd["model.time_mlp_out.weight"], sd["model.time_mlp_out.bias"]))
+    suffix = F.linear(x_t, sd["model.action_in_proj.weight"], sd["model.action_in_proj.bias"])
+    Sp, Ss = prefix.shape[1], suffix.shape[1]
+    input_mask = torch.cat([prefix_mask, torch.ones(B, Ss, dtype=torch.bool)], dim=1)
+    ar = torch.tensor([False] * Sp + [True] + [False] * (T - 1))
+    allow = pi0_make_attn_mask(input_mask, ar)[:, None]
+    positions = torch.cumsum(input_mask.long(), dim=1) - 1
+    H, KVH, hd = L["num_attention_heads"], L["num_key_value_heads"], L["head_dim"]
+    cos, sin = rope_tables(positions, hd, L.get("rope_theta", 10000.0))
+    c, s = cos[:, None], sin[:, None]
+    xs, prefixes, cfgs, conds = [prefix, suffix], ["model.llm.", "model.action_expert."], [L, E], [None, cond]
+    for li in range(L["num_hidden_layers"]):
+        qs, ks, vs, gates = [], [], [], []
+        for x, pf, cc, cd in zip(xs, prefixes, cfgs, conds):
+            q = f"{pf}layers.{li}."
+            h, g = ada_rms_norm(x, sd, q + "input_layernorm.", cc["rms_norm_eps"], cd)
+            n = h.shape[1]
+            gates.append(g)
+            qs.append(F.linear(h, sd[q + "self_attn.q_proj.weight"]).view(B, n, H, hd).transpose(1, 2))
+            ks.append(F.linear(h, sd[q + "self_attn.k_proj.weight"]).view(B, n, KVH, hd).transpose(1, 2))
+            vs.append(F.linear(h, sd[q + "self_attn.v_proj.weight"]).view(B, n, KVH, hd).transpose(1, 2))
+        qh, kh, vh = torch.cat(qs, dim=2), torch.cat(ks, dim=2), torch.cat(vs, dim=2)
+        qh = qh * c + rotate_half(qh) * s
+        kh = kh * c + rotate_half(kh) * s
+        G = H // KVH
+        sc = (qh @ kh.repeat_interleave(G, dim=1).transpose(-1, -2)) * hd ** -0.5
+        sc = sc + torch.where(allow, 0.0, -2.3819763e38)
+        p = torch.softmax(sc.float(), dim=-1)
+        o = (p @ vh.repeat_interleave(G, dim=1)).transpose(1, 2).reshape(B, Sp + Ss, H * hd)
+        outs, start = [], 0
+        for x, pf, cc, cd, g1 in zip(xs, prefixes, cfgs, conds, gates):
+            q = f"{pf}layers.{li}."
+            n = x.shape[1]
+            a = F.linear(o[:, start:start + n], sd[q + "self_attn.o_proj.weight"])
+            start += n
+            r = x + a if g1 is None else x + a * g1
+            h, g2 = ada_rms_norm(r, sd, q + "post_attention_layernorm.", cc["rms_norm_eps"], cd)
+            act = ACT[cc.get("hidden_act", "gelu_pytorch_tanh")]
+            m = F.linear(act(F.linear(h, sd[q + "mlp.gate_proj.weight"])) * F.linear(h, sd[q + "mlp.up_proj.weight"]),
+                         sd[q + "mlp.down_proj.weight"])
+            outs.append(r + m if g2 is None else r + m * g2)
+        xs = outs
+    suffix_out, _ = ada_rms_norm(xs[1], sd, "model.action_expert.norm.", E["rms_norm_eps"], cond)
+    v_t = F.linear(suffix_out[:, -T:], sd["model.action_out_proj.weight"], sd["model.action_out_proj.bias"])
+    return dict(v_t=v_t, suffix_out=suffix_out, prefix_tokens=prefix, input_mask=input_mask, adarms_cond=cond)
+
+
+def pi05_forward(sd, cfg: dict, input_ids, attention_mask, images, image_masks, actions, noise, time):
+    """Pi05ForCausalLM.forward (pi05_arch.py:333-420) with injected noise / time."""
+    te = time[:, None, None]
+    x_t = te * noise + (1 - te) * actions
+    u_t = noise - actions
+    out = pi05_velocity(sd, cfg, input_ids, attention_mask, images, image_masks, x_t, time)
+    out["u_t"] = u_t
+    out["loss"] = ((out["v_t"] - u_t) ** 2).mean()
+    return out
+
+
+def pi05_inference(sd, cfg: dict, input_ids, attention_mask, images, image_masks, noise, diffusion_steps: int = 10):
+    """Pi05ForCausalLM.inference_action (pi05_arch.py:424-514), cache-free restatement (see pi0_inference)."""
+    B = noise.shape[0]
+    dt = -1.0 / diffusion_steps
+    x, time = noise, torch.tensor(1.0)
+    while time > -dt / 2:
+        v = pi05_velocity(sd, cfg, input_ids, attention_mask, images, image_masks, x, time.broadcast_to(B))["v_t"]
+        x = x + v * dt
+        time = time + dt
+    return x
+
+
+# ----------------------------------------------------------------------------------------------
 # CogACT inference — cogact_arch.py:149-198, diffusion.py:626-673 (ddim_sample), :990-1112 (respacing)
 # ----------------------------------------------------------------------------------------------
 def ddim_tables(num_steps: int = 100, ddim_steps: int = 10):

@@ -128,6 +128,20 @@ def test_memvla_tiny_matches_reference():
     assert [len(v) for v in out["banks"]["cog"].banks.values()] == [2, 2]
 
 
+def test_pi05_tiny_matches_reference():
+    fx = torch.load(GOLDEN / "pi05_tiny.pt", weights_only=False)
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    i, ref = fx["inputs"], fx["outputs"]
+    out = vla_oracle.pi05_forward(sd, fx["cfg"], i["input_ids"], i["attention_mask"], i["images"], i["image_masks"],
+                                  i["actions"], i["noise"], i["time"])
+    assert abs(out["loss"].item() - ref["loss"].item()) < 1e-5
+    assert (out["v_t"] - ref["v_t"]).abs().max().item() < 1e-4
+    for steps, r in ref["inference"].items():
+        got = vla_oracle.pi05_inference(sd, fx["cfg"], i["input_ids"], i["attention_mask"], i["images"],
+                                        i["image_masks"], r["noise"], steps)
+        assert (got - r["actions"]).abs().max().item() < 1e-4
+
+
 def test_pi0_attn_mask_truth_table():
     """make_attn_mask (pi0_arch.py:22-33): prefix bidirectional, state token sees prefix + itself, action tokens see
     prefix + state + each other; invalid positions neither attend nor are attended."""
