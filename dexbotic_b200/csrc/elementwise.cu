@@ -366,7 +366,41 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x
     Pack8<T>::store(dx + i * 8, d);
   }
 }
-template <typename T>
+// act(x) and act'(x) together.  kAct = 4 (SiLU) / 2 (tanh-GELU) are the bf16 fast paths: one MUFU.EX2 + one MUFU.RCP
+// (or one MUFU.TANH) per element instead of two exponentials and IEEE divisions — at 8 elements per 16-byte pack the
+// generic path is MUFU-bound, not HBM-bound.  Their error (2 ulp fp32) vanishes in the bf16 rounding of the outputs.
+// kAct = -1: the exact runtime-dispatched functions (fp32 tensors, other activations).
+template <int kAct>
+__device__ __forceinline__ void act_pair(float x, int act, float& f, float& df) {
+  if constexpr (kAct == 4) {
+    const float s = __fdividef(1.0f, 1.0f + __expf(-x));
+    f = x * s;
+    df = s + f * (1.0f - s);
+  } else if constexpr (kAct == 2) {
+    const float x2 = x * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.7978845608028654f * (x + 0.044715f * x * x2)));
+    f = 0.5f * x * (1.0f + t);
+    df = 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * 0.7978845608028654f * (1.0f + 0.134145f * x2);
+  } else {
+    f = act_fwd(x, act);
+    df = act_grad(x, act);
+  }
+}
+template <int kAct>
+__device__ __forceinline__ float act_only(float x, int act) {
+  if constexpr (kAct == 4) {
+    return x * __fdividef(1.0f, 1.0f + __expf(-x));
+  } else if constexpr (kAct == 2) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+    return 0.5f * x * (1.0f + t);
+  } else {
+    return act_fwd(x, act);
+  }
+}
+
+template <typename T, int kAct>
 __global__ void glu_fwd_kernel(const T* __restrict__ g, const T* __restrict__ u, T* __restrict__ h, int64_t n8,
                                int act) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -379,8 +413,8 @@ __global__ void glu_fwd_kernel(const T* __restrict__ g, const T* __restrict__ u,
     Pack8<T>::load(u + (i + stride) * 8, b1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      a0[j] = act_fwd(a0[j], act) * b0[j];
-      a1[j] = act_fwd(a1[j], act) * b1[j];
+      a0[j] = act_only<kAct>(a0[j], act) * b0[j];
+      a1[j] = act_only<kAct>(a1[j], act) * b1[j];
     }
     Pack8<T>::store(h + i * 8, a0);
     Pack8<T>::store(h + (i + stride) * 8, a1);
@@ -390,12 +424,12 @@ __global__ void glu_fwd_kernel(const T* __restrict__ g, const T* __restrict__ u,
     Pack8<T>::load(g + i * 8, a);
     Pack8<T>::load(u + i * 8, b);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = act_fwd(a[j], act) * b[j];
+    for (int j = 0; j < 8; ++j) a[j] = act_only<kAct>(a[j], act) * b[j];
     Pack8<T>::store(h + i * 8, a);
   }
 }
 // dg = dh*u*act'(g), du = dh*act(g); dg/du may alias g/u; optional h_out = act(g)*u
-template <typename T>
+template <typename T, int kAct>
 __global__ void glu_bwd_kernel(const T* dh, const T* g, const T* u, T* dg, T* du, T* h_out,
                                int64_t n8, int act) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
@@ -405,8 +439,9 @@ __global__ void glu_bwd_kernel(const T* dh, const T* g, const T* u, T* dg, T* du
     Pack8<T>::load(dh + i * 8, d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float f = act_fwd(a[j], act);
-      og[j] = d[j] * b[j] * act_grad(a[j], act);
+      float f, df;
+      act_pair<kAct>(a[j], act, f, df);
+      og[j] = d[j] * b[j] * df;
       ou[j] = d[j] * f;
       oh[j] = f * b[j];
     }
@@ -830,8 +865,13 @@ int b200_act_bwd(const void* dy, const void* x, void* dx, int64_t n, int act, in
 int b200_glu_fwd(const void* g, const void* u, void* h, int64_t n, int act, int dtype, void* stream) {
   B200_CHECK(n % 8 == 0, "glu_fwd: n must be a multiple of 8");
   if (n == 0) return 0;
-  DISPATCH_T(dtype, (glu_fwd_kernel<T><<<grid_1d(n / 8, 256), 256, 0, STREAM>>>((const T*)g, (const T*)u, (T*)h,
-                                                                                n / 8, act)));
+  const int g1 = grid_1d(n / 8, 256);
+  if (dtype == B200_BF16 && act == B200_ACT_SILU)
+    glu_fwd_kernel<bf16, 4><<<g1, 256, 0, STREAM>>>((const bf16*)g, (const bf16*)u, (bf16*)h, n / 8, act);
+  else if (dtype == B200_BF16 && act == B200_ACT_GELU_TANH)
+    glu_fwd_kernel<bf16, 2><<<g1, 256, 0, STREAM>>>((const bf16*)g, (const bf16*)u, (bf16*)h, n / 8, act);
+  else
+    DISPATCH_T(dtype, (glu_fwd_kernel<T, -1><<<g1, 256, 0, STREAM>>>((const T*)g, (const T*)u, (T*)h, n / 8, act)));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -839,8 +879,16 @@ int b200_glu_bwd(const void* dh, const void* g, const void* u, void* dg, void* d
                  int dtype, void* stream) {
   B200_CHECK(n % 8 == 0, "glu_bwd: n must be a multiple of 8");
   if (n == 0) return 0;
-  DISPATCH_T(dtype, (glu_bwd_kernel<T><<<grid_1d(n / 8, 256), 256, 0, STREAM>>>(
-                        (const T*)dh, (const T*)g, (const T*)u, (T*)dg, (T*)du, (T*)h_out, n / 8, act)));
+  const int g1 = grid_1d(n / 8, 256);
+  if (dtype == B200_BF16 && act == B200_ACT_SILU)
+    glu_bwd_kernel<bf16, 4><<<g1, 256, 0, STREAM>>>((const bf16*)dh, (const bf16*)g, (const bf16*)u, (bf16*)dg, (bf16*)du,
+                                                    (bf16*)h_out, n / 8, act);
+  else if (dtype == B200_BF16 && act == B200_ACT_GELU_TANH)
+    glu_bwd_kernel<bf16, 2><<<g1, 256, 0, STREAM>>>((const bf16*)dh, (const bf16*)g, (const bf16*)u, (bf16*)dg, (bf16*)du,
+                                                    (bf16*)h_out, n / 8, act);
+  else
+    DISPATCH_T(dtype, (glu_bwd_kernel<T, -1><<<g1, 256, 0, STREAM>>>((const T*)dh, (const T*)g, (const T*)u, (T*)dg,
+                                                                     (T*)du, (T*)h_out, n / 8, act)));
   B200_LAUNCH_OK();
   return 0;
 }
