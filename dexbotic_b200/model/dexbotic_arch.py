@@ -312,8 +312,7 @@ class Decoder:
             q = f"{prefix}layers.{i}."
             bw.grad_range = store.grad_range([n for n in store.order if n.startswith(q)])
         self.final_norm = Norm(kind, eps, store.w(prefix + "norm.weight"), None, store.g(prefix + "norm.weight"))
-        if all(bw.grad_range is not None for bw in self.blocks):
-            store.set_param_chunks([bw.grad_range for bw in self.blocks])
+        store.set_param_chunks([bw.grad_range for bw in self.blocks])
         self.theta = rope_theta_of(cfg)
         self._rope_cache = None
         # layers [0, keep_layers) keep their intermediates (no recompute in backward); the rest recompute.
@@ -359,6 +358,8 @@ def kept_bytes_per_block(bc: BlockCfg, B: int, S: int, es: int = 2) -> int:
 def plan_keep_layers(store: ParamStore, bc: BlockCfg, n_layers: int, B: int, S: int, device, reserve_gb: float = 14.0) -> int:
     """How many blocks can keep their intermediates instead of being recomputed, from the HBM that is free
     right now (minus Adam moments still to be allocated, backward transients and a fragmentation reserve)."""
+    if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        reserve_gb += 6.0        # NCCL channel / NVLS buffers grow with the number of peers and are allocated lazily
     free, _ = torch.cuda.mem_get_info(device)
     cached = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
     moments = 0 if store.exp_avg is not None else 8 * store.n_train

@@ -120,6 +120,8 @@ class Pi05ForCausalLM(B200Module):
             self.mods.append((Lin.of(store, q + "input_layernorm.dense.weight", q + "input_layernorm.dense.bias"),
                               Lin.of(store, q + "post_attention_layernorm.dense.weight",
                                      q + "post_attention_layernorm.dense.bias")))
+        store.set_param_chunks([store.grad_range([n for n in store.order if n.startswith(f"model.{m}.layers.{i}.")])
+                                for i in range(L) for m in ("llm", "action_expert")])
         self.final_mod = Lin.of(store, "model.action_expert.norm.dense.weight", "model.action_expert.norm.dense.bias")
         self.final_norm = plain()
         mk = lambda n: Lin.of(store, f"model.{n}.weight", f"model.{n}.bias")  # noqa: E731
@@ -218,6 +220,8 @@ class Pi05ForCausalLM(B200Module):
         xp, xs = prefix, suffix
         for i, streams in enumerate(self.layers):
             last = i == len(self.layers) - 1
+            st.wait_chunk(2 * i)
+            st.wait_chunk(2 * i + 1)
             m1, m2 = self._mods(cond, i)
             xp, xs = MoTLayerFn.apply(xp, xs, streams, env, st, (not last, True), m1, m2)
         fm = LinearFn.apply(cond, self.final_mod, None, st, True, None)
@@ -262,6 +266,7 @@ class Pi05ForCausalLM(B200Module):
         if not states.is_cuda:
             raise RuntimeError("dexbotic_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         from .pi0_arch import Pi0ForCausalLM
+        self.store.wait_all_params()
         cfg, dev = self.config, states.device
         B, T, A = states.shape[0], cfg.chunk_size, cfg.action_dim
         H, KVH, hd = self.H, self.KVH, self.hd

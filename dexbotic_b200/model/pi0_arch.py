@@ -468,6 +468,9 @@ class Pi0ForCausalLM(B200Module):
         assert L == cfg_get(exp, "num_hidden_layers")
         self.layers = [(_stream_w(store, llm, "model.llm.", i), _stream_w(store, exp, "model.action_expert.", i))
                        for i in range(L)]
+        # optimizer / forward overlap (ParamStore.async_optimizer): chunk 2i = LLM layer i, chunk 2i+1 = expert layer i
+        store.set_param_chunks([store.grad_range([n for n in store.order if n.startswith(f"model.{m}.layers.{i}.")])
+                                for i in range(L) for m in ("llm", "action_expert")])
         self.expert_norm = Norm("rms1p", cfg_get(exp, "rms_norm_eps", 1e-6), store.w("model.action_expert.norm.weight"),
                                 None, store.g("model.action_expert.norm.weight"))
         mk = lambda n: Lin.of(store, f"model.{n}.weight", f"model.{n}.bias")  # noqa: E731
@@ -549,6 +552,7 @@ class Pi0ForCausalLM(B200Module):
         if not states.is_cuda:
             raise RuntimeError("dexbotic_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         cfg, dev = self.config, states.device
+        self.store.wait_all_params()
         B, T, A = states.shape[0], cfg.chunk_size, cfg.action_dim
         H, KVH, hd = self.H, self.KVH, self.hd
         W, C, Wkv = (H + 2 * KVH) * hd, H * hd, 2 * KVH * hd
@@ -659,6 +663,8 @@ class Pi0ForCausalLM(B200Module):
         xp, xs = prefix, suffix
         for i, streams in enumerate(self.layers):
             last = i == len(self.layers) - 1
+            st.wait_chunk(2 * i)
+            st.wait_chunk(2 * i + 1)
             xp, xs = MoTLayerFn.apply(xp, xs, streams, env, st, (not last, True), None, None)
         suffix_out = NormFn.apply(xs, self.expert_norm, st)
         tail = suffix_out.view(B, Ss, self.w)[:, -T:].reshape(B * T, self.w).contiguous()

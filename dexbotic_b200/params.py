@@ -182,7 +182,7 @@ class ParamStore:
     def set_param_chunks(self, bounds: list) -> None:
         """Region-A element ranges (e.g. one per decoder block, BlockW.grad_range) whose AdamW update may still be in
         flight when the next forward starts; the consumer calls wait_chunk(i) right before reading chunk i."""
-        self._chunk_bounds = [tuple(b) for b in bounds if b is not None]
+        self._chunk_bounds = [None if b is None else tuple(b) for b in bounds]    # None: nothing trainable there
 
     def wait_chunk(self, i: int) -> None:
         ev = self._chunk_events.pop(i, None)
@@ -270,7 +270,7 @@ class ParamStore:
                        self.step_count, clip)
 
         segs = self.segments(lrs, weight_decay)
-        if not (self.async_optimizer and self._chunk_bounds):
+        if not (self.async_optimizer and any(b is not None for b in self._chunk_bounds)):
             self.wait_all_params()
             for seg in segs:
                 update(*seg)
@@ -283,11 +283,10 @@ class ParamStore:
             if region != "A":
                 rest.append((a, b, lr, wd, region))
                 continue
+            hits = sorted((max(a, c[0]), min(b, c[1]), i) for i, c in enumerate(self._chunk_bounds)
+                          if c is not None and max(a, c[0]) < min(b, c[1]))   # disjoint, listed in FORWARD order
             cur = a
-            for i, (ca, cb) in enumerate(self._chunk_bounds):
-                lo, hi = max(cur, ca), min(b, cb)
-                if lo >= hi:
-                    continue
+            for lo, hi, i in hits:
                 if cur < lo:
                     rest.append((cur, lo, lr, wd, region))
                 per_chunk[i].append((lo, hi, lr, wd, region))

@@ -108,3 +108,30 @@ def test_pi0_inference_cache_equals_joint_forward():
     want = noise - out.logits.float()
     rel, cos = _rel(one, want)
     assert rel < 1e-2 and cos > 0.9999, (rel, cos)
+
+
+def test_pi0_overlapped_optimizer_equals_synchronous():
+    """ParamStore.async_optimizer with the mixture-of-transformers layout: chunk 2i = LLM layer i, 2i+1 = expert layer i."""
+    fx = torch.load(GOLDEN / "pi0_tiny.pt", weights_only=False)
+    i = {k: v.cuda() for k, v in fx["inputs"].items()}
+    runs = []
+    for async_opt in (False, True):
+        model = _build(fx)
+        model.train()
+        model.store.async_optimizer = async_opt
+        assert len(model.store._chunk_bounds) == 2 * len(model.layers)
+        ls = []
+        for _ in range(4):
+            model.zero_grad()
+            out = model(input_ids=i["input_ids"], attention_mask=i["attention_mask"], images=i["images"],
+                        image_masks=i["image_masks"], actions=i["actions"], states=i["states"], noise=i["noise"],
+                        time=i["time"])
+            out.loss.backward()
+            model.optimizer_step(base_lr=1e-3)
+            ls.append(out.loss.item())
+        if async_opt:
+            assert model.store._chunk_events
+        model.state_dict()
+        assert not model.store._chunk_events
+        runs.append(ls)
+    assert max(abs(a - b) for a, b in zip(*runs)) < 5e-3 * abs(runs[0][0]), runs
