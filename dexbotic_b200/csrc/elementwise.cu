@@ -367,7 +367,7 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x
   }
 }
 // act(x) and act'(x) together.  kAct = 4 (SiLU) / 2 (tanh-GELU) are the bf16 fast paths: one MUFU.EX2 + one MUFU.RCP
-// (or one MUFU.TANH) per element instead of two exponentials and IEEE divisions — at 8 elements per 16-byte pack the
+// per element instead of two exponentials and IEEE divisions — at 8 elements per 16-byte pack the
 // generic path is MUFU-bound, not HBM-bound.  Their error (2 ulp fp32) vanishes in the bf16 rounding of the outputs.
 // kAct = -1: the exact runtime-dispatched functions (fp32 tensors, other activations).
 template <int kAct>
@@ -378,8 +378,8 @@ __device__ __forceinline__ void act_pair(float x, int act, float& f, float& df) 
     df = s + f * (1.0f - s);
   } else if constexpr (kAct == 2) {
     const float x2 = x * x;
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.7978845608028654f * (x + 0.044715f * x * x2)));
+    // tanh(u) = 1 - 2 / (1 + e^{2u}): one ex2 + one rcp, ~2 ulp (tanh.approx.f32 would be 2^-11)
+    const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * 0.7978845608028654f * (x + 0.044715f * x * x2)));
     f = 0.5f * x * (1.0f + t);
     df = 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * 0.7978845608028654f * (1.0f + 0.134145f * x2);
   } else {
@@ -392,8 +392,7 @@ __device__ __forceinline__ float act_only(float x, int act) {
   if constexpr (kAct == 4) {
     return x * __fdividef(1.0f, 1.0f + __expf(-x));
   } else if constexpr (kAct == 2) {
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+    const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * 0.7978845608028654f * (x + 0.044715f * x * x * x)));
     return 0.5f * x * (1.0f + t);
   } else {
     return act_fwd(x, act);
