@@ -310,7 +310,7 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
         return {k: (v.to(dev, non_blocking=True) if hasattr(v, "to") else v) for k, v in hb.items()}
 
     # data-parallel: gradient all-reduce only (north_star), in place on the flat buffers, overlapped with backward
-    overlap = GradientOverlap(model.store)
+    overlap = GradientOverlap(model.store, reserve_sms=int(os.environ.get("B200_DP_RESERVE_SMS", "0")))
     # the HBM-bound per-block AdamW of step t runs on a side stream under the tensor-bound forward of step t+1
     # (ParamStore.adamw_step); the timed region below waits for the LAST step's updates before it closes
     model.store.async_optimizer = True

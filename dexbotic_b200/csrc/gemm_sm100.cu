@@ -564,6 +564,11 @@ static int encode_mn_5d(CUtensorMap* m, int fp32, const void* ptr, uint64_t mn, 
   return 0;
 }
 
+// SMs the persistent GEMM may occupy (0 = all).  The data-parallel overlap lowers it while a collective's CTAs hold
+// some SMs: a persistent grid sized for ALL SMs would leave its last CTAs queued behind the collective and run their
+// statically assigned tiles as a second wave.
+static int g_sm_limit = 0;
+
 template <int kBlockN, int kCtas>
 static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
   using Cfg = GemmCfg<kBlockN, kCtas>;
@@ -573,7 +578,8 @@ static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
                                    Cfg::kSmemBytes));
     configured = true;
   }
-  int units = num_sms() / kCtas;                       // CTAs, or CTA pairs
+  const int sms = (g_sm_limit > 0 && g_sm_limit < num_sms()) ? g_sm_limit : num_sms();
+  int units = sms / kCtas;                             // CTAs, or CTA pairs
   if (kp.total_tiles < units) units = kp.total_tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(units * kCtas);
@@ -605,7 +611,12 @@ static bool use_cta_pairs() {
 
 using namespace b200;
 
-extern "C" int b200_gemm(const b200_gemm_args* a, void* stream_) {
+extern "C" int b200_set_gemm_sm_limit(int sms) {
+  g_sm_limit = sms < 0 ? 0 : sms;
+  return 0;
+}
+
+int b200_gemm(const b200_gemm_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B200_CHECK(a != nullptr, "b200_gemm: null args");
   B200_CHECK(a->m > 0 && a->n > 0 && a->k > 0, "b200_gemm: empty problem m=%lld n=%lld k=%lld", (long long)a->m,

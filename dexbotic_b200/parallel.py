@@ -46,16 +46,28 @@ class GradientOverlap:
     compute stream), so NVLink traffic hides behind the backward of the earlier layers.  `finish()` reduces what
     is left (embeddings, projector, tower front end, fp32 action head) and joins the streams."""
 
-    def __init__(self, store: ParamStore, group=None, bucket_bytes: int = 512 << 20):
+    def __init__(self, store: ParamStore, group=None, bucket_bytes: int = 512 << 20, reserve_sms: int = 0):
         self.store, self.group, self.bucket_bytes = store, group, bucket_bytes
         self.enabled = dist.is_initialized() and dist.get_world_size(group) > 1
+        # reserve_sms > 0: while collectives are in flight the persistent GEMM leaves that many SMs to NCCL (set
+        # NCCL_MAX_CTAS to the same number before init_process_group) instead of queueing CTAs behind its kernels
+        self.reserve_sms = reserve_sms
+        self._limited = False
         self.works = []
         self.done = []          # list of (start, end) already reduced this step (element offsets in grad_a)
         self.pending = None     # (start, end) accumulated but not launched yet
         if self.enabled:
             store.grad_ready_hook = self.on_ready
 
+    def _limit(self, on: bool) -> None:
+        if self.reserve_sms > 0 and on != self._limited:
+            from . import _lib
+            n = torch.cuda.get_device_properties(self.store.device).multi_processor_count
+            _lib.load().b200_set_gemm_sm_limit((n - self.reserve_sms) // 2 * 2 if on else 0)
+            self._limited = on
+
     def _launch(self, a: int, b: int) -> None:
+        self._limit(True)
         chunk = self.store.grad_a[a:b]
         self.works.append(dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
         self.done.append((a, b))
@@ -92,4 +104,5 @@ class GradientOverlap:
             self.works.append(dist.all_reduce(self.store.grad_b, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
         for w in self.works:
             w.wait()
+        self._limit(False)
         self.works, self.done = [], []

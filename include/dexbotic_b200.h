@@ -40,6 +40,10 @@ int b200_version(void);
 const char* b200_last_error(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t b200_launch_count(void);
+/* Number of SMs the persistent GEMM grid may occupy (0 = all of them).  Host-side knob for the data-parallel overlap
+ * (HF Trainer's DDP all-reduce during backward, trainer.py:110,121): while an NCCL collective holds R SMs, a grid
+ * sized for all SMs queues its last CTAs behind the collective. */
+int b200_set_gemm_sm_limit(int sms);
 
 /* ------------------------------------------------------------------ GEMM ----------
  * D[z] = epilogue( alpha * sum_seg A[zA(seg)] x B[zB(seg)] )      (tcgen05 / TMEM / TMA)
