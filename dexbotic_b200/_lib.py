@@ -50,7 +50,7 @@ class GemmArgs(C.Structure):
 
 _CTYPE = {
     "void": None, "int": C.c_int, "float": C.c_float, "int32_t": C.c_int32, "int64_t": C.c_int64,
-    "uint64_t": C.c_uint64,
+    "uint64_t": C.c_uint64, "double": C.c_double,
 }
 
 

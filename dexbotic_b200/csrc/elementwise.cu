@@ -654,9 +654,12 @@ __global__ void mse_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
 template <typename G>
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const G* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v,
-                                                    bf16* __restrict__ shadow, int64_t n, float lr, float b1, float b2,
-                                                    float eps, float wd, float bc1, float bc2,
-                                                    const float* __restrict__ clip) {
+                                                    bf16* __restrict__ shadow, int64_t n, float b2, float omb1,
+                                                    float omb2, float eps, float decay, float step_size,
+                                                    float bc2_sqrt, const float* __restrict__ clip) {
+  // torch.optim.AdamW arithmetic (torch/optim/adamw.py, single-tensor path) with its host scalars evaluated in
+  // double exactly as Python does and rounded to fp32 once: exp_avg.lerp_(g, 1-b1); exp_avg_sq.mul_(b2).addcmul_(g, g,
+  // value=1-b2); p.mul_(1 - lr*wd); denom = sqrt(exp_avg_sq) / sqrt(bc2) + eps; p.addcdiv_(exp_avg, denom, -lr/bc1)
   const float cs = clip != nullptr ? *clip : 1.0f;
   const int64_t n8 = n >> 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
@@ -668,10 +671,10 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float gg = gv[j] * cs;
-      mv[j] = b1 * mv[j] + (1.0f - b1) * gg;
-      vv[j] = b2 * vv[j] + (1.0f - b2) * gg * gg;
-      const float denom = sqrtf(vv[j] / bc2) + eps;
-      pv[j] = pv[j] * (1.0f - lr * wd) - lr * (mv[j] / bc1) / denom;
+      mv[j] = mv[j] + omb1 * (gg - mv[j]);
+      vv[j] = b2 * vv[j] + omb2 * gg * gg;
+      const float denom = sqrtf(vv[j]) / bc2_sqrt + eps;
+      pv[j] = pv[j] * decay - step_size * (mv[j] / denom);
     }
     Pack8<float>::store(p + i * 8, pv);
     Pack8<float>::store(m + i * 8, mv);
@@ -681,9 +684,9 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   if (blockIdx.x == 0) {
     for (int64_t i = (n8 << 3) + threadIdx.x; i < n; i += blockDim.x) {
       const float gg = to_f(g[i]) * cs;
-      const float mm = b1 * m[i] + (1.0f - b1) * gg;
-      const float vv = b2 * v[i] + (1.0f - b2) * gg * gg;
-      const float pp = p[i] * (1.0f - lr * wd) - lr * (mm / bc1) / (sqrtf(vv / bc2) + eps);
+      const float mm = m[i] + omb1 * (gg - m[i]);
+      const float vv = b2 * v[i] + omb2 * gg * gg;
+      const float pp = p[i] * decay - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
       m[i] = mm;
       v[i] = vv;
       p[i] = pp;
@@ -955,20 +958,21 @@ int b200_mse_bwd(const void* a, const void* b, int64_t n, const float* gscale, v
   return 0;
 }
 
-int b200_adamw(float* p, const void* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1,
-               float beta2, float eps, float weight_decay, int64_t step, const float* clip, int g_dtype,
+int b200_adamw(float* p, const void* g, float* m, float* v, void* shadow_bf16, int64_t n, double lr, double beta1,
+               double beta2, double eps, double weight_decay, int64_t step, const float* clip, int g_dtype,
                void* stream) {
   if (n == 0) return 0;
   B200_CHECK(step >= 1, "adamw: step must be >= 1");
-  const float bc1 = 1.0f - powf(beta1, (float)step);
-  const float bc2 = 1.0f - powf(beta2, (float)step);
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  const float b2 = (float)beta2, omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2), e = (float)eps;
+  const float decay = (float)(1.0 - lr * weight_decay), step_size = (float)(lr / bc1), bc2_sqrt = (float)sqrt(bc2);
   if (g_dtype == B200_F32)
-    adamw_kernel<float><<<grid_1d(n / 8 + 1, 256), 256, 0, STREAM>>>(p, (const float*)g, m, v, (bf16*)shadow_bf16, n,
-                                                                     lr, beta1, beta2, eps, weight_decay, bc1, bc2,
-                                                                     clip);
+    adamw_kernel<float><<<grid_1d(n / 8 + 1, 256), 256, 0, STREAM>>>(p, (const float*)g, m, v, (bf16*)shadow_bf16, n, b2,
+                                                                     omb1, omb2, e, decay, step_size, bc2_sqrt, clip);
   else
-    adamw_kernel<bf16><<<grid_1d(n / 8 + 1, 256), 256, 0, STREAM>>>(p, (const bf16*)g, m, v, (bf16*)shadow_bf16, n, lr,
-                                                                    beta1, beta2, eps, weight_decay, bc1, bc2, clip);
+    adamw_kernel<bf16><<<grid_1d(n / 8 + 1, 256), 256, 0, STREAM>>>(p, (const bf16*)g, m, v, (bf16*)shadow_bf16, n, b2,
+                                                                    omb1, omb2, e, decay, step_size, bc2_sqrt, clip);
   B200_LAUNCH_OK();
   return 0;
 }

@@ -88,9 +88,10 @@ int b200_mse_fwd(const void* a, const void* b, int64_t n, float* out, int dtype,
 int b200_mse_bwd(const void* a, const void* b, int64_t n, const float* gscale, void* da, int dtype, void* stream);
 
 /* torch.optim.AdamW step on a flat fp32 master buffer (trainer.py:25-36 create_optimizer); gradient
- * in g (g_dtype), optional bf16 shadow of the updated weights, device-side clip coefficient. */
-int b200_adamw(float* p, const void* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1,
-               float beta2, float eps, float weight_decay, int64_t step, const float* clip, int g_dtype, void* stream);
+ * in g (g_dtype), optional bf16 shadow of the updated weights, device-side clip coefficient.  Hyper-parameters are
+ * doubles: torch evaluates 1-beta, the bias corrections and lr/bc1 in Python doubles and rounds to fp32 once. */
+int b200_adamw(float* p, const void* g, float* m, float* v, void* shadow_bf16, int64_t n, double lr, double beta1,
+               double beta2, double eps, double weight_decay, int64_t step, const float* clip, int g_dtype, void* stream);
 
 int b200_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
 int b200_add(const void* a, const void* b, void* y, int64_t n, int dtype, void* stream);
