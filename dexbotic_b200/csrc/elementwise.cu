@@ -56,57 +56,55 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const T* __restrict__ 
 // dx = r*g - x*r^3*mean(g.x),  g = dy*w_eff ;  dw[col] += sum_rows dy * x * r.
 // x / dy are read once per row (kept in registers between the two phases).  dw partials go to a per-block row of
 // `ws` (no atomics; reduced by colsum afterwards) when a workspace is given, else fp32 atomics.
-template <typename T>
-__global__ void __launch_bounds__(256, 4) rmsnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
-                                                             const T* __restrict__ w, const float* __restrict__ rstd,
-                                                             T* dx, float* __restrict__ dw, float* __restrict__ ws,
-                                                             int M, int D, int unit_offset, int accumulate_dx) {
+template <typename T, int kPacks>
+__global__ void __launch_bounds__(256, kPacks <= 2 ? 3 : 2) rmsnorm_bwd_kernel(
+    const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ rstd, T* dx,
+    float* __restrict__ dw, float* __restrict__ ws, int M, int D, int unit_offset, int accumulate_dx) {
+  // kPacks = packs of 8 columns per thread (2 covers D <= 16 * blockDim: every decoder / tower width); the row's
+  // x / dy / dw-partials live in registers, the weight vector is re-read per row (7 KB, L1-resident) — with it in
+  // registers too the kernel spilled ~0.7 KB per thread.
   __shared__ float red[33];
-  float wacc[kMaxPacks][8], we[kMaxPacks][8];
+  const float uo = unit_offset ? 1.0f : 0.0f;
+  float wacc[kPacks][8];
 #pragma unroll
-  for (int k = 0; k < kMaxPacks; ++k) {
-    const int i = (threadIdx.x + k * blockDim.x) * 8;
+  for (int k = 0; k < kPacks; ++k) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) wacc[k][j] = 0.0f;
-    if (i < D) {
-      Pack8<T>::load(w + i, we[k]);
-      if (unit_offset) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) we[k][j] += 1.0f;
-      }
-    }
   }
   for (int row = blockIdx.x; row < M; row += gridDim.x) {
     const T* xr = x + (size_t)row * D;
     const T* dyr = dy + (size_t)row * D;
     T* dxr = dx + (size_t)row * D;
     const float r = rstd[row];
-    float xv[kMaxPacks][8], dv[kMaxPacks][8];
+    float xv[kPacks][8], gv[kPacks][8];      // gv = dy * w_eff
     float c = 0.0f;
 #pragma unroll
-    for (int k = 0; k < kMaxPacks; ++k) {
+    for (int k = 0; k < kPacks; ++k) {
       const int i = (threadIdx.x + k * blockDim.x) * 8;
       if (i < D) {
+        float we[8];
         Pack8<T>::load(xr + i, xv[k]);
-        Pack8<T>::load(dyr + i, dv[k]);
+        Pack8<T>::load(dyr + i, gv[k]);
+        Pack8<T>::load(w + i, we);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          c += dv[k][j] * we[k][j] * xv[k][j];
-          wacc[k][j] += dv[k][j] * xv[k][j] * r;
+          wacc[k][j] += gv[k][j] * xv[k][j] * r;
+          gv[k][j] *= we[j] + uo;
+          c += gv[k][j] * xv[k][j];
         }
       }
     }
     c = block_sum(c, red);
     const float coef = c * r * r * r / (float)D;
 #pragma unroll
-    for (int k = 0; k < kMaxPacks; ++k) {
+    for (int k = 0; k < kPacks; ++k) {
       const int i = (threadIdx.x + k * blockDim.x) * 8;
       if (i < D) {
         float o[8];
         if (accumulate_dx) Pack8<T>::load(dxr + i, o);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float t = r * dv[k][j] * we[k][j] - xv[k][j] * coef;
+          const float t = r * gv[k][j] - xv[k][j] * coef;
           o[j] = accumulate_dx ? o[j] + t : t;
         }
         Pack8<T>::store(dxr + i, o);
@@ -115,7 +113,7 @@ __global__ void __launch_bounds__(256, 4) rmsnorm_bwd_kernel(const T* __restrict
   }
   if (dw != nullptr) {
 #pragma unroll
-    for (int k = 0; k < kMaxPacks; ++k) {
+    for (int k = 0; k < kPacks; ++k) {
       const int i = (threadIdx.x + k * blockDim.x) * 8;
       if (i < D) {
         if (ws != nullptr) {
@@ -177,54 +175,49 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
-                                                               const T* __restrict__ w, const float* __restrict__ mean,
-                                                               const float* __restrict__ rstd, T* dx,
-                                                               float* __restrict__ dw, float* __restrict__ db,
-                                                               float* __restrict__ ws, int M, int D,
-                                                               int accumulate_dx) {
+template <typename T, int kPacks>
+__global__ void __launch_bounds__(256, kPacks <= 2 ? 2 : 1) layernorm_bwd_kernel(
+    const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ mean,
+    const float* __restrict__ rstd, T* dx, float* __restrict__ dw, float* __restrict__ db, float* __restrict__ ws, int M,
+    int D, int accumulate_dx) {
+  // same register budget as rmsnorm_bwd: x-hat / g / dw / db partials in registers, the weight re-read per row
   __shared__ float red[33];
-  float wacc[kMaxPacks][8], bacc[kMaxPacks][8], wv[kMaxPacks][8];
+  float wacc[kPacks][8], bacc[kPacks][8];
 #pragma unroll
-  for (int k = 0; k < kMaxPacks; ++k) {
-    const int i = (threadIdx.x + k * blockDim.x) * 8;
+  for (int k = 0; k < kPacks; ++k) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      wacc[k][j] = bacc[k][j] = 0.0f;
-      wv[k][j] = 1.0f;
-    }
-    if (w != nullptr && i < D) Pack8<T>::load(w + i, wv[k]);
+    for (int j = 0; j < 8; ++j) wacc[k][j] = bacc[k][j] = 0.0f;
   }
   for (int row = blockIdx.x; row < M; row += gridDim.x) {
     const T* xr = x + (size_t)row * D;
     const T* dyr = dy + (size_t)row * D;
     T* dxr = dx + (size_t)row * D;
     const float mu = mean[row], r = rstd[row];
-    float xh[kMaxPacks][8], gv[kMaxPacks][8];
+    float xh[kPacks][8], gv[kPacks][8];
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
-    for (int k = 0; k < kMaxPacks; ++k) {
+    for (int k = 0; k < kPacks; ++k) {
       const int i = (threadIdx.x + k * blockDim.x) * 8;
       if (i < D) {
-        float xv[8], dv[8];
+        float xv[8], wv[8];
         Pack8<T>::load(xr + i, xv);
-        Pack8<T>::load(dyr + i, dv);
+        Pack8<T>::load(dyr + i, gv[k]);
+        if (w != nullptr) Pack8<T>::load(w + i, wv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[k][j] = (xv[j] - mu) * r;
-          gv[k][j] = dv[j] * wv[k][j];
+          wacc[k][j] += gv[k][j] * xh[k][j];
+          bacc[k][j] += gv[k][j];
+          if (w != nullptr) gv[k][j] *= wv[j];
           s1 += gv[k][j];
           s2 += gv[k][j] * xh[k][j];
-          wacc[k][j] += dv[j] * xh[k][j];
-          bacc[k][j] += dv[j];
         }
       }
     }
     s1 = block_sum(s1, red) / (float)D;
     s2 = block_sum(s2, red) / (float)D;
 #pragma unroll
-    for (int k = 0; k < kMaxPacks; ++k) {
+    for (int k = 0; k < kPacks; ++k) {
       const int i = (threadIdx.x + k * blockDim.x) * 8;
       if (i < D) {
         float o[8];
@@ -239,7 +232,7 @@ __global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const T* __restri
     }
   }
 #pragma unroll
-  for (int k = 0; k < kMaxPacks; ++k) {
+  for (int k = 0; k < kPacks; ++k) {
     const int i = (threadIdx.x + k * blockDim.x) * 8;
     if (i < D) {
       if (ws != nullptr) {
@@ -749,6 +742,17 @@ using namespace b200;
     __VA_ARGS__;                                 \
   }
 
+// Persistent grid of the backward norm kernels: exactly the number of blocks that are resident at once (a grid sized
+// for more than fit would run a second, partial wave of the grid-stride loop).  The workspace has one row per block; the
+// bound below (16 blocks per SM) is what callers allocate.
+template <typename K>
+static int resident_grid(K kernel, int nt, int64_t rows) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (per_sm > 16) per_sm = 16;
+  return grid_for_rows(rows, per_sm);
+}
+
 extern "C" {
 
 int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t M, int64_t D, float eps,
@@ -762,10 +766,10 @@ int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t
   return 0;
 }
 
-// rows of fp32 workspace the backward norm kernels want (one per launched block); 0 -> atomics path
+// rows of fp32 workspace the backward norm kernels want (upper bound on the launched blocks); 0 -> atomics path
 int64_t b200_norm_bwd_workspace_rows(int64_t M, int64_t D) {
-  const int nt = norm_threads(D);
-  return grid_for_rows(M, 1024 / nt);
+  (void)D;
+  return grid_for_rows(M, 16);
 }
 
 int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw,
@@ -774,11 +778,19 @@ int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* 
   B200_CHECK(D % 8 == 0 && D <= 8 * 256 * kMaxPacks, "rmsnorm_bwd: unsupported D=%lld", (long long)D);
   if (M == 0) return 0;
   const int nt = norm_threads(D);
-  const int grid = grid_for_rows(M, 1024 / nt);
+  int grid;
   float* ws = dw != nullptr ? workspace : nullptr;
-  DISPATCH_T(dtype, (rmsnorm_bwd_kernel<T><<<grid, nt, 0, STREAM>>>(
-                        (const T*)dy, (const T*)x, (const T*)w, rstd, (T*)dx, dw, ws, (int)M, (int)D, unit_offset,
-                        accumulate_dx)));
+  if (D <= (int64_t)16 * nt) {
+    DISPATCH_T(dtype, grid = resident_grid(rmsnorm_bwd_kernel<T, 2>, nt, M));
+    DISPATCH_T(dtype, (rmsnorm_bwd_kernel<T, 2><<<grid, nt, 0, STREAM>>>(
+                          (const T*)dy, (const T*)x, (const T*)w, rstd, (T*)dx, dw, ws, (int)M, (int)D, unit_offset,
+                          accumulate_dx)));
+  } else {
+    DISPATCH_T(dtype, grid = resident_grid(rmsnorm_bwd_kernel<T, kMaxPacks>, nt, M));
+    DISPATCH_T(dtype, (rmsnorm_bwd_kernel<T, kMaxPacks><<<grid, nt, 0, STREAM>>>(
+                          (const T*)dy, (const T*)x, (const T*)w, rstd, (T*)dx, dw, ws, (int)M, (int)D, unit_offset,
+                          accumulate_dx)));
+  }
   B200_LAUNCH_OK();
   if (ws != nullptr) {   // dw[D] += column sums of the [grid, D] partials
     dim3 g2((unsigned)ceil_div(D / 8, 64), (unsigned)ceil_div(grid, 64));
@@ -793,7 +805,9 @@ int b200_layernorm_fwd(const void* x, const void* w, const void* b, void* y, flo
   B200_CHECK(D % 8 == 0, "layernorm_fwd: D=%lld must be a multiple of 8", (long long)D);
   if (M == 0) return 0;
   const int nt = norm_threads(D);
-  DISPATCH_T(dtype, (layernorm_fwd_kernel<T><<<grid_for_rows(M, 2048 / nt), nt, 0, STREAM>>>(
+  int grid;
+  DISPATCH_T(dtype, grid = resident_grid(layernorm_fwd_kernel<T>, nt, M));
+  DISPATCH_T(dtype, (layernorm_fwd_kernel<T><<<grid, nt, 0, STREAM>>>(
                         (const T*)x, (const T*)w, (const T*)b, (T*)y, mean, rstd, (int)M, (int)D, eps)));
   B200_LAUNCH_OK();
   return 0;
@@ -812,12 +826,20 @@ int b200_layernorm_bwd(const void* dy, const void* x, const void* w, const float
     return 0;
   }
   const int nt = norm_threads(D);
-  const int grid = grid_for_rows(M, 1024 / nt);
+  int grid;
   // workspace rows hold [dw partial | db partial]; it is only usable when both gradients are wanted
   float* ws = (dw != nullptr && db != nullptr) ? workspace : nullptr;
-  DISPATCH_T(dtype, (layernorm_bwd_kernel<T><<<grid, nt, 0, STREAM>>>(
-                        (const T*)dy, (const T*)x, (const T*)w, mean, rstd, (T*)dx, dw, db, ws, (int)M, (int)D,
-                        accumulate_dx)));
+  if (D <= (int64_t)16 * nt) {
+    DISPATCH_T(dtype, grid = resident_grid(layernorm_bwd_kernel<T, 2>, nt, M));
+    DISPATCH_T(dtype, (layernorm_bwd_kernel<T, 2><<<grid, nt, 0, STREAM>>>(
+                          (const T*)dy, (const T*)x, (const T*)w, mean, rstd, (T*)dx, dw, db, ws, (int)M, (int)D,
+                          accumulate_dx)));
+  } else {
+    DISPATCH_T(dtype, grid = resident_grid(layernorm_bwd_kernel<T, kMaxPacks>, nt, M));
+    DISPATCH_T(dtype, (layernorm_bwd_kernel<T, kMaxPacks><<<grid, nt, 0, STREAM>>>(
+                          (const T*)dy, (const T*)x, (const T*)w, mean, rstd, (T*)dx, dw, db, ws, (int)M, (int)D,
+                          accumulate_dx)));
+  }
   B200_LAUNCH_OK();
   if (ws != nullptr) {
     dim3 g2((unsigned)ceil_div(2 * D / 8, 64), (unsigned)ceil_div(grid, 64));
@@ -842,7 +864,9 @@ int b200_rope(void* qkv, const int32_t* pos, const float* cos_t, const float* si
   if (M == 0) return 0;
   int work = n_rot_heads * (head_dim / 16);
   int block = work < 32 ? 32 : (work > 512 ? 512 : ((work + 31) / 32) * 32);
-  DISPATCH_T(dtype, (rope_kernel<T><<<grid_for_rows(M), block, 0, STREAM>>>((T*)qkv, pos, cos_t, sin_t, (int)M,
+  int grid;
+  DISPATCH_T(dtype, grid = resident_grid(rope_kernel<T>, block, M));
+  DISPATCH_T(dtype, (rope_kernel<T><<<grid, block, 0, STREAM>>>((T*)qkv, pos, cos_t, sin_t, (int)M,
                                                                             n_rot_heads, head_dim, row_stride,
                                                                             inverse)));
   B200_LAUNCH_OK();
