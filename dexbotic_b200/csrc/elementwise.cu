@@ -745,6 +745,19 @@ using namespace b200;
 // Persistent grid of the backward norm kernels: exactly the number of blocks that are resident at once (a grid sized
 // for more than fit would run a second, partial wave of the grid-stride loop).  The workspace has one row per block; the
 // bound below (16 blocks per SM) is what callers allocate.
+// 1-D grid-stride launch sized to what is resident at once (blocks beyond that would start only after whole first-wave
+// blocks finish their strided share, leaving the SMs at partial occupancy for the tail).
+template <typename K>
+static int grid_fit(K kernel, int64_t work_items, int block) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  int64_t g = ceil_div(work_items, block);
+  const int64_t cap = (int64_t)num_sms() * per_sm;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
 template <typename K>
 static int resident_grid(K kernel, int nt, int64_t rows) {
   int per_sm = 0;
@@ -876,14 +889,14 @@ int b200_rope(void* qkv, const int32_t* pos, const float* cos_t, const float* si
 int b200_act_fwd(const void* x, void* y, int64_t n, int act, int dtype, void* stream) {
   B200_CHECK(n % 8 == 0, "act_fwd: n must be a multiple of 8");
   if (n == 0) return 0;
-  DISPATCH_T(dtype, (act_fwd_kernel<T><<<grid_1d(n / 8, 256), 256, 0, STREAM>>>((const T*)x, (T*)y, n / 8, act)));
+  DISPATCH_T(dtype, (act_fwd_kernel<T><<<grid_fit(act_fwd_kernel<T>, n / 8, 256), 256, 0, STREAM>>>((const T*)x, (T*)y, n / 8, act)));
   B200_LAUNCH_OK();
   return 0;
 }
 int b200_act_bwd(const void* dy, const void* x, void* dx, int64_t n, int act, int dtype, void* stream) {
   B200_CHECK(n % 8 == 0, "act_bwd: n must be a multiple of 8");
   if (n == 0) return 0;
-  DISPATCH_T(dtype, (act_bwd_kernel<T><<<grid_1d(n / 8, 256), 256, 0, STREAM>>>((const T*)dy, (const T*)x, (T*)dx,
+  DISPATCH_T(dtype, (act_bwd_kernel<T><<<grid_fit(act_bwd_kernel<T>, n / 8, 256), 256, 0, STREAM>>>((const T*)dy, (const T*)x, (T*)dx,
                                                                                 n / 8, act)));
   B200_LAUNCH_OK();
   return 0;
@@ -891,13 +904,15 @@ int b200_act_bwd(const void* dy, const void* x, void* dx, int64_t n, int act, in
 int b200_glu_fwd(const void* g, const void* u, void* h, int64_t n, int act, int dtype, void* stream) {
   B200_CHECK(n % 8 == 0, "glu_fwd: n must be a multiple of 8");
   if (n == 0) return 0;
-  const int g1 = grid_1d(n / 8, 256);
   if (dtype == B200_BF16 && act == B200_ACT_SILU)
-    glu_fwd_kernel<bf16, 4><<<g1, 256, 0, STREAM>>>((const bf16*)g, (const bf16*)u, (bf16*)h, n / 8, act);
+    glu_fwd_kernel<bf16, 4><<<grid_fit(glu_fwd_kernel<bf16, 4>, n / 8, 256), 256, 0, STREAM>>>(
+        (const bf16*)g, (const bf16*)u, (bf16*)h, n / 8, act);
   else if (dtype == B200_BF16 && act == B200_ACT_GELU_TANH)
-    glu_fwd_kernel<bf16, 2><<<g1, 256, 0, STREAM>>>((const bf16*)g, (const bf16*)u, (bf16*)h, n / 8, act);
+    glu_fwd_kernel<bf16, 2><<<grid_fit(glu_fwd_kernel<bf16, 2>, n / 8, 256), 256, 0, STREAM>>>(
+        (const bf16*)g, (const bf16*)u, (bf16*)h, n / 8, act);
   else
-    DISPATCH_T(dtype, (glu_fwd_kernel<T, -1><<<g1, 256, 0, STREAM>>>((const T*)g, (const T*)u, (T*)h, n / 8, act)));
+    DISPATCH_T(dtype, (glu_fwd_kernel<T, -1><<<grid_fit(glu_fwd_kernel<T, -1>, n / 8, 256), 256, 0, STREAM>>>(
+                          (const T*)g, (const T*)u, (T*)h, n / 8, act)));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -905,16 +920,15 @@ int b200_glu_bwd(const void* dh, const void* g, const void* u, void* dg, void* d
                  int dtype, void* stream) {
   B200_CHECK(n % 8 == 0, "glu_bwd: n must be a multiple of 8");
   if (n == 0) return 0;
-  const int g1 = grid_1d(n / 8, 256);
   if (dtype == B200_BF16 && act == B200_ACT_SILU)
-    glu_bwd_kernel<bf16, 4><<<g1, 256, 0, STREAM>>>((const bf16*)dh, (const bf16*)g, (const bf16*)u, (bf16*)dg, (bf16*)du,
-                                                    (bf16*)h_out, n / 8, act);
+    glu_bwd_kernel<bf16, 4><<<grid_fit(glu_bwd_kernel<bf16, 4>, n / 8, 256), 256, 0, STREAM>>>(
+        (const bf16*)dh, (const bf16*)g, (const bf16*)u, (bf16*)dg, (bf16*)du, (bf16*)h_out, n / 8, act);
   else if (dtype == B200_BF16 && act == B200_ACT_GELU_TANH)
-    glu_bwd_kernel<bf16, 2><<<g1, 256, 0, STREAM>>>((const bf16*)dh, (const bf16*)g, (const bf16*)u, (bf16*)dg, (bf16*)du,
-                                                    (bf16*)h_out, n / 8, act);
+    glu_bwd_kernel<bf16, 2><<<grid_fit(glu_bwd_kernel<bf16, 2>, n / 8, 256), 256, 0, STREAM>>>(
+        (const bf16*)dh, (const bf16*)g, (const bf16*)u, (bf16*)dg, (bf16*)du, (bf16*)h_out, n / 8, act);
   else
-    DISPATCH_T(dtype, (glu_bwd_kernel<T, -1><<<g1, 256, 0, STREAM>>>((const T*)dh, (const T*)g, (const T*)u, (T*)dg,
-                                                                     (T*)du, (T*)h_out, n / 8, act)));
+    DISPATCH_T(dtype, (glu_bwd_kernel<T, -1><<<grid_fit(glu_bwd_kernel<T, -1>, n / 8, 256), 256, 0, STREAM>>>(
+                          (const T*)dh, (const T*)g, (const T*)u, (T*)dg, (T*)du, (T*)h_out, n / 8, act)));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -1009,15 +1023,19 @@ int b200_clip_coef(const float* sumsq, float max_norm, float* clip, float* norm_
 
 int b200_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream) {
   if (n == 0) return 0;
-  const int g = grid_1d(n / 8 + 1, 256);
+  const int64_t w8 = n / 8 + 1;
   if (src_dtype == B200_F32 && dst_dtype == B200_BF16)
-    cast_kernel<float, bf16><<<g, 256, 0, STREAM>>>((const float*)src, (bf16*)dst, n);
+    cast_kernel<float, bf16><<<grid_fit(cast_kernel<float, bf16>, w8, 256), 256, 0, STREAM>>>((const float*)src,
+                                                                                             (bf16*)dst, n);
   else if (src_dtype == B200_BF16 && dst_dtype == B200_F32)
-    cast_kernel<bf16, float><<<g, 256, 0, STREAM>>>((const bf16*)src, (float*)dst, n);
+    cast_kernel<bf16, float><<<grid_fit(cast_kernel<bf16, float>, w8, 256), 256, 0, STREAM>>>((const bf16*)src,
+                                                                                             (float*)dst, n);
   else if (src_dtype == B200_F32)
-    cast_kernel<float, float><<<g, 256, 0, STREAM>>>((const float*)src, (float*)dst, n);
+    cast_kernel<float, float><<<grid_fit(cast_kernel<float, float>, w8, 256), 256, 0, STREAM>>>((const float*)src,
+                                                                                               (float*)dst, n);
   else
-    cast_kernel<bf16, bf16><<<g, 256, 0, STREAM>>>((const bf16*)src, (bf16*)dst, n);
+    cast_kernel<bf16, bf16><<<grid_fit(cast_kernel<bf16, bf16>, w8, 256), 256, 0, STREAM>>>((const bf16*)src,
+                                                                                           (bf16*)dst, n);
   B200_LAUNCH_OK();
   return 0;
 }
@@ -1025,7 +1043,7 @@ int b200_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtyp
 int b200_add(const void* a, const void* b, void* y, int64_t n, int dtype, void* stream) {
   B200_CHECK(n % 8 == 0, "add: n must be a multiple of 8");
   if (n == 0) return 0;
-  DISPATCH_T(dtype, (add_kernel<T><<<grid_1d(n / 8, 256), 256, 0, STREAM>>>((const T*)a, (const T*)b, (T*)y, n / 8)));
+  DISPATCH_T(dtype, (add_kernel<T><<<grid_fit(add_kernel<T>, n / 8, 256), 256, 0, STREAM>>>((const T*)a, (const T*)b, (T*)y, n / 8)));
   B200_LAUNCH_OK();
   return 0;
 }
