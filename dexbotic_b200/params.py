@@ -48,6 +48,28 @@ class _Slot:
     g_offset: int     # element offset in the global (A then B) fp32 master / moment buffers
 
 
+def split_segments(segs: list, chunk_bounds: list):
+    """Partition optimizer segments (a, b, lr, wd, region) at the chunk boundaries (region-A element ranges, disjoint,
+    listed in FORWARD order, None = nothing trainable).  Returns (rest, per_chunk): every element of every segment
+    lands in exactly one piece; region-B segments are never split."""
+    rest, per_chunk = [], [[] for _ in chunk_bounds]
+    for a, b, lr, wd, region in segs:
+        if region != "A":
+            rest.append((a, b, lr, wd, region))
+            continue
+        hits = sorted((max(a, c[0]), min(b, c[1]), i) for i, c in enumerate(chunk_bounds)
+                      if c is not None and max(a, c[0]) < min(b, c[1]))
+        cur = a
+        for lo, hi, i in hits:
+            if cur < lo:
+                rest.append((cur, lo, lr, wd, region))
+            per_chunk[i].append((lo, hi, lr, wd, region))
+            cur = hi
+        if cur < b:
+            rest.append((cur, b, lr, wd, region))
+    return rest, per_chunk
+
+
 class ParamStore:
     """Regions: A = trainable, bf16 compute; B = trainable, fp32 compute; FA / FB = frozen counterparts
     (master + shadow only: no gradient, no optimizer state — e.g. lm_head in CogACT, or a frozen tower)."""
@@ -278,21 +300,7 @@ class ParamStore:
 
         # split every segment at the chunk boundaries: `rest` (embeddings, towers, heads ...) first, then the chunks in
         # forward order, all on the side stream; the caller's stream waits for `rest` only
-        rest, per_chunk = [], [[] for _ in self._chunk_bounds]
-        for a, b, lr, wd, region in segs:
-            if region != "A":
-                rest.append((a, b, lr, wd, region))
-                continue
-            hits = sorted((max(a, c[0]), min(b, c[1]), i) for i, c in enumerate(self._chunk_bounds)
-                          if c is not None and max(a, c[0]) < min(b, c[1]))   # disjoint, listed in FORWARD order
-            cur = a
-            for lo, hi, i in hits:
-                if cur < lo:
-                    rest.append((cur, lo, lr, wd, region))
-                per_chunk[i].append((lo, hi, lr, wd, region))
-                cur = hi
-            if cur < b:
-                rest.append((cur, b, lr, wd, region))
+        rest, per_chunk = split_segments(segs, self._chunk_bounds)
         main = torch.cuda.current_stream()
         if self._opt_stream is None:
             self._opt_stream = torch.cuda.Stream(device=dev)

@@ -61,3 +61,40 @@ def test_param_store_layout_cpu():
     assert st.first_write(g) and not st.first_write(g)
     st.zero_grad()
     assert st.first_write(g)
+
+
+def test_optimizer_chunk_split_covers_every_element_once():
+    """ParamStore.adamw_step's overlapped path: segments split at the per-block chunk boundaries must tile the
+    trainable range exactly (no parameter updated twice or skipped), for sorted, interleaved (pi0: LLM / expert
+    layers alternate) and partly frozen (None) chunk lists, and for segments that alternate weight decay."""
+    import random
+    from dexbotic_b200.params import split_segments
+    rnd = random.Random(0)
+    for trial in range(200):
+        n = rnd.randrange(2000, 6000)
+        # segments: consecutive runs over [0, n) in region A with alternating (lr, wd), then one region-B segment
+        cuts = sorted(rnd.sample(range(64, n, 64), rnd.randrange(1, 8)))
+        segs, prev = [], 0
+        for j, c in enumerate(cuts + [n]):
+            segs.append((prev, c, 1e-3 if j % 3 else 2e-3, 0.0 if j % 2 else 0.1, "A"))
+            prev = c
+        segs.append((n, n + 500, 1e-4, 0.0, "B"))
+        # chunks: disjoint ranges, shuffled order, some None
+        pts = sorted(rnd.sample(range(0, n, 32), 2 * rnd.randrange(1, 6)))
+        chunks = [(pts[i], pts[i + 1]) for i in range(0, len(pts), 2)]
+        rnd.shuffle(chunks)
+        chunks = [c if rnd.random() > 0.2 else None for c in chunks]
+        rest, per_chunk = split_segments(segs, chunks)
+        assert len(per_chunk) == len(chunks)
+        cover = [0] * (n + 500)
+        for piece in rest + [p for ps in per_chunk for p in ps]:
+            a, b, lr, wd, region = piece
+            assert a < b
+            src = [sg for sg in segs if sg[0] <= a and b <= sg[1] and sg[4] == region]
+            assert len(src) == 1 and (lr, wd) == (src[0][2], src[0][3]), "a piece keeps its segment's lr / wd"
+            for e in range(a, b):
+                cover[e] += 1
+        assert all(c == 1 for c in cover), (trial, [i for i, c in enumerate(cover) if c != 1][:5])
+        for i, c in enumerate(chunks):
+            for a, b, *_ in per_chunk[i]:
+                assert c is not None and c[0] <= a and b <= c[1], "chunk pieces stay inside their chunk"
