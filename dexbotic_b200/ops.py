@@ -172,7 +172,8 @@ def _qkv_ptrs(qkv: torch.Tensor, sh: AttnShape):
 
 def _fused_scores_ok(qkv: torch.Tensor, sh: AttnShape) -> bool:
     import os
-    return (qkv.dtype == torch.bfloat16 and sh.hd <= 128 and sh.S <= 512 and
+    # the persistent kernel keeps a per-CTA item list of <= 1024 (head, tile) entries: ~148 * 250 heads
+    return (qkv.dtype == torch.bfloat16 and sh.hd <= 128 and sh.hd % 8 == 0 and sh.S <= 512 and sh.B * sh.H <= 30000 and
             os.environ.get("B200_FUSED_ATTN_SCORES", "1") != "0")
 
 
