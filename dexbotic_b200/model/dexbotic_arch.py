@@ -464,10 +464,14 @@ class DexboticVLMModel:
             pad = torch.full((B, A), -(2 ** 31), device=src.device, dtype=torch.int32)
             src_ext = torch.cat([src, pad], dim=1)
             shifted = torch.cat([pad, src], dim=1)              # src[b, s - A] for the tail
-            # append_token_id None: zero rows (the caller adds its own embeddings there, OFT's action_query)
-            fill = -(2 ** 31) if append_token_id is None else append_token_id
-            src = torch.where(idx < ln, src_ext, torch.where(idx < ln + A, torch.full_like(src_ext, fill),
-                                                             shifted)).contiguous()
+            # append_token_id: one id for all appended rows, None = zero rows (the caller adds its own embeddings
+            # there: OFT's action_query), or a list of per-position ids / None (proprio token + placeholders)
+            PAD = -(2 ** 31)
+            ids_row = append_token_id if isinstance(append_token_id, (list, tuple)) else [append_token_id] * A
+            assert len(ids_row) == A
+            fill_row = torch.tensor([PAD if t is None else int(t) for t in ids_row], device=src.device, dtype=torch.int32)
+            fill = fill_row[(idx - ln).clamp(0, A - 1).long()]
+            src = torch.where(idx < ln, src_ext, torch.where(idx < ln + A, fill, shifted)).contiguous()
             new_mask = (idx < ln + A).to(torch.uint8).contiguous()
             pos = idx.expand(B, S + A).contiguous()             # HF default position ids: arange (position_ids=None)
             new_labels = torch.cat([new_labels, torch.full((B, A), IGNORE_INDEX, device=src.device,

@@ -67,8 +67,6 @@ class OFTDiscreteForCausalLM(B200Module):
     def __init__(self, config: OFTDiscreteConfig, device="cuda"):
         super().__init__()
         assert "Discrete" in config.action_model_type, "this class mirrors the OFT-discrete forward only"
-        if config.use_proprio:
-            raise NotImplementedError("use_proprio (ProprioProjector) is not wired yet")
         self.config = config
         llm, vis = config.llm_config, config.mm_vision_tower
         d, V = cfg_get(llm, "hidden_size"), cfg_get(llm, "vocab_size")
@@ -77,9 +75,22 @@ class OFTDiscreteForCausalLM(B200Module):
                  + projector_specs(config.mm_projector_type, cfg_get(vis, "hidden_size"), d,
                                    trainable=not config.freeze_mm_projector)
                  + [ParamSpec("lm_head.weight", (V, d), "lm_head", trainable=True, no_decay=False)])
+        if config.use_proprio:                       # DiscreteActionHead.proprio_projector (model.py:298-301), fp32
+            q = "model.action_head.proprio_projector."
+            specs += [ParamSpec(q + "fc1.weight", (d, config.proprio_dim), "action_head", "fp32"),
+                      ParamSpec(q + "fc1.bias", (d,), "action_head", "fp32"),
+                      ParamSpec(q + "fc2.weight", (d, d), "action_head", "fp32"),
+                      ParamSpec(q + "fc2.bias", (d,), "action_head", "fp32")]
         store = self._materialize(specs, device)
+        for name in store.order:
+            if store.slots[name].region == "B":
+                self.get_parameter(name).grad = store.g(name)
         self.model_engine = DexboticVLMModel(store, config)
         self.model_engine.action_head = DiscreteActionHead(V, config.action_dim, config.chunk_size, config.num_bins)
+        self.proprio = None
+        if config.use_proprio:
+            q = "model.action_head.proprio_projector."
+            self.proprio = (Lin.of(store, q + "fc1.weight", q + "fc1.bias"), Lin.of(store, q + "fc2.weight", q + "fc2.bias"))
         self.lm_head_lin = Lin.of(store, "lm_head.weight")
 
     def _after_weights_changed(self) -> None:
@@ -126,12 +137,20 @@ class OFTDiscreteForCausalLM(B200Module):
         if labels is not None:
             input_ids, attention_mask, discrete_action_labels = self._strip_action_labels(input_ids, attention_mask,
                                                                                           labels, A)
-        emb, _, new_mask, pos, S, lengths = eng._prepare_inputs_labels_for_multimodal(
-            input_ids, attention_mask, None, images, append_tokens=A, append_token_id=1)
         B = input_ids.shape[0]
-        hidden2d = eng.llm.forward(emb.view(B * S, -1), B, S, new_mask, pos)
-        # extract_action_hidden_states (oft_arch.py:204-210): rows [len, len + A) of every sample
-        rows = (torch.arange(B, device=hidden2d.device, dtype=torch.int32)[:, None] * S + lengths[:, None]
+        P0 = 1 if cfg.use_proprio else 0            # a proprio state token precedes the placeholders (:132-137)
+        emb, _, new_mask, pos, S, lengths = eng._prepare_inputs_labels_for_multimodal(
+            input_ids, attention_mask, None, images, append_tokens=A + P0, append_token_id=[None] * P0 + [1] * A)
+        x2d = emb.view(B * S, -1)
+        if cfg.use_proprio:
+            assert states is not None, "states is required when use_proprio is True"
+            h = LinearFn.apply(states.float().contiguous(), self.proprio[0], "gelu", self.store, False, eng.anchor.t)
+            st_tok = LinearFn.apply(h, self.proprio[1], None, self.store, True, None).to(emb.dtype)
+            srow = (torch.arange(B, device=emb.device, dtype=torch.int32) * S + lengths).contiguous()
+            x2d = InsertRowsFn.apply(x2d, st_tok, srow)
+        hidden2d = eng.llm.forward(x2d, B, S, new_mask, pos)
+        # extract_action_hidden_states (oft_arch.py:204-210): rows [len, len + A) of every sample (minus the state row)
+        rows = (torch.arange(B, device=hidden2d.device, dtype=torch.int32)[:, None] * S + lengths[:, None] + P0
                 + torch.arange(A, device=hidden2d.device, dtype=torch.int32)[None, :]).reshape(-1).contiguous()
         action_hidden = GatherRowsFn.apply(hidden2d, rows)                       # [B*A, D]
         logits2d = LinearFn.apply(action_hidden, self.lm_head_lin, None, self.store, True, None)   # lm_head, :168
@@ -142,9 +161,9 @@ class OFTDiscreteForCausalLM(B200Module):
         return CausalLMOutputDexbotic(loss=loss, logits=logits2d.view(B, A, -1))
 
     @torch.no_grad()
-    def predict_action_bins(self, input_ids, images, attention_mask=None) -> torch.Tensor:
+    def predict_action_bins(self, input_ids, images, attention_mask=None, states=None) -> torch.Tensor:
         """Parallel decoding (oft_discrete_arch.py:207-224): int64 bin indices [B, chunk*dim] in [0, num_bins-2]."""
-        out = self.forward(input_ids=input_ids, attention_mask=attention_mask, images=images)
+        out = self.forward(input_ids=input_ids, attention_mask=attention_mask, images=images, states=states)
         B, A, V = out.logits.shape
         return ops.argmax_last(out.logits.reshape(B * A, V).contiguous(), self.config.num_bins - 1).view(B, A)
 
@@ -152,7 +171,7 @@ class OFTDiscreteForCausalLM(B200Module):
     def inference_action(self, input_ids, image_tensor, inference_args={}, **kwargs):
         """oft_discrete_arch.py:207-235."""
         action_norms = inference_args.get("action_norms")
-        idx = self.predict_action_bins(input_ids, image_tensor)
+        idx = self.predict_action_bins(input_ids, image_tensor, states=inference_args.get("states"))
         cont = self.model_engine.action_head.discrete_tokens_to_continuous(idx)
         actions = cont[0].float().cpu().numpy()
         actions = np.clip(actions, -1, 1)                                 # _denorm, dexbotic_arch.py:546-563

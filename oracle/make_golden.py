@@ -233,6 +233,53 @@ def make_oft_discrete_tiny(seed: int = 4321):
     print("[oft_discrete_tiny] wrote fixture")
 
 
+def make_oft_discrete_proprio_tiny(seed: int = 4322):
+    """OFT-discrete with the proprio state token (oft_discrete_arch.py:132-137,161-162)."""
+    llm, clip, cfg = tiny_cogact_configs()
+    llm.vocab_size = 512
+    cfg = dict(cfg, chunk_size=8, action_dim=7, num_bins=256, use_proprio=True, proprio_dim=9)
+    cfg["llm"] = dict(cfg["llm"], vocab_size=512)
+    model = ref_loader.build_reference_oft_discrete(llm, clip, 7, 8, 256, use_proprio=True, proprio_dim=9)
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    g = torch.Generator().manual_seed(seed)
+    B, A = 3, 56
+    L = 10 + A + 1 + 3
+    ids = torch.randint(1, 250, (B, L), generator=g)
+    ids[:, 1] = vla_oracle.IMAGE_TOKEN_INDEX
+    mask = torch.ones(B, L, dtype=torch.long)
+    mask[1, L - 3:] = 0
+    mask[2, L - 1:] = 0
+    labels = torch.full((B, L), -100, dtype=torch.long)
+    for b in range(B):
+        npl = int(mask[b].sum())
+        tok = torch.randint(512 - 255, 512, (A,), generator=g)
+        ids[b, npl - 1 - A:npl - 1] = tok
+        labels[b, npl - 1 - A:npl - 1] = tok
+    images = torch.randn(B, 3, 28, 28, generator=g)
+    actions = torch.rand(B, 8 * 7, generator=g) * 2 - 1
+    states = torch.randn(B, 9, generator=g)
+    out = model(input_ids=ids, attention_mask=mask, images=images, labels=labels, actions=actions, states=states)
+    out.loss.backward()
+    ora = vla_oracle.oft_discrete_forward(sd, cfg, ids, mask, images, labels, states)
+    d_loss = abs(ora["loss"].item() - out.loss.item())
+    d_log = (ora["logits"] - out.logits).abs().max().item()
+    print(f"[oft_discrete_proprio] reference loss {out.loss.item():.8f} oracle {ora['loss'].item():.8f}; logits max|d|={d_log:.2e}")
+    assert d_loss < 1e-5 and d_log < 1e-4
+    params = dict(model.named_parameters())
+    grads = {n: params[n].grad.clone() for n in
+             ["lm_head.weight", "model.action_head.proprio_projector.fc1.weight",
+              "model.action_head.proprio_projector.fc2.bias", "model.llm.layers.1.mlp.up_proj.weight",
+              "model.llm.embed_tokens.weight"]}
+    torch.save(dict(seed=seed, cfg=cfg, shapes={k: tuple(v.shape) for k, v in sd.items()},
+                    inputs=dict(input_ids=ids, attention_mask=mask, images=images, labels=labels, actions=actions,
+                                states=states),
+                    outputs=dict(loss=out.loss.detach(), logits=out.logits.detach(), grads=grads)),
+               GOLDEN / "oft_discrete_proprio_tiny.pt")
+    print("[oft_discrete_proprio] wrote fixture")
+
+
 def make_oft_linear_tiny(seed: int = 8642):
     """OFTForCausalLM with the L1-regression head, with and without the proprio token (oft_arch.py:58-166)."""
     out_fx = {}
@@ -576,6 +623,7 @@ if __name__ == "__main__":
     make_pi05_tiny()
     make_memvla_tiny()
     make_oft_discrete_tiny()
+    make_oft_discrete_proprio_tiny()
     make_oft_linear_tiny()
     make_splice_cases()
     make_integer_kats()

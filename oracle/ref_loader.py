@@ -184,13 +184,13 @@ def build_reference_cogact(llm_config, clip_config, action_model_type: str = "Di
 
 
 def build_reference_oft_discrete(llm_config, clip_config, action_dim: int = 7, chunk_size: int = 8, num_bins: int = 256,
-                                 mm_projector_type: str = "mlp2x_gelu"):
+                                 mm_projector_type: str = "mlp2x_gelu", use_proprio: bool = False, proprio_dim=None):
     """Reference OFTDiscreteForCausalLM (oft_discrete_arch.py:20-24) with random-init weights."""
     load_reference()
     from dexbotic.model.oft.oft_discrete_arch import OFTDiscreteConfig, OFTDiscreteForCausalLM
     cfg = OFTDiscreteConfig(llm_config=llm_config, mm_projector_type=mm_projector_type, mm_vision_tower=clip_config,
                             action_model_type="Discrete", action_dim=action_dim, chunk_size=chunk_size,
-                            use_proprio=False, proprio_dim=None, num_bins=num_bins)
+                            use_proprio=use_proprio, proprio_dim=proprio_dim, num_bins=num_bins)
     return OFTDiscreteForCausalLM(cfg)
 
 

@@ -520,7 +520,7 @@ def data_action_to_bin(action: np.ndarray, vocab_size: int = 255) -> np.ndarray:
 # ----------------------------------------------------------------------------------------------
 # OFT-discrete training forward — oft_discrete_arch.py:26-205, oft_arch.py:169-210
 # ----------------------------------------------------------------------------------------------
-def oft_discrete_forward(sd, cfg: dict, input_ids, attention_mask, images, labels=None):
+def oft_discrete_forward(sd, cfg: dict, input_ids, attention_mask, images, labels=None, states=None):
     """Returns dict(loss, logits [B, A, V], action_labels).  A = chunk_size * action_dim placeholder tokens
     (embed_tokens of token id 1) are inserted after the last valid token of every sample."""
     A = cfg["chunk_size"] * cfg["action_dim"]
@@ -542,19 +542,27 @@ def oft_discrete_forward(sd, cfg: dict, input_ids, attention_mask, images, label
     emb, _, msk, _ = splice(sd["model.llm.embed_tokens.weight"], feats, input_ids, attention_mask, None,
                             cfg.get("tokenizer_model_max_length"), "right")
     S, D = emb.shape[1], emb.shape[2]
-    act_emb = sd["model.llm.embed_tokens.weight"][torch.ones(A, dtype=torch.long)]       # :125-130
+    act_emb = sd["model.llm.embed_tokens.weight"][torch.ones(A, dtype=torch.long)][None].expand(B, A, D)   # :125-130
+    if cfg.get("use_proprio"):                                         # :132-137 state token in front
+        h = "model.action_head.proprio_projector."
+        st = F.linear(F.gelu(F.linear(states, sd[h + "fc1.weight"], sd[h + "fc1.bias"])), sd[h + "fc2.weight"],
+                      sd[h + "fc2.bias"])
+        act_emb = torch.cat([st.reshape(B, -1, D), act_emb], dim=1)
+    n_act = act_emb.shape[1]
     lens = msk.long().sum(dim=1)
-    emb2 = torch.zeros(B, S + A, D, dtype=emb.dtype)
-    msk2 = torch.zeros(B, S + A, dtype=torch.bool)
+    emb2 = torch.zeros(B, S + n_act, D, dtype=emb.dtype)
+    msk2 = torch.zeros(B, S + n_act, dtype=torch.bool)
     for i in range(B):                                                 # insert_action_embedding, oft_arch.py:169-201
         n = int(lens[i])
         emb2[i, :n] = emb[i, :n]
-        emb2[i, n:n + A] = act_emb
-        emb2[i, n + A:] = emb[i, n:]
-        msk2[i, :n + A] = True
-    pid = torch.arange(S + A)[None, :].expand(B, S + A)                # position_ids=None -> HF arange
+        emb2[i, n:n + n_act] = act_emb[i]
+        emb2[i, n + n_act:] = emb[i, n:]
+        msk2[i, :n + n_act] = True
+    pid = torch.arange(S + n_act)[None, :].expand(B, S + n_act)        # position_ids=None -> HF arange
     hs = decoder_forward(sd, "model.llm.", emb2, msk2, pid, cfg["llm"])
-    ah = torch.stack([hs[i, int(lens[i]):int(lens[i]) + A] for i in range(B)])           # :204-210
+    ah = torch.stack([hs[i, int(lens[i]):int(lens[i]) + n_act] for i in range(B)])       # :204-210
+    if cfg.get("use_proprio"):
+        ah = ah[:, 1:]                                                 # :161-162
     logits = F.linear(ah, sd["lm_head.weight"])
     loss = None
     if action_labels is not None:

@@ -227,3 +227,35 @@ def test_oft_linear_production_dims_one_layer_matches_oracle():
         if not (rel < 0.35 and cos > 0.94):                 # sign()-gradient of the L1 loss, see the tiny test
             bad.append((name, round(rel, 4), round(cos, 5)))
     assert not bad, bad
+
+
+def test_oft_discrete_with_proprio_matches_reference_golden():
+    """OFT-discrete with use_proprio: a projected state token in front of the placeholder tokens, dropped again before
+    lm_head (oft_discrete_arch.py:132-137,161-162)."""
+    from dexbotic_b200.model import OFTDiscreteConfig, OFTDiscreteForCausalLM
+    from oracle.weights import seeded_state_dict
+    fx = torch.load(GOLDEN / "oft_discrete_proprio_tiny.pt", weights_only=False)
+    cfg = fx["cfg"]
+    c = OFTDiscreteConfig(llm_config=cfg["llm"], mm_vision_tower=cfg["vision"], mm_projector_type="mlp2x_gelu",
+                          action_model_type="Discrete", action_dim=cfg["action_dim"], chunk_size=cfg["chunk_size"],
+                          num_bins=cfg["num_bins"], use_proprio=True, proprio_dim=cfg["proprio_dim"])
+    model = OFTDiscreteForCausalLM(c, device="cuda")
+    sd = {k: v for k, v in seeded_state_dict(fx["shapes"], fx["seed"]).items() if "position_ids" not in k}
+    model.load_state_dict(sd, strict=True)
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == \
+        {k: tuple(v) for k, v in fx["shapes"].items() if "position_ids" not in k}
+    model.train()
+    i = {k: v.cuda() for k, v in fx["inputs"].items()}
+    model.zero_grad()
+    out = model(input_ids=i["input_ids"], attention_mask=i["attention_mask"], images=i["images"], labels=i["labels"],
+                actions=i["actions"], states=i["states"])
+    ref = fx["outputs"]
+    assert abs(out.loss.item() - ref["loss"].item()) < 2e-2 * abs(ref["loss"].item()), (out.loss.item(), ref["loss"].item())
+    a, b = out.logits.float().flatten(), ref["logits"].cuda().flatten()
+    assert ((a - b).norm() / b.norm()).item() < 4e-2
+    out.loss.backward()
+    for name, gref in ref["grads"].items():
+        g, r = model.store.g(name).float().flatten(), gref.cuda().flatten()
+        rel = ((g - r).norm() / (r.norm() + 1e-12)).item()
+        cos = torch.nn.functional.cosine_similarity(g, r, dim=0).item()
+        assert rel < 0.12 and cos > 0.99, (name, rel, cos)
