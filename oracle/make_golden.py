@@ -585,6 +585,44 @@ def make_pi05_tiny(seed: int = 9753):
     print("[pi05_tiny] wrote fixture; params without grad:", len(none_grad), [n for n in names if n not in grads])
 
 
+def make_memvla_inference_tiny(seed: int = 1357):
+    """MemVLA inference_action over four consecutive frames of one episode (memory grows, then token-merges at
+    mem_length 2), dropout 0: reference vs oracle, per-frame noise and outputs stored."""
+    llm, clip, cfg = tiny_cogact_configs()
+    model = ref_loader.build_reference_memvla(llm, clip, "DiT-S", **MEMVLA_MEM)
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    mcfg = dict(cfg, mem=MEMVLA_MEM)
+    m = MEMVLA_MEM
+    banks = {r: vla_oracle.MemBankOracle(sd, "model.per_cog_mem_bank.", r, m["mem_length"], m["retrieval_layers"],
+                                         m["dataloader_type"], m["use_timestep_pe"], m["fusion_type"],
+                                         m["consolidate_type"], m["update_fused"]) for r in ("per", "cog")}
+    g = torch.Generator().manual_seed(seed + 11)
+    L = 11
+    norms = {"min": [-1.0] * 7, "max": [1.0] * 7}
+    frames = []
+    for f in range(4):
+        ids = torch.randint(1, 128, (1, L), generator=g)
+        ids[:, 1] = vla_oracle.IMAGE_TOKEN_INDEX
+        images = torch.randn(1, 3, 28, 28, generator=g)
+        torch.manual_seed(seed + 20 + f)
+        acts = model.inference_action(ids, images, "True" if f == 0 else "False",
+                                      {"cfg_scale": 1.5, "num_ddim_steps": 10, "action_norms": norms})
+        torch.manual_seed(seed + 20 + f)
+        noise = torch.randn(1, 16, 7)                                # memvla_arch.py:704-709
+        ora = vla_oracle.memvla_inference(sd, mcfg, banks, ids, images, noise, f, 1.5, 10)
+        ref = torch.tensor(acts)
+        d = (ora[0].clamp(-1, 1) - ref).abs().max().item()
+        print(f"[memvla_inference] frame {f}: oracle vs reference max|d|={d:.2e}; bank length "
+              f"{len(banks['cog'].banks[(0, 0)])}")
+        assert d < 1e-4
+        frames.append(dict(input_ids=ids, images=images, noise=noise, actions=ref))
+    assert len(banks["cog"].banks[(0, 0)]) == 2
+    torch.save(dict(seed=seed, cfg=mcfg, shapes={k: tuple(v.shape) for k, v in sd.items()}, frames=frames),
+               GOLDEN / "memvla_inference_tiny.pt")
+
+
 def make_cogact_inference_tiny(seed: int = 1234):
     """CogACT inference_action (CFG 1.5, 10-step DDIM, eta=0) from the reference (cogact_arch.py:149-198)."""
     llm, clip, cfg = tiny_cogact_configs()
@@ -622,6 +660,7 @@ if __name__ == "__main__":
     make_pi0_inference_tiny()
     make_pi05_tiny()
     make_memvla_tiny()
+    make_memvla_inference_tiny()
     make_oft_discrete_tiny()
     make_oft_discrete_proprio_tiny()
     make_oft_linear_tiny()

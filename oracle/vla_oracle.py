@@ -886,14 +886,10 @@ def ddim_tables(num_steps: int = 100, ddim_steps: int = 10):
     return tmap, ac2, np.append(1.0, ac2[:-1])
 
 
-def cogact_inference(sd, cfg: dict, input_ids, images, noise, cfg_scale: float = 1.5, num_ddim_steps: int = 10):
-    """CogACTForCausalLM.inference_action up to (excluding) _denorm: returns samples [B, T, A] (normalised actions)."""
-    feats = clip_vision_features(sd, "model.mm_vision_tower.", images, cfg["vision"])
-    feats = mlp_projector(sd, "model.mm_projector.", feats, cfg.get("projector_depth", 2))
-    emb, _, msk, pid = splice(sd["model.llm.embed_tokens.weight"], feats, input_ids, None, None,
-                              cfg.get("tokenizer_model_max_length"), "right")
-    hs = decoder_forward(sd, "model.llm.", emb, msk, pid, cfg["llm"])
-    cog = hs[:, -1, :][:, None]                                             # :158
+def ddim_sample(sd, cfg: dict, cog, noise, cfg_scale: float = 1.5, num_ddim_steps: int = 10, per_token=None):
+    """ddim_sample_loop (diffusion.py:714-795) with eta = 0, clip_denoised=False, classifier-free guidance through
+    forward_with_cfg (dit.py:294-311).  per_token (MemVLA): repeated twice along the batch like the reference does
+    (memvla_arch.py:722)."""
     B = cog.shape[0]
     width = sd["model.action_head.net.x_embedder.linear.weight"].shape[0]
     heads = DIT_HEADS[width]
@@ -905,20 +901,50 @@ def cogact_inference(sd, cfg: dict, input_ids, images, noise, cfg_scale: float =
         z = torch.cat([cog, unc], 0)
     else:
         z = cog
+    pt = None if per_token is None else per_token.repeat(2, 1, 1)
     tmap, ac, ac_prev = ddim_tables(cfg.get("diffusion_steps", 100), num_ddim_steps)
     f32 = lambda v: torch.tensor(v, dtype=torch.float64).float()          # noqa: E731 (_extract_into_tensor)
     for i in reversed(range(len(tmap))):
         t = torch.full((x.shape[0],), tmap[i], dtype=torch.long)
         if use_cfg:                                                          # forward_with_cfg, dit.py:294-311
             half = x[: x.shape[0] // 2]
-            out = dit_forward(sd, "model.action_head.", torch.cat([half, half], 0), t, z, None, heads)
+            out = dit_forward(sd, "model.action_head.", torch.cat([half, half], 0), t, z, None, heads, per_token=pt)
             cond, uncond = out.chunk(2, dim=0)
             e = uncond + cfg_scale * (cond - uncond)
             eps_model = torch.cat([e, e], 0)
         else:
-            eps_model = dit_forward(sd, "model.action_head.", x, t, z, None, heads)
+            eps_model = dit_forward(sd, "model.action_head.", x, t, z, None, heads, per_token=pt)
         sr, srm1 = f32(np.sqrt(1.0 / ac[i])), f32(np.sqrt(1.0 / ac[i] - 1))
         pred_x0 = sr * x - srm1 * eps_model                                  # _predict_xstart_from_eps
         eps = (sr * x - pred_x0) / srm1                                      # _predict_eps_from_xstart
         x = pred_x0 * torch.sqrt(f32(ac_prev[i])) + torch.sqrt(1 - f32(ac_prev[i])) * eps   # eta = 0
     return x[:B] if use_cfg else x
+
+
+def _inference_trunk(sd, cfg: dict, input_ids, images):
+    feats = clip_vision_features(sd, "model.mm_vision_tower.", images, cfg["vision"])
+    feats = mlp_projector(sd, "model.mm_projector.", feats, cfg.get("projector_depth", 2))
+    emb, _, msk, pid = splice(sd["model.llm.embed_tokens.weight"], feats, input_ids, None, None,
+                              cfg.get("tokenizer_model_max_length"), "right")
+    hs = decoder_forward(sd, "model.llm.", emb, msk, pid, cfg["llm"])
+    return hs[:, -1, :][:, None], feats                                     # cognition = last position (:158)
+
+
+def cogact_inference(sd, cfg: dict, input_ids, images, noise, cfg_scale: float = 1.5, num_ddim_steps: int = 10):
+    """CogACTForCausalLM.inference_action up to (excluding) _denorm: returns samples [B, T, A] (normalised actions)."""
+    cog, _ = _inference_trunk(sd, cfg, input_ids, images)
+    return ddim_sample(sd, cfg, cog, noise, cfg_scale, num_ddim_steps)
+
+
+def memvla_inference(sd, cfg: dict, banks: dict, input_ids, images, noise, timestep: int, cfg_scale: float = 1.5,
+                     num_ddim_steps: int = 10):
+    """One MemVLAForCausalLM.inference_action call (memvla_arch.py:666-745), excluding _denorm: the cognition token
+    and the compressed perceptual tokens of this frame go through the memory bank in eval mode (every frame of the
+    running episode has id (0, 0), :334-337), which also appends them to it; then CFG + DDIM with per_token.
+    `banks` = {"per": MemBankOracle, "cog": MemBankOracle} carried across the frames of an episode."""
+    cog, feats = _inference_trunk(sd, cfg, input_ids, images)
+    per = bottleneck_se(sd, "model.per_compr.", feats)
+    ts = [torch.tensor(timestep)]
+    cog = banks["cog"].process_batch(cog, [(0, 0)], ts, training=False)
+    per = banks["per"].process_batch(per, [(0, 0)], ts, training=False)
+    return ddim_sample(sd, cfg, cog, noise, cfg_scale, num_ddim_steps, per_token=per)

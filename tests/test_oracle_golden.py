@@ -142,6 +142,18 @@ def test_pi05_tiny_matches_reference():
         assert (got - r["actions"]).abs().max().item() < 1e-4
 
 
+def test_memvla_inference_matches_reference():
+    fx = torch.load(GOLDEN / "memvla_inference_tiny.pt", weights_only=False)
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    m = fx["cfg"]["mem"]
+    banks = {r: vla_oracle.MemBankOracle(sd, "model.per_cog_mem_bank.", r, m["mem_length"], m["retrieval_layers"],
+                                         m["dataloader_type"], m["use_timestep_pe"], m["fusion_type"],
+                                         m["consolidate_type"], m["update_fused"]) for r in ("per", "cog")}
+    for f, fr in enumerate(fx["frames"]):
+        got = vla_oracle.memvla_inference(sd, fx["cfg"], banks, fr["input_ids"], fr["images"], fr["noise"], f)
+        assert (got[0].clamp(-1, 1) - fr["actions"]).abs().max().item() < 1e-4
+
+
 def test_pi0_attn_mask_truth_table():
     """make_attn_mask (pi0_arch.py:22-33): prefix bidirectional, state token sees prefix + itself, action tokens see
     prefix + state + each other; invalid positions neither attend nor are attended."""
