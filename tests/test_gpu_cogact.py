@@ -285,7 +285,9 @@ def test_reference_facing_surface_and_checkpoint_roundtrip(tmp_path):
     assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
     with torch.no_grad():
         l1 = again(**kw).loss.item()
-    assert l0 == l1, (l0, l1)
+    # same weights, same inputs; the scalar MSE reduction sums block partials with fp32 atomics, so the two losses agree
+    # to the last ulp or two rather than bitwise
+    assert abs(l0 - l1) <= 2e-6 * abs(l0), (l0, l1)
 
 
 def test_overlapped_optimizer_equals_synchronous():
