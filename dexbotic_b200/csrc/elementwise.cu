@@ -599,6 +599,10 @@ __global__ void colsum_strided_kernel(const float* __restrict__ x, float* __rest
   for (int j = 0; j < 8; ++j) atomicAdd(out + col8 + j, acc[j]);
 }
 
+// scratch of the grid-wide deterministic reductions (launches of one stream are ordered; grid <= 8 x SMs)
+__device__ float g_partials[4096];
+__device__ unsigned g_ticket;
+
 template <typename T>
 __global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ x, int64_t n, float* __restrict__ out) {
   __shared__ float red[33];
@@ -616,7 +620,20 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ x, int
       acc += v * v;
     }
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(out, acc);
+  // deterministic grid reduction: per-block partials, the last block to finish adds them up in block order
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    g_partials[blockIdx.x] = acc;
+    __threadfence();
+    last = atomicInc(&g_ticket, gridDim.x - 1) == gridDim.x - 1;   // wraps to 0: ready for the next launch
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float tot = 0.0f;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) tot += __ldcg(&g_partials[i]);
+  tot = block_sum(tot, red);
+  if (threadIdx.x == 0) *out += tot;
 }
 
 // mean((a-b)^2) forward: out += sum/(n) ; backward: da = 2*(a-b)/n * gscale  (db = -da)
@@ -983,7 +1000,8 @@ int b200_sumsq(const void* x, int64_t n, float* out, int dtype, void* stream) {
 
 int b200_mse_fwd(const void* a, const void* b, int64_t n, float* out, int dtype, void* stream) {
   if (n == 0) return 0;
-  DISPATCH_T(dtype, (mse_fwd_kernel<T><<<grid_1d(n, 256), 256, 0, STREAM>>>((const T*)a, (const T*)b, n,
+  // action-chunk losses are a few 10^4 elements: one block = a fixed summation order (run-to-run identical losses)
+  DISPATCH_T(dtype, (mse_fwd_kernel<T><<<n <= (1 << 22) ? 1 : grid_1d(n, 256), 256, 0, STREAM>>>((const T*)a, (const T*)b, n,
                                                                             1.0f / (float)n, out)));
   B200_LAUNCH_OK();
   return 0;

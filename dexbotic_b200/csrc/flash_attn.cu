@@ -1,0 +1,1125 @@
+// Flash attention for sm_100a (bf16, head_dim <= 256, self-attention over a packed qkv buffer): forward and backward
+// with the score block resident in TMEM — no [B, H, S, S] tensor exists at any point; the forward saves one fp32
+// log-sum-exp per query row and the backward recomputes P from it.
+//
+//   flash_fwd_kernel<T>   one CTA works on T query tiles (128 rows each) that share a KV head.  Per 64-key block:
+//                         S = Q K^T (tcgen05.mma -> TMEM, double buffered per tile), online softmax by one warpgroup per
+//                         tile (one thread = one query row, no cross-thread exchange; the running maximum is only
+//                         refreshed — and O rescaled in TMEM via tcgen05.ld/st — when it grows by more than 2^8),
+//                         P -> bf16 -> 128B-swizzled smem, O += P V (tcgen05.mma, O stays in TMEM for the whole tile).
+//                         T = 2 for head_dim <= 128 (two rows of work keep MUFU and the tensor pipe busy at the same
+//                         time), T = 1 for head_dim 256 (TMEM: 2 x 64 score columns + 256 output columns).
+//   flash_dq_kernel       CTA = (batch, head, query tile); per key block S and dP = dO V^T in TMEM, dS = scale * P *
+//                         (dP - delta) -> smem, dQ += dS K accumulated in TMEM over all key blocks, written once.
+//   flash_dkv_kernel      CTA = (batch, KV head, 128-key tile); loops over the G query heads of the group and the query
+//                         blocks that see the tile.  Works on the transposed problem (S^T = K Q^T: TMEM lanes = keys) so
+//                         that P^T / dS^T land in smem as K-major A operands: dV += P^T dO, dK += dS^T Q accumulate in
+//                         TMEM over heads and query blocks — the GQA group reduction happens in the accumulator, no
+//                         atomics, run-to-run deterministic.  head_dim 256 runs dV and dK as two items (TMEM budget).
+//   attn_delta_kernel     delta[b,h,q] = rowsum(dO * O), the softmax-backward row term.
+//
+// Every operand tile is staged by TMA as 64-column atoms of [rows][128 B] (SWIZZLE_128B); the same smem image serves as
+// a K-major operand (contraction over head_dim: S, dP) and as an MN-major operand (contraction over its rows: P V,
+// dS K, P^T dO, dS^T Q), so K / V / Q / dO are loaded once per use site and never transposed.
+//
+// Mask rule (b200_softmax_fwd's): allowed(q, k) = k < S && (keymask == NULL || keymask[b, k]) &&
+// (causal ? k <= q : true) && (bid == NULL || bid_k[b, k] <= bid_q[b, q]).
+//
+// Reference arithmetic replaced: F.scaled_dot_product_attention / eager softmax attention inside HF Qwen2 / Llama /
+// Gemma / CLIP / SigLIP attention and its autograd backward (called from dexbotic_arch.py:55-62, clip_encoder.py:50-54,
+// siglip_encoder.py:79-84; pi0's joint attention pi0_arch.py:185-192 with make_attn_mask pi0_arch.py:22-33).
+#include <cuda.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/dexbotic_b200_ops.h"
+#include "common.h"
+#define B200_SPIN_LIMIT (1u << 24)   // a protocol dead-lock traps within seconds instead of hanging the device
+#include "ptx.cuh"
+
+namespace b200 {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int kFaMaxStages = 4;
+constexpr int kAtom128 = 128 * 128;   // bytes of one 64-column atom of a 128-row tile
+constexpr int kAtom64 = 64 * 128;     // ... of a 64-row block
+constexpr float kRescaleThreshold = 8.0f;   // log2 units: P <= 2^8 under a stale maximum
+
+struct FaParams {
+  CUtensorMap tmQ, tmK, tmV, tmDO;
+  int B, H, KVH, G, S, hd;
+  int katoms;    // ceil(hd / 64): 64-column atoms per tile row
+  int ksteps;    // ceil(hd / 16): UMMA K steps of a head_dim contraction
+  int n_hd;      // hd rounded up to 16: MMA N of the products whose output is head_dim wide
+  int o_chunks;  // ceil(hd / 32): 32-column TMEM chunks of such an output
+  int m_tiles;   // ceil(S / 128)
+  int n_qblk;    // ceil(S / 64)
+  int stages;
+  int causal;
+  int n_items;
+  int n_modes;   // dkv: 1 (dV and dK together) or 2 (head_dim > 128: separate items)
+  float scale, sl2;
+  const uint8_t* keymask;
+  const int* bid_q;
+  const int* bid_k;
+  bf16* out;            // fwd: O rows; bwd: unused
+  float* lse;           // [B, H, S] log2-domain log-sum-exp
+  const float* delta;   // [B, H, S]
+  bf16 *dq, *dk, *dv;
+  long long o_ld, o_sh, o_sb;      // element strides of out (row, head, batch)
+  long long g_ld, gq_sh, gkv_sh, g_sb;   // strides of dq / dk / dv
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t low_mask(int n) { return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
+
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024, descriptor version 1, SWIZZLE_128B
+constexpr uint32_t kLoKMajor = (16u >> 4) << 16;                        // LBO unused for K-major operands
+constexpr uint32_t kLoMN64 = (8192u >> 4) << 16;                        // MN-major, 64-row atoms: next atom 8 KB on
+
+// D (=, then +=) A B^T contracted over head_dim; A / B tiles are [rows][hd] atom images, used K-major.
+__device__ __forceinline__ void mma_over_hd(uint32_t d_tmem, uint32_t a_addr, uint32_t a_atom, uint32_t b_addr,
+                                            uint32_t b_atom, int ksteps, uint32_t idesc) {
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint32_t off = (uint32_t)(ks & 3) * 32u;
+    const uint32_t a_lo = kLoKMajor | ((a_addr + (uint32_t)(ks >> 2) * a_atom + off) >> 4);
+    const uint32_t b_lo = kLoKMajor | ((b_addr + (uint32_t)(ks >> 2) * b_atom + off) >> 4);
+    umma_issue<1, false>(d_tmem, a_lo, kDescHi, b_lo, kDescHi, idesc, ks != 0 ? 1u : 0u);
+  }
+}
+// D (+)= A B contracted over the 64 rows of B: A = one [128][64] K-major atom (P, dS, P^T, dS^T), B = a 64-row block
+// [64][hd] read MN-major (N = head_dim).
+__device__ __forceinline__ void mma_over_rows64(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc,
+                                                uint32_t accumulate) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint32_t a_lo = kLoKMajor | ((a_addr + (uint32_t)ks * 32u) >> 4);
+    const uint32_t b_lo = kLoMN64 | ((b_addr + (uint32_t)ks * 2048u) >> 4);
+    umma_issue<1, false>(d_tmem, a_lo, kDescHi, b_lo, kDescHi, idesc, (accumulate | (uint32_t)(ks != 0)) ? 1u : 0u);
+  }
+}
+
+__device__ __forceinline__ int visible_blocks(const FaParams& p, int tile) {
+  const int keys = p.causal ? min(p.S, tile * 128 + 128) : p.S;
+  return (keys + 63) >> 6;
+}
+
+// Row-per-thread validity bits of 32 consecutive keys [k0, k0 + 32) for query row q (row-wise kernels: fwd, dq).
+// Key-side bits (range, padding) come from one ballot; the causal rule is a per-row bit count; the block-id rule is
+// evaluated per element only when the warp's keys are not all visible to all its rows.
+__device__ __forceinline__ uint32_t row_bits32(const FaParams& p, int b, int q, int bq, int k0, int lane) {
+  const int k = k0 + lane;
+  const bool kv = k < p.S && (p.keymask == nullptr || p.keymask[(size_t)b * p.S + k] != 0);
+  uint32_t w = __ballot_sync(0xffffffffu, kv);
+  if (p.causal) w &= low_mask(q + 1 - k0);
+  if (p.bid_k != nullptr) {
+    const int bk = k < p.S ? p.bid_k[(size_t)b * p.S + k] : 0x7fffffff;
+    int mx = kv ? bk : (int)0x80000000;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (__any_sync(0xffffffffu, bq < mx)) {
+      uint32_t w2 = 0;
+      for (int j = 0; j < 32; ++j) {
+        const int bkj = __shfl_sync(0xffffffffu, bk, j);
+        if (bkj <= bq) w2 |= 1u << j;
+      }
+      w &= w2;
+    }
+  }
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------------- forward
+struct FwdItem {
+  int b, kvh, n;
+  int h[2], tile[2], nblk[2];
+};
+template <int kTiles>
+__device__ __forceinline__ FwdItem fwd_item(const FaParams& p, int it) {
+  FwdItem r;
+  if (kTiles == 2) {
+    const int BK = p.B * p.KVH;
+    const int pr = it / BK, bk = it - pr * BK;
+    r.b = bk / p.KVH;
+    r.kvh = bk - r.b * p.KVH;
+    const int entries = p.G * p.m_tiles;
+    r.n = 0;
+    for (int t = 0; t < 2; ++t) {
+      const int e = 2 * pr + t;
+      if (e < entries) {
+        const int tq = e / p.G;
+        r.tile[t] = p.m_tiles - 1 - tq;          // widest (most key blocks under a causal mask) first
+        r.h[t] = r.kvh * p.G + (e - tq * p.G);
+        r.nblk[t] = visible_blocks(p, r.tile[t]);
+      } else {
+        r.tile[t] = 0;
+        r.h[t] = 0;
+        r.nblk[t] = 0;
+      }
+      r.n = max(r.n, r.nblk[t]);
+    }
+  } else {
+    const int BH = p.B * p.H;
+    const int pr = it / BH, bh = it - pr * BH;
+    r.b = bh / p.H;
+    r.h[0] = bh - r.b * p.H;
+    r.kvh = r.h[0] / p.G;
+    r.tile[0] = p.m_tiles - 1 - pr;
+    r.nblk[0] = visible_blocks(p, r.tile[0]);
+    r.n = r.nblk[0];
+    r.h[1] = r.tile[1] = r.nblk[1] = 0;
+  }
+  return r;
+}
+
+template <int kTiles>
+__global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const __grid_constant__ FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_q_full, bar_q_empty, bar_kv_full[kFaMaxStages], bar_kv_empty[kFaMaxStages];
+  __shared__ uint64_t bar_s_full[2][2], bar_p_full[2], bar_pv_done[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sQ = smem;                                   // kTiles x katoms x [128][128 B]
+  uint8_t* sP = sQ + kTiles * p.katoms * kAtom128;      // kTiles x [128][128 B]
+  uint8_t* sRing = sP + kTiles * kAtom128;              // stages x (K: katoms x [64][128 B] | V: the same)
+  const int stage_bytes = 2 * p.katoms * kAtom64;
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(&bar_q_full, 1);
+    mbar_init(&bar_q_empty, 1);
+    for (int i = 0; i < kFaMaxStages; ++i) {
+      mbar_init(&bar_kv_full[i], 1);
+      mbar_init(&bar_kv_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&bar_s_full[t][0], 1);
+      mbar_init(&bar_s_full[t][1], 1);
+      mbar_init(&bar_p_full[t], 128);
+      mbar_init(&bar_pv_done[t], 1);
+    }
+    mbar_fence_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+  }
+  if (warp == 2) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int stages = p.stages;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0, qi = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
+        const FwdItem im = fwd_item<kTiles>(p, it);
+        mbar_wait(&bar_q_empty, (uint32_t)(qi & 1) ^ 1u);
+        int nvalid = 0;
+        for (int t = 0; t < kTiles; ++t) nvalid += im.nblk[t] > 0 ? 1 : 0;
+        mbar_expect_tx(&bar_q_full, (uint32_t)(nvalid * p.katoms * kAtom128));
+        for (int t = 0; t < kTiles; ++t) {
+          if (im.nblk[t] == 0) continue;
+          for (int a = 0; a < p.katoms; ++a)
+            tma_load_4d(sQ + (t * p.katoms + a) * kAtom128, &p.tmQ, &bar_q_full, a * 64, im.tile[t] * 128, im.h[t],
+                        im.b);
+        }
+        for (int j = 0; j < im.n; ++j) {
+          mbar_wait(&bar_kv_empty[stage], phase ^ 1u);
+          mbar_expect_tx(&bar_kv_full[stage], (uint32_t)stage_bytes);
+          uint8_t* sK = sRing + stage * stage_bytes;
+          uint8_t* sV = sK + p.katoms * kAtom64;
+          for (int a = 0; a < p.katoms; ++a) {
+            tma_load_4d(sK + a * kAtom64, &p.tmK, &bar_kv_full[stage], a * 64, j * 64, im.kvh, im.b);
+            tma_load_4d(sV + a * kAtom64, &p.tmV, &bar_kv_full[stage], a * 64, j * 64, im.kvh, im.b);
+          }
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc(1u, 0, 0, 128, 64);
+      const uint32_t idesc_pv = umma_idesc(1u, 0, 1, 128, (uint32_t)p.n_hd);
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), ring_addr = smem_u32(sRing);
+      uint32_t blk[2] = {0u, 0u};   // running block counter per tile: S buffer = blk & 1
+      int stage = 0, qi = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
+        const FwdItem im = fwd_item<kTiles>(p, it);
+        mbar_wait(&bar_q_full, (uint32_t)(qi & 1));
+        mbar_wait(&bar_kv_full[stage], phase);
+        tc_fence_after();
+        for (int t = 0; t < kTiles; ++t) {
+          if (im.nblk[t] == 0) continue;
+          const uint32_t buf = blk[t] & 1u;
+          mma_over_hd(tmem + t * 128 + buf * 64, q_addr + t * p.katoms * kAtom128, kAtom128,
+                      ring_addr + stage * stage_bytes, kAtom64, p.ksteps, idesc_s);
+          umma_commit(&bar_s_full[t][buf]);
+        }
+        if (im.n == 1) umma_commit(&bar_q_empty);
+        for (int j = 0; j < im.n; ++j) {
+          if (j + 1 < im.n) {   // the next block's scores first: the softmax warps never wait for the P V product
+            int ns = stage + 1;
+            uint32_t nph = phase;
+            if (ns == stages) {
+              ns = 0;
+              nph ^= 1u;
+            }
+            mbar_wait(&bar_kv_full[ns], nph);
+            tc_fence_after();
+            for (int t = 0; t < kTiles; ++t) {
+              if (j + 1 >= im.nblk[t]) continue;
+              const uint32_t buf = (blk[t] + 1u) & 1u;
+              mma_over_hd(tmem + t * 128 + buf * 64, q_addr + t * p.katoms * kAtom128, kAtom128,
+                          ring_addr + ns * stage_bytes, kAtom64, p.ksteps, idesc_s);
+              umma_commit(&bar_s_full[t][buf]);
+            }
+            if (j + 2 == im.n) umma_commit(&bar_q_empty);   // every S product of this item has been issued
+          }
+          const uint32_t v_addr = ring_addr + stage * stage_bytes + p.katoms * kAtom64;
+          for (int t = 0; t < kTiles; ++t) {
+            if (j >= im.nblk[t]) continue;
+            mbar_wait(&bar_p_full[t], blk[t] & 1u);
+            tc_fence_after();
+            const uint32_t o_tmem = tmem + (kTiles == 2 ? 256u + t * 128u : 128u);
+            mma_over_rows64(o_tmem, p_addr + t * kAtom128, v_addr, idesc_pv, j > 0 ? 1u : 0u);
+            umma_commit(&bar_pv_done[t]);
+            ++blk[t];
+          }
+          umma_commit(&bar_kv_empty[stage]);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ----------------------------------------------------- softmax warpgroup of tile t: one thread = one query row
+    const int t = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t o_tmem = lane_base + (kTiles == 2 ? 256u + t * 128u : 128u);
+    uint8_t* prow = sP + t * kAtom128 + r * 128;
+    const int sw = r & 7;
+    uint32_t cnt = 0;
+    for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+      const FwdItem im = fwd_item<kTiles>(p, it);
+      const int nblk = im.nblk[t];
+      if (nblk == 0) continue;
+      const int b = im.b, h = im.h[t];
+      const int q = im.tile[t] * 128 + r;
+      const bool row_ok = q < p.S;
+      const int bq = (p.bid_q != nullptr && row_ok) ? p.bid_q[(size_t)b * p.S + q] : 0;
+      float m_ref = -INFINITY, l = 0.0f;
+      for (int j = 0; j < nblk; ++j) {
+        const uint32_t buf = cnt & 1u;
+        const uint32_t bits0 = row_bits32(p, b, q, bq, j * 64, lane);
+        const uint32_t bits1 = row_bits32(p, b, q, bq, j * 64 + 32, lane);
+        mbar_wait(&bar_s_full[t][buf], (cnt >> 1) & 1u);
+        tc_fence_after();
+        uint32_t s0[32], s1[32];
+        tmem_ld_32x32(lane_base + t * 128 + buf * 64, s0);
+        tmem_ld_32x32(lane_base + t * 128 + buf * 64 + 32, s1);
+        tmem_ld_wait();
+        float mx = -INFINITY;
+        if (__all_sync(0xffffffffu, (bits0 & bits1) == 0xffffffffu)) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (!((bits0 >> i) & 1u)) s0[i] = 0xff800000u;   // -inf
+            if (!((bits1 >> i) & 1u)) s1[i] = 0xff800000u;
+            mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+          }
+        }
+        const float m_blk = mx * p.sl2;
+        if (j == 0) {
+          m_ref = m_blk;
+        } else {
+          const bool need = m_blk > m_ref + kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {
+            // refresh the reference maximum: O and l shrink by 2^(m_ref - m_new) (rows that do not need it: x1)
+            const float m_new = need ? m_blk : m_ref;
+            const float alpha = need ? ex2f(m_ref - m_new) : 1.0f;
+            mbar_wait(&bar_pv_done[t], (cnt - 1u) & 1u);
+            tc_fence_after();
+            for (int c = 0; c < p.o_chunks; ++c) {
+              uint32_t o[32];
+              tmem_ld_32x32(o_tmem + c * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x32(o_tmem + c * 32, o);
+            }
+            tmem_st_wait();
+            l *= alpha;
+            m_ref = m_new;
+          }
+        }
+        const float m_use = m_ref == -INFINITY ? 0.0f : m_ref;
+        uint32_t pk[32];
+        float sum0 = 0.0f, sum1 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a0 = ex2f(fmaf(__uint_as_float(s0[2 * i]), p.sl2, -m_use));
+          const float a1 = ex2f(fmaf(__uint_as_float(s0[2 * i + 1]), p.sl2, -m_use));
+          const float c0 = ex2f(fmaf(__uint_as_float(s1[2 * i]), p.sl2, -m_use));
+          const float c1 = ex2f(fmaf(__uint_as_float(s1[2 * i + 1]), p.sl2, -m_use));
+          sum0 += a0 + a1;
+          sum1 += c0 + c1;
+          pk[i] = pack2(a0, a1);
+          pk[16 + i] = pack2(c0, c1);
+        }
+        l += sum0 + sum1;
+        if (cnt > 0) mbar_wait(&bar_pv_done[t], (cnt - 1u) & 1u);   // the P buffer's previous reader has retired
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(prow + ((c ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&bar_p_full[t]);
+        ++cnt;
+      }
+      // ---- epilogue: O / l -> bf16 rows, log-sum-exp
+      mbar_wait(&bar_pv_done[t], (cnt - 1u) & 1u);
+      tc_fence_after();
+      const float inv = l > 0.0f ? 1.0f / l : 0.0f;
+      bf16* orow = p.out + (long long)b * p.o_sb + (long long)q * p.o_ld + (long long)h * p.o_sh;
+      for (int c = 0; c < p.o_chunks; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32(o_tmem + c * 32, o);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = c * 32 + g * 8;
+            if (col < p.hd) {
+              uint4 u;
+              u.x = pack2(__uint_as_float(o[g * 8]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+              u.y = pack2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+              u.z = pack2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+              u.w = pack2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+              *reinterpret_cast<uint4*>(orow + col) = u;
+            }
+          }
+        }
+      }
+      if (row_ok && p.lse != nullptr)
+        p.lse[((size_t)b * p.H + h) * p.S + q] = l > 0.0f ? m_ref + log2f(l) : INFINITY;
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// -------------------------------------------------------------------------------------------- backward: dQ
+// smem: Q tile | dO tile | dS [128][64] | ring of (K block | V block).  TMEM: S @0/64, dP @128/192, dQ @256.
+__global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant__ FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_qdo_full, bar_qdo_empty, bar_kv_full[kFaMaxStages], bar_kv_empty[kFaMaxStages];
+  __shared__ uint64_t bar_sdp_full[2], bar_ds_full, bar_ds_empty, bar_dq_full;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sQ = smem;
+  uint8_t* sDO = sQ + p.katoms * kAtom128;
+  uint8_t* sDS = sDO + p.katoms * kAtom128;
+  uint8_t* sRing = sDS + kAtom128;
+  const int stage_bytes = 2 * p.katoms * kAtom64;
+  const int stages = p.stages;
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(&bar_qdo_full, 1);
+    mbar_init(&bar_qdo_empty, 1);
+    for (int i = 0; i < kFaMaxStages; ++i) {
+      mbar_init(&bar_kv_full[i], 1);
+      mbar_init(&bar_kv_empty[i], 1);
+    }
+    mbar_init(&bar_sdp_full[0], 1);
+    mbar_init(&bar_sdp_full[1], 1);
+    mbar_init(&bar_ds_full, 256);
+    mbar_init(&bar_ds_empty, 1);
+    mbar_init(&bar_dq_full, 1);
+    mbar_fence_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+    tma_prefetch_desc(&p.tmDO);
+  }
+  if (warp == 2) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int BH = p.B * p.H;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, qi = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
+        const int pr = it / BH, bh = it - pr * BH;
+        const int b = bh / p.H, h = bh - b * p.H, kvh = h / p.G, tile = p.m_tiles - 1 - pr;
+        const int n = visible_blocks(p, tile);
+        mbar_wait(&bar_qdo_empty, (uint32_t)(qi & 1) ^ 1u);
+        mbar_expect_tx(&bar_qdo_full, (uint32_t)(2 * p.katoms * kAtom128));
+        for (int a = 0; a < p.katoms; ++a) {
+          tma_load_4d(sQ + a * kAtom128, &p.tmQ, &bar_qdo_full, a * 64, tile * 128, h, b);
+          tma_load_4d(sDO + a * kAtom128, &p.tmDO, &bar_qdo_full, a * 64, tile * 128, h, b);
+        }
+        for (int j = 0; j < n; ++j) {
+          mbar_wait(&bar_kv_empty[stage], phase ^ 1u);
+          mbar_expect_tx(&bar_kv_full[stage], (uint32_t)stage_bytes);
+          uint8_t* sK = sRing + stage * stage_bytes;
+          uint8_t* sV = sK + p.katoms * kAtom64;
+          for (int a = 0; a < p.katoms; ++a) {
+            tma_load_4d(sK + a * kAtom64, &p.tmK, &bar_kv_full[stage], a * 64, j * 64, kvh, b);
+            tma_load_4d(sV + a * kAtom64, &p.tmV, &bar_kv_full[stage], a * 64, j * 64, kvh, b);
+          }
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc(1u, 0, 0, 128, 64);
+      const uint32_t idesc_dq = umma_idesc(1u, 0, 1, 128, (uint32_t)p.n_hd);
+      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), ds_addr = smem_u32(sDS), ring_addr = smem_u32(sRing);
+      const bool prefetch = stages >= 2;
+      uint32_t cnt = 0;
+      int stage = 0, qi = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
+        const int pr = it / BH;
+        const int n = visible_blocks(p, p.m_tiles - 1 - pr);
+        mbar_wait(&bar_qdo_full, (uint32_t)(qi & 1));
+        // S and dP of block jn into buffer (cnt_of_that_block & 1), from ring stage st
+        auto issue_sdp = [&](int jn, uint32_t c, int st, uint32_t ph) {
+          mbar_wait(&bar_kv_full[st], ph);
+          tc_fence_after();
+          const uint32_t buf = c & 1u;
+          const uint32_t k_addr = ring_addr + st * stage_bytes;
+          mma_over_hd(tmem + buf * 64, q_addr, kAtom128, k_addr, kAtom64, p.ksteps, idesc_s);
+          mma_over_hd(tmem + 128 + buf * 64, do_addr, kAtom128, k_addr + p.katoms * kAtom64, kAtom64, p.ksteps, idesc_s);
+          umma_commit(&bar_sdp_full[buf]);
+          if (jn + 1 == n) umma_commit(&bar_qdo_empty);
+        };
+        issue_sdp(0, cnt, stage, phase);
+        for (int j = 0; j < n; ++j) {
+          int ns = stage + 1;
+          uint32_t nph = phase;
+          if (ns == stages) {
+            ns = 0;
+            nph ^= 1u;
+          }
+          if (prefetch && j + 1 < n) issue_sdp(j + 1, cnt + 1u, ns, nph);
+          mbar_wait(&bar_ds_full, cnt & 1u);
+          tc_fence_after();
+          mma_over_rows64(tmem + 256, ds_addr, ring_addr + stage * stage_bytes, idesc_dq, j > 0 ? 1u : 0u);
+          umma_commit(&bar_ds_empty);
+          umma_commit(&bar_kv_empty[stage]);
+          if (!prefetch && j + 1 < n) issue_sdp(j + 1, cnt + 1u, ns, nph);
+          stage = ns;
+          phase = nph;
+          ++cnt;
+        }
+        umma_commit(&bar_dq_full);
+      }
+    }
+  } else if (warp >= 4) {
+    // 8 warps: lane quarter = warp & 3, column half = (warp - 4) / 4 of each 64-key block; no row reductions in backward
+    const int quarter = warp & 3, half = (warp - 4) >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    uint8_t* dsrow = sDS + r * 128;
+    const int sw = r & 7;
+    uint32_t cnt = 0;
+    int qi = 0;
+    for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
+      const int pr = it / BH, bh = it - pr * BH;
+      const int b = bh / p.H, h = bh - b * p.H, tile = p.m_tiles - 1 - pr;
+      const int n = visible_blocks(p, tile);
+      const int q = tile * 128 + r;
+      const bool row_ok = q < p.S;
+      const size_t stat = ((size_t)b * p.H + h) * p.S + q;
+      const float L = row_ok ? p.lse[stat] : INFINITY;
+      const float dl = row_ok ? p.delta[stat] : 0.0f;
+      const int bq = (p.bid_q != nullptr && row_ok) ? p.bid_q[(size_t)b * p.S + q] : 0;
+      for (int j = 0; j < n; ++j) {
+        const uint32_t buf = cnt & 1u;
+        const uint32_t bits = row_bits32(p, b, q, bq, j * 64 + half * 32, lane);
+        mbar_wait(&bar_sdp_full[buf], (cnt >> 1) & 1u);
+        tc_fence_after();
+        uint32_t s[32], dp[32];
+        tmem_ld_32x32(lane_base + buf * 64 + half * 32, s);
+        tmem_ld_32x32(lane_base + 128 + buf * 64 + half * 32, dp);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float v[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 2 * i + e;
+            const float pe = ((bits >> c) & 1u) ? ex2f(fmaf(__uint_as_float(s[c]), p.sl2, -L)) : 0.0f;
+            v[e] = pe * (__uint_as_float(dp[c]) - dl) * p.scale;
+          }
+          pk[i] = pack2(v[0], v[1]);
+        }
+        if (cnt > 0) mbar_wait(&bar_ds_empty, (cnt - 1u) & 1u);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(dsrow + (((half * 4 + c) ^ sw) << 4)) =
+              make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&bar_ds_full);
+        ++cnt;
+      }
+      mbar_wait(&bar_dq_full, (uint32_t)(qi & 1));
+      tc_fence_after();
+      bf16* drow = p.dq + (long long)b * p.g_sb + (long long)q * p.g_ld + (long long)h * p.gq_sh;
+      for (int c = half; c < p.o_chunks; c += 2) {
+        uint32_t o[32];
+        tmem_ld_32x32(lane_base + 256 + c * 32, o);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = c * 32 + g * 8;
+            if (col < p.hd) {
+              uint4 u;
+              u.x = pack2(__uint_as_float(o[g * 8]), __uint_as_float(o[g * 8 + 1]));
+              u.y = pack2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
+              u.z = pack2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
+              u.w = pack2(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
+              *reinterpret_cast<uint4*>(drow + col) = u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// --------------------------------------------------------------------------------------- backward: dK and dV
+// Transposed problem: TMEM lanes = the 128 keys of the tile, columns = 64 query rows of a block.
+// smem: K tile | V tile | P^T [128][64] | dS^T [128][64] | ring of (Q block | dO block).
+// TMEM: S^T @0/64, dP^T @128/192, accumulators @256 (mode 0: dV @256, dK @384; mode 1: dV only; mode 2: dK only).
+struct DkvItem {
+  int b, kvh, jt, mode, ib0, nsteps;
+};
+__device__ __forceinline__ DkvItem dkv_item(const FaParams& p, int it) {
+  DkvItem r;
+  const int per = p.B * p.KVH * p.n_modes;
+  r.jt = it / per;                       // key tile 0 sees the most query blocks under a causal mask: first
+  int x = it - r.jt * per;
+  r.mode = p.n_modes == 2 ? 1 + (x % 2) : 0;
+  x /= p.n_modes;
+  r.b = x / p.KVH;
+  r.kvh = x - r.b * p.KVH;
+  r.ib0 = p.causal ? 2 * r.jt : 0;
+  r.nsteps = p.G * (p.n_qblk - r.ib0);
+  return r;
+}
+
+__global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant__ FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_kv_full, bar_kv_empty, bar_ring_full[kFaMaxStages], bar_ring_empty[kFaMaxStages];
+  __shared__ uint64_t bar_sdp_full[2], bar_pds_full, bar_pds_empty, bar_acc_full;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float stats[8][3][32];   // per softmax warp: lse, delta, block id of its 32 query columns
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + p.katoms * kAtom128;
+  uint8_t* sPT = sV + p.katoms * kAtom128;
+  uint8_t* sDST = p.n_modes == 2 ? sPT : sPT + kAtom128;   // head_dim > 128: an item needs only one of the two
+  uint8_t* sRing = sDST + kAtom128;
+  const int stage_bytes = 2 * p.katoms * kAtom64;
+  const int stages = p.stages;
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(&bar_kv_full, 1);
+    mbar_init(&bar_kv_empty, 1);
+    for (int i = 0; i < kFaMaxStages; ++i) {
+      mbar_init(&bar_ring_full[i], 1);
+      mbar_init(&bar_ring_empty[i], 1);
+    }
+    mbar_init(&bar_sdp_full[0], 1);
+    mbar_init(&bar_sdp_full[1], 1);
+    mbar_init(&bar_pds_full, 256);
+    mbar_init(&bar_pds_empty, 1);
+    mbar_init(&bar_acc_full, 1);
+    mbar_fence_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+    tma_prefetch_desc(&p.tmDO);
+  }
+  if (warp == 2) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, qi = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
+        const DkvItem im = dkv_item(p, it);
+        mbar_wait(&bar_kv_empty, (uint32_t)(qi & 1) ^ 1u);
+        const bool need_v = im.mode != 1;
+        mbar_expect_tx(&bar_kv_full, (uint32_t)((need_v ? 2 : 1) * p.katoms * kAtom128));
+        for (int a = 0; a < p.katoms; ++a) {
+          tma_load_4d(sK + a * kAtom128, &p.tmK, &bar_kv_full, a * 64, im.jt * 128, im.kvh, im.b);
+          if (need_v) tma_load_4d(sV + a * kAtom128, &p.tmV, &bar_kv_full, a * 64, im.jt * 128, im.kvh, im.b);
+        }
+        for (int hh = 0; hh < p.G; ++hh) {
+          const int h = im.kvh * p.G + hh;
+          for (int ib = im.ib0; ib < p.n_qblk; ++ib) {
+            mbar_wait(&bar_ring_empty[stage], phase ^ 1u);
+            mbar_expect_tx(&bar_ring_full[stage], (uint32_t)stage_bytes);
+            uint8_t* sQb = sRing + stage * stage_bytes;
+            uint8_t* sDOb = sQb + p.katoms * kAtom64;
+            for (int a = 0; a < p.katoms; ++a) {
+              tma_load_4d(sQb + a * kAtom64, &p.tmQ, &bar_ring_full[stage], a * 64, ib * 64, h, im.b);
+              tma_load_4d(sDOb + a * kAtom64, &p.tmDO, &bar_ring_full[stage], a * 64, ib * 64, h, im.b);
+            }
+            if (++stage == stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_st = umma_idesc(1u, 0, 0, 128, 64);
+      const uint32_t idesc_acc = umma_idesc(1u, 0, 1, 128, (uint32_t)p.n_hd);
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
+      const uint32_t ring_addr = smem_u32(sRing);
+      const bool prefetch = stages >= 2;
+      uint32_t cnt = 0;
+      int stage = 0, qi = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
+        const DkvItem im = dkv_item(p, it);
+        const int n = im.nsteps;
+        const bool do_dv = im.mode != 2, do_dk = im.mode != 1;
+        const uint32_t dv_tmem = tmem + 256, dk_tmem = tmem + (im.mode == 0 ? 384u : 256u);
+        mbar_wait(&bar_kv_full, (uint32_t)(qi & 1));
+        auto issue_sdp = [&](int sn, uint32_t c, int st, uint32_t ph) {
+          mbar_wait(&bar_ring_full[st], ph);
+          tc_fence_after();
+          const uint32_t buf = c & 1u;
+          const uint32_t qb_addr = ring_addr + st * stage_bytes;
+          mma_over_hd(tmem + buf * 64, k_addr, kAtom128, qb_addr, kAtom64, p.ksteps, idesc_st);
+          if (do_dk)
+            mma_over_hd(tmem + 128 + buf * 64, v_addr, kAtom128, qb_addr + p.katoms * kAtom64, kAtom64, p.ksteps,
+                        idesc_st);
+          umma_commit(&bar_sdp_full[buf]);
+          if (sn + 1 == n) umma_commit(&bar_kv_empty);
+        };
+        issue_sdp(0, cnt, stage, phase);
+        for (int s = 0; s < n; ++s) {
+          int ns = stage + 1;
+          uint32_t nph = phase;
+          if (ns == stages) {
+            ns = 0;
+            nph ^= 1u;
+          }
+          if (prefetch && s + 1 < n) issue_sdp(s + 1, cnt + 1u, ns, nph);
+          mbar_wait(&bar_pds_full, cnt & 1u);
+          tc_fence_after();
+          const uint32_t qb_addr = ring_addr + stage * stage_bytes;
+          if (do_dv) mma_over_rows64(dv_tmem, pt_addr, qb_addr + p.katoms * kAtom64, idesc_acc, s > 0 ? 1u : 0u);
+          if (do_dk) mma_over_rows64(dk_tmem, dst_addr, qb_addr, idesc_acc, s > 0 ? 1u : 0u);
+          umma_commit(&bar_pds_empty);
+          umma_commit(&bar_ring_empty[stage]);
+          if (!prefetch && s + 1 < n) issue_sdp(s + 1, cnt + 1u, ns, nph);
+          stage = ns;
+          phase = nph;
+          ++cnt;
+        }
+        umma_commit(&bar_acc_full);
+      }
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3, half = (warp - 4) >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    float (*st)[32] = stats[warp - 4];
+    uint8_t* ptrow = sPT + r * 128;
+    uint8_t* dsrow = sDST + r * 128;
+    const int sw = r & 7;
+    uint32_t cnt = 0;
+    int qi = 0;
+    for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
+      const DkvItem im = dkv_item(p, it);
+      const bool do_dv = im.mode != 2, do_dk = im.mode != 1;
+      const int b = im.b;
+      const int key = im.jt * 128 + r;
+      const bool key_in = key < p.S;
+      const bool key_ok = key_in && (p.keymask == nullptr || p.keymask[(size_t)b * p.S + key] != 0);
+      const int bk = (p.bid_k != nullptr && key_in) ? p.bid_k[(size_t)b * p.S + key] : 0;
+      for (int hh = 0; hh < p.G; ++hh) {
+        const int h = im.kvh * p.G + hh;
+        for (int ib = im.ib0; ib < p.n_qblk; ++ib) {
+          const uint32_t buf = cnt & 1u;
+          const int q0 = ib * 64 + half * 32;
+          {
+            const int qq = q0 + lane;
+            const bool qok = qq < p.S;
+            const size_t stat = ((size_t)b * p.H + h) * p.S + qq;
+            __syncwarp();
+            st[0][lane] = qok ? p.lse[stat] : INFINITY;
+            st[1][lane] = qok ? p.delta[stat] : 0.0f;
+            st[2][lane] = __int_as_float((p.bid_q != nullptr && qok) ? p.bid_q[(size_t)b * p.S + qq] : 0);
+            __syncwarp();
+          }
+          uint32_t bits = key_ok ? 0xffffffffu : 0u;
+          if (p.causal) bits &= ~low_mask(key - q0);      // column c is visible iff q0 + c >= key
+          if (p.bid_k != nullptr) {
+            uint32_t w2 = 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (bk <= __float_as_int(st[2][c])) w2 |= 1u << c;
+            bits &= w2;
+          }
+          mbar_wait(&bar_sdp_full[buf], (cnt >> 1) & 1u);
+          tc_fence_after();
+          uint32_t s[32], dp[32];
+          tmem_ld_32x32(lane_base + buf * 64 + half * 32, s);
+          if (do_dk) tmem_ld_32x32(lane_base + 128 + buf * 64 + half * 32, dp);
+          tmem_ld_wait();
+          uint32_t pp[16], pd[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float pv[2], dv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = 2 * i + e;
+              pv[e] = ((bits >> c) & 1u) ? ex2f(fmaf(__uint_as_float(s[c]), p.sl2, -st[0][c])) : 0.0f;
+              dv[e] = do_dk ? pv[e] * (__uint_as_float(dp[c]) - st[1][c]) * p.scale : 0.0f;
+            }
+            pp[i] = pack2(pv[0], pv[1]);
+            pd[i] = pack2(dv[0], dv[1]);
+          }
+          if (cnt > 0) mbar_wait(&bar_pds_empty, (cnt - 1u) & 1u);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int off = ((half * 4 + c) ^ sw) << 4;
+            if (do_dv) *reinterpret_cast<uint4*>(ptrow + off) = make_uint4(pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
+            if (do_dk) *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(pd[4 * c], pd[4 * c + 1], pd[4 * c + 2], pd[4 * c + 3]);
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(&bar_pds_full);
+          ++cnt;
+        }
+      }
+      // ---- epilogue: the accumulated dV / dK rows of this key tile
+      mbar_wait(&bar_acc_full, (uint32_t)(qi & 1));
+      tc_fence_after();
+      for (int which = 0; which < 2; ++which) {
+        if (which == 0 ? !do_dv : !do_dk) continue;
+        const uint32_t acc = lane_base + (which == 0 ? 256u : (im.mode == 0 ? 384u : 256u));
+        bf16* drow = (which == 0 ? p.dv : p.dk) + (long long)b * p.g_sb + (long long)key * p.g_ld +
+                     (long long)im.kvh * p.gkv_sh;
+        for (int c = half; c < p.o_chunks; c += 2) {
+          uint32_t o[32];
+          tmem_ld_32x32(acc + c * 32, o);
+          tmem_ld_wait();
+          if (key_in) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = c * 32 + g * 8;
+              if (col < p.hd) {
+                uint4 u;
+                u.x = pack2(__uint_as_float(o[g * 8]), __uint_as_float(o[g * 8 + 1]));
+                u.y = pack2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
+                u.z = pack2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
+                u.w = pack2(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
+                *reinterpret_cast<uint4*>(drow + col) = u;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// delta[b, h, q] = sum_d dO[b, q, h, d] * O[b, q, h, d]: one warp per (b, q, h) row
+__global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
+                                  int B, int H, int S, int hd, long long ld, long long sh, long long sb) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= (long long)B * S * H) return;
+  const int h = (int)(row % H);
+  const long long bq = row / H;
+  const int q = (int)(bq % S), b = (int)(bq / S);
+  const long long off = (long long)b * sb + (long long)q * ld + (long long)h * sh;
+  float acc = 0.0f;
+  for (int c = lane * 8; c < hd; c += 256) {
+    const uint4 a = *reinterpret_cast<const uint4*>(o + off + c);
+    const uint4 d = *reinterpret_cast<const uint4*>(dout + off + c);
+    const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&d);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = __bfloat1622float2(ah[i]), y = __bfloat1622float2(dh[i]);
+      acc += x.x * y.x + x.y * y.y;
+    }
+  }
+#pragma unroll
+  for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+  if (lane == 0) delta[((size_t)b * H + h) * S + q] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFnFa)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// (hd, S, heads, B) view with element strides (1, ld, s_head, s_batch); box = (64, box_rows): one 64-column atom
+static int encode_rows(CUtensorMap* m, const void* ptr, uint64_t hd, uint64_t S, uint64_t heads, uint64_t B, int64_t ld,
+                       int64_t s_head, int64_t s_batch, uint32_t box_rows, const char* what) {
+  static EncodeTiledFnFa fn = nullptr;
+  if (fn == nullptr) {
+    void* pfn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &pfn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFnFa>(pfn);
+  }
+  B200_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {hd, S, heads, B};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)s_head * 2, (cuuint64_t)s_batch * 2};
+  cuuint32_t box[4] = {64, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 3; ++i)
+    B200_CHECK(strides[i] % 16 == 0 && strides[i] > 0, "%s: stride %d not a positive multiple of 16 bytes", what, i + 1);
+  B200_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "%s: base pointer not 16-byte aligned", what);
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
+  return 0;
+}
+
+constexpr int kSmemBudget = 227 * 1024 - 4096;   // dynamic bytes available next to the static barriers / stats
+
+static int fill_common(FaParams& kp, int64_t B, int64_t H, int64_t KVH, int64_t S, int64_t hd, float scale, int causal,
+                       const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k) {
+  B200_CHECK(hd % 8 == 0 && hd >= 16 && hd <= 256, "flash_attn: head_dim=%lld unsupported (multiple of 8, <= 256)",
+             (long long)hd);
+  B200_CHECK(B > 0 && S > 0 && H > 0 && KVH > 0 && H % KVH == 0, "flash_attn: bad geometry");
+  B200_CHECK((bid_q == nullptr) == (bid_k == nullptr), "flash_attn: bid_q and bid_k go together");
+  B200_CHECK(B * H * ceil_div(S, 64) < (1ll << 30), "flash_attn: problem too large");
+  memset(&kp, 0, sizeof(kp));
+  kp.B = (int)B;
+  kp.H = (int)H;
+  kp.KVH = (int)KVH;
+  kp.G = (int)(H / KVH);
+  kp.S = (int)S;
+  kp.hd = (int)hd;
+  kp.katoms = (int)ceil_div(hd, 64);
+  kp.ksteps = (int)ceil_div(hd, 16);
+  kp.n_hd = (int)ceil_div(hd, 16) * 16;
+  kp.o_chunks = (int)ceil_div(hd, 32);
+  kp.m_tiles = (int)ceil_div(S, 128);
+  kp.n_qblk = (int)ceil_div(S, 64);
+  kp.causal = causal;
+  kp.scale = scale;
+  kp.sl2 = scale * 1.4426950408889634f;
+  kp.keymask = keymask;
+  kp.bid_q = bid_q;
+  kp.bid_k = bid_k;
+  kp.n_modes = 1;
+  return 0;
+}
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+  B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B,
+                                   int64_t H, int64_t KVH, int64_t S, int64_t head_dim, int64_t qkv_ld,
+                                   int64_t qkv_s_head, int64_t qkv_s_batch, int64_t o_ld, int64_t o_s_head,
+                                   int64_t o_s_batch, float scale, int causal, const uint8_t* keymask,
+                                   const int32_t* bid_q, const int32_t* bid_k, void* stream) {
+  FaParams kp;
+  if (fill_common(kp, B, H, KVH, S, head_dim, scale, causal, keymask, bid_q, bid_k)) return 1;
+  B200_CHECK(o_ld % 8 == 0 && o_s_head % 8 == 0 && o_s_batch % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "flash_attn_fwd: output rows must be 16-byte aligned");
+  if (encode_rows(&kp.tmQ, q, head_dim, S, H, B, qkv_ld, qkv_s_head, qkv_s_batch, 128, "flash Q")) return 1;
+  if (encode_rows(&kp.tmK, k, head_dim, S, KVH, B, qkv_ld, qkv_s_head, qkv_s_batch, 64, "flash K")) return 1;
+  if (encode_rows(&kp.tmV, v, head_dim, S, KVH, B, qkv_ld, qkv_s_head, qkv_s_batch, 64, "flash V")) return 1;
+  kp.out = (bf16*)out;
+  kp.lse = lse;
+  kp.o_ld = o_ld;
+  kp.o_sh = o_s_head;
+  kp.o_sb = o_s_batch;
+  const int tiles = head_dim <= 128 ? 2 : 1;
+  const int fixed = tiles * kp.katoms * kAtom128 + tiles * kAtom128;
+  const int stage_bytes = 2 * kp.katoms * kAtom64;
+  int stages = (kSmemBudget - 1024 - fixed) / stage_bytes;
+  if (stages > kFaMaxStages) stages = kFaMaxStages;
+  B200_CHECK(stages >= 2, "flash_attn_fwd: shared memory budget exceeded");
+  kp.stages = stages;
+  const int smem = 1024 + fixed + stages * stage_bytes;
+  if (tiles == 2) {
+    kp.n_items = (int)(B * KVH * ceil_div((int64_t)kp.G * kp.m_tiles, 2));
+    if (set_smem(flash_fwd_kernel<2>, smem)) return 1;
+    const unsigned grid = (unsigned)(kp.n_items < num_sms() ? kp.n_items : num_sms());
+    flash_fwd_kernel<2><<<grid, 384, smem, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
+  } else {
+    kp.n_items = (int)(B * H * kp.m_tiles);
+    if (set_smem(flash_fwd_kernel<1>, smem)) return 1;
+    const unsigned grid = (unsigned)(kp.n_items < num_sms() ? kp.n_items : num_sms());
+    flash_fwd_kernel<1><<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
+  }
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                                   const float* lse, float* delta, void* dq, void* dk, void* dv, int64_t B, int64_t H,
+                                   int64_t KVH, int64_t S, int64_t head_dim, int64_t qkv_ld, int64_t qkv_s_head,
+                                   int64_t qkv_s_batch, int64_t o_ld, int64_t o_s_head, int64_t o_s_batch,
+                                   int64_t g_ld, int64_t g_s_head, int64_t g_s_batch, float scale, int causal,
+                                   const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FaParams kp;
+  if (fill_common(kp, B, H, KVH, S, head_dim, scale, causal, keymask, bid_q, bid_k)) return 1;
+  B200_CHECK(lse != nullptr && delta != nullptr, "flash_attn_bwd: lse and the delta workspace are required");
+  B200_CHECK(o_ld % 8 == 0 && o_s_head % 8 == 0 && o_s_batch % 8 == 0 && g_ld % 8 == 0 && g_s_head % 8 == 0 &&
+                 g_s_batch % 8 == 0,
+             "flash_attn_bwd: rows must be 16-byte aligned");
+  B200_CHECK(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dq) |
+               reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 15) == 0,
+             "flash_attn_bwd: pointers must be 16-byte aligned");
+  // 1. delta = rowsum(dO * O)
+  {
+    const long long rows = (long long)B * S * H;
+    const int warps = 8;
+    attn_delta_kernel<<<(unsigned)ceil_div(rows, warps), warps * 32, 0, stream>>>(
+        (const bf16*)out, (const bf16*)dout, delta, (int)B, (int)H, (int)S, (int)head_dim, o_ld, o_s_head, o_s_batch);
+    B200_LAUNCH_OK();
+  }
+  kp.lse = const_cast<float*>(lse);
+  kp.delta = delta;
+  kp.dq = (bf16*)dq;
+  kp.dk = (bf16*)dk;
+  kp.dv = (bf16*)dv;
+  kp.g_ld = g_ld;
+  kp.gq_sh = g_s_head;
+  kp.gkv_sh = g_s_head;
+  kp.g_sb = g_s_batch;
+  const int stage_bytes = 2 * kp.katoms * kAtom64;
+  // 2. dQ: CTA = (b, h, query tile)
+  {
+    FaParams a = kp;
+    if (encode_rows(&a.tmQ, q, head_dim, S, H, B, qkv_ld, qkv_s_head, qkv_s_batch, 128, "flash dq Q")) return 1;
+    if (encode_rows(&a.tmDO, dout, head_dim, S, H, B, o_ld, o_s_head, o_s_batch, 128, "flash dq dO")) return 1;
+    if (encode_rows(&a.tmK, k, head_dim, S, KVH, B, qkv_ld, qkv_s_head, qkv_s_batch, 64, "flash dq K")) return 1;
+    if (encode_rows(&a.tmV, v, head_dim, S, KVH, B, qkv_ld, qkv_s_head, qkv_s_batch, 64, "flash dq V")) return 1;
+    const int fixed = 2 * a.katoms * kAtom128 + kAtom128;
+    int stages = (kSmemBudget - 1024 - fixed) / stage_bytes;
+    if (stages > kFaMaxStages) stages = kFaMaxStages;
+    B200_CHECK(stages >= 1, "flash_attn_bwd(dq): shared memory budget exceeded");
+    a.stages = stages;
+    a.n_items = (int)(B * H * a.m_tiles);
+    const int smem = 1024 + fixed + stages * stage_bytes;
+    if (set_smem(flash_dq_kernel, smem)) return 1;
+    const unsigned grid = (unsigned)(a.n_items < num_sms() ? a.n_items : num_sms());
+    flash_dq_kernel<<<grid, 384, smem, stream>>>(a);
+    B200_LAUNCH_OK();
+  }
+  // 3. dK, dV: CTA = (b, kv head, 128-key tile [, dV | dK])
+  {
+    FaParams a = kp;
+    if (encode_rows(&a.tmQ, q, head_dim, S, H, B, qkv_ld, qkv_s_head, qkv_s_batch, 64, "flash dkv Q")) return 1;
+    if (encode_rows(&a.tmDO, dout, head_dim, S, H, B, o_ld, o_s_head, o_s_batch, 64, "flash dkv dO")) return 1;
+    if (encode_rows(&a.tmK, k, head_dim, S, KVH, B, qkv_ld, qkv_s_head, qkv_s_batch, 128, "flash dkv K")) return 1;
+    if (encode_rows(&a.tmV, v, head_dim, S, KVH, B, qkv_ld, qkv_s_head, qkv_s_batch, 128, "flash dkv V")) return 1;
+    a.n_modes = head_dim > 128 ? 2 : 1;
+    const int fixed = 2 * a.katoms * kAtom128 + (a.n_modes == 2 ? 1 : 2) * kAtom128;
+    int stages = (kSmemBudget - 1024 - fixed) / stage_bytes;
+    if (stages > kFaMaxStages) stages = kFaMaxStages;
+    B200_CHECK(stages >= 1, "flash_attn_bwd(dkv): shared memory budget exceeded");
+    a.stages = stages;
+    a.n_items = (int)(B * KVH * a.m_tiles * a.n_modes);
+    const int smem = 1024 + fixed + stages * stage_bytes;
+    if (set_smem(flash_dkv_kernel, smem)) return 1;
+    const unsigned grid = (unsigned)(a.n_items < num_sms() ? a.n_items : num_sms());
+    flash_dkv_kernel<<<grid, 384, smem, stream>>>(a);
+    B200_LAUNCH_OK();
+  }
+  return 0;
+}

@@ -213,7 +213,7 @@ def block_backward(store: ParamStore, dy: torch.Tensor, x2d: torch.Tensor, bw: B
     linear_wgrad(store, dx1, s["attn"], bw.o)
     dattn = linear_dgrad(dx1, bw.o)
     dqkv = ops.attention_bwd(dattn.view(env.B, env.S, -1), s["qkv"].view(env.B, env.S, -1), s["probs"], s["sh"],
-                             causal=env.causal)
+                             causal=env.causal, out=s["attn"], keymask=env.keymask, bid_q=env.bid, bid_k=env.bid)
     dqkv2d = dqkv.view(x2d.shape[0], -1)
     if c.rope:
         ops.rope_(dqkv2d, env.pos, env.cos, env.sin, c.heads + c.kv_heads, c.head_dim, inverse=True)

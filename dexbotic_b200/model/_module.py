@@ -68,6 +68,37 @@ class B200Module(nn.Module):
         if name == "model_engine" and "model" in self._modules:
             self._modules["model"].__dict__["_engine"] = value
 
+    # ------------------------------------------------------------------ dtype / device (reference: torch_dtype=bf16)
+    @property
+    def dtype(self) -> torch.dtype:
+        """The compute dtype, as the reference's `model.dtype` reads it after `from_pretrained(torch_dtype=bfloat16)`
+        (cogact_exp.py:145-177 casts the image tensor with it).  Storage stays fp32 master + bf16 shadow."""
+        return torch.bfloat16
+
+    @property
+    def device(self) -> torch.device:
+        return self.store.device
+
+    def _apply(self, fn, recurse: bool = True):
+        """`model.to(torch.bfloat16)`, `.half()`, `.float()`, `.cuda(1)` would rebind every Parameter to a fresh tensor
+        that is no longer a view of the ParamStore master buffer: the kernels would keep training the store while
+        state_dict() / save_pretrained() serialise stale copies.  Dtype requests are already satisfied (bf16 compute
+        copies are maintained by the store), so a conversion that changes nothing is a no-op and anything else is an
+        error instead of a silent detach."""
+        store = self.__dict__.get("store")
+        if store is None:
+            return super()._apply(fn, recurse)
+        probe = torch.empty(0, device=store.device, dtype=torch.float32)
+        res = fn(probe)
+        if res.device != probe.device:
+            raise RuntimeError(
+                f"{type(self).__name__}: moving the model ({probe.device} -> {res.device}) would detach the parameters "
+                "from the flat ParamStore buffers; construct it with device=... instead")
+        return self          # dtype casts: the master stays fp32, the kernels read the store's bf16 shadow
+
+    def to(self, *args, **kwargs):
+        return self._apply(lambda t: t.to(*args, **kwargs))
+
     def state_dict(self, *args, **kwargs):
         self.store.wait_all_params()           # an overlapped optimizer step may still be writing the master buffer
         return super().state_dict(*args, **kwargs)
@@ -139,6 +170,11 @@ class B200Module(nn.Module):
         d = Path(pretrained_model_name_or_path)
         cfg_dict = json.loads((d / "config.json").read_text())
         cfg_dict.pop("model_type", None)
+        # loader arguments HF accepts but that do not describe the model (the reference passes torch_dtype=bfloat16)
+        for k in ("torch_dtype", "dtype", "device_map", "low_cpu_mem_usage", "attn_implementation", "trust_remote_code",
+                  "use_safetensors", "cache_dir", "local_files_only", "revision", "token"):
+            config_overrides.pop(k, None)
+        cfg_dict.pop("torch_dtype", None)
         cfg_dict.update(config_overrides)
         config = cls.config_class(**{k: v for k, v in cfg_dict.items() if k not in ("architectures", "transformers_version")})
         model = cls(config, device=device)

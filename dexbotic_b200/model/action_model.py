@@ -37,7 +37,7 @@ def action_head_specs(model_type: str, token_size: int, action_dim: int, chunk_s
     g, c = "action_head", "fp32"
     T = chunk_size - 1 + 2                                         # future_action_window_size + 2 (dit.py:228-236)
     P = lambda n, s, **k: ParamSpec(prefix + n, s, g, c, trainable=trainable, **k)  # noqa: E731
-    sp = [P("positional_embedding", (T, w), no_decay=True)]
+    sp = [P("positional_embedding", (T, w))]
     if per_token_size is None:
         # history_embedder is built but never called (dit.py:205-207 "Action history is not used now")
         sp += [ParamSpec(prefix + "history_embedder.linear.weight", (w, action_dim), g, c, trainable=False),
@@ -47,7 +47,7 @@ def action_head_specs(model_type: str, token_size: int, action_dim: int, chunk_s
     sp += [P("x_embedder.linear.weight", (w, action_dim)), P("x_embedder.linear.bias", (w,)),
           P("t_embedder.mlp.0.weight", (w, 256)), P("t_embedder.mlp.0.bias", (w,)),
           P("t_embedder.mlp.2.weight", (w, w)), P("t_embedder.mlp.2.bias", (w,)),
-          P("z_embedder.uncondition", (1, token_size), no_decay=True),
+          P("z_embedder.uncondition", (1, token_size)),
           P("z_embedder.linear.weight", (w, token_size)), P("z_embedder.linear.bias", (w,))]
     for i in range(depth):
         q = f"blocks.{i}."

@@ -199,7 +199,7 @@ def oft_linear_head_specs(d: int, action_dim: int, chunk: int, use_proprio: bool
     g, c = "action_head", "fp32"
     P = lambda n, s, **k: ParamSpec(prefix + n, s, g, c, trainable=trainable, **k)  # noqa: E731
     din = d * action_dim
-    sp = [P("action_query", (1, chunk * action_dim, d), no_decay=True),
+    sp = [P("action_query", (1, chunk * action_dim, d)),
           P("model.layer_norm1.weight", (din,)), P("model.layer_norm1.bias", (din,)),
           P("model.fc1.weight", (d, din)), P("model.fc1.bias", (d,))]
     for i in range(2):

@@ -317,13 +317,13 @@ class MoTLayerFn(torch.autograd.Function):
             ctx.save_for_backward(x_p, x_s, mod1, mod2)
         else:
             ctx.save_for_backward(x_p, x_s)
-        ctx.misc = (streams, env, store, tail, joint, probs, st1, keep, sh)
+        ctx.misc = (streams, env, store, tail, joint, probs, st1, keep, sh, attn)
         return outs[0], outs[1]
 
     @staticmethod
     def backward(ctx, dy_p, dy_s):
         x_p, x_s, *mods = ctx.saved_tensors
-        streams, env, store, tail, joint, probs, st1, keep, sh = ctx.misc
+        streams, env, store, tail, joint, probs, st1, keep, sh, attn = ctx.misc
         ctx.misc = None
         B, (Sp, Ss) = env.B, env.lens
         S = Sp + Ss
@@ -370,7 +370,7 @@ class MoTLayerFn(torch.autograd.Function):
             ops.copy3d_(da, dattn, B, n, C, n * C, C, S * C, C, dst_off=off * C)
             dx1s.append((dx1, dgate1) if ad is not None else dx1)
             off += n
-        dqkv = ops.attention_bwd(dattn, joint, probs, sh)
+        dqkv = ops.attention_bwd(dattn, joint, probs, sh, out=attn, keymask=env.keymask, bid_q=env.bid, bid_k=env.bid)
         ops.rope_(dqkv, env.pos, env.cos, env.sin, env.heads + env.kv_heads, env.head_dim, inverse=True)
         dxs = []
         off = 0

@@ -188,13 +188,57 @@ def attn_scores(a_ptr: int, a_ld: int, a_s_head: int, a_s_batch: int, b_ptr: int
     return out
 
 
+def _flash_ok(qkv: torch.Tensor, sh: AttnShape) -> bool:
+    import os
+    return (qkv.dtype == torch.bfloat16 and sh.hd % 8 == 0 and 16 <= sh.hd <= 256 and qkv.is_contiguous() and
+            os.environ.get("B200_FLASH_ATTN", "1") != "0")
+
+
+def flash_attention_fwd(qkv: torch.Tensor, sh: AttnShape, *, keymask=None, bid_q=None, bid_k=None, causal: bool = False,
+                        out: Optional[torch.Tensor] = None):
+    """Flash attention over packed qkv: returns (out [B,S,H*hd], lse [B,H,S] fp32, log2 domain).  No P tensor."""
+    _cuda(qkv, keymask, bid_q, bid_k)
+    B, S, H, KVH, hd, W = sh.B, sh.S, sh.H, sh.KVH, sh.hd, sh.W
+    if out is None:
+        out = torch.empty((B, S, H * hd), device=qkv.device, dtype=qkv.dtype)
+    lse = torch.empty((B, H, S), device=qkv.device, dtype=torch.float32)
+    q, k, v = _qkv_ptrs(qkv, sh)
+    _lib.check(_lib.load().b200_flash_attn_fwd(q, k, v, out.data_ptr(), lse.data_ptr(), B, H, KVH, S, hd, W, hd, S * W,
+                                               H * hd, hd, S * H * hd, float(sh.scale), int(causal), _p(keymask),
+                                               _p(bid_q), _p(bid_k), _stream()), "flash_attn_fwd")
+    return out, lse
+
+
+def flash_attention_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, sh: AttnShape, *,
+                        keymask=None, bid_q=None, bid_k=None, causal: bool = False,
+                        dqkv: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Gradient of flash_attention_fwd w.r.t. the packed qkv buffer (every element of dqkv is written)."""
+    _cuda(dout, qkv, out, lse)
+    B, S, H, KVH, hd, W = sh.B, sh.S, sh.H, sh.KVH, sh.hd, sh.W
+    assert dout.is_contiguous() and dout.shape == (B, S, H * hd) and out.is_contiguous() and out.shape == dout.shape
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    delta = torch.empty((B, H, S), device=qkv.device, dtype=torch.float32)
+    q, k, v = _qkv_ptrs(qkv, sh)
+    dq, dk, dv = _qkv_ptrs(dqkv, sh)
+    _lib.check(_lib.load().b200_flash_attn_bwd(q, k, v, out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                                               delta.data_ptr(), dq, dk, dv, B, H, KVH, S, hd, W, hd, S * W, H * hd, hd,
+                                               S * H * hd, W, hd, S * W, float(sh.scale), int(causal), _p(keymask),
+                                               _p(bid_q), _p(bid_k), _stream()), "flash_attn_bwd")
+    return dqkv
+
+
 def attention_fwd(qkv: torch.Tensor, sh: AttnShape, *, keymask: Optional[torch.Tensor] = None,
                   bid_q: Optional[torch.Tensor] = None, bid_k: Optional[torch.Tensor] = None, causal: bool = False,
                   scores: Optional[torch.Tensor] = None, probs: Optional[torch.Tensor] = None,
                   out: Optional[torch.Tensor] = None):
-    """softmax(mask(Q K^T / sqrt(hd))) V over packed qkv (RoPE already applied).  Returns (out[B,S,H*hd], probs)."""
+    """softmax(mask(Q K^T / sqrt(hd))) V over packed qkv (RoPE already applied).  Returns (out[B,S,H*hd], saved):
+    saved is the fp32 log-sum-exp [B,H,S] on the flash path (bf16), the probabilities [B,H,S,ld_p] otherwise (fp32
+    action heads); attention_bwd takes either."""
     _cuda(qkv)
     B, S, H, KVH, hd, G, W = sh.B, sh.S, sh.H, sh.KVH, sh.hd, sh.G, sh.W
+    if _flash_ok(qkv, sh):
+        return flash_attention_fwd(qkv, sh, keymask=keymask, bid_q=bid_q, bid_k=bid_k, causal=causal, out=out)
     dt = _dt(qkv)
     dev = qkv.device
     if probs is None:
@@ -254,9 +298,16 @@ def attention_cross(q_packed: torch.Tensor, kv: torch.Tensor, B: int, Sq: int, S
 
 def attention_bwd(dout: torch.Tensor, qkv: torch.Tensor, probs: torch.Tensor, sh: AttnShape, *, causal: bool = False,
                   dqkv: Optional[torch.Tensor] = None, scratch: Optional[torch.Tensor] = None,
-                  dprobs: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Gradient of attention_fwd w.r.t. the packed qkv buffer (before the inverse RoPE)."""
+                  dprobs: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, keymask=None,
+                  bid_q=None, bid_k=None) -> torch.Tensor:
+    """Gradient of attention_fwd w.r.t. the packed qkv buffer (before the inverse RoPE).  `probs` is what
+    attention_fwd returned second: the log-sum-exp (flash path: `out` and the mask arguments are then required, P is
+    recomputed) or the probabilities."""
     _cuda(dout, qkv, probs)
+    if probs.dim() == 3:
+        assert out is not None, "attention_bwd: the flash path needs the forward output"
+        return flash_attention_bwd(dout, qkv, out.view(sh.B, sh.S, -1), probs, sh, keymask=keymask, bid_q=bid_q,
+                                   bid_k=bid_k, causal=causal, dqkv=dqkv)
     B, S, H, KVH, hd, G, W = sh.B, sh.S, sh.H, sh.KVH, sh.hd, sh.G, sh.W
     dt = _dt(qkv)
     dev = qkv.device

@@ -30,7 +30,7 @@ class ParamSpec:
     compute: str = "bf16"         # dtype the kernels read: "bf16" (region A) or "fp32" (region B)
     fuse: Optional[str] = None    # consecutive specs with the same tag are packed without padding
     trainable: bool = True
-    no_decay: Optional[bool] = None   # default: 1-D tensors and biases are not decayed
+    no_decay: Optional[bool] = None   # default: the reference's rule (LayerNorm children and *bias* names)
 
     @property
     def numel(self) -> int:
@@ -46,6 +46,21 @@ class _Slot:
     region: str
     offset: int       # element offset inside the region
     g_offset: int     # element offset in the global (A then B) fp32 master / moment buffers
+
+
+# nn.LayerNorm children of the reference's models, by module name (RMSNorm modules — input_layernorm,
+# post_attention_layernorm, norm — are NOT nn.LayerNorm and are therefore decayed by base_exp.py:102-103)
+_LAYERNORM_PARENTS = {"layer_norm1", "layer_norm2", "pre_layrnorm", "post_layernorm", "layernorm", "attn_norm",
+                      "ffn_norm", "norm3"}
+
+
+def _is_layernorm_weight(name: str) -> bool:
+    parts = name.split(".")
+    if len(parts) < 2 or parts[-1] != "weight":
+        return False
+    if parts[-2] in _LAYERNORM_PARENTS:
+        return True
+    return len(parts) >= 4 and parts[-4] == "mlp_resnet_blocks" and parts[-2] == "0"   # ffn = Sequential(LayerNorm, ...)
 
 
 def split_segments(segs: list, chunk_bounds: list):
@@ -108,8 +123,12 @@ class ParamStore:
         self.exp_avg_sq: Optional[torch.Tensor] = None
         self.step_count = 0
         self._written: set[int] = set()       # grad tensors (by data_ptr) written since zero_grad
+        self._written_ranges: list[tuple[int, int]] = []   # the same, as element ranges of grad_a
+        # trainable region-A tensors as sorted element ranges: finalize_grads() zeroes the ones no kernel wrote
+        self._a_slots = sorted((s.offset, s.offset + s.spec.numel) for s in self.slots.values() if s.region == "A")
         self._always_zero: list[tuple[int, int]] = []   # region-A ranges that need an explicit memset per step
-        self.grad_ready_hook = None            # callable(region, start, end) — data-parallel overlap
+        self.grad_ready_hook = None            # callable(start, end): grad_a[start:end] is final — data-parallel overlap
+        self.zero_grad_hook = None             # callable(): a new step starts (the overlap resets its bookkeeping)
         # Optional overlap of the optimizer with the NEXT step's forward: AdamW is HBM-bound, the forward GEMMs are
         # tensor-bound, so the per-block updates run on a side stream in forward order and block i's forward waits
         # only for its own event (set_param_chunks / wait_chunk).  Off by default: every reader of the weights has to
@@ -192,7 +211,33 @@ class ParamStore:
         if key in self._written:
             return False
         self._written.add(key)
+        a = (key - self.grad_a.data_ptr()) // 2
+        self._written_ranges.append((a, a + g.numel()))
         return True
+
+    def finalize_grads(self) -> int:
+        """Region-A gradients are overwritten by the first wgrad of a step instead of being memset (15 GB at 7B), so a
+        trainable tensor that no kernel reached this step (a branch not taken, a forward without its head) would keep
+        the previous step's gradient.  The reference leaves such parameters at grad=None and AdamW skips them; here
+        they are zeroed before the norm / optimizer read them.  Returns the number of tensors zeroed (normally 0)."""
+        if not self._a_slots:
+            return 0
+        import bisect
+        merged: list[list[int]] = []
+        for a, b in sorted(self._written_ranges):
+            if merged and a <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], b)
+            else:
+                merged.append([a, b])
+        starts = [m[0] for m in merged]
+        zeroed = 0
+        for a, b in self._a_slots:
+            i = bisect.bisect_right(starts, a) - 1
+            if i >= 0 and merged[i][1] >= b:
+                continue
+            self.grad_a[a:b].zero_()
+            zeroed += 1
+        return zeroed
 
     def mark_sparse_grad(self, name: str) -> None:
         """Gradient rows written by scatter (embedding table): needs a real memset every step."""
@@ -217,10 +262,14 @@ class ParamStore:
 
     def zero_grad(self) -> None:
         self._written.clear()
+        self._written_ranges.clear()
         self.grad_b.zero_()
         for a, b in self._always_zero:
             self.grad_a[a:b].zero_()
             self._written.add(self.grad_a[a:].data_ptr())
+            self._written_ranges.append((a, b))
+        if self.zero_grad_hook is not None:
+            self.zero_grad_hook()
 
     def scratch_f32(self, n: int, tag: str = "") -> torch.Tensor:
         """Zeroed fp32 scratch (norm-weight / bias gradient accumulators)."""
@@ -248,7 +297,10 @@ class ParamStore:
             if not s.spec.trainable:
                 continue
             lr = lrs.get(s.spec.group, lrs["llm"])
-            nd = s.spec.no_decay if s.spec.no_decay is not None else (len(s.spec.shape) <= 1 or name.endswith("bias"))
+            # base_exp.py:102-103: everything is decayed except nn.LayerNorm children and names containing "bias"
+            # (RMSNorm weights, class_embedding, positional_embedding ... ARE decayed there); specs of LayerNorm
+            # weights carry no_decay=True
+            nd = s.spec.no_decay if s.spec.no_decay is not None else ("bias" in name or _is_layernorm_weight(name))
             wd = 0.0 if nd else weight_decay
             a, b = s.g_offset, s.g_offset + s.spec.numel
             b_al = (b + ALIGN - 1) // ALIGN * ALIGN
@@ -273,6 +325,7 @@ class ParamStore:
             self.exp_avg = torch.zeros(self.n_train, device=dev, dtype=torch.float32)
             self.exp_avg_sq = torch.zeros(self.n_train, device=dev, dtype=torch.float32)
         self.step_count += 1
+        self.finalize_grads()
         clip = None
         norm = torch.zeros((), device=dev, dtype=torch.float32)
         if max_grad_norm is not None:

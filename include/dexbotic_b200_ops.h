@@ -77,6 +77,27 @@ int b200_attn_scores(const void* a, const void* b, const void* p_in, void* out, 
                      int64_t b_ld, int64_t b_s_head, int64_t b_s_batch, int64_t p_ld, float scale, int causal,
                      const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k, int mode, void* stream);
 
+/* Flash attention (bf16, head_dim % 8 == 0 and <= 256, self-attention): O = softmax_mask(scale * Q K^T) V with the score
+ * blocks resident in TMEM — no [B, H, S, S] tensor is written; lse[B, H, S] (fp32, log2 domain: scale*log2(e)*rowmax +
+ * log2(rowsum)) is all the backward needs besides O.  q / k / v: (head_dim, S, heads, B) strided views of a packed qkv
+ * buffer (element strides qkv_ld per row, qkv_s_head per head, qkv_s_batch per batch; H heads for q, KVH for k / v);
+ * out: same form with its own strides.  Mask rule as b200_softmax_fwd (causal / key padding / pi0 block ids).
+ * Replaces F.scaled_dot_product_attention (HF Qwen2 / Llama / CLIP / SigLIP attention, dexbotic_arch.py:55-62,
+ * clip_encoder.py:50-54, siglip_encoder.py:79-84) and pi0's eager joint attention (pi0_arch.py:22-33,185-192). */
+int b200_flash_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H,
+                        int64_t KVH, int64_t S, int64_t head_dim, int64_t qkv_ld, int64_t qkv_s_head,
+                        int64_t qkv_s_batch, int64_t o_ld, int64_t o_s_head, int64_t o_s_batch, float scale, int causal,
+                        const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k, void* stream);
+/* Its backward: recomputes P from lse; dq / dk / dv use the strides (g_ld, g_s_head, g_s_batch) (the packed dqkv
+ * buffer), dout the strides of out.  dK / dV are reduced over the query heads of a GQA group inside the kernel's
+ * TMEM accumulators (no atomics: deterministic).  delta: fp32 workspace [B, H, S]. */
+int b200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                        const float* lse, float* delta, void* dq, void* dk, void* dv, int64_t B, int64_t H, int64_t KVH,
+                        int64_t S, int64_t head_dim, int64_t qkv_ld, int64_t qkv_s_head, int64_t qkv_s_batch,
+                        int64_t o_ld, int64_t o_s_head, int64_t o_s_batch, int64_t g_ld, int64_t g_s_head,
+                        int64_t g_s_batch, float scale, int causal, const uint8_t* keymask, const int32_t* bid_q,
+                        const int32_t* bid_k, void* stream);
+
 /* out[N] (fp32) += column sums of x[M,N]  (bias gradients) */
 int b200_colsum(const void* x, float* out, int64_t M, int64_t N, int dtype, void* stream);
 /* *out (fp32) += sum(x^2)  (global grad-norm, trainer.py:122 max_grad_norm=1.0) */

@@ -161,6 +161,8 @@ def _ref_attention(qkv, B, S, H, KVH, hd, keymask, bid):
     (2, 365, 28, 4, 128, True, torch.bfloat16),    # OFT length: 384 + 128 TMEM columns
     (2, 512, 4, 4, 72, False, torch.bfloat16),     # SigLIP head_dim 72, Sk = 512 (TMEM full)
     (2, 130, 2, 1, 96, True, torch.bfloat16),
+    (2, 867, 8, 1, 256, True, torch.bfloat16),     # pi0 joint sequence: Gemma head_dim 256, 8 q heads on 1 kv head
+    (2, 256, 16, 16, 72, False, torch.bfloat16),   # SigLIP-So400m tower
 ])
 def test_attention_fwd_bwd(B, S, H, KVH, hd, causal, dtype):
     o = ops()
@@ -181,7 +183,9 @@ def test_attention_fwd_bwd(B, S, H, KVH, hd, causal, dtype):
     _check(out * rowmask, ref * rowmask, S, dtype, "attention fwd")
 
     dout = _rand((B, S, H * hd), dtype, 21) * rowmask.to(dtype)
-    dqkv = o.attention_bwd(dout, qkv, probs, sh, causal=bool(causal and S % 2 == 1))
+    idx_causal = bool(causal and S % 2 == 1)
+    dqkv = o.attention_bwd(dout, qkv, probs, sh, causal=idx_causal, out=out, keymask=keymask,
+                           bid_q=None if idx_causal else bid, bid_k=None if idx_causal else bid)
     (ref * rowmask).backward(dout.float())
     _check(dqkv, qkv_ref.grad, S * 4, dtype, "attention bwd")
 
