@@ -309,8 +309,15 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
     def to_dev(hb):
         return {k: (v.to(dev, non_blocking=True) if hasattr(v, "to") else v) for k, v in hb.items()}
 
-    # data-parallel: gradient all-reduce only (north_star), in place on the flat buffers, overlapped with backward
-    overlap = GradientOverlap(model.store, reserve_sms=int(os.environ.get("B200_DP_RESERVE_SMS", "0")))
+    # data-parallel exchange, in place on the flat buffers and overlapped with backward.  Default: ZeRO-1
+    # (reduce-scatter of gradients, AdamW on 1/N of every chunk, all-gather of the bf16 weights under the next forward);
+    # B200_DP=allreduce selects the plain gradient all-reduce + replicated AdamW
+    dp_mode = os.environ.get("B200_DP", "zero1") if world > 1 else "none"
+    if dp_mode == "zero1":
+        from dexbotic_b200.parallel import ShardedDataParallel
+        overlap = ShardedDataParallel(model.store)
+    else:
+        overlap = GradientOverlap(model.store, reserve_sms=int(os.environ.get("B200_DP_RESERVE_SMS", "0")))
     # the HBM-bound per-block AdamW of step t runs on a side stream under the tensor-bound forward of step t+1
     # (ParamStore.adamw_step); the timed region below waits for the LAST step's updates before it closes
     model.store.async_optimizer = True
@@ -397,7 +404,10 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
                                 "blocks keep activations (rest recompute);") +
                                " inputs << L2 but weights+grads+moments stream through HBM every step "
                                "(>120 GB for the 7B model), so L2 is cold for the timed kernels",
-                   "global_batch": B * world, "seq_len": S, "parallelism": f"dp{world}",
+                   "global_batch": B * world, "seq_len": S,
+                   "parallelism": f"dp{world}" + ("" if world == 1 else
+                                                  " (ZeRO-1: reduce-scatter grads, sharded AdamW, all-gather bf16 weights)"
+                                                  if dp_mode == "zero1" else " (gradient all-reduce)"),
                    "train_tflop_per_sample": round(flops_sample / 1e12, 3)},
         "e2e": {"value": round(e2e, 3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
@@ -447,16 +457,145 @@ def run_reference(args) -> dict:
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
+def run_reference_gpu(args) -> dict:
+    """--impl reference_gpu: the number the north_star is written against — the UNMODIFIED reference
+    model classes (vendored under git-ignored baseline/_ref/ by tools/install_reference.sh, imported through the compat
+    loader oracle/ref_loader.py because this image has transformers 5.5) training on the same B200 with the reference's
+    own settings: fp32 parameters + bf16 autocast (HF Trainer bf16=True, base_exp.py:253), tf32 allowed (:254), HF's
+    default SDPA attention + cuBLAS, gradient_checkpointing=True non-reentrant (base_exp.py:245, trainer.py:120),
+    torch.optim.AdamW, max_grad_norm=1.0 (trainer.py:122), plain DDP for N>1 (deepspeed=None; DeepSpeed is not
+    installable offline).  Same synthetic batches and shapes as our arm; nothing of dexbotic_b200 is on this path."""
+    import torch
+    import torch.distributed as dist
+    from oracle import ref_loader
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    w = WORKLOADS[args.workload]
+    torch.manual_seed(1234)
+    with torch.device(dev):
+        if w.get("kind") == "pi0":
+            model = ref_loader.build_reference_pi0(dict(w["llm"]), dict(w["expert"]), dict(w["vision"]),
+                                                   action_dim=w["action_dim"], chunk_size=w["chunk_size"])
+        elif w.get("kind") is None:
+            from transformers import CLIPVisionConfig, Qwen2Config
+            llm = {k: v for k, v in w["llm"].items() if k != "model_type"}
+            model = ref_loader.build_reference_cogact(Qwen2Config(max_position_embeddings=4096, **llm),
+                                                      CLIPVisionConfig(**w["vision"]), w["action_model_type"],
+                                                      action_dim=w["action_dim"], chunk_size=w["chunk_size"])
+        else:
+            raise SystemExit(f"reference_gpu: workload {args.workload} not wired")
+    model.to(dev)
+    for p_ in model.model.parameters():          # base_exp.py:318-321: everything under model.model trains
+        p_.requires_grad = True
+    model.train()
+    model.gradient_checkpointing_enable(gradient_checkpointing_kwargs={"use_reentrant": False})
+    params = [p_ for p_ in model.parameters() if p_.requires_grad]
+    opt = torch.optim.AdamW(params, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, fused=True)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+    B = args.ref_batch or w["batch"]
+    accum = max(1, w["batch"] // B)
+    wb = dict(w, batch=B)
+    host = [make_batch(wb, rank * accum + i, pinned=True) for i in range(accum)]
+
+    def to_dev(hb):
+        out = {}
+        for k, v in hb.items():
+            if not hasattr(v, "to"):
+                continue
+            v = v.to(dev, non_blocking=True)
+            out[k] = v.to(torch.bfloat16) if (v.is_floating_point() and k == "images") else v
+        return out
+
+    def step(batches):
+        opt.zero_grad(set_to_none=True)
+        loss = None
+        for bt in batches:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = net(**bt)
+            (out.loss / len(batches)).backward()
+            loss = out.loss
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return loss
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    resident = [to_dev(h) for h in host]
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+
+    def timed(n, from_host):
+        sync_all()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        last = None
+        for _ in range(n):
+            loss = step([to_dev(h) for h in host] if from_host else resident)
+            if from_host:
+                last = loss.item()
+        e.record()
+        sync_all()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, (last if from_host else loss.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, loss_dev = timed(args.steps, False)
+    ms_e2e, _ = timed(args.steps, True)
+    clocks = sampler.stop() if rank == 0 else {}
+    per_step = w["batch"] * world
+    h2d = sum(v.numel() * v.element_size() for h in host for v in h.values() if hasattr(v, "numel"))
+    import transformers
+    res = {"impl": "reference_gpu", "metric": METRIC, "value": round(per_step * args.steps / (ms_dev * 1e-3), 3),
+           "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "bf16 autocast over fp32 parameters (HF Trainer bf16=True)", "data": "synthetic",
+           "config": {"workload": f"{args.workload}: unmodified reference classes from baseline/_ref via the compat "
+                                  f"loader, transformers {transformers.__version__}, torch {torch.__version__}; SDPA + "
+                                  "cuBLAS, gradient_checkpointing (non-reentrant), fused torch AdamW, clip 1.0, "
+                                  f"micro-batch {B} x {accum} accumulation = {w['batch']}/GPU, "
+                                  + ("DDP (find_unused_parameters)" if world > 1 else "single GPU"),
+                      "global_batch": per_step, "parallelism": f"dp{world}"},
+           "e2e": {"value": round(per_step * args.steps / (ms_e2e * 1e-3), 3), "unit": "samples/s",
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
+           "clocks": clocks, "loss": round(float(loss_dev), 5),
+           "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
+    if world > 1:
+        dist.destroy_process_group()
+    return res if rank == 0 else {}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference_gpu"])
+    ap.add_argument("--ref-batch", type=int, default=0,
+                    help="reference_gpu: micro-batch per GPU (gradient accumulation up to the workload's batch)")
     ap.add_argument("--workload", default="cogact_7b", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    res = run_reference(args) if args.impl == "reference" else run_ours(args)
+    res = (run_reference(args) if args.impl == "reference" else
+           run_reference_gpu(args) if args.impl == "reference_gpu" else run_ours(args))
     if res:
         print(json.dumps(res), flush=True)
 

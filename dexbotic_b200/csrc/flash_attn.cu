@@ -87,50 +87,84 @@ constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 10
 constexpr uint32_t kLoKMajor = (16u >> 4) << 16;                        // LBO unused for K-major operands
 constexpr uint32_t kLoMN64 = (8192u >> 4) << 16;                        // MN-major, 64-row atoms: next atom 8 KB on
 
-// D (=, then +=) A B^T contracted over head_dim; A / B tiles are [rows][hd] atom images, used K-major.
-__device__ __forceinline__ void mma_over_hd(uint32_t d_tmem, uint32_t a_addr, uint32_t a_atom, uint32_t b_addr,
-                                            uint32_t b_atom, int ksteps, uint32_t idesc) {
-  for (int ks = 0; ks < ksteps; ++ks) {
-    const uint32_t off = (uint32_t)(ks & 3) * 32u;
-    const uint32_t a_lo = kLoKMajor | ((a_addr + (uint32_t)(ks >> 2) * a_atom + off) >> 4);
-    const uint32_t b_lo = kLoKMajor | ((b_addr + (uint32_t)(ks >> 2) * b_atom + off) >> 4);
-    umma_issue<1, false>(d_tmem, a_lo, kDescHi, b_lo, kDescHi, idesc, ks != 0 ? 1u : 0u);
+// One tcgen05.mma (bf16, fp32 accumulate in TMEM) with a compile-time accumulate flag: the issuing thread does two
+// adds and the issue per instruction (both operands share the descriptor high word).
+template <bool kAcc>
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\nsetp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "n"(kAcc ? 1 : 0)
+      : "memory");
+}
+// D = A B^T contracted over head_dim (overwrites D); A / B tiles are [rows][hd] atom images, used K-major.
+// a_lo / b_lo: descriptor low words of the tiles' first atoms; *_atom16: atom size in 16-byte units.
+__device__ __forceinline__ void mma_over_hd(uint32_t d_tmem, uint32_t a_lo, uint32_t a_atom16, uint32_t b_lo,
+                                            uint32_t b_atom16, int ksteps, uint32_t idesc) {
+  umma_bf16<false>(d_tmem, a_lo, b_lo, idesc);
+  int ks = 1;
+  for (; ks < 4 && ks < ksteps; ++ks) umma_bf16<true>(d_tmem, a_lo + 2u * ks, b_lo + 2u * ks, idesc);
+  for (; ks + 4 <= ksteps; ks += 4) {
+    a_lo += a_atom16;
+    b_lo += b_atom16;
+    umma_bf16<true>(d_tmem, a_lo, b_lo, idesc);
+    umma_bf16<true>(d_tmem, a_lo + 2u, b_lo + 2u, idesc);
+    umma_bf16<true>(d_tmem, a_lo + 4u, b_lo + 4u, idesc);
+    umma_bf16<true>(d_tmem, a_lo + 6u, b_lo + 6u, idesc);
+  }
+  if (ks < ksteps) {          // partial last atom (head_dim 72 / 96 ...)
+    a_lo += a_atom16;
+    b_lo += b_atom16;
+    for (int r = 0; ks < ksteps; ++ks, ++r) umma_bf16<true>(d_tmem, a_lo + 2u * r, b_lo + 2u * r, idesc);
   }
 }
 // D (+)= A B contracted over the 64 rows of B: A = one [128][64] K-major atom (P, dS, P^T, dS^T), B = a 64-row block
-// [64][hd] read MN-major (N = head_dim).
-__device__ __forceinline__ void mma_over_rows64(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc,
-                                                uint32_t accumulate) {
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    const uint32_t a_lo = kLoKMajor | ((a_addr + (uint32_t)ks * 32u) >> 4);
-    const uint32_t b_lo = kLoMN64 | ((b_addr + (uint32_t)ks * 2048u) >> 4);
-    umma_issue<1, false>(d_tmem, a_lo, kDescHi, b_lo, kDescHi, idesc, (accumulate | (uint32_t)(ks != 0)) ? 1u : 0u);
-  }
+// [64][hd] read MN-major (N = head_dim).  a_lo: K-major low word of A; b_lo: MN-major low word of B.
+__device__ __forceinline__ void mma_over_rows64(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                bool accumulate) {
+  if (accumulate)
+    umma_bf16<true>(d_tmem, a_lo, b_lo, idesc);
+  else
+    umma_bf16<false>(d_tmem, a_lo, b_lo, idesc);
+  umma_bf16<true>(d_tmem, a_lo + 2u, b_lo + 128u, idesc);
+  umma_bf16<true>(d_tmem, a_lo + 4u, b_lo + 256u, idesc);
+  umma_bf16<true>(d_tmem, a_lo + 6u, b_lo + 384u, idesc);
 }
+__device__ __forceinline__ uint32_t lo_kmajor(uint32_t addr) { return kLoKMajor | (addr >> 4); }
+__device__ __forceinline__ uint32_t lo_mn64(uint32_t addr) { return kLoMN64 | (addr >> 4); }
 
 __device__ __forceinline__ int visible_blocks(const FaParams& p, int tile) {
   const int keys = p.causal ? min(p.S, tile * 128 + 128) : p.S;
   return (keys + 63) >> 6;
 }
 
-// Row-per-thread validity bits of 32 consecutive keys [k0, k0 + 32) for query row q (row-wise kernels: fwd, dq).
-// Key-side bits (range, padding) come from one ballot; the causal rule is a per-row bit count; the block-id rule is
-// evaluated per element only when the warp's keys are not all visible to all its rows.
-__device__ __forceinline__ uint32_t row_bits32(const FaParams& p, int b, int q, int bq, int k0, int lane) {
-  const int k = k0 + lane;
-  const bool kv = k < p.S && (p.keymask == nullptr || p.keymask[(size_t)b * p.S + k] != 0);
-  uint32_t w = __ballot_sync(0xffffffffu, kv);
+// Key-side mask data of key (k0 + lane), loaded one block ahead of its use (a global load on the per-block critical
+// path of a row-per-thread softmax costs more than the softmax itself).
+struct KeyInfo {
+  int bk;     // block id of the key (pi0 rule), INT_MAX when the rule is off / out of range
+  bool ok;    // in range and not padding
+};
+__device__ __forceinline__ KeyInfo load_key(const FaParams& p, int b, int k) {
+  KeyInfo r;
+  const bool in = k < p.S;
+  r.ok = in && (p.keymask == nullptr || p.keymask[(size_t)b * p.S + k] != 0);
+  r.bk = (p.bid_k != nullptr && in) ? p.bid_k[(size_t)b * p.S + k] : 0x7fffffff;
+  return r;
+}
+// Validity bits of the 32 keys [k0, k0 + 32) for query row q (row-wise kernels: fwd, dq).  Key-side bits come from one
+// ballot; the causal rule is a per-row bit count; the block-id rule is evaluated per element only when the warp's keys
+// are not all visible to all its rows.
+__device__ __forceinline__ uint32_t row_bits32(const FaParams& p, KeyInfo ki, int q, int bq, int k0) {
+  uint32_t w = __ballot_sync(0xffffffffu, ki.ok);
   if (p.causal) w &= low_mask(q + 1 - k0);
   if (p.bid_k != nullptr) {
-    const int bk = k < p.S ? p.bid_k[(size_t)b * p.S + k] : 0x7fffffff;
-    int mx = kv ? bk : (int)0x80000000;
+    int mx = ki.ok ? ki.bk : (int)0x80000000;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (__any_sync(0xffffffffu, bq < mx)) {
       uint32_t w2 = 0;
       for (int j = 0; j < 32; ++j) {
-        const int bkj = __shfl_sync(0xffffffffu, bk, j);
+        const int bkj = __shfl_sync(0xffffffffu, ki.bk, j);
         if (bkj <= bq) w2 |= 1u << j;
       }
       w &= w2;
@@ -182,6 +216,50 @@ __device__ __forceinline__ FwdItem fwd_item(const FaParams& p, int it) {
   return r;
 }
 
+// store one 32-column TMEM chunk of an output row as bf16 (columns >= hd are not written)
+__device__ __forceinline__ void store_chunk_bf16(bf16* row, int c, int hd, const uint32_t (&o)[32], float mul) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = c * 32 + g * 8;
+    if (col < hd) {
+      uint4 u;
+      u.x = pack2(__uint_as_float(o[g * 8]) * mul, __uint_as_float(o[g * 8 + 1]) * mul);
+      u.y = pack2(__uint_as_float(o[g * 8 + 2]) * mul, __uint_as_float(o[g * 8 + 3]) * mul);
+      u.z = pack2(__uint_as_float(o[g * 8 + 4]) * mul, __uint_as_float(o[g * 8 + 5]) * mul);
+      u.w = pack2(__uint_as_float(o[g * 8 + 6]) * mul, __uint_as_float(o[g * 8 + 7]) * mul);
+      *reinterpret_cast<uint4*>(row + col) = u;
+    }
+  }
+}
+// rows of a [128 x hd] fp32 TMEM accumulator -> bf16 global rows; chunks c0, c0 + cstep, ... two TMEM loads in flight
+__device__ __forceinline__ void store_acc_rows(uint32_t acc_tmem, bf16* row, bool row_ok, int c0, int cstep, int o_chunks,
+                                               int hd, float mul) {
+  for (int c = c0; c < o_chunks; c += 2 * cstep) {
+    uint32_t oa[32], ob[32];
+    const bool two = c + cstep < o_chunks;
+    tmem_ld_32x32(acc_tmem + c * 32, oa);
+    if (two) tmem_ld_32x32(acc_tmem + (c + cstep) * 32, ob);
+    tmem_ld_wait();
+    if (row_ok) {
+      store_chunk_bf16(row, c, hd, oa, mul);
+      if (two) store_chunk_bf16(row, c + cstep, hd, ob, mul);
+    }
+  }
+}
+// One arrival per warp: every lane has fenced its own writes / TMEM reads, __syncwarp orders them before lane 0's
+// (release) arrive.  256 threads arriving on one mbarrier serialise (~32 cycles per warp instruction on one address).
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+__device__ __forceinline__ void release(uint64_t* bar, bool used) {
+  if (used)
+    umma_commit(bar);     // arrives when this thread's MMAs (the readers of the buffer) have retired
+  else
+    mbar_arrive(bar);
+}
+
+// warp roles: 0 TMA producer | 1 MMA issuer of tile 0 | 2 TMEM allocator | 3 MMA issuer of tile 1 | 4.. softmax
 template <int kTiles>
 __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const __grid_constant__ FaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -198,15 +276,15 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
 
   if (warp == 1 && lane == 0) {
     mbar_init(&bar_q_full, 1);
-    mbar_init(&bar_q_empty, 1);
+    mbar_init(&bar_q_empty, kTiles);
     for (int i = 0; i < kFaMaxStages; ++i) {
       mbar_init(&bar_kv_full[i], 1);
-      mbar_init(&bar_kv_empty[i], 1);
+      mbar_init(&bar_kv_empty[i], kTiles);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&bar_s_full[t][0], 1);
       mbar_init(&bar_s_full[t][1], 1);
-      mbar_init(&bar_p_full[t], 128);
+      mbar_init(&bar_p_full[t], 4);        // one arrival per softmax warp
       mbar_init(&bar_pv_done[t], 1);
     }
     mbar_fence_init();
@@ -257,62 +335,61 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
         }
       }
     }
-  } else if (warp == 1) {
-    // -------------------------------------------------------------------- MMA issuer
+  } else if (warp == 1 || (kTiles == 2 && warp == 3)) {
+    // -------------------------------------- MMA issuer of tile t: the two tiles of a CTA run decoupled from each other
     if (lane == 0) {
+      const int t = warp == 1 ? 0 : 1;
       const uint32_t idesc_s = umma_idesc(1u, 0, 0, 128, 64);
       const uint32_t idesc_pv = umma_idesc(1u, 0, 1, 128, (uint32_t)p.n_hd);
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), ring_addr = smem_u32(sRing);
-      uint32_t blk[2] = {0u, 0u};   // running block counter per tile: S buffer = blk & 1
+      const uint32_t q_lo = lo_kmajor(smem_u32(sQ) + t * p.katoms * kAtom128);
+      const uint32_t p_lo = lo_kmajor(smem_u32(sP) + t * kAtom128);
+      const uint32_t ring_addr = smem_u32(sRing);
+      const uint32_t s_tmem = tmem + t * 128, o_tmem = tmem + (kTiles == 2 ? 256u + t * 128u : 128u);
+      uint32_t blk = 0;   // running block counter of this tile: S buffer = blk & 1
       int stage = 0, qi = 0;
       uint32_t phase = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
         const FwdItem im = fwd_item<kTiles>(p, it);
+        const int nb = im.nblk[t], n = im.n;
         mbar_wait(&bar_q_full, (uint32_t)(qi & 1));
-        mbar_wait(&bar_kv_full[stage], phase);
-        tc_fence_after();
-        for (int t = 0; t < kTiles; ++t) {
-          if (im.nblk[t] == 0) continue;
-          const uint32_t buf = blk[t] & 1u;
-          mma_over_hd(tmem + t * 128 + buf * 64, q_addr + t * p.katoms * kAtom128, kAtom128,
-                      ring_addr + stage * stage_bytes, kAtom64, p.ksteps, idesc_s);
-          umma_commit(&bar_s_full[t][buf]);
+        if (nb > 0) {
+          mbar_wait(&bar_kv_full[stage], phase);
+          tc_fence_after();
+          mma_over_hd(s_tmem + (blk & 1u) * 64, q_lo, kAtom128 >> 4, lo_kmajor(ring_addr + stage * stage_bytes),
+                      kAtom64 >> 4, p.ksteps, idesc_s);
+          umma_commit(&bar_s_full[t][blk & 1u]);
         }
-        if (im.n == 1) umma_commit(&bar_q_empty);
-        for (int j = 0; j < im.n; ++j) {
-          if (j + 1 < im.n) {   // the next block's scores first: the softmax warps never wait for the P V product
-            int ns = stage + 1;
-            uint32_t nph = phase;
-            if (ns == stages) {
-              ns = 0;
-              nph ^= 1u;
-            }
-            mbar_wait(&bar_kv_full[ns], nph);
-            tc_fence_after();
-            for (int t = 0; t < kTiles; ++t) {
-              if (j + 1 >= im.nblk[t]) continue;
-              const uint32_t buf = (blk[t] + 1u) & 1u;
-              mma_over_hd(tmem + t * 128 + buf * 64, q_addr + t * p.katoms * kAtom128, kAtom128,
-                          ring_addr + ns * stage_bytes, kAtom64, p.ksteps, idesc_s);
-              umma_commit(&bar_s_full[t][buf]);
-            }
-            if (j + 2 == im.n) umma_commit(&bar_q_empty);   // every S product of this item has been issued
+        if (n == 1) release(&bar_q_empty, nb > 0);
+        for (int j = 0; j < n; ++j) {
+          int ns = stage + 1;
+          uint32_t nph = phase;
+          if (ns == stages) {
+            ns = 0;
+            nph ^= 1u;
           }
-          const uint32_t v_addr = ring_addr + stage * stage_bytes + p.katoms * kAtom64;
-          for (int t = 0; t < kTiles; ++t) {
-            if (j >= im.nblk[t]) continue;
-            mbar_wait(&bar_p_full[t], blk[t] & 1u);
+          if (j + 1 < n) {   // the next block's scores first: the softmax warps never wait for the P V product
+            if (j + 1 < nb) {
+              mbar_wait(&bar_kv_full[ns], nph);
+              tc_fence_after();
+              mma_over_hd(s_tmem + ((blk + 1u) & 1u) * 64, q_lo, kAtom128 >> 4,
+                          lo_kmajor(ring_addr + ns * stage_bytes), kAtom64 >> 4, p.ksteps, idesc_s);
+              umma_commit(&bar_s_full[t][(blk + 1u) & 1u]);
+            }
+            if (j + 2 == n) release(&bar_q_empty, nb > 0);   // every S product of this item has been issued
+          }
+          if (j < nb) {
+            mbar_wait(&bar_p_full[t], blk & 1u);
             tc_fence_after();
-            const uint32_t o_tmem = tmem + (kTiles == 2 ? 256u + t * 128u : 128u);
-            mma_over_rows64(o_tmem, p_addr + t * kAtom128, v_addr, idesc_pv, j > 0 ? 1u : 0u);
+            mma_over_rows64(o_tmem, p_lo, lo_mn64(ring_addr + stage * stage_bytes + p.katoms * kAtom64), idesc_pv,
+                            j > 0);
             umma_commit(&bar_pv_done[t]);
-            ++blk[t];
+            ++blk;
+          } else {
+            mbar_wait(&bar_kv_full[stage], phase);   // a stage this tile does not use: still no running ahead of the ring
           }
-          umma_commit(&bar_kv_empty[stage]);
-          if (++stage == stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          release(&bar_kv_empty[stage], j < nb);
+          stage = ns;
+          phase = nph;
         }
       }
     }
@@ -335,10 +412,16 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
       const bool row_ok = q < p.S;
       const int bq = (p.bid_q != nullptr && row_ok) ? p.bid_q[(size_t)b * p.S + q] : 0;
       float m_ref = -INFINITY, l = 0.0f;
+      KeyInfo k0n = load_key(p, b, lane), k1n = load_key(p, b, 32 + lane);
       for (int j = 0; j < nblk; ++j) {
         const uint32_t buf = cnt & 1u;
-        const uint32_t bits0 = row_bits32(p, b, q, bq, j * 64, lane);
-        const uint32_t bits1 = row_bits32(p, b, q, bq, j * 64 + 32, lane);
+        const KeyInfo k0c = k0n, k1c = k1n;
+        if (j + 1 < nblk) {    // next block's mask bytes: in flight while this block is processed
+          k0n = load_key(p, b, (j + 1) * 64 + lane);
+          k1n = load_key(p, b, (j + 1) * 64 + 32 + lane);
+        }
+        const uint32_t bits0 = row_bits32(p, k0c, q, bq, j * 64);
+        const uint32_t bits1 = row_bits32(p, k1c, q, bq, j * 64 + 32);
         mbar_wait(&bar_s_full[t][buf], (cnt >> 1) & 1u);
         tc_fence_after();
         uint32_t s0[32], s1[32];
@@ -402,7 +485,7 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
           *reinterpret_cast<uint4*>(prow + ((c ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(&bar_p_full[t]);
+        warp_arrive(&bar_p_full[t], lane);
         ++cnt;
       }
       // ---- epilogue: O / l -> bf16 rows, log-sum-exp
@@ -410,25 +493,7 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
       tc_fence_after();
       const float inv = l > 0.0f ? 1.0f / l : 0.0f;
       bf16* orow = p.out + (long long)b * p.o_sb + (long long)q * p.o_ld + (long long)h * p.o_sh;
-      for (int c = 0; c < p.o_chunks; ++c) {
-        uint32_t o[32];
-        tmem_ld_32x32(o_tmem + c * 32, o);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = c * 32 + g * 8;
-            if (col < p.hd) {
-              uint4 u;
-              u.x = pack2(__uint_as_float(o[g * 8]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
-              u.y = pack2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
-              u.z = pack2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
-              u.w = pack2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
-              *reinterpret_cast<uint4*>(orow + col) = u;
-            }
-          }
-        }
-      }
+      store_acc_rows(o_tmem, orow, row_ok, 0, 1, p.o_chunks, p.hd, inv);
       if (row_ok && p.lse != nullptr)
         p.lse[((size_t)b * p.H + h) * p.S + q] = l > 0.0f ? m_ref + log2f(l) : INFINITY;
       tc_fence_before();
@@ -444,11 +509,12 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
 
 // -------------------------------------------------------------------------------------------- backward: dQ
 // smem: Q tile | dO tile | dS [128][64] | ring of (K block | V block).  TMEM: S @0/64, dP @128/192, dQ @256.
+// warp roles: 0 TMA | 1 issuer A (S, dP of the next block) | 2 TMEM allocator | 3 issuer B (dQ += dS K) | 4-11 softmax
 __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant__ FaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar_qdo_full, bar_qdo_empty, bar_kv_full[kFaMaxStages], bar_kv_empty[kFaMaxStages];
-  __shared__ uint64_t bar_sdp_full[2], bar_ds_full, bar_ds_empty, bar_dq_full;
+  __shared__ uint64_t bar_sdp_full[2], bar_sdp_free[2], bar_ds_full, bar_ds_empty, bar_dq_full;
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -466,9 +532,11 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
       mbar_init(&bar_kv_full[i], 1);
       mbar_init(&bar_kv_empty[i], 1);
     }
-    mbar_init(&bar_sdp_full[0], 1);
-    mbar_init(&bar_sdp_full[1], 1);
-    mbar_init(&bar_ds_full, 256);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_sdp_full[i], 1);
+      mbar_init(&bar_sdp_free[i], 8);     // one arrival per softmax warp
+    }
+    mbar_init(&bar_ds_full, 8);
     mbar_init(&bar_ds_empty, 1);
     mbar_init(&bar_dq_full, 1);
     mbar_fence_init();
@@ -518,46 +586,53 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
       }
     }
   } else if (warp == 1) {
+    // issuer A: S = Q K^T and dP = dO V^T of block c into buffer c & 1, as far ahead as the two buffers allow
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc(1u, 0, 0, 128, 64);
-      const uint32_t idesc_dq = umma_idesc(1u, 0, 1, 128, (uint32_t)p.n_hd);
-      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), ds_addr = smem_u32(sDS), ring_addr = smem_u32(sRing);
-      const bool prefetch = stages >= 2;
+      const uint32_t q_lo = lo_kmajor(smem_u32(sQ)), do_lo = lo_kmajor(smem_u32(sDO));
+      const uint32_t ring_addr = smem_u32(sRing);
       uint32_t cnt = 0;
       int stage = 0, qi = 0;
       uint32_t phase = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
-        const int pr = it / BH;
-        const int n = visible_blocks(p, p.m_tiles - 1 - pr);
+        const int n = visible_blocks(p, p.m_tiles - 1 - it / BH);
         mbar_wait(&bar_qdo_full, (uint32_t)(qi & 1));
-        // S and dP of block jn into buffer (cnt_of_that_block & 1), from ring stage st
-        auto issue_sdp = [&](int jn, uint32_t c, int st, uint32_t ph) {
-          mbar_wait(&bar_kv_full[st], ph);
-          tc_fence_after();
-          const uint32_t buf = c & 1u;
-          const uint32_t k_addr = ring_addr + st * stage_bytes;
-          mma_over_hd(tmem + buf * 64, q_addr, kAtom128, k_addr, kAtom64, p.ksteps, idesc_s);
-          mma_over_hd(tmem + 128 + buf * 64, do_addr, kAtom128, k_addr + p.katoms * kAtom64, kAtom64, p.ksteps, idesc_s);
-          umma_commit(&bar_sdp_full[buf]);
-          if (jn + 1 == n) umma_commit(&bar_qdo_empty);
-        };
-        issue_sdp(0, cnt, stage, phase);
         for (int j = 0; j < n; ++j) {
-          int ns = stage + 1;
-          uint32_t nph = phase;
-          if (ns == stages) {
-            ns = 0;
-            nph ^= 1u;
+          const uint32_t buf = cnt & 1u;
+          if (cnt >= 2) mbar_wait(&bar_sdp_free[buf], ((cnt >> 1) - 1u) & 1u);   // the buffer's previous block was read
+          mbar_wait(&bar_kv_full[stage], phase);
+          tc_fence_after();
+          const uint32_t k_lo = lo_kmajor(ring_addr + stage * stage_bytes);
+          mma_over_hd(tmem + buf * 64, q_lo, kAtom128 >> 4, k_lo, kAtom64 >> 4, p.ksteps, idesc_s);
+          mma_over_hd(tmem + 128 + buf * 64, do_lo, kAtom128 >> 4, k_lo + ((p.katoms * kAtom64) >> 4), kAtom64 >> 4,
+                      p.ksteps, idesc_s);
+          umma_commit(&bar_sdp_full[buf]);
+          if (j + 1 == n) umma_commit(&bar_qdo_empty);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
           }
-          if (prefetch && j + 1 < n) issue_sdp(j + 1, cnt + 1u, ns, nph);
+          ++cnt;
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // issuer B: dQ += dS K as soon as the softmax warps have written dS
+    if (lane == 0) {
+      const uint32_t idesc_dq = umma_idesc(1u, 0, 1, 128, (uint32_t)p.n_hd);
+      const uint32_t ds_lo = lo_kmajor(smem_u32(sDS));
+      const uint32_t ring_addr = smem_u32(sRing);
+      uint32_t cnt = 0;
+      int stage = 0;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+        const int n = visible_blocks(p, p.m_tiles - 1 - it / BH);
+        for (int j = 0; j < n; ++j) {
           mbar_wait(&bar_ds_full, cnt & 1u);
           tc_fence_after();
-          mma_over_rows64(tmem + 256, ds_addr, ring_addr + stage * stage_bytes, idesc_dq, j > 0 ? 1u : 0u);
+          mma_over_rows64(tmem + 256, ds_lo, lo_mn64(ring_addr + stage * stage_bytes), idesc_dq, j > 0);
           umma_commit(&bar_ds_empty);
           umma_commit(&bar_kv_empty[stage]);
-          if (!prefetch && j + 1 < n) issue_sdp(j + 1, cnt + 1u, ns, nph);
-          stage = ns;
-          phase = nph;
+          if (++stage == stages) stage = 0;
           ++cnt;
         }
         umma_commit(&bar_dq_full);
@@ -582,15 +657,20 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
       const float L = row_ok ? p.lse[stat] : INFINITY;
       const float dl = row_ok ? p.delta[stat] : 0.0f;
       const int bq = (p.bid_q != nullptr && row_ok) ? p.bid_q[(size_t)b * p.S + q] : 0;
+      KeyInfo kn = load_key(p, b, half * 32 + lane);
       for (int j = 0; j < n; ++j) {
         const uint32_t buf = cnt & 1u;
-        const uint32_t bits = row_bits32(p, b, q, bq, j * 64 + half * 32, lane);
+        const KeyInfo kc = kn;
+        if (j + 1 < n) kn = load_key(p, b, (j + 1) * 64 + half * 32 + lane);
+        const uint32_t bits = row_bits32(p, kc, q, bq, j * 64 + half * 32);
         mbar_wait(&bar_sdp_full[buf], (cnt >> 1) & 1u);
         tc_fence_after();
         uint32_t s[32], dp[32];
         tmem_ld_32x32(lane_base + buf * 64 + half * 32, s);
         tmem_ld_32x32(lane_base + 128 + buf * 64 + half * 32, dp);
         tmem_ld_wait();
+        tc_fence_before();
+        warp_arrive(&bar_sdp_free[buf], lane);
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -609,33 +689,16 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
           *reinterpret_cast<uint4*>(dsrow + (((half * 4 + c) ^ sw) << 4)) =
               make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(&bar_ds_full);
+        warp_arrive(&bar_ds_full, lane);
         ++cnt;
       }
       mbar_wait(&bar_dq_full, (uint32_t)(qi & 1));
       tc_fence_after();
       bf16* drow = p.dq + (long long)b * p.g_sb + (long long)q * p.g_ld + (long long)h * p.gq_sh;
-      for (int c = half; c < p.o_chunks; c += 2) {
-        uint32_t o[32];
-        tmem_ld_32x32(lane_base + 256 + c * 32, o);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = c * 32 + g * 8;
-            if (col < p.hd) {
-              uint4 u;
-              u.x = pack2(__uint_as_float(o[g * 8]), __uint_as_float(o[g * 8 + 1]));
-              u.y = pack2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
-              u.z = pack2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
-              u.w = pack2(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
-              *reinterpret_cast<uint4*>(drow + col) = u;
-            }
-          }
-        }
-      }
+      store_acc_rows(lane_base + 256, drow, row_ok, half, 2, p.o_chunks, p.hd, 1.0f);
       tc_fence_before();
+      // all eight warps have left the dQ accumulator before issuer B may overwrite it: their next arrival on ds_full
+      // (block 0 of the next item) comes after this point in program order
     }
   }
   tc_fence_before();
@@ -650,6 +713,7 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
 // Transposed problem: TMEM lanes = the 128 keys of the tile, columns = 64 query rows of a block.
 // smem: K tile | V tile | P^T [128][64] | dS^T [128][64] | ring of (Q block | dO block).
 // TMEM: S^T @0/64, dP^T @128/192, accumulators @256 (mode 0: dV @256, dK @384; mode 1: dV only; mode 2: dK only).
+// warp roles: 0 TMA | 1 issuer A (S^T, dP^T) | 2 TMEM allocator | 3 issuer B (dV += P^T dO, dK += dS^T Q) | 4-11 softmax
 struct DkvItem {
   int b, kvh, jt, mode, ib0, nsteps;
 };
@@ -671,7 +735,7 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar_kv_full, bar_kv_empty, bar_ring_full[kFaMaxStages], bar_ring_empty[kFaMaxStages];
-  __shared__ uint64_t bar_sdp_full[2], bar_pds_full, bar_pds_empty, bar_acc_full;
+  __shared__ uint64_t bar_sdp_full[2], bar_sdp_free[2], bar_pds_full, bar_pds_empty, bar_acc_full;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float stats[8][3][32];   // per softmax warp: lse, delta, block id of its 32 query columns
 
@@ -691,9 +755,11 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
       mbar_init(&bar_ring_full[i], 1);
       mbar_init(&bar_ring_empty[i], 1);
     }
-    mbar_init(&bar_sdp_full[0], 1);
-    mbar_init(&bar_sdp_full[1], 1);
-    mbar_init(&bar_pds_full, 256);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_sdp_full[i], 1);
+      mbar_init(&bar_sdp_free[i], 8);
+    }
+    mbar_init(&bar_pds_full, 8);
     mbar_init(&bar_pds_empty, 1);
     mbar_init(&bar_acc_full, 1);
     mbar_fence_init();
@@ -744,52 +810,60 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
+    // issuer A: S^T = K Q^T and dP^T = V dO^T of step c into buffer c & 1
     if (lane == 0) {
       const uint32_t idesc_st = umma_idesc(1u, 0, 0, 128, 64);
-      const uint32_t idesc_acc = umma_idesc(1u, 0, 1, 128, (uint32_t)p.n_hd);
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
+      const uint32_t k_lo = lo_kmajor(smem_u32(sK)), v_lo = lo_kmajor(smem_u32(sV));
       const uint32_t ring_addr = smem_u32(sRing);
-      const bool prefetch = stages >= 2;
       uint32_t cnt = 0;
       int stage = 0, qi = 0;
       uint32_t phase = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
         const DkvItem im = dkv_item(p, it);
         const int n = im.nsteps;
+        const bool do_dk = im.mode != 1;
+        mbar_wait(&bar_kv_full, (uint32_t)(qi & 1));
+        for (int sidx = 0; sidx < n; ++sidx) {
+          const uint32_t buf = cnt & 1u;
+          if (cnt >= 2) mbar_wait(&bar_sdp_free[buf], ((cnt >> 1) - 1u) & 1u);
+          mbar_wait(&bar_ring_full[stage], phase);
+          tc_fence_after();
+          const uint32_t qb_lo = lo_kmajor(ring_addr + stage * stage_bytes);
+          mma_over_hd(tmem + buf * 64, k_lo, kAtom128 >> 4, qb_lo, kAtom64 >> 4, p.ksteps, idesc_st);
+          if (do_dk)
+            mma_over_hd(tmem + 128 + buf * 64, v_lo, kAtom128 >> 4, qb_lo + ((p.katoms * kAtom64) >> 4), kAtom64 >> 4,
+                        p.ksteps, idesc_st);
+          umma_commit(&bar_sdp_full[buf]);
+          if (sidx + 1 == n) umma_commit(&bar_kv_empty);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          ++cnt;
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // issuer B: the accumulating products, as soon as P^T / dS^T of a step are in smem
+    if (lane == 0) {
+      const uint32_t idesc_acc = umma_idesc(1u, 0, 1, 128, (uint32_t)p.n_hd);
+      const uint32_t pt_lo = lo_kmajor(smem_u32(sPT)), dst_lo = lo_kmajor(smem_u32(sDST));
+      const uint32_t ring_addr = smem_u32(sRing);
+      uint32_t cnt = 0;
+      int stage = 0;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+        const DkvItem im = dkv_item(p, it);
         const bool do_dv = im.mode != 2, do_dk = im.mode != 1;
         const uint32_t dv_tmem = tmem + 256, dk_tmem = tmem + (im.mode == 0 ? 384u : 256u);
-        mbar_wait(&bar_kv_full, (uint32_t)(qi & 1));
-        auto issue_sdp = [&](int sn, uint32_t c, int st, uint32_t ph) {
-          mbar_wait(&bar_ring_full[st], ph);
-          tc_fence_after();
-          const uint32_t buf = c & 1u;
-          const uint32_t qb_addr = ring_addr + st * stage_bytes;
-          mma_over_hd(tmem + buf * 64, k_addr, kAtom128, qb_addr, kAtom64, p.ksteps, idesc_st);
-          if (do_dk)
-            mma_over_hd(tmem + 128 + buf * 64, v_addr, kAtom128, qb_addr + p.katoms * kAtom64, kAtom64, p.ksteps,
-                        idesc_st);
-          umma_commit(&bar_sdp_full[buf]);
-          if (sn + 1 == n) umma_commit(&bar_kv_empty);
-        };
-        issue_sdp(0, cnt, stage, phase);
-        for (int s = 0; s < n; ++s) {
-          int ns = stage + 1;
-          uint32_t nph = phase;
-          if (ns == stages) {
-            ns = 0;
-            nph ^= 1u;
-          }
-          if (prefetch && s + 1 < n) issue_sdp(s + 1, cnt + 1u, ns, nph);
+        for (int sidx = 0; sidx < im.nsteps; ++sidx) {
           mbar_wait(&bar_pds_full, cnt & 1u);
           tc_fence_after();
           const uint32_t qb_addr = ring_addr + stage * stage_bytes;
-          if (do_dv) mma_over_rows64(dv_tmem, pt_addr, qb_addr + p.katoms * kAtom64, idesc_acc, s > 0 ? 1u : 0u);
-          if (do_dk) mma_over_rows64(dk_tmem, dst_addr, qb_addr, idesc_acc, s > 0 ? 1u : 0u);
+          if (do_dv) mma_over_rows64(dv_tmem, pt_lo, lo_mn64(qb_addr + p.katoms * kAtom64), idesc_acc, sidx > 0);
+          if (do_dk) mma_over_rows64(dk_tmem, dst_lo, lo_mn64(qb_addr), idesc_acc, sidx > 0);
           umma_commit(&bar_pds_empty);
           umma_commit(&bar_ring_empty[stage]);
-          if (!prefetch && s + 1 < n) issue_sdp(s + 1, cnt + 1u, ns, nph);
-          stage = ns;
-          phase = nph;
+          if (++stage == stages) stage = 0;
           ++cnt;
         }
         umma_commit(&bar_acc_full);
@@ -813,20 +887,34 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
       const bool key_in = key < p.S;
       const bool key_ok = key_in && (p.keymask == nullptr || p.keymask[(size_t)b * p.S + key] != 0);
       const int bk = (p.bid_k != nullptr && key_in) ? p.bid_k[(size_t)b * p.S + key] : 0;
+      // per-column statistics of a step (lse, delta, block id of query q0 + lane), loaded one step ahead
+      auto load_stats = [&](int hh, int ib, float& o_l, float& o_d, int& o_b) {
+        const int qq = ib * 64 + half * 32 + lane;
+        const bool qok = qq < p.S;
+        const size_t stat = ((size_t)b * p.H + (im.kvh * p.G + hh)) * p.S + qq;
+        o_l = qok ? p.lse[stat] : INFINITY;
+        o_d = (qok && do_dk) ? p.delta[stat] : 0.0f;
+        o_b = (p.bid_q != nullptr && qok) ? p.bid_q[(size_t)b * p.S + qq] : 0;
+      };
+      float n_l, n_d;
+      int n_b;
+      load_stats(0, im.ib0, n_l, n_d, n_b);
       for (int hh = 0; hh < p.G; ++hh) {
-        const int h = im.kvh * p.G + hh;
         for (int ib = im.ib0; ib < p.n_qblk; ++ib) {
           const uint32_t buf = cnt & 1u;
           const int q0 = ib * 64 + half * 32;
+          __syncwarp();
+          st[0][lane] = n_l;
+          st[1][lane] = n_d;
+          st[2][lane] = __int_as_float(n_b);
+          __syncwarp();
           {
-            const int qq = q0 + lane;
-            const bool qok = qq < p.S;
-            const size_t stat = ((size_t)b * p.H + h) * p.S + qq;
-            __syncwarp();
-            st[0][lane] = qok ? p.lse[stat] : INFINITY;
-            st[1][lane] = qok ? p.delta[stat] : 0.0f;
-            st[2][lane] = __int_as_float((p.bid_q != nullptr && qok) ? p.bid_q[(size_t)b * p.S + qq] : 0);
-            __syncwarp();
+            int nh = hh, nib = ib + 1;
+            if (nib == p.n_qblk) {
+              nib = im.ib0;
+              ++nh;
+            }
+            if (nh < p.G) load_stats(nh, nib, n_l, n_d, n_b);
           }
           uint32_t bits = key_ok ? 0xffffffffu : 0u;
           if (p.causal) bits &= ~low_mask(key - q0);      // column c is visible iff q0 + c >= key
@@ -843,6 +931,8 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
           tmem_ld_32x32(lane_base + buf * 64 + half * 32, s);
           if (do_dk) tmem_ld_32x32(lane_base + 128 + buf * 64 + half * 32, dp);
           tmem_ld_wait();
+          tc_fence_before();
+          warp_arrive(&bar_sdp_free[buf], lane);
           uint32_t pp[16], pd[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -864,39 +954,17 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
             if (do_dk) *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(pd[4 * c], pd[4 * c + 1], pd[4 * c + 2], pd[4 * c + 3]);
           }
           fence_proxy_async_smem();
-          tc_fence_before();
-          mbar_arrive(&bar_pds_full);
+          warp_arrive(&bar_pds_full, lane);
           ++cnt;
         }
       }
       // ---- epilogue: the accumulated dV / dK rows of this key tile
       mbar_wait(&bar_acc_full, (uint32_t)(qi & 1));
       tc_fence_after();
-      for (int which = 0; which < 2; ++which) {
-        if (which == 0 ? !do_dv : !do_dk) continue;
-        const uint32_t acc = lane_base + (which == 0 ? 256u : (im.mode == 0 ? 384u : 256u));
-        bf16* drow = (which == 0 ? p.dv : p.dk) + (long long)b * p.g_sb + (long long)key * p.g_ld +
-                     (long long)im.kvh * p.gkv_sh;
-        for (int c = half; c < p.o_chunks; c += 2) {
-          uint32_t o[32];
-          tmem_ld_32x32(acc + c * 32, o);
-          tmem_ld_wait();
-          if (key_in) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = c * 32 + g * 8;
-              if (col < p.hd) {
-                uint4 u;
-                u.x = pack2(__uint_as_float(o[g * 8]), __uint_as_float(o[g * 8 + 1]));
-                u.y = pack2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
-                u.z = pack2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
-                u.w = pack2(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
-                *reinterpret_cast<uint4*>(drow + col) = u;
-              }
-            }
-          }
-        }
-      }
+      const long long roff = (long long)b * p.g_sb + (long long)key * p.g_ld + (long long)im.kvh * p.gkv_sh;
+      if (do_dv) store_acc_rows(lane_base + 256, p.dv + roff, key_in, half, 2, p.o_chunks, p.hd, 1.0f);
+      if (do_dk)
+        store_acc_rows(lane_base + (im.mode == 0 ? 384u : 256u), p.dk + roff, key_in, half, 2, p.o_chunks, p.hd, 1.0f);
       tc_fence_before();
     }
   }
@@ -908,31 +976,43 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
   }
 }
 
-// delta[b, h, q] = sum_d dO[b, q, h, d] * O[b, q, h, d]: one warp per (b, q, h) row
-__global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
-                                  int B, int H, int S, int hd, long long ld, long long sh, long long sb) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= (long long)B * S * H) return;
-  const int h = (int)(row % H);
-  const long long bq = row / H;
-  const int q = (int)(bq % S), b = (int)(bq / S);
-  const long long off = (long long)b * sb + (long long)q * ld + (long long)h * sh;
-  float acc = 0.0f;
-  for (int c = lane * 8; c < hd; c += 256) {
-    const uint4 a = *reinterpret_cast<const uint4*>(o + off + c);
-    const uint4 d = *reinterpret_cast<const uint4*>(dout + off + c);
-    const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
-    const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&d);
+// delta[b, h, q] = sum_d dO[b, q, h, d] * O[b, q, h, d].  HBM-bound (reads O and dO once): one thread per 16-byte
+// chunk, kLanes = head_dim chunks (rounded up to a power of two) lanes per row, shuffle reduction inside the group.
+template <int kLanes>
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout,
+                                                         float* __restrict__ delta, int B, int H, int S, int hd,
+                                                         long long ld, long long sh, long long sb) {
+  const long long rows = (long long)B * S * H;
+  const int sub = threadIdx.x % kLanes;
+  const long long row0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
+  const long long stride = (long long)gridDim.x * blockDim.x / kLanes;
+  for (long long row = row0;; row += stride) {   // whole warps stay converged for the shuffles
+    const bool live = row < rows;
+    float acc = 0.0f;
+    int b = 0, h = 0, q = 0;
+    if (live) {
+      h = (int)(row % H);
+      const long long bq = row / H;
+      q = (int)(bq % S);
+      b = (int)(bq / S);
+      const long long off = (long long)b * sb + (long long)q * ld + (long long)h * sh;
+      for (int c = sub * 8; c < hd; c += kLanes * 8) {
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(o + off + c));
+        const uint4 y = __ldg(reinterpret_cast<const uint4*>(dout + off + c));
+        const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&x);
+        const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&y);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 x = __bfloat1622float2(ah[i]), y = __bfloat1622float2(dh[i]);
-      acc += x.x * y.x + x.y * y.y;
+        for (int i = 0; i < 4; ++i) {
+          const float2 u = __bfloat1622float2(xh[i]), v = __bfloat1622float2(yh[i]);
+          acc += u.x * v.x + u.y * v.y;
+        }
+      }
     }
-  }
 #pragma unroll
-  for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
-  if (lane == 0) delta[((size_t)b * H + h) * S + q] = acc;
+    for (int o2 = kLanes / 2; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+    if (live && sub == 0) delta[((size_t)b * H + h) * S + q] = acc;
+    if (!__any_sync(0xffffffffu, row + stride < rows)) break;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1067,9 +1147,15 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
   // 1. delta = rowsum(dO * O)
   {
     const long long rows = (long long)B * S * H;
-    const int warps = 8;
-    attn_delta_kernel<<<(unsigned)ceil_div(rows, warps), warps * 32, 0, stream>>>(
-        (const bf16*)out, (const bf16*)dout, delta, (int)B, (int)H, (int)S, (int)head_dim, o_ld, o_s_head, o_s_batch);
+    const int chunks = (int)(head_dim / 8);
+    const int lanes = chunks <= 4 ? 4 : (chunks <= 8 ? 8 : (chunks <= 16 ? 16 : 32));
+    long long blocks = ceil_div(rows * lanes, 256);
+    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+#define B200_DELTA(L)                                                                                              \
+  attn_delta_kernel<L><<<(unsigned)blocks, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, (int)B, (int)H, \
+                                                             (int)S, (int)head_dim, o_ld, o_s_head, o_s_batch)
+    if (lanes == 4) B200_DELTA(4); else if (lanes == 8) B200_DELTA(8); else if (lanes == 16) B200_DELTA(16); else B200_DELTA(32);
+#undef B200_DELTA
     B200_LAUNCH_OK();
   }
   kp.lse = const_cast<float*>(lse);

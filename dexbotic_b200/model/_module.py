@@ -101,6 +101,8 @@ class B200Module(nn.Module):
 
     def state_dict(self, *args, **kwargs):
         self.store.wait_all_params()           # an overlapped optimizer step may still be writing the master buffer
+        if self.store.sharder is not None:     # ZeRO-1: every rank holds the current fp32 master of its pieces only
+            self.store.sharder.gather_master()
         return super().state_dict(*args, **kwargs)
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):

@@ -129,6 +129,7 @@ class ParamStore:
         self._always_zero: list[tuple[int, int]] = []   # region-A ranges that need an explicit memset per step
         self.grad_ready_hook = None            # callable(start, end): grad_a[start:end] is final — data-parallel overlap
         self.zero_grad_hook = None             # callable(): a new step starts (the overlap resets its bookkeeping)
+        self.sharder = None                    # parallel.ShardedDataParallel (ZeRO-1): owns the optimizer step if set
         # Optional overlap of the optimizer with the NEXT step's forward: AdamW is HBM-bound, the forward GEMMs are
         # tensor-bound, so the per-block updates run on a side stream in forward order and block i's forward waits
         # only for its own event (set_param_chunks / wait_chunk).  Off by default: every reader of the weights has to
@@ -320,6 +321,8 @@ class ParamStore:
     def adamw_step(self, lrs: dict, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
                    max_grad_norm: Optional[float] = 1.0, grad_scale: float = 1.0):
         """One fused AdamW step over every trainable segment; returns the (device) gradient norm."""
+        if self.sharder is not None and self.sharder.enabled:
+            return self.sharder.step(lrs, betas, eps, weight_decay, max_grad_norm)
         dev = self.device
         if self.exp_avg is None:
             self.exp_avg = torch.zeros(self.n_train, device=dev, dtype=torch.float32)

@@ -3,7 +3,8 @@
 Loads the UNMODIFIED reference (dexmal/dexbotic, read-only at /root/reference) in this container so
 that the oracle restatement (oracle/vla_oracle.py) can be validated against it and golden vectors can be
 generated (oracle/make_golden.py).  /root/reference does not exist on the GPU box; nothing under
-tests/ -m gpu, smoke() or bench.py imports this module.
+tests/ -m gpu, smoke() or bench.py's own arm imports this module (`bench.py --impl reference_gpu`, the reference's
+PyTorch GPU baseline, loads the vendored copy under baseline/_ref/ through it).
 
 Compatibility recipe, all in memory, /root/reference untouched:
   1. import transformers first (it probes find_spec('timm'));
@@ -22,7 +23,11 @@ import sys
 import types
 from pathlib import Path
 
+# /root/reference in the build container; on the GPU box the same unmodified tree vendored by
+# tools/install_reference.sh into the git-ignored baseline/_ref/ (used by `bench.py --impl reference_gpu` only)
 REFERENCE_ROOT = Path("/root/reference")
+if not (REFERENCE_ROOT / "dexbotic" / "model" / "dexbotic_arch.py").exists():
+    REFERENCE_ROOT = Path(__file__).resolve().parent.parent / "baseline" / "_ref"
 
 
 def reference_available() -> bool:
@@ -332,3 +337,45 @@ def build_reference_pi05(llm_config: dict, action_config: dict, vision_config: d
                          processor_config="unused", mm_projector_type="linear", action_dim=action_dim,
                          chunk_size=chunk_size)
     return mod.Pi05ForCausalLM(cfg)
+
+
+_navila_loaded = False
+
+
+def load_reference_navila():
+    """navila_arch.py: the same un-defaulted dataclass field as DexboticConfig (`llm_config`), and a SigLIP tower built
+    from a config object: build_vision_tower() insists on a processor_config for config objects
+    (mm_vision/builder.py:26-29) and DexboticVLMModel passes none for NaVILA (dexbotic_arch.py:100-104), so a
+    SiglipVisionConfig is routed to SiglipVisionTower directly with its default select_layer=-2 — exactly what the
+    string name "google/siglip-so400m-patch14-384" resolves to (builder.py:16-17), minus the download."""
+    global _navila_loaded
+    load_reference_pi0()          # SigLIP load_model patch
+    if _navila_loaded:
+        return sys.modules["dexbotic.model.navila.navila_arch"]
+    from transformers import SiglipVisionConfig
+    from dexbotic.model.modules.mm_vision import builder as vbuilder
+    from dexbotic.model.modules.mm_vision.siglip import siglip_encoder
+    prev = vbuilder.build_vision_tower
+
+    def build_vision_tower(mm_vision_tower, **kwargs):
+        if isinstance(mm_vision_tower, SiglipVisionConfig) and "processor_config" not in kwargs:
+            return siglip_encoder.SiglipVisionTower(mm_vision_tower, processor_config="unused")
+        return prev(mm_vision_tower, **kwargs)
+
+    vbuilder.build_vision_tower = build_vision_tower
+    sys.modules["dexbotic.model.dexbotic_arch"].build_vision_tower = build_vision_tower
+    import dexbotic.model.navila  # noqa: F401
+    mod = _exec_patched("dexbotic.model.navila.navila_arch", "dexbotic/model/navila/navila_arch.py",
+                        [("    llm_config: str | PretrainedConfig\n", "    llm_config: str | PretrainedConfig = None\n")])
+    _navila_loaded = True
+    return mod
+
+
+def build_reference_navila(llm_config: dict, vision_config, time_token_ids=None, soft_ce_std: float = 1.0):
+    """Reference NaVILAForCausalLM (navila_arch.py:222-231), random init.  llm_config: dict with `model_type`
+    (NaVILAModel resolves it through CONFIG_MAPPING, :27-31); vision_config: a SiglipVisionConfig."""
+    mod = load_reference_navila()
+    cfg = mod.NaVILAConfig(llm_config=dict(llm_config), mm_projector_type="mlp_downsample", mm_vision_tower=vision_config)
+    if time_token_ids:
+        cfg.time_token_ids, cfg.soft_ce_std = list(time_token_ids), soft_ce_std
+    return mod.NaVILAForCausalLM(cfg)

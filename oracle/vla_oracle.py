@@ -625,9 +625,11 @@ def oft_l1_forward(sd, cfg: dict, input_ids, attention_mask, images, actions=Non
 # ----------------------------------------------------------------------------------------------
 # pi0 — dexbotic/model/pi0/pi0_arch.py (SigLIP tower: modules/mm_vision/siglip/siglip_encoder.py:61-86)
 # ----------------------------------------------------------------------------------------------
-def siglip_vision_features(sd, prefix: str, images: torch.Tensor, cfg: dict) -> torch.Tensor:
+def siglip_vision_features(sd, prefix: str, images: torch.Tensor, cfg: dict, select_layer=None) -> torch.Tensor:
     """HF SiglipVisionModel(...).last_hidden_state (select_layer=None, siglip_encoder.py:62-63): conv(+bias) patchify,
-    learned position embedding, pre-LN encoder with gelu_tanh MLP, post_layernorm.  No CLS token."""
+    learned position embedding, pre-LN encoder with gelu_tanh MLP, post_layernorm.  No CLS token.
+    select_layer=-2 (the tower's default, siglip_encoder.py:13,64-65): hidden_states[-2] = the output of the
+    second-to-last encoder layer, no post_layernorm."""
     p = prefix + "vision_tower.vision_model."
     patch, heads, eps = cfg["patch_size"], cfg["num_attention_heads"], cfg.get("layer_norm_eps", 1e-6)
     act = ACT[cfg.get("hidden_act", "gelu_pytorch_tanh")]
@@ -635,7 +637,8 @@ def siglip_vision_features(sd, prefix: str, images: torch.Tensor, cfg: dict) -> 
                  stride=patch).flatten(2).transpose(1, 2)
     x = x + sd[p + "embeddings.position_embedding.weight"][None]
     D = x.shape[-1]
-    for i in range(cfg["num_hidden_layers"]):
+    n_layers = cfg["num_hidden_layers"] if select_layer is None else cfg["num_hidden_layers"] + 1 + select_layer
+    for i in range(n_layers):
         q = f"{p}encoder.layers.{i}."
         h = F.layer_norm(x, (D,), sd[q + "layer_norm1.weight"], sd[q + "layer_norm1.bias"], eps)
         x = x + _mha(h, sd[q + "self_attn.q_proj.weight"], sd[q + "self_attn.q_proj.bias"],
@@ -645,6 +648,8 @@ def siglip_vision_features(sd, prefix: str, images: torch.Tensor, cfg: dict) -> 
         h = F.layer_norm(x, (D,), sd[q + "layer_norm2.weight"], sd[q + "layer_norm2.bias"], eps)
         x = x + F.linear(act(F.linear(h, sd[q + "mlp.fc1.weight"], sd[q + "mlp.fc1.bias"])),
                          sd[q + "mlp.fc2.weight"], sd[q + "mlp.fc2.bias"])
+    if select_layer is not None:
+        return x
     return F.layer_norm(x, (D,), sd[p + "post_layernorm.weight"], sd[p + "post_layernorm.bias"], eps)
 
 
@@ -948,3 +953,74 @@ def memvla_inference(sd, cfg: dict, banks: dict, input_ids, images, noise, times
     cog = banks["cog"].process_batch(cog, [(0, 0)], ts, training=False)
     per = banks["per"].process_batch(per, [(0, 0)], ts, training=False)
     return ddim_sample(sd, cfg, cog, noise, cfg_scale, num_ddim_steps, per_token=per)
+
+
+# ----------------------------------------------------------------------------------------------
+# NaVILA — dexbotic/model/navila/navila_arch.py (VLM + (soft) cross entropy), navila/loss.py,
+# mm_projector/builder.py:9-33,61-68 (mlp_downsample)
+# ----------------------------------------------------------------------------------------------
+def downsample_2x2(x: torch.Tensor) -> torch.Tensor:
+    """DownSampleBlock (mm_projector/builder.py:9-33): [N, h*w, C] -> [N, ceil(h/2)*ceil(w/2), 4C].  The token grid
+    (row-major, rows = first axis) is zero-padded to even sides; output token t = j * ceil(h/2) + i concatenates the
+    cells (2i, 2j), (2i, 2j+1), (2i+1, 2j), (2i+1, 2j+1) in that order — the two view/permute steps of flat_square
+    written as one gather (checked equal to the reference module in oracle/make_golden.py:make_navila_tiny)."""
+    N, T, C = x.shape
+    h = w = int(T ** 0.5)
+    g = x.reshape(N, h, w, C)
+    g = F.pad(g, (0, 0, 0, w % 2, 0, h % 2))
+    H2, W2 = g.shape[1] // 2, g.shape[2] // 2
+    g = g.reshape(N, H2, 2, W2, 2, C)                     # [N, i, di, j, dj, C]
+    out = g.permute(0, 3, 1, 2, 4, 5)                     # [N, j, i, di, dj, C]
+    return out.reshape(N, W2 * H2, 4 * C)
+
+
+def navila_projector(sd, prefix: str, feats: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """mlp_downsample: DownSampleBlock, LayerNorm(4C), Linear(4C, d), GELU(erf), Linear(d, d)."""
+    x = downsample_2x2(feats)
+    x = F.layer_norm(x, (x.shape[-1],), sd[prefix + "1.weight"], sd[prefix + "1.bias"], eps)
+    x = F.gelu(F.linear(x, sd[prefix + "2.weight"], sd[prefix + "2.bias"]))
+    return F.linear(x, sd[prefix + "4.weight"], sd[prefix + "4.bias"])
+
+
+def soft_cross_entropy(logits: torch.Tensor, targets: torch.Tensor, soft_tokens, std: float = 1.0) -> torch.Tensor:
+    """navila/loss.py:11-70: shifted CE where a target that is one of `soft_tokens` (the time tokens) is replaced by a
+    Gaussian over the soft-token IDs, exp(-(target_id - soft_id)^2 / (2 std^2)) normalised; sum / number of valid
+    targets."""
+    out = logits[..., :-1, :].reshape(-1, logits.shape[-1])
+    tgt = targets[..., 1:].reshape(-1)
+    keep = tgt != IGNORE_INDEX
+    out, tgt = out[keep], tgt[keep]
+    if out.numel() == 0:
+        return torch.zeros((), dtype=logits.dtype)
+    soft = torch.as_tensor(soft_tokens, dtype=tgt.dtype)
+    is_soft = torch.isin(tgt, soft)
+    lsm = F.log_softmax(out.float(), dim=-1)
+    loss = -lsm[~is_soft].gather(1, tgt[~is_soft][:, None]).sum()
+    if is_soft.any():
+        d = torch.exp(-((tgt[is_soft][:, None] - soft[None, :]) ** 2).float() / (2 * std ** 2))
+        d = d / d.sum(dim=1, keepdim=True)
+        loss = loss - (lsm[is_soft][:, soft] * d).sum()
+    return loss / tgt.shape[0]
+
+
+def navila_forward(sd, cfg: dict, input_ids, attention_mask, images, labels, time_token_ids=None, soft_ce_std=1.0):
+    """NaVILAForCausalLM.forward (navila_arch.py:362-497), training path without sequence packing (HF decoders do not
+    take seqlens_in_batch, :415-417): SigLIP (select_layer -2) -> mlp_downsample -> splice (every row carries the same
+    number of <image> tokens, each consuming its share of the row's features, :166-205) -> decoder -> lm_head ->
+    HF ForCausalLMLoss (shifted, mean over labels != -100) or soft_cross_entropy when time_token_ids is set (:474-489).
+    images [B, 3, H, W] or [B, n, 3, H, W].  Returns dict(loss, logits, labels, attention_mask)."""
+    B = input_ids.shape[0]
+    imgs = images.reshape(-1, *images.shape[-3:])
+    feats = siglip_vision_features(sd, "model.mm_vision_tower.", imgs, cfg["vision"], select_layer=-2)
+    feats = navila_projector(sd, "model.mm_projector.", feats)                      # [B*n, P', d]
+    emb, lab, msk, pid = splice(sd["model.llm.embed_tokens.weight"], feats, input_ids, attention_mask, labels,
+                                cfg.get("tokenizer_model_max_length"), cfg.get("tokenizer_padding_side", "right"))
+    hidden = decoder_forward(sd, "model.llm.", emb, msk, pid, cfg["llm"])
+    logits = F.linear(hidden, sd["lm_head.weight"])
+    if time_token_ids:
+        loss = soft_cross_entropy(logits, lab, time_token_ids, soft_ce_std)
+    else:
+        sl = logits[:, :-1].reshape(-1, logits.shape[-1]).float()
+        st = lab[:, 1:].reshape(-1)
+        loss = F.cross_entropy(sl, st, ignore_index=IGNORE_INDEX, reduction="mean")
+    return dict(loss=loss, logits=logits, labels=lab, attention_mask=msk)

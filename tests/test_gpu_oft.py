@@ -259,3 +259,50 @@ def test_oft_discrete_with_proprio_matches_reference_golden():
         rel = ((g - r).norm() / (r.norm() + 1e-12)).item()
         cos = torch.nn.functional.cosine_similarity(g, r, dim=0).item()
         assert rel < 0.12 and cos > 0.99, (name, rel, cos)
+
+
+def test_oft_discrete_full_vocabulary_ce_and_argmax_match_oracle():
+    """The discrete head at the PRODUCTION vocabulary (Qwen2.5: V = 152 064) on 56 action rows x B = 4 samples
+    (BASELINE.json config 4: chunk 8 x dim 7): fused fp32 cross-entropy loss and gradient against torch's fp32
+    F.cross_entropy on the same bf16 logits (ignore_index rows included), and the restricted argmax over the last
+    255 entries against the oracle's restatement of oft_discrete_arch.py:222-224 — bit-exact, including exact ties
+    (first maximum wins) and maxima that sit OUTSIDE the action range (must be ignored)."""
+    import numpy as np
+    from dexbotic_b200 import ops
+    from oracle import vla_oracle
+    V, rows = 152064, 56 * 4
+    g = torch.Generator(device="cuda").manual_seed(77)
+    logits = (torch.randn((rows, V), device="cuda", generator=g) * 2.0).to(torch.bfloat16)
+    labels = torch.randint(V - 255, V, (rows,), device="cuda", generator=g)
+    labels[5] = -100
+    labels[100:104] = -100
+    # ties inside the action range (bf16 makes them exact), and a larger value just outside it
+    logits[3, V - 200] = 30.0
+    logits[3, V - 100] = 30.0
+    logits[3, V - 17] = 30.0
+    logits[7, V - 255] = 25.0
+    logits[7, V - 1] = 25.0
+    logits[9, V - 256] = 99.0          # index V-256 is NOT an action token
+    logits[11, :] = 1.5                # a whole row of equal logits: index 0 of the range wins
+    # ---- restricted argmax: bit-exact
+    got = ops.argmax_last(logits, 255).cpu().numpy()
+    ref = vla_oracle.oft_argmax_decode(logits.float().cpu().numpy(), 255)
+    assert got.dtype == np.int64 and np.array_equal(got, ref)
+    assert got[3] == 255 - 200 and got[7] == 0 and got[11] == 0 and 0 <= got.min() and got.max() <= 254
+    # ---- cross entropy forward / backward (fp32 accumulation over the bf16 logits)
+    loss_sum, n_valid, lse = ops.cross_entropy_fwd(logits, labels)
+    lr = logits.float().requires_grad_(True)
+    ref_loss = torch.nn.functional.cross_entropy(lr, labels, ignore_index=-100, reduction="mean")
+    assert int(n_valid.item()) == rows - 5
+    loss = loss_sum.item() / n_valid.item()
+    assert abs(loss - ref_loss.item()) < 2e-5 * abs(ref_loss.item()), (loss, ref_loss.item())
+    assert torch.allclose(lse, torch.logsumexp(lr.detach(), -1), rtol=0, atol=2e-5)
+    d = ops.cross_entropy_bwd(logits, labels, lse, n_valid)
+    ref_loss.backward()
+    assert d.dtype == torch.bfloat16
+    dr = lr.grad
+    assert (d[5].abs().max().item() == 0.0) and (d[100:104].abs().max().item() == 0.0)     # ignored rows: exactly 0
+    err = (d.float() - dr).abs().max().item()
+    assert err <= 2.0 ** -8 * dr.abs().max().item() + 1e-9, (err, dr.abs().max().item())   # one bf16 rounding
+    rowsum = d.float().sum(-1).abs().max().item()
+    assert rowsum < 1e-3 * dr.abs().max().item() * 40, rowsum                                # softmax - onehot sums to 0

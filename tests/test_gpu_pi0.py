@@ -46,7 +46,11 @@ def test_pi0_tiny_matches_reference_golden():
         rel, cos = _rel(model.store.g(name), gref.cuda())
         # vision-tower gradients are the deepest in the graph (tower -> projector -> every joint layer) and, at the
         # tiny widths of this fixture (hidden 32, head_dim 16), carry the most bf16 rounding noise
-        lim, cmin = (0.2, 0.98) if "mm_vision_tower" in name else (0.12, 0.99)
+        # The attention backward recomputes P from the saved log-sum-exp and takes the softmax row term as
+        # rowsum(dO * O) with O in bf16 (flash attention); at head_dim 16 / width 32 that rounding is a visible share
+        # of the gradient (0.12-0.15 relative on the input-side projections), at the production widths it is not
+        # (test_pi0_production_dims_one_layer_matches_oracle holds 0.08).
+        lim, cmin = (0.2, 0.98) if "mm_vision_tower" in name else (0.16, 0.99)
         if not (rel < lim and cos > cmin):
             bad.append((name, round(rel, 4), round(cos, 5)))
     assert not bad, bad
@@ -107,7 +111,10 @@ def test_pi0_inference_cache_equals_joint_forward():
                     time=torch.ones(B, device="cuda"))
     want = noise - out.logits.float()
     rel, cos = _rel(one, want)
-    assert rel < 1e-2 and cos > 0.9999, (rel, cos)
+    # the cached-prefix step runs the suffix rows through the Sq != Sk attention (normalised bf16 probabilities), the
+    # joint forward through the flash kernel (unnormalised bf16 P, fp32 normalisation at the end): two bf16 roundings
+    # of the same softmax, visible at this fixture's head_dim 16
+    assert rel < 2e-2 and cos > 0.9998, (rel, cos)
 
 
 def test_pi0_overlapped_optimizer_equals_synchronous():
@@ -135,3 +142,67 @@ def test_pi0_overlapped_optimizer_equals_synchronous():
         assert not model.store._chunk_events
         runs.append(ls)
     assert max(abs(a - b) for a, b in zip(*runs)) < 5e-3 * abs(runs[0][0]), runs
+
+
+def test_pi0_production_dims_one_layer_matches_oracle():
+    """One joint layer at the PRODUCTION geometry of BASELINE.json config 3: Gemma-2B (d=2048, 8 q heads on 1 kv head,
+    head_dim 256, GeGLU 16384) + the 300M action expert (d=1024, same heads), one SigLIP-So400m layer (d=1152, 16 heads
+    x 72, MLP 4304) over 3 cameras x 256 patches, joint sequence 768 + 48 + 51 = 867 > 512 — the flash-attention kernel
+    variant with 256-wide heads, the block-causal pi0 mask and left/right padding inside it."""
+    from oracle import vla_oracle
+    from oracle.weights import seeded_state_dict
+    from dexbotic_b200.model import Pi0Config, Pi0ForCausalLM
+    llm = dict(model_type="gemma", vocab_size=512, hidden_size=2048, intermediate_size=16384, num_hidden_layers=1,
+               num_attention_heads=8, num_key_value_heads=1, head_dim=256, rms_norm_eps=1e-6, rope_theta=10000.0,
+               hidden_act="gelu_pytorch_tanh")
+    exp = dict(llm, hidden_size=1024, intermediate_size=4096)
+    vis = dict(model_type="siglip_vision_model", hidden_size=1152, intermediate_size=4304, num_hidden_layers=1,
+               num_attention_heads=16, image_size=224, patch_size=14, hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6)
+    T, A, B, L = 50, 32, 2, 48
+    cfg = dict(llm=llm, expert=exp, vision=vis, chunk_size=T, action_dim=A)
+    model = Pi0ForCausalLM(Pi0Config(llm_config=llm, action_config=exp, vision_config=vis, action_dim=A, chunk_size=T),
+                           device="cuda")
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 21)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    g = torch.Generator().manual_seed(31)
+    ids = torch.randint(1, 512, (B, L), generator=g)
+    mask = torch.ones(B, L, dtype=torch.bool)
+    mask[1, 29:] = False
+    images = torch.randn(B, 3, 3, 224, 224, generator=g)
+    image_masks = torch.ones(B, 3, dtype=torch.bool)
+    image_masks[1, 2] = False                       # a missing camera: 256 masked keys inside the prefix
+    actions = torch.randn(B, T, A, generator=g)
+    states = torch.randn(B, A, generator=g)
+    noise = torch.randn(B, T, A, generator=g)
+    time = torch.rand(B, generator=g) * 0.999 + 0.001
+    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ora = vla_oracle.pi0_forward(sd_g, cfg, ids, mask, images, image_masks, actions, states, noise, time)
+    ora["loss"].backward()
+    model.zero_grad()
+    out = model(input_ids=ids.cuda(), attention_mask=mask.cuda(), images=images.cuda(), image_masks=image_masks.cuda(),
+                actions=actions.cuda(), states=states.cuda(), noise=noise.cuda(), time=time.cuda())
+    assert abs(out.loss.item() - ora["loss"].item()) < 2e-2 * abs(ora["loss"].item()), (out.loss.item(), ora["loss"].item())
+    rel, cos = _rel(out.logits.cpu(), ora["v_t"].detach())
+    assert rel < 5e-2 and cos > 0.998, (rel, cos)
+    out.loss.backward()
+    bad = []
+    # (the prefix stream's q_proj has no gradient in a one-layer model: the last layer's prefix outputs are unused)
+    for name in ["model.llm.layers.0.self_attn.k_proj.weight",
+                 "model.llm.layers.0.self_attn.v_proj.weight", "model.action_expert.layers.0.self_attn.q_proj.weight",
+                 "model.action_expert.layers.0.self_attn.k_proj.weight",
+                 "model.action_expert.layers.0.self_attn.v_proj.weight",
+                 "model.action_expert.layers.0.self_attn.o_proj.weight",
+                 "model.action_expert.layers.0.mlp.down_proj.weight", "model.action_in_proj.weight",
+                 "model.action_time_mlp_in.weight", "model.state_proj.weight", "model.mm_projector.weight",
+                 "model.mm_vision_tower.vision_tower.vision_model.encoder.layers.0.self_attn.q_proj.weight",
+                 "model.mm_vision_tower.vision_tower.vision_model.encoder.layers.0.mlp.fc1.weight"]:
+        gm = model.store.g(name)
+        go = sd_g[name].grad
+        if gm is None or go is None:
+            assert gm is None and (go is None or go.abs().max() == 0), name
+            continue
+        rel, cos = _rel(gm.cpu(), go)
+        if not (rel < 0.08 and cos > 0.995):
+            bad.append((name, round(rel, 4), round(cos, 5)))
+    assert not bad, bad

@@ -12,7 +12,7 @@ import bench  # noqa: E402
 def main():
     import os
     import torch.distributed as dist
-    from dexbotic_b200.parallel import GradientOverlap
+    from dexbotic_b200.parallel import GradientOverlap, ShardedDataParallel
     w = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cogact_7b"]
     local, world = int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
@@ -20,7 +20,9 @@ def main():
     if world > 1:                      # torchrun: profile rank 0 of a data-parallel step (NCCL kernels included)
         dist.init_process_group("nccl", device_id=dev)
     model = bench.build_model(w, dev)
-    overlap = GradientOverlap(model.store)
+    overlap = (ShardedDataParallel(model.store) if world > 1 and os.environ.get("B200_DP", "zero1") == "zero1"
+               else GradientOverlap(model.store))
+    model.store.async_optimizer = True
     model.init_weights_(seed=1234)
     model.train()
     batch = {k: (v.to(dev) if hasattr(v, "to") else v) for k, v in bench.make_batch(w, 0, pinned=False).items()}
