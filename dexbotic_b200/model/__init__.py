@@ -2,11 +2,12 @@
 forward signatures, config fields and state-dict keys; the arithmetic runs in libdexbotic_b200.so."""
 from .dexbotic_arch import (CausalLMOutputDexbotic, DexboticConfig, DexboticVLMModel, IGNORE_INDEX,  # noqa: F401
                             IMAGE_TOKEN_INDEX)
-from .cogact_arch import CogActConfig, CogActModel, CogACTForCausalLM  # noqa: F401
+from .cogact_arch import CogActConfig, CogActModel, CogACTForCausalLM, HybridCogACTForCausalLM  # noqa: F401
 from .oft_arch import OFTConfig, OFTDiscreteConfig, OFTDiscreteForCausalLM, OFTForCausalLM  # noqa: F401
 from .pi0_arch import Pi0Config, Pi0ForCausalLM  # noqa: F401
 from .memvla_arch import MemVLAConfig, MemVLAForCausalLM, MemVLAModel  # noqa: F401
 from .pi05_arch import Pi05Config, Pi05ForCausalLM  # noqa: F401
+from .navila_arch import NaVILAConfig, NaVILAForCausalLM, NaVILAModel  # noqa: F401
 
 # model_type string (DexboticConfig subclasses' `model_type`, written to config.json by save_pretrained) -> classes
 MODEL_TYPES = {
@@ -16,6 +17,7 @@ MODEL_TYPES = {
     OFTConfig.model_type: (OFTConfig, OFTForCausalLM),
     OFTDiscreteConfig.model_type: (OFTDiscreteConfig, OFTDiscreteForCausalLM),
     MemVLAConfig.model_type: (MemVLAConfig, MemVLAForCausalLM),
+    NaVILAConfig.model_type: (NaVILAConfig, NaVILAForCausalLM),
 }
 
 

@@ -195,8 +195,11 @@ class ActionModel:
         return out.view(N, T + 1, A)[:, 1:, :]
 
     def loss(self, module, x, z, noise: Optional[torch.Tensor] = None, timestep: Optional[torch.Tensor] = None,
-             drop_mask: Optional[torch.Tensor] = None, training: bool = True, per_token=None, groups: int = 1):
-        """ActionModel.loss (action_models.py:102-125).  noise / timestep / drop_mask may be injected for parity."""
+             drop_mask: Optional[torch.Tensor] = None, training: bool = True, per_token=None, groups: int = 1,
+             sample_weight: Optional[torch.Tensor] = None):
+        """ActionModel.loss (action_models.py:102-125).  noise / timestep / drop_mask may be injected for parity.
+        sample_weight [N] (hybrid co-training, hybrid_cogact_arch.py:182-187: reduction="none", per-sample mean times
+        has_action, summed and divided by sum(has_action) + 1e-6): sum_n w_n mean_{t,a}(d_n^2) / (sum w + 1e-6)."""
         N = x.shape[0]
         if noise is None:
             noise = torch.randn_like(x)
@@ -208,7 +211,12 @@ class ActionModel:
         x_t = _QSampleFn.apply(x, noise, t32, self.sqrt_ac, self.sqrt_1mac)
         pred = self.net(module, x_t, t32, z, drop_mask, per_token, groups)
         assert pred.shape == noise.shape == x.shape
-        return MSELossFn.apply(pred, noise)
+        if sample_weight is None:
+            return MSELossFn.apply(pred, noise)
+        # mean over all N*T*A of w_n d^2 equals (1/N) sum_n w_n mean_ta(d_n^2): scale both sides by sqrt(w_n) (a few KB)
+        w = sample_weight.reshape(N).to(torch.float32)
+        r = w.sqrt()[:, None, None]
+        return MSELossFn.apply(pred * r, noise * r) * (N / (w.sum() + 1e-6))
 
 
     # ------------------------------------------------------------------ inference (cogact_arch.py:149-198)

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .. import ops
-from ..functional import CastFn, GatherRowsFn
+from ..functional import CastFn, CrossEntropyFn, GatherRowsFn, Lin, LinearFn
 from ..params import ParamSpec
 from ._module import B200Module
 from .action_model import ActionModel, action_head_specs
@@ -49,6 +49,7 @@ class CogActModel(DexboticVLMModel):
 class CogACTForCausalLM(B200Module):
     """cogact_arch.py:47-198."""
     config_class = CogActConfig
+    lm_head_trainable = False      # lm_head exists in the reference (cogact_arch.py:52) but is unused by plain CogACT
 
     def __init__(self, config: CogActConfig, device="cuda"):
         super().__init__()
@@ -62,8 +63,8 @@ class CogACTForCausalLM(B200Module):
                                    trainable=not config.freeze_mm_projector)
                  + action_head_specs(config.action_model_type, d, config.action_dim, config.chunk_size,
                                      trainable=not getattr(config, "freeze_action_head", False))
-                 # lm_head exists in the reference (cogact_arch.py:52) but never receives a gradient in CogACT
-                 + [ParamSpec("lm_head.weight", (V, d), "lm_head", trainable=False)])
+                 # lm_head never receives a gradient in CogACT; the hybrid (text + action) variant trains it
+                 + [ParamSpec("lm_head.weight", (V, d), "lm_head", trainable=self.lm_head_trainable, no_decay=False)])
         store = self._materialize(specs, device)
         # fp32 (region B) parameters take their torch .grad directly from the flat gradient buffer
         for name in store.order:
@@ -154,3 +155,65 @@ class CogACTForCausalLM(B200Module):
         norm = self.store.adamw_step(lrs, betas, eps, weight_decay, max_grad_norm)
         self.model_engine.refresh()
         return norm
+
+
+class HybridCogACTForCausalLM(CogACTForCausalLM):
+    """cogact/hybrid_cogact_arch.py:51-255: co-training of language and actions.  On top of CogACT's forward:
+    text_loss = HF ForCausalLMLoss(lm_head(hidden), labels) * has_text.any() and an action loss weighted per sample by
+    has_action; `loss = text_loss + action_loss`, both also returned (DexboticTrainer.compute_loss logs every *_loss,
+    trainer.py:126-138).  As in the reference (:131-141), the rows without text are masked only when NO row has text,
+    which leaves zero targets: text_loss (and the sum) is NaN for such a batch — reproduced, not repaired."""
+    lm_head_trainable = True
+
+    def __init__(self, config: CogActConfig, device="cuda"):
+        super().__init__(config, device=device)
+        self.lm_head_lin = Lin.of(self.store, "lm_head.weight")
+
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
+                labels=None, use_cache=None, output_attentions=None, output_hidden_states=None, images=None,
+                return_dict=None, cache_position=None, actions=None, states=None, repeated_diffusion_steps: int = 4,
+                has_action: Optional[torch.Tensor] = None, has_text: Optional[torch.Tensor] = None,
+                noise=None, timesteps=None, drop_mask=None, **kwargs) -> CausalLMOutputDexbotic:
+        if images is None or input_ids is None:
+            raise NotImplementedError("training forward needs input_ids and images")
+        if not input_ids.is_cuda:
+            raise RuntimeError("dexbotic_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        eng, cfg = self.model_engine, self.config
+        emb, new_labels, new_mask, pos, S, _ = eng._prepare_inputs_labels_for_multimodal(
+            input_ids, attention_mask, labels, images)
+        B = input_ids.shape[0]
+        hidden2d = eng.llm.forward(emb.view(B * S, -1), B, S, new_mask, pos)
+        text_loss = action_loss = None
+        if labels is not None:
+            assert has_action is not None and has_text is not None, "has_action / has_text must be provided"
+            ht = has_text.bool().view(-1)
+            any_text = bool(ht.any())                              # one host sync, as the reference's `if` (:134)
+            tgt = new_labels[:, 1:]
+            keep = (tgt != -100) if any_text else torch.zeros_like(tgt, dtype=torch.bool)
+            bs = keep.nonzero(as_tuple=False)
+            if bs.shape[0] == 0:                                   # mean over zero targets: NaN, times has_text.any()
+                text_loss = hidden2d.new_full((), float("nan"), dtype=torch.float32)
+            else:
+                rows = (bs[:, 0] * S + bs[:, 1]).to(torch.int32).contiguous()
+                logits2d = LinearFn.apply(GatherRowsFn.apply(hidden2d, rows), self.lm_head_lin, None, self.store, True,
+                                          None)
+                text_loss = CrossEntropyFn.apply(logits2d, tgt[keep].contiguous()) * float(any_text)
+        if actions is not None:
+            assert has_action is not None, "has_action must be provided"
+            idx = ops.last_valid_index(new_mask)
+            cog32 = CastFn.apply(GatherRowsFn.apply(hidden2d, idx), torch.float32)[:, None, :]
+            a = actions.reshape(B, -1, cfg.action_dim).to(torch.float32)[:, :cfg.chunk_size, :]
+            R = repeated_diffusion_steps
+            w = has_action.reshape(-1).to(torch.float32).repeat(R)
+            action_loss = eng.action_head.loss(self, a.repeat(R, 1, 1), cog32.repeat(R, 1, 1), noise, timesteps,
+                                               drop_mask, training=self.training, sample_weight=w)
+        loss = None
+        if text_loss is not None and action_loss is not None:
+            loss = text_loss + action_loss
+        elif text_loss is not None:
+            loss = text_loss
+        elif action_loss is not None:
+            loss = action_loss
+        out = CausalLMOutputDexbotic(loss=loss, logits=hidden2d.view(B, S, -1))
+        out.text_loss, out.action_loss = text_loss, action_loss
+        return out

@@ -256,7 +256,9 @@ class CLIPVisionTower:
     def refresh(self) -> None:
         """bf16 K-padded copy of the conv weight (588 -> 592 columns: TMA rows must be 16-byte multiples)."""
         K = self.C * self.patch * self.patch
-        w = self.store.master_view(self.prefix + "embeddings.patch_embedding.weight").view(self.D, K)
+        # read the compute copy (bf16 shadow: complete on every rank), not the fp32 master — under ZeRO-1 a rank's
+        # master holds current values only for the pieces it owns
+        w = self.store.w(self.prefix + "embeddings.patch_embedding.weight").view(self.D, K)
         ops.copy2d_(w, self.patch_w_pad, self.D, K)
 
     def forward(self, anchor: _Anchor, images: torch.Tensor) -> torch.Tensor:

@@ -37,8 +37,13 @@ class Pi0Config(DexboticConfig):
 
 
 # ------------------------------------------------------------------------------------ specs
-def siglip_specs(cfg, trainable: bool, prefix: str = "model.mm_vision_tower.vision_tower.vision_model.") -> list[ParamSpec]:
+def siglip_specs(cfg, trainable: bool, prefix: str = "model.mm_vision_tower.vision_tower.vision_model.",
+                 select_layer=None) -> list[ParamSpec]:
+    """select_layer=-2 (the tower's default outside pi0, siglip_encoder.py:13): the last encoder layer and the
+    post_layernorm never reach the output — the reference leaves them without gradient, here they are frozen."""
     D, inter, L = cfg_get(cfg, "hidden_size"), cfg_get(cfg, "intermediate_size"), cfg_get(cfg, "num_hidden_layers")
+    n_used = L if select_layer is None else L + 1 + select_layer
+    all_trainable = trainable
     ps, img, C = cfg_get(cfg, "patch_size"), cfg_get(cfg, "image_size"), cfg_get(cfg, "num_channels", 3)
     P = (img // ps) ** 2
     g = "vision"
@@ -47,6 +52,7 @@ def siglip_specs(cfg, trainable: bool, prefix: str = "model.mm_vision_tower.visi
           ParamSpec(prefix + "embeddings.position_embedding.weight", (P, D), g, trainable=trainable, no_decay=False)]
     for i in range(L):
         q = f"{prefix}encoder.layers.{i}."
+        trainable = all_trainable and i < n_used
         for n in ("layer_norm1", "layer_norm2"):
             sp.append(ParamSpec(f"{q}{n}.weight", (D,), g, trainable=trainable))
             sp.append(ParamSpec(f"{q}{n}.bias", (D,), g, trainable=trainable))
@@ -60,6 +66,7 @@ def siglip_specs(cfg, trainable: bool, prefix: str = "model.mm_vision_tower.visi
                ParamSpec(q + "mlp.fc1.bias", (inter,), g, trainable=trainable),
                ParamSpec(q + "mlp.fc2.weight", (D, inter), g, trainable=trainable),
                ParamSpec(q + "mlp.fc2.bias", (D,), g, trainable=trainable)]
+    trainable = all_trainable and select_layer is None
     sp += [ParamSpec(prefix + "post_layernorm.weight", (D,), g, trainable=trainable),
            ParamSpec(prefix + "post_layernorm.bias", (D,), g, trainable=trainable)]
     # multi-head attention pooling head: part of HF SiglipVisionModel's state dict, never on this path
@@ -139,8 +146,10 @@ class SiglipEmbedFn(torch.autograd.Function):
 class SiglipVisionTower:
     """modules/mm_vision/siglip/siglip_encoder.py with select_layer=None: last_hidden_state (post-LN), no CLS."""
 
-    def __init__(self, store: ParamStore, cfg, prefix: str = "model.mm_vision_tower.vision_tower.vision_model."):
+    def __init__(self, store: ParamStore, cfg, prefix: str = "model.mm_vision_tower.vision_tower.vision_model.",
+                 select_layer=None):
         self.store, self.cfg, self.prefix = store, cfg, prefix
+        self.select_layer = select_layer     # None: last_hidden_state (post-LN); -2: output of the second-to-last layer
         self.D, self.patch = cfg_get(cfg, "hidden_size"), cfg_get(cfg, "patch_size")
         self.P = (cfg_get(cfg, "image_size") // self.patch) ** 2
         self.C = cfg_get(cfg, "num_channels", 3)
@@ -174,7 +183,9 @@ class SiglipVisionTower:
 
     def refresh(self):
         K = self.C * self.patch * self.patch
-        w = self.store.master_view(self.prefix + "embeddings.patch_embedding.weight").view(self.D, K)
+        # read the compute copy (bf16 shadow: complete on every rank), not the fp32 master — under ZeRO-1 a rank's
+        # master holds current values only for the pieces it owns
+        w = self.store.w(self.prefix + "embeddings.patch_embedding.weight").view(self.D, K)
         ops.copy2d_(w, self.patch_w_pad, self.D, K)
 
     def forward(self, anchor: _Anchor, images: torch.Tensor) -> torch.Tensor:
@@ -182,8 +193,11 @@ class SiglipVisionTower:
         N = images.shape[0]
         x = SiglipEmbedFn.apply(anchor.t, images, self)
         env = AttnEnv(B=N, S=self.P)
-        for bw in self.blocks:
+        n_used = len(self.blocks) if self.select_layer is None else len(self.blocks) + 1 + self.select_layer
+        for bw in self.blocks[:n_used]:
             x = TransformerBlockFn.apply(x, bw, env, self.store, False)
+        if self.select_layer is not None:
+            return x
         return NormFn.apply(x, self.post_ln, self.store)
 
 

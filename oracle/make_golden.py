@@ -653,7 +653,152 @@ def make_cogact_inference_tiny(seed: int = 1234):
                     inputs=dict(input_ids=ids, images=images), outputs=outs), GOLDEN / "cogact_inference_tiny.pt")
 
 
+def make_hybrid_cogact_tiny(seed: int = 4321):
+    """HybridCogACTForCausalLM (hybrid_cogact_arch.py:60-218): mixed batch (some rows text-only, some action-only, some
+    both) and an action-only batch (text loss is NaN in the reference: see the oracle's docstring)."""
+    llm, clip, cfg = tiny_cogact_configs()
+    model = ref_loader.build_reference_hybrid_cogact(llm, clip, "DiT-S")
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    g = torch.Generator().manual_seed(seed)
+    B, L, R = 4, 14, 4
+    ids = torch.randint(1, 128, (B, L), generator=g)
+    ids[:, 1] = vla_oracle.IMAGE_TOKEN_INDEX
+    mask = torch.ones(B, L, dtype=torch.long)
+    mask[1, 10:] = 0
+    images = torch.randn(B, 3, 28, 28, generator=g)
+    actions = torch.rand(B, 16 * 7, generator=g) * 2 - 1
+    labels = ids.clone()
+    labels[:, :7] = vla_oracle.IGNORE_INDEX
+    labels[mask == 0] = vla_oracle.IGNORE_INDEX
+    cases = {}
+    for name, has_action, has_text in (("mixed", [1, 0, 1, 1], [1, 1, 0, 1]), ("no_text", [1, 1, 0, 1], [0, 0, 0, 0])):
+        ha, ht = torch.tensor(has_action).view(B, 1), torch.tensor(has_text).view(B, 1)
+        lab = labels.clone()
+        lab[ht.view(-1) == 0] = vla_oracle.IGNORE_INDEX            # the collator gives text-less rows no targets
+        model.zero_grad()
+        torch.manual_seed(seed + 1)
+        out = model(input_ids=ids, attention_mask=mask, images=images, actions=actions, labels=lab, has_action=ha,
+                    has_text=ht, repeated_diffusion_steps=R)
+        torch.manual_seed(seed + 1)
+        noise = torch.randn(R * B, 16, 7)
+        timesteps = torch.randint(0, 100, (R * B,))
+        drop = torch.rand(R * B) < 0.1
+        sd_g = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+        ora = vla_oracle.hybrid_cogact_forward(sd_g, cfg, ids, mask, images, actions, lab, ha, ht, noise, timesteps,
+                                               drop, R)
+        d_act = abs(ora["action_loss"].item() - out.action_loss.item())
+        same_text = (torch.isnan(out.text_loss) and torch.isnan(ora["text_loss"])) or \
+            abs(ora["text_loss"].item() - out.text_loss.item()) < 1e-5
+        print(f"[hybrid_cogact/{name}] reference text {out.text_loss.item():.6f} action {out.action_loss.item():.6f}; "
+              f"oracle text {ora['text_loss'].item():.6f} action {ora['action_loss'].item():.6f}")
+        assert d_act < 1e-5 and same_text
+        grads = {}
+        if name == "mixed":
+            out.loss.backward()
+            ora["loss"].backward()
+            params = dict(model.named_parameters())
+            for n in ["lm_head.weight", "model.llm.layers.0.self_attn.q_proj.weight", "model.llm.layers.1.mlp.down_proj.weight",
+                      "model.llm.embed_tokens.weight", "model.mm_projector.0.weight",
+                      "model.action_head.net.final_layer.linear.weight", "model.action_head.net.blocks.0.attn.qkv.weight"]:
+                gr = params[n].grad
+                rel = ((sd_g[n].grad - gr).norm() / gr.norm()).item()
+                assert rel < 1e-4, (n, rel)
+                grads[n] = gr.detach().clone()
+        cases[name] = dict(inputs=dict(input_ids=ids, attention_mask=mask, images=images, actions=actions, labels=lab,
+                                       has_action=ha, has_text=ht, noise=noise, timesteps=timesteps, drop_mask=drop,
+                                       repeated_diffusion_steps=R),
+                           outputs=dict(text_loss=out.text_loss.detach(), action_loss=out.action_loss.detach(),
+                                        loss=out.loss.detach(), grads=grads))
+    torch.save(dict(seed=seed, cfg=cfg, shapes={k: tuple(v.shape) for k, v in sd.items()}, cases=cases),
+               GOLDEN / "hybrid_cogact_tiny.pt")
+    print(f"[hybrid_cogact_tiny] wrote {GOLDEN / 'hybrid_cogact_tiny.pt'}")
+
+
+def tiny_navila_configs():
+    from transformers import SiglipVisionConfig
+    llm = dict(model_type="llama", vocab_size=160, hidden_size=64, intermediate_size=160, num_hidden_layers=2,
+               num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256, rope_theta=10000.0,
+               rms_norm_eps=1e-6, hidden_act="silu")
+    # 70 / 14 = 5 x 5 patches: an ODD grid, so the 2x2 down-sampling pads it to 6 x 6 -> 9 tokens of 4 x 32 channels
+    vis_kw = dict(hidden_size=32, intermediate_size=64, num_hidden_layers=3, num_attention_heads=2, image_size=70,
+                  patch_size=14, hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6)
+    return llm, SiglipVisionConfig(**vis_kw), dict(vis_kw, model_type="siglip_vision_model")
+
+
+def make_navila_tiny(seed: int = 1357):
+    """NaVILAForCausalLM training forward (navila_arch.py:362-497): plain shifted CE and the soft cross entropy over the
+    time tokens (navila/loss.py), single-image rows and a 2-frame 5-D batch."""
+    ref_loader.load_reference_navila()
+    from dexbotic.model.modules.mm_projector.builder import DownSampleBlock
+    llm, vis_cfg, vis = tiny_navila_configs()
+    x = torch.randn(2, 25, 6)
+    assert torch.equal(DownSampleBlock()(x), vla_oracle.downsample_2x2(x))
+    time_tokens = [150, 151, 152, 153, 154, 155]
+    cfg = dict(llm=llm, vision=vis, tokenizer_model_max_length=None, tokenizer_padding_side="right")
+    cases = {}
+    for name, soft, frames in (("ce", None, 1), ("soft_ce", time_tokens, 1), ("ce_two_frames", None, 2)):
+        model = ref_loader.build_reference_navila(llm, vis_cfg, time_token_ids=soft, soft_ce_std=1.5)
+        sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        g = torch.Generator().manual_seed(seed + len(name))
+        B, L = 3, 16
+        ids = torch.randint(1, 150, (B, L), generator=g)
+        ids[:, 2] = vla_oracle.IMAGE_TOKEN_INDEX
+        if frames == 2:
+            ids[:, 5] = vla_oracle.IMAGE_TOKEN_INDEX
+        mask = torch.ones(B, L, dtype=torch.long)
+        mask[1, 12:] = 0
+        labels = ids.clone()
+        labels[:, :8] = vla_oracle.IGNORE_INDEX                      # the prompt is not a target
+        labels[mask == 0] = vla_oracle.IGNORE_INDEX
+        if soft:                                                     # some targets are time tokens, incl. both ends
+            labels[0, 9], labels[0, 12], labels[2, 10], labels[1, 9] = 150, 155, 152, 153
+            ids[0, 9], ids[0, 12], ids[2, 10], ids[1, 9] = 150, 155, 152, 153
+        images = torch.randn(B, 3, 70, 70, generator=g) if frames == 1 else torch.randn(B, 2, 3, 70, 70, generator=g)
+        out = model(input_ids=ids, attention_mask=mask, images=images, labels=labels)
+        out.loss.backward()
+        sd_g = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+        ora = vla_oracle.navila_forward(sd_g, cfg, ids, mask, images, labels, time_token_ids=soft, soft_ce_std=1.5)
+        ora["loss"].backward()
+        d_loss = abs(ora["loss"].item() - out.loss.item())
+        valid = ora["attention_mask"][:, :, None]
+        d_log = ((ora["logits"] - out.logits) * valid).abs().max().item()
+        names = ["model.llm.layers.0.self_attn.q_proj.weight", "model.llm.layers.1.mlp.down_proj.weight",
+                 "model.llm.embed_tokens.weight", "model.llm.norm.weight", "lm_head.weight",
+                 "model.mm_projector.1.weight", "model.mm_projector.2.weight", "model.mm_projector.4.bias",
+                 "model.mm_vision_tower.vision_tower.vision_model.encoder.layers.0.self_attn.k_proj.weight",
+                 "model.mm_vision_tower.vision_tower.vision_model.encoder.layers.1.mlp.fc2.weight",
+                 "model.mm_vision_tower.vision_tower.vision_model.embeddings.patch_embedding.weight",
+                 "model.mm_vision_tower.vision_tower.vision_model.embeddings.position_embedding.weight"]
+        params = dict(model.named_parameters())
+        grads, worst = {}, 0.0
+        for n in names:
+            gr = params[n].grad
+            grads[n] = gr.detach().clone()
+            worst = max(worst, ((sd_g[n].grad - gr).norm() / gr.norm()).item())
+        none_grad = sorted(n for n, p_ in params.items() if p_.grad is None or p_.grad.abs().max() == 0)
+        print(f"[navila_tiny/{name}] reference loss {out.loss.item():.8f} oracle {ora['loss'].item():.8f} "
+              f"|d|={d_loss:.2e}; logits max|d|={d_log:.2e}; grads rel {worst:.2e}; {len(none_grad)} params without grad")
+        assert d_loss < 1e-5 and d_log < 2e-4 and worst < 1e-4
+        cases[name] = dict(inputs=dict(input_ids=ids, attention_mask=mask, images=images, labels=labels),
+                           time_token_ids=soft, soft_ce_std=1.5,
+                           outputs=dict(loss=out.loss.detach(), logits=(out.logits * valid).detach(),
+                                        valid=ora["attention_mask"], grads=grads, none_grad=none_grad))
+    torch.save(dict(seed=seed, cfg=cfg, shapes={k: tuple(v.shape) for k, v in sd.items()}, cases=cases),
+               GOLDEN / "navila_tiny.pt")
+    print(f"[navila_tiny] wrote {GOLDEN / 'navila_tiny.pt'}")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:                      # python oracle/make_golden.py make_navila_tiny
+        for fn in sys.argv[1:]:
+            globals()[fn]()
+        sys.exit(0)
+    make_navila_tiny()
+    make_hybrid_cogact_tiny()
     make_cogact_tiny()
     make_cogact_inference_tiny()
     make_pi0_tiny()

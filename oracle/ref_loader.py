@@ -379,3 +379,13 @@ def build_reference_navila(llm_config: dict, vision_config, time_token_ids=None,
     if time_token_ids:
         cfg.time_token_ids, cfg.soft_ce_std = list(time_token_ids), soft_ce_std
     return mod.NaVILAForCausalLM(cfg)
+
+
+def build_reference_hybrid_cogact(llm_config, clip_config, action_model_type: str = "DiT-S", action_dim: int = 7,
+                                  chunk_size: int = 16, mm_projector_type: str = "mlp2x_gelu"):
+    """Reference HybridCogACTForCausalLM (cogact/hybrid_cogact_arch.py:51-58): text + action co-training."""
+    load_reference()
+    from dexbotic.model.cogact.hybrid_cogact_arch import CogActConfig, HybridCogACTForCausalLM
+    cfg = CogActConfig(llm_config=llm_config, mm_projector_type=mm_projector_type, mm_vision_tower=clip_config,
+                       action_model_type=action_model_type, action_dim=action_dim, chunk_size=chunk_size)
+    return HybridCogACTForCausalLM(cfg)

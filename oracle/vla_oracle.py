@@ -334,6 +334,36 @@ def cogact_forward(sd, cfg: dict, input_ids, attention_mask, images, actions, no
                 attention_mask=msk, position_ids=pid, labels=lab, image_features=feats, noise_pred=pred)
 
 
+def hybrid_cogact_forward(sd, cfg: dict, input_ids, attention_mask, images, actions, labels, has_action, has_text,
+                          noise, timesteps, drop_mask, repeated_diffusion_steps: int = 4):
+    """HybridCogACTForCausalLM.forward (cogact/hybrid_cogact_arch.py:60-218): co-training of text and actions.
+    text_loss = HF ForCausalLMLoss(lm_head(hidden), labels) * has_text.any()  — as written at :131-141, the labels of
+    the rows without text are only masked when NO row has text (`~has_text.any()`), which leaves no target at all: the
+    mean over zero targets is NaN there (reproduced, not repaired);
+    action_loss = sum_n has_action[n] * mean_{t,a}((eps_pred - eps)^2) / (sum_n has_action[n] + 1e-6) over the R
+    repeats (:182-187).  loss = text_loss + action_loss."""
+    tr = cogact_like_trunk(sd, cfg, input_ids, attention_mask, images, labels)
+    hs, cog, lab = tr["last_hidden"], tr["cognition"], tr["labels"]
+    logits = F.linear(hs, sd["lm_head.weight"])
+    ht = has_text.bool().view(-1)
+    text_labels = lab.clone()
+    if not bool(ht.any()):
+        text_labels[~ht] = IGNORE_INDEX
+    sl = logits[:, :-1].reshape(-1, logits.shape[-1]).float()
+    st = text_labels[:, 1:].reshape(-1)
+    text_loss = F.cross_entropy(sl, st, ignore_index=IGNORE_INDEX, reduction="mean") * ht.any().float()
+    A, T, R = cfg["action_dim"], cfg["chunk_size"], repeated_diffusion_steps
+    a = actions.reshape(actions.shape[0], -1, A)[:, :T].float()
+    sa, sb = cosine_schedule(cfg.get("diffusion_steps", 100))
+    x_t = q_sample(a.repeat(R, 1, 1), timesteps, noise, sa, sb)
+    width = sd["model.action_head.net.x_embedder.linear.weight"].shape[0]
+    pred = dit_forward(sd, "model.action_head.", x_t, timesteps, cog.repeat(R, 1, 1), drop_mask, DIT_HEADS[width])
+    w = has_action.reshape(-1).float().repeat(R)
+    action_loss = (((pred - noise) ** 2).mean(dim=[1, 2]) * w).sum() / (w.sum() + 1e-6)
+    return dict(loss=text_loss + action_loss, text_loss=text_loss, action_loss=action_loss, last_hidden=hs,
+                attention_mask=tr["attention_mask"])
+
+
 # ----------------------------------------------------------------------------------------------
 # MemVLA — memvla_arch.py:82-427 (memory modules), :546-664 (training forward)
 # ----------------------------------------------------------------------------------------------

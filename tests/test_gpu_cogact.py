@@ -325,3 +325,39 @@ def test_overlapped_optimizer_equals_synchronous():
     noise, got = dist(finals[0], finals[1]), dist(finals[0], finals[2])
     bad = {k: (got[k], noise[k]) for k in got if got[k] > 3 * noise[k] + 2e-3}
     assert not bad, bad
+
+
+def test_hybrid_cogact_matches_reference_golden():
+    """HybridCogACTForCausalLM (text + action co-training, hybrid_cogact_arch.py:60-218) vs the unmodified reference:
+    a mixed batch (has_text / has_action differ per row: text loss, weighted action loss, gradients incl. lm_head) and
+    an action-only batch (the reference's text loss is NaN there; the action loss still matches)."""
+    from dexbotic_b200.model import CogActConfig, HybridCogACTForCausalLM
+    from oracle.weights import seeded_state_dict
+    fx = torch.load(GOLDEN / "hybrid_cogact_tiny.pt", weights_only=False)
+    cfg = fx["cfg"]
+    c = CogActConfig(llm_config=cfg["llm"], mm_vision_tower=cfg["vision"], action_model_type="DiT-S", action_dim=7,
+                     chunk_size=16)
+    model = HybridCogACTForCausalLM(c)
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == {k: tuple(v) for k, v in fx["shapes"].items()}
+    model.load_state_dict(seeded_state_dict(fx["shapes"], fx["seed"]))
+    model.train()
+    for name in ("mixed", "no_text"):
+        case = fx["cases"][name]
+        i = {k: (v.cuda() if hasattr(v, "cuda") else v) for k, v in case["inputs"].items()}
+        ref = case["outputs"]
+        model.zero_grad()
+        out = model(**i)
+        assert abs(out.action_loss.item() - ref["action_loss"].item()) < 2e-2 * abs(ref["action_loss"].item())
+        if name == "no_text":
+            assert torch.isnan(out.text_loss) and torch.isnan(ref["text_loss"]) and torch.isnan(out.loss)
+            continue
+        assert abs(out.text_loss.item() - ref["text_loss"].item()) < 2e-2 * abs(ref["text_loss"].item())
+        assert abs(out.loss.item() - ref["loss"].item()) < 2e-2 * abs(ref["loss"].item())
+        assert set(k for k in out.keys() if k.endswith("_loss")) == {"text_loss", "action_loss"}
+        out.loss.backward()
+        bad = []
+        for pname, gref in ref["grads"].items():
+            rel, cos = _rel(model.store.g(pname).cpu(), gref)
+            if not (rel < 0.12 and cos > 0.99):
+                bad.append((pname, round(rel, 4), round(cos, 5)))
+        assert not bad, bad

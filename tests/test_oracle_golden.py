@@ -177,3 +177,43 @@ def test_cogact_inference_matches_reference():
         assert (x[0].clamp(-1, 1) - o["actions_sample0"]).abs().max().item() < 1e-4
     tmap, ac, ac_prev = vla_oracle.ddim_tables(100, 10)
     assert tmap == list(range(0, 100, 10)) and ac_prev[0] == 1.0 and abs(ac[0] - 0.999684309 ** 2) < 1e-8
+
+
+@pytest.mark.parametrize("case", ["ce", "soft_ce", "ce_two_frames"])
+def test_navila_tiny_matches_reference(case):
+    """NaVILA (VLM + shifted CE / soft CE over the time tokens, one or two frames per row) vs the unmodified
+    reference's loss, logits and gradients (oracle/make_golden.py:make_navila_tiny)."""
+    fx = torch.load(GOLDEN / "navila_tiny.pt", weights_only=False)
+    c = fx["cases"][case]
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    sd = {k: (v.requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    i = c["inputs"]
+    out = vla_oracle.navila_forward(sd, fx["cfg"], i["input_ids"], i["attention_mask"], i["images"], i["labels"],
+                                    time_token_ids=c["time_token_ids"], soft_ce_std=c["soft_ce_std"])
+    assert abs(out["loss"].item() - c["outputs"]["loss"].item()) < 1e-5
+    valid = c["outputs"]["valid"][:, :, None]
+    assert ((out["logits"] * valid) - c["outputs"]["logits"]).abs().max().item() < 2e-4
+    out["loss"].backward()
+    for name, gref in c["outputs"]["grads"].items():
+        rel = ((sd[name].grad - gref).norm() / gref.norm()).item()
+        assert rel < 1e-4, (name, rel)
+    for name in c["outputs"]["none_grad"]:
+        g = sd[name].grad
+        assert g is None or g.abs().max().item() == 0.0, name
+
+
+def test_hybrid_cogact_tiny_matches_reference():
+    """Text + action co-training (hybrid_cogact_arch.py:60-218): weighted action loss, text loss, NaN on text-less batches."""
+    fx = torch.load(GOLDEN / "hybrid_cogact_tiny.pt", weights_only=False)
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    for name, case in fx["cases"].items():
+        i = case["inputs"]
+        out = vla_oracle.hybrid_cogact_forward(sd, fx["cfg"], i["input_ids"], i["attention_mask"], i["images"],
+                                               i["actions"], i["labels"], i["has_action"], i["has_text"], i["noise"],
+                                               i["timesteps"], i["drop_mask"], i["repeated_diffusion_steps"])
+        ref = case["outputs"]
+        assert abs(out["action_loss"].item() - ref["action_loss"].item()) < 1e-5
+        if name == "no_text":
+            assert torch.isnan(out["text_loss"]) and torch.isnan(ref["text_loss"])
+        else:
+            assert abs(out["text_loss"].item() - ref["text_loss"].item()) < 1e-5
