@@ -64,6 +64,10 @@ def test_config_json_round_trip_for_every_policy():
                                     action_dim=32, chunk_size=10),
         "dexbotic_pi05": m.Pi05Config(llm_config=gemma, action_config=dict(gemma, hidden_size=32, adarms_cond_dim=32),
                                       vision_config=siglip, action_dim=32, chunk_size=10),
+        "dexbotic_navila": m.NaVILAConfig(llm_config=dict(model_type="llama", vocab_size=128, hidden_size=64,
+                                                          intermediate_size=160, num_hidden_layers=2,
+                                                          num_attention_heads=4, num_key_value_heads=2),
+                                          mm_vision_tower=siglip, time_token_ids=[120, 121, 122], soft_ce_std=1.5),
     }
     assert set(made) == set(m.MODEL_TYPES)
     for mt, cfg in made.items():
