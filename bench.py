@@ -266,6 +266,9 @@ def run_ours(args) -> dict:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     w = WORKLOADS[args.workload]
+    if world > 1 and os.environ.get("B200_DP", "zero1") == "zero1" and os.environ.get("B200_DP_TRANSPORT", "ce") == "ce":
+        from dexbotic_b200.params import ParamStore
+        ParamStore.SYMMETRIC = True          # gradient / weight buffers in symmetric memory: copy-engine exchange
     model = build_model(w, dev)
     model.init_weights_(seed=1234)          # same seeded random init on every rank (no checkpoints offline)
     model.train()
@@ -406,7 +409,10 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
                                "(>120 GB for the 7B model), so L2 is cold for the timed kernels",
                    "global_batch": B * world, "seq_len": S,
                    "parallelism": f"dp{world}" + ("" if world == 1 else
-                                                  " (ZeRO-1: reduce-scatter grads, sharded AdamW, all-gather bf16 weights)"
+                                                  (" (ZeRO-1 over NVLink copy engines: pull-reduce-scatter of gradients, "
+                                                   "sharded AdamW, push-all-gather of bf16 weights; no SM-resident collective)"
+                                                   if getattr(overlap, "ce", False) else
+                                                   " (ZeRO-1: NCCL reduce-scatter grads, sharded AdamW, all-gather bf16 weights)")
                                                   if dp_mode == "zero1" else " (gradient all-reduce)"),
                    "train_tflop_per_sample": round(flops_sample / 1e12, 3)},
         "e2e": {"value": round(e2e, 3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

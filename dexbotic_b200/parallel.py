@@ -13,8 +13,18 @@ Two modes (both shard the episode batch, one process per GPU, NCCL over NVLink /
   competes with the backward GEMMs is gone, the 28 B/parameter AdamW sweep shrinks N-fold (39 ms -> 5 ms at N = 8 for
   the 7B model) and 8 B/parameter of optimizer state leave every GPU but one.
 
-The exchange step stays a library collective on purpose: gradients are produced by the tcgen05 wgrad GEMMs directly
-into the flat bf16 buffer the collective reads — no packing, no copies.
+Transports of the sharded mode:
+  "nccl"  reduce_scatter_tensor / all_gather_into_tensor in place on the flat buffers.  NCCL's kernels are resident on
+          SMs while the persistent tcgen05 GEMM owns all 148 of them: both slow down (the 5-8 % weak-scaling loss
+          measured at N = 2..8).
+  "ce"    the same exchange on the COPY ENGINES over NVLink / NVSwitch peer memory, no SM-resident collective at all:
+          the gradient and weight buffers are symmetric memory (ParamStore.SYMMETRIC), every rank PULLS its piece of a
+          finished chunk out of its peers' gradient buffers (cudaMemcpy peer-to-peer on a side stream, bracketed by
+          stream-ordered cross-rank barriers on the symmetric-memory signal pads), adds the N pieces in fp32, updates,
+          and PUSHES its piece of the new bf16 weights into the peers' weight buffers.  The only SM work left is the
+          1/N-sized sum and two one-CTA barrier kernels per chunk.
+Gradients are produced by the tcgen05 wgrad GEMMs directly into the flat bf16 buffer the exchange reads — no packing,
+no copies.
 """
 from __future__ import annotations
 
@@ -169,7 +179,7 @@ class ShardedDataParallel:
     shards first (`gather_master`).  With world size 1 nothing is sharded and the store's own path runs."""
 
     def __init__(self, store: ParamStore, group=None, adamw_fn: Optional[Callable] = None,
-                 sumsq_fn: Optional[Callable] = None, clip_fn: Optional[Callable] = None):
+                 sumsq_fn: Optional[Callable] = None, clip_fn: Optional[Callable] = None, transport: str = "auto"):
         self.store, self.group = store, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -203,6 +213,20 @@ class ShardedDataParallel:
         self.exp_avg = self.exp_avg_sq = None      # [n_local + n_b] fp32: this rank's pieces, then region B (replicated)
         self._side = None
         self._keep = None
+        # copy-engine transport: both exchanged buffers must be symmetric memory
+        want_ce = transport == "ce" or (transport == "auto" and getattr(store, "symmetric", False))
+        self.ce = bool(self.enabled and self.nccl and want_ce)
+        if self.ce:
+            if not getattr(store, "symmetric", False):
+                raise RuntimeError("transport='ce' needs ParamStore.SYMMETRIC = True before the model is built")
+            import torch.distributed._symmetric_memory as symm_mem
+            pg = group if group is not None else dist.group.WORLD
+            self._h_grad = symm_mem.rendezvous(store.grad_a, pg)      # collective: maps every peer's buffer
+            self._h_shadow = symm_mem.rendezvous(store.shadow, pg)
+            self._comm = torch.cuda.Stream(device=store.device)
+            mx = max((b - a) // self.world for a, b in self.chunks)
+            self._staging = torch.empty((self.world - 1, mx), device=store.device, dtype=torch.bfloat16)
+            self._acc = torch.empty(mx, device=store.device, dtype=torch.float32)
         if self.enabled:
             store.sharder = self
             store.grad_ready_hook = self.on_ready
@@ -223,7 +247,45 @@ class ShardedDataParallel:
         self.works = []
         self.reduced = set()
 
+    def _reduce_scatter_ce(self, ci: int) -> None:
+        """Copy-engine reduce-scatter of one chunk: after a cross-rank barrier (every rank has enqueued this chunk's
+        wgrads before it), pull piece `rank` out of each peer's gradient buffer, sum in fp32, write the average back
+        in place.  Runs on the exchange stream; the compute stream goes on with the next block's backward."""
+        st = self.store
+        pa, pb = self.piece[ci]
+        sz = pb - pa
+        cs = self._comm
+        cs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cs):
+            self._h_grad.barrier(channel=0)
+            for step in range(1, self.world):
+                peer = (self.rank - step) % self.world
+                src = self._h_grad.get_buffer(peer, (sz,), torch.bfloat16, pa)
+                self._staging[step - 1, :sz].copy_(src)
+            self._h_grad.barrier(channel=0)            # every peer has taken its piece of this rank's chunk
+            acc = self._acc[:sz]
+            acc.copy_(st.grad_a[pa:pb])
+            for k in range(self.world - 1):
+                acc.add_(self._staging[k, :sz])
+            acc.mul_(1.0 / self.world)
+            st.grad_a[pa:pb].copy_(acc)
+        self.reduced.add(ci)
+
+    def _push_shadow_ce(self, ci: int) -> None:
+        """Copy-engine all-gather of one chunk's new bf16 weights: push this rank's piece into every peer's weight
+        buffer, then a barrier — when it completes on a rank, all N pieces of the chunk have landed there.  (No peer
+        can still be reading the chunk: its reduce-scatter barrier of this step came after its last use.)"""
+        st = self.store
+        pa, pb = self.piece[ci]
+        sz = pb - pa
+        for step in range(1, self.world):
+            peer = (self.rank + step) % self.world
+            self._h_shadow.get_buffer(peer, (sz,), torch.bfloat16, pa).copy_(st.shadow[pa:pb])
+        self._h_shadow.barrier(channel=0)
+
     def _reduce_scatter(self, ci: int) -> None:
+        if self.ce:
+            return self._reduce_scatter_ce(ci)
         a, b = self.chunks[ci]
         buf = self.store.grad_a[a:b]
         pa, pb = self.piece[ci]
@@ -263,6 +325,8 @@ class ShardedDataParallel:
         for w in self.works:
             w.wait()
         self.works = []
+        if self.ce:
+            torch.cuda.current_stream().wait_stream(self._comm)
 
     # ------------------------------------------------------------------ optimizer
     def _segments_of(self, segs: list, lo: int, hi: int) -> list:
@@ -310,6 +374,8 @@ class ShardedDataParallel:
                             st.shadow[x:y], lr, betas[0], betas[1], eps, wd, st.step_count, clip)
 
         def gather(ci: int) -> None:
+            if self.ce:
+                return self._push_shadow_ce(ci)
             a, b = self.chunks[ci]
             pa, pb = self.piece[ci]
             if self.nccl:

@@ -89,8 +89,23 @@ class ParamStore:
     """Regions: A = trainable, bf16 compute; B = trainable, fp32 compute; FA / FB = frozen counterparts
     (master + shadow only: no gradient, no optimizer state — e.g. lm_head in CogACT, or a frozen tower)."""
 
+    # True (set by the launcher before the model is built, multi-GPU only): the bf16 gradient and weight buffers are
+    # allocated as symmetric memory, so that peers can be mapped into them and the data-parallel exchange can run on
+    # the copy engines over NVLink (parallel.ShardedDataParallel, transport "ce") instead of in SM-resident kernels.
+    SYMMETRIC = False
+
+    def _alloc_exchanged(self, n: int, dtype) -> torch.Tensor:
+        if ParamStore.SYMMETRIC and self.device.type == "cuda" and n > 0:
+            import torch.distributed._symmetric_memory as symm_mem
+            t = symm_mem.empty(n, dtype=dtype, device=self.device)
+            t.zero_()
+            self.symmetric = True
+            return t
+        return torch.zeros(n, device=self.device, dtype=dtype)
+
     def __init__(self, specs: list[ParamSpec], device):
         self.device = torch.device(device)
+        self.symmetric = False
         self.slots: dict[str, _Slot] = {}
         self.order: list[str] = []
         size = {"A": 0, "B": 0, "FA": 0, "FB": 0}
@@ -115,9 +130,9 @@ class ParamStore:
         # one fp32 master for everything; trainable tensors first so moments / AdamW cover a prefix
         self.master = torch.zeros(n_train + self.n_fa + self.n_fb, device=dev, dtype=torch.float32)
         self.n_train = n_train
-        self.shadow = torch.zeros(self.n_a, device=dev, dtype=torch.bfloat16)
+        self.shadow = self._alloc_exchanged(self.n_a, torch.bfloat16)
         self.shadow_f = torch.zeros(self.n_fa, device=dev, dtype=torch.bfloat16)
-        self.grad_a = torch.zeros(self.n_a, device=dev, dtype=torch.bfloat16)
+        self.grad_a = self._alloc_exchanged(self.n_a, torch.bfloat16)
         self.grad_b = torch.zeros(self.n_b, device=dev, dtype=torch.float32)
         self.exp_avg: Optional[torch.Tensor] = None
         self.exp_avg_sq: Optional[torch.Tensor] = None

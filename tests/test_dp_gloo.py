@@ -213,11 +213,15 @@ def _zero1_worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_zero1_sharded_step_equals_unsharded_world2():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_zero1_sharded_step_equals_unsharded(world):
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_zero1_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
-    assert ret[0] and ret[1]
+    mp.spawn(_zero1_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))
 
 
 def _overlap_worker(rank, world, port, ret):

@@ -84,11 +84,16 @@ def _worker(rank, world, port, mode, ret):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=dev)
     from dexbotic_b200.parallel import GradientOverlap, ShardedDataParallel
+    from dexbotic_b200.params import ParamStore
+    ParamStore.SYMMETRIC = mode == "zero1_ce"       # copy-engine transport: exchanged buffers in symmetric memory
     model = _model(dev)
     model.store.async_optimizer = True
-    dp = (ShardedDataParallel(model.store) if mode == "zero1" else GradientOverlap(model.store, bucket_bytes=1 << 16))
+    dp = (ShardedDataParallel(model.store) if mode.startswith("zero1")
+          else GradientOverlap(model.store, bucket_bytes=1 << 16))
+    if mode.startswith("zero1"):
+        assert dp.ce == (mode == "zero1_ce")
     losses, grads, sd = _train(model, dp, rank * B, (rank + 1) * B, dev)
-    if mode == "zero1":     # 1/N of the moments per rank, and the shard pieces tile region A
+    if mode.startswith("zero1"):     # 1/N of the moments per rank, and the shard pieces tile region A
         assert dp.exp_avg.numel() == model.store.n_a // world + model.store.n_b
         pieces = [None] * world
         dist.all_gather_object(pieces, dp.piece)
@@ -97,7 +102,7 @@ def _worker(rank, world, port, mode, ret):
         assert all(a[1] == b[0] for a, b in zip(cover[:-1], cover[1:]))
     # after the exchange, rank 0's gradient view: all-reduce -> whole buffer averaged; zero1 -> only its pieces
     ret[rank] = dict(losses=losses, sd=sd, grad_a=grads[0].cpu(), grad_b=grads[1].cpu(),
-                     pieces=dp.piece if mode == "zero1" else None)
+                     pieces=dp.piece if mode.startswith("zero1") else None)
     dist.destroy_process_group()
 
 
@@ -118,13 +123,14 @@ def test_two_ranks_train_like_one_rank_with_twice_the_batch():
     torch.cuda.empty_cache()
     ar0, ar1 = _run_dp("allreduce")
     z0, z1 = _run_dp("zero1")
-    # (1) the replicas stay identical, in both modes
-    for a, b in ((ar0, ar1), (z0, z1)):
+    c0, c1 = _run_dp("zero1_ce")
+    # (1) the replicas stay identical, in every mode
+    for a, b in ((ar0, ar1), (z0, z1), (c0, c1)):
         for k in a["sd"]:
             assert torch.equal(a["sd"][k], b["sd"][k]), k
     # (2) mean of the per-rank losses == the full-batch loss (equal sample counts), every step
     for step in range(STEPS):
-        for r0, r1 in ((ar0, ar1), (z0, z1)):
+        for r0, r1 in ((ar0, ar1), (z0, z1), (c0, c1)):
             mean = 0.5 * (r0["losses"][step] + r1["losses"][step])
             assert abs(mean - s_losses[step]) < 5e-3 * abs(s_losses[step]), (step, mean, s_losses[step])
     # (3) step-0 gradients: average of two bf16 half-batch gradients vs the bf16 full-batch gradient
@@ -138,19 +144,25 @@ def test_two_ranks_train_like_one_rank_with_twice_the_batch():
     for r in (z0, z1):
         for a, b in r["pieces"]:
             assert torch.equal(r["grad_a"][a:b], ga[a:b])
-    # (4) the two exchange modes give the same trained weights (same averaged gradients, same optimizer arithmetic)
+    # (4) the two NCCL exchange modes give the same trained weights (same averaged gradients, same optimizer arithmetic)
     for k in ar0["sd"]:
         assert torch.allclose(ar0["sd"][k], z0["sd"][k], rtol=0, atol=1e-7), k
+    # the copy-engine transport averages in fp32 (one rounding) where NCCL rounds twice: same gradient to bf16 precision
+    for r in (c0, c1):
+        for a, b in r["pieces"]:
+            d = (r["grad_a"][a:b] - ga[a:b]).norm() / ga[a:b].norm().clamp_min(1e-20)
+            assert d < 1e-2, (a, b, d.item())
     # (5) and they track the single-GPU run: AdamW's first steps move every weight by ~lr, so compare the UPDATE
     #     direction (a sign flip on a near-zero gradient costs 2*lr on that element, bf16 rounding makes a few)
     init = _model(dev).state_dict()
     bad = []
-    for k in s_sd:
-        d_s = (s_sd[k] - init[k].float().cpu()).flatten()
-        d_p = (ar0["sd"][k] - init[k].float().cpu()).flatten()
-        if d_s.norm() == 0:
-            continue
-        c = torch.nn.functional.cosine_similarity(d_s, d_p, dim=0).item()
-        if c < 0.97:
-            bad.append((k, round(c, 4)))
+    for run, tag in ((ar0, "allreduce"), (c0, "zero1_ce")):
+        for k in s_sd:
+            d_s = (s_sd[k] - init[k].float().cpu()).flatten()
+            d_p = (run["sd"][k] - init[k].float().cpu()).flatten()
+            if d_s.norm() == 0:
+                continue
+            c = torch.nn.functional.cosine_similarity(d_s, d_p, dim=0).item()
+            if c < 0.97:
+                bad.append((tag, k, round(c, 4)))
     assert not bad, bad[:8]

@@ -11,7 +11,15 @@ from tools.bench_gemm import timeit  # noqa: E402
 PEAK = 6485.5
 
 
+ONCE = "--once" in sys.argv      # one launch per kernel, no timing: the run that ncu replays (tools: see profiles/README.md)
+
+
 def report(name, nbytes, fn):
+    if ONCE:
+        fn()
+        torch.cuda.synchronize()
+        print(f"{name:28s} algorithmic {nbytes/1e6:9.1f} MB", flush=True)
+        return
     t = timeit(fn, reps=7)
     print(f"{name:28s} {t*1e3:8.1f} us  {nbytes/t/1e6:7.0f} GB/s  {100*nbytes/t/1e6/PEAK:5.1f}% of measured copy peak", flush=True)
 
@@ -69,6 +77,23 @@ def main():
     report("adamw (268M params)", 28 * n, lambda: ops.adamw_(p32, g16, m32, v32, s16, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1))
     ss = torch.zeros((), device=dev)
     report("sumsq bf16", 2 * n, lambda: ops.sumsq_(g16, ss))
+    del p32, m32, v32, g16, s16
+    # flash-attention row term and the image-token splice (CogACT-7B: 32 x 309 rows of 3584, 256 image rows each)
+    o = torch.randn(B, S, H * 128, device=dev, dtype=bf)
+    do = torch.randn(B, S, H * 128, device=dev, dtype=bf)
+    qkv3 = torch.randn(B, S, (H + 8) * 128, device=dev, dtype=bf)
+    out_f, lse = ops.flash_attention_fwd(qkv3, sh, keymask=km, causal=True)
+    report("flash bwd (delta+dq+dkv)", 2 * o.numel() * 2, lambda: ops.flash_attention_bwd(do, qkv3, out_f, lse, sh, keymask=km, causal=True))
+    table = torch.randn(152064, d, device=dev, dtype=bf)
+    feats = torch.randn(B * 257, d, device=dev, dtype=bf)
+    ids = torch.randint(1000, 30000, (B, 54), device=dev)
+    ids[:, 1] = -200
+    mask8 = torch.ones(B, 54, device=dev, dtype=torch.uint8)
+    lengths = ops.splice_lengths(ids, mask8, 256, 0)
+    Ssp = int(lengths.max().item())
+    src, _, _, _ = ops.splice_plan(ids, mask8, None, 256, 0, Ssp, False)
+    emb = torch.empty(B, Ssp, d, device=dev, dtype=bf)
+    report("splice_gather", 2 * B * Ssp * d * 2, lambda: ops.splice_gather(src, table, feats, out=emb))
 
 
 if __name__ == "__main__":
