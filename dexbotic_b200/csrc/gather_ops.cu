@@ -280,6 +280,49 @@ __global__ void __launch_bounds__(256) argmax_last_kernel(const T* __restrict__ 
   if (threadIdx.x == 0) idx[blockIdx.x] = si[0] == INT_MAX ? 0 : si[0];
 }
 
+// Temperature sampling over the last n_last logits of a row (OFTDiscreteForCausalLM.generate_action,
+// oft_discrete_arch.py:264-270: softmax(logits[..., -n_last:] / T) then one multinomial draw).  The draw is the inverse
+// CDF at the caller's uniform u[row] in [0, 1): the smallest j with sum_{i<=j} p_i > u * sum_i p_i, in fp32 with a
+// fixed summation order (one warp per row, lane-strided partial sums + shuffle scan) — reproducible given u.
+template <typename T>
+__global__ void __launch_bounds__(32) sample_last_kernel(const T* __restrict__ logits, int64_t V, int n_last,
+                                                         float inv_temp, const float* __restrict__ u,
+                                                         int64_t* __restrict__ idx) {
+  const int lane = threadIdx.x;
+  const T* row = logits + (size_t)blockIdx.x * V + (V - n_last);
+  const int per = (n_last + 31) / 32;                  // consecutive entries per lane: lane l owns [l*per, (l+1)*per)
+  float mx = -INFINITY;
+  for (int j = lane * per; j < min(n_last, (lane + 1) * per); ++j) mx = fmaxf(mx, to_f(row[j]) * inv_temp);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float part = 0.0f;
+  for (int j = lane * per; j < min(n_last, (lane + 1) * per); ++j) part += expf(to_f(row[j]) * inv_temp - mx);
+  float incl = part;                                   // inclusive scan over lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const float total = __shfl_sync(0xffffffffu, incl, 31);
+  const float target = u[blockIdx.x] * total;
+  const float before = incl - part;
+  int found = INT_MAX;
+  if (target < incl && target >= before) {             // the draw falls into this lane's run
+    float c = before;
+    for (int j = lane * per; j < min(n_last, (lane + 1) * per); ++j) {
+      c += expf(to_f(row[j]) * inv_temp - mx);
+      if (target < c) {
+        found = j;
+        break;
+      }
+    }
+    if (found == INT_MAX) found = min(n_last, (lane + 1) * per) - 1;   // rounding at the run's end
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, o));
+  if (lane == 0) idx[blockIdx.x] = found == INT_MAX ? n_last - 1 : found;
+}
+
 // ------------------------------------------------------------ cross entropy
 template <typename T>
 __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels,
@@ -482,6 +525,16 @@ int b200_argmax_last(const void* logits, int64_t rows, int64_t V, int n_last, in
   if (rows == 0) return 0;
   B200_CHECK(n_last > 0 && n_last <= V, "argmax_last: bad n_last");
   DISPATCH_T(dtype, (argmax_last_kernel<T><<<(unsigned)rows, 256, 0, STREAM>>>((const T*)logits, V, n_last, idx)));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_sample_last(const void* logits, int64_t rows, int64_t V, int n_last, float temperature, const float* u,
+                     int64_t* idx, int dtype, void* stream) {
+  if (rows == 0) return 0;
+  B200_CHECK(n_last > 0 && n_last <= V && temperature > 0.0f && u != nullptr, "sample_last: bad arguments");
+  DISPATCH_T(dtype, (sample_last_kernel<T><<<(unsigned)rows, 32, 0, STREAM>>>((const T*)logits, V, n_last,
+                                                                              1.0f / temperature, u, idx)));
   B200_LAUNCH_OK();
   return 0;
 }

@@ -178,6 +178,29 @@ class OFTDiscreteForCausalLM(B200Module):
         mn, mx = np.array(action_norms["min"]).reshape(1, -1), np.array(action_norms["max"]).reshape(1, -1)
         return (mn + (actions + 1) * 0.5 * (mx - mn)).tolist()
 
+    @torch.no_grad()
+    def generate_action(self, input_ids, pixel_values, attention_masks, temperature, inference_args={},
+                        u: Optional[torch.Tensor] = None, **kwargs):
+        """oft_discrete_arch.py:237-282: parallel decoding with temperature sampling instead of argmax — one draw per
+        action token from softmax(logits[..., -(num_bins-1):] / temperature).  Returns (de-normalised actions for every
+        sample, response token ids = bin index + vocab_size - num_bins + 1).  `u` [B, chunk*dim] injects the uniforms
+        (parity / reproducibility); default: torch.rand on the device."""
+        cfg = self.config
+        assert "Discrete" in cfg.action_model_type, "generate_action is only for discrete action model."
+        action_norms = inference_args.get("action_norms")
+        out = self.forward(input_ids=input_ids, attention_mask=attention_masks, images=pixel_values,
+                           states=inference_args.get("states"))
+        B, A, V = out.logits.shape
+        if u is None:
+            u = torch.rand(B * A, device=out.logits.device, dtype=torch.float32)
+        idx = ops.sample_last(out.logits.reshape(B * A, V).contiguous(), cfg.num_bins - 1, float(temperature),
+                              u.reshape(-1).float().contiguous()).view(B, A)
+        response_ids = idx + cfg.vocab_size - cfg.num_bins + 1
+        cont = self.model_engine.action_head.discrete_tokens_to_continuous(idx)
+        actions = np.clip(cont.float().cpu().numpy(), -1, 1)                       # _denorm, dexbotic_arch.py:546-563
+        mn, mx = np.array(action_norms["min"]).reshape(1, 1, -1), np.array(action_norms["max"]).reshape(1, 1, -1)
+        return (mn + (actions + 1) * 0.5 * (mx - mn)).tolist(), response_ids
+
     def zero_grad(self, set_to_none: bool = False):
         self.store.zero_grad()
 

@@ -659,6 +659,17 @@ def argmax_last(logits2d, n_last: int):
     return idx
 
 
+def sample_last(logits2d, n_last: int, temperature: float, u: torch.Tensor):
+    """One draw per row from softmax(logits[:, -n_last:] / temperature): inverse CDF at the uniforms u [rows] (fp32)."""
+    _cuda(logits2d, u)
+    rows, V = logits2d.shape
+    assert logits2d.is_contiguous() and u.dtype == torch.float32 and u.numel() == rows and u.is_contiguous()
+    idx = torch.empty(rows, device=logits2d.device, dtype=torch.int64)
+    _lib.check(_lib.load().b200_sample_last(logits2d.data_ptr(), rows, V, n_last, float(temperature), u.data_ptr(),
+                                            idx.data_ptr(), _dt(logits2d), _stream()), "sample_last")
+    return idx
+
+
 def cross_entropy_fwd(logits2d, labels):
     _cuda(logits2d, labels)
     rows, V = logits2d.shape

@@ -157,6 +157,11 @@ int b200_timestep_embedding(const float* t, void* out, int64_t B, int dim, float
 int b200_discretize_actions(const float* actions, int64_t n, int n_bins, int64_t* bins, void* stream);
 int b200_bins_to_continuous(const int64_t* bins, int64_t n, int n_bins, float* out, void* stream);
 int b200_argmax_last(const void* logits, int64_t rows, int64_t V, int n_last, int64_t* idx, int dtype, void* stream);
+/* One temperature-scaled draw per row from softmax(logits[row, V - n_last :] / temperature)
+ * (OFTDiscreteForCausalLM.generate_action, oft_discrete_arch.py:264-270: softmax + torch.multinomial(.., 1)).
+ * u[rows]: uniforms in [0, 1) supplied by the caller (torch's generator on the host side); idx = inverse CDF at u. */
+int b200_sample_last(const void* logits, int64_t rows, int64_t V, int n_last, float temperature, const float* u,
+                     int64_t* idx, int dtype, void* stream);
 /* Cross entropy over fp32-upcast logits rows with int64 labels (ignore_index=-100), mean over valid rows:
  * *loss += sum(-log softmax[label]) / n_valid ; lse[rows] saved.  Backward: dlogits = (softmax - onehot) * g / n_valid.
  * oft_discrete_arch.py:187-191 (F.cross_entropy under fp32 autocast); DexboticForCausalLM loss (dexbotic_arch.py:489). */

@@ -540,6 +540,17 @@ def oft_argmax_decode(logits: np.ndarray, n_last: int = 255) -> np.ndarray:
     return np.argmax(logits[..., -n_last:], axis=-1).astype(np.int64)
 
 
+def oft_sample_decode(logits: np.ndarray, n_last: int, temperature: float, u: np.ndarray) -> np.ndarray:
+    """oft_discrete_arch.py:264-270 (generate_action): softmax(logits[..., -n_last:] / T), one multinomial draw per row.
+    torch.multinomial's draw is not reproducible outside torch; the sampling DISTRIBUTION is what is specified, and a
+    draw from it is the inverse CDF at a uniform u in [0, 1) — restated here in float64."""
+    z = logits[..., -n_last:].astype(np.float64) / temperature
+    p = np.exp(z - z.max(axis=-1, keepdims=True))
+    cdf = np.cumsum(p, axis=-1)
+    target = u.astype(np.float64)[..., None] * cdf[..., -1:]
+    return np.minimum((cdf <= target).sum(axis=-1), n_last - 1).astype(np.int64)
+
+
 def data_action_to_bin(action: np.ndarray, vocab_size: int = 255) -> np.ndarray:
     """data/dataset/transform/action.py:386-390 (_action2bin): np.round((a+1)/2*(V-1)) clipped to [0,V-1].
     NOTE the 254-vs-255 scale mismatch with the model side is the reference's; reproduced, not fixed."""

@@ -145,8 +145,12 @@ def test_two_ranks_train_like_one_rank_with_twice_the_batch():
         for a, b in r["pieces"]:
             assert torch.equal(r["grad_a"][a:b], ga[a:b])
     # (4) the two NCCL exchange modes give the same trained weights (same averaged gradients, same optimizer arithmetic)
+    diffs = []
     for k in ar0["sd"]:
-        assert torch.allclose(ar0["sd"][k], z0["sd"][k], rtol=0, atol=1e-7), k
+        d = (ar0["sd"][k] - z0["sd"][k]).abs()
+        if d.max().item() > 1e-7:
+            diffs.append((k, float(d.max()), int((d > 1e-7).sum()), d.numel()))
+    assert not diffs, diffs[:10]
     # the copy-engine transport averages in fp32 (one rounding) where NCCL rounds twice: same gradient to bf16 precision
     for r in (c0, c1):
         for a, b in r["pieces"]:

@@ -306,3 +306,74 @@ def test_oft_discrete_full_vocabulary_ce_and_argmax_match_oracle():
     assert err <= 2.0 ** -8 * dr.abs().max().item() + 1e-9, (err, dr.abs().max().item())   # one bf16 rounding
     rowsum = d.float().sum(-1).abs().max().item()
     assert rowsum < 1e-3 * dr.abs().max().item() * 40, rowsum                                # softmax - onehot sums to 0
+
+
+def test_oft_generate_action_sampling_matches_oracle_distribution():
+    """generate_action's draw (oft_discrete_arch.py:264-270): softmax(logits[..., -255:] / T) then one multinomial
+    sample per action token.  (a) given the uniforms, the kernel's inverse-CDF index equals the oracle's float64
+    restatement wherever u is not within 1e-4 of a CDF boundary (fp32 vs fp64 prefix sums); (b) over 200k draws the
+    empirical frequencies match the softmax probabilities (chi-square); (c) T -> 0 degenerates to the argmax path;
+    (d) the model-level call returns response ids = index + vocab_size - num_bins + 1 and actions in the norm range."""
+    import numpy as np
+    from dexbotic_b200 import ops
+    from oracle import vla_oracle
+    V, rows, n_last = 4096, 512, 255
+    g = torch.Generator(device="cuda").manual_seed(5)
+    logits = (torch.randn((rows, V), device="cuda", generator=g) * 2.5).to(torch.bfloat16)
+    u = torch.rand(rows, device="cuda", generator=g)
+    for T in (1.0, 0.7, 1.6):
+        got = ops.sample_last(logits, n_last, T, u).cpu().numpy()
+        lf = logits.float().cpu().numpy()
+        ref = vla_oracle.oft_sample_decode(lf, n_last, T, u.cpu().numpy())
+        z = lf[:, -n_last:].astype(np.float64) / T
+        p = np.exp(z - z.max(-1, keepdims=True))
+        cdf = np.cumsum(p, -1) / p.sum(-1, keepdims=True)
+        near = np.abs(cdf - u.cpu().numpy().astype(np.float64)[:, None]).min(-1) < 1e-4
+        assert np.array_equal(got[~near], ref[~near]), (T, int((got != ref).sum()))
+        assert (np.abs(got[near] - ref[near]) <= 1).all()
+        assert got.min() >= 0 and got.max() <= n_last - 1
+    # (b) distribution of one row
+    row = logits[7:8].expand(200_000, V).contiguous()
+    uu = torch.rand(200_000, device="cuda", generator=g)
+    draws = ops.sample_last(row, n_last, 1.0, uu).cpu().numpy()
+    z = logits[7].float().cpu().numpy()[-n_last:].astype(np.float64)
+    p = np.exp(z - z.max())
+    p /= p.sum()
+    cnt = np.bincount(draws, minlength=n_last).astype(np.float64)
+    big = p * 200_000 >= 20                      # cells with enough expected mass for the chi-square statistic
+    chi2 = (((cnt - p * 200_000) ** 2) / (p * 200_000))[big].sum()
+    assert chi2 < big.sum() + 6 * (2 * big.sum()) ** 0.5, (chi2, int(big.sum()))
+    # (c) cold temperature == restricted argmax (first maximum wins does not matter: bf16 ties have measure ~0 here)
+    cold = ops.sample_last(logits, n_last, 1e-3, u).cpu()
+    assert torch.equal(cold, ops.argmax_last(logits, n_last).cpu())
+
+
+def test_oft_generate_action_model_call():
+    from dexbotic_b200.model import OFTDiscreteConfig, OFTDiscreteForCausalLM
+    from oracle.weights import seeded_state_dict
+    fx = torch.load(GOLDEN / "oft_discrete_tiny.pt", weights_only=False)
+    cfg = fx["cfg"]
+    c = OFTDiscreteConfig(llm_config=cfg["llm"], mm_vision_tower=cfg["vision"], action_model_type="Discrete",
+                          action_dim=cfg["action_dim"], chunk_size=cfg["chunk_size"], num_bins=cfg.get("num_bins", 256))
+    model = OFTDiscreteForCausalLM(c)
+    model.load_state_dict(seeded_state_dict(fx["shapes"], fx["seed"]))
+    model.eval()
+    i = fx["inputs"]
+    A = c.chunk_size * c.action_dim
+    # an inference prompt has no action-label tokens: strip them as the training forward does, keep unpadded rows only
+    ids, mask, _ = model._strip_action_labels(i["input_ids"].cuda(), i["attention_mask"].cuda(), i["labels"].cuda(), A)
+    n = int(mask.sum(1).min())
+    ids, mask, images = ids[:, :n].contiguous(), mask[:, :n].contiguous(), i["images"].cuda()
+    assert bool(mask.all())
+    norms = {"min": [-2.0] * c.action_dim, "max": [3.0] * c.action_dim}
+    u = torch.rand(ids.shape[0], A, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    acts, resp = model.generate_action(ids, images, mask, 0.9, {"action_norms": norms}, u=u)
+    acts2, resp2 = model.generate_action(ids, images, mask, 0.9, {"action_norms": norms}, u=u)
+    assert torch.equal(resp, resp2) and acts == acts2                       # reproducible given the uniforms
+    V = c.vocab_size
+    assert resp.shape == (ids.shape[0], A) and int(resp.min()) >= V - c.num_bins + 1 and int(resp.max()) <= V - 1
+    a = torch.tensor(acts)
+    assert a.shape == (ids.shape[0], c.chunk_size, c.action_dim) and a.min() >= -2.0 and a.max() <= 3.0
+    cold, _ = model.generate_action(ids, images, mask, 1e-3, {"action_norms": norms}, u=u)
+    greedy = model.inference_action(ids, images, {"action_norms": norms})   # argmax decode of sample 0
+    assert np.allclose(np.array(cold[0]), np.array(greedy), atol=1e-6)
