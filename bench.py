@@ -266,10 +266,18 @@ def run_ours(args) -> dict:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     w = WORKLOADS[args.workload]
-    if world > 1 and os.environ.get("B200_DP", "zero1") == "zero1" and os.environ.get("B200_DP_TRANSPORT", "ce") == "ce":
-        from dexbotic_b200.params import ParamStore
-        ParamStore.SYMMETRIC = True          # gradient / weight buffers in symmetric memory: copy-engine exchange
-    model = build_model(w, dev)
+    want_ce = (world > 1 and os.environ.get("B200_DP", "zero1") == "zero1"
+               and os.environ.get("B200_DP_TRANSPORT", "ce") == "ce")
+    from dexbotic_b200.params import ParamStore
+    ParamStore.SYMMETRIC = want_ce           # gradient / weight buffers in symmetric memory: copy-engine exchange
+    try:
+        model = build_model(w, dev)
+    except Exception as e:                   # symmetric allocation unavailable on this box: NCCL transport instead
+        if not want_ce:
+            raise
+        print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); using the NCCL transport", file=sys.stderr)
+        ParamStore.SYMMETRIC = False
+        model = build_model(w, dev)
     model.init_weights_(seed=1234)          # same seeded random init on every rank (no checkpoints offline)
     model.train()
     host = make_batch(w, rank, pinned=True)
@@ -318,7 +326,11 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
     dp_mode = os.environ.get("B200_DP", "zero1") if world > 1 else "none"
     if dp_mode == "zero1":
         from dexbotic_b200.parallel import ShardedDataParallel
-        overlap = ShardedDataParallel(model.store)
+        try:
+            overlap = ShardedDataParallel(model.store)
+        except Exception as e:               # peer mapping failed: same sharded optimizer over NCCL
+            print(f"[bench] copy-engine transport unavailable ({type(e).__name__}: {e}); NCCL transport", file=sys.stderr)
+            overlap = ShardedDataParallel(model.store, transport="nccl")
     else:
         overlap = GradientOverlap(model.store, reserve_sms=int(os.environ.get("B200_DP_RESERVE_SMS", "0")))
     # the HBM-bound per-block AdamW of step t runs on a side stream under the tensor-bound forward of step t+1

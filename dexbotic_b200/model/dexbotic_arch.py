@@ -452,7 +452,10 @@ class DexboticVLMModel:
         # 5-D images: the n views of a sample form ONE image entry of n*P tokens (dexbotic_arch.py:163-175)
         P_entry = P * views
         lengths = ops.splice_lengths(ids, mask_u8, P_entry, max_len)
-        S = int(lengths.max().item())
+        # the padded length is the one device->host read of this path; `static_seq_len` (a config field the caller sets
+        # to an upper bound, e.g. L - n_image_tokens + n_image_tokens * P) removes it: rows are padded up to it and the
+        # whole step becomes CUDA-graph capturable
+        S = int(getattr(cfg, "static_seq_len", 0) or 0) or int(lengths.max().item())
         left = cfg.tokenizer_padding_side == "left"
         src, new_labels, new_mask, pos = ops.splice_plan(ids, mask_u8, labels, P_entry, max_len, S, left)
         # feature rows carry a CLS row per image view: token j of the dense numbering lives at row j + j // P + 1

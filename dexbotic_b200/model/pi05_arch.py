@@ -133,6 +133,8 @@ class Pi05ForCausalLM(B200Module):
         self.theta = rope_theta_of(llm)
         self._rope = None
         self.d, self.w = d, w
+        from .pi0_arch import MoTEngine
+        self.model_engine = MoTEngine(self)
 
     def _after_weights_changed(self) -> None:
         self.tower.refresh()

@@ -201,6 +201,27 @@ class SiglipVisionTower:
         return NormFn.apply(x, self.post_ln, self.store)
 
 
+class MoTEngine:
+    """What `model.model` answers for pi0 / pi0.5 (Pi0Model inherits DexboticVLMModel's accessors, dexbotic_arch.py:
+    122-155): the properties the reference's optimizer grouping and freeze logic read (base_exp.py:95-203, 318-330)."""
+    mm_projector_prefix = "mm_projector"
+    mm_vision_prefix = "mm_vision"
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    backbone = property(lambda self: self._owner.layers)
+    mm_projector_module = property(lambda self: self._owner.proj)
+    mm_vision_module = property(lambda self: self._owner.tower)
+
+    def initialize_model(self, extra_config: dict):
+        for key, value in extra_config.items():
+            setattr(self._owner.config, key, value)
+
+    def refresh(self):
+        self._owner.tower.refresh()
+
+
 # ------------------------------------------------------------------- mixture of transformers
 @dataclass
 class StreamW:
@@ -496,6 +517,7 @@ class Pi0ForCausalLM(B200Module):
         self.theta = rope_theta_of(llm)
         self._rope = None
         self.d, self.w = d, w
+        self.model_engine = MoTEngine(self)
 
     def _after_weights_changed(self) -> None:
         self.tower.refresh()

@@ -361,3 +361,72 @@ def test_hybrid_cogact_matches_reference_golden():
             if not (rel < 0.12 and cos > 0.99):
                 bad.append((pname, round(rel, 4), round(cos, 5)))
         assert not bad, bad
+
+
+def test_training_step_is_cuda_graph_capturable():
+    """with `static_seq_len` set there is no host sync on the forward / backward path — zero_grad + forward
+    + backward of a CogACT step are captured into ONE CUDA graph (every kernel launched through the C-ABI on the
+    capturing stream, TMA descriptors passed by value) and replayed on new inputs: the replayed loss and gradients equal
+    the eager ones bit for bit."""
+    from dexbotic_b200.model import CogActConfig, CogACTForCausalLM
+    from oracle.weights import seeded_state_dict
+    fx = torch.load(GOLDEN / "cogact_tiny.pt", weights_only=False)
+    cfg = fx["cfg"]
+    i = fx["inputs"]
+    B, L = i["input_ids"].shape
+    P = (cfg["vision"]["image_size"] // cfg["vision"]["patch_size"]) ** 2
+    c = CogActConfig(llm_config=cfg["llm"], mm_vision_tower=cfg["vision"], action_model_type="DiT-S", action_dim=7,
+                     chunk_size=16, static_seq_len=L - 1 + P)
+    model = CogACTForCausalLM(c)
+    model.load_state_dict(seeded_state_dict(fx["shapes"], fx["seed"]))
+    model.train()
+    R = i["repeated_diffusion_steps"]
+
+    def make(seed):
+        g = torch.Generator().manual_seed(seed)
+        ids = torch.randint(1, 128, (B, L), generator=g)
+        ids[:, 1] = -200
+        mask = torch.ones(B, L, dtype=torch.long)
+        mask[seed % B, L - 3:] = 0
+        return dict(input_ids=ids.cuda(), attention_mask=mask.cuda(), images=torch.randn(B, 3, 28, 28, generator=g).cuda(),
+                    actions=(torch.rand(B, 112, generator=g) * 2 - 1).cuda(),
+                    noise=torch.randn(R * B, 16, 7, generator=g).cuda(),
+                    timesteps=torch.randint(0, 100, (R * B,), generator=g).cuda(),
+                    drop_mask=(torch.rand(R * B, generator=g) < 0.2).cuda())
+
+    def step(batch):
+        model.zero_grad()
+        out = model(repeated_diffusion_steps=R, **batch)
+        out.loss.backward()
+        return out.loss
+
+    static = make(0)
+    for _ in range(3):                       # warm-up on a side stream (allocator pools, keep-layer planning)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            step(static)
+        torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss_static = step(static)
+    for seed in (1, 2):
+        new = make(seed)
+        eager = step(new).item()
+        torch.cuda.synchronize()
+        ga, gb = model.store.grad_a.clone(), model.store.grad_b.clone()
+        model.store.grad_a.fill_(7.0)        # poison: the replay must rewrite every gradient it owns
+        for k in static:
+            static[k].copy_(new[k])
+        graph.replay()
+        torch.cuda.synchronize()
+        assert loss_static.item() == eager, (loss_static.item(), eager)
+        rep = model.store.grad_a
+        mask = rep != 7.0                    # what the replay wrote
+        covered = 0
+        last = -1
+        for a, b in sorted(model.store._written_ranges):
+            covered += max(0, b - max(a, last))
+            last = max(last, b)
+        assert int(mask.sum()) >= covered - 8, (int(mask.sum()), covered)       # every gradient tensor was rewritten
+        assert torch.equal(rep[mask], ga[mask]) and torch.equal(model.store.grad_b, gb)
