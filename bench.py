@@ -68,6 +68,19 @@ WORKLOADS = {
         vision=dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
                     image_size=224, patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5),
         action_dim=7, chunk_size=8, batch=32, instr_tokens=32, template_tokens=20, extra_tokens=56),
+    # BASELINE.json configs[3]: OFT with the discrete action tokenizer head, chunk 8 x dim 7 = 56 action tokens
+    # (Qwen2.5-7B-shaped decoder as the reference instantiates it; per-GPU share of the global batch 128 on 8 GPUs)
+    "oft_discrete_7b": dict(
+        kind="oft_discrete",
+        llm=dict(model_type="qwen2", vocab_size=152064, hidden_size=3584, intermediate_size=18944,
+                 num_hidden_layers=28, num_attention_heads=28, num_key_value_heads=4, rms_norm_eps=1e-6,
+                 rope_theta=1e6, hidden_act="silu"),
+        vision=dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                    image_size=224, patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5),
+        action_dim=7, chunk_size=8, batch=16, instr_tokens=32, template_tokens=20, extra_tokens=56, num_bins=256),
+    # (BASELINE.json configs[4] words MemVLA as "multi-view (3 cams)": the reference's MemVLA forward is single-view only —
+    # with 5-D images its memory bank indexes episode_ids[i] for i >= B, memvla_arch.py:351-353 — so the measurable
+    # configuration is `memvla_7b` above, the single-view layout the reference supports)
     # small stand-in with the same structure for smoke tests / CPU-only debugging of the harness
     "cogact_tiny": dict(
         llm=dict(model_type="qwen2", vocab_size=1024, hidden_size=256, intermediate_size=704, num_hidden_layers=2,
@@ -106,8 +119,11 @@ def train_flops_per_sample(w: dict, S: int) -> float:
     V = w["vision"]
     dv, mv, lv = V["hidden_size"], V["intermediate_size"], V["num_hidden_layers"] - 1
     T = (V["image_size"] // V["patch_size"]) ** 2 + 1
-    vit = lv * (2 * T * (4 * dv * dv + 2 * dv * mv) + 4 * T * T * dv)
-    proj = 2 * (T - 1) * (dv * d + d * d)
+    nv = w.get("n_views", 1)
+    vit = nv * lv * (2 * T * (4 * dv * dv + 2 * dv * mv) + 4 * T * T * dv)
+    proj = nv * 2 * (T - 1) * (dv * d + d * d)
+    if w.get("kind") == "oft_discrete":    # lm_head on the 56 action rows only (oft_discrete_arch.py:166-168)
+        return 3.0 * (dec + vit + proj + 2 * w["extra_tokens"] * d * L["vocab_size"])
     if w.get("kind") == "oft_l1":      # MLPResNet head: fc1 [A*d -> d] + 2 residual blocks + fc2, per chunk row
         A, Tc = w["action_dim"], w["chunk_size"]
         head = Tc * 2 * (A * d * d + 2 * d * d + d * A)
@@ -134,7 +150,7 @@ def make_batch(w: dict, rank: int, pinned: bool):
                      actions=torch.randn(B, w["chunk_size"], w["action_dim"], generator=g),
                      states=torch.randn(B, w["action_dim"], generator=g))
         return {k: v.pin_memory() for k, v in batch.items()} if pinned else batch
-    L = 2 + w["instr_tokens"] + w["template_tokens"]
+    L = 2 + w["instr_tokens"] + w["template_tokens"] + (w["extra_tokens"] if w.get("kind") == "oft_discrete" else 0)
     V = w["llm"]["vocab_size"]
     ids = torch.randint(1000 if V > 40000 else 1, min(30000, V), (B, L), generator=g)
     ids[:, 0] = 1
@@ -145,9 +161,22 @@ def make_batch(w: dict, rank: int, pinned: bool):
             n = int(torch.randint(1, 9, (), generator=g).item())
             mask[b, L - n:] = 0
     img = w["vision"]["image_size"]
-    images = torch.randn(B, 3, img, img, generator=g)
+    nv = w.get("n_views", 1)
+    images = torch.randn(B, 3, img, img, generator=g) if nv == 1 else torch.randn(B, nv, 3, img, img, generator=g)
     actions = torch.rand(B, w["chunk_size"] * w["action_dim"], generator=g) * 2 - 1
     batch = dict(input_ids=ids, attention_mask=mask, images=images, actions=actions)
+    if w.get("kind") == "oft_discrete":
+        # the A action-label tokens sit right before the last valid token of every row (oft_discrete_arch.py:66-106);
+        # labels there are action token ids U{V-255 .. V-1}, everything else is ignored
+        A = w["extra_tokens"]
+        labels = torch.full((B, L), -100, dtype=torch.long)
+        npl = mask.sum(1)
+        for b in range(B):
+            lo = int(npl[b]) - A - 1
+            tok = torch.randint(V - w["num_bins"] + 1, V, (A,), generator=g)
+            ids[b, lo:lo + A] = tok
+            labels[b, lo:lo + A] = tok
+        batch["labels"] = labels
     if pinned:
         batch = {k: v.pin_memory() for k, v in batch.items()}
     if w.get("kind") == "memvla":      # (dataset, episode, frame): consecutive frames of B/group episodes
@@ -298,6 +327,12 @@ def build_model(w: dict, dev):
                            action_model_type=w["action_model_type"], action_dim=w["action_dim"],
                            chunk_size=w["chunk_size"], **w["mem"])
         model = MemVLAForCausalLM(cfg, device=dev)
+    elif w.get("kind") == "oft_discrete":
+        from dexbotic_b200.model import OFTDiscreteConfig, OFTDiscreteForCausalLM
+        cfg = OFTDiscreteConfig(llm_config=w["llm"], mm_vision_tower=w["vision"], mm_projector_type="mlp2x_gelu",
+                                action_model_type="Discrete", action_dim=w["action_dim"], chunk_size=w["chunk_size"],
+                                num_bins=w["num_bins"])
+        model = OFTDiscreteForCausalLM(cfg, device=dev)
     elif w.get("kind") == "oft_l1":
         from dexbotic_b200.model import OFTConfig, OFTForCausalLM
         cfg = OFTConfig(llm_config=w["llm"], mm_vision_tower=w["vision"], mm_projector_type="mlp2x_gelu",
@@ -382,6 +417,9 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
         S = out.logits.shape[1]
     if w.get("kind") == "pi0":
         S = w["n_cam"] * (w["vision"]["image_size"] // w["vision"]["patch_size"]) ** 2 + w["text_tokens"] + w["chunk_size"] + 1
+    if w.get("kind") == "oft_discrete":  # logits are [B, 56, V] there; S = text + image + 56 action placeholders
+        S = (1 + w["instr_tokens"] + w["template_tokens"] + (w["vision"]["image_size"] // w["vision"]["patch_size"]) ** 2
+             + w["extra_tokens"])
     if w.get("kind") == "oft_l1":       # logits are the predicted actions there; S = text + image + action-query rows
         S = (1 + w["instr_tokens"] + w["template_tokens"] + (w["vision"]["image_size"] // w["vision"]["patch_size"]) ** 2
              + w["extra_tokens"])

@@ -314,7 +314,10 @@ class Decoder:
             q = f"{prefix}layers.{i}."
             bw.grad_range = store.grad_range([n for n in store.order if n.startswith(q)])
         self.final_norm = Norm(kind, eps, store.w(prefix + "norm.weight"), None, store.g(prefix + "norm.weight"))
-        store.set_param_chunks([bw.grad_range for bw in self.blocks])
+        # optimizer / forward overlap: chunk 0 = the embedding table (first read at the image-token splice, after the
+        # vision tower has run), chunk i + 1 = decoder block i
+        self.embed_chunk = store.grad_range([prefix + "embed_tokens.weight"]) if self.embed_g is not None else None
+        store.set_param_chunks([self.embed_chunk] + [bw.grad_range for bw in self.blocks])
         self.theta = rope_theta_of(cfg)
         self._rope_cache = None
         # layers [0, keep_layers) keep their intermediates (no recompute in backward); the rest recompute.
@@ -337,7 +340,7 @@ class Decoder:
         env = AttnEnv(B=B, S=S, keymask=mask_u8, causal=True, pos=pos_i32.reshape(-1), cos=cos, sin=sin)
         keep = self._decide_keep_layers(x2d) if torch.is_grad_enabled() else 0
         for i, bw in enumerate(self.blocks):
-            self.store.wait_chunk(i)        # block i's AdamW update of the previous step (ParamStore.async_optimizer)
+            self.store.wait_chunk(i + 1)    # block i's AdamW update of the previous step (ParamStore.async_optimizer)
             x2d = TransformerBlockFn.apply(x2d, bw, env, self.store, i >= keep)
         return NormFn.apply(x2d, self.final_norm, self.store)
 
@@ -482,6 +485,7 @@ class DexboticVLMModel:
             new_labels = torch.cat([new_labels, torch.full((B, A), IGNORE_INDEX, device=src.device,
                                                            dtype=new_labels.dtype)], dim=1)
             S = S + A
+        self.store.wait_chunk(0)              # the embedding table's update of the previous step
         emb = SpliceFn.apply(feats, src, self.llm.embed_w, self.llm.embed_g, self.store)
         return emb, new_labels, new_mask, pos, S, lengths
 

@@ -138,6 +138,7 @@ class NaVILAForCausalLM(B200Module):
         S = int(lengths.max().item())
         src, new_labels, new_mask, pos = ops.splice_plan(ids, mask_u8, labels, P, max_len, S,
                                                          cfg.tokenizer_padding_side == "left")
+        self.store.wait_chunk(0)              # the embedding table's update of the previous step
         emb = SpliceFn.apply(feats, src, eng.llm.embed_w, eng.llm.embed_g, self.store)
         return emb, new_labels, new_mask, pos, S
 

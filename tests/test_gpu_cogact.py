@@ -303,7 +303,7 @@ def test_overlapped_optimizer_equals_synchronous():
         model, _ = _build(fx["cfg"], fx["shapes"], fx["seed"])
         model.train()
         model.store.async_optimizer = async_opt
-        assert len(model.store._chunk_bounds) == len(model.model_engine.llm.blocks)
+        assert len(model.store._chunk_bounds) == 1 + len(model.model_engine.llm.blocks)     # embedding table + blocks
         ls = []
         for _ in range(4):
             model.zero_grad()
@@ -401,14 +401,17 @@ def test_training_step_is_cuda_graph_capturable():
         return out.loss
 
     static = make(0)
-    for _ in range(3):                       # warm-up on a side stream (allocator pools, keep-layer planning)
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
+    # warm-up and capture on ONE side stream: autograd caches every leaf's AccumulateGrad node together with the stream
+    # it first ran on; a capture on a different stream would have to synchronise with that (uncaptured) stream
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):                   # allocator pools, keep-layer planning
             step(static)
-        torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
+    with torch.cuda.graph(graph, stream=s):
         loss_static = step(static)
     for seed in (1, 2):
         new = make(seed)
@@ -429,4 +432,6 @@ def test_training_step_is_cuda_graph_capturable():
             covered += max(0, b - max(a, last))
             last = max(last, b)
         assert int(mask.sum()) >= covered - 8, (int(mask.sum()), covered)       # every gradient tensor was rewritten
-        assert torch.equal(rep[mask], ga[mask]) and torch.equal(model.store.grad_b, gb)
+        assert torch.equal(rep[mask], ga[mask])
+        # fp32 action-head gradients: same kernels, but their bias / norm reductions end in fp32 atomics (order varies)
+        assert torch.allclose(model.store.grad_b, gb, rtol=1e-4, atol=1e-6)

@@ -345,7 +345,12 @@ def test_oft_generate_action_sampling_matches_oracle_distribution():
     assert chi2 < big.sum() + 6 * (2 * big.sum()) ** 0.5, (chi2, int(big.sum()))
     # (c) cold temperature == restricted argmax (first maximum wins does not matter: bf16 ties have measure ~0 here)
     cold = ops.sample_last(logits, n_last, 1e-3, u).cpu()
-    assert torch.equal(cold, ops.argmax_last(logits, n_last).cpu())
+    tail = logits[:, -n_last:].float().cpu()
+    unique = (tail == tail.max(-1, keepdim=True).values).sum(-1) == 1     # bf16 ties split the mass: any of them is right
+    assert int(unique.sum()) > 0.8 * rows
+    assert torch.equal(cold[unique], ops.argmax_last(logits, n_last).cpu()[unique])
+    tied = (~unique).nonzero().flatten().tolist()
+    assert all(tail[r, cold[r]] == tail[r].max() for r in tied)
 
 
 def test_oft_generate_action_model_call():

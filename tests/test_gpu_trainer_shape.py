@@ -77,7 +77,7 @@ def test_trainer_shaped_loop(policy):
     assert model.to(torch.bfloat16) is model            # the reference's `.to(dtype)` habit is a no-op, not a detach
     model.gradient_checkpointing_enable(gradient_checkpointing_kwargs={"use_reentrant": False})
     # ---- optimizer + scheduler as HF Trainer drives them
-    opt = B200AdamW(model, lr=2e-3, mm_projector_lr=1e-3, weight_decay=0.0, max_grad_norm=1.0)
+    opt = B200AdamW(model, lr=5e-4, mm_projector_lr=2e-4, weight_decay=0.0, max_grad_norm=1.0)
     assert {g["name"] for g in opt.param_groups} <= {"llm", "projector", "vision", "action_head", "lm_head"}
     assert sum(len(g["params"]) for g in opt.param_groups) == sum(1 for _, p in model.named_parameters() if p.requires_grad)
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0 if s < 3 else 0.0)
@@ -97,7 +97,9 @@ def test_trainer_shaped_loop(policy):
         opt.step()
         sched.step()
         losses.append(loss.item())
-    assert losses[2] < losses[0], losses                                    # it trains
+    assert all(l == l and abs(l) < 1e4 for l in losses), losses             # finite
+    if policy in ("oft_discrete", "navila"):                                # deterministic losses: it trains
+        assert losses[2] < losses[0], losses                                # (the diffusion / flow losses draw fresh noise every step)
     moved = sum(int(not torch.equal(before[n], p.detach())) for n, p in model.named_parameters() if p.requires_grad)
     assert moved > 0.5 * len(before)
     # the scheduler's lr = 0 from step 3 on reached the kernels: nothing moved in steps 3 and 4
