@@ -217,6 +217,24 @@ int b200_gate_fuse_fwd(const void* z, const void* x1, const void* x2, void* out,
 int b200_gate_fuse_bwd(const void* dout, const void* z, const void* x1, const void* x2, void* dz, void* dx1, void* dx2,
                        int64_t n, int dtype, void* stream);
 
+/* GPU-side input pipeline.
+ * b200_image_preprocess: PreprocessRGB.__call__ with image_aspect_ratio='pad' (dexbotic/data/dataset/rgb_preprocess.py:
+ * 13-44): expand2square with background (bg_r, bg_g, bg_b) -> PIL bicubic resize to out_size x out_size (HF
+ * CLIPImageProcessor.preprocess) -> rescale / normalise.  src: uint8 [B, H, W, 3] device frames; coeff_* / bounds_*:
+ * Pillow's fixed-point (22-bit) coefficient tables and (first, count) tap windows for the horizontal (square side ->
+ * out_size) and the vertical pass, computed on the host exactly as Resample.c does; lut: float [3, 256] = the
+ * processor's ((v * rescale) - mean_c) / std_c per channel; tmp: uint8 workspace [B, max(H, W), out_size, 3]; dst:
+ * [B, 3, out_size, out_size] (dtype); dst_u8 (optional): the resized uint8 image [B, out_size, out_size, 3].  The uint8
+ * image is bit-exact vs Pillow, the tensor bit-exact vs the processor. */
+int b200_image_preprocess(const uint8_t* src, int64_t B, int64_t H, int64_t W, int64_t out_size, const int32_t* coeff_h,
+                          const int32_t* bounds_h, int ksize_h, const int32_t* coeff_v, const int32_t* bounds_v,
+                          int ksize_v, int bg_r, int bg_g, int bg_b, const float* lut, uint8_t* tmp, void* dst,
+                          uint8_t* dst_u8, int dtype, void* stream);
+/* ActionNorm._normalize (dexbotic/data/dataset/transform/action.py:268-275): quantile=1: (x - a) / (b - a + 1e-6) * 2 - 1
+ * with a = min, b = max; quantile=0: (x - a) / (b + 1e-6) with a = mean, b = std.  float64 in, fp32 out. */
+int b200_action_normalize(const double* x, const double* a, const double* b, float* out, int64_t rows, int64_t D,
+                          int quantile, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
