@@ -716,6 +716,51 @@ def make_hybrid_cogact_tiny(seed: int = 4321):
     print(f"[hybrid_cogact_tiny] wrote {GOLDEN / 'hybrid_cogact_tiny.pt'}")
 
 
+def make_image_preprocess(seed: int = 97):
+    """PreprocessRGB (rgb_preprocess.py:13-44, image_aspect_ratio='pad', both pad modes) with the PIL-backed HF CLIP image
+    processor (what `CLIPImageProcessor` is under the reference's pinned transformers 4.5x; 5.5 renamed it
+    CLIPImageProcessorPil and made a torchvision backend the default), and ActionNorm (action.py:229-275)."""
+    import numpy as np
+    from PIL import Image
+    from transformers import CLIPImageProcessorPil
+    from oracle import image_oracle
+    ref_loader.load_reference()
+    from dexbotic.data.dataset.rgb_preprocess import PreprocessRGB
+    from dexbotic.data.dataset.transform.action import ActionNorm
+    rng = np.random.default_rng(seed)
+    out = {}
+    for size in (32, 224):
+        proc = CLIPImageProcessorPil(size={"shortest_edge": size}, crop_size={"height": size, "width": size})
+        for mode in ("mean", "zero"):
+            pp = PreprocessRGB(proc, image_aspect_ratio="pad", image_pad_mode=mode)
+            for (H, W) in ((60, 80), (90, 50), (33, 33), (240, 320)):
+                if size == 224 and H < 200:
+                    continue
+                img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+                img[: H // 3] = np.linspace(0, 255, W)[None, :, None].astype(np.uint8)     # ramps + noise: ringing, clipping
+                ref = pp(Image.fromarray(img)).numpy()
+                ora, u8 = image_oracle.preprocess_rgb(img, size, proc.image_mean, proc.image_std, proc.rescale_factor, mode)
+                sq = image_oracle.expand2square(img, (0, 0, 0) if mode == "zero" else tuple(int(x * 255) for x in proc.image_mean))
+                pil = np.asarray(Image.fromarray(sq).resize((size, size), resample=Image.BICUBIC))
+                assert np.array_equal(ref, ora) and np.array_equal(pil, u8), (size, mode, H, W)
+                key = f"s{size}_{mode}_{H}x{W}"
+                out[key + "_img"], out[key + "_ref"], out[key + "_u8"] = img, ref, pil
+    out["image_mean"], out["image_std"] = np.array(proc.image_mean), np.array(proc.image_std)
+    # action normalisation, both modes, through the reference transform
+    a = rng.normal(size=(17, 7)) * 3
+    stats = dict(min=rng.normal(size=7) - 4, max=rng.normal(size=7) + 4, mean=rng.normal(size=7),
+                 std=np.abs(rng.normal(size=7)) + 0.1)          # numpy arrays: the transform subtracts them directly
+    for q in (True, False):
+        ref = ActionNorm({"action": stats}, use_quantiles=q)({"action": a.copy()})["action"]
+        assert np.array_equal(ref, image_oracle.action_normalize(a, stats, q)) and ref.dtype == np.float32
+        out[f"action_{'quantile' if q else 'meanstd'}"] = ref
+    out["action_in"] = a
+    for k, v in stats.items():
+        out["stat_" + k] = np.array(v)
+    np.savez_compressed(GOLDEN / "image_preprocess.npz", **out)
+    print(f"[image_preprocess] {len(out)} arrays -> {GOLDEN / 'image_preprocess.npz'}; oracle == reference == Pillow")
+
+
 def tiny_navila_configs():
     from transformers import SiglipVisionConfig
     llm = dict(model_type="llama", vocab_size=160, hidden_size=64, intermediate_size=160, num_hidden_layers=2,
@@ -799,6 +844,7 @@ if __name__ == "__main__":
         sys.exit(0)
     make_navila_tiny()
     make_hybrid_cogact_tiny()
+    make_image_preprocess()
     make_cogact_tiny()
     make_cogact_inference_tiny()
     make_pi0_tiny()
