@@ -1,7 +1,7 @@
 """Mirror of dexbotic/model/oft/{oft_arch.py, oft_discrete_arch.py}: OFTConfig /
-OFTForCausalLM with the `Linear` L1-regression head (oft_arch.py:58-166, oft/action_model/model.py:104-165) and
-OFTDiscreteConfig / OFTDiscreteForCausalLM (the discrete action tokenizer), with the reference's forward signatures.
-The `DiT` DiffusionActionHead variant needs diffusers' DDIMScheduler (un-pinned, not installable offline): not built.
+OFTForCausalLM with the `Linear` L1-regression head (oft_arch.py:58-166, oft/action_model/model.py:104-165) or the `DiT`
+DiffusionActionHead (model.py:197-271; its diffusers scheduler is restated in model/ddim.py), and OFTDiscreteConfig /
+OFTDiscreteForCausalLM (the discrete action tokenizer), with the reference's forward signatures.
 
 Integer semantics (bit-exact, tests/test_gpu_oft.py): inference indices = argmax over the last num_bins-1
 vocabulary logits, first maximum wins (oft_discrete_arch.py:222-224); bins -> continuous idx/(num_bins-1)*2-1
@@ -9,15 +9,17 @@ vocabulary logits, first maximum wins (oft_discrete_arch.py:222-224); bins -> co
 """
 from __future__ import annotations
 
+import math
 from typing import List, Optional
 
 import numpy as np
 import torch
 
 from .. import ops
-from ..functional import CastFn, CrossEntropyFn, GatherRowsFn, Lin, LinearFn, Norm, NormFn
+from ..functional import CastFn, CrossEntropyFn, GatherRowsFn, Lin, LinearFn, MSELossFn, Norm, NormFn
 from ..params import ParamSpec
 from ._module import B200Module
+from .ddim import DDIMScheduler
 from .dexbotic_arch import (CausalLMOutputDexbotic, DexboticConfig, DexboticVLMModel, cfg_get, clip_specs, llm_specs,
                             projector_specs)
 
@@ -283,16 +285,89 @@ class L1RegressionActionHead:
         return LinearFn.apply(h, self.proprio[1], None, st, True, None)
 
 
+def oft_diffusion_head_specs(d: int, action_dim: int, use_proprio: bool, proprio_dim, trainable: bool = True,
+                             prefix: str = "model.action_head.") -> list[ParamSpec]:
+    """DiffusionActionHead (oft/action_model/model.py:197-226): NoisePredictionModel(MLPResNet) + NoisyActionProjector
+    (+ ProprioProjector); the time encoder and the scheduler hold no parameters."""
+    g, c = "action_head", "fp32"
+    P = lambda n, s, **k: ParamSpec(prefix + n, s, g, c, trainable=trainable, **k)  # noqa: E731
+    din, m = d * action_dim, "noise_predictor.mlp_resnet."
+    sp = [P(m + "layer_norm1.weight", (din,)), P(m + "layer_norm1.bias", (din,)),
+          P(m + "fc1.weight", (d, din)), P(m + "fc1.bias", (d,))]
+    for i in range(2):
+        q = f"{m}mlp_resnet_blocks.{i}.ffn."
+        sp += [P(q + "0.weight", (d,)), P(q + "0.bias", (d,)), P(q + "1.weight", (d, d)), P(q + "1.bias", (d,))]
+    sp += [P(m + "layer_norm2.weight", (d,)), P(m + "layer_norm2.bias", (d,)),
+           P(m + "fc2.weight", (action_dim, d)), P(m + "fc2.bias", (action_dim,)),
+           P("noisy_action_projector.fc1.weight", (d, 1)), P("noisy_action_projector.fc1.bias", (d,)),
+           P("noisy_action_projector.fc2.weight", (d, d)), P("noisy_action_projector.fc2.bias", (d,))]
+    if use_proprio:
+        sp += [P("proprio_projector.fc1.weight", (d, proprio_dim)), P("proprio_projector.fc1.bias", (d,)),
+               P("proprio_projector.fc2.weight", (d, d)), P("proprio_projector.fc2.bias", (d,))]
+    return sp
+
+
+def sinusoidal_timestep_encoding(t: torch.Tensor, dim: int) -> torch.Tensor:
+    """SinusoidalPositionalEncoding (oft/action_model/model.py:57-80): [sin(t * w) | cos(t * w)],
+    w_i = exp(-i * ln(10000) / (dim/2 - 1)); fp32.  B values: host-sized work, evaluated with torch on the device."""
+    assert dim % 2 == 0, f"# dimensions must be even but got {dim}"
+    half = dim // 2
+    w = torch.exp(torch.arange(half, device=t.device) * -math.log(10000) / (half - 1))
+    e = t[:, None] * w[None, :]
+    return torch.cat((e.sin(), e.cos()), dim=-1)
+
+
+class DiffusionActionHead(L1RegressionActionHead):
+    """oft/action_model/model.py:197-271: the MLPResNet predicts the noise that was added to the action chunk; the noisy
+    actions enter the LLM as one token per scalar (NoisyActionProjector) behind a diffusion-timestep token."""
+
+    def __init__(self, store, d: int, action_dim: int, chunk: int, use_proprio: bool, num_diffusion_steps: int = 100,
+                 prefix: str = "model.action_head."):
+        self.store, self.d, self.action_dim, self.action_chunk = store, d, action_dim, chunk
+        L = lambda n: Lin.of(store, prefix + n + ".weight", prefix + n + ".bias")  # noqa: E731
+        N_ = lambda n: Norm("ln", 1e-5, store.w(prefix + n + ".weight"), store.w(prefix + n + ".bias"),  # noqa: E731
+                            store.g(prefix + n + ".weight"), store.g(prefix + n + ".bias"))
+        m = "noise_predictor.mlp_resnet."
+        self.ln1, self.fc1 = N_(m + "layer_norm1"), L(m + "fc1")
+        self.blocks = [(N_(f"{m}mlp_resnet_blocks.{i}.ffn.0"), L(f"{m}mlp_resnet_blocks.{i}.ffn.1")) for i in range(2)]
+        self.ln2, self.fc2 = N_(m + "layer_norm2"), L(m + "fc2")
+        self.nap = (L("noisy_action_projector.fc1"), L("noisy_action_projector.fc2"))
+        self.proprio = (L("proprio_projector.fc1"), L("proprio_projector.fc2")) if use_proprio else None
+        self.noise_scheduler = DDIMScheduler(num_train_timesteps=num_diffusion_steps, beta_schedule="squaredcos_cap_v2")
+        self.num_diffusion_steps = num_diffusion_steps
+
+    def time_encoder(self, timesteps: torch.Tensor) -> torch.Tensor:
+        return sinusoidal_timestep_encoding(timesteps, self.d)
+
+    def sample_noisy_actions(self, ground_truth_actions: torch.Tensor) -> dict:
+        """model.py:227-257: noise ~ N(0,1), one timestep per sample, closed-form forward diffusion, timestep token."""
+        B, dev = ground_truth_actions.shape[0], ground_truth_actions.device
+        noise = torch.randn(B, self.action_chunk, self.action_dim, device=dev, dtype=ground_truth_actions.dtype)
+        timesteps = torch.randint(0, self.noise_scheduler.config.num_train_timesteps, (B,), device=dev)
+        noisy = self.noise_scheduler.add_noise(ground_truth_actions, noise, timesteps)
+        temb = self.time_encoder(timesteps).to(noisy.dtype).unsqueeze(1)
+        return dict(noise=noise, noisy_actions=noisy, diffusion_timestep_embeddings=temb)
+
+    def noisy_action_projector(self, noisy_actions: torch.Tensor, anchor) -> torch.Tensor:
+        """[B, chunk, action_dim] -> [B * chunk * action_dim, d]: Linear(1, d), GELU, Linear(d, d) (model.py:33-55)."""
+        st = self.store
+        x = noisy_actions.reshape(-1, 1).float().contiguous()
+        h = LinearFn.apply(x, self.nap[0], "gelu", st, False, anchor)
+        return LinearFn.apply(h, self.nap[1], None, st, True, None)
+
+    predict_noise = L1RegressionActionHead.predict_action       # same MLPResNet over [B, chunk, action_dim * d]
+
+
 class OFTForCausalLM(B200Module):
-    """oft_arch.py:50-251 with action_model_type 'Linear'."""
+    """oft_arch.py:50-251 with action_model_type 'Linear' (L1 regression) or 'DiT' (DiffusionActionHead)."""
     config_class = OFTConfig
 
     def __init__(self, config: OFTConfig, device="cuda"):
         super().__init__()
-        if "Linear" not in (config.action_model_type or ""):
-            raise NotImplementedError("OFTForCausalLM mirrors the L1-regression ('Linear') head; the 'DiT' head needs "
-                                      "diffusers' DDIMScheduler (oft/action_model/model.py:9,220) and is not built; "
-                                      "'Discrete' is OFTDiscreteForCausalLM")
+        amt = config.action_model_type or ""
+        if "Linear" not in amt and "DiT" not in amt:
+            raise NotImplementedError(f"OFTForCausalLM: action_model_type {amt!r}; 'Discrete' is OFTDiscreteForCausalLM")
+        self.diffusion = "Linear" not in amt                    # builder.py:16-35 tests 'Linear' first
         self.config = config
         llm, vis = config.llm_config, config.mm_vision_tower
         d, V = cfg_get(llm, "hidden_size"), cfg_get(llm, "vocab_size")
@@ -300,15 +375,17 @@ class OFTForCausalLM(B200Module):
                  + clip_specs(vis, trainable=not config.freeze_mm_vision)
                  + projector_specs(config.mm_projector_type, cfg_get(vis, "hidden_size"), d,
                                    trainable=not config.freeze_mm_projector)
-                 + oft_linear_head_specs(d, config.action_dim, config.chunk_size, config.use_proprio, config.proprio_dim)
-                 + [ParamSpec("lm_head.weight", (V, d), "lm_head", trainable=False)])   # never used by this head
+                 + (oft_diffusion_head_specs(d, config.action_dim, config.use_proprio, config.proprio_dim)
+                    if self.diffusion else
+                    oft_linear_head_specs(d, config.action_dim, config.chunk_size, config.use_proprio, config.proprio_dim))
+                 + [ParamSpec("lm_head.weight", (V, d), "lm_head", trainable=False)])   # never used by these heads
         store = self._materialize(specs, device)
         for name in store.order:
             if store.slots[name].region == "B":
                 self.get_parameter(name).grad = store.g(name)
         self.model_engine = DexboticVLMModel(store, config)
-        self.model_engine.action_head = L1RegressionActionHead(store, d, config.action_dim, config.chunk_size,
-                                                               config.use_proprio)
+        head_cls = DiffusionActionHead if self.diffusion else L1RegressionActionHead
+        self.model_engine.action_head = head_cls(store, d, config.action_dim, config.chunk_size, config.use_proprio)
 
     def _after_weights_changed(self) -> None:
         self.model_engine.refresh()
@@ -336,17 +413,31 @@ class OFTForCausalLM(B200Module):
         head = eng.action_head
         B, A, T = input_ids.shape[0], cfg.action_dim, cfg.chunk_size
         n_q = T * A
-        n_act = n_q + (1 if cfg.use_proprio else 0)
+        n_act = n_q + (1 if cfg.use_proprio else 0) + (1 if self.diffusion else 0)
         if attention_mask is None:
             attention_mask = torch.ones_like(input_ids)
+        a = None
+        if actions is not None:                                                        # :81-83
+            a = actions.reshape(B, -1, A)[:, :T, :].to(torch.float32)
         emb, _, new_mask, pos, S, lengths = eng._prepare_inputs_labels_for_multimodal(
             input_ids, attention_mask, None, images, append_tokens=n_act, append_token_id=None)
         dev = emb.device
         d = emb.shape[-1]
-        # action embeddings: [proprio token |] action_query, the same learned rows for every sample (:107-121)
-        aq = self.get_parameter("model.action_head.action_query")                     # fp32 [1, n_q, d]
-        act = aq.expand(B, n_q, d)
-        if cfg.use_proprio:
+        noise = None
+        if self.diffusion:
+            # [timestep token | one token per noisy action scalar] (:106-116)
+            if noisy_dict is None:
+                assert a is not None, "actions (or a noisy_dict) are required by the diffusion head"
+                noisy_dict = head.sample_noisy_actions(a)
+            noise = noisy_dict["noise"]
+            temb = noisy_dict["diffusion_timestep_embeddings"].to(device=dev, dtype=torch.float32)
+            proj = head.noisy_action_projector(noisy_dict["noisy_actions"].to(dev), eng.anchor.t).view(B, n_q, d)
+            act = torch.cat([temb.expand(B, 1, d), proj], dim=1)
+        else:
+            # the same learned action_query rows for every sample (:104-105)
+            aq = self.get_parameter("model.action_head.action_query")                 # fp32 [1, n_q, d]
+            act = aq.expand(B, n_q, d)
+        if cfg.use_proprio:                                                            # proprio token in front (:118-121)
             assert states is not None, "states is required when use_proprio is True"
             s_tok = head.proprio_projector(states, eng.anchor.t).view(B, 1, d)
             act = torch.cat([s_tok, act], dim=1)
@@ -355,22 +446,41 @@ class OFTForCausalLM(B200Module):
                 + torch.arange(n_act, device=dev, dtype=torch.int32)[None, :]).reshape(-1).contiguous()
         emb2d = InsertRowsFn.apply(emb.view(B * S, d), act2d, rows)
         hidden2d = eng.llm.forward(emb2d, B, S, new_mask, pos)
-        # extract_action_hidden_states (:204-210), minus the proprio row (:139-140)
+        # extract_action_hidden_states (:204-210), minus the proprio row (:139-140) and the timestep row (:147)
         qrows = rows.view(B, n_act)[:, n_act - n_q:].reshape(-1).contiguous()
         ah = CastFn.apply(GatherRowsFn.apply(hidden2d, qrows), torch.float32)         # [B*n_q, d]
-        predicted = head.predict_action(ah, B)
+        predicted = head.predict_action(ah, B)                                         # actions, or the noise estimate
         loss = None
-        if actions is not None:                                                        # :149-152, fp32
-            a = actions.reshape(B, -1, A)[:, :T, :].to(torch.float32)
-            loss = (a - predicted).abs().mean()
+        if a is not None:                                                              # :149-154, fp32
+            if self.diffusion:
+                loss = MSELossFn.apply(predicted, noise.to(device=dev, dtype=torch.float32))
+            else:
+                loss = (a - predicted).abs().mean()
         return CausalLMOutputDexbotic(loss=loss, logits=predicted)
 
     @torch.no_grad()
-    def inference_action(self, input_ids, image_tensor, inference_args={}, **kwargs):
-        """oft_arch.py:212-251 ('Linear' branch)."""
+    def inference_action(self, input_ids, image_tensor, inference_args={}, noise: Optional[torch.Tensor] = None, **kwargs):
+        """oft_arch.py:212-251.  'Linear': one forward.  'DiT': DDIM loop from N(0,1) (`noise` lets a caller fix the
+        starting sample), one model call per step with the timestep token of that step (:225-250)."""
+        cfg, head = self.config, self.model_engine.action_head
         action_norms = inference_args.get("action_norms")
-        out = self.forward(input_ids=input_ids, images=image_tensor, states=inference_args.get("states"))
-        actions = np.clip(out.logits[0].float().cpu().numpy(), -1, 1)        # _denorm, dexbotic_arch.py:546-563
+        states = inference_args.get("states")
+        if not self.diffusion:
+            predicted = self.forward(input_ids=input_ids, images=image_tensor, states=states).logits
+        else:
+            sched = head.noise_scheduler
+            sched.set_timesteps(inference_args.get("num_ddim_steps", 10))
+            dev = input_ids.device
+            if noise is None:
+                noise = torch.randn(input_ids.size(0), cfg.chunk_size, cfg.action_dim, device=dev, dtype=torch.float32)
+            cur = noise.to(device=dev, dtype=torch.float32)
+            for t in sched.timesteps.tolist():
+                temb = head.time_encoder(torch.tensor([float(t)], device=dev)).unsqueeze(1)
+                out = self.forward(input_ids=input_ids, images=image_tensor, states=states,
+                                   noisy_dict=dict(noise=noise, noisy_actions=cur, diffusion_timestep_embeddings=temb))
+                cur = sched.step(out.logits, t, cur).prev_sample
+            predicted = cur
+        actions = np.clip(predicted[0].float().cpu().numpy(), -1, 1)         # _denorm, dexbotic_arch.py:546-563
         mn, mx = np.array(action_norms["min"]).reshape(1, -1), np.array(action_norms["max"]).reshape(1, -1)
         return (mn + (actions + 1) * 0.5 * (mx - mn)).tolist()
 

@@ -326,6 +326,72 @@ def make_oft_linear_tiny(seed: int = 8642):
     print("[oft_linear_tiny] wrote fixture")
 
 
+def make_oft_diffusion_tiny(seed: int = 8643):
+    """OFTForCausalLM with the `DiT` DiffusionActionHead (oft_arch.py:103-154, model.py:197-271), with and without the
+    proprio token: training forward/backward at a fixed noisy_dict, and the DDIM inference loop from a fixed start.  The
+    reference code runs around the restated scheduler (oracle/ddim_oracle.py): the scheduler's parity is unpinned."""
+    out_fx = {}
+    for use_proprio in (False, True):
+        llm, clip, cfg = tiny_cogact_configs()
+        cfg = dict(cfg, chunk_size=8, action_dim=7, use_proprio=use_proprio, proprio_dim=9 if use_proprio else None)
+        model = ref_loader.build_reference_oft_diffusion(llm, clip, 7, 8, use_proprio, cfg["proprio_dim"])
+        sd = seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        g = torch.Generator().manual_seed(seed)
+        B, L = 3, 12
+        ids = torch.randint(1, 128, (B, L), generator=g)
+        ids[:, 1] = vla_oracle.IMAGE_TOKEN_INDEX
+        mask = torch.ones(B, L, dtype=torch.long)
+        mask[1, L - 3:] = 0
+        mask[2, L - 1:] = 0
+        images = torch.randn(B, 3, 28, 28, generator=g)
+        actions = torch.rand(B, 8 * 7, generator=g) * 2 - 1
+        states = torch.randn(B, 9, generator=g) if use_proprio else None
+        torch.manual_seed(seed + 1)
+        noisy = model.model.action_head.sample_noisy_actions(actions.reshape(B, 8, 7))
+        out = model(input_ids=ids, attention_mask=mask, images=images, actions=actions, states=states, noisy_dict=noisy)
+        out.loss.backward()
+        ora = vla_oracle.oft_diffusion_forward(sd, cfg, ids, mask, images, noisy, actions, states)
+        d_loss = abs(ora["loss"].item() - out.loss.item())
+        d_pred = (ora["predicted_noise"] - out.logits).abs().max().item()
+        print(f"[oft_diffusion_tiny proprio={use_proprio}] reference loss {out.loss.item():.8f} oracle "
+              f"{ora['loss'].item():.8f}; noise max|d|={d_pred:.2e}")
+        assert d_loss < 1e-5 and d_pred < 1e-4
+        names = ["model.action_head.noisy_action_projector.fc1.weight", "model.action_head.noisy_action_projector.fc2.weight",
+                 "model.action_head.noise_predictor.mlp_resnet.fc1.weight",
+                 "model.action_head.noise_predictor.mlp_resnet.layer_norm1.weight",
+                 "model.action_head.noise_predictor.mlp_resnet.mlp_resnet_blocks.1.ffn.1.weight",
+                 "model.action_head.noise_predictor.mlp_resnet.fc2.bias", "model.llm.layers.1.mlp.up_proj.weight",
+                 "model.llm.layers.0.self_attn.v_proj.weight", "model.mm_projector.2.weight",
+                 "model.llm.embed_tokens.weight"]
+        if use_proprio:
+            names += ["model.action_head.proprio_projector.fc1.weight", "model.action_head.proprio_projector.fc2.bias"]
+        params = dict(model.named_parameters())
+        grads = {n: params[n].grad.clone() for n in names}
+        # inference: the reference draws its own start noise from the global RNG (oft_arch.py:226-229)
+        model.eval()
+        norms = dict(min=[-1.0] * 7, max=[1.0] * 7)
+        torch.manual_seed(seed + 2)
+        ref_actions = model.inference_action(ids[:1], images[:1], dict(action_norms=norms, num_ddim_steps=5,
+                                                                       states=states[:1] if use_proprio else None))
+        torch.manual_seed(seed + 2)
+        start = torch.randn(1, 8, 7, dtype=images.dtype)
+        ora_actions = vla_oracle.oft_diffusion_inference(sd, cfg, ids[:1], images[:1], start, 5,
+                                                         states[:1] if use_proprio else None)
+        d_inf = (torch.tensor(ref_actions) - ora_actions[0].clamp(-1, 1)).abs().max().item()
+        print(f"[oft_diffusion_tiny proprio={use_proprio}] inference max|d|={d_inf:.2e}")
+        assert d_inf < 1e-4
+        out_fx[use_proprio] = dict(cfg=cfg, shapes={k: tuple(v.shape) for k, v in sd.items()},
+                                   inputs=dict(input_ids=ids, attention_mask=mask, images=images, actions=actions,
+                                               states=states, noisy_dict={k: v.detach() for k, v in noisy.items()},
+                                               start_noise=start, num_ddim_steps=5),
+                                   outputs=dict(loss=out.loss.detach(), predicted_noise=out.logits.detach(),
+                                                grads=grads, inference_actions=torch.tensor(ref_actions)))
+    torch.save(dict(seed=seed, cases=out_fx), GOLDEN / "oft_diffusion_tiny.pt")
+    print("[oft_diffusion_tiny] wrote fixture")
+
+
 def tiny_pi0_configs():
     llm = dict(model_type="gemma", vocab_size=128, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
                num_attention_heads=4, num_key_value_heads=1, head_dim=16, rms_norm_eps=1e-6, rope_theta=10000.0,
@@ -855,5 +921,6 @@ if __name__ == "__main__":
     make_oft_discrete_tiny()
     make_oft_discrete_proprio_tiny()
     make_oft_linear_tiny()
+    make_oft_diffusion_tiny()
     make_splice_cases()
     make_integer_kats()

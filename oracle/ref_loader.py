@@ -10,7 +10,7 @@ Compatibility recipe, all in memory, /root/reference untouched:
   1. import transformers first (it probes find_spec('timm'));
   2. inject stub modules for the un-vendored, un-pinned third-party deps the reference imports:
      timm.models.vision_transformer.{Attention, Mlp} (restated from timm's published definition: fused
-     qkv Linear, SDPA, proj; fc1/act/fc2) and diffusers' DDIMScheduler (import-only);
+     qkv Linear, SDPA, proj; fc1/act/fc2) and diffusers' DDIMScheduler (oracle/ddim_oracle.py, restated);
   3. exec dexbotic_arch.py / pi0_arch.py with the un-defaulted dataclass fields given `= None` (transformers
      >= 5 turns PretrainedConfig subclasses into dataclasses);
   4. vision towers are built from config objects instead of from_pretrained (no network / weights).
@@ -98,9 +98,9 @@ def _install_diffusers_stub():
     if "diffusers" in sys.modules:
         return
 
-    class DDIMScheduler:  # import-only: the OFT *discrete* path never instantiates it
-        def __init__(self, *a, **k):
-            raise NotImplementedError("diffusers is not available in this container")
+    # diffusers is absent: the reference's DiffusionActionHead runs around the restated scheduler (parity of the
+    # scheduler itself is unpinned, see oracle/ddim_oracle.py)
+    from oracle.ddim_oracle import DDIMSchedulerOracle as DDIMScheduler
 
     _stub_module("diffusers")
     _stub_module("diffusers.schedulers")
@@ -206,6 +206,18 @@ def build_reference_oft_linear(llm_config, clip_config, action_dim: int = 7, chu
     from dexbotic.model.oft.oft_arch import OFTConfig, OFTForCausalLM
     cfg = OFTConfig(llm_config=llm_config, mm_projector_type=mm_projector_type, mm_vision_tower=clip_config,
                     action_model_type="Linear", action_dim=action_dim, chunk_size=chunk_size,
+                    use_proprio=use_proprio, proprio_dim=proprio_dim)
+    return OFTForCausalLM(cfg)
+
+
+def build_reference_oft_diffusion(llm_config, clip_config, action_dim: int = 7, chunk_size: int = 8,
+                                  use_proprio: bool = False, proprio_dim=None, mm_projector_type: str = "mlp2x_gelu"):
+    """Reference OFTForCausalLM with the `DiT` DiffusionActionHead (oft/action_model/model.py:197-271) built around the
+    restated DDIM scheduler."""
+    load_reference()
+    from dexbotic.model.oft.oft_arch import OFTConfig, OFTForCausalLM
+    cfg = OFTConfig(llm_config=llm_config, mm_projector_type=mm_projector_type, mm_vision_tower=clip_config,
+                    action_model_type="DiT", action_dim=action_dim, chunk_size=chunk_size,
                     use_proprio=use_proprio, proprio_dim=proprio_dim)
     return OFTForCausalLM(cfg)
 

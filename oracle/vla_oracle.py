@@ -663,6 +663,75 @@ def oft_l1_forward(sd, cfg: dict, input_ids, attention_mask, images, actions=Non
     return dict(loss=loss, predicted_actions=pred, action_hidden=ah)
 
 
+def sinusoidal_timestep_encoding(t: torch.Tensor, dim: int) -> torch.Tensor:
+    """SinusoidalPositionalEncoding.forward (oft/action_model/model.py:71-80)."""
+    half = dim // 2
+    w = torch.exp(torch.arange(half) * -math.log(10000) / (half - 1))
+    e = t[:, None] * w[None, :]
+    return torch.cat((e.sin(), e.cos()), dim=-1)
+
+
+def oft_diffusion_forward(sd, cfg: dict, input_ids, attention_mask, images, noisy_dict: dict, actions=None, states=None):
+    """OFTForCausalLM.forward with the `DiT` DiffusionActionHead (oft_arch.py:103-154; head model.py:197-271): the
+    action rows are [proprio token |] timestep token | NoisyActionProjector(one scalar per token); the MLPResNet reads
+    the hidden states of the noisy-action rows chunk-wise and predicts the noise; loss = MSE(noise_pred, noise).
+    `noisy_dict` = dict(noise, noisy_actions, diffusion_timestep_embeddings) as sample_noisy_actions returns it."""
+    A, T = cfg["action_dim"], cfg["chunk_size"]
+    B = input_ids.shape[0]
+    feats = clip_vision_features(sd, "model.mm_vision_tower.", images, cfg["vision"])
+    feats = mlp_projector(sd, "model.mm_projector.", feats, cfg.get("projector_depth", 2))
+    emb, _, msk, _ = splice(sd["model.llm.embed_tokens.weight"], feats, input_ids, attention_mask, None,
+                            cfg.get("tokenizer_model_max_length"), "right")
+    h = "model.action_head."
+    na = noisy_dict["noisy_actions"].reshape(B, -1).unsqueeze(-1)                              # :113
+    act = F.linear(F.gelu(F.linear(na, sd[h + "noisy_action_projector.fc1.weight"], sd[h + "noisy_action_projector.fc1.bias"])),
+                   sd[h + "noisy_action_projector.fc2.weight"], sd[h + "noisy_action_projector.fc2.bias"])
+    act = torch.cat([noisy_dict["diffusion_timestep_embeddings"].expand(B, 1, -1), act], dim=1)   # :115
+    if cfg.get("use_proprio"):
+        st = F.linear(F.gelu(F.linear(states, sd[h + "proprio_projector.fc1.weight"], sd[h + "proprio_projector.fc1.bias"])),
+                      sd[h + "proprio_projector.fc2.weight"], sd[h + "proprio_projector.fc2.bias"])
+        act = torch.cat([st.reshape(B, -1, emb.shape[-1]), act], dim=1)
+    n_act = act.shape[1]
+    S, D = emb.shape[1], emb.shape[2]
+    lens = msk.long().sum(dim=1)
+    emb2 = torch.zeros(B, S + n_act, D, dtype=emb.dtype)
+    msk2 = torch.zeros(B, S + n_act, dtype=torch.bool)
+    for i in range(B):                                                 # insert_action_embedding, oft_arch.py:169-201
+        n = int(lens[i])
+        emb2[i, :n] = emb[i, :n]
+        emb2[i, n:n + n_act] = act[i]
+        emb2[i, n + n_act:] = emb[i, n:]
+        msk2[i, :n + n_act] = True
+    pid = torch.arange(S + n_act)[None, :].expand(B, S + n_act)
+    hs = decoder_forward(sd, "model.llm.", emb2, msk2, pid, cfg["llm"])
+    ah = torch.stack([hs[i, int(lens[i]):int(lens[i]) + n_act] for i in range(B)])       # :204-210
+    if cfg.get("use_proprio"):
+        ah = ah[:, 1:]                                                                    # :139-140
+    ah = ah[:, 1:]                                                                        # timestep row, :147
+    pred = mlp_resnet(sd, h + "noise_predictor.mlp_resnet.", ah.reshape(B, T, -1))
+    loss = None
+    if actions is not None:
+        loss = F.mse_loss(pred, noisy_dict["noise"], reduction="mean")
+    return dict(loss=loss, predicted_noise=pred, action_hidden=ah)
+
+
+def oft_diffusion_inference(sd, cfg: dict, input_ids, images, noise, num_ddim_steps: int = 10, states=None,
+                            num_diffusion_steps: int = 100):
+    """OFTForCausalLM.inference_action, `DiT` branch (oft_arch.py:224-250): DDIM loop, one full model call per step."""
+    from oracle.ddim_oracle import DDIMSchedulerOracle
+    sched = DDIMSchedulerOracle(num_train_timesteps=num_diffusion_steps, beta_schedule="squaredcos_cap_v2")
+    sched.set_timesteps(num_ddim_steps)
+    D = sd["model.llm.embed_tokens.weight"].shape[1]
+    cur = noise
+    mask = torch.ones_like(input_ids)
+    for t in sched.timesteps:
+        temb = sinusoidal_timestep_encoding(torch.Tensor([t]), D).unsqueeze(1)
+        out = oft_diffusion_forward(sd, cfg, input_ids, mask, images,
+                                    dict(noise=noise, noisy_actions=cur, diffusion_timestep_embeddings=temb), None, states)
+        cur = sched.step(out["predicted_noise"], t, cur).prev_sample
+    return cur
+
+
 # ----------------------------------------------------------------------------------------------
 # pi0 — dexbotic/model/pi0/pi0_arch.py (SigLIP tower: modules/mm_vision/siglip/siglip_encoder.py:61-86)
 # ----------------------------------------------------------------------------------------------

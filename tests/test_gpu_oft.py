@@ -155,6 +155,83 @@ def test_oft_linear_training_and_inference():
     assert t.shape == (8, 7) and torch.isfinite(t).all() and t.abs().max() <= 2.0
 
 
+def _build_diffusion(case, seed):
+    from dexbotic_b200.model import OFTConfig, OFTForCausalLM
+    from oracle.weights import seeded_state_dict
+    cfg = case["cfg"]
+    c = OFTConfig(llm_config=cfg["llm"], mm_vision_tower=cfg["vision"], mm_projector_type="mlp2x_gelu",
+                  action_model_type="DiT", action_dim=cfg["action_dim"], chunk_size=cfg["chunk_size"],
+                  use_proprio=cfg["use_proprio"], proprio_dim=cfg["proprio_dim"])
+    model = OFTForCausalLM(c, device="cuda")
+    sd = {k: v for k, v in seeded_state_dict(case["shapes"], seed).items() if "position_ids" not in k}
+    model.load_state_dict(sd, strict=True)
+    return model
+
+
+@pytest.mark.parametrize("use_proprio", [False, True])
+def test_oft_diffusion_matches_reference_golden(use_proprio):
+    """OFTForCausalLM + DiffusionActionHead (oft_arch.py:103-154, oft/action_model/model.py:197-271) vs the reference
+    run at the same noisy_dict: state-dict keys, predicted noise, MSE loss, gradients; then the DDIM inference loop from
+    the same start noise."""
+    fx = torch.load(GOLDEN / "oft_diffusion_tiny.pt", weights_only=False)
+    case = fx["cases"][use_proprio]
+    model = _build_diffusion(case, fx["seed"])
+    ours = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert ours == {k: tuple(v) for k, v in case["shapes"].items() if "position_ids" not in k}
+    model.train()
+    i = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in case["inputs"].items()}
+    nd = {k: v.cuda() for k, v in case["inputs"]["noisy_dict"].items()}
+    model.zero_grad()
+    out = model(input_ids=i["input_ids"], attention_mask=i["attention_mask"], images=i["images"], actions=i["actions"],
+                states=i["states"], noisy_dict=nd)
+    ref = case["outputs"]
+    assert abs(out.loss.item() - ref["loss"].item()) < 2e-2 * abs(ref["loss"].item()), (out.loss.item(), ref["loss"].item())
+    a, b = out.logits.float().flatten(), ref["predicted_noise"].cuda().flatten()
+    rel = ((a - b).norm() / b.norm()).item()
+    assert rel < 5e-2, rel
+    out.loss.backward()
+    bad = []
+    for name, gref in ref["grads"].items():
+        g = model.store.g(name).float().flatten()
+        r = gref.cuda().flatten()
+        relg = ((g - r).norm() / (r.norm() + 1e-12)).item()
+        cos = torch.nn.functional.cosine_similarity(g, r, dim=0).item()
+        if not (relg < 0.12 and cos > 0.99):
+            bad.append((name, round(relg, 4), round(cos, 5)))
+    assert not bad, bad
+    model.eval()
+    st = i["states"][:1] if use_proprio else None
+    acts = model.inference_action(i["input_ids"][:1], i["images"][:1],
+                                  {"action_norms": {"min": [-1.0] * 7, "max": [1.0] * 7}, "states": st,
+                                   "num_ddim_steps": case["inputs"]["num_ddim_steps"]}, noise=i["start_noise"])
+    d = (torch.tensor(acts) - ref["inference_actions"]).abs().max().item()
+    assert d < 8e-2, d                    # 5 bf16 trunk passes feed each other; the oracle agrees to 2e-5 in fp32
+
+
+def test_oft_diffusion_training_reduces_the_noise_loss():
+    fx = torch.load(GOLDEN / "oft_diffusion_tiny.pt", weights_only=False)
+    case = fx["cases"][True]
+    model = _build_diffusion(case, fx["seed"])
+    model.train()
+    i = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in case["inputs"].items()}
+    nd = {k: v.cuda() for k, v in case["inputs"]["noisy_dict"].items()}
+    losses = []
+    for _ in range(8):
+        model.zero_grad()
+        out = model(input_ids=i["input_ids"], attention_mask=i["attention_mask"], images=i["images"],
+                    actions=i["actions"], states=i["states"], noisy_dict=nd)
+        out.loss.backward()
+        model.optimizer_step(base_lr=1e-3)
+        losses.append(out.loss.item())
+    assert losses[-1] < 0.8 * losses[0], losses
+    # sampled noisy_dict path (model.py:227-257): shapes, dtype, timestep range
+    model.zero_grad()
+    out = model(input_ids=i["input_ids"], attention_mask=i["attention_mask"], images=i["images"], actions=i["actions"],
+                states=i["states"])
+    assert torch.isfinite(out.loss) and out.logits.shape == (3, 8, 7)
+    out.loss.backward()
+
+
 def test_layernorm_wide_rows():
     """D = action_dim * hidden = 25088 (OFT MLPResNet input LayerNorm) takes the streaming backward kernel."""
     from dexbotic_b200 import ops

@@ -115,6 +115,56 @@ def test_oft_linear_tiny_matches_reference():
         assert (out["predicted_actions"] - ref["predicted_actions"]).abs().max().item() < 1e-4
 
 
+def test_oft_diffusion_tiny_matches_reference():
+    """OFT `DiT` head: oracle forward (fixed noisy_dict) and DDIM inference vs the reference code run around the restated
+    scheduler (oracle/ddim_oracle.py; the scheduler itself is parity-unpinned: diffusers is absent)."""
+    fx = torch.load(GOLDEN / "oft_diffusion_tiny.pt", weights_only=False)
+    for use_proprio, case in fx["cases"].items():
+        sd = seeded_state_dict(case["shapes"], fx["seed"])
+        i, ref = case["inputs"], case["outputs"]
+        out = vla_oracle.oft_diffusion_forward(sd, case["cfg"], i["input_ids"], i["attention_mask"], i["images"],
+                                               i["noisy_dict"], i["actions"], i["states"])
+        assert abs(out["loss"].item() - ref["loss"].item()) < 1e-5
+        assert (out["predicted_noise"] - ref["predicted_noise"]).abs().max().item() < 1e-4
+        st = i["states"][:1] if use_proprio else None
+        acts = vla_oracle.oft_diffusion_inference(sd, case["cfg"], i["input_ids"][:1], i["images"][:1], i["start_noise"],
+                                                  i["num_ddim_steps"], st)
+        assert (acts[0].clamp(-1, 1) - ref["inference_actions"]).abs().max().item() < 1e-4
+
+
+def test_product_ddim_scheduler_matches_the_restated_one():
+    """dexbotic_b200.model.ddim (host arithmetic, no CUDA) vs oracle/ddim_oracle.py: tables, add_noise, timesteps, step —
+    and two closed-form properties of the DDIM update: with the true noise it returns sqrt(a_prev) x0 + sqrt(1-a_prev) eps,
+    and the last step (prev_t < 0, alpha = 1) returns the clipped x0 estimate."""
+    from dexbotic_b200.model.ddim import DDIMScheduler
+    from oracle.ddim_oracle import DDIMSchedulerOracle
+    a, b = DDIMSchedulerOracle(100, "squaredcos_cap_v2"), DDIMScheduler(100)
+    assert (a.alphas_cumprod - b.alphas_cumprod).abs().max().item() < 1e-6
+    assert 0.99 < float(b.alphas_cumprod[0]) < 1 and float(b.alphas_cumprod[-1]) < 1e-5
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.rand(4, 8, 7, generator=g) * 2 - 1
+    eps = torch.randn(4, 8, 7, generator=g)
+    t = torch.tensor([0, 17, 50, 99])
+    assert (a.add_noise(x0, eps, t) - b.add_noise(x0, eps, t)).abs().max().item() < 1e-6
+    for n in (5, 10, 25, 100):
+        a.set_timesteps(n)
+        b.set_timesteps(n)
+        assert a.timesteps.tolist() == b.timesteps.tolist() and len(b.timesteps) == n and b.timesteps[-1] == 0
+        x = torch.randn(4, 8, 7, generator=g)
+        for ts in b.timesteps.tolist():
+            pa, pb = a.step(eps, ts, x).prev_sample, b.step(eps, ts, x).prev_sample
+            assert (pa - pb).abs().max().item() < 2e-5
+            x = pb
+    b.set_timesteps(10)
+    ts = 50
+    xt = b.add_noise(x0, eps, torch.full((4,), ts))
+    prev = b.step(eps, ts, xt).prev_sample
+    ap = float(b.alphas_cumprod[ts - 10])
+    assert (prev - (ap ** 0.5 * x0 + (1 - ap) ** 0.5 * eps)).abs().max().item() < 1e-4
+    last = b.step(eps, 0, b.add_noise(x0, eps, torch.zeros(4, dtype=torch.long)))
+    assert (last.prev_sample - x0).abs().max().item() < 1e-4
+
+
 def test_memvla_tiny_matches_reference():
     """MemVLA oracle (BottleneckSE, memory bank with token-merge consolidation, DiT per_attn) vs the reference."""
     fx = torch.load(GOLDEN / "memvla_tiny.pt", weights_only=False)
