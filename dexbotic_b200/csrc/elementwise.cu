@@ -689,7 +689,19 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
                                                     float* __restrict__ m, float* __restrict__ v,
                                                     bf16* __restrict__ shadow, int64_t n, float b2, float omb1,
                                                     float omb2, float eps, float decay, float step_size,
-                                                    float bc2_sqrt, const float* __restrict__ clip) {
+                                                    float bc2_sqrt, const float* __restrict__ clip,
+                                                    const float* __restrict__ hyper) {
+  // hyper != NULL: the seven scalars come from device memory (b200_adamw_dev): a captured CUDA graph of the step is
+  // replayed with new learning rates / bias corrections without re-capturing
+  if (hyper != nullptr) {
+    b2 = hyper[0];
+    omb1 = hyper[1];
+    omb2 = hyper[2];
+    eps = hyper[3];
+    decay = hyper[4];
+    step_size = hyper[5];
+    bc2_sqrt = hyper[6];
+  }
   // torch.optim.AdamW arithmetic (torch/optim/adamw.py, single-tensor path) with its host scalars evaluated in
   // double exactly as Python does and rounded to fp32 once: exp_avg.lerp_(g, 1-b1); exp_avg_sq.mul_(b2).addcmul_(g, g,
   // value=1-b2); p.mul_(1 - lr*wd); denom = sqrt(exp_avg_sq) / sqrt(bc2) + eps; p.addcdiv_(exp_avg, denom, -lr/bc1)
@@ -1051,10 +1063,47 @@ int b200_adamw(float* p, const void* g, float* m, float* v, void* shadow_bf16, i
   const float decay = (float)(1.0 - lr * weight_decay), step_size = (float)(lr / bc1), bc2_sqrt = (float)sqrt(bc2);
   if (g_dtype == B200_F32)
     adamw_kernel<float><<<grid_1d(n / 8 + 1, 256), 256, 0, STREAM>>>(p, (const float*)g, m, v, (bf16*)shadow_bf16, n, b2,
-                                                                     omb1, omb2, e, decay, step_size, bc2_sqrt, clip);
+                                                                     omb1, omb2, e, decay, step_size, bc2_sqrt, clip,
+                                                                     nullptr);
   else
     adamw_kernel<bf16><<<grid_1d(n / 8 + 1, 256), 256, 0, STREAM>>>(p, (const bf16*)g, m, v, (bf16*)shadow_bf16, n, b2,
-                                                                    omb1, omb2, e, decay, step_size, bc2_sqrt, clip);
+                                                                    omb1, omb2, e, decay, step_size, bc2_sqrt, clip,
+                                                                    nullptr);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_adamw_hyper(double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step, float* out8) {
+  // the seven fp32 scalars of one AdamW update exactly as b200_adamw derives them (double arithmetic, rounded once);
+  // step == 0 yields the identity update (weights, moments unchanged)
+  if (step <= 0) {
+    const float id[8] = {1.0f, 0.0f, 0.0f, 1.0f, 1.0f, 0.0f, 1.0f, 0.0f};
+    for (int i = 0; i < 8; ++i) out8[i] = id[i];
+    return 0;
+  }
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  out8[0] = (float)beta2;
+  out8[1] = (float)(1.0 - beta1);
+  out8[2] = (float)(1.0 - beta2);
+  out8[3] = (float)eps;
+  out8[4] = (float)(1.0 - lr * weight_decay);
+  out8[5] = (float)(lr / bc1);
+  out8[6] = (float)sqrt(bc2);
+  out8[7] = 0.0f;
+  return 0;
+}
+
+int b200_adamw_dev(float* p, const void* g, float* m, float* v, void* shadow_bf16, int64_t n, const float* hyper8,
+                   const float* clip, int g_dtype, void* stream) {
+  if (n == 0) return 0;
+  B200_CHECK(hyper8 != nullptr, "adamw_dev: hyper8 (device pointer to the 8-float scalar block) is required");
+  if (g_dtype == B200_F32)
+    adamw_kernel<float><<<grid_1d(n / 8 + 1, 256), 256, 0, STREAM>>>(p, (const float*)g, m, v, (bf16*)shadow_bf16, n, 0.f,
+                                                                     0.f, 0.f, 0.f, 0.f, 0.f, 1.f, clip, hyper8);
+  else
+    adamw_kernel<bf16><<<grid_1d(n / 8 + 1, 256), 256, 0, STREAM>>>(p, (const bf16*)g, m, v, (bf16*)shadow_bf16, n, 0.f,
+                                                                    0.f, 0.f, 0.f, 0.f, 0.f, 1.f, clip, hyper8);
   B200_LAUNCH_OK();
   return 0;
 }

@@ -70,7 +70,16 @@ struct FaParams {
   bf16 *dq, *dk, *dv;
   long long o_ld, o_sh, o_sb;      // element strides of out (row, head, batch)
   long long g_ld, gq_sh, gkv_sh, g_sb;   // strides of dq / dk / dv
+  long long* trace;     // debugging: clock64() stamps of CTA 0 (b200_flash_attn_set_trace), NULL in production
 };
+
+// slot-major [slot][64] table of clock64() stamps taken by CTA 0 for its first 64 steps (tools/trace_flash.py)
+#define FA_TRACE(slot, idx)                                                                      \
+  do {                                                                                           \
+    if (p.trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (idx) < 64u)        \
+      p.trace[(slot) * 64 + (idx)] = clock64();                                                  \
+  } while (0)
+
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -303,31 +312,37 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
   const int stages = p.stages;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------ TMA producer: the whole warp runs the loop, one elected lane issues
+    {
       int stage = 0, qi = 0;
       uint32_t phase = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
         const FwdItem im = fwd_item<kTiles>(p, it);
-        mbar_wait(&bar_q_empty, (uint32_t)(qi & 1) ^ 1u);
-        int nvalid = 0;
-        for (int t = 0; t < kTiles; ++t) nvalid += im.nblk[t] > 0 ? 1 : 0;
-        mbar_expect_tx(&bar_q_full, (uint32_t)(nvalid * p.katoms * kAtom128));
-        for (int t = 0; t < kTiles; ++t) {
-          if (im.nblk[t] == 0) continue;
-          for (int a = 0; a < p.katoms; ++a)
-            tma_load_4d(sQ + (t * p.katoms + a) * kAtom128, &p.tmQ, &bar_q_full, a * 64, im.tile[t] * 128, im.h[t],
-                        im.b);
-        }
-        for (int j = 0; j < im.n; ++j) {
-          mbar_wait(&bar_kv_empty[stage], phase ^ 1u);
-          mbar_expect_tx(&bar_kv_full[stage], (uint32_t)stage_bytes);
-          uint8_t* sK = sRing + stage * stage_bytes;
-          uint8_t* sV = sK + p.katoms * kAtom64;
-          for (int a = 0; a < p.katoms; ++a) {
-            tma_load_4d(sK + a * kAtom64, &p.tmK, &bar_kv_full[stage], a * 64, j * 64, im.kvh, im.b);
-            tma_load_4d(sV + a * kAtom64, &p.tmV, &bar_kv_full[stage], a * 64, j * 64, im.kvh, im.b);
+        mbar_wait_u(&bar_q_empty, (uint32_t)(qi & 1) ^ 1u);
+        if (elect_one()) {
+          int nvalid = 0;
+          for (int t = 0; t < kTiles; ++t) nvalid += im.nblk[t] > 0 ? 1 : 0;
+          mbar_expect_tx(&bar_q_full, (uint32_t)(nvalid * p.katoms * kAtom128));
+          for (int t = 0; t < kTiles; ++t) {
+            if (im.nblk[t] == 0) continue;
+            for (int a = 0; a < p.katoms; ++a)
+              tma_load_4d(sQ + (t * p.katoms + a) * kAtom128, &p.tmQ, &bar_q_full, a * 64, im.tile[t] * 128, im.h[t],
+                          im.b);
           }
+        }
+        __syncwarp();
+        for (int j = 0; j < im.n; ++j) {
+          mbar_wait_u(&bar_kv_empty[stage], phase ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(&bar_kv_full[stage], (uint32_t)stage_bytes);
+            uint8_t* sK = sRing + stage * stage_bytes;
+            uint8_t* sV = sK + p.katoms * kAtom64;
+            for (int a = 0; a < p.katoms; ++a) {
+              tma_load_4d(sK + a * kAtom64, &p.tmK, &bar_kv_full[stage], a * 64, j * 64, im.kvh, im.b);
+              tma_load_4d(sV + a * kAtom64, &p.tmV, &bar_kv_full[stage], a * 64, j * 64, im.kvh, im.b);
+            }
+          }
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
@@ -336,8 +351,9 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
       }
     }
   } else if (warp == 1 || (kTiles == 2 && warp == 3)) {
-    // -------------------------------------- MMA issuer of tile t: the two tiles of a CTA run decoupled from each other
-    if (lane == 0) {
+    // -------------------------------------- MMA issuer of tile t: the two tiles of a CTA run decoupled from each other.
+    // The whole warp runs the loop (warp-uniform control flow); one elected lane issues MMAs and commits.
+    {
       const int t = warp == 1 ? 0 : 1;
       const uint32_t idesc_s = umma_idesc(1u, 0, 0, 128, 64);
       const uint32_t idesc_pv = umma_idesc(1u, 0, 1, 128, (uint32_t)p.n_hd);
@@ -351,15 +367,20 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
         const FwdItem im = fwd_item<kTiles>(p, it);
         const int nb = im.nblk[t], n = im.n;
-        mbar_wait(&bar_q_full, (uint32_t)(qi & 1));
+        mbar_wait_u(&bar_q_full, (uint32_t)(qi & 1));
         if (nb > 0) {
-          mbar_wait(&bar_kv_full[stage], phase);
+          mbar_wait_u(&bar_kv_full[stage], phase);
           tc_fence_after();
-          mma_over_hd(s_tmem + (blk & 1u) * 64, q_lo, kAtom128 >> 4, lo_kmajor(ring_addr + stage * stage_bytes),
-                      kAtom64 >> 4, p.ksteps, idesc_s);
-          umma_commit(&bar_s_full[t][blk & 1u]);
         }
-        if (n == 1) release(&bar_q_empty, nb > 0);
+        if (elect_one()) {
+          if (nb > 0) {
+            mma_over_hd(s_tmem + (blk & 1u) * 64, q_lo, kAtom128 >> 4, lo_kmajor(ring_addr + stage * stage_bytes),
+                        kAtom64 >> 4, p.ksteps, idesc_s);
+            umma_commit(&bar_s_full[t][blk & 1u]);
+          }
+          if (n == 1) release(&bar_q_empty, nb > 0);
+        }
+        __syncwarp();
         for (int j = 0; j < n; ++j) {
           int ns = stage + 1;
           uint32_t nph = phase;
@@ -369,25 +390,40 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
           }
           if (j + 1 < n) {   // the next block's scores first: the softmax warps never wait for the P V product
             if (j + 1 < nb) {
-              mbar_wait(&bar_kv_full[ns], nph);
+              mbar_wait_u(&bar_kv_full[ns], nph);
               tc_fence_after();
-              mma_over_hd(s_tmem + ((blk + 1u) & 1u) * 64, q_lo, kAtom128 >> 4,
-                          lo_kmajor(ring_addr + ns * stage_bytes), kAtom64 >> 4, p.ksteps, idesc_s);
-              umma_commit(&bar_s_full[t][(blk + 1u) & 1u]);
             }
-            if (j + 2 == n) release(&bar_q_empty, nb > 0);   // every S product of this item has been issued
+            if (elect_one()) {
+              if (j + 1 < nb) {
+                mma_over_hd(s_tmem + ((blk + 1u) & 1u) * 64, q_lo, kAtom128 >> 4,
+                            lo_kmajor(ring_addr + ns * stage_bytes), kAtom64 >> 4, p.ksteps, idesc_s);
+                umma_commit(&bar_s_full[t][(blk + 1u) & 1u]);
+              }
+              if (j + 2 == n) release(&bar_q_empty, nb > 0);   // every S product of this item has been issued
+            }
+            __syncwarp();
           }
           if (j < nb) {
-            mbar_wait(&bar_p_full[t], blk & 1u);
+            if (t == 0) FA_TRACE(16, blk);
+            mbar_wait_u(&bar_p_full[t], blk & 1u);
             tc_fence_after();
-            mma_over_rows64(o_tmem, p_lo, lo_mn64(ring_addr + stage * stage_bytes + p.katoms * kAtom64), idesc_pv,
-                            j > 0);
-            umma_commit(&bar_pv_done[t]);
-            ++blk;
+            if (t == 0) FA_TRACE(17, blk);
           } else {
-            mbar_wait(&bar_kv_full[stage], phase);   // a stage this tile does not use: still no running ahead of the ring
+            mbar_wait_u(&bar_kv_full[stage], phase);   // a stage this tile does not use: still no running ahead of the ring
           }
-          release(&bar_kv_empty[stage], j < nb);
+          if (elect_one()) {
+            if (j < nb) {
+              mma_over_rows64(o_tmem, p_lo, lo_mn64(ring_addr + stage * stage_bytes + p.katoms * kAtom64), idesc_pv,
+                              j > 0);
+              umma_commit(&bar_pv_done[t]);
+            }
+            release(&bar_kv_empty[stage], j < nb);
+          }
+          __syncwarp();
+          if (j < nb) {
+            if (t == 0) FA_TRACE(18, blk);
+            ++blk;
+          }
           stage = ns;
           phase = nph;
         }
@@ -422,12 +458,15 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
         }
         const uint32_t bits0 = row_bits32(p, k0c, q, bq, j * 64);
         const uint32_t bits1 = row_bits32(p, k1c, q, bq, j * 64 + 32);
+        if (warp == 4 && lane == 0) FA_TRACE(19, cnt);
         mbar_wait(&bar_s_full[t][buf], (cnt >> 1) & 1u);
         tc_fence_after();
+        if (warp == 4 && lane == 0) FA_TRACE(20, cnt);
         uint32_t s0[32], s1[32];
         tmem_ld_32x32(lane_base + t * 128 + buf * 64, s0);
         tmem_ld_32x32(lane_base + t * 128 + buf * 64 + 32, s1);
         tmem_ld_wait();
+        if (warp == 4 && lane == 0) FA_TRACE(21, cnt);
         float mx = -INFINITY;
         if (__all_sync(0xffffffffu, (bits0 & bits1) == 0xffffffffu)) {
 #pragma unroll
@@ -465,6 +504,7 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
           }
         }
         const float m_use = m_ref == -INFINITY ? 0.0f : m_ref;
+        if (warp == 4 && lane == 0) FA_TRACE(22, cnt);
         uint32_t pk[32];
         float sum0 = 0.0f, sum1 = 0.0f;
 #pragma unroll
@@ -479,23 +519,29 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
           pk[16 + i] = pack2(c0, c1);
         }
         l += sum0 + sum1;
+        if (warp == 4 && lane == 0) FA_TRACE(23, cnt);
         if (cnt > 0) mbar_wait(&bar_pv_done[t], (cnt - 1u) & 1u);   // the P buffer's previous reader has retired
+        if (warp == 4 && lane == 0) FA_TRACE(24, cnt);
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           *reinterpret_cast<uint4*>(prow + ((c ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         fence_proxy_async_smem();
         tc_fence_before();
         warp_arrive(&bar_p_full[t], lane);
+        if (warp == 4 && lane == 0) FA_TRACE(25, cnt);
         ++cnt;
       }
       // ---- epilogue: O / l -> bf16 rows, log-sum-exp
+      if (warp == 4 && lane == 0) FA_TRACE(26, cnt - 1u);
       mbar_wait(&bar_pv_done[t], (cnt - 1u) & 1u);
       tc_fence_after();
+      if (warp == 4 && lane == 0) FA_TRACE(27, cnt - 1u);
       const float inv = l > 0.0f ? 1.0f / l : 0.0f;
       bf16* orow = p.out + (long long)b * p.o_sb + (long long)q * p.o_ld + (long long)h * p.o_sh;
       store_acc_rows(o_tmem, orow, row_ok, 0, 1, p.o_chunks, p.hd, inv);
       if (row_ok && p.lse != nullptr)
         p.lse[((size_t)b * p.H + h) * p.S + q] = l > 0.0f ? m_ref + log2f(l) : INFINITY;
+      if (warp == 4 && lane == 0) FA_TRACE(28, cnt - 1u);
       tc_fence_before();
     }
   }
@@ -556,28 +602,34 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
   const int BH = p.B * p.H;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // TMA producer: whole warp, one elected lane issues
       int stage = 0, qi = 0;
       uint32_t phase = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
         const int pr = it / BH, bh = it - pr * BH;
         const int b = bh / p.H, h = bh - b * p.H, kvh = h / p.G, tile = p.m_tiles - 1 - pr;
         const int n = visible_blocks(p, tile);
-        mbar_wait(&bar_qdo_empty, (uint32_t)(qi & 1) ^ 1u);
-        mbar_expect_tx(&bar_qdo_full, (uint32_t)(2 * p.katoms * kAtom128));
-        for (int a = 0; a < p.katoms; ++a) {
-          tma_load_4d(sQ + a * kAtom128, &p.tmQ, &bar_qdo_full, a * 64, tile * 128, h, b);
-          tma_load_4d(sDO + a * kAtom128, &p.tmDO, &bar_qdo_full, a * 64, tile * 128, h, b);
-        }
-        for (int j = 0; j < n; ++j) {
-          mbar_wait(&bar_kv_empty[stage], phase ^ 1u);
-          mbar_expect_tx(&bar_kv_full[stage], (uint32_t)stage_bytes);
-          uint8_t* sK = sRing + stage * stage_bytes;
-          uint8_t* sV = sK + p.katoms * kAtom64;
+        mbar_wait_u(&bar_qdo_empty, (uint32_t)(qi & 1) ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&bar_qdo_full, (uint32_t)(2 * p.katoms * kAtom128));
           for (int a = 0; a < p.katoms; ++a) {
-            tma_load_4d(sK + a * kAtom64, &p.tmK, &bar_kv_full[stage], a * 64, j * 64, kvh, b);
-            tma_load_4d(sV + a * kAtom64, &p.tmV, &bar_kv_full[stage], a * 64, j * 64, kvh, b);
+            tma_load_4d(sQ + a * kAtom128, &p.tmQ, &bar_qdo_full, a * 64, tile * 128, h, b);
+            tma_load_4d(sDO + a * kAtom128, &p.tmDO, &bar_qdo_full, a * 64, tile * 128, h, b);
           }
+        }
+        __syncwarp();
+        for (int j = 0; j < n; ++j) {
+          mbar_wait_u(&bar_kv_empty[stage], phase ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(&bar_kv_full[stage], (uint32_t)stage_bytes);
+            uint8_t* sK = sRing + stage * stage_bytes;
+            uint8_t* sV = sK + p.katoms * kAtom64;
+            for (int a = 0; a < p.katoms; ++a) {
+              tma_load_4d(sK + a * kAtom64, &p.tmK, &bar_kv_full[stage], a * 64, j * 64, kvh, b);
+              tma_load_4d(sV + a * kAtom64, &p.tmV, &bar_kv_full[stage], a * 64, j * 64, kvh, b);
+            }
+          }
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
@@ -587,7 +639,8 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
     }
   } else if (warp == 1) {
     // issuer A: S = Q K^T and dP = dO V^T of block c into buffer c & 1, as far ahead as the two buffers allow
-    if (lane == 0) {
+    // (whole warp in the loop, one elected lane issues: see ptx.cuh elect_one)
+    {
       const uint32_t idesc_s = umma_idesc(1u, 0, 0, 128, 64);
       const uint32_t q_lo = lo_kmajor(smem_u32(sQ)), do_lo = lo_kmajor(smem_u32(sDO));
       const uint32_t ring_addr = smem_u32(sRing);
@@ -596,18 +649,25 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
       uint32_t phase = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
         const int n = visible_blocks(p, p.m_tiles - 1 - it / BH);
-        mbar_wait(&bar_qdo_full, (uint32_t)(qi & 1));
+        mbar_wait_u(&bar_qdo_full, (uint32_t)(qi & 1));
         for (int j = 0; j < n; ++j) {
           const uint32_t buf = cnt & 1u;
-          if (cnt >= 2) mbar_wait(&bar_sdp_free[buf], ((cnt >> 1) - 1u) & 1u);   // the buffer's previous block was read
-          mbar_wait(&bar_kv_full[stage], phase);
+          FA_TRACE(0, cnt);
+          if (cnt >= 2) mbar_wait_u(&bar_sdp_free[buf], ((cnt >> 1) - 1u) & 1u);   // the buffer's previous block was read
+          FA_TRACE(1, cnt);
+          mbar_wait_u(&bar_kv_full[stage], phase);
           tc_fence_after();
-          const uint32_t k_lo = lo_kmajor(ring_addr + stage * stage_bytes);
-          mma_over_hd(tmem + buf * 64, q_lo, kAtom128 >> 4, k_lo, kAtom64 >> 4, p.ksteps, idesc_s);
-          mma_over_hd(tmem + 128 + buf * 64, do_lo, kAtom128 >> 4, k_lo + ((p.katoms * kAtom64) >> 4), kAtom64 >> 4,
-                      p.ksteps, idesc_s);
-          umma_commit(&bar_sdp_full[buf]);
-          if (j + 1 == n) umma_commit(&bar_qdo_empty);
+          FA_TRACE(2, cnt);
+          if (elect_one()) {
+            const uint32_t k_lo = lo_kmajor(ring_addr + stage * stage_bytes);
+            mma_over_hd(tmem + buf * 64, q_lo, kAtom128 >> 4, k_lo, kAtom64 >> 4, p.ksteps, idesc_s);
+            mma_over_hd(tmem + 128 + buf * 64, do_lo, kAtom128 >> 4, k_lo + ((p.katoms * kAtom64) >> 4), kAtom64 >> 4,
+                        p.ksteps, idesc_s);
+            umma_commit(&bar_sdp_full[buf]);
+            if (j + 1 == n) umma_commit(&bar_qdo_empty);
+          }
+          __syncwarp();
+          FA_TRACE(3, cnt);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
@@ -618,7 +678,7 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
     }
   } else if (warp == 3) {
     // issuer B: dQ += dS K as soon as the softmax warps have written dS
-    if (lane == 0) {
+    {
       const uint32_t idesc_dq = umma_idesc(1u, 0, 1, 128, (uint32_t)p.n_hd);
       const uint32_t ds_lo = lo_kmajor(smem_u32(sDS));
       const uint32_t ring_addr = smem_u32(sRing);
@@ -627,15 +687,20 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
         const int n = visible_blocks(p, p.m_tiles - 1 - it / BH);
         for (int j = 0; j < n; ++j) {
-          mbar_wait(&bar_ds_full, cnt & 1u);
+          mbar_wait_u(&bar_ds_full, cnt & 1u);
           tc_fence_after();
-          mma_over_rows64(tmem + 256, ds_lo, lo_mn64(ring_addr + stage * stage_bytes), idesc_dq, j > 0);
-          umma_commit(&bar_ds_empty);
-          umma_commit(&bar_kv_empty[stage]);
+          FA_TRACE(4, cnt);
+          if (elect_one()) {
+            mma_over_rows64(tmem + 256, ds_lo, lo_mn64(ring_addr + stage * stage_bytes), idesc_dq, j > 0);
+            umma_commit(&bar_ds_empty);
+            umma_commit(&bar_kv_empty[stage]);
+            if (j + 1 == n) umma_commit(&bar_dq_full);
+          }
+          __syncwarp();
+          FA_TRACE(5, cnt);
           if (++stage == stages) stage = 0;
           ++cnt;
         }
-        umma_commit(&bar_dq_full);
       }
     }
   } else if (warp >= 4) {
@@ -663,14 +728,17 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
         const KeyInfo kc = kn;
         if (j + 1 < n) kn = load_key(p, b, (j + 1) * 64 + half * 32 + lane);
         const uint32_t bits = row_bits32(p, kc, q, bq, j * 64 + half * 32);
+        if (warp == 4 && lane == 0) FA_TRACE(6, cnt);
         mbar_wait(&bar_sdp_full[buf], (cnt >> 1) & 1u);
         tc_fence_after();
+        if (warp == 4 && lane == 0) FA_TRACE(7, cnt);
         uint32_t s[32], dp[32];
         tmem_ld_32x32(lane_base + buf * 64 + half * 32, s);
         tmem_ld_32x32(lane_base + 128 + buf * 64 + half * 32, dp);
         tmem_ld_wait();
         tc_fence_before();
         warp_arrive(&bar_sdp_free[buf], lane);
+        if (warp == 4 && lane == 0) FA_TRACE(8, cnt);
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -683,19 +751,25 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
           }
           pk[i] = pack2(v[0], v[1]);
         }
+        if (warp == 4 && lane == 0) FA_TRACE(9, cnt);
         if (cnt > 0) mbar_wait(&bar_ds_empty, (cnt - 1u) & 1u);
+        if (warp == 4 && lane == 0) FA_TRACE(10, cnt);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           *reinterpret_cast<uint4*>(dsrow + (((half * 4 + c) ^ sw) << 4)) =
               make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         fence_proxy_async_smem();
         warp_arrive(&bar_ds_full, lane);
+        if (warp == 4 && lane == 0) FA_TRACE(11, cnt);
         ++cnt;
       }
+      if (warp == 4 && lane == 0) FA_TRACE(12, cnt - 1u);
       mbar_wait(&bar_dq_full, (uint32_t)(qi & 1));
       tc_fence_after();
+      if (warp == 4 && lane == 0) FA_TRACE(13, cnt - 1u);
       bf16* drow = p.dq + (long long)b * p.g_sb + (long long)q * p.g_ld + (long long)h * p.gq_sh;
       store_acc_rows(lane_base + 256, drow, row_ok, half, 2, p.o_chunks, p.hd, 1.0f);
+      if (warp == 4 && lane == 0) FA_TRACE(14, cnt - 1u);
       tc_fence_before();
       // all eight warps have left the dQ accumulator before issuer B may overwrite it: their next arrival on ds_full
       // (block 0 of the next item) comes after this point in program order
@@ -778,29 +852,35 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
   const uint32_t tmem = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // TMA producer: whole warp, one elected lane issues
       int stage = 0, qi = 0;
       uint32_t phase = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qi) {
         const DkvItem im = dkv_item(p, it);
-        mbar_wait(&bar_kv_empty, (uint32_t)(qi & 1) ^ 1u);
+        mbar_wait_u(&bar_kv_empty, (uint32_t)(qi & 1) ^ 1u);
         const bool need_v = im.mode != 1;
-        mbar_expect_tx(&bar_kv_full, (uint32_t)((need_v ? 2 : 1) * p.katoms * kAtom128));
-        for (int a = 0; a < p.katoms; ++a) {
-          tma_load_4d(sK + a * kAtom128, &p.tmK, &bar_kv_full, a * 64, im.jt * 128, im.kvh, im.b);
-          if (need_v) tma_load_4d(sV + a * kAtom128, &p.tmV, &bar_kv_full, a * 64, im.jt * 128, im.kvh, im.b);
+        if (elect_one()) {
+          mbar_expect_tx(&bar_kv_full, (uint32_t)((need_v ? 2 : 1) * p.katoms * kAtom128));
+          for (int a = 0; a < p.katoms; ++a) {
+            tma_load_4d(sK + a * kAtom128, &p.tmK, &bar_kv_full, a * 64, im.jt * 128, im.kvh, im.b);
+            if (need_v) tma_load_4d(sV + a * kAtom128, &p.tmV, &bar_kv_full, a * 64, im.jt * 128, im.kvh, im.b);
+          }
         }
+        __syncwarp();
         for (int hh = 0; hh < p.G; ++hh) {
           const int h = im.kvh * p.G + hh;
           for (int ib = im.ib0; ib < p.n_qblk; ++ib) {
-            mbar_wait(&bar_ring_empty[stage], phase ^ 1u);
-            mbar_expect_tx(&bar_ring_full[stage], (uint32_t)stage_bytes);
-            uint8_t* sQb = sRing + stage * stage_bytes;
-            uint8_t* sDOb = sQb + p.katoms * kAtom64;
-            for (int a = 0; a < p.katoms; ++a) {
-              tma_load_4d(sQb + a * kAtom64, &p.tmQ, &bar_ring_full[stage], a * 64, ib * 64, h, im.b);
-              tma_load_4d(sDOb + a * kAtom64, &p.tmDO, &bar_ring_full[stage], a * 64, ib * 64, h, im.b);
+            mbar_wait_u(&bar_ring_empty[stage], phase ^ 1u);
+            if (elect_one()) {
+              mbar_expect_tx(&bar_ring_full[stage], (uint32_t)stage_bytes);
+              uint8_t* sQb = sRing + stage * stage_bytes;
+              uint8_t* sDOb = sQb + p.katoms * kAtom64;
+              for (int a = 0; a < p.katoms; ++a) {
+                tma_load_4d(sQb + a * kAtom64, &p.tmQ, &bar_ring_full[stage], a * 64, ib * 64, h, im.b);
+                tma_load_4d(sDOb + a * kAtom64, &p.tmDO, &bar_ring_full[stage], a * 64, ib * 64, h, im.b);
+              }
             }
+            __syncwarp();
             if (++stage == stages) {
               stage = 0;
               phase ^= 1u;
@@ -810,8 +890,8 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // issuer A: S^T = K Q^T and dP^T = V dO^T of step c into buffer c & 1
-    if (lane == 0) {
+    // issuer A: S^T = K Q^T and dP^T = V dO^T of step c into buffer c & 1 (whole warp in the loop, elected lane issues)
+    {
       const uint32_t idesc_st = umma_idesc(1u, 0, 0, 128, 64);
       const uint32_t k_lo = lo_kmajor(smem_u32(sK)), v_lo = lo_kmajor(smem_u32(sV));
       const uint32_t ring_addr = smem_u32(sRing);
@@ -822,19 +902,26 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
         const DkvItem im = dkv_item(p, it);
         const int n = im.nsteps;
         const bool do_dk = im.mode != 1;
-        mbar_wait(&bar_kv_full, (uint32_t)(qi & 1));
+        mbar_wait_u(&bar_kv_full, (uint32_t)(qi & 1));
         for (int sidx = 0; sidx < n; ++sidx) {
           const uint32_t buf = cnt & 1u;
-          if (cnt >= 2) mbar_wait(&bar_sdp_free[buf], ((cnt >> 1) - 1u) & 1u);
-          mbar_wait(&bar_ring_full[stage], phase);
+          FA_TRACE(32, cnt);
+          if (cnt >= 2) mbar_wait_u(&bar_sdp_free[buf], ((cnt >> 1) - 1u) & 1u);
+          FA_TRACE(33, cnt);
+          mbar_wait_u(&bar_ring_full[stage], phase);
           tc_fence_after();
-          const uint32_t qb_lo = lo_kmajor(ring_addr + stage * stage_bytes);
-          mma_over_hd(tmem + buf * 64, k_lo, kAtom128 >> 4, qb_lo, kAtom64 >> 4, p.ksteps, idesc_st);
-          if (do_dk)
-            mma_over_hd(tmem + 128 + buf * 64, v_lo, kAtom128 >> 4, qb_lo + ((p.katoms * kAtom64) >> 4), kAtom64 >> 4,
-                        p.ksteps, idesc_st);
-          umma_commit(&bar_sdp_full[buf]);
-          if (sidx + 1 == n) umma_commit(&bar_kv_empty);
+          FA_TRACE(34, cnt);
+          if (elect_one()) {
+            const uint32_t qb_lo = lo_kmajor(ring_addr + stage * stage_bytes);
+            mma_over_hd(tmem + buf * 64, k_lo, kAtom128 >> 4, qb_lo, kAtom64 >> 4, p.ksteps, idesc_st);
+            if (do_dk)
+              mma_over_hd(tmem + 128 + buf * 64, v_lo, kAtom128 >> 4, qb_lo + ((p.katoms * kAtom64) >> 4), kAtom64 >> 4,
+                          p.ksteps, idesc_st);
+            umma_commit(&bar_sdp_full[buf]);
+            if (sidx + 1 == n) umma_commit(&bar_kv_empty);
+          }
+          __syncwarp();
+          FA_TRACE(35, cnt);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
@@ -845,7 +932,7 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
     }
   } else if (warp == 3) {
     // issuer B: the accumulating products, as soon as P^T / dS^T of a step are in smem
-    if (lane == 0) {
+    {
       const uint32_t idesc_acc = umma_idesc(1u, 0, 1, 128, (uint32_t)p.n_hd);
       const uint32_t pt_lo = lo_kmajor(smem_u32(sPT)), dst_lo = lo_kmajor(smem_u32(sDST));
       const uint32_t ring_addr = smem_u32(sRing);
@@ -856,17 +943,22 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
         const bool do_dv = im.mode != 2, do_dk = im.mode != 1;
         const uint32_t dv_tmem = tmem + 256, dk_tmem = tmem + (im.mode == 0 ? 384u : 256u);
         for (int sidx = 0; sidx < im.nsteps; ++sidx) {
-          mbar_wait(&bar_pds_full, cnt & 1u);
+          mbar_wait_u(&bar_pds_full, cnt & 1u);
           tc_fence_after();
-          const uint32_t qb_addr = ring_addr + stage * stage_bytes;
-          if (do_dv) mma_over_rows64(dv_tmem, pt_lo, lo_mn64(qb_addr + p.katoms * kAtom64), idesc_acc, sidx > 0);
-          if (do_dk) mma_over_rows64(dk_tmem, dst_lo, lo_mn64(qb_addr), idesc_acc, sidx > 0);
-          umma_commit(&bar_pds_empty);
-          umma_commit(&bar_ring_empty[stage]);
+          FA_TRACE(36, cnt);
+          if (elect_one()) {
+            const uint32_t qb_addr = ring_addr + stage * stage_bytes;
+            if (do_dv) mma_over_rows64(dv_tmem, pt_lo, lo_mn64(qb_addr + p.katoms * kAtom64), idesc_acc, sidx > 0);
+            if (do_dk) mma_over_rows64(dk_tmem, dst_lo, lo_mn64(qb_addr), idesc_acc, sidx > 0);
+            umma_commit(&bar_pds_empty);
+            umma_commit(&bar_ring_empty[stage]);
+            if (sidx + 1 == im.nsteps) umma_commit(&bar_acc_full);
+          }
+          __syncwarp();
+          FA_TRACE(37, cnt);
           if (++stage == stages) stage = 0;
           ++cnt;
         }
-        umma_commit(&bar_acc_full);
       }
     }
   } else if (warp >= 4) {
@@ -925,14 +1017,17 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
               if (bk <= __float_as_int(st[2][c])) w2 |= 1u << c;
             bits &= w2;
           }
+          if (warp == 4 && lane == 0) FA_TRACE(38, cnt);
           mbar_wait(&bar_sdp_full[buf], (cnt >> 1) & 1u);
           tc_fence_after();
+          if (warp == 4 && lane == 0) FA_TRACE(39, cnt);
           uint32_t s[32], dp[32];
           tmem_ld_32x32(lane_base + buf * 64 + half * 32, s);
           if (do_dk) tmem_ld_32x32(lane_base + 128 + buf * 64 + half * 32, dp);
           tmem_ld_wait();
           tc_fence_before();
           warp_arrive(&bar_sdp_free[buf], lane);
+          if (warp == 4 && lane == 0) FA_TRACE(40, cnt);
           uint32_t pp[16], pd[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -946,7 +1041,9 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
             pp[i] = pack2(pv[0], pv[1]);
             pd[i] = pack2(dv[0], dv[1]);
           }
+          if (warp == 4 && lane == 0) FA_TRACE(41, cnt);
           if (cnt > 0) mbar_wait(&bar_pds_empty, (cnt - 1u) & 1u);
+          if (warp == 4 && lane == 0) FA_TRACE(42, cnt);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int off = ((half * 4 + c) ^ sw) << 4;
@@ -955,6 +1052,7 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
           }
           fence_proxy_async_smem();
           warp_arrive(&bar_pds_full, lane);
+          if (warp == 4 && lane == 0) FA_TRACE(43, cnt);
           ++cnt;
         }
       }
@@ -1048,6 +1146,8 @@ static int encode_rows(CUtensorMap* m, const void* ptr, uint64_t hd, uint64_t S,
 
 constexpr int kSmemBudget = 227 * 1024 - 4096;   // dynamic bytes available next to the static barriers / stats
 
+static long long* g_fa_trace = nullptr;
+
 static int fill_common(FaParams& kp, int64_t B, int64_t H, int64_t KVH, int64_t S, int64_t hd, float scale, int causal,
                        const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k) {
   B200_CHECK(hd % 8 == 0 && hd >= 16 && hd <= 256, "flash_attn: head_dim=%lld unsupported (multiple of 8, <= 256)",
@@ -1075,6 +1175,7 @@ static int fill_common(FaParams& kp, int64_t B, int64_t H, int64_t KVH, int64_t 
   kp.bid_q = bid_q;
   kp.bid_k = bid_k;
   kp.n_modes = 1;
+  kp.trace = g_fa_trace;
   return 0;
 }
 
@@ -1087,6 +1188,11 @@ static int set_smem(K kernel, int bytes) {
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_flash_attn_set_trace(void* buf) {
+  b200::g_fa_trace = reinterpret_cast<long long*>(buf);
+  return 0;
+}
 
 extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B,
                                    int64_t H, int64_t KVH, int64_t S, int64_t head_dim, int64_t qkv_ld,

@@ -213,28 +213,33 @@ __device__ __forceinline__ void mma_issue_loop(const GemmKParams& p, uint8_t* sm
   uint32_t phase = 0;
   int acc = 0;
   uint32_t acc_phase = 0;
+  // The whole warp runs this loop (warp-uniform control flow, waits spin inside one asm block); one elected lane
+  // issues.  Under `if (lane == 0)` ptxas wrapped every UTCHMMA / UTCBAR in an elect-and-loop sequence.
   for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
-    mbar_wait_fast(&tempty_bar[acc], acc_phase ^ 1);
+    mbar_wait_u(&tempty_bar[acc], acc_phase ^ 1);
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + acc * kBlockN;
     uint32_t accum = 0;
     for (int kb = 0; kb < k_blocks; ++kb) {
-      mbar_wait_fast(&full_bar[stage], phase);
+      mbar_wait_u(&full_bar[stage], phase);
       tc_fence_after();
-      const uint32_t a_lo = a_lo0 | (smem16 + stage * (Cfg::kStageBytes >> 4));
-      const uint32_t b_lo = b_lo0 | (smem16 + stage * (Cfg::kStageBytes >> 4) + (kStageABytes >> 4));
-      umma_issue<kCtas, kTF32>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accum);
-      umma_issue<kCtas, kTF32>(d_tmem, a_lo + a_step, a_hi, b_lo + b_step, b_hi, idesc, 1u);
-      umma_issue<kCtas, kTF32>(d_tmem, a_lo + 2 * a_step, a_hi, b_lo + 2 * b_step, b_hi, idesc, 1u);
-      umma_issue<kCtas, kTF32>(d_tmem, a_lo + 3 * a_step, a_hi, b_lo + 3 * b_step, b_hi, idesc, 1u);
+      if (elect_one()) {
+        const uint32_t a_lo = a_lo0 | (smem16 + stage * (Cfg::kStageBytes >> 4));
+        const uint32_t b_lo = b_lo0 | (smem16 + stage * (Cfg::kStageBytes >> 4) + (kStageABytes >> 4));
+        umma_issue<kCtas, kTF32>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accum);
+        umma_issue<kCtas, kTF32>(d_tmem, a_lo + a_step, a_hi, b_lo + b_step, b_hi, idesc, 1u);
+        umma_issue<kCtas, kTF32>(d_tmem, a_lo + 2 * a_step, a_hi, b_lo + 2 * b_step, b_hi, idesc, 1u);
+        umma_issue<kCtas, kTF32>(d_tmem, a_lo + 3 * a_step, a_hi, b_lo + 3 * b_step, b_hi, idesc, 1u);
+        umma_commit_n<kCtas>(&empty_bar[stage]);  // smem slot is free (in both CTAs of a pair) once these retire
+        if (kb + 1 == k_blocks) umma_commit_n<kCtas>(&tfull_bar[acc]);  // accumulator complete -> epilogue (of both CTAs)
+      }
+      __syncwarp();
       accum = 1u;
-      umma_commit_n<kCtas>(&empty_bar[stage]);  // smem slot is free (in both CTAs of a pair) once these retire
       if (++stage == Cfg::kStages) {
         stage = 0;
         phase ^= 1;
       }
     }
-    umma_commit_n<kCtas>(&tfull_bar[acc]);  // accumulator complete -> epilogue (of both CTAs)
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;
   }
@@ -292,8 +297,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
@@ -307,7 +312,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         const int a_atom0 = tc.m0 / p.atom_elems, b_atom0 = bn0 / p.atom_elems;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           const int k0 = kin * p.bk_elems;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_u(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kStageABytes;
           const int a_c2 = a_zbase + seg * p.a_seg;
@@ -352,6 +358,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                             tc.zh);
             }
           }
+          }
+          __syncwarp();
           if (++kin == p.kbps) {
             kin = 0;
             ++seg;
@@ -365,7 +373,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0 && leader) {
+    if (leader) {
       if (p.ab_fp32)
         mma_issue_loop<kBlockN, kCtas, true>(p, smem, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base, tile0,
                                              tile_step);

@@ -51,6 +51,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// The same wait with the spin loop INSIDE one asm block: the compiler sees straight-line code, so a warp that waits as a
+// whole keeps warp-uniform control flow (and with it uniform-register operands for the tcgen05 / TMA instructions that
+// follow).  A dead-locked protocol traps after B200_SPIN_LIMIT polls instead of hanging the device.
+__device__ __forceinline__ void mbar_wait_u(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p, q;\n.reg .u32 n;\nmov.u32 n, 0;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "add.u32 n, n, 1;\nsetp.gt.u32 q, n, %2;\n@q trap;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "n"(B200_SPIN_LIMIT)
+      : "memory");
+}
+// One lane of a converged warp (deterministic for a given mask).  Code under `if (elect_one())` inside warp-uniform
+// control flow compiles to back-to-back UTCHMMA / UTMALDG; the same code under `if (lane == 0)` makes ptxas wrap every
+// such instruction in an elect-and-loop sequence (measured: ~95 instead of ~10 cycles per issued MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 // -------------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -318,6 +318,7 @@ class SpliceFn(torch.autograd.Function):
     def backward(ctx, dout):
         (src,) = ctx.saved_tensors
         d_feats = torch.zeros(ctx.fshape, device=dout.device, dtype=dout.dtype)
+        ctx.store.begin_sparse_write(ctx.g_table)
         ops.splice_scatter(src, dout.contiguous(), ctx.g_table, d_feats)
         return d_feats, None, None, None, None
 

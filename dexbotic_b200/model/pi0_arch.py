@@ -458,6 +458,7 @@ class PrefixEmbedFn(torch.autograd.Function):
         if g_table is not None:
             d_text = torch.empty((B * L, D), device=dout.device, dtype=dout.dtype)
             ops.copy3d_(dout, d_text, B, L, D, Sp * D, D, L * D, D, alpha=math.sqrt(D), src_off=n_cam * P * D)
+            store.begin_sparse_write(g_table)
             ops.splice_scatter(ids32, d_text, g_table, None)
         return d_feats, None, None, None, None, None, None, None, None
 

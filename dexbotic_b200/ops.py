@@ -526,6 +526,21 @@ def adamw_(p32, g, m, v, shadow_bf16, lr, beta1, beta2, eps, wd, step: int, clip
                                       int(step), _p(clip), _dt(g), _stream()), "adamw")
 
 
+def adamw_hyper_(out8: torch.Tensor, lr, beta1, beta2, eps, wd, step: int) -> None:
+    """Fill a HOST float32[8] block with the seven scalars b200_adamw derives from its doubles (step <= 0: identity)."""
+    assert out8.device.type == "cpu" and out8.dtype == torch.float32 and out8.numel() >= 8 and out8.is_contiguous()
+    _lib.check(_lib.load().b200_adamw_hyper(float(lr), float(beta1), float(beta2), float(eps), float(wd), int(step),
+                                            out8.data_ptr()), "adamw_hyper")
+
+
+def adamw_dev_(p32, g, m, v, shadow_bf16, hyper8: torch.Tensor, clip=None):
+    """adamw_ with its scalars read from the device block `hyper8` (graph-replayable optimizer, graph.py)."""
+    _cuda(p32, g, m, v, shadow_bf16, clip, hyper8)
+    assert p32.dtype == m.dtype == v.dtype == hyper8.dtype == torch.float32 and hyper8.numel() >= 8
+    _lib.check(_lib.load().b200_adamw_dev(p32.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(shadow_bf16),
+                                          p32.numel(), hyper8.data_ptr(), _p(clip), _dt(g), _stream()), "adamw_dev")
+
+
 def cast_(src, dst):
     _cuda(src, dst)
     assert src.numel() == dst.numel() and src.is_contiguous() and dst.is_contiguous()

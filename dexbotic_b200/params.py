@@ -256,10 +256,18 @@ class ParamStore:
         return zeroed
 
     def mark_sparse_grad(self, name: str) -> None:
-        """Gradient rows written by scatter (embedding table): needs a real memset every step."""
+        """Gradient rows written by scatter (embedding table): the writer calls begin_sparse_write() first."""
         s = self.slots[name]
         assert s.region == "A"
         self._always_zero.append((s.offset, s.offset + s.spec.numel))
+
+    def begin_sparse_write(self, g: Optional[torch.Tensor]) -> None:
+        """Rows of a scatter-written gradient that receive nothing must read as zero: the first writer of a step memsets
+        the tensor.  This happens in backward — not in zero_grad(): with `async_optimizer` the previous step's AdamW of
+        the table may still be reading this gradient on the side stream when zero_grad() runs, whereas the forward has
+        waited for that chunk (wait_chunk) long before the first backward kernel."""
+        if g is not None and self.first_write(g):
+            g.zero_()
 
     # ---------------------------------------------------------------- optimizer / forward overlap
     def set_param_chunks(self, bounds: list) -> None:
@@ -280,10 +288,6 @@ class ParamStore:
         self._written.clear()
         self._written_ranges.clear()
         self.grad_b.zero_()
-        for a, b in self._always_zero:
-            self.grad_a[a:b].zero_()
-            self._written.add(self.grad_a[a:].data_ptr())
-            self._written_ranges.append((a, b))
         if self.zero_grad_hook is not None:
             self.zero_grad_hook()
 

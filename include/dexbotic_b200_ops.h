@@ -88,6 +88,10 @@ int b200_flash_attn_fwd(const void* q, const void* k, const void* v, void* out, 
                         int64_t KVH, int64_t S, int64_t head_dim, int64_t qkv_ld, int64_t qkv_s_head,
                         int64_t qkv_s_batch, int64_t o_ld, int64_t o_s_head, int64_t o_s_batch, float scale, int causal,
                         const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k, void* stream);
+/* Debugging hook (tools/trace_flash.py): when buf != NULL, CTA 0 of the flash kernels writes clock64() stamps of its
+ * pipeline events into buf (int64 [64 slots][64 steps]); NULL (the default) switches it off. */
+int b200_flash_attn_set_trace(void* buf);
+
 /* Its backward: recomputes P from lse; dq / dk / dv use the strides (g_ld, g_s_head, g_s_batch) (the packed dqkv
  * buffer), dout the strides of out.  dK / dV are reduced over the query heads of a GQA group inside the kernel's
  * TMEM accumulators (no atomics: deterministic).  delta: fp32 workspace [B, H, S]. */
@@ -113,6 +117,14 @@ int b200_mse_bwd(const void* a, const void* b, int64_t n, const float* gscale, v
  * doubles: torch evaluates 1-beta, the bias corrections and lr/bc1 in Python doubles and rounds to fp32 once. */
 int b200_adamw(float* p, const void* g, float* m, float* v, void* shadow_bf16, int64_t n, double lr, double beta1,
                double beta2, double eps, double weight_decay, int64_t step, const float* clip, int g_dtype, void* stream);
+
+/* The same update with its seven scalars read from device memory (hyper8: b2, 1-b1, 1-b2, eps, 1-lr*wd, lr/bc1,
+ * sqrt(bc2), pad): a CUDA graph that contains the optimizer is replayed with new learning rates and step counts by
+ * rewriting that block.  b200_adamw_hyper fills a host block with exactly the values b200_adamw would use (step <= 0:
+ * the identity update). */
+int b200_adamw_hyper(double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step, float* out8);
+int b200_adamw_dev(float* p, const void* g, float* m, float* v, void* shadow_bf16, int64_t n, const float* hyper8,
+                   const float* clip, int g_dtype, void* stream);
 
 int b200_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
 int b200_add(const void* a, const void* b, void* y, int64_t n, int dtype, void* stream);

@@ -372,9 +372,16 @@ def make_oft_diffusion_tiny(seed: int = 8643):
         # inference: the reference draws its own start noise from the global RNG (oft_arch.py:226-229)
         model.eval()
         norms = dict(min=[-1.0] * 7, max=[1.0] * 7)
+        traj = []                                   # (timestep token, x_t fed to the model, predicted noise) per DDIM step
+        hook = model.register_forward_hook(
+            lambda m, a, kw, out: traj.append((kw["noisy_dict"]["diffusion_timestep_embeddings"].clone(),
+                                               kw["noisy_dict"]["noisy_actions"].clone(), out.logits.clone())),
+            with_kwargs=True)
         torch.manual_seed(seed + 2)
         ref_actions = model.inference_action(ids[:1], images[:1], dict(action_norms=norms, num_ddim_steps=5,
                                                                        states=states[:1] if use_proprio else None))
+        hook.remove()
+        assert len(traj) == 5
         torch.manual_seed(seed + 2)
         start = torch.randn(1, 8, 7, dtype=images.dtype)
         ora_actions = vla_oracle.oft_diffusion_inference(sd, cfg, ids[:1], images[:1], start, 5,
@@ -387,7 +394,8 @@ def make_oft_diffusion_tiny(seed: int = 8643):
                                                states=states, noisy_dict={k: v.detach() for k, v in noisy.items()},
                                                start_noise=start, num_ddim_steps=5),
                                    outputs=dict(loss=out.loss.detach(), predicted_noise=out.logits.detach(),
-                                                grads=grads, inference_actions=torch.tensor(ref_actions)))
+                                                grads=grads, inference_actions=torch.tensor(ref_actions),
+                                                trajectory=[tuple(x.detach() for x in st) for st in traj]))
     torch.save(dict(seed=seed, cases=out_fx), GOLDEN / "oft_diffusion_tiny.pt")
     print("[oft_diffusion_tiny] wrote fixture")
 
