@@ -49,6 +49,7 @@ constexpr float kRescaleThreshold = 8.0f;   // log2 units: P <= 2^8 under a stal
 
 struct FaParams {
   CUtensorMap tmQ, tmK, tmV, tmDO;
+  CUtensorMap tmO;      // fwd: out rows, dq: dq rows (box 64 columns x 32 rows: one warp's slice of an atom)
   int B, H, KVH, G, S, hd;
   int katoms;    // ceil(hd / 64): 64-column atoms per tile row
   int ksteps;    // ceil(hd / 16): UMMA K steps of a head_dim contraction
@@ -60,10 +61,12 @@ struct FaParams {
   int causal;
   int n_items;
   int n_modes;   // dkv: 1 (dV and dK together) or 2 (head_dim > 128: separate items)
+  int tma_epi;   // dq: output rows leave through smem staging + TMA (needs 32 KB of shared memory)
   float scale, sl2;
   const uint8_t* keymask;
   const int* bid_q;
   const int* bid_k;
+  const int4* mask_ws;  // [B][n_qblk][2] summary of the key / query side masks (attn_mask_prep_kernel), NULL: no such masks
   bf16* out;            // fwd: O rows; bwd: unused
   float* lse;           // [B, H, S] log2-domain log-sum-exp
   const float* delta;   // [B, H, S]
@@ -147,39 +150,93 @@ __device__ __forceinline__ int visible_blocks(const FaParams& p, int tile) {
   return (keys + 63) >> 6;
 }
 
-// Key-side mask data of key (k0 + lane), loaded one block ahead of its use (a global load on the per-block critical
-// path of a row-per-thread softmax costs more than the softmax itself).
-struct KeyInfo {
-  int bk;     // block id of the key (pi0 rule), INT_MAX when the rule is off / out of range
-  bool ok;    // in range and not padding
-};
-__device__ __forceinline__ KeyInfo load_key(const FaParams& p, int b, int k) {
-  KeyInfo r;
-  const bool in = k < p.S;
-  r.ok = in && (p.keymask == nullptr || p.keymask[(size_t)b * p.S + k] != 0);
-  r.bk = (p.bid_k != nullptr && in) ? p.bid_k[(size_t)b * p.S + k] : 0x7fffffff;
-  return r;
-}
-// Validity bits of the 32 keys [k0, k0 + 32) for query row q (row-wise kernels: fwd, dq).  Key-side bits come from one
-// ballot; the causal rule is a per-row bit count; the block-id rule is evaluated per element only when the warp's keys
-// are not all visible to all its rows.
-__device__ __forceinline__ uint32_t row_bits32(const FaParams& p, KeyInfo ki, int q, int bq, int k0) {
-  uint32_t w = __ballot_sync(0xffffffffu, ki.ok);
-  if (p.causal) w &= low_mask(q + 1 - k0);
-  if (p.bid_k != nullptr) {
-    int mx = ki.ok ? ki.bk : (int)0x80000000;
+// Mask summary per (batch row, 64-key block), written by attn_mask_prep_kernel once per call, so that the softmax warps
+// read ONE 16-byte word per block instead of evaluating the mask inputs key by key:
+//   entry 0 (key side):   x / y = validity bits (in range and not padding) of keys [64j, 64j+32) / [64j+32, 64j+64),
+//                         z / w = max / min block id (pi0 rule) over the valid keys (INT_MIN / INT_MAX when none)
+//   entry 1 (query side): x / y = min / max block id of queries [64j, 64j+32), z / w = the same of [64j+32, 64j+64)
+// Without a keymask and block ids the table is not needed (mask_ws == NULL): the bits follow from S alone.
+__global__ void __launch_bounds__(128) attn_mask_prep_kernel(const uint8_t* __restrict__ keymask,
+                                                             const int* __restrict__ bid_q,
+                                                             const int* __restrict__ bid_k, int B, int S, int n_blk,
+                                                             int4* __restrict__ ws) {
+  const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= B * n_blk) return;
+  const int b = w / n_blk, j = w - b * n_blk;
+  int4 ke, qe;
+  int kmax = (int)0x80000000, kmin = 0x7fffffff;
+  uint32_t bits[2];
+  int qmin[2], qmax[2];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (__any_sync(0xffffffffu, bq < mx)) {
-      uint32_t w2 = 0;
-      for (int j = 0; j < 32; ++j) {
-        const int bkj = __shfl_sync(0xffffffffu, ki.bk, j);
-        if (bkj <= bq) w2 |= 1u << j;
+  for (int h = 0; h < 2; ++h) {
+    const int k = j * 64 + h * 32 + lane;
+    const bool in = k < S;
+    const bool ok = in && (keymask == nullptr || keymask[(size_t)b * S + k] != 0);
+    bits[h] = __ballot_sync(0xffffffffu, ok);
+    if (bid_k != nullptr && ok) {
+      const int v = bid_k[(size_t)b * S + k];
+      kmax = max(kmax, v);
+      kmin = min(kmin, v);
+    }
+    int lo = 0x7fffffff, hi = (int)0x80000000;
+    if (bid_q != nullptr && in) lo = hi = bid_q[(size_t)b * S + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    qmin[h] = lo;
+    qmax[h] = hi;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+  }
+  if (lane == 0) {
+    ke.x = (int)bits[0];
+    ke.y = (int)bits[1];
+    ke.z = kmax;
+    ke.w = kmin;
+    qe.x = qmin[0];
+    qe.y = qmax[0];
+    qe.z = qmin[1];
+    qe.w = qmax[1];
+    ws[(size_t)w * 2] = ke;
+    ws[(size_t)w * 2 + 1] = qe;
+  }
+}
+
+// key-side entry of block j (registers only when there is no table)
+__device__ __forceinline__ int4 load_kblk(const FaParams& p, int b, int j) {
+  if (p.mask_ws != nullptr) return __ldg(p.mask_ws + ((size_t)b * p.n_qblk + j) * 2);
+  const int n = p.S - j * 64;
+  return make_int4((int)low_mask(n), (int)low_mask(n - 32), (int)0x80000000, 0x7fffffff);
+}
+// Validity bits of the 64 keys of block j for query row q (row-wise kernels: fwd, dq).  The pi0 block-id rule only
+// costs a per-key evaluation in blocks whose valid keys straddle the row's block id.
+__device__ __forceinline__ void row_mask(const FaParams& p, const int4 ki, int b, int q, int bq, int k0, uint32_t& lo,
+                                         uint32_t& hi) {
+  lo = (uint32_t)ki.x;
+  hi = (uint32_t)ki.y;
+  if (p.causal) {
+    lo &= low_mask(q + 1 - k0);
+    hi &= low_mask(q - 31 - k0);
+  }
+  if (p.bid_k != nullptr && bq < ki.z) {      // some valid key of the block belongs to a later block than this row
+    if (bq < ki.w) {
+      lo = hi = 0u;
+    } else {
+      const int* bk = p.bid_k + (size_t)b * p.S + k0;
+      uint32_t w0 = 0u, w1 = 0u;
+      for (int c = 0; c < 32; ++c) {
+        if (k0 + c < p.S && bk[c] <= bq) w0 |= 1u << c;
+        if (k0 + 32 + c < p.S && bk[32 + c] <= bq) w1 |= 1u << c;
       }
-      w &= w2;
+      lo &= w0;
+      hi &= w1;
     }
   }
-  return w;
 }
 
 // ---------------------------------------------------------------------------------------------------- forward
@@ -252,6 +309,50 @@ __device__ __forceinline__ void store_acc_rows(uint32_t acc_tmem, bf16* row, boo
     if (row_ok) {
       store_chunk_bf16(row, c, hd, oa, mul);
       if (two) store_chunk_bf16(row, c + cstep, hd, ob, mul);
+    }
+  }
+}
+// The same through shared memory and TMA: one warp's 32 rows of a [128 x hd] fp32 accumulator -> bf16 -> the warp's 4 KB
+// slice of a 128B-swizzled [128][128 B] atom image -> cp.async.bulk.tensor store (full 128-byte lines; rows >= S and
+// columns >= hd are clipped by the tensor map).  Atoms a0, a0 + astep, ...  `stage` must be 1024-byte aligned.
+__device__ __forceinline__ void store_acc_tma(const CUtensorMap* tm, uint32_t acc_tmem, uint8_t* stage, int lane, int a0,
+                                              int astep, int katoms, int o_chunks, float mul, int row0, int c2, int c3,
+                                              bool any_row) {
+  uint8_t* srow = stage + lane * 128;
+  const int sw = lane & 7;
+  for (int a = a0; a < katoms; a += astep) {
+    uint32_t oa[32], ob[32];
+    const bool two = 2 * a + 1 < o_chunks;
+    tmem_ld_32x32(acc_tmem + a * 64, oa);
+    if (two) tmem_ld_32x32(acc_tmem + a * 64 + 32, ob);
+    tmem_ld_wait();
+    if (lane == 0) tma_store_wait_read<0>();     // the previous store out of this slice has been read
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 u;
+      u.x = pack2(__uint_as_float(oa[g * 8]) * mul, __uint_as_float(oa[g * 8 + 1]) * mul);
+      u.y = pack2(__uint_as_float(oa[g * 8 + 2]) * mul, __uint_as_float(oa[g * 8 + 3]) * mul);
+      u.z = pack2(__uint_as_float(oa[g * 8 + 4]) * mul, __uint_as_float(oa[g * 8 + 5]) * mul);
+      u.w = pack2(__uint_as_float(oa[g * 8 + 6]) * mul, __uint_as_float(oa[g * 8 + 7]) * mul);
+      *reinterpret_cast<uint4*>(srow + ((g ^ sw) << 4)) = u;
+    }
+    if (two) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 u;
+        u.x = pack2(__uint_as_float(ob[g * 8]) * mul, __uint_as_float(ob[g * 8 + 1]) * mul);
+        u.y = pack2(__uint_as_float(ob[g * 8 + 2]) * mul, __uint_as_float(ob[g * 8 + 3]) * mul);
+        u.z = pack2(__uint_as_float(ob[g * 8 + 4]) * mul, __uint_as_float(ob[g * 8 + 5]) * mul);
+        u.w = pack2(__uint_as_float(ob[g * 8 + 6]) * mul, __uint_as_float(ob[g * 8 + 7]) * mul);
+        *reinterpret_cast<uint4*>(srow + (((4 + g) ^ sw) << 4)) = u;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && any_row) {
+      tma_store_4d(tm, stage, a * 64, row0, c2, c3);
+      tma_store_commit();
     }
   }
 }
@@ -436,7 +537,8 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     const uint32_t o_tmem = lane_base + (kTiles == 2 ? 256u + t * 128u : 128u);
-    uint8_t* prow = sP + t * kAtom128 + r * 128;
+    uint8_t* pslice = sP + t * kAtom128 + quarter * 4096;    // this warp's 32 rows of the P tile (also its output stage)
+    uint8_t* prow = pslice + lane * 128;
     const int sw = r & 7;
     uint32_t cnt = 0;
     for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
@@ -448,38 +550,39 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
       const bool row_ok = q < p.S;
       const int bq = (p.bid_q != nullptr && row_ok) ? p.bid_q[(size_t)b * p.S + q] : 0;
       float m_ref = -INFINITY, l = 0.0f;
-      KeyInfo k0n = load_key(p, b, lane), k1n = load_key(p, b, 32 + lane);
+      int4 kin = load_kblk(p, b, 0);
       for (int j = 0; j < nblk; ++j) {
         const uint32_t buf = cnt & 1u;
-        const KeyInfo k0c = k0n, k1c = k1n;
-        if (j + 1 < nblk) {    // next block's mask bytes: in flight while this block is processed
-          k0n = load_key(p, b, (j + 1) * 64 + lane);
-          k1n = load_key(p, b, (j + 1) * 64 + 32 + lane);
-        }
-        const uint32_t bits0 = row_bits32(p, k0c, q, bq, j * 64);
-        const uint32_t bits1 = row_bits32(p, k1c, q, bq, j * 64 + 32);
-        if (warp == 4 && lane == 0) FA_TRACE(19, cnt);
+        const int4 kic = kin;
+        if (j + 1 < nblk) kin = load_kblk(p, b, j + 1);    // next block's mask word: in flight during this block
+        uint32_t bits0, bits1;
+        row_mask(p, kic, b, q, bq, j * 64, bits0, bits1);
+        const bool full = __all_sync(0xffffffffu, (bits0 & bits1) == 0xffffffffu);
+        if (warp == 4) FA_TRACE(19, cnt);
         mbar_wait(&bar_s_full[t][buf], (cnt >> 1) & 1u);
         tc_fence_after();
-        if (warp == 4 && lane == 0) FA_TRACE(20, cnt);
+        if (warp == 4) FA_TRACE(20, cnt);
         uint32_t s0[32], s1[32];
         tmem_ld_32x32(lane_base + t * 128 + buf * 64, s0);
         tmem_ld_32x32(lane_base + t * 128 + buf * 64 + 32, s1);
         tmem_ld_wait();
-        if (warp == 4 && lane == 0) FA_TRACE(21, cnt);
-        float mx = -INFINITY;
-        if (__all_sync(0xffffffffu, (bits0 & bits1) == 0xffffffffu)) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
-        } else {
+        if (warp == 4) FA_TRACE(21, cnt);
+        if (!full) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if (!((bits0 >> i) & 1u)) s0[i] = 0xff800000u;   // -inf
             if (!((bits1 >> i) & 1u)) s1[i] = 0xff800000u;
-            mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
           }
         }
-        const float m_blk = mx * p.sl2;
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          mx4[0] = fmaxf(mx4[0], __uint_as_float(s0[i]));
+          mx4[1] = fmaxf(mx4[1], __uint_as_float(s0[16 + i]));
+          mx4[2] = fmaxf(mx4[2], __uint_as_float(s1[i]));
+          mx4[3] = fmaxf(mx4[3], __uint_as_float(s1[16 + i]));
+        }
+        const float m_blk = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.sl2;
         if (j == 0) {
           m_ref = m_blk;
         } else {
@@ -504,46 +607,54 @@ __global__ void __launch_bounds__(128 + 128 * kTiles, 1) flash_fwd_kernel(const 
           }
         }
         const float m_use = m_ref == -INFINITY ? 0.0f : m_ref;
-        if (warp == 4 && lane == 0) FA_TRACE(22, cnt);
+        if (warp == 4) FA_TRACE(22, cnt);
         uint32_t pk[32];
-        float sum0 = 0.0f, sum1 = 0.0f;
+        float sum0 = 0.0f, sum1 = 0.0f, sum2 = 0.0f, sum3 = 0.0f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float a0 = ex2f(fmaf(__uint_as_float(s0[2 * i]), p.sl2, -m_use));
           const float a1 = ex2f(fmaf(__uint_as_float(s0[2 * i + 1]), p.sl2, -m_use));
           const float c0 = ex2f(fmaf(__uint_as_float(s1[2 * i]), p.sl2, -m_use));
           const float c1 = ex2f(fmaf(__uint_as_float(s1[2 * i + 1]), p.sl2, -m_use));
-          sum0 += a0 + a1;
-          sum1 += c0 + c1;
+          sum0 += a0;
+          sum1 += a1;
+          sum2 += c0;
+          sum3 += c1;
           pk[i] = pack2(a0, a1);
           pk[16 + i] = pack2(c0, c1);
         }
-        l += sum0 + sum1;
-        if (warp == 4 && lane == 0) FA_TRACE(23, cnt);
-        if (cnt > 0) mbar_wait(&bar_pv_done[t], (cnt - 1u) & 1u);   // the P buffer's previous reader has retired
-        if (warp == 4 && lane == 0) FA_TRACE(24, cnt);
+        l += (sum0 + sum1) + (sum2 + sum3);
+        if (warp == 4) FA_TRACE(23, cnt);
+        if (j == 0) {
+          if (lane == 0) tma_store_wait_read<0>();     // the previous item's output has left this slice of sP
+          __syncwarp();
+        } else {
+          mbar_wait(&bar_pv_done[t], (cnt - 1u) & 1u);   // the P buffer's previous reader has retired
+        }
+        if (warp == 4) FA_TRACE(24, cnt);
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           *reinterpret_cast<uint4*>(prow + ((c ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         fence_proxy_async_smem();
         tc_fence_before();
         warp_arrive(&bar_p_full[t], lane);
-        if (warp == 4 && lane == 0) FA_TRACE(25, cnt);
+        if (warp == 4) FA_TRACE(25, cnt);
         ++cnt;
       }
-      // ---- epilogue: O / l -> bf16 rows, log-sum-exp
-      if (warp == 4 && lane == 0) FA_TRACE(26, cnt - 1u);
+      // ---- epilogue: O / l -> bf16 rows (through this warp's slice of sP and a TMA store), log-sum-exp
+      if (warp == 4) FA_TRACE(26, cnt - 1u);
       mbar_wait(&bar_pv_done[t], (cnt - 1u) & 1u);
       tc_fence_after();
-      if (warp == 4 && lane == 0) FA_TRACE(27, cnt - 1u);
+      if (warp == 4) FA_TRACE(27, cnt - 1u);
       const float inv = l > 0.0f ? 1.0f / l : 0.0f;
-      bf16* orow = p.out + (long long)b * p.o_sb + (long long)q * p.o_ld + (long long)h * p.o_sh;
-      store_acc_rows(o_tmem, orow, row_ok, 0, 1, p.o_chunks, p.hd, inv);
+      const int row0 = im.tile[t] * 128 + quarter * 32;
+      store_acc_tma(&p.tmO, o_tmem, pslice, lane, 0, 1, p.katoms, p.o_chunks, inv, row0, h, b, row0 < p.S);
       if (row_ok && p.lse != nullptr)
         p.lse[((size_t)b * p.H + h) * p.S + q] = l > 0.0f ? m_ref + log2f(l) : INFINITY;
-      if (warp == 4 && lane == 0) FA_TRACE(28, cnt - 1u);
+      if (warp == 4) FA_TRACE(28, cnt - 1u);
       tc_fence_before();
     }
+    if (lane == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -704,11 +815,13 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // 8 warps: lane quarter = warp & 3, column half = (warp - 4) / 4 of each 64-key block; no row reductions in backward
+    // 8 warps: lane quarter = warp & 3, column half = (warp - 4) / 4 of each 64-key block; no row reductions in backward.
+    // dS is written WITHOUT the softmax scale (it is applied once to the dQ accumulator in the epilogue).
     const int quarter = warp & 3, half = (warp - 4) >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     uint8_t* dsrow = sDS + r * 128;
+    uint8_t* stage_out = sRing + stages * stage_bytes + (warp - 4) * 4096;   // TMA staging of this warp's dQ rows
     const int sw = r & 7;
     uint32_t cnt = 0;
     int qi = 0;
@@ -722,58 +835,77 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
       const float L = row_ok ? p.lse[stat] : INFINITY;
       const float dl = row_ok ? p.delta[stat] : 0.0f;
       const int bq = (p.bid_q != nullptr && row_ok) ? p.bid_q[(size_t)b * p.S + q] : 0;
-      KeyInfo kn = load_key(p, b, half * 32 + lane);
+      int4 kin = load_kblk(p, b, 0);
       for (int j = 0; j < n; ++j) {
         const uint32_t buf = cnt & 1u;
-        const KeyInfo kc = kn;
-        if (j + 1 < n) kn = load_key(p, b, (j + 1) * 64 + half * 32 + lane);
-        const uint32_t bits = row_bits32(p, kc, q, bq, j * 64 + half * 32);
-        if (warp == 4 && lane == 0) FA_TRACE(6, cnt);
+        const int4 kic = kin;
+        if (j + 1 < n) kin = load_kblk(p, b, j + 1);
+        uint32_t b0, b1;
+        row_mask(p, kic, b, q, bq, j * 64, b0, b1);
+        const uint32_t bits = half ? b1 : b0;
+        const bool full = __all_sync(0xffffffffu, bits == 0xffffffffu);
+        if (warp == 4) FA_TRACE(6, cnt);
         mbar_wait(&bar_sdp_full[buf], (cnt >> 1) & 1u);
         tc_fence_after();
-        if (warp == 4 && lane == 0) FA_TRACE(7, cnt);
+        if (warp == 4) FA_TRACE(7, cnt);
         uint32_t s[32], dp[32];
         tmem_ld_32x32(lane_base + buf * 64 + half * 32, s);
         tmem_ld_32x32(lane_base + 128 + buf * 64 + half * 32, dp);
         tmem_ld_wait();
         tc_fence_before();
         warp_arrive(&bar_sdp_free[buf], lane);
-        if (warp == 4 && lane == 0) FA_TRACE(8, cnt);
+        if (warp == 4) FA_TRACE(8, cnt);
         uint32_t pk[16];
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float v[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int c = 2 * i + e;
-            const float pe = ((bits >> c) & 1u) ? ex2f(fmaf(__uint_as_float(s[c]), p.sl2, -L)) : 0.0f;
-            v[e] = pe * (__uint_as_float(dp[c]) - dl) * p.scale;
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2f(fmaf(__uint_as_float(s[2 * i]), p.sl2, -L));
+            const float p1 = ex2f(fmaf(__uint_as_float(s[2 * i + 1]), p.sl2, -L));
+            pk[i] = pack2(p0 * (__uint_as_float(dp[2 * i]) - dl), p1 * (__uint_as_float(dp[2 * i + 1]) - dl));
           }
-          pk[i] = pack2(v[0], v[1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = 2 * i + e;
+              const float pe = ((bits >> c) & 1u) ? ex2f(fmaf(__uint_as_float(s[c]), p.sl2, -L)) : 0.0f;
+              v[e] = pe * (__uint_as_float(dp[c]) - dl);
+            }
+            pk[i] = pack2(v[0], v[1]);
+          }
         }
-        if (warp == 4 && lane == 0) FA_TRACE(9, cnt);
+        if (warp == 4) FA_TRACE(9, cnt);
         if (cnt > 0) mbar_wait(&bar_ds_empty, (cnt - 1u) & 1u);
-        if (warp == 4 && lane == 0) FA_TRACE(10, cnt);
+        if (warp == 4) FA_TRACE(10, cnt);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           *reinterpret_cast<uint4*>(dsrow + (((half * 4 + c) ^ sw) << 4)) =
               make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         fence_proxy_async_smem();
         warp_arrive(&bar_ds_full, lane);
-        if (warp == 4 && lane == 0) FA_TRACE(11, cnt);
+        if (warp == 4) FA_TRACE(11, cnt);
         ++cnt;
       }
-      if (warp == 4 && lane == 0) FA_TRACE(12, cnt - 1u);
+      if (warp == 4) FA_TRACE(12, cnt - 1u);
       mbar_wait(&bar_dq_full, (uint32_t)(qi & 1));
       tc_fence_after();
-      if (warp == 4 && lane == 0) FA_TRACE(13, cnt - 1u);
-      bf16* drow = p.dq + (long long)b * p.g_sb + (long long)q * p.g_ld + (long long)h * p.gq_sh;
-      store_acc_rows(lane_base + 256, drow, row_ok, half, 2, p.o_chunks, p.hd, 1.0f);
-      if (warp == 4 && lane == 0) FA_TRACE(14, cnt - 1u);
+      if (warp == 4) FA_TRACE(13, cnt - 1u);
+      if (p.tma_epi) {
+        const int row0 = tile * 128 + quarter * 32;
+        store_acc_tma(&p.tmO, lane_base + 256, stage_out, lane, half, 2, p.katoms, p.o_chunks, p.scale, row0, h, b,
+                      row0 < p.S);
+      } else {
+        bf16* drow = p.dq + (long long)b * p.g_sb + (long long)q * p.g_ld + (long long)h * p.gq_sh;
+        store_acc_rows(lane_base + 256, drow, row_ok, half, 2, p.o_chunks, p.hd, p.scale);
+      }
+      if (warp == 4) FA_TRACE(14, cnt - 1u);
       tc_fence_before();
       // all eight warps have left the dQ accumulator before issuer B may overwrite it: their next arrival on ds_full
       // (block 0 of the next item) comes after this point in program order
     }
+    if (lane == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -1011,39 +1143,69 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
           uint32_t bits = key_ok ? 0xffffffffu : 0u;
           if (p.causal) bits &= ~low_mask(key - q0);      // column c is visible iff q0 + c >= key
           if (p.bid_k != nullptr) {
-            uint32_t w2 = 0;
+            // query-side summary of this half block: every query at or after the key's block id, or none, or mixed
+            const int4 qe = __ldg(p.mask_ws + ((size_t)b * p.n_qblk + ib) * 2 + 1);
+            const int qmin = half ? qe.z : qe.x, qmax = half ? qe.w : qe.y;
+            if (bk > qmin) {
+              if (bk > qmax) {
+                bits = 0u;
+              } else {
+                uint32_t w2 = 0;
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (bk <= __float_as_int(st[2][c])) w2 |= 1u << c;
-            bits &= w2;
+                for (int c = 0; c < 32; ++c)
+                  if (bk <= __float_as_int(st[2][c])) w2 |= 1u << c;
+                bits &= w2;
+              }
+            }
           }
-          if (warp == 4 && lane == 0) FA_TRACE(38, cnt);
+          const bool full = __all_sync(0xffffffffu, bits == 0xffffffffu);
+          if (warp == 4) FA_TRACE(38, cnt);
           mbar_wait(&bar_sdp_full[buf], (cnt >> 1) & 1u);
           tc_fence_after();
-          if (warp == 4 && lane == 0) FA_TRACE(39, cnt);
+          if (warp == 4) FA_TRACE(39, cnt);
           uint32_t s[32], dp[32];
           tmem_ld_32x32(lane_base + buf * 64 + half * 32, s);
           if (do_dk) tmem_ld_32x32(lane_base + 128 + buf * 64 + half * 32, dp);
           tmem_ld_wait();
           tc_fence_before();
           warp_arrive(&bar_sdp_free[buf], lane);
-          if (warp == 4 && lane == 0) FA_TRACE(40, cnt);
+          if (warp == 4) FA_TRACE(40, cnt);
+          // P^T = exp2(S^T * sl2 - lse[q]); dS^T = P^T * (dP^T - delta[q]) (the softmax scale goes into the dK epilogue)
           uint32_t pp[16], pd[16];
+          if (full) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float pv[2], dv[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int c = 2 * i + e;
-              pv[e] = ((bits >> c) & 1u) ? ex2f(fmaf(__uint_as_float(s[c]), p.sl2, -st[0][c])) : 0.0f;
-              dv[e] = do_dk ? pv[e] * (__uint_as_float(dp[c]) - st[1][c]) * p.scale : 0.0f;
+            for (int i = 0; i < 8; ++i) {
+              const float4 Lv = *reinterpret_cast<const float4*>(&st[0][4 * i]);
+              const float p0 = ex2f(fmaf(__uint_as_float(s[4 * i]), p.sl2, -Lv.x));
+              const float p1 = ex2f(fmaf(__uint_as_float(s[4 * i + 1]), p.sl2, -Lv.y));
+              const float p2 = ex2f(fmaf(__uint_as_float(s[4 * i + 2]), p.sl2, -Lv.z));
+              const float p3 = ex2f(fmaf(__uint_as_float(s[4 * i + 3]), p.sl2, -Lv.w));
+              pp[2 * i] = pack2(p0, p1);
+              pp[2 * i + 1] = pack2(p2, p3);
+              if (do_dk) {
+                const float4 Dv = *reinterpret_cast<const float4*>(&st[1][4 * i]);
+                pd[2 * i] = pack2(p0 * (__uint_as_float(dp[4 * i]) - Dv.x), p1 * (__uint_as_float(dp[4 * i + 1]) - Dv.y));
+                pd[2 * i + 1] =
+                    pack2(p2 * (__uint_as_float(dp[4 * i + 2]) - Dv.z), p3 * (__uint_as_float(dp[4 * i + 3]) - Dv.w));
+              }
             }
-            pp[i] = pack2(pv[0], pv[1]);
-            pd[i] = pack2(dv[0], dv[1]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float pv[2], dv[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int c = 2 * i + e;
+                pv[e] = ((bits >> c) & 1u) ? ex2f(fmaf(__uint_as_float(s[c]), p.sl2, -st[0][c])) : 0.0f;
+                dv[e] = do_dk ? pv[e] * (__uint_as_float(dp[c]) - st[1][c]) : 0.0f;
+              }
+              pp[i] = pack2(pv[0], pv[1]);
+              pd[i] = pack2(dv[0], dv[1]);
+            }
           }
-          if (warp == 4 && lane == 0) FA_TRACE(41, cnt);
+          if (warp == 4) FA_TRACE(41, cnt);
           if (cnt > 0) mbar_wait(&bar_pds_empty, (cnt - 1u) & 1u);
-          if (warp == 4 && lane == 0) FA_TRACE(42, cnt);
+          if (warp == 4) FA_TRACE(42, cnt);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int off = ((half * 4 + c) ^ sw) << 4;
@@ -1052,7 +1214,7 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
           }
           fence_proxy_async_smem();
           warp_arrive(&bar_pds_full, lane);
-          if (warp == 4 && lane == 0) FA_TRACE(43, cnt);
+          if (warp == 4) FA_TRACE(43, cnt);
           ++cnt;
         }
       }
@@ -1062,7 +1224,7 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
       const long long roff = (long long)b * p.g_sb + (long long)key * p.g_ld + (long long)im.kvh * p.gkv_sh;
       if (do_dv) store_acc_rows(lane_base + 256, p.dv + roff, key_in, half, 2, p.o_chunks, p.hd, 1.0f);
       if (do_dk)
-        store_acc_rows(lane_base + (im.mode == 0 ? 384u : 256u), p.dk + roff, key_in, half, 2, p.o_chunks, p.hd, 1.0f);
+        store_acc_rows(lane_base + (im.mode == 0 ? 384u : 256u), p.dk + roff, key_in, half, 2, p.o_chunks, p.hd, p.scale);
       tc_fence_before();
     }
   }
@@ -1179,6 +1341,20 @@ static int fill_common(FaParams& kp, int64_t B, int64_t H, int64_t KVH, int64_t 
   return 0;
 }
 
+// mask summary table (see attn_mask_prep_kernel): needed when a key mask or the block-id rule is present
+static int prep_masks(FaParams& kp, int32_t* mask_ws, cudaStream_t stream) {
+  kp.mask_ws = nullptr;
+  if (kp.keymask == nullptr && kp.bid_k == nullptr) return 0;
+  B200_CHECK(mask_ws != nullptr, "flash_attn: mask_ws (int32 [B, ceil(S/64), 8]) is required with a key mask / block ids");
+  B200_CHECK((reinterpret_cast<uintptr_t>(mask_ws) & 15) == 0, "flash_attn: mask_ws must be 16-byte aligned");
+  const int warps = kp.B * kp.n_qblk;
+  attn_mask_prep_kernel<<<(unsigned)ceil_div((int64_t)warps * 32, 128), 128, 0, stream>>>(
+      kp.keymask, kp.bid_q, kp.bid_k, kp.B, kp.S, kp.n_qblk, reinterpret_cast<int4*>(mask_ws));
+  B200_LAUNCH_OK();
+  kp.mask_ws = reinterpret_cast<const int4*>(mask_ws);
+  return 0;
+}
+
 template <typename K>
 static int set_smem(K kernel, int bytes) {
   B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -1198,9 +1374,11 @@ extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, 
                                    int64_t H, int64_t KVH, int64_t S, int64_t head_dim, int64_t qkv_ld,
                                    int64_t qkv_s_head, int64_t qkv_s_batch, int64_t o_ld, int64_t o_s_head,
                                    int64_t o_s_batch, float scale, int causal, const uint8_t* keymask,
-                                   const int32_t* bid_q, const int32_t* bid_k, void* stream) {
+                                   const int32_t* bid_q, const int32_t* bid_k, int32_t* mask_ws, void* stream) {
   FaParams kp;
   if (fill_common(kp, B, H, KVH, S, head_dim, scale, causal, keymask, bid_q, bid_k)) return 1;
+  if (prep_masks(kp, mask_ws, reinterpret_cast<cudaStream_t>(stream))) return 1;
+  if (encode_rows(&kp.tmO, out, head_dim, S, H, B, o_ld, o_s_head, o_s_batch, 32, "flash O")) return 1;
   B200_CHECK(o_ld % 8 == 0 && o_s_head % 8 == 0 && o_s_batch % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              "flash_attn_fwd: output rows must be 16-byte aligned");
   if (encode_rows(&kp.tmQ, q, head_dim, S, H, B, qkv_ld, qkv_s_head, qkv_s_batch, 128, "flash Q")) return 1;
@@ -1239,10 +1417,12 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
                                    int64_t KVH, int64_t S, int64_t head_dim, int64_t qkv_ld, int64_t qkv_s_head,
                                    int64_t qkv_s_batch, int64_t o_ld, int64_t o_s_head, int64_t o_s_batch,
                                    int64_t g_ld, int64_t g_s_head, int64_t g_s_batch, float scale, int causal,
-                                   const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k, void* stream_) {
+                                   const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k, int32_t* mask_ws,
+                                   void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   FaParams kp;
   if (fill_common(kp, B, H, KVH, S, head_dim, scale, causal, keymask, bid_q, bid_k)) return 1;
+  if (prep_masks(kp, mask_ws, stream)) return 1;
   B200_CHECK(lse != nullptr && delta != nullptr, "flash_attn_bwd: lse and the delta workspace are required");
   B200_CHECK(o_ld % 8 == 0 && o_s_head % 8 == 0 && o_s_batch % 8 == 0 && g_ld % 8 == 0 && g_s_head % 8 == 0 &&
                  g_s_batch % 8 == 0,
@@ -1281,13 +1461,16 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
     if (encode_rows(&a.tmDO, dout, head_dim, S, H, B, o_ld, o_s_head, o_s_batch, 128, "flash dq dO")) return 1;
     if (encode_rows(&a.tmK, k, head_dim, S, KVH, B, qkv_ld, qkv_s_head, qkv_s_batch, 64, "flash dq K")) return 1;
     if (encode_rows(&a.tmV, v, head_dim, S, KVH, B, qkv_ld, qkv_s_head, qkv_s_batch, 64, "flash dq V")) return 1;
+    if (encode_rows(&a.tmO, dq, head_dim, S, H, B, g_ld, g_s_head, g_s_batch, 32, "flash dq out")) return 1;
     const int fixed = 2 * a.katoms * kAtom128 + kAtom128;
-    int stages = (kSmemBudget - 1024 - fixed) / stage_bytes;
+    const int staging = 8 * 4096;       // one 32-row slice per softmax warp for the TMA-store epilogue
+    a.tma_epi = (kSmemBudget - 1024 - fixed - staging) / stage_bytes >= 2 ? 1 : 0;
+    int stages = (kSmemBudget - 1024 - fixed - (a.tma_epi ? staging : 0)) / stage_bytes;
     if (stages > kFaMaxStages) stages = kFaMaxStages;
     B200_CHECK(stages >= 1, "flash_attn_bwd(dq): shared memory budget exceeded");
     a.stages = stages;
     a.n_items = (int)(B * H * a.m_tiles);
-    const int smem = 1024 + fixed + stages * stage_bytes;
+    const int smem = 1024 + fixed + stages * stage_bytes + (a.tma_epi ? staging : 0);
     if (set_smem(flash_dq_kernel, smem)) return 1;
     const unsigned grid = (unsigned)(a.n_items < num_sms() ? a.n_items : num_sms());
     flash_dq_kernel<<<grid, 384, smem, stream>>>(a);

@@ -194,6 +194,13 @@ def _flash_ok(qkv: torch.Tensor, sh: AttnShape) -> bool:
             os.environ.get("B200_FLASH_ATTN", "1") != "0")
 
 
+def _flash_mask_ws(B: int, S: int, device, keymask, bid_k):
+    """Workspace of the kernels' per-block mask summary (b200_flash_attn_fwd: mask_ws); None without key-side masks."""
+    if keymask is None and bid_k is None:
+        return None
+    return torch.empty((B, (S + 63) // 64, 8), device=device, dtype=torch.int32)
+
+
 def flash_attention_fwd(qkv: torch.Tensor, sh: AttnShape, *, keymask=None, bid_q=None, bid_k=None, causal: bool = False,
                         out: Optional[torch.Tensor] = None):
     """Flash attention over packed qkv: returns (out [B,S,H*hd], lse [B,H,S] fp32, log2 domain).  No P tensor."""
@@ -203,9 +210,10 @@ def flash_attention_fwd(qkv: torch.Tensor, sh: AttnShape, *, keymask=None, bid_q
         out = torch.empty((B, S, H * hd), device=qkv.device, dtype=qkv.dtype)
     lse = torch.empty((B, H, S), device=qkv.device, dtype=torch.float32)
     q, k, v = _qkv_ptrs(qkv, sh)
+    ws = _flash_mask_ws(B, S, qkv.device, keymask, bid_k)
     _lib.check(_lib.load().b200_flash_attn_fwd(q, k, v, out.data_ptr(), lse.data_ptr(), B, H, KVH, S, hd, W, hd, S * W,
                                                H * hd, hd, S * H * hd, float(sh.scale), int(causal), _p(keymask),
-                                               _p(bid_q), _p(bid_k), _stream()), "flash_attn_fwd")
+                                               _p(bid_q), _p(bid_k), _p(ws), _stream()), "flash_attn_fwd")
     return out, lse
 
 
@@ -221,10 +229,11 @@ def flash_attention_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor
     delta = torch.empty((B, H, S), device=qkv.device, dtype=torch.float32)
     q, k, v = _qkv_ptrs(qkv, sh)
     dq, dk, dv = _qkv_ptrs(dqkv, sh)
+    ws = _flash_mask_ws(B, S, qkv.device, keymask, bid_k)
     _lib.check(_lib.load().b200_flash_attn_bwd(q, k, v, out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
                                                delta.data_ptr(), dq, dk, dv, B, H, KVH, S, hd, W, hd, S * W, H * hd, hd,
                                                S * H * hd, W, hd, S * W, float(sh.scale), int(causal), _p(keymask),
-                                               _p(bid_q), _p(bid_k), _stream()), "flash_attn_bwd")
+                                               _p(bid_q), _p(bid_k), _p(ws), _stream()), "flash_attn_bwd")
     return dqkv
 
 

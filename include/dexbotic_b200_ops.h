@@ -82,12 +82,14 @@ int b200_attn_scores(const void* a, const void* b, const void* p_in, void* out, 
  * log2(rowsum)) is all the backward needs besides O.  q / k / v: (head_dim, S, heads, B) strided views of a packed qkv
  * buffer (element strides qkv_ld per row, qkv_s_head per head, qkv_s_batch per batch; H heads for q, KVH for k / v);
  * out: same form with its own strides.  Mask rule as b200_softmax_fwd (causal / key padding / pi0 block ids).
+ * mask_ws: int32 workspace [B, ceil(S/64), 8] (16-byte aligned) for the per-block mask summary the kernels read;
+ * required when keymask or block ids are given, may be NULL otherwise.
  * Replaces F.scaled_dot_product_attention (HF Qwen2 / Llama / CLIP / SigLIP attention, dexbotic_arch.py:55-62,
  * clip_encoder.py:50-54, siglip_encoder.py:79-84) and pi0's eager joint attention (pi0_arch.py:22-33,185-192). */
 int b200_flash_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H,
                         int64_t KVH, int64_t S, int64_t head_dim, int64_t qkv_ld, int64_t qkv_s_head,
                         int64_t qkv_s_batch, int64_t o_ld, int64_t o_s_head, int64_t o_s_batch, float scale, int causal,
-                        const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k, void* stream);
+                        const uint8_t* keymask, const int32_t* bid_q, const int32_t* bid_k, int32_t* mask_ws, void* stream);
 /* Debugging hook (tools/trace_flash.py): when buf != NULL, CTA 0 of the flash kernels writes clock64() stamps of its
  * pipeline events into buf (int64 [64 slots][64 steps]); NULL (the default) switches it off. */
 int b200_flash_attn_set_trace(void* buf);
@@ -100,7 +102,7 @@ int b200_flash_attn_bwd(const void* q, const void* k, const void* v, const void*
                         int64_t S, int64_t head_dim, int64_t qkv_ld, int64_t qkv_s_head, int64_t qkv_s_batch,
                         int64_t o_ld, int64_t o_s_head, int64_t o_s_batch, int64_t g_ld, int64_t g_s_head,
                         int64_t g_s_batch, float scale, int causal, const uint8_t* keymask, const int32_t* bid_q,
-                        const int32_t* bid_k, void* stream);
+                        const int32_t* bid_k, int32_t* mask_ws, void* stream);
 
 /* out[N] (fp32) += column sums of x[M,N]  (bias gradients) */
 int b200_colsum(const void* x, float* out, int64_t M, int64_t N, int dtype, void* stream);
