@@ -207,9 +207,26 @@ __global__ void __launch_bounds__(128) attn_mask_prep_kernel(const uint8_t* __re
   }
 }
 
+// Read-only global loads that are ISSUED where they are written: a plain (invariant) load is sunk by the compiler to its
+// first use — a whole pipeline step later — which exposes the L2 / DRAM latency these prefetches are meant to hide.
+__device__ __forceinline__ int4 ldg_now(const int4* ptr) {
+  int4 r;
+  asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
+  return r;
+}
+__device__ __forceinline__ float ldg_now(const float* ptr) {
+  float r;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(ptr));
+  return r;
+}
+__device__ __forceinline__ int ldg_now(const int* ptr) {
+  int r;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(r) : "l"(ptr));
+  return r;
+}
 // key-side entry of block j (registers only when there is no table)
 __device__ __forceinline__ int4 load_kblk(const FaParams& p, int b, int j) {
-  if (p.mask_ws != nullptr) return __ldg(p.mask_ws + ((size_t)b * p.n_qblk + j) * 2);
+  if (p.mask_ws != nullptr) return ldg_now(p.mask_ws + ((size_t)b * p.n_qblk + j) * 2);
   const int n = p.S - j * 64;
   return make_int4((int)low_mask(n), (int)low_mask(n - 32), (int)0x80000000, 0x7fffffff);
 }
@@ -223,18 +240,26 @@ __device__ __forceinline__ void row_mask(const FaParams& p, const int4 ki, int b
     lo &= low_mask(q + 1 - k0);
     hi &= low_mask(q - 31 - k0);
   }
-  if (p.bid_k != nullptr && bq < ki.z) {      // some valid key of the block belongs to a later block than this row
-    if (bq < ki.w) {
-      lo = hi = 0u;
-    } else {
+  if (p.bid_k != nullptr) {
+    // ki.z / ki.w = max / min block id over the block's valid keys: rows at or past the max see all of them, rows
+    // before the min none; only a block whose keys straddle some row's id is evaluated key by key (whole warp: the keys'
+    // ids are loaded once, coalesced, and broadcast by shuffles)
+    const bool mixed = bq < ki.z && bq >= ki.w;
+    if (__any_sync(0xffffffffu, mixed)) {
+      const int lane = threadIdx.x & 31;
       const int* bk = p.bid_k + (size_t)b * p.S + k0;
+      const int v0 = k0 + lane < p.S ? bk[lane] : 0x7fffffff;
+      const int v1 = k0 + 32 + lane < p.S ? bk[32 + lane] : 0x7fffffff;
       uint32_t w0 = 0u, w1 = 0u;
+#pragma unroll
       for (int c = 0; c < 32; ++c) {
-        if (k0 + c < p.S && bk[c] <= bq) w0 |= 1u << c;
-        if (k0 + 32 + c < p.S && bk[32 + c] <= bq) w1 |= 1u << c;
+        if (__shfl_sync(0xffffffffu, v0, c) <= bq) w0 |= 1u << c;
+        if (__shfl_sync(0xffffffffu, v1, c) <= bq) w1 |= 1u << c;
       }
       lo &= w0;
       hi &= w1;
+    } else if (bq < ki.w) {
+      lo = hi = 0u;
     }
   }
 }
@@ -832,8 +857,8 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
       const int q = tile * 128 + r;
       const bool row_ok = q < p.S;
       const size_t stat = ((size_t)b * p.H + h) * p.S + q;
-      const float L = row_ok ? p.lse[stat] : INFINITY;
-      const float dl = row_ok ? p.delta[stat] : 0.0f;
+      const float L = row_ok ? ldg_now(p.lse + stat) : INFINITY;
+      const float dl = row_ok ? ldg_now(p.delta + stat) : 0.0f;
       const int bq = (p.bid_q != nullptr && row_ok) ? p.bid_q[(size_t)b * p.S + q] : 0;
       int4 kin = load_kblk(p, b, 0);
       for (int j = 0; j < n; ++j) {
@@ -1116,9 +1141,9 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
         const int qq = ib * 64 + half * 32 + lane;
         const bool qok = qq < p.S;
         const size_t stat = ((size_t)b * p.H + (im.kvh * p.G + hh)) * p.S + qq;
-        o_l = qok ? p.lse[stat] : INFINITY;
-        o_d = (qok && do_dk) ? p.delta[stat] : 0.0f;
-        o_b = (p.bid_q != nullptr && qok) ? p.bid_q[(size_t)b * p.S + qq] : 0;
+        o_l = qok ? ldg_now(p.lse + stat) : INFINITY;
+        o_d = (qok && do_dk) ? ldg_now(p.delta + stat) : 0.0f;
+        o_b = (p.bid_q != nullptr && qok) ? ldg_now(p.bid_q + (size_t)b * p.S + qq) : 0;
       };
       float n_l, n_d;
       int n_b;
@@ -1144,7 +1169,7 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
           if (p.causal) bits &= ~low_mask(key - q0);      // column c is visible iff q0 + c >= key
           if (p.bid_k != nullptr) {
             // query-side summary of this half block: every query at or after the key's block id, or none, or mixed
-            const int4 qe = __ldg(p.mask_ws + ((size_t)b * p.n_qblk + ib) * 2 + 1);
+            const int4 qe = ldg_now(p.mask_ws + ((size_t)b * p.n_qblk + ib) * 2 + 1);
             const int qmin = half ? qe.z : qe.x, qmax = half ? qe.w : qe.y;
             if (bk > qmin) {
               if (bk > qmax) {
@@ -1173,21 +1198,26 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
           // P^T = exp2(S^T * sl2 - lse[q]); dS^T = P^T * (dP^T - delta[q]) (the softmax scale goes into the dK epilogue)
           uint32_t pp[16], pd[16];
           if (full) {
+            // all statistics first (8 broadcast LDS.128), then 32 independent exponentials: P overwrites s, dS overwrites dp
+            {
+              float Lr[32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 Lv = *reinterpret_cast<const float4*>(&st[0][4 * i]);
-              const float p0 = ex2f(fmaf(__uint_as_float(s[4 * i]), p.sl2, -Lv.x));
-              const float p1 = ex2f(fmaf(__uint_as_float(s[4 * i + 1]), p.sl2, -Lv.y));
-              const float p2 = ex2f(fmaf(__uint_as_float(s[4 * i + 2]), p.sl2, -Lv.z));
-              const float p3 = ex2f(fmaf(__uint_as_float(s[4 * i + 3]), p.sl2, -Lv.w));
-              pp[2 * i] = pack2(p0, p1);
-              pp[2 * i + 1] = pack2(p2, p3);
-              if (do_dk) {
-                const float4 Dv = *reinterpret_cast<const float4*>(&st[1][4 * i]);
-                pd[2 * i] = pack2(p0 * (__uint_as_float(dp[4 * i]) - Dv.x), p1 * (__uint_as_float(dp[4 * i + 1]) - Dv.y));
-                pd[2 * i + 1] =
-                    pack2(p2 * (__uint_as_float(dp[4 * i + 2]) - Dv.z), p3 * (__uint_as_float(dp[4 * i + 3]) - Dv.w));
-              }
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(&Lr[4 * i]) = *reinterpret_cast<const float4*>(&st[0][4 * i]);
+#pragma unroll
+              for (int c = 0; c < 32; ++c) s[c] = __float_as_uint(ex2f(fmaf(__uint_as_float(s[c]), p.sl2, -Lr[c])));
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pp[i] = pack2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
+            if (do_dk) {
+              float Dr[32];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(&Dr[4 * i]) = *reinterpret_cast<const float4*>(&st[1][4 * i]);
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                pd[i] = pack2(__uint_as_float(s[2 * i]) * (__uint_as_float(dp[2 * i]) - Dr[2 * i]),
+                              __uint_as_float(s[2 * i + 1]) * (__uint_as_float(dp[2 * i + 1]) - Dr[2 * i + 1]));
             }
           } else {
 #pragma unroll
