@@ -93,6 +93,10 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// 0xffff in the halves of a packed bf16 pair whose bits (c, c + 1) of `bits` are set
+__device__ __forceinline__ uint32_t pair_mask(uint32_t bits, int c) {
+  return (((bits >> c) & 1u) ? 0x0000ffffu : 0u) | (((bits >> (c + 1)) & 1u) ? 0xffff0000u : 0u);
+}
 __device__ __forceinline__ uint32_t low_mask(int n) { return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
 
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024, descriptor version 1, SWIZZLE_128B
@@ -880,26 +884,18 @@ __global__ void __launch_bounds__(384, 1) flash_dq_kernel(const __grid_constant_
         tc_fence_before();
         warp_arrive(&bar_sdp_free[buf], lane);
         if (warp == 4) FA_TRACE(8, cnt);
+        // every element is computed; masked ones are then cleared in the packed words (an exponential of a masked score
+        // may be inf, its product NaN: the AND removes the bit pattern, nothing is multiplied by it)
         uint32_t pk[16];
-        if (full) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2f(fmaf(__uint_as_float(s[2 * i]), p.sl2, -L));
-            const float p1 = ex2f(fmaf(__uint_as_float(s[2 * i + 1]), p.sl2, -L));
-            pk[i] = pack2(p0 * (__uint_as_float(dp[2 * i]) - dl), p1 * (__uint_as_float(dp[2 * i + 1]) - dl));
-          }
-        } else {
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2f(fmaf(__uint_as_float(s[2 * i]), p.sl2, -L));
+          const float p1 = ex2f(fmaf(__uint_as_float(s[2 * i + 1]), p.sl2, -L));
+          pk[i] = pack2(p0 * (__uint_as_float(dp[2 * i]) - dl), p1 * (__uint_as_float(dp[2 * i + 1]) - dl));
+        }
+        if (!full) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float v[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int c = 2 * i + e;
-              const float pe = ((bits >> c) & 1u) ? ex2f(fmaf(__uint_as_float(s[c]), p.sl2, -L)) : 0.0f;
-              v[e] = pe * (__uint_as_float(dp[c]) - dl);
-            }
-            pk[i] = pack2(v[0], v[1]);
-          }
+          for (int i = 0; i < 16; ++i) pk[i] &= pair_mask(bits, 2 * i);
         }
         if (warp == 4) FA_TRACE(9, cnt);
         if (cnt > 0) mbar_wait(&bar_ds_empty, (cnt - 1u) & 1u);
@@ -1197,40 +1193,37 @@ __global__ void __launch_bounds__(384, 1) flash_dkv_kernel(const __grid_constant
           if (warp == 4) FA_TRACE(40, cnt);
           // P^T = exp2(S^T * sl2 - lse[q]); dS^T = P^T * (dP^T - delta[q]) (the softmax scale goes into the dK epilogue)
           uint32_t pp[16], pd[16];
-          if (full) {
-            // all statistics first (8 broadcast LDS.128), then 32 independent exponentials: P overwrites s, dS overwrites dp
-            {
-              float Lr[32];
+          if (do_dk) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<float4*>(&Lr[4 * i]) = *reinterpret_cast<const float4*>(&st[0][4 * i]);
-#pragma unroll
-              for (int c = 0; c < 32; ++c) s[c] = __float_as_uint(ex2f(fmaf(__uint_as_float(s[c]), p.sl2, -Lr[c])));
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pp[i] = pack2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
-            if (do_dk) {
-              float Dr[32];
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<float4*>(&Dr[4 * i]) = *reinterpret_cast<const float4*>(&st[1][4 * i]);
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                pd[i] = pack2(__uint_as_float(s[2 * i]) * (__uint_as_float(dp[2 * i]) - Dr[2 * i]),
-                              __uint_as_float(s[2 * i + 1]) * (__uint_as_float(dp[2 * i + 1]) - Dr[2 * i + 1]));
+            for (int i = 0; i < 8; ++i) {
+              const float4 Lv = *reinterpret_cast<const float4*>(&st[0][4 * i]);
+              const float4 Dv = *reinterpret_cast<const float4*>(&st[1][4 * i]);
+              const float p0 = ex2f(fmaf(__uint_as_float(s[4 * i]), p.sl2, -Lv.x));
+              const float p1 = ex2f(fmaf(__uint_as_float(s[4 * i + 1]), p.sl2, -Lv.y));
+              const float p2 = ex2f(fmaf(__uint_as_float(s[4 * i + 2]), p.sl2, -Lv.z));
+              const float p3 = ex2f(fmaf(__uint_as_float(s[4 * i + 3]), p.sl2, -Lv.w));
+              pp[2 * i] = pack2(p0, p1);
+              pp[2 * i + 1] = pack2(p2, p3);
+              pd[2 * i] = pack2(p0 * (__uint_as_float(dp[4 * i]) - Dv.x), p1 * (__uint_as_float(dp[4 * i + 1]) - Dv.y));
+              pd[2 * i + 1] = pack2(p2 * (__uint_as_float(dp[4 * i + 2]) - Dv.z), p3 * (__uint_as_float(dp[4 * i + 3]) - Dv.w));
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float pv[2], dv[2];
+            for (int i = 0; i < 8; ++i) {
+              const float4 Lv = *reinterpret_cast<const float4*>(&st[0][4 * i]);
+              pp[2 * i] = pack2(ex2f(fmaf(__uint_as_float(s[4 * i]), p.sl2, -Lv.x)),
+                                ex2f(fmaf(__uint_as_float(s[4 * i + 1]), p.sl2, -Lv.y)));
+              pp[2 * i + 1] = pack2(ex2f(fmaf(__uint_as_float(s[4 * i + 2]), p.sl2, -Lv.z)),
+                                    ex2f(fmaf(__uint_as_float(s[4 * i + 3]), p.sl2, -Lv.w)));
+              pd[2 * i] = pd[2 * i + 1] = 0u;
+            }
+          }
+          if (!full) {      // masked elements: clear the packed halves (see flash_dq_kernel)
 #pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int c = 2 * i + e;
-                pv[e] = ((bits >> c) & 1u) ? ex2f(fmaf(__uint_as_float(s[c]), p.sl2, -st[0][c])) : 0.0f;
-                dv[e] = do_dk ? pv[e] * (__uint_as_float(dp[c]) - st[1][c]) : 0.0f;
-              }
-              pp[i] = pack2(pv[0], pv[1]);
-              pd[i] = pack2(dv[0], dv[1]);
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t m = pair_mask(bits, 2 * i);
+              pp[i] &= m;
+              pd[i] &= m;
             }
           }
           if (warp == 4) FA_TRACE(41, cnt);

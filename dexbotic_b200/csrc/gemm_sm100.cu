@@ -606,6 +606,16 @@ static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
   return 0;
 }
 
+// experiment: CTA pairs with 256 x 128 tiles when block_n = 128 is requested explicitly (B200_GEMM_PAIR128=1)
+static bool use_pair128() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_GEMM_PAIR128");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static bool use_cta_pairs() {
   static int v = -1;
   if (v < 0) {
@@ -653,7 +663,7 @@ int b200_gemm(const b200_gemm_args* a, void* stream_) {
   kp.n_per_tile = a->dual_b ? 128 : bn;
   // CTA pairs (256-row tiles) for the large GEMMs: every MN-major operand must be 5-D describable
   const int atom_e = 128 / es;
-  const bool pair = use_cta_pairs() && bn == 256 && a->m >= 1024 && (!a->a_mn_major || a->m % atom_e == 0) &&
+  const bool pair = use_cta_pairs() && (bn == 256 || (bn == 128 && use_pair128() && !a->dual_b)) && a->m >= 1024 && (!a->a_mn_major || a->m % atom_e == 0) &&
                     (!a->b_mn_major || a->n % atom_e == 0) && a->block_n >= 0;
   kp.m_blocks = (int)ceil_div(a->m, pair ? 2 * kBlockM : kBlockM);
   kp.n_blocks = (int)ceil_div(a->n, kp.n_per_tile);
@@ -755,7 +765,7 @@ int b200_gemm(const b200_gemm_args* a, void* stream_) {
     case 64:
       return launch_gemm<64, 1>(kp, stream);
     case 128:
-      return launch_gemm<128, 1>(kp, stream);
+      return pair ? launch_gemm<128, 2>(kp, stream) : launch_gemm<128, 1>(kp, stream);
     default:
       return pair ? launch_gemm<256, 2>(kp, stream) : launch_gemm<256, 1>(kp, stream);
   }
