@@ -45,6 +45,7 @@ class GemmArgs(C.Structure):
         ("res_ld", C.c_int64), ("res_s2", C.c_int64), ("res_s3", C.c_int64),
         ("aux", C.c_void_p), ("aux2", C.c_void_p), ("aux_ld", C.c_int64),
         ("act", C.c_int32), ("dual_b", C.c_int32), ("block_n", C.c_int32),
+        ("glu_bwd", C.c_int32), ("glu_g", C.c_void_p), ("glu_u", C.c_void_p), ("d2", C.c_void_p), ("glu_ld", C.c_int64),
     ]
 
 

@@ -342,8 +342,7 @@ __global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     float v[8];
     Pack8<T>::load(x + i * 8, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = act_fwd(v[j], act);
+    act_fwd_n(v, act);
     Pack8<T>::store(y + i * 8, v);
   }
 }
@@ -354,44 +353,10 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x
     float v[8], d[8];
     Pack8<T>::load(x + i * 8, v);
     Pack8<T>::load(dy + i * 8, d);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) d[j] *= act_grad(v[j], act);
+    act_grad_mul_n(d, v, act);
     Pack8<T>::store(dx + i * 8, d);
   }
 }
-// act(x) and act'(x) together.  kAct = 4 (SiLU) / 2 (tanh-GELU) are the bf16 fast paths: one MUFU.EX2 + one MUFU.RCP
-// per element instead of two exponentials and IEEE divisions — at 8 elements per 16-byte pack the
-// generic path is MUFU-bound, not HBM-bound.  Their error (2 ulp fp32) vanishes in the bf16 rounding of the outputs.
-// kAct = -1: the exact runtime-dispatched functions (fp32 tensors, other activations).
-template <int kAct>
-__device__ __forceinline__ void act_pair(float x, int act, float& f, float& df) {
-  if constexpr (kAct == 4) {
-    const float s = __fdividef(1.0f, 1.0f + __expf(-x));
-    f = x * s;
-    df = s + f * (1.0f - s);
-  } else if constexpr (kAct == 2) {
-    const float x2 = x * x;
-    // tanh(u) = 1 - 2 / (1 + e^{2u}): one ex2 + one rcp, ~2 ulp (tanh.approx.f32 would be 2^-11)
-    const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * 0.7978845608028654f * (x + 0.044715f * x * x2)));
-    f = 0.5f * x * (1.0f + t);
-    df = 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * 0.7978845608028654f * (1.0f + 0.134145f * x2);
-  } else {
-    f = act_fwd(x, act);
-    df = act_grad(x, act);
-  }
-}
-template <int kAct>
-__device__ __forceinline__ float act_only(float x, int act) {
-  if constexpr (kAct == 4) {
-    return x * __fdividef(1.0f, 1.0f + __expf(-x));
-  } else if constexpr (kAct == 2) {
-    const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * 0.7978845608028654f * (x + 0.044715f * x * x * x)));
-    return 0.5f * x * (1.0f + t);
-  } else {
-    return act_fwd(x, act);
-  }
-}
-
 template <typename T, int kAct>
 __global__ void glu_fwd_kernel(const T* __restrict__ g, const T* __restrict__ u, T* __restrict__ h, int64_t n8,
                                int act) {

@@ -21,6 +21,7 @@
 #include "../../include/dexbotic_b200.h"
 #include "common.h"
 #include "ptx.cuh"
+#include "vec.cuh"
 
 namespace b200 {
 
@@ -46,6 +47,11 @@ struct GemmKParams {
   int a_kadv, b_kadv, a_lbo, b_lbo, a_sbo, b_sbo, a_lt, b_lt;
   int ab_fp32, d_fp32;
   int dual;
+  int glu_bwd;          // epilogue = SwiGLU / GeGLU backward: D = dg, d2 = du from the accumulator (dh) and g, u
+  const void* glu_g;
+  const void* glu_u;
+  void* d2;
+  long long glu_ld;
   int n_per_tile;  // output columns per tile (kBlockN, or 128 in dual mode)
   float alpha;
   const void* bias;
@@ -69,25 +75,6 @@ struct GemmCfg {
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 4 * kStagingPerWarp + kBarBytes;
 };
-
-__device__ __forceinline__ float apply_act(float x, int act) {
-  switch (act) {
-    case B200_ACT_GELU_ERF:
-      return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-    case B200_ACT_GELU_TANH: {
-      float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-      return 0.5f * x * (1.0f + tanhf(u));
-    }
-    case B200_ACT_QUICK_GELU:
-      return x / (1.0f + __expf(-1.702f * x));
-    case B200_ACT_SILU:
-      return x / (1.0f + __expf(-x));
-    case B200_ACT_RELU:
-      return fmaxf(x, 0.0f);
-    default:
-      return x;
-  }
-}
 
 // Load up to 32 consecutive elements starting at p (16-byte aligned when valid >= 32).
 template <typename T>
@@ -413,6 +400,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           float v[32];
           tmem_ld_32x32(trow + col0, r);
           if (p.dual) {
+            // act(gate) * up with the glu kernels' arithmetic (vec.cuh act_only: one ex2 + one rcp per element)
             uint32_t r2[32];
             tmem_ld_32x32(trow + 128 + col0, r2);
             tmem_ld_wait();
@@ -426,8 +414,49 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
               store_row32_any(p.aux, aux_row + n, p.d_fp32, valid, g);
               store_row32_any(p.aux2, aux_row + n, p.d_fp32, valid, u);
             }
+            if (p.act == B200_ACT_SILU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(g[j], p.act) * u[j];
+              for (int j = 0; j < 32; ++j) v[j] = act_only<4>(g[j], 4) * u[j];
+            } else if (p.act == B200_ACT_GELU_TANH) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = act_only<2>(g[j], 2) * u[j];
+            } else {
+              act_fwd_n(g, p.act);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = g[j] * u[j];
+            }
+          } else if (p.glu_bwd) {
+            // accumulator = dh (gradient of act(g) * u): D <- dg = dh * u * act'(g), d2 <- du = dh * act(g)
+            tmem_ld_wait();
+            float g[32], u[32];
+            const long long grow = static_cast<long long>(row) * p.glu_ld + n;
+            if (row_ok && valid > 0) {
+              load_row32_any(p.glu_g, grow, 0, valid, g);
+              load_row32_any(p.glu_u, grow, 0, valid, u);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) g[j] = u[j] = 0.0f;
+            }
+            if (p.act == B200_ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float dh = __uint_as_float(r[j]) * p.alpha;
+                float f, df;
+                act_pair<4>(g[j], 4, f, df);
+                v[j] = dh * u[j] * df;
+                u[j] = dh * f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float dh = __uint_as_float(r[j]) * p.alpha;
+                float f, df;
+                act_pair<2>(g[j], 2, f, df);
+                v[j] = dh * u[j] * df;
+                u[j] = dh * f;
+              }
+            }
+            if (row_ok && valid > 0) store_row32_any(p.d2, grow, 0, valid, u);
           } else {
             tmem_ld_wait();
 #pragma unroll
@@ -439,10 +468,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
               for (int j = 0; j < 32; ++j) v[j] += bv[j];
             }
             if (p.aux != nullptr && row_ok && valid > 0) store_row32_any(p.aux, aux_row + n, p.d_fp32, valid, v);
-            if (p.act != B200_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-            }
+            if (p.act != B200_ACT_NONE) act_fwd_n(v, p.act);     // ONE dispatch per 32 columns (see vec.cuh)
           }
           if (p.res != nullptr && row_ok && valid > 0) {
             float rv[32];
@@ -606,16 +632,6 @@ static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
   return 0;
 }
 
-// experiment: CTA pairs with 256 x 128 tiles when block_n = 128 is requested explicitly (B200_GEMM_PAIR128=1)
-static bool use_pair128() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B200_GEMM_PAIR128");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
 static bool use_cta_pairs() {
   static int v = -1;
   if (v < 0) {
@@ -663,7 +679,9 @@ int b200_gemm(const b200_gemm_args* a, void* stream_) {
   kp.n_per_tile = a->dual_b ? 128 : bn;
   // CTA pairs (256-row tiles) for the large GEMMs: every MN-major operand must be 5-D describable
   const int atom_e = 128 / es;
-  const bool pair = use_cta_pairs() && (bn == 256 || (bn == 128 && use_pair128() && !a->dual_b)) && a->m >= 1024 && (!a->a_mn_major || a->m % atom_e == 0) &&
+  // (256 x 128 pair tiles were measured at 0.6x the 256 x 256 rate on the N = 3584 shapes: operand traffic per FLOP is
+  // 1.5x, the kernel turns shared-memory bound; the partial last wave of 256-wide tiles costs less)
+  const bool pair = use_cta_pairs() && bn == 256 && a->m >= 1024 && (!a->a_mn_major || a->m % atom_e == 0) &&
                     (!a->b_mn_major || a->n % atom_e == 0) && a->block_n >= 0;
   kp.m_blocks = (int)ceil_div(a->m, pair ? 2 * kBlockM : kBlockM);
   kp.n_blocks = (int)ceil_div(a->n, kp.n_per_tile);
@@ -697,6 +715,20 @@ int b200_gemm(const b200_gemm_args* a, void* stream_) {
   kp.ab_fp32 = fp32;
   kp.d_fp32 = a->d_dtype == B200_F32;
   kp.dual = a->dual_b ? 1 : 0;
+  kp.glu_bwd = a->glu_bwd ? 1 : 0;
+  kp.glu_g = a->glu_g;
+  kp.glu_u = a->glu_u;
+  kp.d2 = a->d2;
+  kp.glu_ld = a->glu_ld;
+  if (kp.glu_bwd) {
+    B200_CHECK(!kp.dual && a->glu_g != nullptr && a->glu_u != nullptr && a->d2 != nullptr && a->d_dtype == B200_BF16 &&
+                   a->residual == nullptr && a->bias == nullptr && a->aux == nullptr && z_lo == 1 && z_hi == 1,
+               "b200_gemm: glu_bwd needs bf16 g / u / d2 and a plain (unbatched, no bias / residual / aux) GEMM");
+    B200_CHECK(a->act == B200_ACT_SILU || a->act == B200_ACT_GELU_TANH, "b200_gemm: glu_bwd supports SiLU and tanh-GELU");
+    B200_CHECK(a->glu_ld % 8 == 0 && ((reinterpret_cast<uintptr_t>(a->glu_g) | reinterpret_cast<uintptr_t>(a->glu_u) |
+                                       reinterpret_cast<uintptr_t>(a->d2)) & 15) == 0,
+               "b200_gemm: glu_bwd operands must be 16-byte aligned rows");
+  }
   kp.alpha = a->alpha == 0.0f ? 1.0f : a->alpha;
   kp.bias = a->bias;
   kp.bias_fp32 = a->bias_dtype == B200_F32;
@@ -765,7 +797,7 @@ int b200_gemm(const b200_gemm_args* a, void* stream_) {
     case 64:
       return launch_gemm<64, 1>(kp, stream);
     case 128:
-      return pair ? launch_gemm<128, 2>(kp, stream) : launch_gemm<128, 1>(kp, stream);
+      return launch_gemm<128, 1>(kp, stream);
     default:
       return pair ? launch_gemm<256, 2>(kp, stream) : launch_gemm<256, 1>(kp, stream);
   }

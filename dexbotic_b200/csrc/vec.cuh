@@ -84,51 +84,131 @@ __device__ __forceinline__ float block_sum(float v, float* red /* >= 33 floats s
   return red[32];
 }
 
-__device__ __forceinline__ float act_fwd(float x, int act) {
-  switch (act) {
-    case 1:  // gelu erf
-      return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-    case 2: {  // gelu tanh
-      float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-      return 0.5f * x * (1.0f + tanhf(u));
-    }
-    case 3:  // quick gelu
-      return x / (1.0f + __expf(-1.702f * x));
-    case 4:  // silu
-      return x / (1.0f + __expf(-x));
-    case 5:
-      return fmaxf(x, 0.0f);
-    default:
-      return x;
+// Activations (codes: dexbotic_b200.h B200_ACT_*).  The templated forms are the arithmetic; the runtime forms dispatch
+// once per call.  Kernels must dispatch once per PACK / register array (act_fwd_n, act_grad_mul_n), never per element:
+// a switch inside an unrolled element loop compiles to one indirect branch (BRX) per element.
+template <int kAct>
+__device__ __forceinline__ float act_fwd_t(float x) {
+  if constexpr (kAct == 1) {          // gelu erf
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  } else if constexpr (kAct == 2) {   // gelu tanh
+    const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+    return 0.5f * x * (1.0f + tanhf(u));
+  } else if constexpr (kAct == 3) {   // quick gelu
+    return x / (1.0f + __expf(-1.702f * x));
+  } else if constexpr (kAct == 4) {   // silu
+    return x / (1.0f + __expf(-x));
+  } else if constexpr (kAct == 5) {
+    return fmaxf(x, 0.0f);
+  } else {
+    return x;
   }
 }
 // d act(x) / dx
+template <int kAct>
+__device__ __forceinline__ float act_grad_t(float x) {
+  if constexpr (kAct == 1) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+  } else if constexpr (kAct == 2) {
+    const float x2 = x * x;
+    const float u = 0.7978845608028654f * (x + 0.044715f * x * x2);
+    const float t = tanhf(u);
+    const float du = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x2);
+    return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+  } else if constexpr (kAct == 3) {
+    const float sg = 1.0f / (1.0f + __expf(-1.702f * x));
+    return sg + 1.702f * x * sg * (1.0f - sg);
+  } else if constexpr (kAct == 4) {
+    const float sg = 1.0f / (1.0f + __expf(-x));
+    return sg + x * sg * (1.0f - sg);
+  } else if constexpr (kAct == 5) {
+    return x > 0.0f ? 1.0f : 0.0f;
+  } else {
+    return 1.0f;
+  }
+}
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  switch (act) {
+    case 1: return act_fwd_t<1>(x);
+    case 2: return act_fwd_t<2>(x);
+    case 3: return act_fwd_t<3>(x);
+    case 4: return act_fwd_t<4>(x);
+    case 5: return act_fwd_t<5>(x);
+    default: return x;
+  }
+}
 __device__ __forceinline__ float act_grad(float x, int act) {
   switch (act) {
-    case 1: {
-      float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-      float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-      return cdf + x * pdf;
-    }
-    case 2: {
-      float x2 = x * x;
-      float u = 0.7978845608028654f * (x + 0.044715f * x * x2);
-      float t = tanhf(u);
-      float du = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x2);
-      return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
-    }
-    case 3: {
-      float s = 1.0f / (1.0f + __expf(-1.702f * x));
-      return s + 1.702f * x * s * (1.0f - s);
-    }
-    case 4: {
-      float s = 1.0f / (1.0f + __expf(-x));
-      return s + x * s * (1.0f - s);
-    }
-    case 5:
-      return x > 0.0f ? 1.0f : 0.0f;
-    default:
-      return 1.0f;
+    case 1: return act_grad_t<1>(x);
+    case 2: return act_grad_t<2>(x);
+    case 3: return act_grad_t<3>(x);
+    case 4: return act_grad_t<4>(x);
+    case 5: return act_grad_t<5>(x);
+    default: return 1.0f;
+  }
+}
+// v[j] = act(v[j]) / d[j] *= act'(x[j]) over a register array, one dispatch for the whole array
+#define B200_ACT_CASE_N(K, BODY)   \
+  case K: {                        \
+    _Pragma("unroll") for (int j = 0; j < N; ++j) { BODY; } \
+    break;                         \
+  }
+template <int N>
+__device__ __forceinline__ void act_fwd_n(float (&v)[N], int act) {
+  switch (act) {
+    B200_ACT_CASE_N(1, v[j] = act_fwd_t<1>(v[j]))
+    B200_ACT_CASE_N(2, v[j] = act_fwd_t<2>(v[j]))
+    B200_ACT_CASE_N(3, v[j] = act_fwd_t<3>(v[j]))
+    B200_ACT_CASE_N(4, v[j] = act_fwd_t<4>(v[j]))
+    B200_ACT_CASE_N(5, v[j] = act_fwd_t<5>(v[j]))
+    default: break;
+  }
+}
+template <int N>
+__device__ __forceinline__ void act_grad_mul_n(float (&d)[N], const float (&x)[N], int act) {
+  switch (act) {
+    B200_ACT_CASE_N(1, d[j] *= act_grad_t<1>(x[j]))
+    B200_ACT_CASE_N(2, d[j] *= act_grad_t<2>(x[j]))
+    B200_ACT_CASE_N(3, d[j] *= act_grad_t<3>(x[j]))
+    B200_ACT_CASE_N(4, d[j] *= act_grad_t<4>(x[j]))
+    B200_ACT_CASE_N(5, d[j] *= act_grad_t<5>(x[j]))
+    default: break;
+  }
+}
+#undef B200_ACT_CASE_N
+
+// act(x) and act'(x) together.  kAct = 4 (SiLU) / 2 (tanh-GELU) are the bf16 fast paths: one MUFU.EX2 + one MUFU.RCP
+// per element instead of two exponentials and IEEE divisions — at 8 elements per 16-byte pack the
+// generic path is MUFU-bound, not HBM-bound.  Their error (2 ulp fp32) vanishes in the bf16 rounding of the outputs.
+// kAct = -1: the exact runtime-dispatched functions (fp32 tensors, other activations).
+template <int kAct>
+__device__ __forceinline__ void act_pair(float x, int act, float& f, float& df) {
+  if constexpr (kAct == 4) {
+    const float s = __fdividef(1.0f, 1.0f + __expf(-x));
+    f = x * s;
+    df = s + f * (1.0f - s);
+  } else if constexpr (kAct == 2) {
+    const float x2 = x * x;
+    // tanh(u) = 1 - 2 / (1 + e^{2u}): one ex2 + one rcp, ~2 ulp (tanh.approx.f32 would be 2^-11)
+    const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * 0.7978845608028654f * (x + 0.044715f * x * x2)));
+    f = 0.5f * x * (1.0f + t);
+    df = 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * 0.7978845608028654f * (1.0f + 0.134145f * x2);
+  } else {
+    f = act_fwd(x, act);
+    df = act_grad(x, act);
+  }
+}
+template <int kAct>
+__device__ __forceinline__ float act_only(float x, int act) {
+  if constexpr (kAct == 4) {
+    return x * __fdividef(1.0f, 1.0f + __expf(-x));
+  } else if constexpr (kAct == 2) {
+    const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * 0.7978845608028654f * (x + 0.044715f * x * x * x)));
+    return 0.5f * x * (1.0f + t);
+  } else {
+    return act_fwd(x, act);
   }
 }
 

@@ -167,13 +167,24 @@ def block_forward(x2d: torch.Tensor, bw: BlockW, env: AttnEnv, mode: str):
     h2, st2 = norm_fwd(x1, bw.norm2)
     saved, y = None, None
     if c.mlp == "glu":
-        g, _ = linear_fwd(h2, bw.gate)
-        u, _ = linear_fwd(h2, bw.up)
+        fused = (bw.gate.b is None and bw.up.b is None
+                 and ops.glu_fusable(h2, bw.gate.w, bw.up.w, bw.down.w, c.act))
+        if fused:
+            # ONE GEMM against gate and up (CTA pair: rank 0 stages gate columns, rank 1 up columns); its epilogue
+            # writes act(g) * u and, for backward, the two pre-activations.  hm is kept: the backward's down-projection
+            # dgrad produces dg / du in its epilogue and no longer recomputes it.
+            g = torch.empty((h2.shape[0], bw.gate.w.shape[0]), device=h2.device, dtype=h2.dtype) if keep else None
+            u = torch.empty_like(g) if keep else None
+            hm = ops.gemm_dual(h2, bw.gate.w, bw.up.w, c.act, aux_gate=g, aux_up=u)
+        else:
+            g, _ = linear_fwd(h2, bw.gate)
+            u, _ = linear_fwd(h2, bw.up)
+            hm = ops.glu_fwd(g, u, c.act) if mode != "saved" else None
         if mode != "saved":
-            hm = ops.glu_fwd(g, u, c.act)
             y, _ = linear_fwd(hm, bw.down, residual=x1)
         if keep:
-            saved = dict(st1=st1, qkv=qkv, probs=probs, attn=attn2d, x1=x1, st2=st2, g=g, u=u, sh=sh)
+            saved = dict(st1=st1, qkv=qkv, probs=probs, attn=attn2d, x1=x1, st2=st2, g=g, u=u, sh=sh,
+                         hm=hm if fused else None)
     else:
         hm, pre = linear_fwd(h2, bw.fc1, act=c.act, want_aux=keep)
         if mode != "saved":
@@ -193,10 +204,15 @@ def block_backward(store: ParamStore, dy: torch.Tensor, x2d: torch.Tensor, bw: B
         h2, _ = norm_fwd(s["x1"], bw.norm2)
     # ---- MLP
     if c.mlp == "glu":
-        dhm = linear_dgrad(dy, bw.down)                                  # [M, inter]
-        # one pass: dg, du (in place over g / u) and hm = act(g)*u (in place over dhm) for the down wgrad
-        dg, du = ops.glu_bwd(dhm, s["g"], s["u"], c.act, dg=s["g"], du=s["u"], h_out=dhm)
-        linear_wgrad(store, dy, dhm, bw.down)
+        if s.get("hm") is not None:
+            # fused: dgrad of the down projection with the GLU backward in its epilogue (dg / du in place over g / u)
+            linear_wgrad(store, dy, s["hm"], bw.down)
+            dg, du = ops.gemm_glu_bwd(dy, bw.down.w, s["g"], s["u"], c.act, dg=s["g"], du=s["u"])
+        else:
+            dhm = linear_dgrad(dy, bw.down)                                  # [M, inter]
+            # one pass: dg, du (in place over g / u) and hm = act(g)*u (in place over dhm) for the down wgrad
+            dg, du = ops.glu_bwd(dhm, s["g"], s["u"], c.act, dg=s["g"], du=s["u"], h_out=dhm)
+            linear_wgrad(store, dy, dhm, bw.down)
         linear_wgrad(store, dg, h2, bw.gate)
         linear_wgrad(store, du, h2, bw.up)
         dh2 = linear_dgrad(dg, bw.gate)

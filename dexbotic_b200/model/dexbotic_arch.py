@@ -353,11 +353,14 @@ class Decoder:
 
 
 def kept_bytes_per_block(bc: BlockCfg, B: int, S: int, es: int = 2) -> int:
-    """Bytes a block keeps alive when it is NOT recomputed: qkv, probs, attn, x1 and the MLP pre-activations."""
+    """Bytes a block keeps alive when it is NOT recomputed: qkv, attn, x1, the MLP pre-activations (GLU: g, u and
+    act(g) * u, which the fused down-projection backward reads instead of recomputing it) and the attention statistics
+    (bf16: one fp32 log-sum-exp per row — flash attention; fp32 blocks keep the probabilities)."""
     M = B * S
     W = (bc.heads + 2 * bc.kv_heads) * bc.head_dim
-    inter = 2 * bc.inter if bc.mlp == "glu" else bc.inter
-    return es * M * (W + bc.heads * bc.head_dim + bc.d + inter) + es * B * bc.heads * S * ((S + 7) // 8 * 8)
+    inter = 3 * bc.inter if bc.mlp == "glu" else bc.inter
+    stats = 4 * B * bc.heads * S if es == 2 else es * B * bc.heads * S * ((S + 7) // 8 * 8)
+    return es * M * (W + bc.heads * bc.head_dim + bc.d + inter) + stats
 
 
 def plan_keep_layers(store: ParamStore, bc: BlockCfg, n_layers: int, B: int, S: int, device, reserve_gb: float = 14.0) -> int:

@@ -338,16 +338,23 @@ class MoTLayerFn(torch.autograd.Function):
                 x1 = gated_residual(x, y_o, ad[0][:, 2 * w_:], B)
                 h2, s2 = norm_fwd(x1, sw.norm2)
                 h2 = ada_apply(h2, ad[1], B)
-            g, _ = linear_fwd(h2, sw.gate)
-            u, _ = linear_fwd(h2, sw.up)
-            hm = ops.glu_fwd(g, u, env.act)
+            fused = (sw.gate.b is None and sw.up.b is None
+                     and ops.glu_fusable(h2, sw.gate.w, sw.up.w, sw.down.w, env.act))
+            if fused:         # one GEMM against gate and up, GeGLU in its epilogue (functional.block_forward)
+                g = torch.empty((h2.shape[0], sw.gate.w.shape[0]), device=h2.device, dtype=h2.dtype)
+                u = torch.empty_like(g)
+                hm = ops.gemm_dual(h2, sw.gate.w, sw.up.w, env.act, aux_gate=g, aux_up=u)
+            else:
+                g, _ = linear_fwd(h2, sw.gate)
+                u, _ = linear_fwd(h2, sw.up)
+                hm = ops.glu_fwd(g, u, env.act)
             if ad is None:
                 y, _ = linear_fwd(hm, sw.down, residual=x1)
             else:
                 y_m, _ = linear_fwd(hm, sw.down)
                 y = gated_residual(x1, y_m, ad[1][:, 2 * w_:], B)
             outs.append(y)
-            keep.append(dict(a=a, x1=x1, s2=s2, g=g, u=u, y_o=y_o, y_m=y_m))
+            keep.append(dict(a=a, x1=x1, s2=s2, g=g, u=u, y_o=y_o, y_m=y_m, hm=hm if fused else None))
         if mod1 is not None:
             ctx.save_for_backward(x_p, x_s, mod1, mod2)
         else:
@@ -384,9 +391,13 @@ class MoTLayerFn(torch.autograd.Function):
                 dym = (dy.view(B, -1, w_) * ad[1][:, None, 2 * w_:]).view(-1, w_).contiguous()
             else:
                 dym = dy
-            dhm = linear_dgrad(dym, sw.down)
-            dg, du = ops.glu_bwd(dhm, kp["g"], kp["u"], env.act, dg=kp["g"], du=kp["u"], h_out=dhm)
-            linear_wgrad(store, dym, dhm, sw.down)
+            if kp.get("hm") is not None:      # down-projection dgrad with the GLU backward in its epilogue
+                linear_wgrad(store, dym, kp["hm"], sw.down)
+                dg, du = ops.gemm_glu_bwd(dym, sw.down.w, kp["g"], kp["u"], env.act, dg=kp["g"], du=kp["u"])
+            else:
+                dhm = linear_dgrad(dym, sw.down)
+                dg, du = ops.glu_bwd(dhm, kp["g"], kp["u"], env.act, dg=kp["g"], du=kp["u"], h_out=dhm)
+                linear_wgrad(store, dym, dhm, sw.down)
             linear_wgrad(store, dg, h2, sw.gate)
             linear_wgrad(store, du, h2, sw.up)
             dh2 = linear_dgrad(dg, sw.gate)

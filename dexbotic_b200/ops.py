@@ -8,6 +8,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional
 
+import os
+
 import torch
 
 from . import _lib
@@ -140,6 +142,47 @@ def gemm_dual(a: torch.Tensor, b_gate: torch.Tensor, b_up: torch.Tensor, act, *,
     g.dual_b = 1
     _lib.check(_lib.load().b200_gemm(C.byref(g), _stream()), "gemm_dual")
     return out
+
+
+def glu_fusable(x2d: torch.Tensor, w_gate: torch.Tensor, w_up: torch.Tensor, w_down: torch.Tensor, act) -> bool:
+    """True when the gate / up / down projections of a GLU MLP can run as the two fused GEMMs (gemm_dual with the
+    pre-activations kept, gemm_glu_bwd): bf16, SiLU or tanh-GELU, TMA-describable operands (B200_FUSED_GLU=0: off)."""
+    if os.environ.get("B200_FUSED_GLU", "1") == "0":
+        return False
+    if x2d.dtype != torch.bfloat16 or act_code(act) not in (2, 4):
+        return False
+    inter, d = w_gate.shape
+    return (d % 64 == 0 and inter % 64 == 0 and w_gate.stride(0) == w_up.stride(0) and w_gate.stride(1) == 1
+            and all(t.data_ptr() % 16 == 0 for t in (x2d, w_gate, w_up, w_down)) and x2d.stride(1) == 1
+            and x2d.stride(0) % 8 == 0 and w_down.stride(0) % 8 == 0 and w_gate.stride(0) % 8 == 0)
+
+
+def gemm_glu_bwd(dy: torch.Tensor, w_down: torch.Tensor, g: torch.Tensor, u: torch.Tensor, act, *,
+                 dg: Optional[torch.Tensor] = None, du: Optional[torch.Tensor] = None):
+    """(dg, du) of h = act(g) * u given dy of y = h @ w_down^T: the dgrad GEMM dh = dy @ w_down with the GLU backward in
+    its epilogue (dh never reaches HBM).  dg / du may alias g / u (in-place)."""
+    _cuda(dy, w_down, g, u, dg, du)
+    M, d = dy.shape
+    inter = w_down.shape[1]
+    assert w_down.shape == (d, inter) and g.shape == u.shape == (M, inter) and g.dtype == u.dtype == dy.dtype == torch.bfloat16
+    assert g.stride(1) == 1 and u.stride(1) == 1 and g.stride(0) == u.stride(0)
+    dg = torch.empty_like(g) if dg is None else dg
+    du = torch.empty_like(u) if du is None else du
+    assert dg.stride() == g.stride() and du.stride() == g.stride()
+    a = GemmArgs()
+    a.a, a.b, a.d = dy.data_ptr(), w_down.data_ptr(), dg.data_ptr()
+    a.ab_dtype, a.d_dtype = _dt(dy), _dt(dg)
+    a.a_mn_major, a.b_mn_major = 0, 1                      # dh = dy [M, d] @ w_down [d, inter]: B is N-contiguous
+    a.m, a.n, a.k = M, inter, d
+    a.a_ld, a.b_ld, a.d_ld = dy.stride(0), w_down.stride(0), dg.stride(0)
+    a.z_lo = a.z_hi = a.k_segs = 1
+    a.a_z2 = a.b_z2 = 1
+    a.a_div = a.a_mul = a.b_div = a.b_mul = 1
+    a.alpha = 1.0
+    a.act = act_code(act)
+    a.glu_bwd, a.glu_g, a.glu_u, a.d2, a.glu_ld = 1, g.data_ptr(), u.data_ptr(), du.data_ptr(), g.stride(0)
+    _lib.check(_lib.load().b200_gemm(C.byref(a), _stream()), "gemm_glu_bwd")
+    return dg, du
 
 
 def gemm_raw(**kw) -> None:

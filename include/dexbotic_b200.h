@@ -98,6 +98,14 @@ typedef struct {
   int32_t act;
   int32_t dual_b;
   int32_t block_n; /* 0 = auto; 64 / 128 / 256 */
+  /* glu_bwd: the accumulator is dh = d(act(g) * u); the epilogue writes D = dg = dh * u * act'(g) and d2 = du =
+   * dh * act(g) (bf16, rows of glu_ld elements; g / u may alias D / d2: every element is read before it is written
+   * by the same thread).  Replaces the glu_bwd kernel after the down-projection dgrad (HF Qwen2MLP / GemmaMLP). */
+  int32_t glu_bwd;
+  const void* glu_g;
+  const void* glu_u;
+  void* d2;
+  int64_t glu_ld;
 } b200_gemm_args;
 
 int b200_gemm(const b200_gemm_args* args, void* stream);

@@ -122,6 +122,28 @@ def test_gemm_dual(act, M):
     _check(out, f(g) * u, K, torch.bfloat16, "dual out")
 
 
+@pytest.mark.parametrize("act", ["silu", "gelu_tanh"])
+@pytest.mark.parametrize("M", [300, 1411])
+def test_gemm_glu_bwd(act, M):
+    """Down-projection dgrad with the GLU backward in its epilogue (dh = dy @ W_down never stored): dg = dh * u * act'(g),
+    du = dh * act(g), against torch autograd in fp32; out of place and in place over g / u."""
+    o = ops()
+    inter, d = 648 + 120, 256
+    dy = _rand((M, d), torch.bfloat16, 15)
+    wd = _rand((d, inter), torch.bfloat16, 16, 0.1)
+    g, u = _rand((M, inter), torch.bfloat16, 17), _rand((M, inter), torch.bfloat16, 18)
+    gr, ur = g.float().requires_grad_(True), u.float().requires_grad_(True)
+    f = torch.nn.functional.silu if act == "silu" else (lambda x: torch.nn.functional.gelu(x, approximate="tanh"))
+    dh = dy.float() @ wd.float()
+    (f(gr) * ur).backward(dh)
+    dg, du = o.gemm_glu_bwd(dy, wd, g, u, act)
+    _check(dg, gr.grad, d, torch.bfloat16, "glu_bwd dg")
+    _check(du, ur.grad, d, torch.bfloat16, "glu_bwd du")
+    g2, u2 = g.clone(), u.clone()
+    o.gemm_glu_bwd(dy, wd, g2, u2, act, dg=g2, du=u2)
+    assert torch.equal(g2, dg) and torch.equal(u2, du)
+
+
 @pytest.mark.parametrize("M,N,K", [(33, 7, 384), (2176, 384, 7), (5, 768, 256)])
 def test_gemm_simt_odd_shapes(M, N, K):
     o = ops()
@@ -324,6 +346,31 @@ def test_adamw_matches_torch():
         o.adamw_(p, g, m, v, shadow, 1e-3, 0.9, 0.95, 1e-8, 0.1, step, clip)
     assert (p - ref_p.data).abs().max().item() < 1e-5
     assert torch.equal(shadow, p.to(torch.bfloat16))
+
+
+def test_adamw_device_scalars_equal_host_scalars():
+    """b200_adamw_dev reads the seven scalars from device memory (a captured optimizer is replayed with new learning
+    rates): bit-identical to b200_adamw; step 0 is the identity update."""
+    o = ops()
+    n = 50021
+    p1 = _rand((n,), torch.float32, 80)
+    p2 = p1.clone()
+    m1, v1, m2, v2 = (torch.zeros_like(p1) for _ in range(4))
+    s1 = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    s2 = torch.empty_like(s1)
+    clip = torch.full((), 0.7, device=DEV)
+    host = torch.zeros(8)
+    for step in range(1, 4):
+        g = _rand((n,), torch.bfloat16, 80 + step)
+        lr = 1e-3 / step
+        o.adamw_(p1, g, m1, v1, s1, lr, 0.9, 0.95, 1e-8, 0.1, step, clip)
+        o.adamw_hyper_(host, lr, 0.9, 0.95, 1e-8, 0.1, step)
+        o.adamw_dev_(p2, g, m2, v2, s2, host.cuda(), clip)
+        assert torch.equal(p1, p2) and torch.equal(m1, m2) and torch.equal(v1, v2) and torch.equal(s1, s2)
+    o.adamw_hyper_(host, 1e-3, 0.9, 0.95, 1e-8, 0.1, 0)
+    before = (p2.clone(), m2.clone(), v2.clone())
+    o.adamw_dev_(p2, g, m2, v2, s2, host.cuda(), clip)
+    assert torch.equal(p2, before[0]) and torch.equal(m2, before[1]) and torch.equal(v2, before[2])
 
 
 # --------------------------------------------------------------- index kernels
