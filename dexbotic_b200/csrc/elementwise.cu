@@ -23,32 +23,88 @@ static inline int grid_for_rows(int64_t rows, int per_sm = 8) {
 }
 
 // ------------------------------------------------------------------ RMSNorm
+// Eight elements held as loaded (prefetch registers: the NEXT row's loads are in flight while this row is reduced).
 template <typename T>
+struct Raw8;
+template <>
+struct Raw8<bf16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const bf16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+};
+template <>
+struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = reinterpret_cast<const float4*>(p)[0];
+    b = reinterpret_cast<const float4*>(p)[1];
+  }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
+// One block per row, kPacks packs of 8 columns per thread held in registers: x is read ONCE, and the loads of the
+// block's next row are issued before this row's reduction (a row is ~7 KB: with one row in flight per block the kernel
+// was latency-bound at 0.59 of the copy bandwidth).
+template <typename T, int kPacks>
 __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w,
                                                           T* __restrict__ y, float* __restrict__ rstd, int M, int D,
                                                           float eps, int unit_offset) {
   __shared__ float red[33];
-  for (int row = blockIdx.x; row < M; row += gridDim.x) {
-    const T* xr = x + (size_t)row * D;
-    T* yr = y + (size_t)row * D;
-    float ss = 0.0f;
-    for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
-      float v[8];
-      Pack8<T>::load(xr + i, v);
+  Raw8<T> nx[kPacks];
+  int row = blockIdx.x;
+  if (row < M) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
+    for (int k = 0; k < kPacks; ++k) {
+      const int i = (threadIdx.x + k * blockDim.x) * 8;
+      if (i < D) nx[k].load(x + (size_t)row * D + i);
+    }
+  }
+  for (; row < M; row += gridDim.x) {
+    float xv[kPacks][8];
+    float ss = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kPacks; ++k) {
+      const int i = (threadIdx.x + k * blockDim.x) * 8;
+      if (i < D) {
+        nx[k].unpack(xv[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += xv[k][j] * xv[k][j];
+      }
+    }
+    const int nrow = row + gridDim.x;
+    if (nrow < M) {
+#pragma unroll
+      for (int k = 0; k < kPacks; ++k) {
+        const int i = (threadIdx.x + k * blockDim.x) * 8;
+        if (i < D) nx[k].load(x + (size_t)nrow * D + i);
+      }
     }
     ss = block_sum(ss, red);
     const float r = rsqrtf(ss / (float)D + eps);
     if (threadIdx.x == 0 && rstd != nullptr) rstd[row] = r;
-    for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
-      float v[8], g[8], o[8];
-      Pack8<T>::load(xr + i, v);
-      Pack8<T>::load(w + i, g);
+    T* yr = y + (size_t)row * D;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = unit_offset ? (v[j] * r) * (1.0f + g[j]) : g[j] * round_to<T>(v[j] * r);
-      Pack8<T>::store(yr + i, o);
+    for (int k = 0; k < kPacks; ++k) {
+      const int i = (threadIdx.x + k * blockDim.x) * 8;
+      if (i < D) {
+        float g[8], o[8];
+        Pack8<T>::load(w + i, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = unit_offset ? (xv[k][j] * r) * (1.0f + g[j]) : g[j] * round_to<T>(xv[k][j] * r);
+        Pack8<T>::store(yr + i, o);
+      }
     }
   }
 }
@@ -71,20 +127,49 @@ __global__ void __launch_bounds__(256, kPacks <= 2 ? 3 : 2) rmsnorm_bwd_kernel(
 #pragma unroll
     for (int j = 0; j < 8; ++j) wacc[k][j] = 0.0f;
   }
+  Raw8<T> nx[kPacks], ndy[kPacks];      // the next row's x / dy: in flight during this row's reduction
+  float nr = 0.0f;
+  if ((int)blockIdx.x < M) {
+    nr = rstd[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kPacks; ++k) {
+      const int i = (threadIdx.x + k * blockDim.x) * 8;
+      if (i < D) {
+        nx[k].load(x + (size_t)blockIdx.x * D + i);
+        ndy[k].load(dy + (size_t)blockIdx.x * D + i);
+      }
+    }
+  }
   for (int row = blockIdx.x; row < M; row += gridDim.x) {
-    const T* xr = x + (size_t)row * D;
-    const T* dyr = dy + (size_t)row * D;
     T* dxr = dx + (size_t)row * D;
-    const float r = rstd[row];
+    const float r = nr;
     float xv[kPacks][8], gv[kPacks][8];      // gv = dy * w_eff
     float c = 0.0f;
 #pragma unroll
     for (int k = 0; k < kPacks; ++k) {
       const int i = (threadIdx.x + k * blockDim.x) * 8;
       if (i < D) {
+        nx[k].unpack(xv[k]);
+        ndy[k].unpack(gv[k]);
+      }
+    }
+    const int nrow = row + gridDim.x;
+    if (nrow < M) {
+      nr = rstd[nrow];
+#pragma unroll
+      for (int k = 0; k < kPacks; ++k) {
+        const int i = (threadIdx.x + k * blockDim.x) * 8;
+        if (i < D) {
+          nx[k].load(x + (size_t)nrow * D + i);
+          ndy[k].load(dy + (size_t)nrow * D + i);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kPacks; ++k) {
+      const int i = (threadIdx.x + k * blockDim.x) * 8;
+      if (i < D) {
         float we[8];
-        Pack8<T>::load(xr + i, xv[k]);
-        Pack8<T>::load(dyr + i, gv[k]);
         Pack8<T>::load(w + i, we);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -789,9 +874,18 @@ int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t
                      int unit_offset, int dtype, void* stream) {
   B200_CHECK(D % 8 == 0, "rmsnorm_fwd: D=%lld must be a multiple of 8", (long long)D);
   if (M == 0) return 0;
+  B200_CHECK(D <= 8 * 256 * kMaxPacks, "rmsnorm_fwd: unsupported D=%lld", (long long)D);
   const int nt = norm_threads(D);
-  DISPATCH_T(dtype, (rmsnorm_fwd_kernel<T><<<grid_for_rows(M, 2048 / nt), nt, 0, STREAM>>>(
-                        (const T*)x, (const T*)w, (T*)y, rstd, (int)M, (int)D, eps, unit_offset)));
+  int grid;
+  if (D <= (int64_t)16 * nt) {
+    DISPATCH_T(dtype, grid = resident_grid(rmsnorm_fwd_kernel<T, 2>, nt, M));
+    DISPATCH_T(dtype, (rmsnorm_fwd_kernel<T, 2><<<grid, nt, 0, STREAM>>>((const T*)x, (const T*)w, (T*)y, rstd, (int)M,
+                                                                          (int)D, eps, unit_offset)));
+  } else {
+    DISPATCH_T(dtype, grid = resident_grid(rmsnorm_fwd_kernel<T, kMaxPacks>, nt, M));
+    DISPATCH_T(dtype, (rmsnorm_fwd_kernel<T, kMaxPacks><<<grid, nt, 0, STREAM>>>((const T*)x, (const T*)w, (T*)y, rstd,
+                                                                                  (int)M, (int)D, eps, unit_offset)));
+  }
   B200_LAUNCH_OK();
   return 0;
 }
