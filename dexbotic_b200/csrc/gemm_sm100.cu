@@ -387,6 +387,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       const long long res_row = tc.zh * p.res_s3 + tc.zl * p.res_s2 + static_cast<long long>(row) * p.res_ld;
       const long long aux_row = tc.zh * p.aux_s3 + tc.zl * p.aux_s2 + static_cast<long long>(row) * p.aux_ld;
 
+      // glu_bwd: raw g / u of the NEXT 32 columns, requested one half-chunk ahead (a thread reads its own row: the
+      // loads are latency-, not bandwidth-bound, and would otherwise sit on the epilogue's critical path)
+      uint4 gq[4], uq[4];
+      const long long glu_row = static_cast<long long>(row) * p.glu_ld;
+      auto glu_issue = [&](int col0) {
+        const int n = tc.n0 + col0;
+        if (row_ok && p.N - n >= 32) {
+          const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.glu_g) + glu_row + n);
+          const uint4* up = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.glu_u) + glu_row + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            gq[i] = __ldg(gp + i);
+            uq[i] = __ldg(up + i);
+          }
+        }
+      };
+      if (p.glu_bwd) glu_issue(0);
+
       for (int c = 0; c < p.n_per_tile; c += chunk_cols) {
         if (tc.n0 + c >= p.N) break;  // warp-uniform: fully out-of-range chunk
         if (lane == 0) tma_store_wait_read<1>();
@@ -427,16 +445,31 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             }
           } else if (p.glu_bwd) {
             // accumulator = dh (gradient of act(g) * u): D <- dg = dh * u * act'(g), d2 <- du = dh * act(g)
-            tmem_ld_wait();
             float g[32], u[32];
-            const long long grow = static_cast<long long>(row) * p.glu_ld + n;
-            if (row_ok && valid > 0) {
+            const long long grow = glu_row + n;
+            if (row_ok && valid >= 32) {          // the prefetched raw packs of this half
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gq[i]);
+                const __nv_bfloat162* uh = reinterpret_cast<const __nv_bfloat162*>(&uq[i]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 gf = __bfloat1622float2(gh[e]), uf = __bfloat1622float2(uh[e]);
+                  g[i * 8 + 2 * e] = gf.x;
+                  g[i * 8 + 2 * e + 1] = gf.y;
+                  u[i * 8 + 2 * e] = uf.x;
+                  u[i * 8 + 2 * e + 1] = uf.y;
+                }
+              }
+            } else if (row_ok && valid > 0) {     // ragged last columns
               load_row32_any(p.glu_g, grow, 0, valid, g);
               load_row32_any(p.glu_u, grow, 0, valid, u);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) g[j] = u[j] = 0.0f;
             }
+            if (col0 + 32 < p.n_per_tile) glu_issue(col0 + 32);
+            tmem_ld_wait();
             if (p.act == B200_ACT_SILU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {

@@ -59,6 +59,20 @@ def main():
     u = torch.empty(M, inter, device=dev, dtype=torch.bfloat16)
     t = timeit(lambda: ops.gemm_dual(a, wg, wu, "silu", out=h, aux_gate=g, aux_up=u))
     print(f"dual swiglu + aux: {t:7.3f} ms {fl / t / 1e9:7.1f} TF/s")
+    # GLU backward: dgrad of the down projection + glu_bwd kernel vs the dgrad with the GLU backward in its epilogue
+    dy = torch.randn(M, d, device=dev, dtype=torch.bfloat16)
+    wd = torch.randn(d, inter, device=dev, dtype=torch.bfloat16) * 0.02
+    dh = torch.empty(M, inter, device=dev, dtype=torch.bfloat16)
+    dg, du = torch.empty_like(g), torch.empty_like(u)
+
+    def unfused():
+        ops.gemm(dy, wd, b_mn=True, out=dh)
+        ops.glu_bwd(dh, g, u, "silu", dg=dg, du=du, h_out=dh)
+
+    t1 = timeit(unfused)
+    t2 = timeit(lambda: ops.gemm_glu_bwd(dy, wd, g, u, "silu", dg=dg, du=du))
+    fl2 = 2.0 * M * inter * d
+    print(f"glu bwd: dgrad + glu_bwd kernel {t1:7.3f} ms | fused epilogue {t2:7.3f} ms {fl2 / t2 / 1e9:7.1f} TF/s")
 
 
 if __name__ == "__main__":
