@@ -232,8 +232,11 @@ __device__ __forceinline__ void mma_issue_loop(const GemmKParams& p, uint8_t* sm
   }
 }
 
+// 168 registers (not the 255 a 256-thread CTA may take): one GEMM CTA per SM then leaves ~22 K registers, so the
+// HBM-bound kernels that run beside it on other streams (the overlapped AdamW, the gradient exchange) can be co-resident
+// instead of waiting for a whole SM.
 template <int kBlockN, int kCtas>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
+__global__ void __maxnreg__(168) gemm_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
   using Cfg = GemmCfg<kBlockN, kCtas>;
   const int cta_rank = kCtas == 2 ? (int)cluster_ctarank() : 0;
   const bool leader = cta_rank == 0;

@@ -593,6 +593,17 @@ def adamw_dev_(p32, g, m, v, shadow_bf16, hyper8: torch.Tensor, clip=None):
                                           p32.numel(), hyper8.data_ptr(), _p(clip), _dt(g), _stream()), "adamw_dev")
 
 
+def reduce_scatter_p2p_(own: torch.Tensor, peers: list, scale: float, ctas: int = 16) -> None:
+    """own = scale * (own + sum(peers)) in place, bf16 with fp32 accumulation in list order; `peers` are views of the
+    other ranks' buffers (symmetric memory, peer-mapped).  One small kernel: see csrc/exchange.cu."""
+    _cuda(own, *peers)
+    assert own.dtype == torch.bfloat16 and own.is_contiguous() and all(t.dtype == own.dtype and t.numel() == own.numel()
+                                                                        and t.is_contiguous() for t in peers)
+    arr = (C.c_void_p * len(peers))(*[t.data_ptr() for t in peers])
+    _lib.check(_lib.load().b200_reduce_scatter_p2p(own.data_ptr(), C.cast(arr, C.c_void_p), len(peers), own.numel(),
+                                                   float(scale), int(ctas), _stream()), "reduce_scatter_p2p")
+
+
 def cast_(src, dst):
     _cuda(src, dst)
     assert src.numel() == dst.numel() and src.is_contiguous() and dst.is_contiguous()

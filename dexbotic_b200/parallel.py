@@ -29,6 +29,7 @@ no copies.
 from __future__ import annotations
 
 import bisect
+import os
 from contextlib import contextmanager
 from typing import Callable, Optional
 
@@ -187,6 +188,7 @@ class ShardedDataParallel:
         self.nccl = self.enabled and dist.get_backend(group) == "nccl"
         # kernels (CUDA) — injectable so that the world-size-2 gloo test can drive the host logic with torch stand-ins
         from . import ops
+        self._ops = ops
         self._adamw = adamw_fn or ops.adamw_
         self._sumsq = sumsq_fn or ops.sumsq_
         self._clip = clip_fn or ops.clip_coef
@@ -224,9 +226,11 @@ class ShardedDataParallel:
             self._h_grad = symm_mem.rendezvous(store.grad_a, pg)      # collective: maps every peer's buffer
             self._h_shadow = symm_mem.rendezvous(store.shadow, pg)
             self._comm = torch.cuda.Stream(device=store.device)
-            mx = max((b - a) // self.world for a, b in self.chunks)
-            self._staging = torch.empty((self.world - 1, mx), device=store.device, dtype=torch.bfloat16)
-            self._acc = torch.empty(mx, device=store.device, dtype=torch.float32)
+            # base addresses of every peer's gradient buffer as this process sees them (peer-mapped): the reduce-scatter
+            # kernel loads its pieces straight from them.  Order = rank order after this rank: a fixed summation order.
+            self._peer_grad = [self._h_grad.get_buffer((self.rank + k) % self.world, (store.grad_a.numel(),),
+                                                       torch.bfloat16, 0) for k in range(1, self.world)]
+            self._rs_ctas = int(os.environ.get("B200_RS_CTAS", "16"))
         if self.enabled:
             store.sharder = self
             store.grad_ready_hook = self.on_ready
@@ -248,27 +252,21 @@ class ShardedDataParallel:
         self.reduced = set()
 
     def _reduce_scatter_ce(self, ci: int) -> None:
-        """Copy-engine reduce-scatter of one chunk: after a cross-rank barrier (every rank has enqueued this chunk's
-        wgrads before it), pull piece `rank` out of each peer's gradient buffer, sum in fp32, write the average back
-        in place.  Runs on the exchange stream; the compute stream goes on with the next block's backward."""
+        """Reduce-scatter of one chunk over peer memory: after a cross-rank barrier (every rank has enqueued this
+        chunk's wgrads before it) ONE small kernel (ops.reduce_scatter_p2p_, exchange.cu) loads piece `rank` out of every
+        peer's gradient buffer over NVLink, sums in fp32 in a fixed order and writes the average back in place; a second
+        barrier tells every rank that its chunk has been read.  Runs on the exchange stream; the compute stream goes on
+        with the next block's backward."""
         st = self.store
         pa, pb = self.piece[ci]
-        sz = pb - pa
         cs = self._comm
         cs.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(cs):
             self._h_grad.barrier(channel=0)
-            for step in range(1, self.world):
-                peer = (self.rank - step) % self.world
-                src = self._h_grad.get_buffer(peer, (sz,), torch.bfloat16, pa)
-                self._staging[step - 1, :sz].copy_(src)
+            if pb > pa:
+                self._ops.reduce_scatter_p2p_(st.grad_a[pa:pb], [t[pa:pb] for t in self._peer_grad], 1.0 / self.world,
+                                        ctas=self._rs_ctas)
             self._h_grad.barrier(channel=0)            # every peer has taken its piece of this rank's chunk
-            acc = self._acc[:sz]
-            acc.copy_(st.grad_a[pa:pb])
-            for k in range(self.world - 1):
-                acc.add_(self._staging[k, :sz])
-            acc.mul_(1.0 / self.world)
-            st.grad_a[pa:pb].copy_(acc)
         self.reduced.add(ci)
 
     def _push_shadow_ce(self, ci: int) -> None:

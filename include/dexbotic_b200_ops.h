@@ -249,6 +249,14 @@ int b200_image_preprocess(const uint8_t* src, int64_t B, int64_t H, int64_t W, i
 int b200_action_normalize(const double* x, const double* a, const double* b, float* out, int64_t rows, int64_t D,
                           int quantile, void* stream);
 
+/* ---- data-parallel exchange over peer memory (ZeRO-1 reduce-scatter, parallel.ShardedDataParallel) -------------
+ * own[0..n) = scale * (own + sum_r peer_ptrs[r][0..n))   bf16, fp32 accumulate in the order of peer_ptrs (deterministic).
+ * peer_ptrs: HOST array of n_peers device pointers that are peer-mapped into this process (symmetric memory); the
+ * caller orders the launch after a cross-rank barrier.  ctas: grid size (<= 0: 16) — kept small on purpose, the
+ * persistent GEMM owns the SMs.  Replaces DeepSpeed's reduce-scatter of script/deepspeed/zero2.json. */
+int b200_reduce_scatter_p2p(void* own, const void* const* peer_ptrs, int n_peers, int64_t n, float scale, int ctas,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif
