@@ -391,6 +391,11 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if gemm_timer is not None:
             gemm_timer.enabled = True
+        # `ncu --profile-from-start off ... B200_PROFILER_RANGE=1 python bench.py`: the launch list covers exactly the
+        # device-timed steps (numbers printed by such a run are not bench values)
+        ranged = bool(os.environ.get("B200_PROFILER_RANGE")) and not from_host
+        if ranged:
+            torch.cuda.profiler.start()
         s.record()
         last = None
         for _ in range(n_steps):
@@ -400,6 +405,9 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
                 last = out.loss.item()             # device->host read of the step's result, every step
         model.store.wait_all_params()              # the last step's overlapped optimizer updates belong to this region
         e.record()
+        if ranged:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         if gemm_timer is not None:
             gemm_timer.enabled = False
         sync_all()

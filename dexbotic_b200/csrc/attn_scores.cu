@@ -409,10 +409,12 @@ extern "C" int b200_attn_scores(const void* a, const void* bmat, const void* p_i
   kp.m_tiles = (int)ceil_div(Sq, 128);
   const int sk_pad = (int)((Sk + 63) / 64 * 64);
   const int smem = 1024 + kp.kblocks * (128 * 128 + sk_pad * 128);
-  static int configured = 0;
-  if (configured < smem) {
+  static unsigned long long configured = 0;      // one bit per device ordinal: the attribute is per device
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !((configured >> dev) & 1ull)) {
     B200_CUDA(cudaFuncSetAttribute(attn_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
+    if (dev < 64) configured |= 1ull << dev;
   }
   kp.Z = (int)(B * H);
   B200_CHECK(kp.m_tiles <= 4 && B * H < (1ll << 28), "attn_scores: geometry out of range");

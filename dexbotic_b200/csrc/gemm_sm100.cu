@@ -642,11 +642,13 @@ static int g_sm_limit = 0;
 template <int kBlockN, int kCtas>
 static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
   using Cfg = GemmCfg<kBlockN, kCtas>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;      // one bit per device ordinal: the attribute is per device
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !((configured >> dev) & 1ull)) {
     B200_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kBlockN, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
-    configured = true;
+    if (dev < 64) configured |= 1ull << dev;
   }
   const int sms = (g_sm_limit > 0 && g_sm_limit < num_sms()) ? g_sm_limit : num_sms();
   int units = sms / kCtas;                             // CTAs, or CTA pairs

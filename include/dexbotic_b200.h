@@ -86,7 +86,8 @@ typedef struct {
   int32_t a_div, a_mul, a_seg;
   int32_t b_div, b_mul, b_seg;
   int32_t k_segs;
-  float alpha;
+  float alpha;       /* scale of the accumulator; 0 (a zero-initialised struct) means 1.0 -- a product scaled by zero
+                        is a memset, not a GEMM, so the value is free to mean "unset" */
   const void* bias; /* [n] or NULL */
   int32_t bias_dtype;
   const void* residual; /* same logical shape as D, or NULL; may alias d (accumulate) */
