@@ -298,7 +298,7 @@ def run_ours(args) -> dict:
     want_ce = (world > 1 and os.environ.get("B200_DP", "zero1") == "zero1"
                and os.environ.get("B200_DP_TRANSPORT", "ce") == "ce")
     from dexbotic_b200.params import ParamStore
-    ParamStore.SYMMETRIC = want_ce           # gradient / weight buffers in symmetric memory: copy-engine exchange
+    ParamStore.SYMMETRIC = want_ce           # gradient / weight buffers in symmetric memory: peer-memory exchange
     try:
         model = build_model(w, dev)
     except Exception as e:                   # symmetric allocation unavailable on this box: NCCL transport instead
@@ -364,7 +364,7 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
         try:
             overlap = ShardedDataParallel(model.store)
         except Exception as e:               # peer mapping failed: same sharded optimizer over NCCL
-            print(f"[bench] copy-engine transport unavailable ({type(e).__name__}: {e}); NCCL transport", file=sys.stderr)
+            print(f"[bench] peer-memory transport unavailable ({type(e).__name__}: {e}); NCCL transport", file=sys.stderr)
             overlap = ShardedDataParallel(model.store, transport="nccl")
     else:
         overlap = GradientOverlap(model.store, reserve_sms=int(os.environ.get("B200_DP_RESERVE_SMS", "0")))
@@ -448,7 +448,7 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
     h2d = sum(v.numel() * v.element_size() for v in host.values() if hasattr(v, "numel"))
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     traffic = None
-    tp = ROOT / "profiles" / "r1_gemm_traffic.json"
+    tp = ROOT / "profiles" / "r2_gemm_traffic.json"
     if tp.exists():       # dram__bytes_read+write of one `ncu --set full` capture of the dominant kernel (committed)
         traffic = json.loads(tp.read_text())
     achieved_tf = gemm_flops / gemm_s / 1e12 if gemm_s > 0 else 0.0
@@ -467,8 +467,10 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
                                "(>120 GB for the 7B model), so L2 is cold for the timed kernels",
                    "global_batch": B * world, "seq_len": S,
                    "parallelism": f"dp{world}" + ("" if world == 1 else
-                                                  (" (ZeRO-1 over NVLink copy engines: pull-reduce-scatter of gradients, "
-                                                   "sharded AdamW, push-all-gather of bf16 weights; no SM-resident collective)"
+                                                  (" (ZeRO-1 over NVLink peer memory: one kernel per gradient chunk loads the "
+                                                   "rank's piece from every peer and averages in fp32 [reduce-scatter], "
+                                                   "sharded AdamW, copy-engine push-all-gather of bf16 weights; no NCCL "
+                                                   "kernel on the data path)"
                                                    if getattr(overlap, "ce", False) else
                                                    " (ZeRO-1: NCCL reduce-scatter grads, sharded AdamW, all-gather bf16 weights)")
                                                   if dp_mode == "zero1" else " (gradient all-reduce)"),
@@ -492,16 +494,31 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
         "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        res["cpu_baseline"] = cpu_baseline(w, S, seconds_budget=20.0)
+        res["cpu_baseline"] = cpu_baseline(w, S, seconds_budget=20.0, workload=args.workload)
     if world > 1:
         dist.destroy_process_group()
     return res if rank == 0 else {}
 
 
-def cpu_baseline(w: dict, S: int, seconds_budget: float = 20.0, steps: int = 1) -> dict:
-    """The oracle port (oracle/cpu_baseline.py) timed on this box's host cores on a bounded sample."""
-    from oracle.cpu_baseline import time_cogact_sample
-    return time_cogact_sample(w, S, seconds_budget=seconds_budget, steps=steps)
+def cpu_baseline(w: dict, S: int, seconds_budget: float = 20.0, steps: int = 1, workload: str = "cogact_7b",
+                 limit_s: float = 150.0) -> dict:
+    """The oracle port (oracle/cpu_baseline.py) timed on this box's host cores on a bounded sample.  It runs in a child
+    process under a wall-clock limit: batch 4 first; if the host cannot finish that in `limit_s`, batch 1; if not even
+    that, the line says so instead of stalling the bench."""
+    last = "not run"
+    for batch, lim in ((4, limit_s), (1, limit_s / 2)):
+        try:
+            env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+            env["CUDA_VISIBLE_DEVICES"] = ""
+            r = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", workload, str(S), str(steps), str(batch)],
+                               cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=lim)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode == 0 and lines:
+                return json.loads(lines[-1])
+            last = f"exit {r.returncode}: {r.stderr.strip()[-200:]}"
+        except subprocess.TimeoutExpired:
+            last = f"batch {batch} did not finish in {lim:.0f} s"
+    return {"value": None, "unit": "samples/s", "cores": None, "kind": "port", "sample": f"unavailable ({last})"}
 
 
 def run_reference(args) -> dict:
@@ -512,7 +529,7 @@ def run_reference(args) -> dict:
         return {}
     w = WORKLOADS[args.workload]
     S = 2 + w["instr_tokens"] + w["template_tokens"] - 1 + (w["vision"]["image_size"] // w["vision"]["patch_size"]) ** 2
-    cb = cpu_baseline(w, S, seconds_budget=30.0, steps=max(1, min(args.steps, 3)))
+    cb = cpu_baseline(w, S, seconds_budget=30.0, steps=max(1, min(args.steps, 3)), workload=args.workload, limit_s=240.0)
     return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / cb["value"], 1) if cb["value"] else None,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

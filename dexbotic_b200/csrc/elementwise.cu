@@ -4,6 +4,7 @@
 // include/dexbotic_b200_ops.h next to each entry point.
 #include "../../include/dexbotic_b200_ops.h"
 #include "common.h"
+#include "ptx.cuh"
 #include "vec.cuh"
 
 namespace b200 {
@@ -109,6 +110,74 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const T* __restrict__ 
   }
 }
 
+// Forward with the rows staged in shared memory by the bulk-copy engine (see rmsnorm_bwd_staged_kernel): a ring of
+// kStages rows of x per block, so kStages - 1 rows per block are in flight instead of the one the prefetch registers hold.
+template <typename T, int kPacks, int kStages>
+__global__ void __launch_bounds__(256) rmsnorm_fwd_staged_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                                 T* __restrict__ y, float* __restrict__ rstd, int M,
+                                                                 int D, float eps, int unit_offset) {
+  extern __shared__ __align__(128) unsigned char stage_mem[];
+  __shared__ float red[33];
+  __shared__ __align__(8) uint64_t full[kStages];
+  const uint32_t row_bytes = (uint32_t)D * (uint32_t)sizeof(T);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      const long long row = (long long)blockIdx.x + (long long)s * gridDim.x;
+      if (row < M) {
+        mbar_expect_tx(&full[s], row_bytes);
+        bulk_copy_g2s(stage_mem + (size_t)s * row_bytes, x + (size_t)row * D, row_bytes, &full[s]);
+      }
+    }
+  }
+  int it = 0;
+  for (int row = blockIdx.x; row < M; row += gridDim.x, ++it) {
+    const int s = it % kStages;
+    mbar_wait(&full[s], (uint32_t)(it / kStages) & 1u);
+    const T* sx = reinterpret_cast<const T*>(stage_mem + (size_t)s * row_bytes);
+    float xv[kPacks][8];
+    float ss = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kPacks; ++k) {
+      const int i = (threadIdx.x + k * blockDim.x) * 8;
+      if (i < D) {
+        Pack8<T>::load(sx + i, xv[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += xv[k][j] * xv[k][j];
+      }
+    }
+    ss = block_sum(ss, red);                   // its barriers order every thread's reads of stage s before the refill
+    if (threadIdx.x == 0) {
+      const long long nrow = (long long)row + (long long)kStages * gridDim.x;
+      if (nrow < M) {
+        mbar_expect_tx(&full[s], row_bytes);
+        bulk_copy_g2s(stage_mem + (size_t)s * row_bytes, x + (size_t)nrow * D, row_bytes, &full[s]);
+      }
+    }
+    const float r = rsqrtf(ss / (float)D + eps);
+    if (threadIdx.x == 0 && rstd != nullptr) rstd[row] = r;
+    T* yr = y + (size_t)row * D;
+#pragma unroll
+    for (int k = 0; k < kPacks; ++k) {
+      const int i = (threadIdx.x + k * blockDim.x) * 8;
+      if (i < D) {
+        float g[8], o[8];
+        Pack8<T>::load(w + i, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = unit_offset ? (xv[k][j] * r) * (1.0f + g[j]) : g[j] * round_to<T>(xv[k][j] * r);
+        Pack8<T>::store(yr + i, o);
+      }
+    }
+  }
+}
+
 // dx = r*g - x*r^3*mean(g.x),  g = dy*w_eff ;  dw[col] += sum_rows dy * x * r.
 // x / dy are read once per row (kept in registers between the two phases).  dw partials go to a per-block row of
 // `ws` (no atomics; reduced by colsum afterwards) when a workspace is given, else fp32 atomics.
@@ -187,6 +256,114 @@ __global__ void __launch_bounds__(256, kPacks <= 2 ? 3 : 2) rmsnorm_bwd_kernel(
       if (i < D) {
         float o[8];
         if (accumulate_dx) Pack8<T>::load(dxr + i, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = r * gv[k][j] - xv[k][j] * coef;
+          o[j] = accumulate_dx ? o[j] + t : t;
+        }
+        Pack8<T>::store(dxr + i, o);
+      }
+    }
+  }
+  if (dw != nullptr) {
+#pragma unroll
+    for (int k = 0; k < kPacks; ++k) {
+      const int i = (threadIdx.x + k * blockDim.x) * 8;
+      if (i < D) {
+        if (ws != nullptr) {
+          Pack8<float>::store(ws + (size_t)blockIdx.x * D + i, wacc[k]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(dw + i + j, wacc[k][j]);
+        }
+      }
+    }
+  }
+}
+
+// The same backward with the rows STAGED IN SHARED MEMORY by the bulk-copy engine (cp.async.bulk, mbarrier
+// complete_tx): a ring of kStages rows of (x | dy | dx-to-accumulate) per block, refilled by one thread as soon as the
+// block has consumed a stage.  The register version above can only keep ONE next row in flight per block (the prefetch
+// registers), i.e. ~42 KB per SM at 3 blocks of a 7 KB row x 2 arrays: by Little's law (6.5 TB/s x ~1-2 us) that is half
+// of what the HBM needs — measured 0.51 of the copy peak, and the accumulate variant issued its dx load AFTER the
+// reduction.  Here kStages - 1 rows of all arrays are in flight per block without costing a register.
+template <typename T, int kPacks, int kStages>
+__global__ void __launch_bounds__(256, 3) rmsnorm_bwd_staged_kernel(
+    const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ rstd, T* dx,
+    float* __restrict__ dw, float* __restrict__ ws, int M, int D, int unit_offset, int accumulate_dx) {
+  extern __shared__ __align__(128) unsigned char stage_mem[];
+  __shared__ float red[33];
+  __shared__ __align__(8) uint64_t full[kStages];
+  const float uo = unit_offset ? 1.0f : 0.0f;
+  const uint32_t row_bytes = (uint32_t)D * (uint32_t)sizeof(T);
+  const uint32_t stage_bytes = (accumulate_dx ? 3u : 2u) * row_bytes;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int row, int s) {          // one thread: arm the stage's barrier, then the 2-3 row copies
+    unsigned char* st = stage_mem + (size_t)s * stage_bytes;
+    mbar_expect_tx(&full[s], stage_bytes);
+    bulk_copy_g2s(st, x + (size_t)row * D, row_bytes, &full[s]);
+    bulk_copy_g2s(st + row_bytes, dy + (size_t)row * D, row_bytes, &full[s]);
+    if (accumulate_dx) bulk_copy_g2s(st + 2 * row_bytes, dx + (size_t)row * D, row_bytes, &full[s]);
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      const long long row = (long long)blockIdx.x + (long long)s * gridDim.x;
+      if (row < M) issue((int)row, s);
+    }
+  }
+  float wacc[kPacks][8];
+#pragma unroll
+  for (int k = 0; k < kPacks; ++k) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wacc[k][j] = 0.0f;
+  }
+  int it = 0;
+  for (int row = blockIdx.x; row < M; row += gridDim.x, ++it) {
+    const int s = it % kStages;
+    const float r = rstd[row];
+    mbar_wait(&full[s], (uint32_t)(it / kStages) & 1u);
+    const T* sx = reinterpret_cast<const T*>(stage_mem + (size_t)s * stage_bytes);
+    const T* sdy = sx + D;
+    const T* sdx = sdy + D;
+    float xv[kPacks][8], gv[kPacks][8];      // gv = dy * w_eff
+    Raw8<T> od[kPacks];
+    float c = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kPacks; ++k) {
+      const int i = (threadIdx.x + k * blockDim.x) * 8;
+      if (i < D) {
+        float we[8];
+        Pack8<T>::load(sx + i, xv[k]);
+        Pack8<T>::load(sdy + i, gv[k]);
+        if (accumulate_dx) od[k].load(sdx + i);
+        Pack8<T>::load(w + i, we);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          wacc[k][j] += gv[k][j] * xv[k][j] * r;
+          gv[k][j] *= we[j] + uo;
+          c += gv[k][j] * xv[k][j];
+        }
+      }
+    }
+    c = block_sum(c, red);                    // its barriers also order every thread's reads of stage s before the refill
+    if (threadIdx.x == 0) {
+      const long long nrow = (long long)row + (long long)kStages * gridDim.x;
+      if (nrow < M) issue((int)nrow, s);
+    }
+    const float coef = c * r * r * r / (float)D;
+    T* dxr = dx + (size_t)row * D;
+#pragma unroll
+    for (int k = 0; k < kPacks; ++k) {
+      const int i = (threadIdx.x + k * blockDim.x) * 8;
+      if (i < D) {
+        float o[8];
+        if (accumulate_dx) od[k].unpack(o);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float t = r * gv[k][j] - xv[k][j] * coef;
@@ -868,6 +1045,23 @@ static int resident_grid(K kernel, int nt, int64_t rows) {
   return grid_for_rows(rows, per_sm);
 }
 
+// SM-resident grid of the staged rmsnorm backward (3 blocks of <= 72 KB of stage ring per SM)
+static int g_norm_staged = 1;          // b200_set_norm_staged(0): the register-prefetch kernels (A/B measurements)
+
+template <typename T>
+static int launch_rmsnorm_bwd_staged(const T* dy, const T* x, const T* w, const float* rstd, T* dx, float* dw, float* ws,
+                                     int64_t M, int64_t D, int unit_offset, int accumulate_dx, int nt, size_t smem,
+                                     int* grid_out, cudaStream_t stream) {
+  auto kernel = rmsnorm_bwd_staged_kernel<T, 2, 3>;
+  B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int grid = grid_for_rows(M, per_sm > 16 ? 16 : per_sm);
+  kernel<<<grid, nt, smem, stream>>>(dy, x, w, rstd, dx, dw, ws, (int)M, (int)D, unit_offset, accumulate_dx);
+  *grid_out = grid;
+  return 0;
+}
+
 extern "C" {
 
 int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t M, int64_t D, float eps,
@@ -877,7 +1071,20 @@ int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t
   B200_CHECK(D <= 8 * 256 * kMaxPacks, "rmsnorm_fwd: unsupported D=%lld", (long long)D);
   const int nt = norm_threads(D);
   int grid;
-  if (D <= (int64_t)16 * nt) {
+  const int64_t row_bytes = D * (dtype == B200_BF16 ? 2 : 4);
+  const bool aligned16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && row_bytes % 16 == 0;
+  if (g_norm_staged && D <= (int64_t)16 * nt && aligned16 && 4 * row_bytes <= 48 * 1024) {
+    const size_t smem = (size_t)(4 * row_bytes);           // 4-deep ring of x rows per block
+    DISPATCH_T(dtype, {
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rmsnorm_fwd_staged_kernel<T, 2, 4>, nt, smem) !=
+              cudaSuccess || per_sm < 1)
+        per_sm = 1;
+      grid = grid_for_rows(M, per_sm > 16 ? 16 : per_sm);
+      rmsnorm_fwd_staged_kernel<T, 2, 4><<<grid, nt, smem, STREAM>>>((const T*)x, (const T*)w, (T*)y, rstd, (int)M,
+                                                                     (int)D, eps, unit_offset);
+    });
+  } else if (D <= (int64_t)16 * nt) {
     DISPATCH_T(dtype, grid = resident_grid(rmsnorm_fwd_kernel<T, 2>, nt, M));
     DISPATCH_T(dtype, (rmsnorm_fwd_kernel<T, 2><<<grid, nt, 0, STREAM>>>((const T*)x, (const T*)w, (T*)y, rstd, (int)M,
                                                                           (int)D, eps, unit_offset)));
@@ -887,6 +1094,11 @@ int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t
                                                                                   (int)M, (int)D, eps, unit_offset)));
   }
   B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200_set_norm_staged(int on) {
+  g_norm_staged = on != 0;
   return 0;
 }
 
@@ -904,7 +1116,18 @@ int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* 
   const int nt = norm_threads(D);
   int grid;
   float* ws = dw != nullptr ? workspace : nullptr;
-  if (D <= (int64_t)16 * nt) {
+  // rows staged in shared memory by the bulk-copy engine (3-deep ring per block): every decoder / tower width in bf16
+  const int64_t row_bytes = D * (dtype == B200_BF16 ? 2 : 4);
+  const int64_t stage_smem = 3 * (accumulate_dx ? 3 : 2) * row_bytes;
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) |
+                           reinterpret_cast<uintptr_t>(dx)) & 15) == 0 && row_bytes % 16 == 0;
+  if (g_norm_staged && D <= (int64_t)16 * nt && aligned16 && stage_smem <= 72 * 1024) {
+    int rc;
+    DISPATCH_T(dtype, rc = launch_rmsnorm_bwd_staged<T>((const T*)dy, (const T*)x, (const T*)w, rstd, (T*)dx, dw, ws, M, D,
+                                                        unit_offset, accumulate_dx, nt, (size_t)stage_smem, &grid,
+                                                        STREAM));
+    if (rc) return rc;
+  } else if (D <= (int64_t)16 * nt) {
     DISPATCH_T(dtype, grid = resident_grid(rmsnorm_bwd_kernel<T, 2>, nt, M));
     DISPATCH_T(dtype, (rmsnorm_bwd_kernel<T, 2><<<grid, nt, 0, STREAM>>>(
                           (const T*)dy, (const T*)x, (const T*)w, rstd, (T*)dx, dw, ws, (int)M, (int)D, unit_offset,

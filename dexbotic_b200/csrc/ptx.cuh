@@ -87,6 +87,14 @@ __device__ __forceinline__ void tc_fence_after() {
 }
 
 // ----------------------------------------------------------------------- TMA
+// 1-D bulk copy global -> shared through the TMA unit (SASS: UBLKCP), completing `bytes` on an mbarrier.  Addresses and
+// size must be multiples of 16.  (The .shared::cluster destination form with a CTA-local address is the CTA's own smem.)
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }

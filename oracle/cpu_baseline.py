@@ -107,10 +107,23 @@ def _time_with_layers(w: dict, n_dec: int, steps: int, B: int = 4) -> float:
     return ts[len(ts) // 2]
 
 
-def time_cogact_sample(w: dict, S: int, seconds_budget: float = 20.0, steps: int = 1) -> dict:
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    torch.set_num_threads(cores)          # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every core it may run on
-    B = 4
+def _host_threads() -> int:
+    """Physical cores this process may run on.  torch's own default is that number; torchrun overrides it with
+    OMP_NUM_THREADS=1, and one thread per LOGICAL core (hyper-threads) makes the many small ops of the port slower, not
+    faster, on a 2-socket host."""
+    n_aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False) or n_aff
+    except Exception:
+        phys = max(1, (os.cpu_count() or 2) // 2)
+    return max(1, min(n_aff, phys))
+
+
+def time_cogact_sample(w: dict, S: int, seconds_budget: float = 20.0, steps: int = 1, batch: int = 4) -> dict:
+    cores = _host_threads()
+    torch.set_num_threads(cores)          # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every physical core
+    B = batch
     t1 = _time_with_layers(w, 1, steps, B)
     t2 = _time_with_layers(w, 2, steps, B)
     n = w["llm"]["num_hidden_layers"]
@@ -122,3 +135,19 @@ def time_cogact_sample(w: dict, S: int, seconds_budget: float = 20.0, steps: int
                        f"full-size layers ({t1:.2f}s, {t2:.2f}s per step) and extrapolated linearly to {n} layers "
                        f"-> {total:.1f} s/step of {B} samples"),
             "seconds_per_sample": round(total / B, 3)}
+
+
+def main() -> None:
+    """`python -m oracle.cpu_baseline <workload> <S> <steps> <batch>`: one JSON line.  bench.py runs the CPU arm in this
+    child process under a wall-clock limit, so a slow host can never stall the GPU bench."""
+    import json
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import bench
+    wl, S, steps, batch = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    print(json.dumps(time_cogact_sample(bench.WORKLOADS[wl], S, steps=steps, batch=batch)), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -233,6 +233,45 @@ def test_rmsnorm(dtype, unit_offset):
     _check(dw, wr.grad, M, dtype, "rmsnorm dw")
 
 
+@pytest.mark.parametrize("D", [256, 1024, 2048, 3584])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_rmsnorm_staged_ring_matches_register_kernels(D, accumulate):
+    """The norm kernels that stage rows in shared memory through the bulk-copy engine (default) against the
+    register-prefetch kernels and fp32 torch, on enough rows that every block walks its mbarrier ring several times
+    (both parities of every stage), with and without the accumulate-into-dx variant."""
+    o = ops()
+    from dexbotic_b200 import _lib
+    lib = _lib.load()
+    M = 6007
+    dtype = torch.bfloat16
+    x, w = _rand((M, D), dtype, 40), _rand((D,), dtype, 41, 0.3)
+    dy = _rand((M, D), dtype, 42)
+    dx0 = _rand((M, D), dtype, 43)
+    res = {}
+    try:
+        for staged in (1, 0):
+            lib.b200_set_norm_staged(staged)
+            y, rstd = o.rmsnorm_fwd(x, w, 1e-6)
+            dw = torch.zeros(D, device=DEV, dtype=torch.float32)
+            dx = dx0.clone() if accumulate else torch.empty_like(x)
+            o.rmsnorm_bwd(dy, x, w, rstd, dx=dx, dw=dw, accumulate_dx=accumulate)
+            torch.cuda.synchronize()
+            res[staged] = (y, rstd, dx, dw)
+    finally:
+        lib.b200_set_norm_staged(1)
+    for a, b, name in zip(res[1][:3], res[0][:3], ("y", "rstd", "dx")):
+        assert torch.equal(a, b), f"staged vs register kernel: {name} differs"      # same per-thread arithmetic
+    torch.testing.assert_close(res[1][3], res[0][3], rtol=2e-4, atol=2e-3)         # dw: different partial grouping
+    xr = x.float().requires_grad_(True)
+    wr = w.float().requires_grad_(True)
+    ref = wr * (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6))
+    _check(res[1][0], ref, 1, dtype, "staged rmsnorm fwd")
+    ref.backward(dy.float())
+    want_dx = xr.grad + (dx0.float() if accumulate else 0)
+    _check(res[1][2], want_dx, 4, dtype, "staged rmsnorm dx")
+    _check(res[1][3], wr.grad, M, dtype, "staged rmsnorm dw")
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("affine", [False, True])
 def test_layernorm(dtype, affine):

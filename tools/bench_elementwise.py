@@ -31,11 +31,17 @@ def main():
     dy = torch.randn(M, d, device=dev, dtype=bf)
     w = torch.randn(d, device=dev, dtype=bf)
     y, rstd = ops.rmsnorm_fwd(x, w, 1e-6)
-    report("rmsnorm_fwd", 2 * M * d * 2, lambda: ops.rmsnorm_fwd(x, w, 1e-6, out=y))
     dx = torch.empty_like(x)
     dw = torch.zeros(d, device=dev)
-    report("rmsnorm_bwd", 3 * M * d * 2, lambda: ops.rmsnorm_bwd(dy, x, w, rstd, dx=dx, dw=dw))
-    report("rmsnorm_bwd(accum)", 4 * M * d * 2, lambda: ops.rmsnorm_bwd(dy, x, w, rstd, dx=dx, dw=dw, accumulate_dx=True))
+    from dexbotic_b200 import _lib
+    for staged in (1, 0):          # 1 = rows staged in smem by the bulk-copy engine (default), 0 = register prefetch
+        _lib.load().b200_set_norm_staged(staged)
+        tag = "" if staged else " [register-prefetch kernel]"
+        report("rmsnorm_fwd" + tag, 2 * M * d * 2, lambda: ops.rmsnorm_fwd(x, w, 1e-6, out=y))
+        report("rmsnorm_bwd" + tag, 3 * M * d * 2, lambda: ops.rmsnorm_bwd(dy, x, w, rstd, dx=dx, dw=dw))
+        report("rmsnorm_bwd(accum)" + tag, 4 * M * d * 2,
+               lambda: ops.rmsnorm_bwd(dy, x, w, rstd, dx=dx, dw=dw, accumulate_dx=True))
+    _lib.load().b200_set_norm_staged(1)
     g = torch.randn(M, I, device=dev, dtype=bf)
     u = torch.randn(M, I, device=dev, dtype=bf)
     h = torch.empty_like(g)
