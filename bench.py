@@ -501,7 +501,7 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
 
 
 def cpu_baseline(w: dict, S: int, seconds_budget: float = 20.0, steps: int = 1, workload: str = "cogact_7b",
-                 limit_s: float = 150.0) -> dict:
+                 limit_s: float = 120.0) -> dict:
     """The oracle port (oracle/cpu_baseline.py) timed on this box's host cores on a bounded sample.  It runs in a child
     process under a wall-clock limit: batch 4 first; if the host cannot finish that in `limit_s`, batch 1; if not even
     that, the line says so instead of stalling the bench."""

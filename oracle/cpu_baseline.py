@@ -5,8 +5,8 @@ Bounded sample (a full 7B fp32 step is ~38 TFLOP per sample and > 120 GB of host
 Adam moments): batch 4 (so that the weight matrices are reused across rows as in the GPU arm's batch, instead of the
 weight-streaming-bound batch 1), full-size ViT-L/14 + projector + DiT, and the decoder timed at 1 and 2 full-size layers;
 the 28-layer time is the linear extrapolation T(1) + (L-1) * (T(2) - T(1)) — decoder layers are identical, so the cost is
-linear in L.  The JSON says `extrapolated: true`.  All host cores are used whatever OMP_NUM_THREADS the launcher left
-(torchrun sets it to 1).
+linear in L.  The JSON says `extrapolated: true`.  bench.py runs this module in a child process without torchrun's OMP_NUM_THREADS=1, under a
+wall-clock limit, so the thread count is torch's default (physical cores) at every N.
 """
 from __future__ import annotations
 
@@ -107,22 +107,12 @@ def _time_with_layers(w: dict, n_dec: int, steps: int, B: int = 4) -> float:
     return ts[len(ts) // 2]
 
 
-def _host_threads() -> int:
-    """Physical cores this process may run on.  torch's own default is that number; torchrun overrides it with
-    OMP_NUM_THREADS=1, and one thread per LOGICAL core (hyper-threads) makes the many small ops of the port slower, not
-    faster, on a 2-socket host."""
-    n_aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    try:
-        import psutil
-        phys = psutil.cpu_count(logical=False) or n_aff
-    except Exception:
-        phys = max(1, (os.cpu_count() or 2) // 2)
-    return max(1, min(n_aff, phys))
-
-
 def time_cogact_sample(w: dict, S: int, seconds_budget: float = 20.0, steps: int = 1, batch: int = 4) -> dict:
-    cores = _host_threads()
-    torch.set_num_threads(cores)          # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every physical core
+    # Threads: torch's own default (one per physical core).  bench.py starts this in a child process WITHOUT the
+    # OMP_NUM_THREADS=1 that torchrun exports, so the same count applies at every N; forcing one thread per LOGICAL core
+    # was measured to make the port several times slower on the GPU boxes' 2-socket hosts.
+    if os.environ.get("B200_CPU_THREADS"):
+        torch.set_num_threads(int(os.environ["B200_CPU_THREADS"]))
     B = batch
     t1 = _time_with_layers(w, 1, steps, B)
     t2 = _time_with_layers(w, 2, steps, B)
