@@ -1056,7 +1056,10 @@ static int resident_grid(K kernel, int nt, int64_t rows) {
 }
 
 // SM-resident grid of the staged rmsnorm backward (3 blocks of <= 72 KB of stage ring per SM)
-static int g_norm_staged = 1;          // b200_set_norm_staged(0): the register-prefetch kernels (A/B measurements)
+// bit 0: rmsnorm backward staged (default: 54 / 63 us against 65 / 87 us for the register-prefetch kernel at [9888, 3584],
+// plain / accumulate); bit 1: rmsnorm forward staged (measured SLOWER, 35.8 vs 30.7 us — a 7 KB row per block and one
+// barrier round trip per row leave the ring's depth unused — so it is off by default and kept for the A/B test)
+static int g_norm_staged = 1;
 
 template <typename T>
 static int launch_rmsnorm_bwd_staged(const T* dy, const T* x, const T* w, const float* rstd, T* dx, float* dw, float* ws,
@@ -1083,7 +1086,7 @@ int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t
   int grid;
   const int64_t row_bytes = D * (dtype == B200_BF16 ? 2 : 4);
   const bool aligned16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && row_bytes % 16 == 0;
-  if (g_norm_staged && D <= (int64_t)16 * nt && aligned16 && 4 * row_bytes <= 48 * 1024) {
+  if ((g_norm_staged & 2) && D <= (int64_t)16 * nt && aligned16 && 4 * row_bytes <= 48 * 1024) {
     const size_t smem = (size_t)(4 * row_bytes);           // 4-deep ring of x rows per block
     DISPATCH_T(dtype, {
       int per_sm = 0;
@@ -1108,7 +1111,7 @@ int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t
 }
 
 int b200_set_norm_staged(int on) {
-  g_norm_staged = on != 0;
+  g_norm_staged = on;
   return 0;
 }
 
@@ -1131,7 +1134,7 @@ int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* 
   const int64_t stage_smem = 3 * (accumulate_dx ? 3 : 2) * row_bytes;
   const bool aligned16 = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) |
                            reinterpret_cast<uintptr_t>(dx)) & 15) == 0 && row_bytes % 16 == 0;
-  if (g_norm_staged && D <= (int64_t)16 * nt && aligned16 && stage_smem <= 72 * 1024) {
+  if ((g_norm_staged & 1) && D <= (int64_t)16 * nt && aligned16 && stage_smem <= 72 * 1024) {
     int rc;
     DISPATCH_T(dtype, rc = launch_rmsnorm_bwd_staged<T>((const T*)dy, (const T*)x, (const T*)w, rstd, (T*)dx, dw, ws, M, D,
                                                         unit_offset, accumulate_dx, nt, (size_t)stage_smem, &grid,
@@ -1316,8 +1319,9 @@ int b200_colsum(const void* x, float* out, int64_t M, int64_t N, int dtype, void
   // enough row blocks to fill the SMs a few times over, as few as possible beyond that (atomics per column)
   const int64_t col_blocks = ceil_div(N / 8, 64);
   int rows_per_block = 256;
-  // (351 blocks of 256 rows on [9888, 4608] kept 39 KB per SM in flight: 0.49 of the copy peak)
-  while (rows_per_block > 64 && col_blocks * ceil_div(M, rows_per_block) < 4 * num_sms()) rows_per_block >>= 1;
+  // (128-row blocks on [9888, 4608] — 702 blocks instead of 351 — measured the same 28.7 us and double the atomics whose
+  // order is the step's only non-determinism: not adopted)
+  while (rows_per_block > 64 && col_blocks * ceil_div(M, rows_per_block) < 2 * num_sms()) rows_per_block >>= 1;
   dim3 grid((unsigned)col_blocks, (unsigned)ceil_div(M, rows_per_block));
   DISPATCH_T(dtype, (colsum_kernel<T><<<grid, 256, 0, STREAM>>>((const T*)x, out, (int)M, (int)N, rows_per_block)));
   B200_LAUNCH_OK();

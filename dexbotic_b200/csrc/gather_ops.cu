@@ -122,11 +122,18 @@ __global__ void splice_gather_kernel(const int32_t* __restrict__ src, const T* _
 }
 
 // Image rows: plain copy.  Token rows: one block per row; the FIRST occurrence of a token id sums the
-// gradient rows of all its occurrences in fp32 and adds the result to d_table once (deterministic).
+// gradient rows of all its occurrences in fp32 (ascending row order) and adds the result to d_table once
+// (deterministic).  The later occurrences are found by the whole block in one strided pass over `src` and sorted in
+// shared memory; the first version let every thread walk all `rows` entries per 8-column chunk: 130 us per token row
+// that is a first occurrence, 2.2 ms per CogACT-7B step for a 71 MB scatter.
+constexpr int kMaxDupRows = 1024;
 template <typename T>
 __global__ void __launch_bounds__(256) splice_scatter_kernel(const int32_t* __restrict__ src,
                                                              const T* __restrict__ dout, T* __restrict__ d_table,
                                                              T* __restrict__ d_feats, int rows, int D) {
+  __shared__ int found[kMaxDupRows];
+  __shared__ int sorted[kMaxDupRows];
+  __shared__ int n_found;
   const int r = blockIdx.x;
   const int s = src[r];
   if (s == kPadSrc) return;
@@ -144,16 +151,44 @@ __global__ void __launch_bounds__(256) splice_scatter_kernel(const int32_t* __re
   if (d_table == nullptr) return;
   int dup = 0;
   for (int i = threadIdx.x; i < r; i += blockDim.x) dup |= (src[i] == s);
+  if (threadIdx.x == 0) n_found = 0;
   if (__syncthreads_or(dup)) return;
+  for (int i = r + 1 + threadIdx.x; i < rows; i += blockDim.x) {
+    if (src[i] == s) {
+      const int k = atomicAdd(&n_found, 1);
+      if (k < kMaxDupRows) found[k] = i;
+    }
+  }
+  __syncthreads();
+  const int n = n_found;
+  if (n <= kMaxDupRows) {
+    // rank sort (row indices are distinct): ascending order = the summation order of the serial walk
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+      const int v = found[t];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) rank += found[j] < v;
+      sorted[rank] = v;
+    }
+    __syncthreads();
+  }
   for (int c = threadIdx.x * 8; c < D; c += blockDim.x * 8) {
     float acc[8];
     Pack8<T>::load(drow + c, acc);
-    for (int i = r + 1; i < rows; ++i) {
-      if (src[i] == s) {
+    if (n <= kMaxDupRows) {
+      for (int k = 0; k < n; ++k) {
         float v[8];
-        Pack8<T>::load(dout + (size_t)i * D + c, v);
+        Pack8<T>::load(dout + (size_t)sorted[k] * D + c, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+    } else {          // more repeats of one token than the list holds: serial walk
+      for (int i = r + 1; i < rows; ++i) {
+        if (src[i] == s) {
+          float v[8];
+          Pack8<T>::load(dout + (size_t)i * D + c, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += v[j];
+        }
       }
     }
     T* o = d_table + (size_t)s * D + c;

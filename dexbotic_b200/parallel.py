@@ -231,6 +231,11 @@ class ShardedDataParallel:
             self._peer_grad = [self._h_grad.get_buffer((self.rank + k) % self.world, (store.grad_a.numel(),),
                                                        torch.bfloat16, 0) for k in range(1, self.world)]
             self._rs_ctas = int(os.environ.get("B200_RS_CTAS", "16"))
+            # after backward (finish()) nothing else runs: the leftover chunks (embedding table, towers, projector, heads)
+            # are exposed time, so their kernels take the whole GPU — NVLink loads are latency-bound, bandwidth scales
+            # with the bytes in flight (770 GB/s x ~3 us = 2.3 MB = 16 B x 145 k threads at N = 2)
+            self._rs_ctas_idle = int(os.environ.get("B200_RS_CTAS_IDLE", "592"))
+            self._in_finish = False
         if self.enabled:
             store.sharder = self
             store.grad_ready_hook = self.on_ready
@@ -265,7 +270,7 @@ class ShardedDataParallel:
             self._h_grad.barrier(channel=0)
             if pb > pa:
                 self._ops.reduce_scatter_p2p_(st.grad_a[pa:pb], [t[pa:pb] for t in self._peer_grad], 1.0 / self.world,
-                                        ctas=self._rs_ctas)
+                                              ctas=self._rs_ctas_idle if self._in_finish else self._rs_ctas)
             self._h_grad.barrier(channel=0)            # every peer has taken its piece of this rank's chunk
         self.reduced.add(ci)
 
@@ -310,9 +315,13 @@ class ShardedDataParallel:
         """After backward: the chunks no hook reported (embeddings, towers, projector, heads) and the fp32 region."""
         if not (self.enabled and self.sync):
             return
-        for ci in range(len(self.chunks)):
-            if ci not in self.reduced:
-                self._reduce_scatter(ci)
+        self._in_finish = True
+        try:
+            for ci in range(len(self.chunks)):
+                if ci not in self.reduced:
+                    self._reduce_scatter(ci)
+        finally:
+            self._in_finish = False
         st = self.store
         if st.n_b:
             if self.nccl:

@@ -27,9 +27,10 @@ int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t
  * b200_norm_bwd_workspace_rows(M, D) x D floats (x 2D for layernorm) for contention-free partial sums; NULL falls
  * back to fp32 atomics. */
 int64_t b200_norm_bwd_workspace_rows(int64_t M, int64_t D);
-/* 1 (default): the norm backward kernels stage their rows in shared memory through the bulk-copy engine (cp.async.bulk +
- * mbarrier ring); 0: the register-prefetch kernels.  Same arithmetic; for A/B measurements. */
-int b200_set_norm_staged(int on);
+/* Bit mask of the RMSNorm kernels that stage their rows in shared memory through the bulk-copy engine (cp.async.bulk +
+ * mbarrier ring) instead of register prefetch: bit 0 = backward (default on), bit 1 = forward (default off: measured
+ * slower).  Same arithmetic either way; for A/B measurements and tests. */
+int b200_set_norm_staged(int mask);
 int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw,
                      float* workspace, int64_t M, int64_t D, int unit_offset, int accumulate_dx, int dtype,
                      void* stream);

@@ -323,7 +323,10 @@ def test_overlapped_optimizer_equals_synchronous():
     # run-to-run noise of the synchronous path (a few reductions use fp32 atomics; Adam turns a sign flip of a
     # near-zero gradient into a full lr-sized step) is the yardstick for the overlapped path
     noise, got = dist(finals[0], finals[1]), dist(finals[0], finals[2])
-    bad = {k: (got[k], noise[k]) for k in got if got[k] > 3 * noise[k] + 2e-3}
+    # k_proj.bias has an exactly-zero true gradient (softmax is invariant to a per-query shift of the scores): what AdamW
+    # normalises there is pure rounding noise of the fp32-atomic bias reductions, not comparable between two runs
+    # (tests/test_gpu_dp.py skips it for the same reason)
+    bad = {k: (got[k], noise[k]) for k in got if got[k] > 3 * noise[k] + 2e-3 and not k.endswith("k_proj.bias")}
     assert not bad, bad
 
 

@@ -34,9 +34,9 @@ def main():
     dx = torch.empty_like(x)
     dw = torch.zeros(d, device=dev)
     from dexbotic_b200 import _lib
-    for staged in (1, 0):          # 1 = rows staged in smem by the bulk-copy engine (default), 0 = register prefetch
+    for staged in (3, 0):          # 3 = rows staged in smem by the bulk-copy engine (fwd + bwd), 0 = register prefetch
         _lib.load().b200_set_norm_staged(staged)
-        tag = "" if staged else " [register-prefetch kernel]"
+        tag = " [staged]" if staged else " [register-prefetch kernel]"
         report("rmsnorm_fwd" + tag, 2 * M * d * 2, lambda: ops.rmsnorm_fwd(x, w, 1e-6, out=y))
         report("rmsnorm_bwd" + tag, 3 * M * d * 2, lambda: ops.rmsnorm_bwd(dy, x, w, rstd, dx=dx, dw=dw))
         report("rmsnorm_bwd(accum)" + tag, 4 * M * d * 2,
