@@ -501,39 +501,45 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
 
 
 def cpu_baseline(w: dict, S: int, seconds_budget: float = 20.0, steps: int = 1, workload: str = "cogact_7b",
-                 limit_s: float = 120.0) -> dict:
-    """The oracle port (oracle/cpu_baseline.py) timed on this box's host cores on a bounded sample.  It runs in a child
-    process under a wall-clock limit: batch 4 first; if the host cannot finish that in `limit_s`, batch 1; if not even
-    that, the line says so instead of stalling the bench."""
+                 limit_s: float = 120.0, prefer_reference: bool = False) -> dict:
+    """The reference's CPU implementation of the step, timed on this box's host cores on a bounded sample, in a child
+    process under a wall-clock limit (a slow host can never stall the bench).  `prefer_reference`: first the UNMODIFIED
+    reference classes from the vendored baseline/_ref (`kind: "reference"`, oracle/cpu_baseline.py:time_reference_sample);
+    else / on failure the oracle port (`kind: "port"`) at batch 4, then batch 1; if nothing finishes the line says so."""
     last = "not run"
-    for batch, lim in ((4, limit_s), (1, limit_s / 2)):
+    plan = ([("reference", 4, 2.25 * limit_s)] if prefer_reference else []) + [("port", 4, limit_s), ("port", 1, limit_s / 2)]
+    if prefer_reference:
+        plan = plan[:2]
+    for kind, batch, lim in plan:
         try:
             env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}
             env["CUDA_VISIBLE_DEVICES"] = ""
-            r = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", workload, str(S), str(steps), str(batch)],
+            r = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", workload, str(S),
+                                str(1 if kind == "reference" else steps), str(batch), kind],
                                cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=lim)
             lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
             if r.returncode == 0 and lines:
                 return json.loads(lines[-1])
-            last = f"exit {r.returncode}: {r.stderr.strip()[-200:]}"
+            last = f"{kind} batch {batch}: exit {r.returncode}: {r.stderr.strip()[-200:]}"
         except subprocess.TimeoutExpired:
-            last = f"batch {batch} did not finish in {lim:.0f} s"
+            last = f"{kind} batch {batch} did not finish in {lim:.0f} s"
     return {"value": None, "unit": "samples/s", "cores": None, "kind": "port", "sample": f"unavailable ({last})"}
 
 
 def run_reference(args) -> dict:
-    """--impl reference: the reference's own CPU implementation of the path (oracle port; the Python reference
-    itself cannot travel to the GPU box), all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, bounded sample per step:
+    the UNMODIFIED reference classes from the vendored baseline/_ref when they load (270 s limit), else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return {}
     w = WORKLOADS[args.workload]
     S = 2 + w["instr_tokens"] + w["template_tokens"] - 1 + (w["vision"]["image_size"] // w["vision"]["patch_size"]) ** 2
-    cb = cpu_baseline(w, S, seconds_budget=30.0, steps=max(1, min(args.steps, 3)), workload=args.workload, limit_s=240.0)
+    cb = cpu_baseline(w, S, seconds_budget=30.0, steps=max(1, min(args.steps, 2)), workload=args.workload, limit_s=120.0,
+                      prefer_reference=True)
     return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / cb["value"], 1) if cb["value"] else None,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload} (CPU oracle port, bounded sample: {cb['sample']})"},
+            "config": {"workload": f"{args.workload} (reference CPU arm, kind={cb.get('kind')}, bounded sample: {cb['sample']})"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 

@@ -16,33 +16,47 @@ struct PeerPtrs {
   const bf16* p[kMaxPeers];
 };
 
-// The loads cross NVLink (~2-3 us latency): every thread keeps all peers' packs of an iteration in flight before it
-// adds.  The grid is deliberately small (the persistent GEMM owns the SMs; a few CTAs move > 100 GB/s, a gradient chunk
-// needs < 50 GB/s to finish under the next block's backward).
+// The loads cross NVLink (~2-3 us latency): every thread keeps kUnroll packs x all peers in flight before it adds.  The
+// grid is deliberately small (the persistent GEMM owns the SMs), so the bytes in flight per thread set the bandwidth:
+// with one pack per peer a 16-CTA grid moved ~30 GB/s at N = 2 (one 16-byte load in flight per thread) — a 233 MB piece
+// took as long as the decoder block's backward it hides under, i.e. the kernel was resident all the time.  kUnroll = 4
+// (N = 2), 2 (N <= 4), 1 (N = 8: seven loads per pack already) keeps ~4-8 loads in flight per thread; the register array
+// is sized per instance (16 / 24 / 28 registers) so that a block still fits next to the GEMM's CTA on an SM.
+template <int kUnroll, int kPeers>      // kPeers: capacity of the in-flight register array (n_peers <= kPeers)
 __global__ void __launch_bounds__(256) reduce_scatter_p2p_kernel(bf16* __restrict__ own, PeerPtrs peers, int n_peers,
                                                                  int64_t n8, float scale) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
-    uint4 raw[kMaxPeers];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n8; i0 += stride * kUnroll) {
+    uint4 raw[kUnroll][kPeers];
 #pragma unroll
-    for (int r = 0; r < kMaxPeers; ++r)
-      if (r < n_peers) raw[r] = __ldcv(reinterpret_cast<const uint4*>(peers.p[r]) + i);   // peer data: never cached stale
-    float acc[8];
-    Pack8<bf16>::load(own + i * 8, acc);
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t i = i0 + u * stride;
 #pragma unroll
-    for (int r = 0; r < kMaxPeers; ++r) {
-      if (r < n_peers) {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[r]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(h[e]);
-          acc[2 * e] += f.x;
-          acc[2 * e + 1] += f.y;
-        }
-      }
+      for (int r = 0; r < kPeers; ++r)
+        if (r < n_peers && i < n8) raw[u][r] = __ldcv(reinterpret_cast<const uint4*>(peers.p[r]) + i);   // never cached stale
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] *= scale;
-    Pack8<bf16>::store(own + i * 8, acc);
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= n8) break;
+      float acc[8];
+      Pack8<bf16>::load(own + i * 8, acc);
+#pragma unroll
+      for (int r = 0; r < kPeers; ++r) {
+        if (r < n_peers) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u][r]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h[e]);
+            acc[2 * e] += f.x;
+            acc[2 * e + 1] += f.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= scale;
+      Pack8<bf16>::store(own + i * 8, acc);
+    }
   }
 }
 
@@ -63,8 +77,13 @@ extern "C" int b200_reduce_scatter_p2p(void* own, const void* const* peer_ptrs, 
   if (ctas <= 0) ctas = 16;
   const int64_t want = ceil_div(n / 8, 256);
   const unsigned grid = (unsigned)(want < ctas ? want : ctas);
-  reduce_scatter_p2p_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<bf16*>(own), pp,
-                                                                                       n_peers, n / 8, scale);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (n_peers == 1)
+    reduce_scatter_p2p_kernel<4, 1><<<grid, 256, 0, st>>>(reinterpret_cast<bf16*>(own), pp, n_peers, n / 8, scale);
+  else if (n_peers <= 3)
+    reduce_scatter_p2p_kernel<2, 3><<<grid, 256, 0, st>>>(reinterpret_cast<bf16*>(own), pp, n_peers, n / 8, scale);
+  else
+    reduce_scatter_p2p_kernel<1, kMaxPeers><<<grid, 256, 0, st>>>(reinterpret_cast<bf16*>(own), pp, n_peers, n / 8, scale);
   B200_LAUNCH_OK();
   return 0;
 }

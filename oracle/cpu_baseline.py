@@ -127,16 +127,71 @@ def time_cogact_sample(w: dict, S: int, seconds_budget: float = 20.0, steps: int
             "seconds_per_sample": round(total / B, 3)}
 
 
+def _time_reference_with_layers(w: dict, n_dec: int, steps: int, B: int) -> float:
+    """One training step of the UNMODIFIED reference CogACTForCausalLM (vendored tree, oracle/ref_loader.py) on the host:
+    fp32 parameters, the reference's own forward (HF Qwen2 + CLIP + its DiT / diffusion loss), backward, clip 1.0
+    (trainer.py:122) and torch AdamW (trainer.py:25-36), `n_dec` full-size decoder layers."""
+    from transformers import CLIPVisionConfig, Qwen2Config
+
+    import bench
+    from . import ref_loader
+    llm = {k: v for k, v in w["llm"].items() if k != "model_type"}
+    llm["num_hidden_layers"] = n_dec
+    torch.manual_seed(1)
+    model = ref_loader.build_reference_cogact(Qwen2Config(max_position_embeddings=4096, **llm),
+                                              CLIPVisionConfig(**w["vision"]), w["action_model_type"],
+                                              action_dim=w["action_dim"], chunk_size=w["chunk_size"])
+    for p_ in model.model.parameters():          # base_exp.py:318-321: everything under model.model trains
+        p_.requires_grad = True
+    model.train()
+    params = [p_ for p_ in model.parameters() if p_.requires_grad]
+    opt = torch.optim.AdamW(params, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    batch = {k: v for k, v in bench.make_batch(dict(w, batch=B), 0, pinned=False).items() if hasattr(v, "to")}
+
+    def one_step() -> float:
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        out = model(**batch)
+        out.loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return time.perf_counter() - t0
+
+    one_step()                                   # warm-up (allocations, thread pool, Adam state)
+    ts = sorted(one_step() for _ in range(max(1, steps)))
+    return ts[len(ts) // 2]
+
+
+def time_reference_sample(w: dict, S: int, steps: int = 1, batch: int = 4) -> dict:
+    """`kind: "reference"`: the same bounded sample as time_cogact_sample, run through the reference's own classes."""
+    if os.environ.get("B200_CPU_THREADS"):
+        torch.set_num_threads(int(os.environ["B200_CPU_THREADS"]))
+    B = batch
+    t1 = _time_reference_with_layers(w, 1, steps, B)
+    t2 = _time_reference_with_layers(w, 2, steps, B)
+    n = w["llm"]["num_hidden_layers"]
+    total = t1 + (n - 1) * max(t2 - t1, 1e-9)
+    return {"value": round(B / total, 5), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "reference",
+            "extrapolated": True,
+            "sample": (f"batch={B} fp32, UNMODIFIED reference CogACTForCausalLM (baseline/_ref via the compat loader) + "
+                       f"clip + torch AdamW on the host cores; full-size ViT / projector / DiT / embedding table, decoder "
+                       f"timed at 1 and 2 full-size layers ({t1:.2f}s, {t2:.2f}s per step) and extrapolated linearly to "
+                       f"{n} layers -> {total:.1f} s/step of {B} samples"),
+            "seconds_per_sample": round(total / B, 3)}
+
+
 def main() -> None:
-    """`python -m oracle.cpu_baseline <workload> <S> <steps> <batch>`: one JSON line.  bench.py runs the CPU arm in this
-    child process under a wall-clock limit, so a slow host can never stall the GPU bench."""
+    """`python -m oracle.cpu_baseline <workload> <S> <steps> <batch> [port|reference]`: one JSON line.  bench.py runs the
+    CPU arm in this child process under a wall-clock limit, so a slow host can never stall the GPU bench."""
     import json
     import sys
     from pathlib import Path
     sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
     import bench
     wl, S, steps, batch = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
-    print(json.dumps(time_cogact_sample(bench.WORKLOADS[wl], S, steps=steps, batch=batch)), flush=True)
+    kind = sys.argv[5] if len(sys.argv) > 5 else "port"
+    fn = time_reference_sample if kind == "reference" else time_cogact_sample
+    print(json.dumps(fn(bench.WORKLOADS[wl], S, steps=steps, batch=batch)), flush=True)
 
 
 if __name__ == "__main__":
