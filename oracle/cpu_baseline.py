@@ -107,6 +107,16 @@ def _time_with_layers(w: dict, n_dec: int, steps: int, B: int = 4) -> float:
     return ts[len(ts) // 2]
 
 
+def _per_layer(t1: float, t2: float) -> tuple[float, str]:
+    """Seconds per decoder layer from the 1- and 2-layer step times.  A decoder layer is >= 30 % of the 2-layer step's
+    arithmetic (6 * tokens * 233 M parameters against ViT-L + embedding AdamW + 2 layers), so when host noise makes
+    t2 - t1 smaller than a quarter of t2 the difference is not a measurement: the floor is used and the JSON says so."""
+    d = t2 - t1
+    if d >= 0.25 * t2:
+        return d, ""
+    return 0.25 * t2, " [t2 - t1 below the arithmetic floor of one layer: 0.25 * t2 used per layer]"
+
+
 def time_cogact_sample(w: dict, S: int, seconds_budget: float = 20.0, steps: int = 1, batch: int = 4) -> dict:
     # Threads: torch's own default (one per physical core).  bench.py starts this in a child process WITHOUT the
     # OMP_NUM_THREADS=1 that torchrun exports, so the same count applies at every N; forcing one thread per LOGICAL core
@@ -117,7 +127,7 @@ def time_cogact_sample(w: dict, S: int, seconds_budget: float = 20.0, steps: int
     t1 = _time_with_layers(w, 1, steps, B)
     t2 = _time_with_layers(w, 2, steps, B)
     n = w["llm"]["num_hidden_layers"]
-    per_layer = max(t2 - t1, 1e-9)
+    per_layer, note = _per_layer(t1, t2)
     total = t1 + (n - 1) * per_layer
     return {"value": round(B / total, 5), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
             "extrapolated": True,
@@ -170,7 +180,8 @@ def time_reference_sample(w: dict, S: int, steps: int = 1, batch: int = 4) -> di
     t1 = _time_reference_with_layers(w, 1, steps, B)
     t2 = _time_reference_with_layers(w, 2, steps, B)
     n = w["llm"]["num_hidden_layers"]
-    total = t1 + (n - 1) * max(t2 - t1, 1e-9)
+    per_layer, note = _per_layer(t1, t2)
+    total = t1 + (n - 1) * per_layer
     return {"value": round(B / total, 5), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "reference",
             "extrapolated": True,
             "sample": (f"batch={B} fp32, UNMODIFIED reference CogACTForCausalLM (baseline/_ref via the compat loader) + "
