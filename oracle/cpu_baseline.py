@@ -133,7 +133,7 @@ def time_cogact_sample(w: dict, S: int, seconds_budget: float = 20.0, steps: int
             "extrapolated": True,
             "sample": (f"batch={B} fp32 oracle port, full-size ViT/projector/DiT + AdamW; decoder timed at 1 and 2 "
                        f"full-size layers ({t1:.2f}s, {t2:.2f}s per step) and extrapolated linearly to {n} layers "
-                       f"-> {total:.1f} s/step of {B} samples"),
+                       f"-> {total:.1f} s/step of {B} samples{note}"),
             "seconds_per_sample": round(total / B, 3)}
 
 
@@ -187,7 +187,7 @@ def time_reference_sample(w: dict, S: int, steps: int = 1, batch: int = 4) -> di
             "sample": (f"batch={B} fp32, UNMODIFIED reference CogACTForCausalLM (baseline/_ref via the compat loader) + "
                        f"clip + torch AdamW on the host cores; full-size ViT / projector / DiT / embedding table, decoder "
                        f"timed at 1 and 2 full-size layers ({t1:.2f}s, {t2:.2f}s per step) and extrapolated linearly to "
-                       f"{n} layers -> {total:.1f} s/step of {B} samples"),
+                       f"{n} layers -> {total:.1f} s/step of {B} samples{note}"),
             "seconds_per_sample": round(total / B, 3)}
 
 
