@@ -494,7 +494,8 @@ def _run_timed(args, w, model, host, B, rank, world, local, dev):
         "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        res["cpu_baseline"] = cpu_baseline(w, S, seconds_budget=20.0, workload=args.workload)
+        res["cpu_baseline"] = cpu_baseline(w, S, seconds_budget=20.0, workload=args.workload, limit_s=90.0,
+                                            prefer_reference=w.get("kind") is None)
     if world > 1:
         dist.destroy_process_group()
     return res if rank == 0 else {}
