@@ -511,6 +511,191 @@ __global__ void __launch_bounds__(256, kPacks <= 2 ? 2 : 1) layernorm_bwd_kernel
   }
 }
 
+// ---- LayerNorm, one WARP per row (D <= 1280: CLIP-L 1024, SigLIP 1152, DiT 384 / 768 / 1024) --------------------------
+// The block-per-row kernels above put 64 threads on a 2 KB row and 8 such blocks on an SM: 8 rows in flight, two block
+// barriers per row, 19 us forward / 34 us backward for [8224, 1024] = 0.26 of the copy peak.  Here a warp owns a row
+// (lane l holds packs l, l + 32, ...): shuffles only, 64 rows in flight per SM.  The backward is split: this kernel
+// writes dx; dw / db are a column reduction over rows (layernorm_dwdb_kernel) that re-reads x / dy out of L2.
+template <typename T, int kP>
+__global__ void __launch_bounds__(256, 3) layernorm_fwd_warp_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                                 const T* __restrict__ b, T* __restrict__ y,
+                                                                 float* __restrict__ mean, float* __restrict__ rstd,
+                                                                 int M, int D, float eps) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int n_pack = D >> 3;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+    const T* xr = x + (size_t)row * D;
+    T* yr = y + (size_t)row * D;
+    float v[kP][8];
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kP; ++k) {
+      const int pk = lane + 32 * k;
+      if (pk < n_pack) {
+        Pack8<T>::load(xr + pk * 8, v[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[k][j];
+      }
+    }
+    const float mu = warp_sum(s) / (float)D;
+    float ss = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kP; ++k) {
+      if (lane + 32 * k < n_pack) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += (v[k][j] - mu) * (v[k][j] - mu);
+      }
+    }
+    const float r = rsqrtf(warp_sum(ss) / (float)D + eps);
+    if (lane == 0) {
+      if (mean != nullptr) mean[row] = mu;
+      if (rstd != nullptr) rstd[row] = r;
+    }
+#pragma unroll
+    for (int k = 0; k < kP; ++k) {
+      const int pk = lane + 32 * k;
+      if (pk < n_pack) {
+        float wv[8], bv[8], o[8];
+        if (w != nullptr) Pack8<T>::load(w + pk * 8, wv);
+        if (b != nullptr) Pack8<T>::load(b + pk * 8, bv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = (v[k][j] - mu) * r;
+          if (w != nullptr) t *= wv[j];
+          if (b != nullptr) t += bv[j];
+          o[j] = t;
+        }
+        Pack8<T>::store(yr + pk * 8, o);
+      }
+    }
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w.  x / dy stay in registers as loaded (Raw8) between the
+// statistics pass and the output pass.
+template <typename T, int kP>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_dx_warp_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                    const T* __restrict__ w,
+                                                                    const float* __restrict__ mean,
+                                                                    const float* __restrict__ rstd, T* dx, int M, int D,
+                                                                    int accumulate_dx) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int n_pack = D >> 3;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+    const T* xr = x + (size_t)row * D;
+    const T* dyr = dy + (size_t)row * D;
+    T* dxr = dx + (size_t)row * D;
+    const float mu = mean[row], r = rstd[row];
+    Raw8<T> rx[kP], rg[kP];
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kP; ++k) {
+      const int pk = lane + 32 * k;
+      if (pk < n_pack) {
+        rx[k].load(xr + pk * 8);
+        rg[k].load(dyr + pk * 8);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kP; ++k) {
+      const int pk = lane + 32 * k;
+      if (pk < n_pack) {
+        float xv[8], gv[8], wv[8];
+        rx[k].unpack(xv);
+        rg[k].unpack(gv);
+        if (w != nullptr) Pack8<T>::load(w + pk * 8, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mu) * r;
+          const float g = w != nullptr ? gv[j] * wv[j] : gv[j];
+          s1 += g;
+          s2 += g * xh;
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int k = 0; k < kP; ++k) {
+      const int pk = lane + 32 * k;
+      if (pk < n_pack) {
+        float xv[8], gv[8], wv[8], o[8];
+        rx[k].unpack(xv);
+        rg[k].unpack(gv);
+        if (w != nullptr) Pack8<T>::load(w + pk * 8, wv);
+        if (accumulate_dx) Pack8<T>::load(dxr + pk * 8, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mu) * r;
+          const float g = w != nullptr ? gv[j] * wv[j] : gv[j];
+          const float t = r * (g - s1 - xh * s2);
+          o[j] = accumulate_dx ? o[j] + t : t;
+        }
+        Pack8<T>::store(dxr + pk * 8, o);
+      }
+    }
+  }
+}
+
+// dw[col] += sum_rows dy * xhat,  db[col] += sum_rows dy.  Block = 64 column-threads (8 columns each) x 4 row groups, two
+// rows of both operands in flight per thread; the row groups are combined in shared memory and one thread per column
+// group issues the block's atomics (the same fp32-atomic finish as colsum: its order is not fixed).
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_dwdb_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                             const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, float* __restrict__ dw,
+                                                             float* __restrict__ db, int M, int D, int rows_per_block) {
+  __shared__ float part[4][64][16];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int col8 = (blockIdx.x * 64 + tx) * 8;
+  const bool live = col8 < D;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float wacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, bacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (live) {
+    int r = r0 + ty;
+    for (; r + 4 < r1; r += 8) {
+      float x0[8], g0[8], x1[8], g1[8];
+      Pack8<T>::load(x + (size_t)r * D + col8, x0);
+      Pack8<T>::load(dy + (size_t)r * D + col8, g0);
+      Pack8<T>::load(x + (size_t)(r + 4) * D + col8, x1);
+      Pack8<T>::load(dy + (size_t)(r + 4) * D + col8, g1);
+      const float m0 = mean[r], s0 = rstd[r], m1 = mean[r + 4], s1 = rstd[r + 4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        wacc[j] += g0[j] * ((x0[j] - m0) * s0) + g1[j] * ((x1[j] - m1) * s1);
+        bacc[j] += g0[j] + g1[j];
+      }
+    }
+    for (; r < r1; r += 4) {
+      float x0[8], g0[8];
+      Pack8<T>::load(x + (size_t)r * D + col8, x0);
+      Pack8<T>::load(dy + (size_t)r * D + col8, g0);
+      const float m0 = mean[r], s0 = rstd[r];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        wacc[j] += g0[j] * ((x0[j] - m0) * s0);
+        bacc[j] += g0[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    part[ty][tx][j] = wacc[j];
+    part[ty][tx][8 + j] = bacc[j];
+  }
+  __syncthreads();
+  if (ty == 0 && live) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (dw != nullptr)
+        atomicAdd(dw + col8 + j, (part[0][tx][j] + part[1][tx][j]) + (part[2][tx][j] + part[3][tx][j]));
+      if (db != nullptr)
+        atomicAdd(db + col8 + j, (part[0][tx][8 + j] + part[1][tx][8 + j]) + (part[2][tx][8 + j] + part[3][tx][8 + j]));
+    }
+  }
+}
+
 // Rows wider than the register-cached kernel holds (D > 8*256*kMaxPacks; OFT's MLPResNet input LayerNorm has
 // D = action_dim * hidden = 25088, oft/action_model/model.py:108,146): one block per row, two streaming passes,
 // dw / db by fp32 atomics (such inputs have a few hundred rows).
@@ -1059,7 +1244,8 @@ static int resident_grid(K kernel, int nt, int64_t rows) {
 // bit 0: rmsnorm backward staged (default: 54 / 63 us against 65 / 87 us for the register-prefetch kernel at [9888, 3584],
 // plain / accumulate); bit 1: rmsnorm forward staged (measured SLOWER, 35.8 vs 30.7 us — a 7 KB row per block and one
 // barrier round trip per row leave the ring's depth unused — so it is off by default and kept for the A/B test)
-static int g_norm_staged = 1;
+// bit 2: LayerNorm forward / backward with one warp per row + a column kernel for dw / db (D <= 1280), default on
+static int g_norm_staged = 1 | 4;
 
 template <typename T>
 static int launch_rmsnorm_bwd_staged(const T* dy, const T* x, const T* w, const float* rstd, T* dx, float* dw, float* ws,
@@ -1073,6 +1259,14 @@ static int launch_rmsnorm_bwd_staged(const T* dy, const T* x, const T* w, const 
   kernel<<<grid, nt, smem, stream>>>(dy, x, w, rstd, dx, dw, ws, (int)M, (int)D, unit_offset, accumulate_dx);
   *grid_out = grid;
   return 0;
+}
+
+template <typename K>
+static int warp_row_grid(K kernel, int64_t M) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int64_t want = ceil_div(M, 8), cap = (int64_t)num_sms() * per_sm;
+  return (int)(want < cap ? want : cap);
 }
 
 extern "C" {
@@ -1164,6 +1358,17 @@ int b200_layernorm_fwd(const void* x, const void* w, const void* b, void* y, flo
                        int64_t D, float eps, int dtype, void* stream) {
   B200_CHECK(D % 8 == 0, "layernorm_fwd: D=%lld must be a multiple of 8", (long long)D);
   if (M == 0) return 0;
+  if ((g_norm_staged & 4) && D <= 1280) {          // one warp per row
+    const int kp = D <= 512 ? 2 : (D <= 1024 ? 4 : 5);
+#define B200_LN_FWD(KP)                                                                                          \
+  DISPATCH_T(dtype, (layernorm_fwd_warp_kernel<T, KP><<<warp_row_grid(layernorm_fwd_warp_kernel<T, KP>, M), 256, 0, \
+                                                        STREAM>>>((const T*)x, (const T*)w, (const T*)b, (T*)y, mean, \
+                                                                  rstd, (int)M, (int)D, eps)))
+    if (kp == 2) { B200_LN_FWD(2); } else if (kp == 4) { B200_LN_FWD(4); } else { B200_LN_FWD(5); }
+#undef B200_LN_FWD
+    B200_LAUNCH_OK();
+    return 0;
+  }
   const int nt = norm_threads(D);
   int grid;
   DISPATCH_T(dtype, grid = resident_grid(layernorm_fwd_kernel<T>, nt, M));
@@ -1183,6 +1388,24 @@ int b200_layernorm_bwd(const void* dy, const void* x, const void* w, const float
                           (const T*)dy, (const T*)x, (const T*)w, mean, rstd, (T*)dx, dw, db, (int)M, (int)D,
                           accumulate_dx)));
     B200_LAUNCH_OK();
+    return 0;
+  }
+  if ((g_norm_staged & 4) && D <= 1280) {          // one warp per row for dx, a column kernel for dw / db
+    const int kp = D <= 512 ? 2 : (D <= 1024 ? 4 : 5);
+#define B200_LN_BWD(KP)                                                                                              \
+  DISPATCH_T(dtype, (layernorm_bwd_dx_warp_kernel<T, KP><<<warp_row_grid(layernorm_bwd_dx_warp_kernel<T, KP>, M), 256, \
+                                                           0, STREAM>>>((const T*)dy, (const T*)x, (const T*)w, mean,   \
+                                                                        rstd, (T*)dx, (int)M, (int)D, accumulate_dx)))
+    if (kp == 2) { B200_LN_BWD(2); } else if (kp == 4) { B200_LN_BWD(4); } else { B200_LN_BWD(5); }
+#undef B200_LN_BWD
+    B200_LAUNCH_OK();
+    if (dw != nullptr || db != nullptr) {
+      const int rows_per_block = 64;
+      dim3 g((unsigned)ceil_div(D / 8, 64), (unsigned)ceil_div(M, rows_per_block));
+      DISPATCH_T(dtype, (layernorm_dwdb_kernel<T><<<g, 256, 0, STREAM>>>((const T*)dy, (const T*)x, mean, rstd, dw, db,
+                                                                         (int)M, (int)D, rows_per_block)));
+      B200_LAUNCH_OK();
+    }
     return 0;
   }
   const int nt = norm_threads(D);

@@ -298,6 +298,48 @@ def test_layernorm(dtype, affine):
         _check(db, br.grad, M, dtype, "layernorm db")
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("D", [384, 768, 1024, 1152, 1280, 1536])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_layernorm_warp_and_block_kernels(dtype, D, accumulate):
+    """LayerNorm with one warp per row + the dw / db column kernel (default for D <= 1280; 1536 takes the block-per-row
+    kernels either way) and the block-per-row kernels (`b200_set_norm_staged` bit 2 cleared), on more rows than warps
+    are resident so that every warp walks several rows: both against fp32 torch, and against each other."""
+    o = ops()
+    from dexbotic_b200 import _lib
+    lib = _lib.load()
+    M = 9001 if dtype == torch.bfloat16 else 2177
+    x = _rand((M, D), dtype, 50, 2.0) + 0.5
+    w, b = _rand((D,), dtype, 51, 0.3) + 1, _rand((D,), dtype, 52, 0.3)
+    dy = _rand((M, D), dtype, 53)
+    dx0 = _rand((M, D), dtype, 54)
+    res = {}
+    try:
+        for mode in (5, 1):
+            lib.b200_set_norm_staged(mode)
+            y, mean, rstd = o.layernorm_fwd(x, w, b, 1e-5)
+            dw, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+            dx = dx0.clone() if accumulate else None
+            dx = o.layernorm_bwd(dy, x, w, mean, rstd, dx=dx, dw=dw, db=db, accumulate_dx=accumulate)
+            torch.cuda.synchronize()
+            res[mode] = (y, mean, rstd, dx, dw, db)
+    finally:
+        lib.b200_set_norm_staged(5)
+    xr = x.float().requires_grad_(True)
+    wr, br = w.float().requires_grad_(True), b.float().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), wr, br, 1e-5)
+    ref.backward(dy.float())
+    want_dx = xr.grad + (dx0.float() if accumulate else 0)
+    for mode, (y, mean, rstd, dx, dw, db) in res.items():
+        _check(y, ref, 1, dtype, f"layernorm fwd mode {mode}")
+        torch.testing.assert_close(mean, x.float().mean(-1), rtol=1e-4, atol=1e-4)
+        _check(dx, want_dx, 8, dtype, f"layernorm dx mode {mode}")
+        _check(dw, wr.grad, M, dtype, f"layernorm dw mode {mode}")
+        _check(db, br.grad, M, dtype, f"layernorm db mode {mode}")
+    torch.testing.assert_close(res[5][2], res[1][2], rtol=1e-5, atol=1e-6)         # rstd: same statistics
+    torch.testing.assert_close(res[5][4], res[1][4], rtol=1e-3, atol=2e-2)         # dw: different summation grouping
+
+
 def _rope_tables(n_pos, hd, theta=1e6):
     inv = 1.0 / (theta ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))
     f = torch.arange(n_pos, dtype=torch.float32)[:, None] * inv[None, :]
