@@ -29,8 +29,8 @@ int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t
 int64_t b200_norm_bwd_workspace_rows(int64_t M, int64_t D);
 /* Bit mask of the RMSNorm kernels that stage their rows in shared memory through the bulk-copy engine (cp.async.bulk +
  * mbarrier ring) instead of register prefetch: bit 0 = backward (default on), bit 1 = forward (default off: measured
- * slower).  Bit 2 (default on): LayerNorm forward / backward with one warp per row and a column kernel for dw / db
- * (D <= 1280) instead of one block per row.  For A/B measurements and tests. */
+ * slower).  Bit 2 (default off, opt-in): LayerNorm forward / backward with one warp per row and a column kernel for
+ * dw / db (D <= 1280) instead of one block per row.  For A/B measurements and tests. */
 int b200_set_norm_staged(int mask);
 int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw,
                      float* workspace, int64_t M, int64_t D, int unit_offset, int accumulate_dx, int dtype,

@@ -302,9 +302,9 @@ def test_layernorm(dtype, affine):
 @pytest.mark.parametrize("D", [384, 768, 1024, 1152, 1280, 1536])
 @pytest.mark.parametrize("accumulate", [False, True])
 def test_layernorm_warp_and_block_kernels(dtype, D, accumulate):
-    """LayerNorm with one warp per row + the dw / db column kernel (default for D <= 1280; 1536 takes the block-per-row
-    kernels either way) and the block-per-row kernels (`b200_set_norm_staged` bit 2 cleared), on more rows than warps
-    are resident so that every warp walks several rows: both against fp32 torch, and against each other."""
+    """LayerNorm with one warp per row + the dw / db column kernel (`b200_set_norm_staged` bit 2, opt-in; D <= 1280 — 1536
+    takes the block-per-row kernels either way) and the default block-per-row kernels, on more rows than warps are
+    resident so that every warp walks several rows: both against fp32 torch, and against each other."""
     o = ops()
     from dexbotic_b200 import _lib
     lib = _lib.load()
@@ -324,7 +324,7 @@ def test_layernorm_warp_and_block_kernels(dtype, D, accumulate):
             torch.cuda.synchronize()
             res[mode] = (y, mean, rstd, dx, dw, db)
     finally:
-        lib.b200_set_norm_staged(5)
+        lib.b200_set_norm_staged(1)          # the library default (staged rmsnorm backward only)
     xr = x.float().requires_grad_(True)
     wr, br = w.float().requires_grad_(True), b.float().requires_grad_(True)
     ref = torch.nn.functional.layer_norm(xr, (D,), wr, br, 1e-5)

@@ -72,10 +72,15 @@ def main():
     xv = torch.randn(8224, 1024, device=dev, dtype=bf)
     wv, bv = torch.randn(1024, device=dev, dtype=bf), torch.randn(1024, device=dev, dtype=bf)
     yv, mean, rs = ops.layernorm_fwd(xv, wv, bv, 1e-5)
-    report("layernorm_fwd [8224,1024]", 2 * xv.numel() * 2, lambda: ops.layernorm_fwd(xv, wv, bv, 1e-5, out=yv))
     dxv = torch.empty_like(xv)
     dwv, dbv = torch.zeros(1024, device=dev), torch.zeros(1024, device=dev)
-    report("layernorm_bwd [8224,1024]", 3 * xv.numel() * 2, lambda: ops.layernorm_bwd(xv, xv, wv, mean, rs, dx=dxv, dw=dwv, db=dbv))
+    for mode in (1, 5):            # 1 = default (block per row), 5 = + one warp per row and a dw / db column kernel (opt-in)
+        _lib.load().b200_set_norm_staged(mode)
+        tag = " [warp per row]" if mode & 4 else ""
+        report("layernorm_fwd [8224,1024]" + tag, 2 * xv.numel() * 2, lambda: ops.layernorm_fwd(xv, wv, bv, 1e-5, out=yv))
+        report("layernorm_bwd [8224,1024]" + tag, 3 * xv.numel() * 2,
+               lambda: ops.layernorm_bwd(xv, xv, wv, mean, rs, dx=dxv, dw=dwv, db=dbv))
+    _lib.load().b200_set_norm_staged(1)
     n = 1 << 28
     p32, m32, v32 = (torch.zeros(n, device=dev) for _ in range(3))
     g16 = torch.zeros(n, device=dev, dtype=bf)
