@@ -17,12 +17,15 @@ Transports of the sharded mode:
   "nccl"  reduce_scatter_tensor / all_gather_into_tensor in place on the flat buffers.  NCCL's kernels are resident on
           SMs while the persistent tcgen05 GEMM owns all 148 of them: both slow down (the 5-8 % weak-scaling loss
           measured at N = 2..8).
-  "ce"    the same exchange on the COPY ENGINES over NVLink / NVSwitch peer memory, no SM-resident collective at all:
-          the gradient and weight buffers are symmetric memory (ParamStore.SYMMETRIC), every rank PULLS its piece of a
-          finished chunk out of its peers' gradient buffers (cudaMemcpy peer-to-peer on a side stream, bracketed by
-          stream-ordered cross-rank barriers on the symmetric-memory signal pads), adds the N pieces in fp32, updates,
-          and PUSHES its piece of the new bf16 weights into the peers' weight buffers.  The only SM work left is the
-          1/N-sized sum and two one-CTA barrier kernels per chunk.
+  "ce"    the same exchange over NVLink / NVSwitch PEER MEMORY, no NCCL kernel on the data path: the gradient and weight
+          buffers are symmetric memory (ParamStore.SYMMETRIC).  Reduce-scatter = one small kernel per finished chunk and
+          rank (csrc/exchange.cu: reduce_scatter_p2p_kernel) that LOADS the rank's piece out of every peer's gradient
+          buffer (ld.global.cv on the peer-mapped addresses, several packs per peer in flight per thread), sums in fp32 in
+          a fixed rank order and writes the average back in place — one pass, bracketed by stream-ordered cross-rank
+          barriers on the symmetric-memory signal pads; 16 CTAs while backward runs (a block fits next to the GEMM's CTA
+          on an SM), the whole GPU for the chunks left after backward.  All-gather = every rank PUSHES its piece of the
+          new bf16 weights into the peers' weight buffers with peer copies on the COPY ENGINES.  Measured at N = 2 on one
+          box: 155.8 samples/s against 153.4 with the NCCL transport (profiles/r2_bench_lines.md).
 Gradients are produced by the tcgen05 wgrad GEMMs directly into the flat bf16 buffer the exchange reads — no packing,
 no copies.
 """
